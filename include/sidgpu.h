@@ -1,0 +1,206 @@
+/* sidgpu.h -- C ABI of the B200-native genotype-calling path (libsidgpu.so).
+ *
+ * The reference (EvolBioInf/sid) has no FFI layer: its boundary is a set of C++ free functions
+ * (call.hpp:12,40-43; pileup.hpp:20-44; lynch.hpp:44-46; stats.hpp:6-13).  Each entry point below
+ * names the reference interface it replaces.  Signatures use plain pointers and sizes only.
+ *
+ * Conventions
+ *   - every function returns an int status (SIDGPU_OK == 0); sidgpu_last_error() gives the text.
+ *   - one ctx per GPU; calls on one ctx are not thread safe; different ctxs are independent.
+ *   - "d_" pointers are device pointers on the ctx's device, "h_" pointers are host pointers.
+ *   - the caller owns every buffer it passes in; the ctx owns scratch, the profile table,
+ *     the site store and its stream.  Pointers handed OUT by the ctx (sidgpu_sites_view,
+ *     sidgpu_unique_view) stay valid until the next call that mutates the session.
+ *   - work is enqueued on the ctx's stream; functions that return host-visible numbers
+ *     synchronise that stream before returning.
+ *   - there is no CPU fallback: every entry point fails with SIDGPU_ECUDA when no sm_100 device
+ *     is usable.
+ */
+#ifndef SIDGPU_H
+#define SIDGPU_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum {
+    SIDGPU_OK = 0,
+    SIDGPU_EINVAL = 1,        /* bad argument */
+    SIDGPU_ECUDA = 2,         /* CUDA runtime / driver error, or no usable device */
+    SIDGPU_EMALFORMED = 3,    /* pileup.cpp:9   "Malformed pileup line" */
+    SIDGPU_EMISSING_MAPQ = 4, /* pileup.cpp:10  "Malformed pileup line or missing mapping qualities" */
+    SIDGPU_EQUAL_SHORT = 5,   /* fewer quality characters than counted bases (call.cpp:330-331 reads
+                                 past the vectors there: undefined behaviour in the reference) */
+    SIDGPU_ECAPACITY = 6,     /* an output buffer passed by the caller is too small */
+    SIDGPU_ENOMEM = 7,
+    SIDGPU_ESTATE = 8,        /* call sequence error (e.g. emit before finish) */
+    SIDGPU_EINTERNAL = 9
+};
+
+/* Calling methods: the `-m` strings of sid.cpp:92-100 and the functions of call.hpp:40-43. */
+enum {
+    SIDGPU_METHOD_LOCAL = 0,            /* callSiteMLError        call.cpp:213-289 */
+    SIDGPU_METHOD_BAYES = 1,            /* callBayes              call.cpp:145-211 */
+    SIDGPU_METHOD_LIKELIHOOD_RATIO = 2, /* callLikelihoodRatio    call.cpp:62-143  */
+    SIDGPU_METHOD_QUALITY = 3           /* callQualityBasedSimple call.cpp:291-372 */
+};
+
+typedef struct sidgpu_ctx sidgpu_ctx;
+
+typedef struct {
+    int device;               /* CUDA device ordinal */
+    size_t max_chunk_bytes;   /* largest text chunk one feed/tokenize call may carry (0: 256 MiB) */
+    size_t max_sites;         /* site-store capacity for methods that keep all sites (0: grow on demand) */
+    int table_log2;           /* initial log2 capacity of the unique-profile table (0: 20); grows */
+    void* stream;             /* cudaStream_t to run on (NULL: the ctx creates its own) */
+} sidgpu_config;
+
+/* Parameters of one calling session: GlobalOptions of sid.cpp:11-17. */
+typedef struct {
+    int method;                 /* SIDGPU_METHOD_* */
+    int estimate_prior;         /* -R */
+    double prior;               /* -r   (<= 0: none) */
+    double error_threshold;     /* -E   default 0.1  */
+    double significance_level;  /* -p   default 0.05 */
+    /* Lynch fit override for tests and multi-GPU: when fit_given != 0 the session uses these
+     * (pi, eps, nucleotide distribution) instead of running the optimiser. */
+    int fit_given;
+    double fit_pi, fit_eps, fit_nd[4];
+} sidgpu_params;
+
+/* ------------------------------------------------------------------------------------------------
+ * Lifetime, memory, errors
+ * --------------------------------------------------------------------------------------------- */
+int sidgpu_create(const sidgpu_config* cfg, sidgpu_ctx** out);
+void sidgpu_destroy(sidgpu_ctx* ctx);
+const char* sidgpu_last_error(const sidgpu_ctx* ctx);   /* ctx may be NULL: error of a failed create */
+const char* sidgpu_version(void);
+int sidgpu_synchronize(sidgpu_ctx* ctx);
+/* Thin allocation/copy helpers so that hosts without a CUDA toolchain (cgo, ctypes, the C++ host)
+ * can stage buffers.  Pinned host memory for the streaming path. */
+int sidgpu_malloc(sidgpu_ctx* ctx, size_t bytes, void** d_ptr);
+int sidgpu_free(sidgpu_ctx* ctx, void* d_ptr);
+int sidgpu_malloc_host(sidgpu_ctx* ctx, size_t bytes, void** h_ptr);
+int sidgpu_free_host(sidgpu_ctx* ctx, void* h_ptr);
+int sidgpu_memcpy_h2d(sidgpu_ctx* ctx, void* d_dst, const void* h_src, size_t bytes);
+int sidgpu_memcpy_d2h(sidgpu_ctx* ctx, void* h_dst, const void* d_src, size_t bytes);
+
+/* ------------------------------------------------------------------------------------------------
+ * K1: tokenizer + profile builder
+ *   replaces readFile (call.cpp:11-20), parsePileupLine (pileup.cpp:13-68),
+ *   parseReadBases (pileup.cpp:70-153) and, with want_qual, parseQualities (pileup.cpp:155-167).
+ * Text layout: `d_text` is the base of a device buffer holding `text_len` valid bytes of mpileup
+ * text.  The call owns the lines whose FIRST byte lies in [range_begin, range_end): a byte p starts a
+ * line iff text[p] != '\n' and (p == 0 or text[p-1] == '\n') -- the sharding rule of SURVEY.md 8(e);
+ * a line that straddles range_end is read to its end (up to text_len).  Empty lines are skipped
+ * (call.cpp:14).  d_text must be 16-byte aligned.
+ * --------------------------------------------------------------------------------------------- */
+typedef struct {
+    uint64_t n_sites;          /* lines parsed by the call */
+    const uint64_t* d_profile; /* per site: A | C<<16 | G<<32 | T<<48, each count mod 65536 (pileup.hpp:7) */
+    const int32_t* d_pos;      /* per site: atoi(position column) */
+    const uint32_t* d_slot;    /* per site: slot of its profile in the unique-profile table */
+    const uint64_t* d_line_off;/* per site: byte offset of the line in d_text (only with want_qual) */
+    /* chromosome names are interned on the device: d_name_ref[i] is a byte offset into d_names,
+     * where a 2-byte little-endian length is followed by the name bytes */
+    const uint32_t* d_name_ref;
+    const char* d_names;
+    uint64_t names_bytes;
+} sidgpu_sites_view;
+
+int sidgpu_tokenize(sidgpu_ctx* ctx, const char* d_text, size_t text_len, size_t range_begin,
+                    size_t range_end, int want_qual, sidgpu_sites_view* out);
+
+/* ------------------------------------------------------------------------------------------------
+ * Calling sessions: the four functions of call.hpp:40-43, streamed.
+ *
+ *   sidgpu_begin(params)
+ *   sidgpu_feed(d_text, ...)      any number of chunks, in file order; chunks must end on a line end
+ *                                 (or be the last one).  For SIDGPU_METHOD_LOCAL without -R and for
+ *                                 SIDGPU_METHOD_QUALITY without -R every feed can be followed at
+ *                                 once by sidgpu_emit_csv for the sites of that chunk.
+ *   sidgpu_finish()               global step: Lynch fit (lynch.cpp:17-35) when the method needs it,
+ *                                 per-unique-profile classification (call.cpp:93-127,176-194,238-273),
+ *                                 Benjamini-Hochberg (stats.cpp:58-80).
+ *   sidgpu_emit_csv(...)          CSV rows (call.hpp:29-38), in site order, sites whose profile has
+ *                                 coverage < 4 dropped for bayes / likelihood_ratio (call.cpp:131-140).
+ * --------------------------------------------------------------------------------------------- */
+int sidgpu_begin(sidgpu_ctx* ctx, const sidgpu_params* params);
+/* Tokenizes one chunk and joins its sites against the unique-profile table (K1 + K3).
+ * n_sites_out (optional) receives the number of sites the chunk added. */
+int sidgpu_feed(sidgpu_ctx* ctx, const char* d_text, size_t text_len, size_t range_begin,
+                size_t range_end, uint64_t* n_sites_out);
+int sidgpu_finish(sidgpu_ctx* ctx);
+/* Formats sites [site_begin, site_begin + n_sites) of the session into d_out (K2 for profiles not yet
+ * classified + K6).  In streaming mode (local/quality without -R) only the sites of the most recent
+ * feed are addressable.  *bytes_out receives the CSV bytes written (no header line). */
+int sidgpu_emit_csv(sidgpu_ctx* ctx, uint64_t site_begin, uint64_t n_sites, char* d_out, size_t out_cap,
+                    uint64_t* bytes_out, uint64_t* rows_out);
+/* Per-site results as arrays instead of text (what OutputRecord carries, call.hpp:14-27):
+ * label 0 hom / 1 het / 255 dropped; gt two chars; confidences as doubles.  Any pointer may be NULL. */
+int sidgpu_emit_records(sidgpu_ctx* ctx, uint64_t site_begin, uint64_t n_sites, uint8_t* d_label,
+                        char* d_gt, double* d_hom_conf, double* d_het_conf);
+
+/* One-call host-buffer path (what the `sid` binary and the call.hpp wrappers use): chunked,
+ * double-buffered pinned H2D of `h_text`, the session above on the device, D2H of the CSV.
+ * h_csv receives the rows (no header); *csv_bytes the size.  Returns SIDGPU_ECAPACITY (with the
+ * needed size in *csv_bytes) when csv_cap is too small. */
+int sidgpu_call_host(sidgpu_ctx* ctx, const sidgpu_params* params, const char* h_text, size_t text_len,
+                     char* h_csv, size_t csv_cap, uint64_t* csv_bytes, uint64_t* n_sites, uint64_t* n_rows);
+
+/* ------------------------------------------------------------------------------------------------
+ * K3: unique-profile histogram   (countUniqueProfiles pileup.cpp:169-196,
+ *                                 computeNucleotideDistribution pileup.cpp:198-217)
+ * --------------------------------------------------------------------------------------------- */
+typedef struct {
+    uint64_t n_unique;          /* entries below */
+    const uint64_t* d_profile;  /* packed profile, lexicographic order of (A,C,G,T) like the reference */
+    const uint64_t* d_count;    /* sites with that profile (64-bit: the reference's uint32 would wrap) */
+    double nd[4];               /* nucleotide distribution over the entries */
+} sidgpu_unique_view;
+/* Compacts and sorts the session's table.  min_coverage = 4 gives the Lynch input (call.cpp:66-70). */
+int sidgpu_histogram(sidgpu_ctx* ctx, uint32_t min_coverage, sidgpu_unique_view* out);
+
+/* ------------------------------------------------------------------------------------------------
+ * K4: Lynch objective   (compoundLikelihood lynch.cpp:37-61 with lynch.hpp:57-74,82-90)
+ * Evaluates -sum_u count_u * log((1-pi) L_hom,u + pi L_het,u) over the last sidgpu_histogram().
+ * _partial leaves the (rank-local) sum in device memory at d_out so that a multi-GPU host can
+ * all-reduce it (NCCL) before reading; sidgpu_lynch_objective returns the local value to the host.
+ * Out-of-box arguments give DBL_MAX (lynch.cpp:41-43).
+ * --------------------------------------------------------------------------------------------- */
+int sidgpu_lynch_objective_partial(sidgpu_ctx* ctx, const double nd[4], double pi, double eps, double* d_out);
+int sidgpu_lynch_objective(sidgpu_ctx* ctx, const double nd[4], double pi, double eps, double* value);
+/* estimateProfileGenotypeLikelihoods (lynch.cpp:17-35) + FunctionMinimizer<2>::run
+ * (optimization.hpp:51-89): Nelder-Mead from (1e-3,1e-3), steps 1e-4, stop at size < 1e-5 or
+ * 1000 iterations; every objective evaluation runs on the device. */
+typedef struct {
+    double pi, eps, fval;
+    int iterations, evaluations, converged;
+} sidgpu_fit;
+int sidgpu_lynch_fit(sidgpu_ctx* ctx, const double nd[4], sidgpu_fit* out);
+/* The fit the session used (after sidgpu_finish). */
+int sidgpu_session_fit(sidgpu_ctx* ctx, sidgpu_fit* out, double nd[4], uint64_t* n_unique);
+
+/* ------------------------------------------------------------------------------------------------
+ * Device-side statistics kernels exposed for tests
+ *   likelihoodRatioTest stats.cpp:29-37, adjustBenjaminiHochberg stats.cpp:58-80,
+ *   `%g` formatting of operator<< call.hpp:29-38.
+ * --------------------------------------------------------------------------------------------- */
+int sidgpu_bh_adjust(sidgpu_ctx* ctx, const double* d_p, uint64_t n, double* d_adjusted);
+/* Formats n doubles like printf("%g"); out is n fixed 16-byte cells, NUL padded. */
+int sidgpu_format_g(sidgpu_ctx* ctx, const double* d_values, uint64_t n, char* d_out16);
+
+/* Counters for benchmarking: kernels launched by this ctx since creation; and, when enabled,
+ * device time per kernel family measured with CUDA events on the ctx's stream around each launch:
+ * ms[0]/launches[0] tokenizer (K1), [1] classification (K2), [2] CSV formatter (K6).
+ * sidgpu_profile(ctx, enable) resets the accumulators. */
+uint64_t sidgpu_launch_count(const sidgpu_ctx* ctx);
+int sidgpu_profile(sidgpu_ctx* ctx, int enable);
+int sidgpu_kernel_times(sidgpu_ctx* ctx, double ms[3], uint64_t launches[3]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,329 @@
+"""Python mirror of the reference's calling interface (call.hpp:12-43) over the C ABI.
+
+The four reference functions take a std::istream and return std::vector<OutputRecord>; here they
+take the pileup text (bytes / bytearray / numpy uint8) and return a list of OutputRecord, with the
+same argument meaning and the same error behaviour (a malformed line raises MalformedPileup, the
+std::invalid_argument of pileup.cpp:9-10).  All work happens in libsidgpu.so on the GPU.
+"""
+import collections
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from ._lib import Config, Fit, Params, SitesView, UniqueView
+
+METHODS = {"local": 0, "bayes": 1, "likelihood_ratio": 2, "quality": 3}
+CSV_HEADER = b"chrom,pos,label,gt,hom_conf,het_conf,conf_type\n"      # sid.cpp:102
+
+OutputRecord = collections.namedtuple(
+    "OutputRecord", "chromosome_name position label genotype confidence_homozygous confidence_heterozygous confidence_type")
+
+
+class SidGpuError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__("sidgpu error %d: %s" % (code, message))
+        self.code = code
+
+
+class MalformedPileup(ValueError):
+    """std::invalid_argument{"Malformed pileup line"} (pileup.cpp:9-10,22-62)."""
+
+
+_MALFORMED_CODES = (3, 4, 5)
+
+
+class DeviceBuffer:
+    def __init__(self, ctx, nbytes):
+        self.ctx = ctx
+        self.nbytes = int(nbytes)
+        p = ctypes.c_void_p()
+        ctx._ck(ctx.lib.sidgpu_malloc(ctx.h, self.nbytes, ctypes.byref(p)))
+        self.ptr = p.value
+
+    def free(self):
+        if self.ptr:
+            self.ctx.lib.sidgpu_free(self.ctx.h, self.ptr)
+            self.ptr = None
+
+    def upload(self, array):
+        a = np.ascontiguousarray(array)
+        assert a.nbytes <= self.nbytes
+        self.ctx._ck(self.ctx.lib.sidgpu_memcpy_h2d(self.ctx.h, self.ptr, a.ctypes.data, a.nbytes))
+        return self
+
+    def download(self, dtype, count):
+        out = np.empty(int(count), dtype=dtype)
+        if out.nbytes:
+            self.ctx._ck(self.ctx.lib.sidgpu_memcpy_d2h(self.ctx.h, out.ctypes.data, self.ptr, out.nbytes))
+        return out
+
+
+def _as_u8(text):
+    if isinstance(text, np.ndarray):
+        return np.ascontiguousarray(text.view(np.uint8).reshape(-1))
+    if isinstance(text, str):
+        text = text.encode()
+    return np.frombuffer(bytes(text) if not isinstance(text, (bytes, bytearray, memoryview)) else text, dtype=np.uint8)
+
+
+class Context:
+    """One GPU context (sidgpu_ctx).  Not thread safe; one per GPU."""
+
+    def __init__(self, device=0, max_chunk_bytes=0, max_sites=0, table_log2=0, stream=None):
+        self.lib = _lib.load()
+        cfg = Config(device, max_chunk_bytes, max_sites, table_log2, stream)
+        h = ctypes.c_void_p()
+        rc = self.lib.sidgpu_create(ctypes.byref(cfg), ctypes.byref(h))
+        if rc != 0:
+            raise SidGpuError(rc, self.lib.sidgpu_last_error(None).decode())
+        self.h = h
+
+    def close(self):
+        if self.h:
+            self.lib.sidgpu_destroy(self.h)
+            self.h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _ck(self, rc):
+        if rc != 0:
+            msg = self.lib.sidgpu_last_error(self.h).decode()
+            if rc in _MALFORMED_CODES:
+                raise MalformedPileup(msg)
+            raise SidGpuError(rc, msg)
+
+    # ---- memory helpers
+    def device_buffer(self, nbytes):
+        return DeviceBuffer(self, nbytes)
+
+    def upload_text(self, text):
+        a = _as_u8(text)
+        buf = DeviceBuffer(self, ((a.nbytes + 15) // 16 + 1) * 16)
+        if a.nbytes:
+            buf.upload(a)
+        buf.text_len = a.nbytes
+        return buf
+
+    def _download(self, ptr, dtype, count):
+        out = np.empty(int(count), dtype=dtype)
+        if out.nbytes:
+            self._ck(self.lib.sidgpu_memcpy_d2h(self.h, out.ctypes.data, ptr, out.nbytes))
+        return out
+
+    @property
+    def launch_count(self):
+        return int(self.lib.sidgpu_launch_count(self.h))
+
+    def profile(self, enable=True):
+        self._ck(self.lib.sidgpu_profile(self.h, 1 if enable else 0))
+
+    def kernel_times(self):
+        """{'tokenize': (ms, launches), 'classify': ..., 'csv': ...} since profile(True)."""
+        ms = (ctypes.c_double * 3)()
+        n = (ctypes.c_uint64 * 3)()
+        self._ck(self.lib.sidgpu_kernel_times(self.h, ms, n))
+        return {k: (ms[i], n[i]) for i, k in enumerate(("tokenize", "classify", "csv"))}
+
+    # ---- K1
+    def tokenize(self, d_text, text_len, begin=0, end=None, want_qual=False):
+        """parsePileupLine/parseReadBases over device text; results copied back as numpy arrays."""
+        end = text_len if end is None else end
+        v = SitesView()
+        ptr = d_text.ptr if isinstance(d_text, DeviceBuffer) else d_text
+        self._ck(self.lib.sidgpu_tokenize(self.h, ptr, text_len, begin, end, 1 if want_qual else 0, ctypes.byref(v)))
+        n = v.n_sites
+        names_pool = self._download(v.d_names, np.uint8, v.names_bytes).tobytes()
+        refs = self._download(v.d_name_ref, np.uint32, n)
+        cache = {}
+
+        def name_of(r):
+            if r not in cache:
+                ln = names_pool[r] | (names_pool[r + 1] << 8)
+                cache[r] = names_pool[r + 2:r + 2 + ln].decode("latin-1")
+            return cache[r]
+
+        return {
+            "n_sites": n,
+            "profile": self._download(v.d_profile, np.uint64, n),
+            "pos": self._download(v.d_pos, np.int32, n),
+            "slot": self._download(v.d_slot, np.uint32, n),
+            "line_off": self._download(v.d_line_off, np.uint64, n) if want_qual else None,
+            "chrom": [name_of(int(r)) for r in refs],
+        }
+
+    # ---- sessions
+    @staticmethod
+    def make_params(method, estimate_prior=False, prior=-1.0, error_threshold=0.1, significance_level=0.05, fit=None):
+        p = Params()
+        p.method = METHODS[method] if isinstance(method, str) else int(method)
+        p.estimate_prior = 1 if estimate_prior else 0
+        p.prior = prior
+        p.error_threshold = error_threshold
+        p.significance_level = significance_level
+        if fit is not None:
+            p.fit_given = 1
+            p.fit_pi, p.fit_eps = fit[0], fit[1]
+            for i in range(4):
+                p.fit_nd[i] = fit[2][i]
+        return p
+
+    def begin(self, params):
+        self._ck(self.lib.sidgpu_begin(self.h, ctypes.byref(params)))
+
+    def feed(self, d_text, text_len, begin=0, end=None):
+        end = text_len if end is None else end
+        n = ctypes.c_uint64()
+        ptr = d_text.ptr if isinstance(d_text, DeviceBuffer) else d_text
+        self._ck(self.lib.sidgpu_feed(self.h, ptr, text_len, begin, end, ctypes.byref(n)))
+        return n.value
+
+    def finish(self):
+        self._ck(self.lib.sidgpu_finish(self.h))
+
+    def emit_csv(self, site_begin, n_sites, d_out, out_cap):
+        b, r = ctypes.c_uint64(), ctypes.c_uint64()
+        ptr = d_out.ptr if isinstance(d_out, DeviceBuffer) else d_out
+        self._ck(self.lib.sidgpu_emit_csv(self.h, site_begin, n_sites, ptr, out_cap, ctypes.byref(b), ctypes.byref(r)))
+        return b.value, r.value
+
+    def emit_records(self, site_begin, n_sites):
+        lab = DeviceBuffer(self, max(n_sites, 1))
+        gt = DeviceBuffer(self, max(2 * n_sites, 2))
+        hom = DeviceBuffer(self, max(8 * n_sites, 8))
+        het = DeviceBuffer(self, max(8 * n_sites, 8))
+        try:
+            self._ck(self.lib.sidgpu_emit_records(self.h, site_begin, n_sites, lab.ptr, gt.ptr, hom.ptr, het.ptr))
+            return (lab.download(np.uint8, n_sites), gt.download(np.uint8, 2 * n_sites).reshape(-1, 2),
+                    hom.download(np.float64, n_sites), het.download(np.float64, n_sites))
+        finally:
+            for b in (lab, gt, hom, het):
+                b.free()
+
+    def session_fit(self):
+        f = Fit()
+        nd = (ctypes.c_double * 4)()
+        nu = ctypes.c_uint64()
+        self._ck(self.lib.sidgpu_session_fit(self.h, ctypes.byref(f), nd, ctypes.byref(nu)))
+        return {"pi": f.pi, "eps": f.eps, "fval": f.fval, "iterations": f.iterations, "evaluations": f.evaluations,
+                "converged": bool(f.converged), "nd": list(nd), "n_unique": nu.value}
+
+    # ---- K3 / K4 / K5
+    def histogram(self, min_coverage=0):
+        v = UniqueView()
+        self._ck(self.lib.sidgpu_histogram(self.h, min_coverage, ctypes.byref(v)))
+        return (self._download(v.d_profile, np.uint64, v.n_unique), self._download(v.d_count, np.uint64, v.n_unique),
+                list(v.nd))
+
+    def lynch_objective(self, nd, pi, eps):
+        a = (ctypes.c_double * 4)(*nd)
+        out = ctypes.c_double()
+        self._ck(self.lib.sidgpu_lynch_objective(self.h, a, pi, eps, ctypes.byref(out)))
+        return out.value
+
+    def lynch_fit(self, nd):
+        a = (ctypes.c_double * 4)(*nd)
+        f = Fit()
+        self._ck(self.lib.sidgpu_lynch_fit(self.h, a, ctypes.byref(f)))
+        return {"pi": f.pi, "eps": f.eps, "fval": f.fval, "iterations": f.iterations, "evaluations": f.evaluations,
+                "converged": bool(f.converged)}
+
+    def bh_adjust(self, p):
+        p = np.ascontiguousarray(p, dtype=np.float64)
+        if p.size == 0:
+            return p.copy()
+        d_in = DeviceBuffer(self, p.nbytes).upload(p)
+        d_out = DeviceBuffer(self, p.nbytes)
+        try:
+            self._ck(self.lib.sidgpu_bh_adjust(self.h, d_in.ptr, p.size, d_out.ptr))
+            return d_out.download(np.float64, p.size)
+        finally:
+            d_in.free()
+            d_out.free()
+
+    def format_g(self, values):
+        v = np.ascontiguousarray(values, dtype=np.float64)
+        if v.size == 0:
+            return []
+        d_in = DeviceBuffer(self, v.nbytes).upload(v)
+        d_out = DeviceBuffer(self, 16 * v.size)
+        try:
+            self._ck(self.lib.sidgpu_format_g(self.h, d_in.ptr, v.size, d_out.ptr))
+            raw = d_out.download(np.uint8, 16 * v.size).reshape(-1, 16)
+            return [bytes(r).split(b"\0")[0].decode() for r in raw]
+        finally:
+            d_in.free()
+            d_out.free()
+
+    # ---- the one-call host path (what the `sid` binary does)
+    def call_host(self, text, params, csv_capacity=None):
+        """Returns (csv_rows_bytes, n_sites, n_rows); the header line is not included."""
+        a = _as_u8(text)
+        cap = int(csv_capacity) if csv_capacity else max(4096, a.nbytes + a.nbytes // 2)
+        while True:
+            out = np.empty(cap, dtype=np.uint8)
+            nb, ns, nr = ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_uint64()
+            rc = self.lib.sidgpu_call_host(self.h, ctypes.byref(params), a.ctypes.data if a.nbytes else None, a.nbytes,
+                                           out.ctypes.data, cap, ctypes.byref(nb), ctypes.byref(ns), ctypes.byref(nr))
+            if rc == 6 and nb.value > cap:      # SIDGPU_ECAPACITY: retry with the size the library reported
+                cap = nb.value + 4096
+                continue
+            self._ck(rc)
+            return out[:nb.value].tobytes(), ns.value, nr.value
+
+
+def parse_csv_rows(rows):
+    """CSV rows (no header) -> list of OutputRecord (call.hpp:23-27)."""
+    out = []
+    for line in rows.split(b"\n"):
+        if not line:
+            continue
+        f = line.decode("latin-1").rsplit(",", 6)
+        out.append(OutputRecord(f[0], int(f[1]), f[2], f[3], float(f[4]), float(f[5]), f[6]))
+    return out
+
+
+_default_ctx = None
+
+
+def default_context():
+    global _default_ctx
+    if _default_ctx is None:
+        _default_ctx = Context()
+    return _default_ctx
+
+
+def _call(text, params, ctx):
+    ctx = ctx or default_context()
+    rows, _, _ = ctx.call_host(text, params)
+    return parse_csv_rows(rows)
+
+
+# call.hpp:40-43 -- same names, same argument order and meaning.
+def callSiteMLError(text, estimate_prior=False, prior=-1.0, error_threshold=0.1, significance_level=0.05, ctx=None):
+    return _call(text, Context.make_params("local", estimate_prior, prior, error_threshold, significance_level), ctx)
+
+
+def callBayes(text, ctx=None):
+    return _call(text, Context.make_params("bayes"), ctx)
+
+
+def callLikelihoodRatio(text, use_prior=False, significance_level=0.05, ctx=None):
+    return _call(text, Context.make_params("likelihood_ratio", use_prior, -1.0, 0.1, significance_level), ctx)
+
+
+def callQualityBasedSimple(text, estimate_prior=False, prior=-1.0, significance_level=0.05, ctx=None):
+    return _call(text, Context.make_params("quality", estimate_prior, prior, 0.1, significance_level), ctx)
+
+
+def sid_csv(text, method="local", estimate_prior=False, prior=-1.0, error_threshold=0.1, significance_level=0.05, ctx=None):
+    """What `sid -m METHOD file` prints on stdout (sid.cpp:92-105), as bytes."""
+    if method not in METHODS:
+        return CSV_HEADER                       # sid.cpp:92-100 has no else branch: header only
+    ctx = ctx or default_context()
+    rows, _, _ = ctx.call_host(text, Context.make_params(method, estimate_prior, prior, error_threshold, significance_level))
+    return CSV_HEADER + rows

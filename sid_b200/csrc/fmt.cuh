@@ -1,0 +1,137 @@
+// Text formatting for the CSV rows of operator<< (call.hpp:29-38): `int` and `double` through
+// iostream defaults, i.e. printf("%d") and printf("%g") (6 significant digits, glibc: correctly
+// rounded, round-half-even on the exact binary value).  fmt_g6 is exact: the decimal digits come
+// from big-integer arithmetic on the double's exact value, never from floating point.
+#pragma once
+#include "common.cuh"
+
+namespace sid {
+
+SID_HD int fmt_i32(int32_t v, char* out) {
+    char tmp[12];
+    int n = 0, len = 0;
+    uint32_t u = v < 0 ? 0u - (uint32_t)v : (uint32_t)v;
+    do { tmp[n++] = (char)('0' + u % 10); u /= 10; } while (u);
+    if (v < 0) out[len++] = '-';
+    while (n) out[len++] = tmp[--n];
+    return len;
+}
+
+SID_HD int digits_i32(int32_t v) {
+    uint32_t u = v < 0 ? 0u - (uint32_t)v : (uint32_t)v;
+    int n = v < 0 ? 2 : 1;
+    while (u >= 10) { u /= 10; ++n; }
+    return n;
+}
+
+// round_half_even(m * 2^e2 * 10^j) for j >= 0, result known to be < 2^40.
+SID_HD uint64_t scaled_round(uint64_t m, int e2, int j) {
+    const int NL = 30;               // 53 + 2.33*345 bits < 30*32
+    uint32_t w[NL];
+    int len = 2;
+    w[0] = (uint32_t)m;
+    w[1] = (uint32_t)(m >> 32);
+    for (int i = 2; i < NL; ++i) w[i] = 0;
+    int rem = j;
+    while (rem > 0) {                // multiply by 5^rem in chunks of 5^13 < 2^32
+        int step = rem > 13 ? 13 : rem;
+        uint32_t mul = 1;
+        for (int i = 0; i < step; ++i) mul *= 5u;
+        uint64_t carry = 0;
+        for (int i = 0; i < len; ++i) {
+            uint64_t t = (uint64_t)w[i] * mul + carry;
+            w[i] = (uint32_t)t;
+            carry = t >> 32;
+        }
+        if (carry && len < NL) w[len++] = (uint32_t)carry;
+        rem -= step;
+    }
+    const int s = e2 + j;            // value = W * 2^s
+    if (s >= 0) {                    // exact integer; small by contract
+        uint64_t v = (uint64_t)w[0] | ((uint64_t)w[1] << 32);
+        return v << s;
+    }
+    const int k = -s;                // drop k bits with round-half-even
+    const int limb = k >> 5, bit = k & 31;
+    uint64_t lo = 0;
+    for (int i = 0; i < 3; ++i) {
+        int idx = limb + i;
+        uint64_t part = idx < len ? (uint64_t)w[idx] : 0;
+        if (i == 0) lo = part >> bit;
+        else if (32 * i - bit < 64) lo |= part << (32 * i - bit);
+    }
+    // half bit is bit (k-1); sticky = any bit below it
+    const int hk = k - 1;
+    const int hl = hk >> 5, hb = hk & 31;
+    const bool half = hl < len ? ((w[hl] >> hb) & 1u) != 0 : false;
+    bool sticky = false;
+    if (hl < len && (w[hl] & ((1u << hb) - 1u))) sticky = true;
+    for (int i = 0; i < hl && i < len && !sticky; ++i) if (w[i]) sticky = true;
+    if (half && (sticky || (lo & 1))) ++lo;
+    return lo;
+}
+
+// printf("%g", x).  out needs 16 bytes; returns the length (no terminator written).
+SID_HD int fmt_g6(double x, char* out) {
+    const uint64_t bits = double_bits(x);
+    const bool neg = (bits >> 63) != 0;
+    const int be = (int)((bits >> 52) & 0x7FF);
+    const uint64_t frac = bits & ((1ull << 52) - 1);
+    int n = 0;
+    if (neg) out[n++] = '-';
+    if (be == 0x7FF) {
+        if (frac) { out[n++] = 'n'; out[n++] = 'a'; out[n++] = 'n'; }
+        else { out[n++] = 'i'; out[n++] = 'n'; out[n++] = 'f'; }
+        return n;
+    }
+    if (be == 0 && frac == 0) { out[n++] = '0'; return n; }
+    uint64_t m;
+    int e2;
+    if (be == 0) { m = frac; e2 = -1074; } else { m = frac | (1ull << 52); e2 = be - 1075; }
+    const int l2 = 63 - clz64(m) + e2;                 // floor(log2 x)
+    int e10 = (l2 * 78913) >> 18;                      // ~ floor(l2 * log10 2), at most one off
+    uint64_t d = 0;
+    if (e10 > 5) {
+        // Values >= 1e6 never occur on this path (p-values and probabilities); keep the output
+        // well-formed with ordinary floating point instead of big-integer division.
+        double y = x < 0 ? -x : x;
+        int e = 0;
+        while (y >= 10.0) { y /= 10.0; ++e; }
+        d = (uint64_t)(y * 100000.0 + 0.5);
+        if (d >= 1000000) { d /= 10; ++e; }
+        e10 = e;
+    } else {
+        for (int it = 0; it < 4; ++it) {
+            d = scaled_round(m, e2, 5 - e10);
+            if (d >= 1000000) { ++e10; if (e10 > 5) { d = 100000; break; } continue; }
+            if (d < 100000) { --e10; continue; }
+            break;
+        }
+    }
+    char dig[6];
+    for (int i = 5; i >= 0; --i) { dig[i] = (char)('0' + d % 10); d /= 10; }
+    int nd = 6;
+    while (nd > 1 && dig[nd - 1] == '0') --nd;        // %g strips trailing zeros
+    if (e10 < -4 || e10 >= 6) {
+        out[n++] = dig[0];
+        if (nd > 1) { out[n++] = '.'; for (int i = 1; i < nd; ++i) out[n++] = dig[i]; }
+        out[n++] = 'e';
+        int e = e10;
+        if (e < 0) { out[n++] = '-'; e = -e; } else out[n++] = '+';
+        if (e >= 100) { out[n++] = (char)('0' + e / 100); e %= 100; }
+        out[n++] = (char)('0' + e / 10);
+        out[n++] = (char)('0' + e % 10);
+    } else if (e10 >= 0) {
+        const int ip = e10 + 1;                        // digits before the decimal point
+        for (int i = 0; i < ip; ++i) out[n++] = i < nd ? dig[i] : '0';
+        if (nd > ip) { out[n++] = '.'; for (int i = ip; i < nd; ++i) out[n++] = dig[i]; }
+    } else {
+        out[n++] = '0';
+        out[n++] = '.';
+        for (int i = 0; i < -e10 - 1; ++i) out[n++] = '0';
+        for (int i = 0; i < nd; ++i) out[n++] = dig[i];
+    }
+    return n;
+}
+
+}  // namespace sid

@@ -1,0 +1,128 @@
+// sidgpu_call_host: the host-buffer path behind the `sid` binary and the call.hpp wrappers
+// (replaces the ifstream + readFile + vector<OutputRecord> + operator<< chain of sid.cpp:85-105).
+// Text goes to the device in line-aligned chunks through two device buffers (copy stream) while
+// the previous chunk is processed (compute stream); CSV comes back through two device buffers
+// (copy-out stream).  With pinned h_text / h_csv the three overlap; pageable memory works too.
+
+namespace {
+
+struct HostPath {
+    sidgpu_ctx* ctx;
+    DevBuf text[2], csv[2];
+    cudaEvent_t ev_in[2] {nullptr, nullptr}, ev_out[2] {nullptr, nullptr};
+    ~HostPath() {
+        for (int i = 0; i < 2; ++i) {
+            release(text[i]);
+            release(csv[i]);
+            if (ev_in[i]) cudaEventDestroy(ev_in[i]);
+            if (ev_out[i]) cudaEventDestroy(ev_out[i]);
+        }
+    }
+};
+
+// End (exclusive) of the chunk starting at `start`: the last line end within max_chunk, or the
+// end of the first line when a single line is longer than that.
+size_t chunk_end(const char* t, size_t len, size_t start, size_t max_chunk) {
+    size_t end = std::min(len, start + max_chunk);
+    if (end == len) return end;
+    const void* nl = memrchr(t + start, '\n', end - start);
+    if (nl) return (size_t)((const char*)nl - t) + 1;
+    const void* fw = memchr(t + end, '\n', len - end);
+    return fw ? (size_t)((const char*)fw - t) + 1 : len;
+}
+
+}  // namespace
+
+extern "C" int sidgpu_call_host(sidgpu_ctx* ctx, const sidgpu_params* params, const char* h_text, size_t text_len,
+                                char* h_csv, size_t csv_cap, uint64_t* csv_bytes, uint64_t* n_sites, uint64_t* n_rows) {
+    if (!ctx || !params || (text_len && !h_text)) return SIDGPU_EINVAL;
+    CK(cudaSetDevice(ctx->device));
+    HostPath hp;
+    hp.ctx = ctx;
+    for (int i = 0; i < 2; ++i) {
+        CK(cudaEventCreateWithFlags(&hp.ev_in[i], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&hp.ev_out[i], cudaEventDisableTiming));
+    }
+    TRY(sidgpu_begin(ctx, params));
+    const size_t max_chunk = ctx->max_chunk;
+    uint64_t total_sites = 0, total_rows = 0, out_off = 0;
+    bool out_overflow = false;
+
+    auto upload = [&](int b, size_t start, size_t end) -> int {
+        const size_t n = end - start;
+        TRY(ensure(ctx, hp.text[b], ((n + 15) & ~(size_t)15) + 16));
+        CK(cudaMemcpyAsync(hp.text[b].p, h_text + start, n, cudaMemcpyHostToDevice, ctx->copy_in));
+        CK(cudaEventRecord(hp.ev_in[b], ctx->copy_in));
+        return SIDGPU_OK;
+    };
+    auto emit_range = [&](int b, uint64_t site_begin, uint64_t count) -> int {
+        if (count == 0) return SIDGPU_OK;
+        CK(cudaEventSynchronize(hp.ev_out[b]));                     // the previous D2H out of csv[b] is done
+        uint64_t bytes = 0, rows = 0;
+        size_t want = std::max<size_t>(hp.csv[b].cap, (size_t)count * 48 + 4096);
+        for (;;) {
+            TRY(ensure(ctx, hp.csv[b], want));
+            const int rc = sidgpu_emit_csv(ctx, site_begin, count, (char*)hp.csv[b].p, hp.csv[b].cap, &bytes, &rows);
+            if (rc == SIDGPU_ECAPACITY) { want = (size_t)bytes + 4096; continue; }
+            if (rc != SIDGPU_OK) return rc;
+            break;
+        }
+        if (out_off + bytes <= csv_cap && h_csv) {
+            CK(cudaMemcpyAsync(h_csv + out_off, hp.csv[b].p, bytes, cudaMemcpyDeviceToHost, ctx->copy_out));
+            CK(cudaEventRecord(hp.ev_out[b], ctx->copy_out));
+        } else {
+            out_overflow = true;
+        }
+        out_off += bytes;
+        total_rows += rows;
+        return SIDGPU_OK;
+    };
+    // one streamed pass over the text; `emit` says whether rows are produced chunk by chunk
+    auto pass = [&](bool emit) -> int {
+        if (text_len == 0) return SIDGPU_OK;
+        size_t start = 0, end = chunk_end(h_text, text_len, 0, max_chunk);
+        TRY(upload(0, start, end));
+        for (int i = 0; start < text_len; ++i) {
+            const int b = i & 1;
+            const size_t next_start = end;
+            size_t next_end = next_start;
+            if (next_start < text_len) {
+                next_end = chunk_end(h_text, text_len, next_start, max_chunk);
+                TRY(upload(b ^ 1, next_start, next_end));           // overlaps with the work on chunk i
+            }
+            CK(cudaStreamWaitEvent(ctx->stream, hp.ev_in[b], 0));
+            uint64_t n = 0;
+            TRY(sidgpu_feed(ctx, (const char*)hp.text[b].p, end - start, 0, end - start, &n));
+            total_sites += n;
+            if (emit) TRY(emit_range(b, 0, n));
+            start = next_start;
+            end = next_end;
+        }
+        return SIDGPU_OK;
+    };
+
+    const bool streaming = ctx->streaming;
+    if (streaming) {
+        TRY(pass(true));
+    } else {
+        TRY(pass(false));
+        TRY(sidgpu_finish(ctx));
+        if (params->method == SIDGPU_METHOD_QUALITY) {
+            total_sites = 0;
+            TRY(pass(true));                                        // second pass with the fitted prior
+        } else {
+            const uint64_t step = (uint64_t)8 << 20;                // sites per emitted block
+            int b = 0;
+            for (uint64_t s = 0; s < ctx->n_sites_total; s += step, b ^= 1) {
+                TRY(emit_range(b, s, std::min<uint64_t>(step, ctx->n_sites_total - s)));
+            }
+        }
+    }
+    CK(cudaStreamSynchronize(ctx->copy_out));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (csv_bytes) *csv_bytes = out_off;
+    if (n_sites) *n_sites = total_sites;
+    if (n_rows) *n_rows = total_rows;
+    if (out_overflow) return ctx->fail(SIDGPU_ECAPACITY, "CSV needs %llu bytes, buffer has %zu", (unsigned long long)out_off, csv_cap);
+    return SIDGPU_OK;
+}

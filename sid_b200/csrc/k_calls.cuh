@@ -1,0 +1,209 @@
+// K2: per-unique-profile classification (+ the text every site with that profile will print).
+//   callSiteMLError body call.cpp:238-273, callBayes body call.cpp:176-194,
+//   callLikelihoodRatio body call.cpp:93-127, likelihoodRatioTest stats.cpp:29-37.
+// K6: CSV rows, operator<< call.hpp:29-38 + sid.cpp:103-105.
+#pragma once
+#include "calls.cuh"
+#include "common.cuh"
+#include "k_tokenize.cuh"
+#include "table.cuh"
+
+namespace sid {
+
+struct ClassifyParams {
+    TableView table;
+    uint32_t first, last;        // range of table.entry_list to classify
+    int method;                  // 0 local, 1 bayes, 2 likelihood_ratio (after BH: p-values given)
+    double prior, error_threshold, alpha;
+    LynchConsts lynch;
+    double pi;
+    int use_prior;
+    const double* adj_hom;       // likelihood_ratio: BH-adjusted p-values per entry index (or NULL)
+    const double* adj_het;
+    const uint32_t* entry_to_unique;   // likelihood_ratio: entry index -> row of adj_* (0xFFFFFFFF: dropped)
+};
+
+#if defined(__CUDACC__)
+
+__device__ __forceinline__ void store_class(const TableView& t, uint32_t slot, const CallResult& r, bool probability) {
+    t.label[slot] = r.label;
+    t.gt[2 * slot] = r.gt0;
+    t.gt[2 * slot + 1] = r.gt1;
+    t.hom[slot] = r.hom;
+    t.het[slot] = r.het;
+    char buf[SUFFIX_BYTES];
+    const int n = format_suffix(r, probability, buf);
+    buf[SUFFIX_BYTES - 1] = (char)n;
+    char* dst = t.suffix + (size_t)slot * SUFFIX_BYTES;
+    for (int i = 0; i < n; ++i) dst[i] = buf[i];
+    dst[SUFFIX_BYTES - 1] = (char)n;
+}
+
+__global__ void __launch_bounds__(128) k_classify(const ClassifyParams p) {
+    const uint32_t e = p.first + blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= p.last) return;
+    const uint32_t slot = p.table.entry_list[e];
+    const uint64_t profile = p.table.keys[slot];
+    CallResult r;
+    if (p.method == 0) {
+        r = call_local(profile, p.prior, p.error_threshold, p.alpha);
+    } else if (p.method == 1) {
+        r = call_bayes(profile, p.lynch, p.pi);
+    } else {
+        int f, s;
+        major_alleles(profile, f, s);
+        r.gt0 = r.gt1 = base_char(f);
+        r.label = 0;
+        const uint32_t u = p.entry_to_unique[e];
+        if (u == 0xFFFFFFFFu) { r.label = 255; r.hom = r.het = 0; }
+        else {
+            r.hom = p.adj_hom[u];
+            r.het = p.adj_het[u];
+            if (r.het < p.alpha) { r.label = 1; r.gt1 = base_char(s); }     // call.cpp:120-123
+        }
+    }
+    store_class(p.table, slot, r, p.method == 1);
+}
+
+// ------------------------------------------------------------------------------------------- K6
+constexpr int CSV_THREADS = 256;
+constexpr int CSV_PER_THREAD = 4;
+constexpr int CSV_TILE = CSV_THREADS * CSV_PER_THREAD;
+
+struct CsvParams {
+    uint64_t site_begin, n_sites;
+    const int32_t* pos;
+    const uint32_t* slot;
+    const uint32_t* name_ref;
+    const char* site_suffix;     // per-site suffixes (quality) or NULL -> table.suffix[slot]
+    TableView table;
+    const char* pool;
+    char* out;
+    uint64_t out_cap;
+    unsigned int* ticket;
+    unsigned long long* status;
+    unsigned long long* bytes_out;
+    unsigned long long* rows_out;
+    uint32_t n_tiles;
+};
+
+__global__ void __launch_bounds__(CSV_THREADS) k_csv(const CsvParams p) {
+    __shared__ uint32_t s_tile;
+    __shared__ uint64_t s_base;
+    __shared__ uint32_t s_warp_sums[CSV_THREADS / 32];
+    __shared__ uint32_t s_warp_rows[CSV_THREADS / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_tile = atomicAdd(p.ticket, 1u);
+        __syncthreads();
+        const uint32_t tile = s_tile;
+        if (tile >= p.n_tiles) break;
+        const uint64_t first = (uint64_t)tile * CSV_TILE + (uint64_t)tid * CSV_PER_THREAD;
+        uint32_t len[CSV_PER_THREAD];
+        uint32_t mine = 0, rows = 0;
+#pragma unroll
+        for (int k = 0; k < CSV_PER_THREAD; ++k) {
+            len[k] = 0;
+            const uint64_t i = first + k;
+            if (i < p.n_sites) {
+                const uint64_t site = p.site_begin + i;
+                const char* sfx = p.site_suffix ? p.site_suffix + site * SUFFIX_BYTES
+                                                : p.table.suffix + (size_t)p.slot[site] * SUFFIX_BYTES;
+                const uint32_t sl = (uint8_t)sfx[SUFFIX_BYTES - 1];
+                if (sl) {
+                    const uint8_t* nm = (const uint8_t*)p.pool + p.name_ref[site];
+                    const uint32_t nl = (uint32_t)nm[0] | ((uint32_t)nm[1] << 8);
+                    len[k] = nl + 1 + (uint32_t)digits_i32(p.pos[site]) + sl;
+                    ++rows;
+                }
+            }
+            mine += len[k];
+        }
+        uint32_t incl = mine, rincl = rows;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+            const uint32_t r = __shfl_up_sync(0xFFFFFFFFu, rincl, d);
+            if (lane >= d) { incl += o; rincl += r; }
+        }
+        if (lane == 31) { s_warp_sums[warp] = incl; s_warp_rows[warp] = rincl; }
+        __syncthreads();
+        uint32_t warp_off = 0, total = 0, total_rows = 0;
+#pragma unroll
+        for (int w = 0; w < CSV_THREADS / 32; ++w) {
+            if (w < warp) warp_off += s_warp_sums[w];
+            total += s_warp_sums[w];
+            total_rows += s_warp_rows[w];
+        }
+        if (tid == 0) {
+            uint64_t base = 0;
+            if (tile == 0) {
+                atomicExch(&p.status[0], LB_FLAG_PREFIX | (unsigned long long)total);
+            } else {
+                atomicExch(&p.status[tile], LB_FLAG_AGG | (unsigned long long)total);
+                uint32_t i = tile - 1;
+                for (;;) {
+                    unsigned long long w;
+                    unsigned int spins = 0;
+                    do {
+                        w = *((volatile unsigned long long*)&p.status[i]);
+                        if ((w >> 62) == 0 && ++spins > (1u << 24)) w = LB_FLAG_PREFIX;
+                    } while ((w >> 62) == 0);
+                    base += w & LB_VALUE_MASK;
+                    if (w & LB_FLAG_PREFIX) break;
+                    --i;
+                }
+                atomicExch(&p.status[tile], LB_FLAG_PREFIX | (unsigned long long)(base + total));
+            }
+            s_base = base;
+            if (tile == p.n_tiles - 1) *p.bytes_out = base + total;
+            if (total_rows) atomicAdd(p.rows_out, (unsigned long long)total_rows);
+        }
+        __syncthreads();
+        uint64_t o = s_base + warp_off + incl - mine;
+#pragma unroll
+        for (int k = 0; k < CSV_PER_THREAD; ++k) {
+            if (!len[k]) continue;
+            if (o + len[k] > p.out_cap) { o += len[k]; continue; }      // host checks bytes_out against the capacity
+            const uint64_t site = p.site_begin + first + k;
+            char* w = p.out + o;
+            const uint8_t* nm = (const uint8_t*)p.pool + p.name_ref[site];
+            const uint32_t nl = (uint32_t)nm[0] | ((uint32_t)nm[1] << 8);
+            for (uint32_t i = 0; i < nl; ++i) w[i] = (char)nm[2 + i];
+            w += nl;
+            *w++ = ',';
+            w += fmt_i32(p.pos[site], w);
+            const char* sfx = p.site_suffix ? p.site_suffix + site * SUFFIX_BYTES
+                                            : p.table.suffix + (size_t)p.slot[site] * SUFFIX_BYTES;
+            const uint32_t sl = (uint8_t)sfx[SUFFIX_BYTES - 1];
+            for (uint32_t i = 0; i < sl; ++i) w[i] = sfx[i];
+            o += len[k];
+        }
+    }
+}
+
+// Per-site records instead of text (OutputRecord, call.hpp:14-27).
+struct RecordParams {
+    uint64_t site_begin, n_sites;
+    const uint32_t* slot;
+    TableView table;
+    uint8_t* label;
+    char* gt;
+    double* hom;
+    double* het;
+};
+
+__global__ void k_records(const RecordParams p) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.n_sites) return;
+    const uint32_t s = p.slot[p.site_begin + i];
+    if (p.label) p.label[i] = p.table.label[s];
+    if (p.gt) { p.gt[2 * i] = p.table.gt[2 * s]; p.gt[2 * i + 1] = p.table.gt[2 * s + 1]; }
+    if (p.hom) p.hom[i] = p.table.hom[s];
+    if (p.het) p.het[i] = p.table.het[s];
+}
+
+#endif  // __CUDACC__
+
+}  // namespace sid

@@ -1,0 +1,100 @@
+// `-m quality`: callQualityBasedSimple body (call.cpp:309-370), one thread per site.
+// The j-th counted base is paired with the j-th base-quality and the j-th mapping-quality
+// character (call.cpp:330-331), exactly as the reference does, including the drift that
+// characters without a base ('*', 'N', '<', '>') cause.  The per-read terms come from four
+// 256-entry tables built on the host with the reference's own expressions
+// (pow(10., q / -10.), log(1 - e), ...), so each term is bit-identical; the running sums use a
+// compensated accumulator in place of x87 long double.
+#pragma once
+#include "calls.cuh"
+#include "common.cuh"
+#include "parse.cuh"
+#include "table.cuh"
+
+namespace sid {
+
+constexpr int QUAL_THREADS = 128;
+// log of the smallest value expl() can return on x87 (2^-16446 rounds to zero): below it the
+// reference's exp(log_probability) is exactly 0 and likelihoodRatioTest takes its l_H0 == 0 branch.
+constexpr double LOG_LDBL_ZERO = -11399.498531488861;
+
+struct QualityParams {
+    const uint8_t* text;
+    uint64_t text_len;
+    const uint64_t* line_off;
+    uint64_t site_begin, n_sites;
+    const double* lut;          // [0,256) log(1-e)  [256,512) log(e)  [512,768) log(1-2e/3)  [768,1024) log(2e/3)
+    double prior, alpha;
+    char* site_suffix;          // SUFFIX_BYTES per site
+    unsigned long long* error;
+};
+
+SID_HD uint32_t phred_of(uint8_t c) {                    // parseQualities pileup.cpp:158-163
+    const uint32_t q = (uint8_t)(c - 33);
+    return q < 1 ? 1u : q;
+}
+
+template <class Src>
+SID_HD CallResult call_quality(const Src& src, uint64_t line_abs, const ParsedLine& pl, const double* lut, double prior,
+                               double alpha) {
+    int ref0, ref1;
+    major_alleles(pl.profile, ref0, ref1);                // call.cpp:311-319
+    const int ri = ref_index((uint8_t)pl.ref);
+    CompSum lh, lt;
+    lh.init();
+    lt.init();
+    BasesState b;
+    b.init();
+    uint32_t j = 0;
+    const uint64_t bases = line_abs + pl.bases_off, bq = line_abs + pl.bq_off, mq = line_abs + pl.mq_off;
+    for (uint32_t i = 0; i < pl.bases_len; ++i) {
+        int r = b.feed(src.at(bases + i));
+        if (r >= 4) r = ri;                               // '.' / ',' stand for the reference base
+        if (r < 0) continue;
+        const uint32_t q1 = phred_of(src.at(bq + j)), q2 = phred_of(src.at(mq + j));
+        const uint32_t q = q1 < q2 ? q1 : q2;             // call.cpp:330
+        ++j;
+        lh.add(r == ref0 ? lut[q] : lut[256 + q]);        // call.cpp:331-335
+        lt.add((r == ref0 || r == ref1) ? lut[512 + q] : lut[768 + q]);   // call.cpp:336-340
+    }
+    const uint32_t n = profile_count(pl.profile, ref0) + profile_count(pl.profile, ref1);   // call.cpp:347-349
+    const uint32_t k = profile_count(pl.profile, ref1);
+    lt.add(lgamma((double)n + 1.0) - lgamma((double)(n - k) + 1.0) - lgamma((double)k + 1.0));
+    lt.add(-(double)n * 0.69314718055994530942);
+    double l1 = lh.value(), l2 = lt.value();
+    if (l1 < LOG_LDBL_ZERO) l1 = neg_inf();               // call.cpp:352-353 exp() underflow
+    if (l2 < LOG_LDBL_ZERO) l2 = neg_inf();
+    if (prior > 0) { l1 += log1p(-prior); l2 += log(prior); }   // call.cpp:354-357
+    CallResult res;
+    res.hom = lrt_log(l2, l1);                            // call.cpp:359
+    res.het = lrt_log(l1, l2);                            // call.cpp:360
+    res.label = 0;
+    res.gt0 = res.gt1 = base_char(ref0);
+    if (res.het < alpha) { res.label = 1; res.gt1 = base_char(ref1); }    // call.cpp:364-367
+    return res;
+}
+
+#if defined(__CUDACC__)
+__global__ void __launch_bounds__(QUAL_THREADS) k_quality(const QualityParams p) {
+    const uint64_t i = (uint64_t)blockIdx.x * QUAL_THREADS + threadIdx.x;
+    if (i >= p.n_sites) return;
+    const uint64_t site = p.site_begin + i;
+    const uint64_t line_abs = p.line_off[site];
+    FlatSrc src {p.text, p.text_len};
+    ParsedLine pl;
+    parse_line(src, line_abs, true, pl);
+    char* dst = p.site_suffix + site * SUFFIX_BYTES;
+    if (pl.status != LINE_OK) {
+        atomicMin(p.error, (unsigned long long)((line_abs << 3) | (uint64_t)pl.status));
+        dst[SUFFIX_BYTES - 1] = 0;
+        return;
+    }
+    const CallResult r = call_quality(src, line_abs, pl, p.lut, p.prior, p.alpha);
+    char buf[SUFFIX_BYTES];
+    const int n = format_suffix(r, false, buf);
+    for (int k = 0; k < n; ++k) dst[k] = buf[k];
+    dst[SUFFIX_BYTES - 1] = (char)n;
+}
+#endif
+
+}  // namespace sid

@@ -1,0 +1,1052 @@
+// libsidgpu.so: the C ABI of include/sidgpu.h over the sm_100a kernels.
+// Host-side orchestration only: buffers, streams, sessions, the Nelder-Mead driver.  All pileup
+// parsing, profile building, likelihoods, p-values, histogramming and CSV formatting run in the
+// kernels of k_*.cuh; there is no CPU implementation of any of them in this library.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "../../include/sidgpu.h"
+#include "k_calls.cuh"
+#include "k_lynch.cuh"
+#include "k_quality.cuh"
+#include "k_tokenize.cuh"
+#include "nelder_mead.hpp"
+
+using namespace sid;
+
+namespace {
+
+std::string g_create_error;
+
+// Device-resident counters every kernel of a ctx shares; mirrored in pinned host memory.
+struct Control {
+    unsigned int tok_ticket;
+    unsigned int csv_ticket;
+    unsigned long long n_sites;
+    unsigned long long error;
+    unsigned long long csv_bytes;
+    unsigned long long csv_rows;
+    unsigned int n_entries;
+    unsigned int special_used;
+    unsigned int table_overflow;
+    unsigned int name_cursor;
+    unsigned int name_overflow;
+    unsigned int n_selected;
+    unsigned int obj_done;
+    unsigned int pad0;
+    unsigned long long nd_acc[5];
+    double objective;
+};
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+enum Phase { PHASE_IDLE = 0, PHASE_FEED = 1, PHASE_FINISHED = 2 };
+
+}  // namespace
+
+struct sidgpu_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    cudaStream_t copy_in = nullptr, copy_out = nullptr;
+    std::string err;
+    uint64_t launches = 0;
+    size_t max_chunk = 0;
+
+    Control* d_ctl = nullptr;
+    Control* h_ctl = nullptr;
+
+    // unique-profile table
+    int table_log2 = 0;
+    TableView tab {};
+    // chromosome names
+    NameDict names {};
+    // look-back status words
+    DevBuf tile_status, csv_status;
+    // site store
+    DevBuf pos, slot, name_ref, profile, line_off, site_suffix;
+    uint64_t site_cap = 0;
+    bool want_profile = false, want_line_off = false, want_site_suffix = false;
+    uint64_t n_sites_total = 0;      // sites in the store (accumulate mode) or in the last chunk (streaming)
+    uint64_t chunk_begin = 0, chunk_sites = 0;
+
+    // session
+    sidgpu_params params {};
+    int phase = PHASE_IDLE;
+    bool streaming = false;          // per-chunk emission possible
+    bool counting = false;
+    uint32_t classified = 0;         // entries [0, classified) carry a class for this session
+    const char* last_text = nullptr; // text of the most recent feed (quality needs it at emit time)
+    uint64_t last_text_len = 0;
+    double session_prior = -1;
+    bool fit_done = false;
+    sidgpu_fit fit {};
+    double fit_nd[4] = {0.25, 0.25, 0.25, 0.25};
+
+    // histogram
+    DevBuf sort_keys, sort_vals, u_profile, u_count, u_logM, entry_to_unique, p_hom, p_het, adj_hom, adj_het, bh_c, bh_block;
+    uint64_t n_unique = 0;
+    bool hist_valid = false;
+    DevBuf partials;
+    DevBuf quality_lut;
+
+    // optional per-kernel timing (sidgpu_profile): event pairs recorded around launches, resolved lazily
+    bool profiling = false;
+    struct Pending { cudaEvent_t a, b; int which; };
+    std::vector<Pending> pending;
+    std::vector<cudaEvent_t> free_events;
+    double kernel_ms[4] = {0, 0, 0, 0};
+    uint64_t kernel_launches[4] = {0, 0, 0, 0};
+
+    int fail(int code, const char* fmt, ...) {
+        char buf[512];
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(buf, sizeof buf, fmt, ap);
+        va_end(ap);
+        err = buf;
+        return code;
+    }
+};
+
+namespace {
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return ctx->fail(SIDGPU_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+#define TRY(call)                  \
+    do {                           \
+        int rc_ = (call);          \
+        if (rc_ != SIDGPU_OK) return rc_; \
+    } while (0)
+
+int ensure(sidgpu_ctx* ctx, DevBuf& b, size_t bytes, bool keep = false) {
+    if (bytes <= b.cap) return SIDGPU_OK;
+    size_t want = std::max(bytes, b.cap + b.cap / 2);
+    void* np = nullptr;
+    cudaError_t e = cudaMalloc(&np, want);
+    if (e != cudaSuccess) {
+        want = bytes;
+        e = cudaMalloc(&np, want);
+    }
+    if (e != cudaSuccess) return ctx->fail(SIDGPU_ENOMEM, "cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+    if (keep && b.p && b.cap) {
+        e = cudaMemcpyAsync(np, b.p, b.cap, cudaMemcpyDeviceToDevice, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) { cudaFree(np); return ctx->fail(SIDGPU_ECUDA, "grow copy failed: %s", cudaGetErrorString(e)); }
+    }
+    if (b.p) cudaFree(b.p);
+    b.p = np;
+    b.cap = want;
+    return SIDGPU_OK;
+}
+
+void release(DevBuf& b) {
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr;
+    b.cap = 0;
+}
+
+template <class T>
+T* ctl_field(sidgpu_ctx* ctx, T Control::*m) { return &(ctx->d_ctl->*m); }
+
+int sync_ctl(sidgpu_ctx* ctx) {
+    CK(cudaMemcpyAsync(ctx->h_ctl, ctx->d_ctl, sizeof(Control), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return SIDGPU_OK;
+}
+
+int check_launch(sidgpu_ctx* ctx, const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return ctx->fail(SIDGPU_ECUDA, "launch of %s failed: %s", what, cudaGetErrorString(e));
+    ctx->launches++;
+    return SIDGPU_OK;
+}
+
+enum { PROF_TOKENIZE = 0, PROF_CLASSIFY = 1, PROF_CSV = 2, PROF_OTHER = 3 };
+
+cudaEvent_t take_event(sidgpu_ctx* ctx) {
+    if (!ctx->free_events.empty()) { cudaEvent_t e = ctx->free_events.back(); ctx->free_events.pop_back(); return e; }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+
+struct ProfScope {
+    sidgpu_ctx* ctx;
+    cudaEvent_t a = nullptr;
+    int which;
+    ProfScope(sidgpu_ctx* c, int w) : ctx(c), which(w) {
+        if (ctx->profiling) { a = take_event(ctx); cudaEventRecord(a, ctx->stream); }
+    }
+    ~ProfScope() {
+        if (a) { cudaEvent_t b = take_event(ctx); cudaEventRecord(b, ctx->stream); ctx->pending.push_back({a, b, which}); }
+    }
+};
+
+void resolve_profile(sidgpu_ctx* ctx) {
+    for (auto& p : ctx->pending) {
+        float ms = 0;
+        if (cudaEventSynchronize(p.b) == cudaSuccess && cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) {
+            ctx->kernel_ms[p.which] += ms;
+            ctx->kernel_launches[p.which]++;
+        }
+        ctx->free_events.push_back(p.a);
+        ctx->free_events.push_back(p.b);
+    }
+    ctx->pending.clear();
+}
+
+// ---- table -------------------------------------------------------------------------------------
+
+void free_table(TableView& t) {
+    cudaFree(t.keys); cudaFree(t.counts); cudaFree(t.entry_list); cudaFree(t.suffix);
+    cudaFree(t.label); cudaFree(t.gt); cudaFree(t.hom); cudaFree(t.het);
+    t = TableView {};
+}
+
+int alloc_table(sidgpu_ctx* ctx, int log2cap, TableView& t) {
+    t = TableView {};
+    const size_t cap = (size_t)1 << log2cap, n = cap + 1;
+    t.cap = (uint32_t)cap;
+    t.mask = (uint32_t)(cap - 1);
+    t.n_entries = ctl_field(ctx, &Control::n_entries);
+    t.special_used = ctl_field(ctx, &Control::special_used);
+    t.overflow = ctl_field(ctx, &Control::table_overflow);
+    cudaError_t e = cudaSuccess;
+    auto A = [&](void** p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, bytes); };
+    A((void**)&t.keys, n * 8);
+    A((void**)&t.counts, n * 8);
+    A((void**)&t.entry_list, n * 4);
+    A((void**)&t.suffix, n * SUFFIX_BYTES);
+    A((void**)&t.label, n);
+    A((void**)&t.gt, n * 2);
+    A((void**)&t.hom, n * 8);
+    A((void**)&t.het, n * 8);
+    if (e != cudaSuccess) { free_table(t); return ctx->fail(SIDGPU_ENOMEM, "profile table of 2^%d slots: %s", log2cap, cudaGetErrorString(e)); }
+    CK(cudaMemsetAsync(t.keys, 0xFF, n * 8, ctx->stream));
+    CK(cudaMemsetAsync(t.counts, 0, n * 8, ctx->stream));
+    CK(cudaMemsetAsync(t.suffix, 0, n * SUFFIX_BYTES, ctx->stream));
+    CK(cudaMemsetAsync(t.label, 255, n, ctx->stream));
+    return SIDGPU_OK;
+}
+
+__global__ void k_rehash(TableView from, TableView to, uint32_t n_entries, uint32_t* remap) {
+    const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_entries) return;
+    const uint32_t s = from.entry_list[e];
+    const uint64_t key = from.keys[s];
+    uint32_t h;
+    if (key == TABLE_EMPTY) {
+        h = to.cap;
+        to.keys[h] = key;
+    } else {
+        h = (uint32_t)mix64(key) & to.mask;
+        for (;;) {
+            const unsigned long long old = atomicCAS(&to.keys[h], (unsigned long long)TABLE_EMPTY, (unsigned long long)key);
+            if (old == TABLE_EMPTY) break;
+            h = (h + 1) & to.mask;
+        }
+    }
+    to.entry_list[e] = h;
+    to.counts[h] = from.counts[s];
+    to.label[h] = from.label[s];
+    to.gt[2 * h] = from.gt[2 * s];
+    to.gt[2 * h + 1] = from.gt[2 * s + 1];
+    to.hom[h] = from.hom[s];
+    to.het[h] = from.het[s];
+    for (int i = 0; i < SUFFIX_BYTES; ++i) to.suffix[(size_t)h * SUFFIX_BYTES + i] = from.suffix[(size_t)s * SUFFIX_BYTES + i];
+    remap[s] = h;
+}
+
+__global__ void k_remap_slots(uint32_t* slot, uint64_t n, const uint32_t* remap) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) slot[i] = remap[slot[i]];
+}
+
+// Grows the table by `shift` powers of two, keeping entries (and their order), counts and classes.
+int grow_table(sidgpu_ctx* ctx, int shift, uint64_t stored_sites) {
+    CK(cudaStreamSynchronize(ctx->stream));
+    TRY(sync_ctl(ctx));
+    const uint32_t n_entries = ctx->h_ctl->n_entries;
+    TableView nt;
+    TRY(alloc_table(ctx, ctx->table_log2 + shift, nt));
+    uint32_t* remap = nullptr;
+    CK(cudaMalloc((void**)&remap, ((size_t)ctx->tab.cap + 1) * 4));
+    if (n_entries) {
+        k_rehash<<<(n_entries + 255) / 256, 256, 0, ctx->stream>>>(ctx->tab, nt, n_entries, remap);
+        TRY(check_launch(ctx, "k_rehash"));
+        if (stored_sites) {
+            k_remap_slots<<<(unsigned)((stored_sites + 255) / 256), 256, 0, ctx->stream>>>((uint32_t*)ctx->slot.p, stored_sites, remap);
+            TRY(check_launch(ctx, "k_remap_slots"));
+        }
+    }
+    CK(cudaMemsetAsync(ctl_field(ctx, &Control::table_overflow), 0, sizeof(unsigned int), ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(remap);
+    free_table(ctx->tab);
+    ctx->tab = nt;
+    ctx->table_log2 += shift;
+    return SIDGPU_OK;
+}
+
+int reset_table(sidgpu_ctx* ctx) {
+    const size_t n = (size_t)ctx->tab.cap + 1;
+    CK(cudaMemsetAsync(ctx->tab.keys, 0xFF, n * 8, ctx->stream));
+    CK(cudaMemsetAsync(ctx->tab.counts, 0, n * 8, ctx->stream));
+    CK(cudaMemsetAsync(ctx->tab.suffix, 0, n * SUFFIX_BYTES, ctx->stream));
+    CK(cudaMemsetAsync(ctx->tab.label, 255, n, ctx->stream));
+    CK(cudaMemsetAsync(ctl_field(ctx, &Control::n_entries), 0, sizeof(unsigned int), ctx->stream));
+    CK(cudaMemsetAsync(ctl_field(ctx, &Control::special_used), 0, sizeof(unsigned int), ctx->stream));
+    CK(cudaMemsetAsync(ctl_field(ctx, &Control::table_overflow), 0, sizeof(unsigned int), ctx->stream));
+    ctx->classified = 0;
+    ctx->hist_valid = false;
+    return SIDGPU_OK;
+}
+
+// ---- site store --------------------------------------------------------------------------------
+
+int ensure_sites(sidgpu_ctx* ctx, uint64_t n, bool keep) {
+    if (n > ctx->site_cap || (ctx->want_profile && ctx->profile.cap < n * 8) || (ctx->want_line_off && ctx->line_off.cap < n * 8) ||
+        (ctx->want_site_suffix && ctx->site_suffix.cap < n * SUFFIX_BYTES)) {
+        const uint64_t cap = std::max<uint64_t>(n, ctx->site_cap);
+        TRY(ensure(ctx, ctx->pos, cap * 4, keep));
+        TRY(ensure(ctx, ctx->slot, cap * 4, keep));
+        TRY(ensure(ctx, ctx->name_ref, cap * 4, keep));
+        if (ctx->want_profile) TRY(ensure(ctx, ctx->profile, cap * 8, keep));
+        if (ctx->want_line_off) TRY(ensure(ctx, ctx->line_off, cap * 8, keep));
+        if (ctx->want_site_suffix) TRY(ensure(ctx, ctx->site_suffix, cap * SUFFIX_BYTES, keep));
+        ctx->site_cap = cap;
+    }
+    return SIDGPU_OK;
+}
+
+const char* status_text(int st) {
+    switch (st) {
+        case LINE_MALFORMED: return "Malformed pileup line";
+        case LINE_MISSING_MAPQ: return "Malformed pileup line or missing mapping qualities";
+        case LINE_QUAL_SHORT: return "fewer quality characters than counted bases";
+        default: return "internal tokenizer error";
+    }
+}
+
+// Runs K1 over [range_begin, range_end) writing sites from index site_base.  On return
+// *n_out holds the number of sites the range produced.
+int run_tokenizer(sidgpu_ctx* ctx, const char* d_text, size_t text_len, size_t range_begin, size_t range_end,
+                  bool want_qual, bool use_table, uint64_t site_base, bool keep_sites, uint64_t* n_out) {
+    if (((uintptr_t)d_text & 15) != 0) return ctx->fail(SIDGPU_EINVAL, "d_text must be 16-byte aligned");
+    if (range_begin > range_end || range_end > text_len) return ctx->fail(SIDGPU_EINVAL, "bad range [%zu,%zu) for text of %zu bytes", range_begin, range_end, text_len);
+    *n_out = 0;
+    if (range_begin == range_end) return SIDGPU_OK;
+    const uint64_t tile0 = range_begin & ~(uint64_t)15;
+    const uint64_t span = range_end - tile0;
+    const uint64_t n_tiles64 = (span + TILE_BYTES - 1) / TILE_BYTES;
+    if (n_tiles64 > 0x7FFFFFFFull) return ctx->fail(SIDGPU_EINVAL, "range too large");
+    const uint32_t n_tiles = (uint32_t)n_tiles64;
+    TRY(ensure(ctx, ctx->tile_status, (size_t)n_tiles * 8));
+
+    uint64_t guess = (range_end - range_begin) / 24 + 4096;
+    for (int attempt = 0;; ++attempt) {
+        TRY(ensure_sites(ctx, site_base + guess, keep_sites || attempt > 0 ? keep_sites : false));
+        CK(cudaMemsetAsync(ctx->tile_status.p, 0, (size_t)n_tiles * 8, ctx->stream));
+        CK(cudaMemsetAsync(ctl_field(ctx, &Control::tok_ticket), 0, sizeof(unsigned int), ctx->stream));
+        CK(cudaMemsetAsync(ctl_field(ctx, &Control::n_sites), 0, sizeof(unsigned long long), ctx->stream));
+        CK(cudaMemsetAsync(ctl_field(ctx, &Control::error), 0xFF, sizeof(unsigned long long), ctx->stream));
+        TokParams p {};
+        p.text = (const uint8_t*)d_text;
+        p.text_len = text_len;
+        p.range_begin = range_begin;
+        p.range_end = range_end;
+        p.tile0 = tile0;
+        p.n_tiles = n_tiles;
+        p.site_base = site_base;
+        p.site_cap = ctx->site_cap;
+        p.profile = ctx->want_profile ? (uint64_t*)ctx->profile.p : nullptr;
+        p.pos = (int32_t*)ctx->pos.p;
+        p.slot = (uint32_t*)ctx->slot.p;
+        p.name_ref = (uint32_t*)ctx->name_ref.p;
+        p.line_off = ctx->want_line_off ? (uint64_t*)ctx->line_off.p : nullptr;
+        p.tile_ticket = ctl_field(ctx, &Control::tok_ticket);
+        p.tile_status = (unsigned long long*)ctx->tile_status.p;
+        p.n_sites = ctl_field(ctx, &Control::n_sites);
+        p.error = ctl_field(ctx, &Control::error);
+        p.table = ctx->tab;
+        p.names = ctx->names;
+        p.use_table = use_table ? 1 : 0;
+        p.count_profiles = 0;
+        p.want_qual = want_qual ? 1 : 0;
+        const int max_ctas = ctx->sm_count * 5;
+        const unsigned grid = (unsigned)std::min<uint64_t>(n_tiles, (uint64_t)max_ctas);
+        {
+            ProfScope prof(ctx, PROF_TOKENIZE);
+            if (want_qual) k_tokenize<false><<<grid, TOK_THREADS, 0, ctx->stream>>>(p);
+            else k_tokenize<true><<<grid, TOK_THREADS, 0, ctx->stream>>>(p);
+        }
+        TRY(check_launch(ctx, "k_tokenize"));
+        TRY(sync_ctl(ctx));
+        const Control& c = *ctx->h_ctl;
+        if (c.name_overflow) return ctx->fail(SIDGPU_ECAPACITY, c.name_overflow == 2 ? "chromosome name longer than 65535 bytes" : "chromosome name dictionary is full");
+        if (c.error != ~0ull) {
+            const int st = (int)(c.error & 7);
+            const unsigned long long off = c.error >> 3;
+            if (st == LINE_MALFORMED + 5) {              // site store too small for this many lines: grow and retry
+                guess = attempt == 0 ? (range_end - range_begin) / 8 + 4096 : (range_end - range_begin) / 2 + 4096;
+                if (attempt >= 2) return ctx->fail(SIDGPU_EINTERNAL, "site store sizing failed");
+                continue;
+            }
+            const int code = st == LINE_MISSING_MAPQ ? SIDGPU_EMISSING_MAPQ : st == LINE_QUAL_SHORT ? SIDGPU_EQUAL_SHORT
+                             : st == LINE_MALFORMED ? SIDGPU_EMALFORMED : SIDGPU_EINTERNAL;
+            return ctx->fail(code, "%s (line starting at byte %llu)", status_text(st), off);
+        }
+        if (c.table_overflow) {
+            TRY(grow_table(ctx, 2, keep_sites ? site_base : 0));
+            continue;
+        }
+        *n_out = c.n_sites;
+        // keep the load factor below one half for the next chunk
+        while ((uint64_t)c.n_entries * 2 > ctx->tab.cap) TRY(grow_table(ctx, 2, site_base + c.n_sites));
+        return SIDGPU_OK;
+    }
+}
+
+__global__ void k_count_slots(const uint32_t* slot, uint64_t begin, uint64_t n, unsigned long long* counts) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) atomicAdd(&counts[slot[begin + i]], 1ull);
+}
+
+LynchConsts host_lynch_consts(const double nd[4], double eps) { return lynch_consts(nd, eps); }
+
+int classify_entries(sidgpu_ctx* ctx, uint32_t first, uint32_t last) {
+    if (first >= last) return SIDGPU_OK;
+    ClassifyParams p {};
+    p.table = ctx->tab;
+    p.first = first;
+    p.last = last;
+    p.method = ctx->params.method == SIDGPU_METHOD_LOCAL ? 0 : ctx->params.method == SIDGPU_METHOD_BAYES ? 1 : 2;
+    p.prior = ctx->session_prior;
+    p.error_threshold = ctx->params.error_threshold;
+    p.alpha = ctx->params.significance_level;
+    if (p.method != 0) {
+        p.lynch = host_lynch_consts(ctx->fit_nd, ctx->fit.eps);
+        p.pi = ctx->fit.pi;
+        p.use_prior = ctx->params.estimate_prior;
+        p.adj_hom = (const double*)ctx->adj_hom.p;
+        p.adj_het = (const double*)ctx->adj_het.p;
+        p.entry_to_unique = (const uint32_t*)ctx->entry_to_unique.p;
+    }
+    {
+        ProfScope prof(ctx, PROF_CLASSIFY);
+        k_classify<<<(last - first + 127) / 128, 128, 0, ctx->stream>>>(p);
+    }
+    return check_launch(ctx, "k_classify");
+}
+
+int sort_pairs(sidgpu_ctx* ctx, unsigned long long* keys, uint32_t* vals, uint32_t n_pow2) {
+    const uint32_t blocks = n_pow2 / BITONIC_BLOCK;
+    k_bitonic_local<<<blocks, BITONIC_BLOCK / 2, 0, ctx->stream>>>(keys, vals, n_pow2, 0, 0, 1);
+    TRY(check_launch(ctx, "k_bitonic_local"));
+    for (uint32_t k = BITONIC_BLOCK * 2; k <= n_pow2; k <<= 1) {
+        for (uint32_t j = k >> 1; j >= BITONIC_BLOCK; j >>= 1) {
+            k_bitonic_step<<<(n_pow2 + 255) / 256, 256, 0, ctx->stream>>>(keys, vals, n_pow2, j, k);
+            TRY(check_launch(ctx, "k_bitonic_step"));
+        }
+        k_bitonic_local<<<blocks, BITONIC_BLOCK / 2, 0, ctx->stream>>>(keys, vals, n_pow2, BITONIC_BLOCK / 2, k, 0);
+        TRY(check_launch(ctx, "k_bitonic_local"));
+    }
+    return SIDGPU_OK;
+}
+
+uint32_t pow2_at_least(uint64_t n) {
+    uint32_t p = BITONIC_BLOCK;
+    while (p < n) p <<= 1;
+    return p;
+}
+
+int build_histogram(sidgpu_ctx* ctx, uint32_t min_cov) {
+    TRY(sync_ctl(ctx));
+    const uint32_t n_entries = ctx->h_ctl->n_entries;
+    const uint32_t np2 = pow2_at_least(n_entries);
+    TRY(ensure(ctx, ctx->sort_keys, (size_t)np2 * 8));
+    TRY(ensure(ctx, ctx->sort_vals, (size_t)np2 * 4));
+    TRY(ensure(ctx, ctx->entry_to_unique, (size_t)std::max<uint32_t>(n_entries, 1) * 4));
+    CK(cudaMemsetAsync(ctl_field(ctx, &Control::n_selected), 0, sizeof(unsigned int), ctx->stream));
+    CK(cudaMemsetAsync(ctl_field(ctx, &Control::nd_acc), 0, 5 * sizeof(unsigned long long), ctx->stream));
+    ctx->n_unique = 0;
+    if (n_entries) {
+        k_fill_u32<<<(n_entries + 255) / 256, 256, 0, ctx->stream>>>((uint32_t*)ctx->entry_to_unique.p, n_entries, 0xFFFFFFFFu);
+        TRY(check_launch(ctx, "k_fill_u32"));
+        k_hist_select<<<(n_entries + 255) / 256, 256, 0, ctx->stream>>>(ctx->tab, n_entries, min_cov, (unsigned long long*)ctx->sort_keys.p,
+                                                                         (uint32_t*)ctx->sort_vals.p, ctl_field(ctx, &Control::n_selected));
+        TRY(check_launch(ctx, "k_hist_select"));
+        TRY(sync_ctl(ctx));
+        const uint32_t n_sel = ctx->h_ctl->n_selected;
+        if (n_sel) {
+            const uint32_t sp2 = pow2_at_least(n_sel);
+            k_fill_pad<<<(sp2 - n_sel + 255) / 256 + 1, 256, 0, ctx->stream>>>((unsigned long long*)ctx->sort_keys.p, (uint32_t*)ctx->sort_vals.p, n_sel, sp2);
+            TRY(check_launch(ctx, "k_fill_pad"));
+            TRY(sort_pairs(ctx, (unsigned long long*)ctx->sort_keys.p, (uint32_t*)ctx->sort_vals.p, sp2));
+            TRY(ensure(ctx, ctx->u_profile, (size_t)n_sel * 8));
+            TRY(ensure(ctx, ctx->u_count, (size_t)n_sel * 8));
+            TRY(ensure(ctx, ctx->u_logM, (size_t)n_sel * 8));
+            k_hist_gather<<<(n_sel + 255) / 256, 256, 0, ctx->stream>>>(ctx->tab, (const uint32_t*)ctx->sort_vals.p, n_sel,
+                                                                         (unsigned long long*)ctx->u_profile.p, (unsigned long long*)ctx->u_count.p,
+                                                                         (double*)ctx->u_logM.p, (uint32_t*)ctx->entry_to_unique.p,
+                                                                         ctl_field(ctx, &Control::nd_acc)[0]);
+            TRY(check_launch(ctx, "k_hist_gather"));
+            TRY(sync_ctl(ctx));
+        }
+        ctx->n_unique = n_sel;
+    }
+    const unsigned long long* acc = ctx->h_ctl->nd_acc;
+    if (ctx->n_unique && acc[4] != 0) {
+        for (int i = 0; i < 4; ++i) ctx->fit_nd[i] = (double)acc[i] / (double)acc[4];     // pileup.cpp:209-213
+    } else {
+        for (int i = 0; i < 4; ++i) ctx->fit_nd[i] = 0.25;                               // pileup.cpp:215
+    }
+    ctx->hist_valid = true;
+    return SIDGPU_OK;
+}
+
+int launch_objective(sidgpu_ctx* ctx, const double nd[4], double pi, double eps, double* d_out) {
+    if (!ctx->hist_valid) return ctx->fail(SIDGPU_ESTATE, "no histogram: call sidgpu_histogram or sidgpu_finish first");
+    const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((ctx->n_unique + OBJ_THREADS - 1) / OBJ_THREADS, (uint64_t)ctx->sm_count * 4));
+    TRY(ensure(ctx, ctx->partials, (size_t)ctx->sm_count * 4 * 16));
+    ObjParams p {};
+    p.u_profile = (const unsigned long long*)ctx->u_profile.p;
+    p.u_count = (const unsigned long long*)ctx->u_count.p;
+    p.u_logM = (const double*)ctx->u_logM.p;
+    p.n_unique = (uint32_t)ctx->n_unique;
+    p.k = host_lynch_consts(nd, eps);
+    p.log1m_pi = log1p(-pi);
+    p.log_pi = log(pi);
+    p.partials = (double*)ctx->partials.p;
+    p.done_blocks = ctl_field(ctx, &Control::obj_done);
+    p.out = d_out;
+    k_lynch_objective<<<grid, OBJ_THREADS, 0, ctx->stream>>>(p);
+    return check_launch(ctx, "k_lynch_objective");
+}
+
+int objective_value(sidgpu_ctx* ctx, const double nd[4], double pi, double eps, double* value) {
+    if (pi < 0 || pi > 1 || eps < 0 || eps > 1) {        // lynch.cpp:41-43
+        *value = std::numeric_limits<double>::max();
+        return SIDGPU_OK;
+    }
+    double* d_obj = ctl_field(ctx, &Control::objective);
+    TRY(launch_objective(ctx, nd, pi, eps, d_obj));
+    CK(cudaMemcpyAsync(&ctx->h_ctl->objective, d_obj, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    *value = ctx->h_ctl->objective;
+    return SIDGPU_OK;
+}
+
+int run_fit(sidgpu_ctx* ctx, const double nd[4], sidgpu_fit* out) {
+    int rc = SIDGPU_OK;
+    auto f = [&](double pi, double eps) {
+        double v = std::numeric_limits<double>::quiet_NaN();
+        if (rc == SIDGPU_OK) rc = objective_value(ctx, nd, pi, eps, &v);
+        return v;
+    };
+    const double x0[2] = {1e-3, 1e-3}, step[2] = {1e-4, 1e-4};       // lynch.cpp:8-10,20
+    NelderMeadResult r = nelder_mead_2d(f, x0, step);
+    if (rc != SIDGPU_OK) return rc;
+    out->pi = r.x[0];
+    out->eps = r.x[1];
+    out->fval = r.fval;
+    out->iterations = r.iterations;
+    out->evaluations = r.evaluations;
+    out->converged = r.converged ? 1 : 0;
+    return SIDGPU_OK;
+}
+
+int bh_adjust(sidgpu_ctx* ctx, const double* d_p, uint32_t n, double* d_adj) {
+    if (n == 0) return SIDGPU_OK;
+    const uint32_t np2 = pow2_at_least(n);
+    TRY(ensure(ctx, ctx->sort_keys, (size_t)np2 * 8));
+    TRY(ensure(ctx, ctx->sort_vals, (size_t)np2 * 4));
+    const uint32_t blocks = (n + BH_THREADS - 1) / BH_THREADS;
+    TRY(ensure(ctx, ctx->bh_c, (size_t)n * 8));
+    TRY(ensure(ctx, ctx->bh_block, (size_t)blocks * 8));
+    unsigned long long* keys = (unsigned long long*)ctx->sort_keys.p;
+    uint32_t* vals = (uint32_t*)ctx->sort_vals.p;
+    k_bh_keys<<<blocks, BH_THREADS, 0, ctx->stream>>>(d_p, n, keys, vals);
+    TRY(check_launch(ctx, "k_bh_keys"));
+    k_fill_pad<<<(np2 - n + 255) / 256 + 1, 256, 0, ctx->stream>>>(keys, vals, n, np2);
+    TRY(check_launch(ctx, "k_fill_pad"));
+    TRY(sort_pairs(ctx, keys, vals, np2));
+    k_bh_scan1<<<blocks, BH_THREADS, 0, ctx->stream>>>(d_p, vals, n, (double*)ctx->bh_c.p, (double*)ctx->bh_block.p);
+    TRY(check_launch(ctx, "k_bh_scan1"));
+    k_bh_scan2<<<1, 1, 0, ctx->stream>>>((double*)ctx->bh_block.p, blocks);
+    TRY(check_launch(ctx, "k_bh_scan2"));
+    k_bh_scatter<<<blocks, BH_THREADS, 0, ctx->stream>>>((const double*)ctx->bh_c.p, (const double*)ctx->bh_block.p, vals, n, d_adj);
+    return check_launch(ctx, "k_bh_scatter");
+}
+
+bool method_streams(const sidgpu_params& p) {
+    return (p.method == SIDGPU_METHOD_LOCAL || p.method == SIDGPU_METHOD_QUALITY) && !p.estimate_prior;
+}
+
+int quality_rows(sidgpu_ctx* ctx, uint64_t site_begin, uint64_t n) {
+    if (!ctx->last_text) return ctx->fail(SIDGPU_ESTATE, "quality needs the text of the chunk: feed before emit");
+    if (n == 0) return SIDGPU_OK;
+    QualityParams q {};
+    q.text = (const uint8_t*)ctx->last_text;
+    q.text_len = ctx->last_text_len;
+    q.line_off = (const uint64_t*)ctx->line_off.p;
+    q.site_begin = site_begin;
+    q.n_sites = n;
+    q.lut = (const double*)ctx->quality_lut.p;
+    q.prior = ctx->session_prior;
+    q.alpha = ctx->params.significance_level;
+    q.site_suffix = (char*)ctx->site_suffix.p;
+    q.error = ctl_field(ctx, &Control::error);
+    CK(cudaMemsetAsync(ctl_field(ctx, &Control::error), 0xFF, sizeof(unsigned long long), ctx->stream));
+    k_quality<<<(unsigned)((n + QUAL_THREADS - 1) / QUAL_THREADS), QUAL_THREADS, 0, ctx->stream>>>(q);
+    return check_launch(ctx, "k_quality");
+}
+
+}  // namespace
+
+// ================================================================================================
+extern "C" {
+
+const char* sidgpu_version(void) { return "sid-b200 0.1 (sm_100a)"; }
+
+const char* sidgpu_last_error(const sidgpu_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+uint64_t sidgpu_launch_count(const sidgpu_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int sidgpu_create(const sidgpu_config* cfg, sidgpu_ctx** out) {
+    if (!out) return SIDGPU_EINVAL;
+    *out = nullptr;
+    sidgpu_config c {};
+    if (cfg) c = *cfg;
+    int n_dev = 0;
+    cudaError_t e = cudaGetDeviceCount(&n_dev);
+    if (e != cudaSuccess || n_dev == 0) {
+        g_create_error = std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") +
+                         " (libsidgpu has no CPU fallback)";
+        return SIDGPU_ECUDA;
+    }
+    if (c.device < 0 || c.device >= n_dev) { g_create_error = "bad device ordinal"; return SIDGPU_EINVAL; }
+    cudaDeviceProp prop;
+    if ((e = cudaSetDevice(c.device)) != cudaSuccess || (e = cudaGetDeviceProperties(&prop, c.device)) != cudaSuccess) {
+        g_create_error = std::string("cudaSetDevice: ") + cudaGetErrorString(e);
+        return SIDGPU_ECUDA;
+    }
+    if (prop.major != 10) {
+        g_create_error = std::string("device '") + prop.name + "' is sm_" + std::to_string(prop.major * 10 + prop.minor) +
+                         "; libsidgpu carries sm_100a code only";
+        return SIDGPU_ECUDA;
+    }
+    sidgpu_ctx* ctx = new sidgpu_ctx;
+    ctx->device = c.device;
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->max_chunk = c.max_chunk_bytes ? c.max_chunk_bytes : ((size_t)256 << 20);
+    auto bail = [&](int rc) { g_create_error = ctx->err; sidgpu_destroy(ctx); return rc; };
+    if (c.stream) ctx->stream = (cudaStream_t)c.stream;
+    else {
+        if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) { ctx->err = cudaGetErrorString(e); return bail(SIDGPU_ECUDA); }
+        ctx->own_stream = true;
+    }
+    if (cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking) != cudaSuccess) { ctx->err = "stream creation failed"; return bail(SIDGPU_ECUDA); }
+    if (cudaMalloc((void**)&ctx->d_ctl, sizeof(Control)) != cudaSuccess || cudaMallocHost((void**)&ctx->h_ctl, sizeof(Control)) != cudaSuccess) {
+        ctx->err = "control block allocation failed";
+        return bail(SIDGPU_ENOMEM);
+    }
+    cudaMemsetAsync(ctx->d_ctl, 0, sizeof(Control), ctx->stream);
+    ctx->table_log2 = c.table_log2 > 0 ? c.table_log2 : 20;
+    int rc = alloc_table(ctx, ctx->table_log2, ctx->tab);
+    if (rc != SIDGPU_OK) return bail(rc);
+    // chromosome-name dictionary: 2^20 slots, 64 MiB of names
+    const uint32_t dict_slots = 1u << 20, pool_cap = 64u << 20;
+    if (cudaMalloc((void**)&ctx->names.slots, (size_t)dict_slots * 8) != cudaSuccess || cudaMalloc((void**)&ctx->names.pool, pool_cap) != cudaSuccess) {
+        ctx->err = "name dictionary allocation failed";
+        return bail(SIDGPU_ENOMEM);
+    }
+    cudaMemsetAsync(ctx->names.slots, 0, (size_t)dict_slots * 8, ctx->stream);
+    cudaMemsetAsync(ctx->names.pool, 0, 16, ctx->stream);
+    ctx->names.mask = dict_slots - 1;
+    ctx->names.pool_cap = pool_cap;
+    ctx->names.cursor = ctl_field(ctx, &Control::name_cursor);
+    ctx->names.overflow = ctl_field(ctx, &Control::name_overflow);
+    const unsigned int four = 4;
+    cudaMemcpyAsync(ctx->names.cursor, &four, sizeof four, cudaMemcpyHostToDevice, ctx->stream);
+    // quality lookup tables: log(1-e), log(e), log(1-2e/3), log(2e/3) with e = 10^(-q/10) (call.cpp:330-341)
+    {
+        std::vector<double> lut(4 * 256);
+        for (int q = 0; q < 256; ++q) {
+            const double error = pow(10., q / -10.);
+            lut[q] = log(1 - error);
+            lut[256 + q] = log(error);
+            lut[512 + q] = log(1 - 2. / 3. * error);
+            lut[768 + q] = log(2. / 3. * error);
+        }
+        rc = ensure(ctx, ctx->quality_lut, lut.size() * 8);
+        if (rc != SIDGPU_OK) return bail(rc);
+        cudaMemcpyAsync(ctx->quality_lut.p, lut.data(), lut.size() * 8, cudaMemcpyHostToDevice, ctx->stream);
+        cudaStreamSynchronize(ctx->stream);
+    }
+    if ((e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) { ctx->err = cudaGetErrorString(e); return bail(SIDGPU_ECUDA); }
+    if (c.max_sites) {
+        rc = ensure_sites(ctx, c.max_sites, false);
+        if (rc != SIDGPU_OK) return bail(rc);
+    }
+    *out = ctx;
+    return SIDGPU_OK;
+}
+
+void sidgpu_destroy(sidgpu_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    resolve_profile(ctx);
+    for (cudaEvent_t e : ctx->free_events) cudaEventDestroy(e);
+    free_table(ctx->tab);
+    cudaFree(ctx->names.slots);
+    cudaFree(ctx->names.pool);
+    for (DevBuf* b : {&ctx->tile_status, &ctx->csv_status, &ctx->pos, &ctx->slot, &ctx->name_ref, &ctx->profile, &ctx->line_off,
+                      &ctx->site_suffix, &ctx->sort_keys, &ctx->sort_vals, &ctx->u_profile, &ctx->u_count, &ctx->u_logM,
+                      &ctx->entry_to_unique, &ctx->p_hom, &ctx->p_het, &ctx->adj_hom, &ctx->adj_het, &ctx->bh_c, &ctx->bh_block,
+                      &ctx->partials, &ctx->quality_lut})
+        release(*b);
+    if (ctx->d_ctl) cudaFree(ctx->d_ctl);
+    if (ctx->h_ctl) cudaFreeHost(ctx->h_ctl);
+    if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
+    if (ctx->copy_out) cudaStreamDestroy(ctx->copy_out);
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int sidgpu_profile(sidgpu_ctx* ctx, int enable) {
+    if (!ctx) return SIDGPU_EINVAL;
+    resolve_profile(ctx);
+    ctx->profiling = enable != 0;
+    for (int i = 0; i < 4; ++i) { ctx->kernel_ms[i] = 0; ctx->kernel_launches[i] = 0; }
+    return SIDGPU_OK;
+}
+
+int sidgpu_kernel_times(sidgpu_ctx* ctx, double ms[3], uint64_t launches[3]) {
+    if (!ctx) return SIDGPU_EINVAL;
+    CK(cudaStreamSynchronize(ctx->stream));
+    resolve_profile(ctx);
+    for (int i = 0; i < 3; ++i) {
+        if (ms) ms[i] = ctx->kernel_ms[i];
+        if (launches) launches[i] = ctx->kernel_launches[i];
+    }
+    return SIDGPU_OK;
+}
+
+int sidgpu_synchronize(sidgpu_ctx* ctx) {
+    if (!ctx) return SIDGPU_EINVAL;
+    CK(cudaStreamSynchronize(ctx->stream));
+    return SIDGPU_OK;
+}
+
+int sidgpu_malloc(sidgpu_ctx* ctx, size_t bytes, void** d_ptr) {
+    if (!ctx || !d_ptr) return SIDGPU_EINVAL;
+    cudaError_t e = cudaMalloc(d_ptr, bytes ? bytes : 16);
+    if (e != cudaSuccess) return ctx->fail(SIDGPU_ENOMEM, "cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e));
+    return SIDGPU_OK;
+}
+int sidgpu_free(sidgpu_ctx* ctx, void* d_ptr) {
+    if (!ctx) return SIDGPU_EINVAL;
+    CK(cudaFree(d_ptr));
+    return SIDGPU_OK;
+}
+int sidgpu_malloc_host(sidgpu_ctx* ctx, size_t bytes, void** h_ptr) {
+    if (!ctx || !h_ptr) return SIDGPU_EINVAL;
+    cudaError_t e = cudaMallocHost(h_ptr, bytes ? bytes : 16);
+    if (e != cudaSuccess) return ctx->fail(SIDGPU_ENOMEM, "cudaMallocHost(%zu): %s", bytes, cudaGetErrorString(e));
+    return SIDGPU_OK;
+}
+int sidgpu_free_host(sidgpu_ctx* ctx, void* h_ptr) {
+    if (!ctx) return SIDGPU_EINVAL;
+    CK(cudaFreeHost(h_ptr));
+    return SIDGPU_OK;
+}
+int sidgpu_memcpy_h2d(sidgpu_ctx* ctx, void* d_dst, const void* h_src, size_t bytes) {
+    if (!ctx) return SIDGPU_EINVAL;
+    CK(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return SIDGPU_OK;
+}
+int sidgpu_memcpy_d2h(sidgpu_ctx* ctx, void* h_dst, const void* d_src, size_t bytes) {
+    if (!ctx) return SIDGPU_EINVAL;
+    CK(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return SIDGPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------- K1
+int sidgpu_tokenize(sidgpu_ctx* ctx, const char* d_text, size_t text_len, size_t range_begin, size_t range_end,
+                    int want_qual, sidgpu_sites_view* out) {
+    if (!ctx || !out) return SIDGPU_EINVAL;
+    CK(cudaSetDevice(ctx->device));
+    ctx->phase = PHASE_IDLE;
+    ctx->want_profile = true;
+    ctx->want_line_off = want_qual != 0;
+    TRY(reset_table(ctx));
+    uint64_t n = 0;
+    TRY(run_tokenizer(ctx, d_text, text_len, range_begin, range_end, want_qual != 0, true, 0, false, &n));
+    ctx->n_sites_total = n;
+    ctx->chunk_begin = 0;
+    ctx->chunk_sites = n;
+    memset(out, 0, sizeof *out);
+    out->n_sites = n;
+    out->d_profile = (const uint64_t*)ctx->profile.p;
+    out->d_pos = (const int32_t*)ctx->pos.p;
+    out->d_slot = (const uint32_t*)ctx->slot.p;
+    out->d_line_off = want_qual ? (const uint64_t*)ctx->line_off.p : nullptr;
+    out->d_name_ref = (const uint32_t*)ctx->name_ref.p;
+    out->d_names = ctx->names.pool;
+    out->names_bytes = ctx->h_ctl->name_cursor;
+    return SIDGPU_OK;
+}
+
+// ------------------------------------------------------------------------------------- sessions
+int sidgpu_begin(sidgpu_ctx* ctx, const sidgpu_params* params) {
+    if (!ctx || !params) return SIDGPU_EINVAL;
+    if (params->method < 0 || params->method > 3) return ctx->fail(SIDGPU_EINVAL, "unknown method %d", params->method);
+    CK(cudaSetDevice(ctx->device));
+    ctx->params = *params;
+    ctx->streaming = method_streams(*params);
+    ctx->counting = !ctx->streaming;
+    ctx->want_profile = false;
+    ctx->want_line_off = params->method == SIDGPU_METHOD_QUALITY;
+    ctx->want_site_suffix = params->method == SIDGPU_METHOD_QUALITY;
+    ctx->session_prior = params->prior;
+    ctx->fit_done = false;
+    ctx->fit = sidgpu_fit {};
+    ctx->n_sites_total = 0;
+    ctx->chunk_begin = ctx->chunk_sites = 0;
+    ctx->last_text = nullptr;
+    TRY(reset_table(ctx));
+    ctx->phase = PHASE_FEED;
+    return SIDGPU_OK;
+}
+
+int sidgpu_feed(sidgpu_ctx* ctx, const char* d_text, size_t text_len, size_t range_begin, size_t range_end, uint64_t* n_sites_out) {
+    if (!ctx) return SIDGPU_EINVAL;
+    const bool second_pass = ctx->phase == PHASE_FINISHED && ctx->params.method == SIDGPU_METHOD_QUALITY;
+    if (ctx->phase != PHASE_FEED && !second_pass) return ctx->fail(SIDGPU_ESTATE, "sidgpu_feed outside a session");
+    CK(cudaSetDevice(ctx->device));
+    const bool is_quality = ctx->params.method == SIDGPU_METHOD_QUALITY;
+    const bool chunk_local = ctx->streaming || second_pass || (is_quality && ctx->phase == PHASE_FEED);
+    // quality with -R: the first pass only needs the histogram; sites are re-fed after the fit
+    const uint64_t base = chunk_local ? 0 : ctx->n_sites_total;
+    uint64_t n = 0;
+    const bool use_table = !(is_quality && (ctx->streaming || second_pass));
+    TRY(run_tokenizer(ctx, d_text, text_len, range_begin, range_end, is_quality, use_table, base, !chunk_local, &n));
+    ctx->last_text = d_text;
+    ctx->last_text_len = text_len;
+    ctx->chunk_begin = base;
+    ctx->chunk_sites = n;
+    ctx->n_sites_total = chunk_local ? n : base + n;
+    if (ctx->counting && ctx->phase == PHASE_FEED && n) {
+        k_count_slots<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>((const uint32_t*)ctx->slot.p, base, n, ctx->tab.counts);
+        TRY(check_launch(ctx, "k_count_slots"));
+        ctx->hist_valid = false;
+    }
+    if (ctx->streaming && ctx->params.method == SIDGPU_METHOD_LOCAL) {
+        const uint32_t n_entries = ctx->h_ctl->n_entries;
+        TRY(classify_entries(ctx, ctx->classified, n_entries));
+        ctx->classified = n_entries;
+    }
+    if (n_sites_out) *n_sites_out = n;
+    return SIDGPU_OK;
+}
+
+int sidgpu_finish(sidgpu_ctx* ctx) {
+    if (!ctx) return SIDGPU_EINVAL;
+    if (ctx->phase != PHASE_FEED) return ctx->fail(SIDGPU_ESTATE, "sidgpu_finish outside a session");
+    CK(cudaSetDevice(ctx->device));
+    if (!ctx->streaming) {
+        TRY(build_histogram(ctx, 4));                                   // call.cpp:66-70,149-153,224-229,296-301
+        if (ctx->params.fit_given) {
+            ctx->fit.pi = ctx->params.fit_pi;
+            ctx->fit.eps = ctx->params.fit_eps;
+            ctx->fit.converged = 1;
+            for (int i = 0; i < 4; ++i) ctx->fit_nd[i] = ctx->params.fit_nd[i];
+        } else {
+            TRY(run_fit(ctx, ctx->fit_nd, &ctx->fit));
+        }
+        ctx->fit_done = true;
+        TRY(sync_ctl(ctx));
+        const uint32_t n_entries = ctx->h_ctl->n_entries;
+        const int m = ctx->params.method;
+        if (m == SIDGPU_METHOD_LOCAL || m == SIDGPU_METHOD_QUALITY) {
+            ctx->session_prior = ctx->fit.pi;                           // call.cpp:233,305
+        }
+        if (m == SIDGPU_METHOD_LIKELIHOOD_RATIO) {
+            const uint32_t nu = (uint32_t)ctx->n_unique;
+            TRY(ensure(ctx, ctx->p_hom, (size_t)std::max(nu, 1u) * 8));
+            TRY(ensure(ctx, ctx->p_het, (size_t)std::max(nu, 1u) * 8));
+            TRY(ensure(ctx, ctx->adj_hom, (size_t)std::max(nu, 1u) * 8));
+            TRY(ensure(ctx, ctx->adj_het, (size_t)std::max(nu, 1u) * 8));
+            if (nu) {
+                k_lr_pvalues<<<(nu + 255) / 256, 256, 0, ctx->stream>>>((const unsigned long long*)ctx->u_profile.p, nu,
+                                                                        host_lynch_consts(ctx->fit_nd, ctx->fit.eps),
+                                                                        ctx->params.estimate_prior, ctx->fit.pi,
+                                                                        (double*)ctx->p_hom.p, (double*)ctx->p_het.p);
+                TRY(check_launch(ctx, "k_lr_pvalues"));
+                TRY(bh_adjust(ctx, (const double*)ctx->p_hom.p, nu, (double*)ctx->adj_hom.p));
+                TRY(bh_adjust(ctx, (const double*)ctx->p_het.p, nu, (double*)ctx->adj_het.p));
+            }
+        }
+        if (m != SIDGPU_METHOD_QUALITY) {
+            TRY(classify_entries(ctx, 0, n_entries));
+            ctx->classified = n_entries;
+        }
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->phase = PHASE_FINISHED;
+    return SIDGPU_OK;
+}
+
+int sidgpu_emit_csv(sidgpu_ctx* ctx, uint64_t site_begin, uint64_t n_sites, char* d_out, size_t out_cap, uint64_t* bytes_out, uint64_t* rows_out) {
+    if (!ctx) return SIDGPU_EINVAL;
+    if (ctx->phase == PHASE_IDLE) return ctx->fail(SIDGPU_ESTATE, "sidgpu_emit_csv outside a session");
+    if (!ctx->streaming && ctx->phase != PHASE_FINISHED) return ctx->fail(SIDGPU_ESTATE, "this method needs sidgpu_finish before rows can be emitted");
+    if (site_begin + n_sites > ctx->n_sites_total) return ctx->fail(SIDGPU_EINVAL, "sites [%llu,+%llu) not in the store (%llu)", (unsigned long long)site_begin, (unsigned long long)n_sites, (unsigned long long)ctx->n_sites_total);
+    CK(cudaSetDevice(ctx->device));
+    if (bytes_out) *bytes_out = 0;
+    if (rows_out) *rows_out = 0;
+    if (n_sites == 0) return SIDGPU_OK;
+    const bool is_quality = ctx->params.method == SIDGPU_METHOD_QUALITY;
+    if (is_quality) TRY(quality_rows(ctx, site_begin, n_sites));
+    const uint32_t n_tiles = (uint32_t)((n_sites + CSV_TILE - 1) / CSV_TILE);
+    TRY(ensure(ctx, ctx->csv_status, (size_t)n_tiles * 8));
+    CK(cudaMemsetAsync(ctx->csv_status.p, 0, (size_t)n_tiles * 8, ctx->stream));
+    CK(cudaMemsetAsync(ctl_field(ctx, &Control::csv_ticket), 0, sizeof(unsigned int), ctx->stream));
+    CK(cudaMemsetAsync(ctl_field(ctx, &Control::csv_bytes), 0, 2 * sizeof(unsigned long long), ctx->stream));
+    CsvParams p {};
+    p.site_begin = site_begin;
+    p.n_sites = n_sites;
+    p.pos = (const int32_t*)ctx->pos.p;
+    p.slot = (const uint32_t*)ctx->slot.p;
+    p.name_ref = (const uint32_t*)ctx->name_ref.p;
+    p.site_suffix = is_quality ? (const char*)ctx->site_suffix.p : nullptr;
+    p.table = ctx->tab;
+    p.pool = ctx->names.pool;
+    p.out = d_out;
+    p.out_cap = out_cap;
+    p.ticket = ctl_field(ctx, &Control::csv_ticket);
+    p.status = (unsigned long long*)ctx->csv_status.p;
+    p.bytes_out = ctl_field(ctx, &Control::csv_bytes);
+    p.rows_out = ctl_field(ctx, &Control::csv_rows);
+    p.n_tiles = n_tiles;
+    const unsigned grid = (unsigned)std::min<uint64_t>(n_tiles, (uint64_t)ctx->sm_count * 8);
+    {
+        ProfScope prof(ctx, PROF_CSV);
+        k_csv<<<grid, CSV_THREADS, 0, ctx->stream>>>(p);
+    }
+    TRY(check_launch(ctx, "k_csv"));
+    TRY(sync_ctl(ctx));
+    if (is_quality && ctx->h_ctl->error != ~0ull) {
+        return ctx->fail(SIDGPU_EQUAL_SHORT, "%s (line starting at byte %llu)", status_text((int)(ctx->h_ctl->error & 7)), ctx->h_ctl->error >> 3);
+    }
+    if (bytes_out) *bytes_out = ctx->h_ctl->csv_bytes;
+    if (rows_out) *rows_out = ctx->h_ctl->csv_rows;
+    if (ctx->h_ctl->csv_bytes > out_cap) return ctx->fail(SIDGPU_ECAPACITY, "CSV needs %llu bytes, buffer has %zu", ctx->h_ctl->csv_bytes, out_cap);
+    return SIDGPU_OK;
+}
+
+int sidgpu_emit_records(sidgpu_ctx* ctx, uint64_t site_begin, uint64_t n_sites, uint8_t* d_label, char* d_gt, double* d_hom, double* d_het) {
+    if (!ctx) return SIDGPU_EINVAL;
+    if (ctx->phase == PHASE_IDLE) return ctx->fail(SIDGPU_ESTATE, "sidgpu_emit_records outside a session");
+    if (!ctx->streaming && ctx->phase != PHASE_FINISHED) return ctx->fail(SIDGPU_ESTATE, "this method needs sidgpu_finish first");
+    if (ctx->params.method == SIDGPU_METHOD_QUALITY) return ctx->fail(SIDGPU_EINVAL, "quality results are per site: use sidgpu_emit_csv");
+    if (site_begin + n_sites > ctx->n_sites_total) return ctx->fail(SIDGPU_EINVAL, "site range not in the store");
+    if (n_sites == 0) return SIDGPU_OK;
+    CK(cudaSetDevice(ctx->device));
+    RecordParams p {site_begin, n_sites, (const uint32_t*)ctx->slot.p, ctx->tab, d_label, d_gt, d_hom, d_het};
+    k_records<<<(unsigned)((n_sites + 255) / 256), 256, 0, ctx->stream>>>(p);
+    TRY(check_launch(ctx, "k_records"));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return SIDGPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------- K3/K4
+int sidgpu_histogram(sidgpu_ctx* ctx, uint32_t min_coverage, sidgpu_unique_view* out) {
+    if (!ctx || !out) return SIDGPU_EINVAL;
+    CK(cudaSetDevice(ctx->device));
+    TRY(build_histogram(ctx, min_coverage));
+    out->n_unique = ctx->n_unique;
+    out->d_profile = (const uint64_t*)ctx->u_profile.p;
+    out->d_count = (const uint64_t*)ctx->u_count.p;
+    for (int i = 0; i < 4; ++i) out->nd[i] = ctx->fit_nd[i];
+    return SIDGPU_OK;
+}
+
+int sidgpu_lynch_objective_partial(sidgpu_ctx* ctx, const double nd[4], double pi, double eps, double* d_out) {
+    if (!ctx || !nd || !d_out) return SIDGPU_EINVAL;
+    CK(cudaSetDevice(ctx->device));
+    if (pi < 0 || pi > 1 || eps < 0 || eps > 1) {
+        const double big = std::numeric_limits<double>::max();
+        CK(cudaMemcpyAsync(d_out, &big, sizeof big, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        return SIDGPU_OK;
+    }
+    return launch_objective(ctx, nd, pi, eps, d_out);
+}
+
+int sidgpu_lynch_objective(sidgpu_ctx* ctx, const double nd[4], double pi, double eps, double* value) {
+    if (!ctx || !nd || !value) return SIDGPU_EINVAL;
+    CK(cudaSetDevice(ctx->device));
+    return objective_value(ctx, nd, pi, eps, value);
+}
+
+int sidgpu_lynch_fit(sidgpu_ctx* ctx, const double nd[4], sidgpu_fit* out) {
+    if (!ctx || !nd || !out) return SIDGPU_EINVAL;
+    CK(cudaSetDevice(ctx->device));
+    return run_fit(ctx, nd, out);
+}
+
+int sidgpu_session_fit(sidgpu_ctx* ctx, sidgpu_fit* out, double nd[4], uint64_t* n_unique) {
+    if (!ctx) return SIDGPU_EINVAL;
+    if (!ctx->fit_done) return ctx->fail(SIDGPU_ESTATE, "no fit in this session");
+    if (out) *out = ctx->fit;
+    if (nd) for (int i = 0; i < 4; ++i) nd[i] = ctx->fit_nd[i];
+    if (n_unique) *n_unique = ctx->n_unique;
+    return SIDGPU_OK;
+}
+
+int sidgpu_bh_adjust(sidgpu_ctx* ctx, const double* d_p, uint64_t n, double* d_adjusted) {
+    if (!ctx || (n && (!d_p || !d_adjusted))) return SIDGPU_EINVAL;
+    if (n > 0x7FFFFFFFull) return ctx->fail(SIDGPU_EINVAL, "too many p-values");
+    CK(cudaSetDevice(ctx->device));
+    TRY(bh_adjust(ctx, d_p, (uint32_t)n, d_adjusted));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return SIDGPU_OK;
+}
+
+int sidgpu_format_g(sidgpu_ctx* ctx, const double* d_values, uint64_t n, char* d_out16) {
+    if (!ctx) return SIDGPU_EINVAL;
+    if (n == 0) return SIDGPU_OK;
+    CK(cudaSetDevice(ctx->device));
+    k_format_g<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(d_values, n, d_out16);
+    TRY(check_launch(ctx, "k_format_g"));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return SIDGPU_OK;
+}
+
+}  // extern "C"
+
+#include "host_path.inl"

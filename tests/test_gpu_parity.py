@@ -1,0 +1,192 @@
+"""GPU: the CUDA path, called through the C ABI, against the oracle and the reference's own
+outputs (tests/golden).  Bit-exact for profiles, positions, names, labels and genotypes; hom_conf /
+het_conf within REL_TOL = 1e-9 relative on the double (and equal printed text up to one unit of
+the sixth digit)."""
+import ctypes
+import json
+import os
+
+import numpy as np
+import pytest
+
+import oracle_py as op
+from test_oracle import GOLDEN, MANIFEST, flags_to_kwargs, read
+
+pytestmark = pytest.mark.gpu
+
+
+def params_from_flags(flags, fit=None):
+    import sid_b200
+    kw = flags_to_kwargs(flags)
+    return sid_b200.Context.make_params(kw["method"], kw.get("estimate_prior", False), kw.get("prior", -1.0),
+                                        kw.get("error_threshold", 0.1), kw.get("alpha", 0.05), fit=fit)
+
+
+@pytest.mark.parametrize("name", ["edge.plp", "depth30.plp", "depth500.plp", "depth5.plp", "depth30_two_chroms.plp", "quality30.plp"])
+def test_tokenizer_bit_exact(native, gpu_ctx, name):
+    text = read(name)
+    want = op.oracle_call(text, "local")
+    d = gpu_ctx.upload_text(text)
+    try:
+        got = gpu_ctx.tokenize(d, len(text))
+    finally:
+        d.free()
+    assert got["n_sites"] == want["n_sites"]
+    assert np.array_equal(got["profile"], want["profiles"])
+    assert np.array_equal(got["pos"], want["pos"])
+    assert got["chrom"] == want["chrom"]
+
+
+def test_tokenizer_shard_ranges_concatenate(native, gpu_ctx):
+    """Byte-range sharding: any split of the text into ranges yields the same sites."""
+    text = read("depth30.plp")
+    want = op.oracle_call(text, "local")
+    d = gpu_ctx.upload_text(text)
+    try:
+        for cuts in ([0, len(text)], [0, 1, len(text)], [0, 100000, 100001, 200003, len(text)], [0, len(text) // 3, 2 * len(text) // 3, len(text)],
+                     [0, 77, 78, 79, 80, 81, 5000, len(text) - 1, len(text)]):
+            prof, pos = [], []
+            for a, b in zip(cuts[:-1], cuts[1:]):
+                g = gpu_ctx.tokenize(d, len(text), a, b)
+                prof.append(g["profile"])
+                pos.append(g["pos"])
+            assert np.array_equal(np.concatenate(prof), want["profiles"]), cuts
+            assert np.array_equal(np.concatenate(pos), want["pos"]), cuts
+    finally:
+        d.free()
+
+
+@pytest.mark.parametrize("case", MANIFEST["cases"], ids=lambda c: c["csv"])
+def test_csv_matches_reference(native, gpu_ctx, case):
+    """`sid -m ...` end to end through sidgpu_call_host against what the reference printed.
+    Methods with a Lynch fit get the reference's (pi, eps) injected -- the optimiser is checked
+    separately (test_lynch_fit) because real GSL is unpinned."""
+    import sid_b200
+    text = read(case["input"])
+    kw = flags_to_kwargs(case["flags"])
+    fit = None
+    if "heterozygosity" in case or kw.get("estimate_prior"):
+        o = op.oracle_call(text, **kw)
+        prof = o["profiles"]
+        cov = op.unpack_profiles(prof).astype(np.int64).sum(axis=1)
+        u, c = op.oracle_unique(prof[cov >= 4])
+        fit = (o["pi"], o["eps"], op.oracle_nd(u, c))
+    rows, n_sites, n_rows = gpu_ctx.call_host(text, params_from_flags(case["flags"], fit))
+    want = read(case["csv"])
+    n, diffs = op.compare_csv(sid_b200.CSV_HEADER + rows, want)
+    assert n == n_rows
+    assert diffs <= max(2, n // 1000), "too many last-digit differences: %d of %d" % (diffs, n)
+
+
+@pytest.mark.parametrize("case", MANIFEST["malformed"], ids=lambda c: c["input"])
+def test_malformed_raises(native, gpu_ctx, case):
+    import sid_b200
+    with pytest.raises(sid_b200.MalformedPileup) as e:
+        gpu_ctx.call_host(read(case["input"]), params_from_flags(case["flags"]))
+    assert case["what"].split(" or ")[-1].lower() in str(e.value).lower()
+
+
+def test_empty_and_blank_inputs(native, gpu_ctx):
+    import sid_b200
+    for text in (b"", b"\n", b"\n\n\n"):
+        rows, n_sites, n_rows = gpu_ctx.call_host(text, sid_b200.Context.make_params("local"))
+        assert rows == b"" and n_sites == 0 and n_rows == 0
+
+
+def test_records_match_oracle(native, gpu_ctx):
+    import sid_b200
+    text = read("depth30.plp")
+    want = op.oracle_call(text, "local")
+    d = gpu_ctx.upload_text(text)
+    try:
+        gpu_ctx.begin(sid_b200.Context.make_params("local"))
+        n = gpu_ctx.feed(d, len(text))
+        lab, gt, hom, het = gpu_ctx.emit_records(0, n)
+    finally:
+        d.free()
+    assert n == want["n"]
+    assert np.array_equal(lab, want["label"]) and np.array_equal(gt, want["gt"])
+    for a, b in ((hom, want["hom"]), (het, want["het"])):
+        for x, y in zip(a, b):
+            assert op.conf_close(x, y)
+
+
+def test_histogram_and_objective(native, gpu_ctx):
+    import sid_b200
+    text = read("depth30.plp")
+    o = op.oracle_call(text, "bayes")
+    prof = o["profiles"]
+    d = gpu_ctx.upload_text(text)
+    try:
+        gpu_ctx.begin(sid_b200.Context.make_params("bayes"))
+        gpu_ctx.feed(d, len(text))
+        for min_cov in (0, 4):
+            cov = op.unpack_profiles(prof).astype(np.int64).sum(axis=1)
+            wu, wc = op.oracle_unique(prof[cov >= min_cov])
+            gu, gc, nd = gpu_ctx.histogram(min_cov)
+            assert np.array_equal(gu, wu) and np.array_equal(gc, wc)          # same order as the reference: lexicographic
+            assert np.allclose(nd, op.oracle_nd(wu, wc), rtol=0, atol=1e-15)
+        for pi, eps in [(1e-3, 1e-3), (1.1e-3, 1e-3), (o["pi"], o["eps"]), (0.5, 0.5), (0.0, 0.0), (1.0, 1.0)]:
+            want = op.oracle_objective(wu, wc, nd, pi, eps)
+            got = gpu_ctx.lynch_objective(nd, pi, eps)
+            assert abs(got - want) <= 1e-11 * abs(want), (pi, eps, got, want)
+        assert gpu_ctx.lynch_objective(nd, -0.5, 0.1) == 1.7976931348623157e308
+    finally:
+        d.free()
+
+
+@pytest.mark.parametrize("case", [c for c in MANIFEST["cases"] if "heterozygosity" in c and c["flags"][1] == "bayes"], ids=lambda c: c["csv"])
+def test_lynch_fit(native, gpu_ctx, case):
+    """Device objective + host Nelder-Mead against the fit the reference logged (its own NM runs
+    on the GSL stand-in, so this pins trajectory robustness, not GSL): pi and eps within 1e-4
+    relative (the stop rule is simplex size < 1e-5)."""
+    import sid_b200
+    text = read(case["input"])
+    gpu_ctx.call_host(text, sid_b200.Context.make_params("bayes"))
+    fit = gpu_ctx.session_fit()
+    assert fit["converged"]
+    assert fit["n_unique"] == case["unique_profiles"]
+    assert abs(fit["pi"] - case["heterozygosity"]) <= 1e-4 * case["heterozygosity"]
+    assert abs(fit["eps"] - case["error"]) <= 1e-4 * case["error"]
+    assert fit["iterations"] == case["iterations"]
+
+
+def test_bh_adjust(native, gpu_ctx):
+    rng = np.random.default_rng(3)
+    for n in (1, 2, 7, 255, 256, 257, 5000, 70001):
+        p = rng.random(n) ** 3
+        p[rng.integers(0, n, size=max(1, n // 10))] = 1.0          # ties, as one of (p1, p2) is always exactly 1
+        p[rng.integers(0, n, size=max(1, n // 20))] = 0.0
+        got = gpu_ctx.bh_adjust(p)
+        want = op.oracle_bh(p)
+        assert np.array_equal(got, want), n
+
+
+def test_format_g_on_device(native, gpu_ctx):
+    rng = np.random.default_rng(4)
+    v = np.concatenate([rng.random(20000), np.exp(-rng.random(20000) * 745), [0.0, 1.0, 0.5, 2.0 ** -9, 5e-324, 1e-5, 9.999995e-5, 0.9999995],
+                        np.arange(1, 400, 2) * 2.0 ** -20])
+    got = gpu_ctx.format_g(v)
+    assert got == ["%g" % x for x in v]
+
+
+def test_full_size_properties(native, gpu_ctx):
+    """Size-independent properties at a size the oracle would need minutes for (4 M sites):
+    one row per site, rows in position order, streamed == whole, het fraction plausible."""
+    import sid_b200
+    from sid_b200 import synth
+    n = 4_000_000
+    text = synth.generate(n, seed=21, **synth.CONFIGS["depth30"])
+    rows, n_sites, n_rows = gpu_ctx.call_host(text, sid_b200.Context.make_params("local"))
+    assert n_sites == n and n_rows == n
+    lines = rows.split(b"\n")
+    assert len(lines) == n + 1 and lines[-1] == b""
+    assert lines[0].startswith(b"chr1,1,") and lines[-2].startswith(b"chr1,%d," % n)
+    het = sum(1 for l in lines[:200000] if b",het," in l)
+    assert 100 < het < 400
+    # the oracle on a slice in the middle of the stream
+    a = np.frombuffer(text, dtype=np.uint8)
+    nl = np.flatnonzero(a == 10)
+    lo, hi = int(nl[1_999_999]) + 1, int(nl[2_019_999]) + 1
+    want = op.oracle_call(a[lo:hi].tobytes(), "local")["csv"].split(b"\n")[1:-1]
+    assert lines[2_000_000:2_020_000] == want

@@ -1,0 +1,155 @@
+"""CPU: the arithmetic the kernels run (sid_b200/csrc/*.cuh compiled for the host by
+tests/hostcheck) against the oracle: tokenizer state machine, %g formatter, per-profile calls,
+Lynch objective.  The same functions are compiled into the sm_100a kernels."""
+import ctypes
+import json
+import math
+import os
+import random
+import struct
+
+import numpy as np
+import pytest
+
+import oracle_py as op
+from test_oracle import GOLDEN, MANIFEST, flags_to_kwargs, read
+
+
+def line_starts(text):
+    a = np.frombuffer(text, dtype=np.uint8)
+    nl = np.flatnonzero(a == 10)
+    starts = np.concatenate(([0], nl + 1))
+    starts = starts[starts < len(a)]
+    return [int(s) for s in starts if a[s] != 10]
+
+
+@pytest.mark.parametrize("name", ["edge.plp", "depth30.plp", "depth500.plp", "depth5.plp", "depth30_two_chroms.plp"])
+def test_tokenizer_matches_oracle(native, name):
+    hc = op.hostcheck()
+    text = read(name)
+    want = op.oracle_call(text, "local")
+    hl = op.HcLine()
+    starts = line_starts(text)
+    assert len(starts) == want["n_sites"]
+    for k, s in enumerate(starts):
+        hc.hc_parse_line(text, len(text), s, 0, ctypes.byref(hl))
+        assert hl.status == 0
+        assert hl.profile == int(want["profiles"][k]), (k, text[s:s + 60])
+        assert hl.pos == int(want["pos"][k])
+        assert text[s + hl.chrom_off:s + hl.chrom_off + hl.chrom_len].decode("latin-1") == want["chrom"][k]
+
+
+@pytest.mark.parametrize("case", MANIFEST["malformed"], ids=lambda c: c["input"])
+def test_tokenizer_rejects_malformed(native, case):
+    hc = op.hostcheck()
+    text = read(case["input"])
+    want_qual = 1 if "quality" in case["flags"] else 0
+    statuses = []
+    hl = op.HcLine()
+    for s in line_starts(text):
+        hc.hc_parse_line(text, len(text), s, want_qual, ctypes.byref(hl))
+        statuses.append(hl.status)
+    assert max(statuses) == (2 if "missing mapping" in case["what"] else 1)
+
+
+def test_format_g_matches_printf(native):
+    hc = op.hostcheck()
+    buf = ctypes.create_string_buffer(32)
+    rnd = random.Random(5)
+    vals = [0.0, 1.0, 0.5, 0.25, 2.0 ** -9, 0.1, 0.05, 1e-5, 1e-4, 9.999995e-5, 9.9999949e-5, 0.9999995, 0.99999949,
+            5e-324, 2.2250738585072014e-308, 1.5, 123456.5, 999999.5, 100000.0, 12345.65, float("nan"), float("inf"), -0.0,
+            1 / 3, 2 / 3, 1e-300, 4.13196e-06, 0.000196638]
+    for i in range(60000):
+        k = i % 3
+        if k == 0:
+            vals.append(rnd.random())
+        elif k == 1:
+            vals.append(math.exp(-rnd.random() * 745))
+        else:
+            vals.append(struct.unpack("<d", struct.pack("<Q", rnd.getrandbits(62) % (0x3FF0000000000000 + 1)))[0])
+    for m in range(1, 40):                  # exact decimal ties: k * 2^-m
+        for k in range(1, 400, 2):
+            vals.append(k * 2.0 ** -m)
+    for x in vals:
+        hc.hc_fmt_g6(x, buf)
+        assert buf.value.decode() == "%g" % x, repr(x)
+
+
+def test_format_int(native):
+    hc = op.hostcheck()
+    buf = ctypes.create_string_buffer(16)
+    for v in [0, 1, -1, 9, 10, 99, 100, 2147483647, -2147483648, 1337, -5]:
+        hc.hc_fmt_i32(v, buf)
+        assert buf.value.decode() == str(v)
+
+
+@pytest.mark.parametrize("case", [c for c in MANIFEST["cases"] if "quality" not in c["flags"]], ids=lambda c: c["csv"])
+def test_calls_match_oracle(native, case):
+    """Per-profile call arithmetic (double, log space) against the oracle (x87 long double), with
+    the oracle's fitted (pi, eps) injected where the method has a fit."""
+    hc = op.hostcheck()
+    kw = flags_to_kwargs(case["flags"])
+    text = read(case["input"])
+    want = op.oracle_call(text, **kw)
+    method = kw["method"]
+    rows = op.parse_rows(want["csv"])
+    # per-site profiles of the emitted rows
+    all_prof = want["profiles"]
+    if method == "local":
+        prof = all_prof
+    else:
+        cov = op.unpack_profiles(all_prof).astype(np.int64).sum(axis=1)
+        prof = all_prof[cov >= 4]
+    assert len(prof) == len(rows)
+    lab, gt = ctypes.c_int(), ctypes.create_string_buffer(3)
+    hom, het = ctypes.c_double(), ctypes.c_double()
+    nd = None
+    if method != "local" or kw.get("estimate_prior"):
+        cov4 = all_prof[op.unpack_profiles(all_prof).astype(np.int64).sum(axis=1) >= 4]
+        u, c = op.oracle_unique(cov4)
+        nd = (ctypes.c_double * 4)(*op.oracle_nd(u, c))
+    prior = kw.get("prior", -1.0)
+    if method == "local" and kw.get("estimate_prior"):
+        prior = want["pi"]
+    seen = {}
+    if method == "likelihood_ratio":
+        u, c = op.oracle_unique(prof)
+        ph, pt = np.empty(len(u)), np.empty(len(u))
+        for i, p in enumerate(u):
+            hc.hc_lr_pvalues(int(p), nd, 1 if kw.get("estimate_prior") else 0, want["pi"], want["eps"], ctypes.byref(hom), ctypes.byref(het))
+            ph[i], pt[i] = hom.value, het.value
+        ah, at = op.oracle_bh(ph), op.oracle_bh(pt)
+        for i, p in enumerate(u):
+            seen[int(p)] = (ah[i], at[i])
+    for k, p in enumerate(prof):
+        p = int(p)
+        if p not in seen:
+            if method == "local":
+                hc.hc_call_local(p, prior, kw.get("error_threshold", 0.1), kw.get("alpha", 0.05), ctypes.byref(lab), gt,
+                                 ctypes.byref(hom), ctypes.byref(het))
+            else:
+                hc.hc_call_bayes(p, nd, want["pi"], want["eps"], ctypes.byref(lab), gt, ctypes.byref(hom), ctypes.byref(het))
+            seen[p] = (hom.value, het.value, lab.value, gt.raw[:2])
+        got = seen[p]
+        assert op.conf_close(got[0], want["hom"][k]), (k, got, want["hom"][k])
+        assert op.conf_close(got[1], want["het"][k]), (k, got, want["het"][k])
+        if method != "likelihood_ratio":
+            assert got[2] == want["label"][k] and got[3] == bytes(want["gt"][k])
+
+
+def test_lynch_objective_matches_oracle(native):
+    hc = op.hostcheck()
+    text = read("depth30.plp")
+    r = op.oracle_call(text, "bayes")
+    prof = r["profiles"]
+    cov = op.unpack_profiles(prof).astype(np.int64).sum(axis=1)
+    u, c = op.oracle_unique(prof[cov >= 4])
+    nd = op.oracle_nd(u, c)
+    a = (ctypes.c_double * 4)(*nd)
+    u = np.ascontiguousarray(u)
+    c = np.ascontiguousarray(c.astype(np.uint64))
+    for pi, eps in [(1e-3, 1e-3), (1e-3 + 1e-4, 1e-3), (r["pi"], r["eps"]), (0.5, 0.5), (0.01, 0.2), (1.0, 1.0), (0.0, 0.0)]:
+        want = op.oracle_objective(u, c, nd, pi, eps)
+        got = hc.hc_lynch_objective(len(u), u.ctypes.data, c.ctypes.data, a, pi, eps)
+        assert abs(got - want) <= 1e-12 * abs(want), (pi, eps, got, want)
+    assert hc.hc_lynch_objective(len(u), u.ctypes.data, c.ctypes.data, a, -0.1, 0.5) == 1.7976931348623157e308
