@@ -13,6 +13,13 @@ namespace sid {
 
 // ---- generic helpers ---------------------------------------------------------------------------
 
+// Order on (key, value) pairs: the value breaks key ties, so padding entries (all-ones key AND
+// all-ones value) sort strictly after every real entry -- also after a real all-ones key (the
+// profile {65535,65535,65535,65535}; a p-value of exactly 0 in the BH keys).
+__device__ __forceinline__ bool pair_greater(unsigned long long ka, uint32_t va, unsigned long long kb, uint32_t vb) {
+    return ka > kb || (ka == kb && va > vb);
+}
+
 // One compare-exchange step of a bitonic sorting network over (key, value) pairs, ascending.
 __global__ void k_bitonic_step(unsigned long long* keys, uint32_t* vals, uint32_t n, uint32_t j, uint32_t k) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -20,11 +27,11 @@ __global__ void k_bitonic_step(unsigned long long* keys, uint32_t* vals, uint32_
     const uint32_t ixj = i ^ j;
     if (ixj <= i || ixj >= n) return;
     const unsigned long long a = keys[i], b = keys[ixj];
+    const uint32_t va = vals[i], vb = vals[ixj];
     const bool up = (i & k) == 0;
-    if ((a > b) == up) {
+    if (pair_greater(a, va, b, vb) == up) {
         keys[i] = b;
         keys[ixj] = a;
-        const uint32_t va = vals[i], vb = vals[ixj];
         vals[i] = vb;
         vals[ixj] = va;
     }
@@ -51,9 +58,10 @@ __global__ void __launch_bounds__(BITONIC_BLOCK / 2) k_bitonic_local(unsigned lo
                 if (x > t) {
                     const bool up = ((base + t) & kk) == 0;
                     const unsigned long long a = sk[t], b = sk[x];
-                    if ((a > b) == up) {
+                    const uint32_t va = sv[t], vb = sv[x];
+                    if (pair_greater(a, va, b, vb) == up) {
                         sk[t] = b; sk[x] = a;
-                        const uint32_t va = sv[t]; sv[t] = sv[x]; sv[x] = va;
+                        sv[t] = vb; sv[x] = va;
                     }
                 }
             }

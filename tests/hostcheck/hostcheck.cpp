@@ -37,36 +37,37 @@ void hc_parse_line(const uint8_t* text, uint64_t len, uint64_t p, int want_qual,
 }
 
 #ifdef SID_HAVE_FAST
-// The SWAR tokenizer the kernel uses.  `text` must be readable (padded) up to a multiple of 16 past len.
-void hc_parse_line_fast(const uint8_t* text, uint64_t len, uint64_t p, hc_line* out) {
+// The SWAR tokenizer the kernel uses.  Returns 1 when the fast grammar accepted the line.
+int hc_parse_line_fast(const uint8_t* text, uint64_t len, uint64_t p, hc_line* out) {
     FastLine fl;
-    parse_line_fast(text, len, p, fl);
     memset(out, 0, sizeof *out);
+    if (!parse_line_fast(text, len, p, fl)) return 0;
     out->status = fl.status; out->pos = fl.pos; out->profile = fl.profile;
     out->chrom_off = fl.chrom_off; out->chrom_len = fl.chrom_len;
+    return 1;
 }
 
-// Parses every line of a text with both tokenizers; returns the number of lines, -(k+1) when line k differs.
-int64_t hc_compare_parsers(const uint8_t* text, uint64_t len, uint64_t* profiles, int32_t* pos, int32_t* status) {
+// Parses every line of a text with both tokenizers.  Returns the number of lines, or -(k+1) when
+// line k differs; *n_fast receives how many lines the fast grammar accepted.
+int64_t hc_compare_parsers(const uint8_t* text, uint64_t len, uint64_t* n_fast) {
     FlatSrc src {text, len};
     int64_t k = 0;
+    uint64_t fast = 0;
     for (uint64_t p = 0; p < len; ++p) {
         if (text[p] == '\n' || (p > 0 && text[p - 1] != '\n')) continue;
         ParsedLine a;
         parse_line(src, p, false, a);
         FastLine b;
-        parse_line_fast(text, len, p, b);
-        if (a.status != b.status) return -(k + 1);
-        if (a.status == LINE_OK && (a.profile != b.profile || a.pos != b.pos || a.chrom_off != b.chrom_off ||
-                                    a.chrom_len != b.chrom_len)) return -(k + 1);
-        if (profiles) profiles[k] = a.profile;
-        if (pos) pos[k] = a.pos;
-        if (status) status[k] = a.status;
+        if (parse_line_fast(text, len, p, b)) {
+            ++fast;
+            if (a.status != LINE_OK || b.status != LINE_OK || a.profile != b.profile || a.pos != b.pos ||
+                a.chrom_off != b.chrom_off || a.chrom_len != b.chrom_len) return -(k + 1);
+        }
         ++k;
     }
+    if (n_fast) *n_fast = fast;
     return k;
 }
-
 #endif
 
 int hc_fmt_g6(double x, char* out) { int n = fmt_g6(x, out); out[n] = 0; return n; }
