@@ -87,7 +87,13 @@ struct CsvParams {
     uint32_t n_tiles;
 };
 
+// Rows of one tile are assembled in shared memory and copied out with aligned 16-byte stores.
+// The staging area starts at (global offset of the tile's first byte) mod 16, so 16-byte chunks of
+// shared memory line up with 16-byte chunks of the output buffer.
+constexpr int CSV_STAGE = 72 * 1024;          // bytes of rows one tile may stage (else: direct global writes)
+
 __global__ void __launch_bounds__(CSV_THREADS) k_csv(const CsvParams p) {
+    extern __shared__ __align__(16) char s_stage[];
     __shared__ uint32_t s_tile;
     __shared__ uint64_t s_base;
     __shared__ uint32_t s_warp_sums[CSV_THREADS / 32];
@@ -100,7 +106,9 @@ __global__ void __launch_bounds__(CSV_THREADS) k_csv(const CsvParams p) {
         const uint32_t tile = s_tile;
         if (tile >= p.n_tiles) break;
         const uint64_t first = (uint64_t)tile * CSV_TILE + (uint64_t)tid * CSV_PER_THREAD;
-        uint32_t len[CSV_PER_THREAD];
+        uint32_t len[CSV_PER_THREAD], nlen[CSV_PER_THREAD], slen[CSV_PER_THREAD], nref[CSV_PER_THREAD];
+        int32_t pos[CSV_PER_THREAD];
+        const char* sfxp[CSV_PER_THREAD];
         uint32_t mine = 0, rows = 0;
 #pragma unroll
         for (int k = 0; k < CSV_PER_THREAD; ++k) {
@@ -110,11 +118,15 @@ __global__ void __launch_bounds__(CSV_THREADS) k_csv(const CsvParams p) {
                 const uint64_t site = p.site_begin + i;
                 const char* sfx = p.site_suffix ? p.site_suffix + site * SUFFIX_BYTES
                                                 : p.table.suffix + (size_t)p.slot[site] * SUFFIX_BYTES;
+                sfxp[k] = sfx;
                 const uint32_t sl = (uint8_t)sfx[SUFFIX_BYTES - 1];
+                slen[k] = sl;
                 if (sl) {
-                    const uint8_t* nm = (const uint8_t*)p.pool + p.name_ref[site];
-                    const uint32_t nl = (uint32_t)nm[0] | ((uint32_t)nm[1] << 8);
-                    len[k] = nl + 1 + (uint32_t)digits_i32(p.pos[site]) + sl;
+                    nref[k] = p.name_ref[site];
+                    pos[k] = p.pos[site];
+                    const uint32_t hdr = *reinterpret_cast<const uint32_t*>(p.pool + nref[k]);   // pool records are 4-byte aligned
+                    nlen[k] = hdr & 0xFFFFu;
+                    len[k] = nlen[k] + 1 + (uint32_t)digits_i32(pos[k]) + sl;
                     ++rows;
                 }
             }
@@ -161,24 +173,49 @@ __global__ void __launch_bounds__(CSV_THREADS) k_csv(const CsvParams p) {
             if (total_rows) atomicAdd(p.rows_out, (unsigned long long)total_rows);
         }
         __syncthreads();
-        uint64_t o = s_base + warp_off + incl - mine;
+        const uint64_t tile_base = s_base;
+        const uint32_t local = warp_off + incl - mine;                 // byte offset of this thread's rows inside the tile
+        if (tile_base + total > p.out_cap) continue;                   // the host reports SIDGPU_ECAPACITY from bytes_out
+        const uint32_t mis = (uint32_t)((uintptr_t)(p.out + tile_base) & 15u);
+        const bool staged = total + mis + 16 <= CSV_STAGE;
+        uint32_t o = local;
 #pragma unroll
         for (int k = 0; k < CSV_PER_THREAD; ++k) {
             if (!len[k]) continue;
-            if (o + len[k] > p.out_cap) { o += len[k]; continue; }      // host checks bytes_out against the capacity
-            const uint64_t site = p.site_begin + first + k;
-            char* w = p.out + o;
-            const uint8_t* nm = (const uint8_t*)p.pool + p.name_ref[site];
-            const uint32_t nl = (uint32_t)nm[0] | ((uint32_t)nm[1] << 8);
-            for (uint32_t i = 0; i < nl; ++i) w[i] = (char)nm[2 + i];
-            w += nl;
+            char* w = staged ? s_stage + mis + o : p.out + tile_base + o;
+            const uint8_t* nm = (const uint8_t*)p.pool + nref[k];
+            for (uint32_t i = 0; i < nlen[k]; ++i) w[i] = (char)nm[2 + i];
+            w += nlen[k];
             *w++ = ',';
-            w += fmt_i32(p.pos[site], w);
-            const char* sfx = p.site_suffix ? p.site_suffix + site * SUFFIX_BYTES
-                                            : p.table.suffix + (size_t)p.slot[site] * SUFFIX_BYTES;
-            const uint32_t sl = (uint8_t)sfx[SUFFIX_BYTES - 1];
-            for (uint32_t i = 0; i < sl; ++i) w[i] = sfx[i];
+            w += fmt_i32(pos[k], w);
+            // suffix: three aligned 16-byte loads, copied byte-wise into the (unaligned) row
+            const uint4* sv = reinterpret_cast<const uint4*>(sfxp[k]);
+            const uint32_t sl = slen[k];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                if ((uint32_t)(16 * c) < sl) {
+                    const uint4 v = sv[c];
+                    const uint32_t wd[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                    for (int b = 0; b < 16; ++b) {
+                        if ((uint32_t)(16 * c + b) < sl) w[16 * c + b] = (char)((wd[b >> 2] >> (8 * (b & 3))) & 0xFF);
+                    }
+                }
+            }
             o += len[k];
+        }
+        if (staged) {
+            __syncthreads();
+            char* g = p.out + tile_base;               // first byte of the tile in global memory
+            // head: bytes up to the first 16-byte boundary; body: aligned vectors; tail: the rest
+            const uint32_t head = mis ? min(16u - mis, total) : 0u;
+            if ((uint32_t)tid < head) g[tid] = s_stage[mis + tid];
+            const uint32_t body = (total - head) >> 4;
+            const uint4* sv = reinterpret_cast<const uint4*>(s_stage + mis + head);    // 16-byte aligned by construction
+            uint4* gv = reinterpret_cast<uint4*>(g + head);
+            for (uint32_t i = tid; i < body; i += CSV_THREADS) gv[i] = sv[i];
+            const uint32_t done = head + (body << 4);
+            if (done + (uint32_t)tid < total) g[done + tid] = s_stage[mis + done + tid];
         }
     }
 }

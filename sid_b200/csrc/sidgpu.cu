@@ -703,6 +703,10 @@ int sidgpu_create(const sidgpu_config* cfg, sidgpu_ctx** out) {
         cudaMemcpyAsync(ctx->quality_lut.p, lut.data(), lut.size() * 8, cudaMemcpyHostToDevice, ctx->stream);
         cudaStreamSynchronize(ctx->stream);
     }
+    if ((e = cudaFuncSetAttribute(k_csv, cudaFuncAttributeMaxDynamicSharedMemorySize, CSV_STAGE)) != cudaSuccess) {
+        ctx->err = std::string("k_csv shared memory opt-in: ") + cudaGetErrorString(e);
+        return bail(SIDGPU_ECUDA);
+    }
     if ((e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) { ctx->err = cudaGetErrorString(e); return bail(SIDGPU_ECUDA); }
     if (c.max_sites) {
         rc = ensure_sites(ctx, c.max_sites, false);
@@ -952,10 +956,10 @@ int sidgpu_emit_csv(sidgpu_ctx* ctx, uint64_t site_begin, uint64_t n_sites, char
     p.bytes_out = ctl_field(ctx, &Control::csv_bytes);
     p.rows_out = ctl_field(ctx, &Control::csv_rows);
     p.n_tiles = n_tiles;
-    const unsigned grid = (unsigned)std::min<uint64_t>(n_tiles, (uint64_t)ctx->sm_count * 8);
+    const unsigned grid = (unsigned)std::min<uint64_t>(n_tiles, (uint64_t)ctx->sm_count * 3);
     {
         ProfScope prof(ctx, PROF_CSV);
-        k_csv<<<grid, CSV_THREADS, 0, ctx->stream>>>(p);
+        k_csv<<<grid, CSV_THREADS, CSV_STAGE, ctx->stream>>>(p);
     }
     TRY(check_launch(ctx, "k_csv"));
     TRY(sync_ctl(ctx));

@@ -153,3 +153,48 @@ def test_lynch_objective_matches_oracle(native):
         got = hc.hc_lynch_objective(len(u), u.ctypes.data, c.ctypes.data, a, pi, eps)
         assert abs(got - want) <= 1e-12 * abs(want), (pi, eps, got, want)
     assert hc.hc_lynch_objective(len(u), u.ctypes.data, c.ctypes.data, a, -0.1, 0.5) == 1.7976931348623157e308
+
+
+def _adversarial_text(seed, n_lines):
+    rnd = random.Random(seed)
+    alphabet = ".,ACGTacgtNn*$^+-0123456789<>#!~^^++--Rr \t]I"
+    heavy = ".,.,.,.,ACGTacgt^$+-12"
+    lines = []
+    for k in range(n_lines):
+        mode = rnd.random()
+        ln = rnd.choice([0, 1, 2, 3, 4, 5, 7, 8, 9, 15, 16, 17, 31, 33, 64, 100, 257])
+        if mode < 0.5:
+            bases = "".join(rnd.choice(heavy) for _ in range(ln))
+        elif mode < 0.9:
+            bases = "".join(rnd.choice(alphabet) for _ in range(ln))
+        else:
+            bases = "".join(chr(rnd.choice([1, 11, 13, 127, 128, 200, 255, 46, 44, 65])) for _ in range(ln))
+        sep = rnd.choice(["\t", "\t", "\t", " ", "\t\t", " \t"])
+        chrom = rnd.choice(["chr1", "c", "chromosome_with_a_long_name", "x" * 40, "chr\x01", "chr\xe9"])
+        pos = rnd.choice(["1", "123456789", "1234567890", "007", "-5", "+3", "12ab", "99999999999999999999", "4294967296"])
+        ref = rnd.choice(list("ACGTNacgtn*") + ["AC", ""])
+        tail = rnd.choice(["\tIIII", "", "\t", "\tII\tJJ", " II"])
+        lines.append(sep.join([chrom, pos, ref, str(ln), bases]) + tail)
+    return ("\n".join(lines) + "\n").encode("latin-1")
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_fast_tokenizer_equals_scalar_on_adversarial_lines(native, seed):
+    """The SWAR tokenizer either refuses a line or returns exactly what the byte-wise one does."""
+    hc = op.hostcheck()
+    text = _adversarial_text(seed, 20000)
+    nf = ctypes.c_uint64()
+    k = hc.hc_compare_parsers(text, len(text), ctypes.byref(nf))
+    assert k > 0, text.split(b"\n")[-k - 1][:200] if k < 0 else None
+    assert nf.value > k // 20          # a fair share of even these lines takes the fast path
+
+
+@pytest.mark.parametrize("name", ["depth30.plp", "depth500.plp", "depth5.plp", "quality30.plp", "edge.plp"])
+def test_fast_tokenizer_covers_normal_text(native, name):
+    hc = op.hostcheck()
+    text = read(name)
+    nf = ctypes.c_uint64()
+    k = hc.hc_compare_parsers(text, len(text), ctypes.byref(nf))
+    assert k > 0
+    if name != "edge.plp":
+        assert nf.value == k          # every ordinary line is handled without the byte-wise fallback
