@@ -15,7 +15,8 @@
 
 namespace sid {
 
-constexpr int TOK_THREADS = 256;
+constexpr int TOK_PARSE_THREADS = 256;             // 8 parse warps
+constexpr int TOK_THREADS = TOK_PARSE_THREADS + 32;   // + 1 service warp (look-back, name of the first line)
 constexpr int TILE_BYTES = 32768;                 // 128 bytes per thread in the line-start scan
 constexpr int TILE_TAIL = 2048;                   // staged past the tile end for straddling lines
 constexpr int TILE_PAD = 16;                      // staged before the tile begin (previous byte)
@@ -64,32 +65,70 @@ struct SmemSrc {
     }
 };
 
-// 16-bit mask of the bytes equal to '\n' in a 16-byte vector.
+// 16-bit mask of the bytes equal to '\n' in a 16-byte vector (exact for all byte values).
 __device__ __forceinline__ uint32_t newline_mask16(uint4 v) {
     uint32_t m = 0;
     const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        const uint32_t eq = __vcmpeq4(w[i], 0x0A0A0A0Au);          // 0xFF per matching byte
-        m |= (((eq & 0x08040201u) * 0x01010101u) >> 24) << (4 * i);
+        const uint32_t x = w[i] ^ 0x0A0A0A0Au;
+        const uint32_t t = ((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x;      // bit 7 set iff the byte is not '\n'
+        const uint32_t z7 = ~t & 0x80808080u;
+        m |= ((z7 * 0x00204081u) >> 28) << (4 * i);                    // gather bits 7,15,23,31 into a nibble
     }
     return m;
+}
+
+// Eight bytes starting at byte offset o of a 4-byte aligned buffer.
+__device__ __forceinline__ uint2 load8_unaligned(const uint8_t* s, uint32_t o) {
+    const uint32_t* sw = reinterpret_cast<const uint32_t*>(s) + (o >> 2);
+    const uint32_t sh = (o & 3) * 8;
+    const uint32_t w0 = sw[0], w1 = sw[1], w2 = sw[2];
+    return make_uint2(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh));
 }
 
 __device__ __forceinline__ void report_error(const TokParams& p, uint64_t line_abs, int status) {
     atomicMin(p.error, (unsigned long long)((line_abs << 3) | (uint64_t)status));
 }
 
+struct LineResult {
+    int status;
+    int32_t pos;
+    uint64_t profile;
+    uint32_t chrom_off, chrom_len;
+};
+
+// Does the name of this line equal the name of the tile's first line?  (8 bytes at a time for the
+// usual short names; the first line's name is known to start at its first byte when l0_ok.)
+__device__ __forceinline__ bool same_name_as_first(const uint8_t* s_text, uint32_t my_off, uint32_t len, uint32_t l0_off,
+                                                   uint2 first8) {
+    if (len <= 7) {
+        const uint2 mine = load8_unaligned(s_text, my_off);
+        const uint32_t bits = 8 * len;
+        uint32_t dlo, dhi, delim;
+        if (len < 4) { dlo = (mine.x ^ first8.x) & ((1u << bits) - 1u); dhi = 0; delim = (first8.x >> bits) & 0xFFu; }
+        else if (len == 4) { dlo = mine.x ^ first8.x; dhi = 0; delim = first8.y & 0xFFu; }
+        else { dlo = mine.x ^ first8.x; dhi = (mine.y ^ first8.y) & ((1u << (bits - 32)) - 1u); delim = (first8.y >> (bits - 32)) & 0xFFu; }
+        return (dlo | dhi) == 0 && (delim == '\t' || delim == ' ');
+    }
+    if (my_off + len + 1 > TILE_SMEM || l0_off + len + 1 > TILE_SMEM) return false;
+    for (uint32_t i = 0; i < len; ++i) if (s_text[my_off + i] != s_text[l0_off + i]) return false;
+    const uint8_t d = s_text[l0_off + len];
+    return d == '\t' || d == ' ';
+}
+
 template <bool FAST>
 __global__ void __launch_bounds__(TOK_THREADS) k_tokenize(const TokParams p) {
     __shared__ __align__(16) uint8_t s_text[TILE_SMEM];
     __shared__ uint16_t s_starts[TILE_MAX_LINES];
-    __shared__ uint32_t s_warp_sums[TOK_THREADS / 32];
-    __shared__ uint32_t s_tile, s_nlines, s_name0_ref, s_name0_len;
-    __shared__ uint64_t s_base, s_name0_abs;
+    __shared__ uint32_t s_warp_sums[TOK_PARSE_THREADS / 32];
+    __shared__ uint32_t s_tile, s_name0_ref, s_ready;
+    __shared__ uint64_t s_base;
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
+    const bool parser = tid < TOK_PARSE_THREADS;
+    if (tid == 0) s_ready = 0;
 
     for (;;) {
         __syncthreads();                                   // protects s_* reuse across iterations
@@ -98,7 +137,7 @@ __global__ void __launch_bounds__(TOK_THREADS) k_tokenize(const TokParams p) {
         const uint32_t tile = s_tile;
         if (tile >= p.n_tiles) break;
         const uint64_t tb = p.tile0 + (uint64_t)tile * TILE_BYTES;      // absolute offset of the tile
-        const uint64_t abs0 = tb - TILE_PAD;                             // may "underflow" for tile 0 at offset 0
+        const uint64_t abs0 = tb - TILE_PAD;                             // wraps for a tile at offset 0; only differences are used
 
         // ---- stage [tb - 16, tb + TILE_BYTES + TILE_TAIL) ; bytes outside the text read as '\n'
         for (int i = tid; i < TILE_SMEM / 16; i += TOK_THREADS) {
@@ -121,21 +160,23 @@ __global__ void __launch_bounds__(TOK_THREADS) k_tokenize(const TokParams p) {
         __syncthreads();
 
         // ---- line starts: byte q starts a line iff text[q] != '\n' and text[q-1] == '\n'
-        // thread t owns bytes [128 t, 128 t + 128) of the tile; 16-byte loads rotated across the
+        // parse thread t owns bytes [128 t, 128 t + 128) of the tile; 16-byte loads rotated across the
         // quarter-warp so that the eight lanes hit eight different bank groups.
-        uint64_t nl_lo = 0, nl_hi = 0;
+        uint64_t st_lo = 0, st_hi = 0;
+        uint32_t my_count = 0, incl = 0;
+        if (parser) {
+            uint64_t nl_lo = 0, nl_hi = 0;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const int g = (k + tid) & 7;
-            const uint4 v = *reinterpret_cast<const uint4*>(s_text + TILE_PAD + tid * 128 + g * 16);
-            const uint64_t m = newline_mask16(v);
-            if (g < 4) nl_lo |= m << (16 * g); else nl_hi |= m << (16 * (g - 4));
-        }
-        const uint64_t prev_nl = s_text[TILE_PAD + tid * 128 - 1] == (uint8_t)'\n' ? 1ull : 0ull;
-        uint64_t st_lo = ((nl_lo << 1) | prev_nl) & ~nl_lo;
-        uint64_t st_hi = ((nl_hi << 1) | (nl_lo >> 63)) & ~nl_hi;
-        // restrict to the owned range [range_begin, range_end)
-        {
+            for (int k = 0; k < 8; ++k) {
+                const int g = (k + tid) & 7;
+                const uint4 v = *reinterpret_cast<const uint4*>(s_text + TILE_PAD + tid * 128 + g * 16);
+                const uint64_t m = newline_mask16(v);
+                if (g < 4) nl_lo |= m << (16 * g); else nl_hi |= m << (16 * (g - 4));
+            }
+            const uint64_t prev_nl = s_text[TILE_PAD + tid * 128 - 1] == (uint8_t)'\n' ? 1ull : 0ull;
+            st_lo = ((nl_lo << 1) | prev_nl) & ~nl_lo;
+            st_hi = ((nl_hi << 1) | (nl_lo >> 63)) & ~nl_hi;
+            // restrict to the owned range [range_begin, range_end)
             const uint64_t first = tb + (uint64_t)tid * 128;
             if (first + 128 <= p.range_begin || first >= p.range_end) { st_lo = 0; st_hi = 0; }
             else {
@@ -149,25 +190,25 @@ __global__ void __launch_bounds__(TOK_THREADS) k_tokenize(const TokParams p) {
                     else st_hi &= (1ull << (keep - 64)) - 1;
                 }
             }
-        }
-        const uint32_t my_count = __popcll(st_lo) + __popcll(st_hi);
-        uint32_t incl = my_count;
+            my_count = __popcll(st_lo) + __popcll(st_hi);
+            incl = my_count;
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-            if (lane >= d) incl += o;
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+                if (lane >= d) incl += o;
+            }
+            if (lane == 31) s_warp_sums[warp] = incl;
         }
-        if (lane == 31) s_warp_sums[warp] = incl;
         __syncthreads();
         uint32_t warp_off = 0, total = 0;
 #pragma unroll
-        for (int w = 0; w < TOK_THREADS / 32; ++w) {
+        for (int w = 0; w < TOK_PARSE_THREADS / 32; ++w) {
             const uint32_t v = s_warp_sums[w];
             if (w < warp) warp_off += v;
             total += v;
         }
-        uint32_t idx = warp_off + incl - my_count;
-        {
+        if (parser) {
+            uint32_t idx = warp_off + incl - my_count;
             uint64_t m = st_lo;
             while (m) { const int b = __ffsll((long long)m) - 1; m &= m - 1; if (idx < TILE_MAX_LINES) s_starts[idx] = (uint16_t)(tid * 128 + b); ++idx; }
             m = st_hi;
@@ -180,105 +221,105 @@ __global__ void __launch_bounds__(TOK_THREADS) k_tokenize(const TokParams p) {
         }
         __syncthreads();
 
-        SmemSrc ssrc {s_text, abs0, (uint32_t)TILE_SMEM, false};
         FlatSrc gsrc {p.text, p.text_len};
-
-        // ---- decoupled look-back over per-tile line counts (thread 0) and the tile's first
-        //      chromosome name (thread 32), concurrently
-        if (tid == 0) {
-            uint64_t base = 0;
-            if (tile == 0) {
-                atomicExch(&p.tile_status[0], LB_FLAG_PREFIX | (unsigned long long)n_lines);
-            } else {
-                atomicExch(&p.tile_status[tile], LB_FLAG_AGG | (unsigned long long)n_lines);
-                uint32_t i = tile - 1;
-                for (;;) {
-                    unsigned long long w;
-                    unsigned int spins = 0;
-                    do {
-                        w = *((volatile unsigned long long*)&p.tile_status[i]);
-                        if ((w >> 62) == 0 && ++spins > (1u << 24)) { report_error(p, tb, LINE_MALFORMED + 4); w = LB_FLAG_PREFIX; }
-                    } while ((w >> 62) == 0);
-                    base += w & LB_VALUE_MASK;
-                    if (w & LB_FLAG_PREFIX) break;
-                    --i;
+        if (!parser) {
+            // ---- service warp: decoupled look-back over per-tile line counts (lane 0) and the
+            //      interned name of the tile's first line (lane 1), while the parse warps work
+            if (lane == 0) {
+                uint64_t base = 0;
+                if (tile == 0) {
+                    atomicExch(&p.tile_status[0], LB_FLAG_PREFIX | (unsigned long long)n_lines);
+                } else {
+                    atomicExch(&p.tile_status[tile], LB_FLAG_AGG | (unsigned long long)n_lines);
+                    uint32_t i = tile - 1;
+                    for (;;) {
+                        unsigned long long w;
+                        unsigned int spins = 0;
+                        do {
+                            w = *((volatile unsigned long long*)&p.tile_status[i]);
+                            if ((w >> 62) == 0 && ++spins > (1u << 24)) { report_error(p, tb, LINE_MALFORMED + 4); w = LB_FLAG_PREFIX; }
+                        } while ((w >> 62) == 0);
+                        base += w & LB_VALUE_MASK;
+                        if (w & LB_FLAG_PREFIX) break;
+                        --i;
+                    }
+                    atomicExch(&p.tile_status[tile], LB_FLAG_PREFIX | (unsigned long long)(base + n_lines));
                 }
-                atomicExch(&p.tile_status[tile], LB_FLAG_PREFIX | (unsigned long long)(base + n_lines));
-            }
-            s_base = base;
-            if (tile == p.n_tiles - 1) *p.n_sites = base + n_lines;
-        } else if (tid == 32) {
-            uint32_t ref = 0, len = 0;
-            uint64_t nabs = 0;
-            if (n_lines > 0) {
-                uint64_t q = tb + s_starts[0];
-                uint8_t c = ssrc.at(q);
-                while (is_delim(c)) c = ssrc.at(++q);
-                nabs = q;
-                while (!is_delim(c) && !is_eol(c)) c = ssrc.at(++q);
-                len = (uint32_t)(q - nabs);
-                if (ssrc.overrun) {                        // absurdly long name: read it from global memory
-                    q = tb + s_starts[0];
-                    c = gsrc.at(q);
-                    while (is_delim(c)) c = gsrc.at(++q);
-                    nabs = q;
+                s_base = base;
+                if (tile == p.n_tiles - 1) *p.n_sites = base + n_lines;
+            } else if (lane == 1) {
+                uint32_t ref = 0;
+                if (n_lines > 0) {
+                    // only a name that starts at the first byte of the line can be shared (same_name_as_first)
+                    const uint64_t nabs = tb + s_starts[0];
+                    uint64_t q = nabs;
+                    uint8_t c = gsrc.at(q);
                     while (!is_delim(c) && !is_eol(c)) c = gsrc.at(++q);
-                    len = (uint32_t)(q - nabs);
+                    const uint32_t len = (uint32_t)(q - nabs);
+                    if (len > 0 && is_delim(c)) ref = name_intern(p.names, gsrc, nabs, len);
                 }
-                if (len > 0) ref = name_intern(p.names, gsrc, nabs, len);
+                s_name0_ref = ref;
             }
-            s_name0_ref = ref;
-            s_name0_len = len;
-            s_name0_abs = nabs;
+            __syncwarp();
+            __threadfence_block();
+            if (lane == 0) *((volatile uint32_t*)&s_ready) = tile + 1;     // publishes s_base and s_name0_ref to the parse warps
+            continue;
         }
-        __syncthreads();
-        const uint64_t base = s_base;
-        const uint32_t name0_ref = s_name0_ref, name0_len = s_name0_len;
-        const uint64_t name0_abs = s_name0_abs;
 
-        // ---- one line per thread
-        for (uint32_t j = tid; j < n_lines; j += TOK_THREADS) {
-            const uint64_t line_abs = tb + s_starts[j];
-            int status;
-            int32_t pos;
-            uint64_t profile;
-            uint32_t chrom_off, chrom_len;
-            bool done = false;
+        // ---- parse warps: groups of 32 consecutive lines, one line per lane.  Every lane runs the
+        //      tokenizer (lanes past the end re-parse the group's first line and drop the result)
+        //      so that the warp reconverges inside it.
+        const uint32_t l0_off = n_lines ? TILE_PAD + s_starts[0] : 0;
+        const uint2 first8 = n_lines ? load8_unaligned(s_text, l0_off) : make_uint2(0, 0);
+        bool have_base = false;
+        uint64_t base = 0;
+        uint32_t name0_ref = 0;
+        for (uint32_t g = warp * 32; g < n_lines; g += TOK_PARSE_THREADS) {
+            const uint32_t j = g + lane;
+            const bool mine = j < n_lines;
+            const uint32_t off = s_starts[mine ? j : g];
+            const uint64_t line_abs = tb + off;
+            LineResult r;
+            bool fast = false;
             if (FAST && !p.want_qual) {
                 FastLine fl;
-                // the fast path reads aligned 16-byte groups; it needs the whole line inside the staged bytes
-                if (parse_line_fast_smem(s_text, abs0, TILE_SMEM, line_abs, fl)) {
-                    status = fl.status; pos = fl.pos; profile = fl.profile; chrom_off = fl.chrom_off; chrom_len = fl.chrom_len;
-                    done = true;
-                }
+                fast = parse_line_fast_smem(s_text, abs0, TILE_SMEM, line_abs, fl);
+                r.status = fl.status; r.pos = fl.pos; r.profile = fl.profile; r.chrom_off = fl.chrom_off; r.chrom_len = fl.chrom_len;
             }
-            if (!done) {
+            if (!fast && mine) {
+                SmemSrc ssrc {s_text, abs0, (uint32_t)TILE_SMEM, false};
                 ParsedLine pl;
-                ssrc.overrun = false;
                 parse_line(ssrc, line_abs, p.want_qual != 0, pl);
                 if (ssrc.overrun) parse_line(gsrc, line_abs, p.want_qual != 0, pl);
-                status = pl.status; pos = pl.pos; profile = pl.profile; chrom_off = pl.chrom_off; chrom_len = pl.chrom_len;
+                r.status = pl.status; r.pos = pl.pos; r.profile = pl.profile; r.chrom_off = pl.chrom_off; r.chrom_len = pl.chrom_len;
             }
-            if (status != LINE_OK) { report_error(p, line_abs, status); continue; }
-            const uint64_t site = p.site_base + base + j;
-            if (site >= p.site_cap) { report_error(p, line_abs, LINE_MALFORMED + 5); continue; }
-            // chromosome name: same as the tile's first line in all but a handful of tiles
-            uint32_t ref;
-            {
-                const uint64_t nabs = line_abs + chrom_off;
-                bool same = chrom_len == name0_len && name0_ref != 0;
-                ssrc.overrun = false;
-                for (uint32_t i = 0; same && i < chrom_len; ++i) same = ssrc.at(nabs + i) == ssrc.at(name0_abs + i);
-                ref = (same && !ssrc.overrun) ? name0_ref : name_intern(p.names, gsrc, nabs, chrom_len);
+            __syncwarp();
+            const bool good = mine && r.status == LINE_OK;
+            bool same = false;
+            uint32_t slot = 0;
+            if (good) {
+                same = r.chrom_off == 0 && same_name_as_first(s_text, TILE_PAD + off, r.chrom_len, l0_off, first8);
+                if (p.use_table) slot = table_find_or_insert(p.table, r.profile);
             }
-            p.pos[site] = pos;
-            p.name_ref[site] = ref;
-            if (p.profile) p.profile[site] = profile;
-            if (p.line_off) p.line_off[site] = line_abs;
-            if (p.use_table) {
-                const uint32_t slot = table_find_or_insert(p.table, profile);
-                p.slot[site] = slot;
-                if (p.count_profiles) atomicAdd(&p.table.counts[slot], 1ull);
+            if (!have_base) {                              // wait for the service warp (usually long done)
+                while (*((volatile uint32_t*)&s_ready) != tile + 1) { }
+                __threadfence_block();
+                base = *((volatile uint64_t*)&s_base);
+                name0_ref = *((volatile uint32_t*)&s_name0_ref);
+                have_base = true;
+            }
+            if (mine && r.status != LINE_OK) report_error(p, line_abs, r.status);
+            if (good) {
+                const uint64_t site = p.site_base + base + j;
+                if (site >= p.site_cap) { report_error(p, line_abs, LINE_MALFORMED + 5); }
+                else {
+                    const uint32_t ref = (same && name0_ref) ? name0_ref : name_intern(p.names, gsrc, line_abs + r.chrom_off, r.chrom_len);
+                    p.pos[site] = r.pos;
+                    p.name_ref[site] = ref;
+                    if (p.profile) p.profile[site] = r.profile;
+                    if (p.line_off) p.line_off[site] = line_abs;
+                    if (p.use_table) p.slot[site] = slot;
+                }
             }
         }
     }

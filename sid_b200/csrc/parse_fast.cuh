@@ -8,8 +8,8 @@
 //   parseReadBases   pileup.cpp:70-153  bases field, 4 bytes per step:
 //       - bytes outside [0x21,0x7f] end the field (tab/space/newline/NUL) or refuse the line
 //       - '^' masks the following byte without a branch; "^^" refuses
-//       - '+' / '-' (outside a masked byte) switch to the byte-wise BasesState for the indel, then
-//         the word loop resumes
+//       - '+' / '-' (outside a masked byte): the length is read byte-wise, the word loop restarts
+//         right after the number with that many bytes to neutralise
 //       - A/C/G/T (case folded) and '.'/',' are counted with per-byte equality flags summed by dp4a
 #pragma once
 #include "common.cuh"
@@ -58,60 +58,74 @@ SID_HD uint32_t eq7(uint32_t x, uint32_t pat, uint32_t excl) {
     return ~t & M80 & ~excl;
 }
 
+#if defined(__CUDA_ARCH__)
+#define SID_SYNCWARP() __syncwarp()
+#else
+#define SID_SYNCWARP() ((void)0)
+#endif
+
 // `s` is a 4-byte aligned staging buffer whose byte 0 is absolute offset abs0 (abs0 % 4 == 0) with
 // `avail` valid bytes (multiple of 4).  Returns false when the line must take the byte-wise path.
+// On the device ALL 32 lanes of a warp must call this together (lanes without a line of their own
+// pass any valid line): the header and the word loop end in a warp-wide reconvergence point, so
+// the code after them runs with full warps again.  A refusal therefore never returns early; it
+// clears `ok` and lets the lane idle to the next reconvergence point.
 SID_HD bool parse_line_fast_smem(const uint8_t* s, uint64_t abs0, uint32_t avail, uint64_t line_abs, FastLine& o) {
     const uint32_t start = (uint32_t)(line_abs - abs0);
-    if (start + 64 > avail) return false;
+    bool ok = start + 64 <= avail;
     const uint32_t safe_end = avail - 8;
-    uint32_t i = start;
+    uint32_t i = ok ? start : 0;
     uint32_t c;
     // ---- chromosome name
     c = s[i];
-    if (c <= 0x20) return false;
+    ok = ok && c > 0x20;
     do { c = s[++i]; } while (c > 0x20 && i < safe_end);
-    if (c != '\t' && c != ' ') return false;
+    ok = ok && (c == '\t' || c == ' ');
     o.chrom_off = 0;
     o.chrom_len = i - start;
+    if (i >= safe_end) i = safe_end - 16;     // refused already; keeps the remaining header reads in bounds
     ++i;
     // ---- position: 1..9 digits
     uint32_t acc = 0, nd = 0;
     for (;;) {
         const uint32_t d = (uint32_t)s[i] - (uint32_t)'0';
-        if (d > 9) break;
+        if (d > 9 || nd > 9) break;
         acc = acc * 10 + d;
         ++i;
-        if (++nd > 9) return false;
+        ++nd;
     }
-    if (nd == 0) return false;
+    ok = ok && nd >= 1 && nd <= 9;
     c = s[i];
-    if (c != '\t' && c != ' ') return false;
+    ok = ok && (c == '\t' || c == ' ');
     ++i;
     // ---- reference base: exactly one character
     const uint32_t ref = s[i];
-    if (ref <= 0x20) return false;
+    ok = ok && ref > 0x20;
     c = s[++i];
-    if (c != '\t' && c != ' ') return false;
+    ok = ok && (c == '\t' || c == ' ');
     ++i;
     // ---- depth column: skipped
     c = s[i];
-    if (c <= 0x20) return false;
+    ok = ok && c > 0x20 && i < safe_end;
+    if (i >= safe_end) i = safe_end;
     do { c = s[++i]; } while (c > 0x20 && i < safe_end);
-    if (c != '\t' && c != ' ') return false;
+    ok = ok && (c == '\t' || c == ' ');
     ++i;
-    if (s[i] <= 0x20) return false;          // empty bases field or doubled delimiter
-    if (i >= safe_end) return false;
+    ok = ok && i < safe_end && s[i] > 0x20;      // empty bases field or doubled delimiter
+    if (i >= safe_end) i = safe_end;
+    SID_SYNCWARP();
 
     // ---- bases field, one 32-bit word per step
     const uint32_t* sw = reinterpret_cast<const uint32_t*>(s);
     const uint32_t n_words = avail >> 2;
     uint32_t idx = i >> 2;
-    const uint32_t sh = (i & 3) * 8;
+    uint32_t sh = (i & 3) * 8;
     uint32_t cur = sw[idx];
     uint32_t a7 = 0, c7 = 0, g7 = 0, t7 = 0, d7 = 0;   // 128 * count
     uint32_t skip = 0;
-    for (;;) {
-        if (idx + 1 >= n_words) return false;          // ran out of staged bytes
+    bool running = ok;
+    while (running) {
+        if (idx + 1 >= n_words) { ok = false; break; }  // ran out of staged bytes
         const uint32_t nxt = sw[idx + 1];
         uint32_t w = funnel_r(cur, nxt, sh);
         cur = nxt;
@@ -119,11 +133,10 @@ SID_HD bool parse_line_fast_smem(const uint8_t* s, uint64_t abs0, uint32_t avail
         // bytes outside [0x21, 0x7f]
         const uint32_t ok7 = ((w | M80) - NEUTRAL) & ~w & M80;
         bool last = false;
-        uint32_t nvalid = 4;
         if (ok7 != M80) {
-            nvalid = (uint32_t)first_flag_byte(ok7 ^ M80);
+            const uint32_t nvalid = (uint32_t)first_flag_byte(ok7 ^ M80);
             const uint32_t b = (w >> (8 * nvalid)) & 0xFFu;
-            if (b != '\t' && b != ' ' && b != '\n' && b != 0) return false;     // a control or 8-bit byte inside the field
+            if (b != '\t' && b != ' ' && b != '\n' && b != 0) { ok = false; break; }   // a control or 8-bit byte inside the field
             const uint32_t keep = nvalid ? (0xFFFFFFFFu >> (32 - 8 * nvalid)) : 0u;
             w = (w & keep) | (NEUTRAL & ~keep);
             last = true;
@@ -137,70 +150,61 @@ SID_HD bool parse_line_fast_smem(const uint8_t* s, uint64_t abs0, uint32_t avail
         }
         // '^' masks the byte after it
         const uint32_t caret7 = eq7(w, 0x5E5E5E5Eu, 0);
-        if (caret7 & (caret7 << 8)) return false;       // "^^": leave the parity to the byte-wise path
+        if (caret7 & (caret7 << 8)) { ok = false; break; }   // "^^": leave the parity to the byte-wise path
         const uint32_t masked7 = caret7 << 8;
-        // '+' / '-' outside masked bytes: byte-wise for the rest of this word and the indel that follows
+        // '+' / '-' outside masked bytes
         const uint32_t pm7 = (eq7(w, 0x2B2B2B2Bu, 0) | eq7(w, 0x2D2D2D2Du, 0)) & ~masked7;
+        uint32_t wc = w;                                 // the bytes to count in this step
+        bool restart = false;
+        uint32_t q = 0;
         if (pm7) {
-            BasesState b;
-            b.init();
-            // everything before the sign is plain: count it with the flags, then feed from the sign on
+            // everything before the sign is plain; the indel length is read byte-wise
+            // (pileup.cpp:131-136); the skipped bases are then neutralised by the word loop itself,
+            // restarted right after the number
             const uint32_t k0 = (uint32_t)first_flag_byte(pm7);
             const uint32_t before = k0 ? (0xFFFFFFFFu >> (32 - 8 * k0)) : 0u;
-            const uint32_t wb = (w & before) | (NEUTRAL & ~before);
-            const uint32_t ex = masked7;
-            const uint32_t f = wb & 0xDFDFDFDFu;
-            a7 = add_flags(eq7(f, 0x41414141u, ex), a7);
-            c7 = add_flags(eq7(f, 0x43434343u, ex), c7);
-            g7 = add_flags(eq7(f, 0x47474747u, ex), g7);
-            t7 = add_flags(eq7(f, 0x54545454u, ex), t7);
-            d7 = add_flags(eq7(wb & 0xFDFDFDFDu, 0x2C2C2C2Cu, ex), d7);
-            // byte-wise from the sign: bytes come from the staged text directly
-            uint32_t q = (idx - 1) * 4 + (sh >> 3) + k0;      // byte offset of the sign in s
-            // (idx was advanced; the word started at ((idx-1)*4 + sh/8))
-            bool ended = false;
-            for (;;) {
-                if (q >= safe_end) return false;
-                const uint32_t ch = s[q];
-                if (ch <= 0x20 || ch >= 0x80) {
-                    if (ch == '\t' || ch == ' ' || ch == '\n' || ch == 0) { ended = true; break; }
-                    return false;
-                }
-                b.feed((uint8_t)ch);
+            wc = (w & before) | (NEUTRAL & ~before);
+            q = (idx - 1) * 4 + (sh >> 3) + k0 + 1;      // first byte after the sign
+            uint32_t n = 0;
+            bool any = false;
+            while (q < safe_end) {
+                const uint32_t d = (uint32_t)s[q] - (uint32_t)'0';
+                if (d > 9) break;
+                if (n < (1u << 26)) n = n * 10 + d;
+                any = true;
                 ++q;
-                // resume the word loop once the state machine is idle again and we are word aligned
-                // with respect to the field's word grid
-                if (b.mode == 0 && b.skip == 0 && ((q - (sh >> 3)) & 3) == 0) break;
             }
-            a7 += 128u * b.cnt[0];
-            c7 += 128u * b.cnt[1];
-            g7 += 128u * b.cnt[2];
-            t7 += 128u * b.cnt[3];
-            d7 += 128u * (b.dots + b.commas);
-            if (ended) break;
-            // a trailing '^' inside the byte-wise stretch leaves skip == 1 only if we stopped right after it,
-            // which the resume condition (skip == 0) excludes
-            idx = (q - (sh >> 3)) >> 2;
-            if (idx >= n_words) return false;
-            cur = sw[idx];
-            continue;
+            if (q >= safe_end) { ok = false; break; }
+            skip = any ? n : 0;                          // a sign without digits is ignored (pileup.cpp:131-133)
+            restart = true;
+            last = false;
+        } else if (caret7 >> 31) {
+            skip = 1;                                    // the masked byte is the first of the next word
         }
-        if (caret7 >> 31) skip = 1;                     // the masked byte is the first of the next word
-        const uint32_t f = w & 0xDFDFDFDFu;
+        const uint32_t f = wc & 0xDFDFDFDFu;
         a7 = add_flags(eq7(f, 0x41414141u, masked7), a7);
         c7 = add_flags(eq7(f, 0x43434343u, masked7), c7);
         g7 = add_flags(eq7(f, 0x47474747u, masked7), g7);
         t7 = add_flags(eq7(f, 0x54545454u, masked7), t7);
-        d7 = add_flags(eq7(w & 0xFDFDFDFDu, 0x2C2C2C2Cu, masked7), d7);
-        if (last) break;
+        d7 = add_flags(eq7(wc & 0xFDFDFDFDu, 0x2C2C2C2Cu, masked7), d7);
+        if (restart) {
+            idx = q >> 2;
+            sh = (q & 3) * 8;
+            cur = sw[idx];
+        }
+        if (last) running = false;
     }
-    uint32_t cnt[4] = {a7 >> 7, c7 >> 7, g7 >> 7, t7 >> 7};
-    const int ri = ref_index((uint8_t)ref);
-    if (ri >= 0) cnt[ri] += d7 >> 7;
-    o.profile = pack_profile(cnt[0], cnt[1], cnt[2], cnt[3]);
+    SID_SYNCWARP();
+    // '.' and ',' stand for the reference base (pileup.cpp:78-83); other reference characters drop them
+    const uint32_t rf = ref & 0xDFu, dots = d7 >> 7;
+    const uint32_t na = (a7 >> 7) + (rf == 'A' ? dots : 0u);
+    const uint32_t nc = (c7 >> 7) + (rf == 'C' ? dots : 0u);
+    const uint32_t ng = (g7 >> 7) + (rf == 'G' ? dots : 0u);
+    const uint32_t nt = (t7 >> 7) + (rf == 'T' ? dots : 0u);
+    o.profile = pack_profile(na, nc, ng, nt);
     o.pos = (int32_t)acc;
     o.status = LINE_OK;
-    return true;
+    return ok;
 }
 
 #if !defined(__CUDACC__)
