@@ -2,26 +2,34 @@
 //   readFile call.cpp:11-20, parsePileupLine pileup.cpp:13-68, parseReadBases pileup.cpp:70-153,
 //   countUniqueProfiles pileup.cpp:169-196 (the counting half), call.cpp:217-221 (profile index).
 //
-// Layout: the text is cut into fixed tiles of TILE_BYTES.  Persistent CTAs take tiles in order
-// from an atomic ticket, stage the tile (+ a tail for the line that straddles its end) in shared
-// memory, find the line starts with SWAR newline masks, obtain the global index of their first
-// line by a decoupled look-back over per-tile line counts (single pass over the text, output
-// dense and in file order), then parse one line per thread out of shared memory.
+// Layout: the text is cut into tiles of eight slices.  Each persistent CTA is warp specialised:
+//   * warp 0 (service) draws tiles in order from an atomic ticket and stages them (+ a tail for
+//     the line that straddles the end) in shared memory with one bulk asynchronous copy
+//     (cp.async.bulk -> mbarrier), one tile ahead of the parse warps; it sums the slices' line
+//     counts and obtains the global index of the tile's first line by a decoupled look-back over
+//     per-tile counts (single pass over the text, output dense and in file order).
+//   * warps 1..8 (parse) each own one slice of the staged tile: the warp finds the line starts of
+//     its slice with SWAR newline masks, then parses them one line per lane.  The slice length is
+//     chosen by the host so that a slice holds about 30 lines.
+// Hand-over in both directions goes through mbarriers; there is no CTA-wide barrier in the loop.
 #pragma once
 #include "common.cuh"
 #include "parse.cuh"
 #include "parse_fast.cuh"
+#include "ptx.cuh"
 #include "table.cuh"
 
 namespace sid {
 
-constexpr int TOK_PARSE_THREADS = 256;             // 8 parse warps
-constexpr int TOK_THREADS = TOK_PARSE_THREADS + 32;   // + 1 service warp (look-back, name of the first line)
-constexpr int TILE_BYTES = 32768;                 // 128 bytes per thread in the line-start scan
+constexpr int TOK_PARSE_WARPS = 8;
+constexpr int TOK_THREADS = 32 * (1 + TOK_PARSE_WARPS);
+constexpr int TOK_STAGES = 2;
+constexpr int SLICE_MAX = 4096;                   // bytes; slices are multiples of 16
+constexpr int SLICE_MIN = 256;
 constexpr int TILE_TAIL = 2048;                   // staged past the tile end for straddling lines
 constexpr int TILE_PAD = 16;                      // staged before the tile begin (previous byte)
-constexpr int TILE_SMEM = TILE_PAD + TILE_BYTES + TILE_TAIL;
-constexpr int TILE_MAX_LINES = TILE_BYTES / 8;    // a valid line has >= 10 bytes
+constexpr int TILE_SMEM_MAX = TILE_PAD + TOK_PARSE_WARPS * SLICE_MAX + TILE_TAIL;
+constexpr int SLICE_MAX_LINES = SLICE_MAX / 8;    // a valid line has >= 10 bytes
 
 constexpr unsigned long long LB_FLAG_AGG = 1ull << 62;
 constexpr unsigned long long LB_FLAG_PREFIX = 2ull << 62;
@@ -48,7 +56,14 @@ struct TokParams {
     TableView table;
     NameDict names;
     int use_table, count_profiles, want_qual;
+    uint32_t slice_bytes;           // multiple of 16 in [SLICE_MIN, SLICE_MAX]; a tile is 8 slices
+    uint32_t text_stride;           // bytes of shared memory per staged tile (tile_smem rounded up to 128)
+    uint32_t lines_cap;             // line-start slots per slice (slice_bytes / 8)
 };
+
+// Dynamic shared memory a launch with this slice length needs.
+inline uint32_t tok_text_stride(uint32_t slice) { return (16u + 8u * slice + 2048u + 127u) & ~127u; }
+inline uint32_t tok_dyn_smem(uint32_t slice) { return 2u * (tok_text_stride(slice) + 8u * (slice / 8u) * 2u); }
 
 #if defined(__CUDACC__)
 
@@ -101,7 +116,7 @@ struct LineResult {
 // Does the name of this line equal the name of the tile's first line?  (8 bytes at a time for the
 // usual short names; the first line's name is known to start at its first byte when l0_ok.)
 __device__ __forceinline__ bool same_name_as_first(const uint8_t* s_text, uint32_t my_off, uint32_t len, uint32_t l0_off,
-                                                   uint2 first8) {
+                                                   uint2 first8, uint32_t avail = TILE_SMEM_MAX) {
     if (len <= 7) {
         const uint2 mine = load8_unaligned(s_text, my_off);
         const uint32_t bits = 8 * len;
@@ -111,183 +126,299 @@ __device__ __forceinline__ bool same_name_as_first(const uint8_t* s_text, uint32
         else { dlo = mine.x ^ first8.x; dhi = (mine.y ^ first8.y) & ((1u << (bits - 32)) - 1u); delim = (first8.y >> (bits - 32)) & 0xFFu; }
         return (dlo | dhi) == 0 && (delim == '\t' || delim == ' ');
     }
-    if (my_off + len + 1 > TILE_SMEM || l0_off + len + 1 > TILE_SMEM) return false;
+    if (my_off + len + 1 > avail || l0_off + len + 1 > avail) return false;
     for (uint32_t i = 0; i < len; ++i) if (s_text[my_off + i] != s_text[l0_off + i]) return false;
     const uint8_t d = s_text[l0_off + len];
     return d == '\t' || d == ' ';
 }
 
+struct StageMeta {
+    uint64_t tb;           // absolute offset of the tile
+    uint64_t base;         // global index of its first line
+    uint32_t prefix[TOK_PARSE_WARPS];   // lines in the slices before slice w
+    uint32_t count[TOK_PARSE_WARPS];    // lines that start in slice w
+    int32_t tile;          // -1: no more tiles
+    uint32_t smem_bytes;   // bytes staged for this tile
+};
+
+struct SmemBytes {         // byte source over a staged tile for name_intern
+    const uint8_t* s;
+    uint64_t abs0;
+    __device__ __forceinline__ uint8_t at(uint64_t off) const { return s[(uint32_t)(off - abs0)]; }
+};
+
+
 template <bool FAST>
 __global__ void __launch_bounds__(TOK_THREADS) k_tokenize(const TokParams p) {
-    __shared__ __align__(16) uint8_t s_text[TILE_SMEM];
-    __shared__ uint16_t s_starts[TILE_MAX_LINES];
-    __shared__ uint32_t s_warp_sums[TOK_PARSE_THREADS / 32];
-    __shared__ uint32_t s_tile, s_name0_ref, s_ready;
-    __shared__ uint64_t s_base;
+    extern __shared__ __align__(128) uint8_t s_dyn[];      // staged text per stage, then line starts per stage and warp
+    __shared__ StageMeta s_meta[TOK_STAGES];
+    __shared__ __align__(8) uint64_t s_full[TOK_STAGES], s_counted[TOK_STAGES], s_ready[TOK_STAGES], s_done[TOK_STAGES];
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
-    const bool parser = tid < TOK_PARSE_THREADS;
-    if (tid == 0) s_ready = 0;
-
-    for (;;) {
-        __syncthreads();                                   // protects s_* reuse across iterations
-        if (tid == 0) s_tile = atomicAdd(p.tile_ticket, 1u);
-        __syncthreads();
-        const uint32_t tile = s_tile;
-        if (tile >= p.n_tiles) break;
-        const uint64_t tb = p.tile0 + (uint64_t)tile * TILE_BYTES;      // absolute offset of the tile
-        const uint64_t abs0 = tb - TILE_PAD;                             // wraps for a tile at offset 0; only differences are used
-
-        // ---- stage [tb - 16, tb + TILE_BYTES + TILE_TAIL) ; bytes outside the text read as '\n'
-        for (int i = tid; i < TILE_SMEM / 16; i += TOK_THREADS) {
-            const int64_t a = (int64_t)tb - TILE_PAD + 16 * (int64_t)i;
-            uint4 v;
-            if (a >= 0 && (uint64_t)a + 16 <= p.text_len) {
-                v = __ldg(reinterpret_cast<const uint4*>(p.text + a));
-            } else {
-                uint32_t w[4] = {0x0A0A0A0Au, 0x0A0A0A0Au, 0x0A0A0A0Au, 0x0A0A0A0Au};
-                for (int b = 0; b < 16; ++b) {
-                    const int64_t q = a + b;
-                    if (q >= 0 && (uint64_t)q < p.text_len) {
-                        w[b >> 2] = (w[b >> 2] & ~(0xFFu << (8 * (b & 3)))) | ((uint32_t)p.text[q] << (8 * (b & 3)));
-                    }
-                }
-                v = make_uint4(w[0], w[1], w[2], w[3]);
-            }
-            reinterpret_cast<uint4*>(s_text)[i] = v;
+    const uint32_t slice = p.slice_bytes;
+    const uint32_t tile_bytes = slice * TOK_PARSE_WARPS;
+    const uint32_t tile_smem = TILE_PAD + tile_bytes + TILE_TAIL;
+    if (tid == 0) {
+        for (int b = 0; b < TOK_STAGES; ++b) {
+            mbar_init(&s_full[b], 1);
+            mbar_init(&s_counted[b], TOK_PARSE_WARPS);
+            mbar_init(&s_ready[b], 1);
+            mbar_init(&s_done[b], TOK_PARSE_WARPS);
         }
-        __syncthreads();
+        mbar_fence_init();
+    }
+    __syncthreads();
+    FlatSrc gsrc {p.text, p.text_len};
 
-        // ---- line starts: byte q starts a line iff text[q] != '\n' and text[q-1] == '\n'
-        // parse thread t owns bytes [128 t, 128 t + 128) of the tile; 16-byte loads rotated across the
-        // quarter-warp so that the eight lanes hit eight different bank groups.
-        uint64_t st_lo = 0, st_hi = 0;
-        uint32_t my_count = 0, incl = 0;
-        if (parser) {
-            uint64_t nl_lo = 0, nl_hi = 0;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const int g = (k + tid) & 7;
-                const uint4 v = *reinterpret_cast<const uint4*>(s_text + TILE_PAD + tid * 128 + g * 16);
-                const uint64_t m = newline_mask16(v);
-                if (g < 4) nl_lo |= m << (16 * g); else nl_hi |= m << (16 * (g - 4));
+    if (warp == 0) {
+        // ================================================================= service warp
+        auto issue_load = [&](int b, uint32_t tile) {
+            const uint64_t tb = p.tile0 + (uint64_t)tile * tile_bytes;
+            uint8_t* txt = s_dyn + (size_t)b * p.text_stride;
+            if (lane == 0) {
+                s_meta[b].tb = tb;
+                s_meta[b].tile = (int32_t)tile;
             }
-            const uint64_t prev_nl = s_text[TILE_PAD + tid * 128 - 1] == (uint8_t)'\n' ? 1ull : 0ull;
-            st_lo = ((nl_lo << 1) | prev_nl) & ~nl_lo;
-            st_hi = ((nl_hi << 1) | (nl_lo >> 63)) & ~nl_hi;
-            // restrict to the owned range [range_begin, range_end)
-            const uint64_t first = tb + (uint64_t)tid * 128;
-            if (first + 128 <= p.range_begin || first >= p.range_end) { st_lo = 0; st_hi = 0; }
-            else {
-                if (first < p.range_begin) {
-                    const int cut = (int)(p.range_begin - first);                 // 1..127 low bits dropped
-                    if (cut >= 64) { st_lo = 0; st_hi &= ~0ull << (cut - 64); } else st_lo &= ~0ull << cut;
+            // stage [tb - 16, tb + tile_bytes + TILE_TAIL); bytes outside the text read as '\n'
+            const bool interior = tb >= TILE_PAD && tb - TILE_PAD + tile_smem <= p.text_len;
+            if (interior) {
+                if (lane == 0) {
+                    fence_proxy_async();
+                    mbar_arrive_expect_tx(&s_full[b], tile_smem);
+                    bulk_load(txt, p.text + (tb - TILE_PAD), tile_smem, &s_full[b]);
                 }
-                if (first + 128 > p.range_end) {
-                    const int keep = (int)(p.range_end - first);                  // 1..127 low bits kept
-                    if (keep <= 64) { st_hi = 0; st_lo &= keep == 64 ? ~0ull : ((1ull << keep) - 1); }
-                    else st_hi &= (1ull << (keep - 64)) - 1;
+            } else {
+                for (uint32_t i = lane; i < tile_smem / 16; i += 32) {
+                    const int64_t a = (int64_t)tb - TILE_PAD + 16 * (int64_t)i;
+                    uint4 v;
+                    if (a >= 0 && (uint64_t)a + 16 <= p.text_len) {
+                        v = __ldg(reinterpret_cast<const uint4*>(p.text + a));
+                    } else {
+                        uint32_t w[4] = {0x0A0A0A0Au, 0x0A0A0A0Au, 0x0A0A0A0Au, 0x0A0A0A0Au};
+                        for (int k = 0; k < 16; ++k) {
+                            const int64_t q = a + k;
+                            if (q >= 0 && (uint64_t)q < p.text_len) {
+                                w[k >> 2] = (w[k >> 2] & ~(0xFFu << (8 * (k & 3)))) | ((uint32_t)p.text[q] << (8 * (k & 3)));
+                            }
+                        }
+                        v = make_uint4(w[0], w[1], w[2], w[3]);
+                    }
+                    reinterpret_cast<uint4*>(txt)[i] = v;
                 }
+                __syncwarp();
+                __threadfence_block();
+                if (lane == 0) mbar_arrive(&s_full[b]);
             }
-            my_count = __popcll(st_lo) + __popcll(st_hi);
-            incl = my_count;
+        };
+        uint32_t next_tile = 0;
+        if (lane == 0) next_tile = atomicAdd(p.tile_ticket, 1u);
+        next_tile = __shfl_sync(0xFFFFFFFFu, next_tile, 0);
+        if (next_tile < p.n_tiles) issue_load(0, next_tile);
+        for (uint32_t it = 0;; ++it) {
+            const int b = it % TOK_STAGES;
+            const uint32_t use = it / TOK_STAGES;
+            const uint32_t tile = next_tile;
+            if (tile >= p.n_tiles) {
+                if (lane == 0) {
+                    s_meta[b].tile = -1;
+                    __threadfence_block();
+                    mbar_arrive(&s_full[b]);
+                }
+                break;
+            }
+            // ---- prefetch: free the next stage, draw the next ticket, start its copy
+            {
+                const int nb = (it + 1) % TOK_STAGES;
+                if (it + 1 >= TOK_STAGES && !mbar_wait(&s_done[nb], ((it + 1) / TOK_STAGES - 1) & 1)) {
+                    if (lane == 0) report_error(p, 0, LINE_MALFORMED + 4);
+                    break;
+                }
+                uint32_t t = 0;
+                if (lane == 0) t = atomicAdd(p.tile_ticket, 1u);
+                next_tile = __shfl_sync(0xFFFFFFFFu, t, 0);
+                if (next_tile < p.n_tiles) issue_load(nb, next_tile);
+            }
+            const uint64_t tb = p.tile0 + (uint64_t)tile * tile_bytes;
+            // ---- the parse warps have counted the lines of their slices
+            if (!mbar_wait(&s_counted[b], use & 1)) {
+                if (lane == 0) report_error(p, tb, LINE_MALFORMED + 4);
+                break;
+            }
+            uint32_t cnt = lane < TOK_PARSE_WARPS ? s_meta[b].count[lane] : 0u;
+            uint32_t incl = cnt;
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
+            for (int d = 1; d < TOK_PARSE_WARPS; d <<= 1) {
                 const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, incl, d);
                 if (lane >= d) incl += o;
             }
-            if (lane == 31) s_warp_sums[warp] = incl;
-        }
-        __syncthreads();
-        uint32_t warp_off = 0, total = 0;
-#pragma unroll
-        for (int w = 0; w < TOK_PARSE_THREADS / 32; ++w) {
-            const uint32_t v = s_warp_sums[w];
-            if (w < warp) warp_off += v;
-            total += v;
-        }
-        if (parser) {
-            uint32_t idx = warp_off + incl - my_count;
-            uint64_t m = st_lo;
-            while (m) { const int b = __ffsll((long long)m) - 1; m &= m - 1; if (idx < TILE_MAX_LINES) s_starts[idx] = (uint16_t)(tid * 128 + b); ++idx; }
-            m = st_hi;
-            while (m) { const int b = __ffsll((long long)m) - 1; m &= m - 1; if (idx < TILE_MAX_LINES) s_starts[idx] = (uint16_t)(tid * 128 + 64 + b); ++idx; }
-        }
-        uint32_t n_lines = total;
-        if (n_lines > TILE_MAX_LINES) {                    // only possible with lines shorter than 8 bytes
-            if (tid == 0) report_error(p, tb, LINE_MALFORMED);
-            n_lines = TILE_MAX_LINES;
-        }
-        __syncthreads();
-
-        FlatSrc gsrc {p.text, p.text_len};
-        if (!parser) {
-            // ---- service warp: decoupled look-back over per-tile line counts (lane 0) and the
-            //      interned name of the tile's first line (lane 1), while the parse warps work
-            if (lane == 0) {
-                uint64_t base = 0;
-                if (tile == 0) {
-                    atomicExch(&p.tile_status[0], LB_FLAG_PREFIX | (unsigned long long)n_lines);
-                } else {
-                    atomicExch(&p.tile_status[tile], LB_FLAG_AGG | (unsigned long long)n_lines);
-                    uint32_t i = tile - 1;
-                    for (;;) {
-                        unsigned long long w;
-                        unsigned int spins = 0;
-                        do {
-                            w = *((volatile unsigned long long*)&p.tile_status[i]);
-                            if ((w >> 62) == 0 && ++spins > (1u << 24)) { report_error(p, tb, LINE_MALFORMED + 4); w = LB_FLAG_PREFIX; }
-                        } while ((w >> 62) == 0);
-                        base += w & LB_VALUE_MASK;
-                        if (w & LB_FLAG_PREFIX) break;
-                        --i;
+            if (lane < TOK_PARSE_WARPS) s_meta[b].prefix[lane] = incl - cnt;
+            const uint32_t n_lines = __shfl_sync(0xFFFFFFFFu, incl, TOK_PARSE_WARPS - 1);
+            // ---- decoupled look-back over the per-tile line counts, 32 predecessors per step
+            uint64_t base = 0;
+            bool lb_ok = true;
+            if (tile == 0) {
+                if (lane == 0) atomicExch(&p.tile_status[0], LB_FLAG_PREFIX | (unsigned long long)n_lines);
+            } else {
+                if (lane == 0) atomicExch(&p.tile_status[tile], LB_FLAG_AGG | (unsigned long long)n_lines);
+                int64_t look = (int64_t)tile - 1;
+                uint32_t polls = 0;
+                for (;;) {
+                    const int64_t i = look - lane;
+                    unsigned long long w = 2ull << 62;                                  // before tile 0: an empty prefix
+                    if (i >= 0) w = *((volatile unsigned long long*)&p.tile_status[i]);
+                    const uint32_t is_prefix = __ballot_sync(0xFFFFFFFFu, (w >> 63) != 0);
+                    const uint32_t is_empty = __ballot_sync(0xFFFFFFFFu, (w >> 62) == 0);
+                    const int fp = is_prefix ? __ffs((int)is_prefix) - 1 : 31;          // last lane that counts
+                    const uint32_t need = fp == 31 ? 0xFFFFFFFFu : ((2u << fp) - 1u);
+                    if (is_empty & need) {
+                        if (++polls > (1u << 22)) { lb_ok = false; break; }
+                        continue;
                     }
-                    atomicExch(&p.tile_status[tile], LB_FLAG_PREFIX | (unsigned long long)(base + n_lines));
+                    unsigned long long v = lane <= fp ? (w & LB_VALUE_MASK) : 0ull;
+#pragma unroll
+                    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, d);
+                    base += v;
+                    if (is_prefix) break;
+                    look -= 32;
                 }
-                s_base = base;
-                if (tile == p.n_tiles - 1) *p.n_sites = base + n_lines;
-            } else if (lane == 1) {
-                uint32_t ref = 0;
-                if (n_lines > 0) {
-                    // only a name that starts at the first byte of the line can be shared (same_name_as_first)
-                    const uint64_t nabs = tb + s_starts[0];
-                    uint64_t q = nabs;
-                    uint8_t c = gsrc.at(q);
-                    while (!is_delim(c) && !is_eol(c)) c = gsrc.at(++q);
-                    const uint32_t len = (uint32_t)(q - nabs);
-                    if (len > 0 && is_delim(c)) ref = name_intern(p.names, gsrc, nabs, len);
-                }
-                s_name0_ref = ref;
+                if (lane == 0) atomicExch(&p.tile_status[tile], LB_FLAG_PREFIX | (unsigned long long)(base + n_lines));
+            }
+            if (!lb_ok && lane == 0) report_error(p, tb, LINE_MALFORMED + 4);
+            if (tile == p.n_tiles - 1 && lane == 0) *p.n_sites = base + n_lines;
+            __syncwarp();
+            if (lane == 0) {
+                s_meta[b].base = base;
+                __threadfence_block();
+                mbar_arrive(&s_ready[b]);               // base and prefixes are published
             }
             __syncwarp();
-            __threadfence_block();
-            if (lane == 0) *((volatile uint32_t*)&s_ready) = tile + 1;     // publishes s_base and s_name0_ref to the parse warps
-            continue;
         }
+        return;
+    }
 
-        // ---- parse warps: groups of 32 consecutive lines, one line per lane.  Every lane runs the
-        //      tokenizer (lanes past the end re-parse the group's first line and drop the result)
-        //      so that the warp reconverges inside it.
-        const uint32_t l0_off = n_lines ? TILE_PAD + s_starts[0] : 0;
-        const uint2 first8 = n_lines ? load8_unaligned(s_text, l0_off) : make_uint2(0, 0);
+    // ===================================================================== parse warps
+    const int pw = warp - 1;                               // slice index
+    uint32_t cache_len = 0, cache_ref = 0;                 // name of the previous first line of this warp (lane 0)
+    uint4 cache_name = make_uint4(0, 0, 0, 0);
+    for (uint32_t it = 0;; ++it) {
+        const int b = it % TOK_STAGES;
+        const uint32_t use = it / TOK_STAGES;
+        if (!mbar_wait(&s_full[b], use & 1)) {
+            if (lane == 0) report_error(p, 0, LINE_MALFORMED + 4);
+            break;
+        }
+        if (s_meta[b].tile < 0) break;
+        const uint8_t* txt = s_dyn + (size_t)b * p.text_stride;
+        uint16_t* starts = reinterpret_cast<uint16_t*>(s_dyn + (size_t)TOK_STAGES * p.text_stride) +
+                           ((size_t)b * TOK_PARSE_WARPS + pw) * p.lines_cap;
+        const uint64_t tb = s_meta[b].tb;
+        const uint64_t abs0 = tb - TILE_PAD;              // wraps for a tile at offset 0; only differences are used
+        // ---- line starts of this warp's slice: byte q starts a line iff text[q] != '\n' and text[q-1] == '\n'.
+        // 16-byte unit u of the slice is scanned by lane u % 32 in round u / 32.
+        uint32_t n_lines = 0;
+        {
+            const uint32_t units = slice / 16;
+            const uint32_t slice_off = (uint32_t)pw * slice;           // offset of the slice inside the tile
+            for (uint32_t u0 = 0; u0 < units; u0 += 32) {
+                const uint32_t u = u0 + lane;
+                uint32_t st = 0;
+                if (u < units) {
+                    const uint8_t* up = txt + TILE_PAD + slice_off + u * 16;
+                    const uint32_t nl = newline_mask16(*reinterpret_cast<const uint4*>(up));
+                    const uint32_t prev_nl = up[-1] == (uint8_t)'\n' ? 1u : 0u;
+                    st = ((nl << 1) | prev_nl) & ~nl & 0xFFFFu;
+                    // restrict to the owned range [range_begin, range_end)
+                    const uint64_t first = tb + slice_off + u * 16;
+                    if (first + 16 <= p.range_begin || first >= p.range_end) st = 0;
+                    else {
+                        if (first < p.range_begin) st &= 0xFFFFu << (uint32_t)(p.range_begin - first);
+                        if (first + 16 > p.range_end) st &= (1u << (uint32_t)(p.range_end - first)) - 1u;
+                    }
+                }
+                const uint32_t my_count = __popc(st);
+                uint32_t incl = my_count;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+                    if (lane >= d) incl += o;
+                }
+                uint32_t idx = n_lines + incl - my_count;
+                while (st) {
+                    const int bit = __ffs((int)st) - 1;
+                    st &= st - 1;
+                    if (idx < p.lines_cap) starts[idx] = (uint16_t)(slice_off + u * 16 + bit);
+                    ++idx;
+                }
+                n_lines += __shfl_sync(0xFFFFFFFFu, incl, 31);
+            }
+            if (n_lines > p.lines_cap) {                   // only possible with lines shorter than 8 bytes
+                if (lane == 0) report_error(p, tb, LINE_MALFORMED);
+                n_lines = p.lines_cap;
+            }
+            __syncwarp();
+            if (lane == 0) {
+                s_meta[b].count[pw] = n_lines;
+                __threadfence_block();
+                mbar_arrive(&s_counted[b]);
+            }
+        }
+        // ---- the name of the slice's first line, interned by lane 0 (kept in registers from tile to tile,
+        //      so the dictionary is only consulted when the name changes)
+        uint32_t l0_off = 0, name0_ref = 0;
+        uint2 first8 = make_uint2(0, 0);
+        if (n_lines) {
+            l0_off = TILE_PAD + starts[0];
+            first8 = load8_unaligned(txt, l0_off);
+            if (lane == 0) {
+                // only a name that starts at the first byte of the line can be shared (same_name_as_first)
+                uint32_t q = l0_off;
+                uint8_t c = txt[q];
+                while (!is_delim(c) && !is_eol(c) && q < tile_smem - 1) c = txt[++q];
+                const uint32_t len = q - l0_off;
+                if (len > 0 && is_delim(c)) {
+                    uint4 nm = make_uint4(0, 0, 0, 0);
+                    if (len <= 16) {
+                        const uint2 hi = load8_unaligned(txt, l0_off + 8);
+                        uint32_t wds[4] = {first8.x, first8.y, hi.x, hi.y};
+                        for (int k = 0; k < 4; ++k) {
+                            const int rem = (int)len - 4 * k;
+                            if (rem <= 0) wds[k] = 0; else if (rem < 4) wds[k] &= (1u << (8 * rem)) - 1u;
+                        }
+                        nm = make_uint4(wds[0], wds[1], wds[2], wds[3]);
+                    }
+                    if (len <= 16 && len == cache_len && cache_ref && nm.x == cache_name.x && nm.y == cache_name.y &&
+                        nm.z == cache_name.z && nm.w == cache_name.w) {
+                        name0_ref = cache_ref;
+                    } else {
+                        SmemBytes sb {txt, abs0};
+                        name0_ref = name_intern(p.names, sb, tb + starts[0], len);
+                        if (len <= 16) { cache_len = len; cache_ref = name0_ref; cache_name = nm; }
+                    }
+                }
+            }
+            name0_ref = __shfl_sync(0xFFFFFFFFu, name0_ref, 0);
+        }
+        // ---- groups of 32 consecutive lines, one line per lane.  Every lane runs the tokenizer (lanes
+        //      past the end re-parse the group's first line and drop the result) so that the warp
+        //      reconverges inside it.
         bool have_base = false;
         uint64_t base = 0;
-        uint32_t name0_ref = 0;
-        for (uint32_t g = warp * 32; g < n_lines; g += TOK_PARSE_THREADS) {
+        for (uint32_t g = 0; g < n_lines; g += 32) {
             const uint32_t j = g + lane;
             const bool mine = j < n_lines;
-            const uint32_t off = s_starts[mine ? j : g];
+            const uint32_t off = starts[mine ? j : g];
             const uint64_t line_abs = tb + off;
             LineResult r;
+            r.status = LINE_MALFORMED;
             bool fast = false;
             if (FAST && !p.want_qual) {
                 FastLine fl;
-                fast = parse_line_fast_smem(s_text, abs0, TILE_SMEM, line_abs, fl);
+                fast = parse_line_fast_smem(txt, abs0, tile_smem, line_abs, fl);
                 r.status = fl.status; r.pos = fl.pos; r.profile = fl.profile; r.chrom_off = fl.chrom_off; r.chrom_len = fl.chrom_len;
             }
             if (!fast && mine) {
-                SmemSrc ssrc {s_text, abs0, (uint32_t)TILE_SMEM, false};
+                SmemSrc ssrc {txt, abs0, tile_smem, false};
                 ParsedLine pl;
                 parse_line(ssrc, line_abs, p.want_qual != 0, pl);
                 if (ssrc.overrun) parse_line(gsrc, line_abs, p.want_qual != 0, pl);
@@ -298,14 +429,14 @@ __global__ void __launch_bounds__(TOK_THREADS) k_tokenize(const TokParams p) {
             bool same = false;
             uint32_t slot = 0;
             if (good) {
-                same = r.chrom_off == 0 && same_name_as_first(s_text, TILE_PAD + off, r.chrom_len, l0_off, first8);
+                same = name0_ref && r.chrom_off == 0 && same_name_as_first(txt, TILE_PAD + off, r.chrom_len, l0_off, first8);
                 if (p.use_table) slot = table_find_or_insert(p.table, r.profile);
             }
-            if (!have_base) {                              // wait for the service warp (usually long done)
-                while (*((volatile uint32_t*)&s_ready) != tile + 1) { }
-                __threadfence_block();
-                base = *((volatile uint64_t*)&s_base);
-                name0_ref = *((volatile uint32_t*)&s_name0_ref);
+            if (!have_base) {                              // the service warp has usually long published it
+                if (!mbar_wait(&s_ready[b], use & 1)) {
+                    if (lane == 0) report_error(p, tb, LINE_MALFORMED + 4);
+                }
+                base = s_meta[b].base + s_meta[b].prefix[pw];
                 have_base = true;
             }
             if (mine && r.status != LINE_OK) report_error(p, line_abs, r.status);
@@ -313,7 +444,7 @@ __global__ void __launch_bounds__(TOK_THREADS) k_tokenize(const TokParams p) {
                 const uint64_t site = p.site_base + base + j;
                 if (site >= p.site_cap) { report_error(p, line_abs, LINE_MALFORMED + 5); }
                 else {
-                    const uint32_t ref = (same && name0_ref) ? name0_ref : name_intern(p.names, gsrc, line_abs + r.chrom_off, r.chrom_len);
+                    const uint32_t ref = same ? name0_ref : name_intern(p.names, gsrc, line_abs + r.chrom_off, r.chrom_len);
                     p.pos[site] = r.pos;
                     p.name_ref[site] = ref;
                     if (p.profile) p.profile[site] = r.profile;
@@ -322,6 +453,9 @@ __global__ void __launch_bounds__(TOK_THREADS) k_tokenize(const TokParams p) {
                 }
             }
         }
+        if (!have_base) mbar_wait(&s_ready[b], use & 1);   // keep the phase of s_ready in step for every warp
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_done[b]);            // this warp is finished with the stage
     }
 }
 

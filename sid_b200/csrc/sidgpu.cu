@@ -64,6 +64,7 @@ struct sidgpu_ctx {
     std::string err;
     uint64_t launches = 0;
     size_t max_chunk = 0;
+    double avg_line_bytes = 80.0;    // running estimate, sizes the tokenizer's slices
 
     Control* d_ctl = nullptr;
     Control* h_ctl = nullptr;
@@ -356,7 +357,11 @@ int run_tokenizer(sidgpu_ctx* ctx, const char* d_text, size_t text_len, size_t r
     if (range_begin == range_end) return SIDGPU_OK;
     const uint64_t tile0 = range_begin & ~(uint64_t)15;
     const uint64_t span = range_end - tile0;
-    const uint64_t n_tiles64 = (span + TILE_BYTES - 1) / TILE_BYTES;
+    // a slice (one parse warp's share of a tile) should hold about 30 lines: 32 lanes, little overflow
+    uint32_t slice = (uint32_t)(ctx->avg_line_bytes * 29.5) & ~15u;
+    slice = std::max<uint32_t>(SLICE_MIN, std::min<uint32_t>(SLICE_MAX, slice));
+    const uint64_t tile_bytes = (uint64_t)slice * TOK_PARSE_WARPS;
+    const uint64_t n_tiles64 = (span + tile_bytes - 1) / tile_bytes;
     if (n_tiles64 > 0x7FFFFFFFull) return ctx->fail(SIDGPU_EINVAL, "range too large");
     const uint32_t n_tiles = (uint32_t)n_tiles64;
     TRY(ensure(ctx, ctx->tile_status, (size_t)n_tiles * 8));
@@ -391,12 +396,18 @@ int run_tokenizer(sidgpu_ctx* ctx, const char* d_text, size_t text_len, size_t r
         p.use_table = use_table ? 1 : 0;
         p.count_profiles = 0;
         p.want_qual = want_qual ? 1 : 0;
-        const int max_ctas = ctx->sm_count * 5;
+        p.slice_bytes = slice;
+        p.text_stride = tok_text_stride(slice);
+        p.lines_cap = slice / 8;
+        const uint32_t dyn_smem = tok_dyn_smem(slice);
+        int per_sm = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tokenize<true>, TOK_THREADS, dyn_smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+        const int max_ctas = ctx->sm_count * per_sm;
         const unsigned grid = (unsigned)std::min<uint64_t>(n_tiles, (uint64_t)max_ctas);
         {
             ProfScope prof(ctx, PROF_TOKENIZE);
-            if (want_qual) k_tokenize<false><<<grid, TOK_THREADS, 0, ctx->stream>>>(p);
-            else k_tokenize<true><<<grid, TOK_THREADS, 0, ctx->stream>>>(p);
+            if (want_qual) k_tokenize<false><<<grid, TOK_THREADS, dyn_smem, ctx->stream>>>(p);
+            else k_tokenize<true><<<grid, TOK_THREADS, dyn_smem, ctx->stream>>>(p);
         }
         TRY(check_launch(ctx, "k_tokenize"));
         TRY(sync_ctl(ctx));
@@ -419,6 +430,7 @@ int run_tokenizer(sidgpu_ctx* ctx, const char* d_text, size_t text_len, size_t r
             continue;
         }
         *n_out = c.n_sites;
+        if (c.n_sites >= 64) ctx->avg_line_bytes = (double)(range_end - range_begin) / (double)c.n_sites;   // sizes the slices of the next call
         // keep the load factor below one half for the next chunk
         while ((uint64_t)c.n_entries * 2 > ctx->tab.cap) TRY(grow_table(ctx, 2, site_base + c.n_sites));
         return SIDGPU_OK;
@@ -703,8 +715,10 @@ int sidgpu_create(const sidgpu_config* cfg, sidgpu_ctx** out) {
         cudaMemcpyAsync(ctx->quality_lut.p, lut.data(), lut.size() * 8, cudaMemcpyHostToDevice, ctx->stream);
         cudaStreamSynchronize(ctx->stream);
     }
-    if ((e = cudaFuncSetAttribute(k_csv, cudaFuncAttributeMaxDynamicSharedMemorySize, CSV_STAGE)) != cudaSuccess) {
-        ctx->err = std::string("k_csv shared memory opt-in: ") + cudaGetErrorString(e);
+    if ((e = cudaFuncSetAttribute(k_tokenize<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tok_dyn_smem(SLICE_MAX))) != cudaSuccess ||
+        (e = cudaFuncSetAttribute(k_tokenize<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tok_dyn_smem(SLICE_MAX))) != cudaSuccess ||
+        (e = cudaFuncSetAttribute(k_csv, cudaFuncAttributeMaxDynamicSharedMemorySize, CSV_STAGE)) != cudaSuccess) {
+        ctx->err = std::string("shared memory opt-in: ") + cudaGetErrorString(e);
         return bail(SIDGPU_ECUDA);
     }
     if ((e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) { ctx->err = cudaGetErrorString(e); return bail(SIDGPU_ECUDA); }
