@@ -273,6 +273,7 @@ __global__ void __launch_bounds__(TOK_THREADS) k_tokenize(const TokParams p) {
                     const uint32_t need = fp == 31 ? 0xFFFFFFFFu : ((2u << fp) - 1u);
                     if (is_empty & need) {
                         if (++polls > (1u << 22)) { lb_ok = false; break; }
+                        __nanosleep(100);
                         continue;
                     }
                     unsigned long long v = lane <= fp ? (w & LB_VALUE_MASK) : 0ull;
@@ -320,6 +321,7 @@ __global__ void __launch_bounds__(TOK_THREADS) k_tokenize(const TokParams p) {
         {
             const uint32_t units = slice / 16;
             const uint32_t slice_off = (uint32_t)pw * slice;           // offset of the slice inside the tile
+            const bool inside = tb + slice_off >= p.range_begin && tb + slice_off + slice <= p.range_end;   // the usual case
             for (uint32_t u0 = 0; u0 < units; u0 += 32) {
                 const uint32_t u = u0 + lane;
                 uint32_t st = 0;
@@ -328,12 +330,13 @@ __global__ void __launch_bounds__(TOK_THREADS) k_tokenize(const TokParams p) {
                     const uint32_t nl = newline_mask16(*reinterpret_cast<const uint4*>(up));
                     const uint32_t prev_nl = up[-1] == (uint8_t)'\n' ? 1u : 0u;
                     st = ((nl << 1) | prev_nl) & ~nl & 0xFFFFu;
-                    // restrict to the owned range [range_begin, range_end)
-                    const uint64_t first = tb + slice_off + u * 16;
-                    if (first + 16 <= p.range_begin || first >= p.range_end) st = 0;
-                    else {
-                        if (first < p.range_begin) st &= 0xFFFFu << (uint32_t)(p.range_begin - first);
-                        if (first + 16 > p.range_end) st &= (1u << (uint32_t)(p.range_end - first)) - 1u;
+                    if (!inside) {                                     // restrict to the owned range [range_begin, range_end)
+                        const uint64_t first = tb + slice_off + u * 16;
+                        if (first + 16 <= p.range_begin || first >= p.range_end) st = 0;
+                        else {
+                            if (first < p.range_begin) st &= 0xFFFFu << (uint32_t)(p.range_begin - first);
+                            if (first + 16 > p.range_end) st &= (1u << (uint32_t)(p.range_end - first)) - 1u;
+                        }
                     }
                 }
                 const uint32_t my_count = __popc(st);
@@ -363,41 +366,12 @@ __global__ void __launch_bounds__(TOK_THREADS) k_tokenize(const TokParams p) {
                 mbar_arrive(&s_counted[b]);
             }
         }
-        // ---- the name of the slice's first line, interned by lane 0 (kept in registers from tile to tile,
-        //      so the dictionary is only consulted when the name changes)
+        // ---- the slice's first line: its name is shared by (almost) all lines of the slice
         uint32_t l0_off = 0, name0_ref = 0;
         uint2 first8 = make_uint2(0, 0);
         if (n_lines) {
             l0_off = TILE_PAD + starts[0];
             first8 = load8_unaligned(txt, l0_off);
-            if (lane == 0) {
-                // only a name that starts at the first byte of the line can be shared (same_name_as_first)
-                uint32_t q = l0_off;
-                uint8_t c = txt[q];
-                while (!is_delim(c) && !is_eol(c) && q < tile_smem - 1) c = txt[++q];
-                const uint32_t len = q - l0_off;
-                if (len > 0 && is_delim(c)) {
-                    uint4 nm = make_uint4(0, 0, 0, 0);
-                    if (len <= 16) {
-                        const uint2 hi = load8_unaligned(txt, l0_off + 8);
-                        uint32_t wds[4] = {first8.x, first8.y, hi.x, hi.y};
-                        for (int k = 0; k < 4; ++k) {
-                            const int rem = (int)len - 4 * k;
-                            if (rem <= 0) wds[k] = 0; else if (rem < 4) wds[k] &= (1u << (8 * rem)) - 1u;
-                        }
-                        nm = make_uint4(wds[0], wds[1], wds[2], wds[3]);
-                    }
-                    if (len <= 16 && len == cache_len && cache_ref && nm.x == cache_name.x && nm.y == cache_name.y &&
-                        nm.z == cache_name.z && nm.w == cache_name.w) {
-                        name0_ref = cache_ref;
-                    } else {
-                        SmemBytes sb {txt, abs0};
-                        name0_ref = name_intern(p.names, sb, tb + starts[0], len);
-                        if (len <= 16) { cache_len = len; cache_ref = name0_ref; cache_name = nm; }
-                    }
-                }
-            }
-            name0_ref = __shfl_sync(0xFFFFFFFFu, name0_ref, 0);
         }
         // ---- groups of 32 consecutive lines, one line per lane.  Every lane runs the tokenizer (lanes
         //      past the end re-parse the group's first line and drop the result) so that the warp
@@ -426,6 +400,34 @@ __global__ void __launch_bounds__(TOK_THREADS) k_tokenize(const TokParams p) {
             }
             __syncwarp();
             const bool good = mine && r.status == LINE_OK;
+            if (g == 0) {
+                // lane 0 holds the slice's first line: intern its name once (kept in registers from tile
+                // to tile, so the dictionary is only consulted when the name changes); only a name that
+                // starts at the first byte of the line can be shared (same_name_as_first)
+                if (lane == 0 && good && r.chrom_off == 0) {
+                    const uint32_t len = r.chrom_len;
+                    uint4 nm = make_uint4(0, 0, 0, 0);
+                    if (len <= 16) {
+                        const uint2 hi = load8_unaligned(txt, l0_off + 8);
+                        uint32_t wds[4] = {first8.x, first8.y, hi.x, hi.y};
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const int rem = (int)len - 4 * k;
+                            if (rem <= 0) wds[k] = 0; else if (rem < 4) wds[k] &= (1u << (8 * rem)) - 1u;
+                        }
+                        nm = make_uint4(wds[0], wds[1], wds[2], wds[3]);
+                    }
+                    if (len <= 16 && len == cache_len && cache_ref && nm.x == cache_name.x && nm.y == cache_name.y &&
+                        nm.z == cache_name.z && nm.w == cache_name.w) {
+                        name0_ref = cache_ref;
+                    } else {
+                        SmemBytes sb {txt, abs0};
+                        name0_ref = name_intern(p.names, sb, line_abs, len);
+                        if (len <= 16) { cache_len = len; cache_ref = name0_ref; cache_name = nm; }
+                    }
+                }
+                name0_ref = __shfl_sync(0xFFFFFFFFu, name0_ref, 0);
+            }
             bool same = false;
             uint32_t slot = 0;
             if (good) {

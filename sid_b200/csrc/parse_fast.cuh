@@ -4,7 +4,9 @@
 // and on adversarial random lines.
 //
 //   parsePileupLine  pileup.cpp:13-68   header: chrom \t pos \t ref \t depth \t  (single delimiters,
-//                                       1..9 digit unsigned position)
+//                                       1..9 digit unsigned position, all within the first 31 bytes):
+//                                       a 32-bit mask of the bytes <= 0x20 locates the four separators,
+//                                       the position is converted eight digits at a time
 //   parseReadBases   pileup.cpp:70-153  bases field, 4 bytes per step:
 //       - bytes outside [0x21,0x7f] end the field (tab/space/newline/NUL) or refuse the line
 //       - '^' masks the following byte without a branch; "^^" refuses
@@ -41,6 +43,21 @@ SID_HD uint32_t add_flags(uint32_t f7, uint32_t acc) {
 #endif
 }
 
+SID_HD uint32_t pop_count(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+    return (uint32_t)__popc(x);
+#else
+    return (uint32_t)__builtin_popcount(x);
+#endif
+}
+SID_HD uint32_t first_bit(uint32_t x) {        // index of the lowest set bit; 32 when x == 0
+#if defined(__CUDA_ARCH__)
+    return x ? (uint32_t)(__ffs((int)x) - 1) : 32u;
+#else
+    return x ? (uint32_t)__builtin_ctz(x) : 32u;
+#endif
+}
+
 SID_HD int first_flag_byte(uint32_t f7) {   // index of the lowest byte whose bit 7 is set; f7 != 0
 #if defined(__CUDA_ARCH__)
     return (__ffs((int)f7) - 1) >> 3;
@@ -72,51 +89,80 @@ SID_HD uint32_t eq7(uint32_t x, uint32_t pat, uint32_t excl) {
 // clears `ok` and lets the lane idle to the next reconvergence point.
 SID_HD bool parse_line_fast_smem(const uint8_t* s, uint64_t abs0, uint32_t avail, uint64_t line_abs, FastLine& o) {
     const uint32_t start = (uint32_t)(line_abs - abs0);
-    bool ok = start + 64 <= avail;
+    bool ok = start + 64 <= avail && start >= 12;
     const uint32_t safe_end = avail - 8;
-    uint32_t i = ok ? start : 0;
-    uint32_t c;
-    // ---- chromosome name
-    c = s[i];
-    ok = ok && c > 0x20;
-    do { c = s[++i]; } while (c > 0x20 && i < safe_end);
-    ok = ok && (c == '\t' || c == ' ');
-    o.chrom_off = 0;
-    o.chrom_len = i - start;
-    if (i >= safe_end) i = safe_end - 16;     // refused already; keeps the remaining header reads in bounds
-    ++i;
-    // ---- position: 1..9 digits
-    uint32_t acc = 0, nd = 0;
-    for (;;) {
-        const uint32_t d = (uint32_t)s[i] - (uint32_t)'0';
-        if (d > 9 || nd > 9) break;
-        acc = acc * 10 + d;
-        ++i;
-        ++nd;
+    const uint32_t* sw = reinterpret_cast<const uint32_t*>(s);
+    // ---- header: the first 32 bytes of the line as eight words; a bit mask of the bytes <= 0x20
+    //      locates the four separators after chrom, pos, ref and depth
+    const uint32_t h0 = ok ? start : 16;
+    uint32_t sepmask = 0;
+    {
+        const uint32_t* hw = sw + (h0 >> 2);
+        const uint32_t hs = (h0 & 3) * 8;
+        uint32_t prev = hw[0];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const uint32_t next = hw[k + 1];
+            const uint32_t w = funnel_r(prev, next, hs);
+            prev = next;
+            const uint32_t sep7 = ~((w | M80) - NEUTRAL) & ~w & M80;     // bit 7 set iff the byte is <= 0x20
+            sepmask |= ((sep7 * 0x00204081u) >> 28) << (4 * k);
+        }
     }
-    ok = ok && nd >= 1 && nd <= 9;
-    c = s[i];
-    ok = ok && (c == '\t' || c == ' ');
-    ++i;
-    // ---- reference base: exactly one character
-    const uint32_t ref = s[i];
-    ok = ok && ref > 0x20;
-    c = s[++i];
-    ok = ok && (c == '\t' || c == ' ');
-    ++i;
-    // ---- depth column: skipped
-    c = s[i];
-    ok = ok && c > 0x20 && i < safe_end;
-    if (i >= safe_end) i = safe_end;
-    do { c = s[++i]; } while (c > 0x20 && i < safe_end);
-    ok = ok && (c == '\t' || c == ' ');
-    ++i;
-    ok = ok && i < safe_end && s[i] > 0x20;      // empty bases field or doubled delimiter
-    if (i >= safe_end) i = safe_end;
+    ok = ok && pop_count(sepmask) >= 4;
+    uint32_t m = sepmask;
+    const uint32_t p1 = first_bit(m); m &= m - 1;
+    const uint32_t p2 = first_bit(m); m &= m - 1;
+    const uint32_t p3 = first_bit(m); m &= m - 1;
+    const uint32_t p4 = first_bit(m);
+    const uint32_t nd = p2 - p1 - 1;
+    // chrom non-empty, 1..9 digits, one reference character, depth non-empty, bases non-empty within reach
+    ok = ok && p1 >= 1 && nd >= 1 && nd <= 9 && p3 == p2 + 2 && p4 > p3 + 1 && p4 <= 30 && ((sepmask >> (p4 + 1)) & 1u) == 0;
+    if (!ok) { /* keep every read below in bounds */ }
+    const uint32_t q1 = ok ? p1 : 1, q2 = ok ? p2 : 3, q3 = ok ? p3 : 5, q4 = ok ? p4 : 7;
+    {
+        const uint32_t c1 = s[h0 + q1], c2 = s[h0 + q2], c3 = s[h0 + q3], c4 = s[h0 + q4];
+        ok = ok && (c1 == '\t' || c1 == ' ') && (c2 == '\t' || c2 == ' ') && (c3 == '\t' || c3 == ' ') && (c4 == '\t' || c4 == ' ');
+    }
+    o.chrom_off = 0;
+    o.chrom_len = q1;
+    const uint32_t ref = s[h0 + q2 + 1];
+    // ---- position: the (up to) eight characters before the second separator, leading ones forced to '0'
+    uint32_t acc;
+    {
+        const uint32_t e = h0 + q2;                           // offset of the separator after the digits
+        const uint32_t ndd = ok ? nd : 1;
+        const uint32_t* pw = sw + ((e - 8) >> 2);
+        const uint32_t ps = ((e - 8) & 3) * 8;
+        const uint32_t w0 = pw[0], w1 = pw[1], w2 = pw[2];
+        uint32_t lo = funnel_r(w0, w1, ps), hi = funnel_r(w1, w2, ps);
+        const uint32_t zero = ndd >= 8 ? 0u : 8u - ndd;       // leading bytes that are not digits of this number
+        if (zero >= 4) {
+            lo = 0x30303030u;
+            const uint32_t mz = zero == 4 ? 0u : ((1u << (8 * (zero - 4))) - 1u);
+            hi = (hi & ~mz) | (0x30303030u & mz);
+        } else if (zero) {
+            const uint32_t mz = (1u << (8 * zero)) - 1u;
+            lo = (lo & ~mz) | (0x30303030u & mz);
+        }
+        const bool dig = ((lo & 0xF0F0F0F0u) == 0x30303030u) && ((hi & 0xF0F0F0F0u) == 0x30303030u) &&
+                         ((((lo & 0x0F0F0F0Fu) + 0x06060606u) | ((hi & 0x0F0F0F0Fu) + 0x06060606u)) & 0x10101010u) == 0;
+        ok = ok && dig;
+        const uint32_t xl = lo & 0x0F0F0F0Fu, xh = hi & 0x0F0F0F0Fu;
+        const uint32_t tl = xl * 10u + (xl >> 8), th = xh * 10u + (xh >> 8);
+        const uint32_t vl = (tl & 0xFFu) * 100u + ((tl >> 16) & 0xFFu), vh = (th & 0xFFu) * 100u + ((th >> 16) & 0xFFu);
+        acc = vl * 10000u + vh;
+        if (ndd == 9) {
+            const uint32_t d9 = (uint32_t)s[e - 9] - (uint32_t)'0';
+            ok = ok && d9 <= 9;
+            acc += d9 * 100000000u;
+        }
+    }
+    uint32_t i = h0 + q4 + 1;                                  // first byte of the bases field
+    if (i >= safe_end) { ok = false; i = 16; }
     SID_SYNCWARP();
 
     // ---- bases field, one 32-bit word per step
-    const uint32_t* sw = reinterpret_cast<const uint32_t*>(s);
     const uint32_t n_words = avail >> 2;
     uint32_t idx = i >> 2;
     uint32_t sh = (i & 3) * 8;
@@ -210,15 +256,18 @@ SID_HD bool parse_line_fast_smem(const uint8_t* s, uint64_t abs0, uint32_t avail
 #if !defined(__CUDACC__)
 // Flat-buffer entry used by the host checks only: stages the line into an aligned scratch copy.
 inline bool parse_line_fast(const uint8_t* text, uint64_t len, uint64_t p, FastLine& o) {
-    // the caller guarantees text is readable up to a multiple of 16 past len (padding reads as '\n')
-    const uint64_t abs0 = p & ~(uint64_t)15;
+    // like a staged tile: 16 bytes of lead-in before the aligned start, '\n' outside the text
+    const int64_t first = (int64_t)(p & ~(uint64_t)15) - 16;
     uint64_t end = p;
     while (end < len && text[end] != '\n') ++end;
-    const uint64_t avail64 = ((end - abs0) + 64 + 15) & ~(uint64_t)15;
+    const uint64_t avail64 = (((int64_t)end - first) + 64 + 15) & ~(uint64_t)15;
     if (avail64 > (1u << 20)) return false;
     static thread_local uint8_t scratch[(1u << 20) + 64] __attribute__((aligned(16)));
-    for (uint64_t k = 0; k < avail64; ++k) scratch[k] = abs0 + k < len ? text[abs0 + k] : (uint8_t)'\n';
-    return parse_line_fast_smem(scratch, abs0, (uint32_t)avail64, p, o);
+    for (uint64_t k = 0; k < avail64; ++k) {
+        const int64_t q = first + (int64_t)k;
+        scratch[k] = (q >= 0 && (uint64_t)q < len) ? text[q] : (uint8_t)'\n';
+    }
+    return parse_line_fast_smem(scratch, (uint64_t)first, (uint32_t)avail64, p, o);
 }
 #endif
 

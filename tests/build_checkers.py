@@ -13,7 +13,7 @@ def build_hostcheck(force=False):
     out = os.path.join(ROOT, "tests", "hostcheck", "libhostcheck.so")
     srcs = _glob("sid_b200/csrc", (".cuh",)) + [os.path.join(ROOT, "tests", "hostcheck", "hostcheck.cpp")]
     if force or _newer(out, srcs):
-        _run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-DSID_HAVE_FAST", "-x", "c++",
+        _run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-Wno-unknown-pragmas", "-DSID_HAVE_FAST", "-x", "c++",
               "tests/hostcheck/hostcheck.cpp", "-o", out])
     return out
 
