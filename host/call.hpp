@@ -1,0 +1,62 @@
+// Host mirror of the reference's calling interface (call.hpp:12-43): same names, argument order
+// and meaning, same error behaviour; the work runs on the GPU through libsidgpu.
+#pragma once
+#include <array>
+#include <iostream>
+#include <string>
+#include <vector>
+
+#include "pileup.hpp"
+
+std::vector<PileupLine> readFile(std::istream& in, bool parse_base_qualities, bool parse_mapping_qualities);   // call.hpp:12
+
+typedef struct {                                      // call.hpp:14-21
+    std::string label {"none"};
+    std::string genotype {"NN"};
+    double confidence_homozygous;
+    double confidence_heterozygous;
+    std::string confidence_type {"unspecified"};
+    std::vector<std::string> additional_data;
+} Classification;
+
+typedef struct {                                      // call.hpp:23-27
+    std::string chromosome_name;
+    int position;
+    Classification classification;
+} OutputRecord;
+
+inline std::ostream& operator<<(std::ostream& os, const OutputRecord& r) {   // call.hpp:29-38
+    os << r.chromosome_name;
+    os << ',' << r.position;
+    os << ',' << r.classification.label;
+    os << ',' << r.classification.genotype;
+    os << ',' << r.classification.confidence_homozygous;
+    os << ',' << r.classification.confidence_heterozygous;
+    os << ',' << r.classification.confidence_type;
+    return os;
+}
+
+// call.hpp:40-43
+std::vector<OutputRecord> callLikelihoodRatio(std::istream& in, const bool use_prior, const double significance_level);
+std::vector<OutputRecord> callBayes(std::istream& in);
+std::vector<OutputRecord> callSiteMLError(std::istream& in, const bool estimate_prior, double prior, double error_threshold, const double significance_level);
+std::vector<OutputRecord> callQualityBasedSimple(std::istream& in, const bool estimate_prior, double prior, const double significance_level);
+
+// ---- beyond the reference: the streaming form the `sid` binary uses --------------------------------
+struct SidRunInfo {
+    uint64_t n_sites = 0, n_rows = 0;
+    bool has_fit = false;
+    double heterozygosity = 0, error_rate = 0;
+    int iterations = 0;
+    bool converged = false;
+    uint64_t unique_profiles = 0;
+};
+// Runs `method` ("local", "bayes", "likelihood_ratio", "quality") over a whole pileup text and writes
+// `header` (when not null, followed by std::endl as in sid.cpp:102) and then the CSV rows to `out`
+// -- like the reference nothing is printed when the input is malformed.  Prints the reference's
+// `# ...` progress lines to `log`.
+SidRunInfo sidCallToStream(const std::string& method, const char* text, size_t len, bool estimate_prior, double prior,
+                           double error_threshold, double significance_level, std::ostream& out, std::ostream& log,
+                           const char* header = nullptr);
+// Selects the GPU (default 0) and the chunk size of the host path for subsequent calls.
+void sidSetDevice(int device, size_t max_chunk_bytes = 0);

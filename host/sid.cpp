@@ -1,0 +1,91 @@
+// `sid [flags] input_file` -- the reference's command line (sid.cpp:11-110) over the GPU path.
+// Same flags and defaults (-m METHOD, -r PRIOR, -R, -p LEVEL, -E ERROR, -h), same CSV on stdout,
+// same `# ...` lines on stderr, same exit codes.  Extra long options: --device N, --chunk-mb N.
+#include <fcntl.h>
+#include <getopt.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <cstdlib>
+#include <cstring>
+#include <iostream>
+#include <stdexcept>
+#include <string>
+
+#include "call.hpp"
+
+struct GlobalOptions {                               // sid.cpp:11-17
+    std::string method {"local"};
+    bool estimate_prior = false;
+    double snp_prior = -1;
+    double significance_level = 0.05;
+    double site_error_threshold = 0.1;
+};
+
+static void help() {                                 // sid.cpp:27-37 (same layout: one line per flag, sorted by letter)
+    std::cout << "sid [flags] input_file" << '\n';
+    std::cout << "\t-E ERROR\tMaximum allowed site error rate for 'local' method. Default: 0.1\n";
+    std::cout << "\t-R\tEstimate SNP prior from data, applicable for methods 'likelihood_ratio', 'local', 'quality'. Conflicts -r.\n";
+    std::cout << "\t-h\tPrint this help message\n";
+    std::cout << "\t-m METHOD\tSelect the method to use for SNP calling: 'likelihood_ratio' , 'bayes', 'local' or 'quality', default: local\n";
+    std::cout << "\t-p LEVEL\tSignificance level for statistical tests, only applicable for methods 'likelihood_ratio', 'local'. Default: 0.05\n";
+    std::cout << "\t-r PRIOR\tUse the given prior for SNPs, applicable for methods 'local', 'quality'. Conflicts -R. Default: no prior\n";
+}
+
+int main(int argc, char** argv) {
+    GlobalOptions o;
+    int device = 0;
+    size_t chunk_mb = 0;
+    static const option LONG[] = {{"device", required_argument, nullptr, 1000}, {"chunk-mb", required_argument, nullptr, 1001}, {nullptr, 0, nullptr, 0}};
+    int flag;
+    while ((flag = getopt_long(argc, argv, "E:Rhm:p:r:", LONG, nullptr)) != -1) {      // optstring as built by sid.cpp:60-69
+        switch (flag) {
+            case 'h': help(); break;
+            case 'm': o.method = optarg; break;
+            case 'r': o.snp_prior = atof(optarg); break;
+            case 'R': o.estimate_prior = true; break;
+            case 'p': o.significance_level = atof(optarg); break;
+            case 'E': o.site_error_threshold = atof(optarg); break;
+            case 1000: device = atoi(optarg); break;
+            case 1001: chunk_mb = (size_t)atol(optarg); break;
+            default: exit(EXIT_FAILURE);             // sid.cpp:80-82
+        }
+    }
+    if (optind >= argc) {                            // sid.cpp:106-109
+        std::cerr << "No file name given!" << std::endl;
+        exit(EXIT_FAILURE);
+    }
+    const char* path = argv[optind];
+    const int fd = open(path, O_RDONLY);
+    struct stat st;
+    if (fd < 0 || fstat(fd, &st) != 0) {             // sid.cpp:86-89
+        std::cerr << "Could not open file: " << path << std::endl;
+        exit(EXIT_FAILURE);
+    }
+    const size_t len = (size_t)st.st_size;
+    const char* text = "";
+    void* map = nullptr;
+    if (len) {
+        map = mmap(nullptr, len, PROT_READ, MAP_PRIVATE, fd, 0);
+        if (map == MAP_FAILED) { std::cerr << "Could not open file: " << path << std::endl; exit(EXIT_FAILURE); }
+        text = (const char*)map;
+    }
+    std::ios::sync_with_stdio(false);
+    try {
+        sidSetDevice(device, chunk_mb << 20);
+        sidCallToStream(o.method, text, len, o.estimate_prior, o.snp_prior, o.site_error_threshold, o.significance_level,
+                        std::cout, std::cerr, "chrom,pos,label,gt,hom_conf,het_conf,conf_type");          // sid.cpp:102
+        std::cout.flush();
+    } catch (const std::invalid_argument& e) {
+        // the reference lets the exception escape: terminate() -> abort, exit status 134
+        std::cerr << "terminate called after throwing an instance of 'std::invalid_argument'\n  what():  " << e.what() << std::endl;
+        std::abort();
+    } catch (const std::exception& e) {
+        std::cerr << "sid: " << e.what() << std::endl;
+        return 2;
+    }
+    if (map) munmap(map, len);
+    close(fd);
+    return 0;
+}

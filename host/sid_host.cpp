@@ -1,0 +1,340 @@
+// Host side of the drop-in: the reference's free functions (call.hpp / pileup.hpp) implemented over
+// the C ABI of libsidgpu.so.  No parsing, likelihood or formatting code lives here -- this file only
+// moves bytes: istream -> pinned host buffer -> sidgpu_call_host -> CSV rows -> OutputRecord.
+#include <cstring>
+#include <iomanip>
+#include <iterator>
+#include <memory>
+#include <sstream>
+#include <stdexcept>
+
+#include "../include/sidgpu.h"
+#include "call.hpp"
+
+namespace {
+
+int g_device = 0;
+size_t g_chunk = 0;
+
+struct Ctx {
+    sidgpu_ctx* h = nullptr;
+    Ctx() {
+        sidgpu_config cfg {};
+        cfg.device = g_device;
+        cfg.max_chunk_bytes = g_chunk;
+        if (sidgpu_create(&cfg, &h) != SIDGPU_OK) throw std::runtime_error(std::string("sidgpu: ") + sidgpu_last_error(nullptr));
+    }
+    ~Ctx() { sidgpu_destroy(h); }
+};
+
+Ctx& ctx() {
+    static std::unique_ptr<Ctx> c;
+    if (!c) c.reset(new Ctx);
+    return *c;
+}
+
+[[noreturn]] void raise(int rc) {
+    const std::string msg = sidgpu_last_error(ctx().h);
+    // pileup.cpp:9-10: the reference throws std::invalid_argument with exactly these texts
+    if (rc == SIDGPU_EMALFORMED) throw std::invalid_argument("Malformed pileup line");
+    if (rc == SIDGPU_EMISSING_MAPQ) throw std::invalid_argument("Malformed pileup line or missing mapping qualities");
+    if (rc == SIDGPU_EQUAL_SHORT) throw std::invalid_argument("Malformed pileup line: " + msg);
+    throw std::runtime_error("sidgpu error " + std::to_string(rc) + ": " + msg);
+}
+
+void check(int rc) { if (rc != SIDGPU_OK) raise(rc); }
+
+struct Pinned {
+    char* p = nullptr;
+    size_t cap = 0;
+    ~Pinned() { if (p) sidgpu_free_host(ctx().h, p); }
+    void reserve(size_t n) {
+        if (n <= cap) return;
+        char* np = nullptr;
+        check(sidgpu_malloc_host(ctx().h, n, (void**)&np));
+        if (p) { std::memcpy(np, p, cap); sidgpu_free_host(ctx().h, p); }
+        p = np;
+        cap = n;
+    }
+};
+
+// Drains a stream into pinned memory (the reference's getline loop, call.cpp:13, reads it all too).
+size_t slurp(std::istream& in, Pinned& buf) {
+    size_t len = 0;
+    buf.reserve(1 << 20);
+    while (in) {
+        if (len == buf.cap) buf.reserve(buf.cap * 2);
+        in.read(buf.p + len, (std::streamsize)(buf.cap - len));
+        len += (size_t)in.gcount();
+    }
+    return len;
+}
+
+int method_id(const std::string& m) {
+    if (m == "local") return SIDGPU_METHOD_LOCAL;
+    if (m == "bayes") return SIDGPU_METHOD_BAYES;
+    if (m == "likelihood_ratio") return SIDGPU_METHOD_LIKELIHOOD_RATIO;
+    if (m == "quality") return SIDGPU_METHOD_QUALITY;
+    return -1;
+}
+
+struct Rows {
+    Pinned csv;
+    uint64_t bytes = 0, sites = 0, rows = 0;
+};
+
+void run(int method, const char* text, size_t len, bool estimate_prior, double prior, double error_threshold,
+         double significance_level, Rows& out, SidRunInfo& info) {
+    sidgpu_params p {};
+    p.method = method;
+    p.estimate_prior = estimate_prior ? 1 : 0;
+    p.prior = prior;
+    p.error_threshold = error_threshold;
+    p.significance_level = significance_level;
+    out.csv.reserve(len + len / 2 + 4096);
+    for (;;) {
+        const int rc = sidgpu_call_host(ctx().h, &p, text, len, out.csv.p, out.csv.cap, &out.bytes, &out.sites, &out.rows);
+        if (rc == SIDGPU_ECAPACITY && out.bytes > out.csv.cap) { out.csv.reserve(out.bytes + 4096); continue; }
+        check(rc);
+        break;
+    }
+    info.n_sites = out.sites;
+    info.n_rows = out.rows;
+    sidgpu_fit fit {};
+    double nd[4];
+    uint64_t nu = 0;
+    if (sidgpu_session_fit(ctx().h, &fit, nd, &nu) == SIDGPU_OK) {
+        info.has_fit = true;
+        info.heterozygosity = fit.pi;
+        info.error_rate = fit.eps;
+        info.iterations = fit.iterations;
+        info.converged = fit.converged != 0;
+        info.unique_profiles = nu;
+    }
+}
+
+// The `# ...` lines the reference writes to std::cerr (call.cpp:72,78-80,155,161-163; optimization.hpp:70,76)
+void log_fit(int method, const SidRunInfo& info, std::ostream& log) {
+    if (!info.has_fit) return;
+    const bool lynch_method = method == SIDGPU_METHOD_BAYES || method == SIDGPU_METHOD_LIKELIHOOD_RATIO;
+    if (lynch_method) log << "# unique profiles: " << info.unique_profiles << std::endl;
+    if (info.converged) log << "# GSL function minimization converged in " << info.iterations << " iterations." << std::endl;
+    else log << "# Error: GSL function minimization did not converge in " << info.iterations << " iterations!" << std::endl;
+    if (lynch_method) {
+        std::ios_base::fmtflags f = log.flags();
+        log << std::scientific;
+        log << "# heterozygosity: " << info.heterozygosity << std::endl;
+        log << "# error: " << info.error_rate << std::endl;
+        log.flags(f);
+    }
+}
+
+std::vector<OutputRecord> to_records(const Rows& r) {
+    std::vector<OutputRecord> out;
+    out.reserve(r.rows);
+    const char* p = r.csv.p;
+    const char* end = p + r.bytes;
+    while (p < end) {
+        const char* nl = (const char*)std::memchr(p, '\n', (size_t)(end - p));
+        if (!nl) nl = end;
+        // split at the LAST six commas: the chromosome name may itself contain commas
+        const char* f[7];
+        int k = 6;
+        f[6] = nl;
+        for (const char* q = nl - 1; q >= p && k > 0; --q) if (*q == ',') f[--k] = q;
+        if (k == 0) {
+            OutputRecord rec;
+            rec.chromosome_name.assign(p, f[0]);
+            rec.position = std::atoi(std::string(f[0] + 1, f[1]).c_str());
+            rec.classification.label.assign(f[1] + 1, f[2]);
+            rec.classification.genotype.assign(f[2] + 1, f[3]);
+            rec.classification.confidence_homozygous = std::strtod(std::string(f[3] + 1, f[4]).c_str(), nullptr);
+            rec.classification.confidence_heterozygous = std::strtod(std::string(f[4] + 1, f[5]).c_str(), nullptr);
+            rec.classification.confidence_type.assign(f[5] + 1, nl);
+            out.push_back(std::move(rec));
+        }
+        p = nl + 1;
+    }
+    return out;
+}
+
+std::vector<OutputRecord> call_stream(int method, std::istream& in, bool estimate_prior, double prior, double error_threshold,
+                                      double significance_level) {
+    Pinned text;
+    const size_t len = slurp(in, text);
+    Rows rows;
+    SidRunInfo info;
+    run(method, text.p, len, estimate_prior, prior, error_threshold, significance_level, rows, info);
+    log_fit(method, info, std::cerr);
+    return to_records(rows);
+}
+
+// Device-side record of one parsed text, copied back.
+struct Parsed {
+    std::vector<uint64_t> profile;
+    std::vector<int32_t> pos;
+    std::vector<uint32_t> name_ref;
+    std::vector<char> names;
+};
+
+Parsed tokenize(const char* text, size_t len, bool want_qual) {
+    Parsed r;
+    char* d = nullptr;
+    check(sidgpu_malloc(ctx().h, ((len + 15) & ~(size_t)15) + 16, (void**)&d));
+    struct Free { char* d; ~Free() { sidgpu_free(ctx().h, d); } } guard {d};
+    if (len) check(sidgpu_memcpy_h2d(ctx().h, d, text, len));
+    sidgpu_sites_view v {};
+    check(sidgpu_tokenize(ctx().h, d, len, 0, len, want_qual ? 1 : 0, &v));
+    r.profile.resize(v.n_sites);
+    r.pos.resize(v.n_sites);
+    r.name_ref.resize(v.n_sites);
+    r.names.resize(v.names_bytes);
+    if (v.n_sites) {
+        check(sidgpu_memcpy_d2h(ctx().h, r.profile.data(), v.d_profile, v.n_sites * 8));
+        check(sidgpu_memcpy_d2h(ctx().h, r.pos.data(), v.d_pos, v.n_sites * 4));
+        check(sidgpu_memcpy_d2h(ctx().h, r.name_ref.data(), v.d_name_ref, v.n_sites * 4));
+    }
+    if (v.names_bytes) check(sidgpu_memcpy_d2h(ctx().h, r.names.data(), v.d_names, v.names_bytes));
+    return r;
+}
+
+profile_t unpack(uint64_t p) {
+    return {uint16_t(p), uint16_t(p >> 16), uint16_t(p >> 32), uint16_t(p >> 48)};
+}
+
+}  // namespace
+
+void sidSetDevice(int device, size_t max_chunk_bytes) {
+    g_device = device;
+    g_chunk = max_chunk_bytes;
+}
+
+// ---- call.hpp:40-43 ------------------------------------------------------------------------------
+std::vector<OutputRecord> callSiteMLError(std::istream& in, const bool estimate_prior, double prior, double error_threshold,
+                                          const double significance_level) {
+    return call_stream(SIDGPU_METHOD_LOCAL, in, estimate_prior, prior, error_threshold, significance_level);
+}
+std::vector<OutputRecord> callBayes(std::istream& in) { return call_stream(SIDGPU_METHOD_BAYES, in, false, -1, 0.1, 0.05); }
+std::vector<OutputRecord> callLikelihoodRatio(std::istream& in, const bool use_prior, const double significance_level) {
+    return call_stream(SIDGPU_METHOD_LIKELIHOOD_RATIO, in, use_prior, -1, 0.1, significance_level);
+}
+std::vector<OutputRecord> callQualityBasedSimple(std::istream& in, const bool estimate_prior, double prior, const double significance_level) {
+    return call_stream(SIDGPU_METHOD_QUALITY, in, estimate_prior, prior, 0.1, significance_level);
+}
+
+SidRunInfo sidCallToStream(const std::string& method, const char* text, size_t len, bool estimate_prior, double prior,
+                           double error_threshold, double significance_level, std::ostream& out, std::ostream& log,
+                           const char* header) {
+    SidRunInfo info;
+    const int m = method_id(method);
+    if (m < 0) {                                    // sid.cpp:92-100: unknown methods print the header only
+        if (header) out << header << std::endl;
+        return info;
+    }
+    Rows rows;
+    Pinned staged;
+    staged.reserve(len + 16);
+    std::memcpy(staged.p, text, len);               // pinned staging: the H2D copies overlap with the kernels
+    run(m, staged.p, len, estimate_prior, prior, error_threshold, significance_level, rows, info);
+    log_fit(m, info, log);
+    if (header) out << header << std::endl;
+    out.write(rows.csv.p, (std::streamsize)rows.bytes);
+    return info;
+}
+
+// ---- pileup.hpp / call.hpp:12 ----------------------------------------------------------------------
+std::vector<PileupLine> parsePileupText(const char* text, size_t len, bool parse_base_qualities, bool parse_mapping_qualities) {
+    const Parsed p = tokenize(text, len, parse_base_qualities || parse_mapping_qualities);
+    std::vector<PileupLine> out(p.pos.size());
+    // reference base: the third column; recovered from the text only to fill the struct (1 byte per line)
+    size_t line = 0, i = 0;
+    while (i < len && line < out.size()) {
+        const char* nl = (const char*)std::memchr(text + i, '\n', len - i);
+        const size_t e = nl ? (size_t)(nl - text) : len;
+        if (e > i) {
+            PileupLine& l = out[line];
+            const uint32_t r = p.name_ref[line];
+            const uint32_t nlen = (uint8_t)p.names[r] | ((uint32_t)(uint8_t)p.names[r + 1] << 8);
+            l.chromosome_name.assign(p.names.data() + r + 2, nlen);
+            l.position = p.pos[line];
+            l.base_counts = unpack(p.profile[line]);
+            size_t q = i;
+            for (int col = 0; col < 2; ++col) {     // skip two columns
+                while (q < e && (text[q] == ' ' || text[q] == '\t')) ++q;
+                while (q < e && text[q] != ' ' && text[q] != '\t') ++q;
+            }
+            while (q < e && (text[q] == ' ' || text[q] == '\t')) ++q;
+            if (q < e) l.reference_base = text[q];
+            ++line;
+        }
+        i = e + 1;
+    }
+    return out;
+}
+
+std::vector<PileupLine> readFile(std::istream& in, bool parse_base_qualities, bool parse_mapping_qualities) {
+    std::string text((std::istreambuf_iterator<char>(in)), std::istreambuf_iterator<char>());
+    return parsePileupText(text.data(), text.size(), parse_base_qualities, parse_mapping_qualities);
+}
+
+PileupLine parsePileupLine(char* line, bool parse_base_qualities, bool parse_mapping_qualities) {
+    const size_t n = std::strlen(line);
+    std::vector<PileupLine> v = parsePileupText(line, n, parse_base_qualities, parse_mapping_qualities);
+    if (v.empty()) throw std::invalid_argument("Malformed pileup line");
+    return v[0];
+}
+
+ReadStack parseReadBases(const char* read_bases, char reference, int coverage) {
+    (void)coverage;                                 // the reference only uses it as a reserve() hint (pileup.cpp:72-73)
+    std::string line = std::string("x\t1\t") + reference + "\t0\t" + read_bases + "\n";
+    ReadStack r;
+    r.counts = {0, 0, 0, 0};
+    if (read_bases[0] == '\0') return r;            // an empty bases string is not a valid column; counts are zero
+    const Parsed p = tokenize(line.data(), line.size(), false);
+    if (!p.profile.empty()) r.counts = unpack(p.profile[0]);
+    return r;
+}
+
+std::vector<UniqueProfile> countUniqueProfiles(const std::vector<PileupLine>& pileup) {
+    std::vector<UniqueProfile> out;
+    if (pileup.empty()) return out;
+    std::vector<uint64_t> prof(pileup.size());
+    for (size_t i = 0; i < pileup.size(); ++i) {
+        const profile_t& c = pileup[i].base_counts;
+        prof[i] = (uint64_t)c[0] | ((uint64_t)c[1] << 16) | ((uint64_t)c[2] << 32) | ((uint64_t)c[3] << 48);
+    }
+    uint64_t* d = nullptr;
+    check(sidgpu_malloc(ctx().h, prof.size() * 8, (void**)&d));
+    struct Free { void* d; ~Free() { sidgpu_free(ctx().h, d); } } guard {d};
+    check(sidgpu_memcpy_h2d(ctx().h, d, prof.data(), prof.size() * 8));
+    sidgpu_unique_view v {};
+    check(sidgpu_count_unique(ctx().h, d, prof.size(), 0, &v));
+    std::vector<uint64_t> up(v.n_unique), uc(v.n_unique);
+    if (v.n_unique) {
+        check(sidgpu_memcpy_d2h(ctx().h, up.data(), v.d_profile, v.n_unique * 8));
+        check(sidgpu_memcpy_d2h(ctx().h, uc.data(), v.d_count, v.n_unique * 8));
+    }
+    out.reserve(v.n_unique);
+    for (size_t i = 0; i < up.size(); ++i) out.emplace_back(unpack(up[i]), (uint32_t)uc[i]);
+    return out;
+}
+
+std::array<double, 4> computeNucleotideDistribution(const std::vector<UniqueProfile>& profiles) {
+    if (profiles.empty()) return {0.25, 0.25, 0.25, 0.25};
+    // weight every profile by its count: expand to (profile, count) pairs on the device
+    std::vector<uint64_t> prof(profiles.size()), cnt(profiles.size());
+    for (size_t i = 0; i < profiles.size(); ++i) {
+        const profile_t& c = profiles[i].profile;
+        prof[i] = (uint64_t)c[0] | ((uint64_t)c[1] << 16) | ((uint64_t)c[2] << 32) | ((uint64_t)c[3] << 48);
+        cnt[i] = profiles[i].count;
+    }
+    uint64_t *dp = nullptr, *dc = nullptr;
+    check(sidgpu_malloc(ctx().h, prof.size() * 8, (void**)&dp));
+    check(sidgpu_malloc(ctx().h, cnt.size() * 8, (void**)&dc));
+    struct Free { void *a, *b; ~Free() { sidgpu_free(ctx().h, a); sidgpu_free(ctx().h, b); } } guard {dp, dc};
+    check(sidgpu_memcpy_h2d(ctx().h, dp, prof.data(), prof.size() * 8));
+    check(sidgpu_memcpy_h2d(ctx().h, dc, cnt.data(), cnt.size() * 8));
+    sidgpu_unique_view v {};
+    check(sidgpu_count_unique_weighted(ctx().h, dp, dc, prof.size(), 0, &v));
+    return {v.nd[0], v.nd[1], v.nd[2], v.nd[3]};
+}

@@ -159,9 +159,15 @@ typedef struct {
     const uint64_t* d_profile;  /* packed profile, lexicographic order of (A,C,G,T) like the reference */
     const uint64_t* d_count;    /* sites with that profile (64-bit: the reference's uint32 would wrap) */
     double nd[4];               /* nucleotide distribution over the entries */
+    uint64_t nd_sums[5];        /* its integer numerators (A,C,G,T) and denominator: what a multi-GPU host all-reduces */
 } sidgpu_unique_view;
 /* Compacts and sorts the session's table.  min_coverage = 4 gives the Lynch input (call.cpp:66-70). */
 int sidgpu_histogram(sidgpu_ctx* ctx, uint32_t min_coverage, sidgpu_unique_view* out);
+/* countUniqueProfiles / computeNucleotideDistribution on caller-supplied profiles (packed as in
+ * sidgpu_sites_view), outside a session: n profiles, optionally weighted by d_counts. */
+int sidgpu_count_unique(sidgpu_ctx* ctx, const uint64_t* d_profiles, uint64_t n, uint32_t min_coverage, sidgpu_unique_view* out);
+int sidgpu_count_unique_weighted(sidgpu_ctx* ctx, const uint64_t* d_profiles, const uint64_t* d_counts, uint64_t n,
+                                 uint32_t min_coverage, sidgpu_unique_view* out);
 
 /* ------------------------------------------------------------------------------------------------
  * K4: Lynch objective   (compoundLikelihood lynch.cpp:37-61 with lynch.hpp:57-74,82-90)
@@ -180,6 +186,10 @@ typedef struct {
     int iterations, evaluations, converged;
 } sidgpu_fit;
 int sidgpu_lynch_fit(sidgpu_ctx* ctx, const double nd[4], sidgpu_fit* out);
+/* Injects (pi, eps, nucleotide distribution) into the running session before sidgpu_finish, instead
+ * of the local optimiser: a multi-GPU host fits on the all-reduced objective and hands every rank
+ * the same result. */
+int sidgpu_set_fit(sidgpu_ctx* ctx, double pi, double eps, const double nd[4]);
 /* The fit the session used (after sidgpu_finish). */
 int sidgpu_session_fit(sidgpu_ctx* ctx, sidgpu_fit* out, double nd[4], uint64_t* n_unique);
 

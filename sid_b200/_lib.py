@@ -32,7 +32,7 @@ class SitesView(ctypes.Structure):
 
 class UniqueView(ctypes.Structure):
     _fields_ = [("n_unique", c_u64), ("d_profile", ctypes.c_void_p), ("d_count", ctypes.c_void_p),
-                ("nd", ctypes.c_double * 4)]
+                ("nd", ctypes.c_double * 4), ("nd_sums", c_u64 * 5)]
 
 
 class Fit(ctypes.Structure):
@@ -65,6 +65,10 @@ PROTOTYPES = {
     "sidgpu_call_host": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(Params), ctypes.c_void_p, ctypes.c_size_t,
                                         ctypes.c_void_p, ctypes.c_size_t, c_u64_p, c_u64_p, c_u64_p]),
     "sidgpu_histogram": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint32, ctypes.POINTER(UniqueView)]),
+    "sidgpu_count_unique": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, c_u64, ctypes.c_uint32, ctypes.POINTER(UniqueView)]),
+    "sidgpu_count_unique_weighted": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, c_u64, ctypes.c_uint32,
+                                                    ctypes.POINTER(UniqueView)]),
+    "sidgpu_set_fit": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_double, ctypes.c_double, c_double_p]),
     "sidgpu_lynch_objective_partial": (ctypes.c_int, [ctypes.c_void_p, c_double_p, ctypes.c_double, ctypes.c_double,
                                                       ctypes.c_void_p]),
     "sidgpu_lynch_objective": (ctypes.c_int, [ctypes.c_void_p, c_double_p, ctypes.c_double, ctypes.c_double, c_double_p]),

@@ -219,6 +219,42 @@ class Context:
         return (self._download(v.d_profile, np.uint64, v.n_unique), self._download(v.d_count, np.uint64, v.n_unique),
                 list(v.nd))
 
+    def histogram_sums(self, min_coverage=4):
+        """(n_unique, [A, C, G, T, total] integer sums) of the session's histogram: what ranks all-reduce."""
+        v = UniqueView()
+        self._ck(self.lib.sidgpu_histogram(self.h, min_coverage, ctypes.byref(v)))
+        return v.n_unique, [int(x) for x in v.nd_sums]
+
+    def count_unique(self, profiles, counts=None, min_coverage=0):
+        """countUniqueProfiles (+ computeNucleotideDistribution) on packed profiles."""
+        p = np.ascontiguousarray(profiles, dtype=np.uint64)
+        v = UniqueView()
+        if p.size == 0:
+            return np.zeros(0, np.uint64), np.zeros(0, np.uint64), [0.25] * 4
+        dp = DeviceBuffer(self, p.nbytes).upload(p)
+        dc = None
+        try:
+            if counts is None:
+                self._ck(self.lib.sidgpu_count_unique(self.h, dp.ptr, p.size, min_coverage, ctypes.byref(v)))
+            else:
+                c = np.ascontiguousarray(counts, dtype=np.uint64)
+                dc = DeviceBuffer(self, c.nbytes).upload(c)
+                self._ck(self.lib.sidgpu_count_unique_weighted(self.h, dp.ptr, dc.ptr, p.size, min_coverage, ctypes.byref(v)))
+            return (self._download(v.d_profile, np.uint64, v.n_unique), self._download(v.d_count, np.uint64, v.n_unique), list(v.nd))
+        finally:
+            dp.free()
+            if dc:
+                dc.free()
+
+    def set_fit(self, pi, eps, nd):
+        a = (ctypes.c_double * 4)(*nd)
+        self._ck(self.lib.sidgpu_set_fit(self.h, pi, eps, a))
+
+    def lynch_objective_partial(self, nd, pi, eps, d_out):
+        """Leaves this rank's -log likelihood sum at device pointer d_out (no host sync)."""
+        a = (ctypes.c_double * 4)(*nd)
+        self._ck(self.lib.sidgpu_lynch_objective_partial(self.h, a, pi, eps, d_out))
+
     def lynch_objective(self, nd, pi, eps):
         a = (ctypes.c_double * 4)(*nd)
         out = ctypes.c_double()

@@ -48,12 +48,13 @@ def build_libsidgpu(force=False):
 def build_sid_cli(force=False):
     out = os.path.join(ROOT, "host", "sid")
     srcs = _glob("host", (".cpp", ".hpp")) + [os.path.join(ROOT, "include", "sidgpu.h")]
-    cpps = sorted(s for s in srcs if s.endswith(".cpp"))
-    if not cpps:
+    if not os.path.exists(os.path.join(ROOT, "host", "sid.cpp")):
         return None
+    link = ["-Lsid_b200", "-lsidgpu", "-Wl,-rpath,$ORIGIN/../sid_b200"]
     if force or _newer(out, srcs + [os.path.join(ROOT, "sid_b200", "libsidgpu.so")]):
-        _run(["g++", "-O2", "-std=c++17", "-Wall", "-Iinclude", "-o", out] + cpps +
-             ["-Lsid_b200", "-lsidgpu", "-Wl,-rpath,$ORIGIN/../sid_b200"])
+        _run(["g++", "-O2", "-std=c++17", "-Wall", "-Iinclude", "-o", out, "host/sid.cpp", "host/sid_host.cpp"] + link)
+        _run(["g++", "-O2", "-std=c++17", "-Wall", "-Iinclude", "-o", os.path.join(ROOT, "host", "api_check"),
+              "host/api_check.cpp", "host/sid_host.cpp"] + link)
     return out
 
 

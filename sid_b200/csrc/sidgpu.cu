@@ -437,6 +437,13 @@ int run_tokenizer(sidgpu_ctx* ctx, const char* d_text, size_t text_len, size_t r
     }
 }
 
+__global__ void k_insert_profiles(TableView t, const uint64_t* profiles, const uint64_t* weights, uint64_t n) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t slot = table_find_or_insert(t, profiles[i]);
+    atomicAdd(&t.counts[slot], weights ? (unsigned long long)weights[i] : 1ull);
+}
+
 __global__ void k_count_slots(const uint32_t* slot, uint64_t begin, uint64_t n, unsigned long long* counts) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) atomicAdd(&counts[slot[begin + i]], 1ull);
@@ -1010,6 +1017,48 @@ int sidgpu_histogram(sidgpu_ctx* ctx, uint32_t min_coverage, sidgpu_unique_view*
     out->d_profile = (const uint64_t*)ctx->u_profile.p;
     out->d_count = (const uint64_t*)ctx->u_count.p;
     for (int i = 0; i < 4; ++i) out->nd[i] = ctx->fit_nd[i];
+    for (int i = 0; i < 5; ++i) out->nd_sums[i] = ctx->n_unique ? ctx->h_ctl->nd_acc[i] : 0;
+    return SIDGPU_OK;
+}
+
+static int count_unique_impl(sidgpu_ctx* ctx, const uint64_t* d_profiles, const uint64_t* d_counts, uint64_t n, uint32_t min_coverage,
+                             sidgpu_unique_view* out) {
+    if (!ctx || !out || (n && !d_profiles)) return SIDGPU_EINVAL;
+    CK(cudaSetDevice(ctx->device));
+    ctx->phase = PHASE_IDLE;
+    for (;;) {
+        TRY(reset_table(ctx));
+        if (n) {
+            k_insert_profiles<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->tab, d_profiles, d_counts, n);
+            TRY(check_launch(ctx, "k_insert_profiles"));
+        }
+        TRY(sync_ctl(ctx));
+        if (ctx->h_ctl->table_overflow || (uint64_t)ctx->h_ctl->n_entries * 2 > ctx->tab.cap) {
+            TRY(grow_table(ctx, 2, 0));
+            continue;
+        }
+        break;
+    }
+    return sidgpu_histogram(ctx, min_coverage, out);
+}
+
+int sidgpu_count_unique(sidgpu_ctx* ctx, const uint64_t* d_profiles, uint64_t n, uint32_t min_coverage, sidgpu_unique_view* out) {
+    return count_unique_impl(ctx, d_profiles, nullptr, n, min_coverage, out);
+}
+
+int sidgpu_count_unique_weighted(sidgpu_ctx* ctx, const uint64_t* d_profiles, const uint64_t* d_counts, uint64_t n,
+                                 uint32_t min_coverage, sidgpu_unique_view* out) {
+    if (n && !d_counts) return SIDGPU_EINVAL;
+    return count_unique_impl(ctx, d_profiles, d_counts, n, min_coverage, out);
+}
+
+int sidgpu_set_fit(sidgpu_ctx* ctx, double pi, double eps, const double nd[4]) {
+    if (!ctx || !nd) return SIDGPU_EINVAL;
+    if (ctx->phase != PHASE_FEED) return ctx->fail(SIDGPU_ESTATE, "sidgpu_set_fit outside a session");
+    ctx->params.fit_given = 1;
+    ctx->params.fit_pi = pi;
+    ctx->params.fit_eps = eps;
+    for (int i = 0; i < 4; ++i) ctx->params.fit_nd[i] = nd[i];
     return SIDGPU_OK;
 }
 

@@ -1,0 +1,69 @@
+"""GPU: the C++ host -- the `sid` binary (sid.cpp flags, CSV, stderr lines, exit codes) and the
+call.hpp / pileup.hpp functions -- against the reference's recorded outputs."""
+import json
+import os
+import re
+import subprocess
+
+import pytest
+
+import oracle_py as op
+from test_oracle import GOLDEN, MANIFEST, read
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SID = os.path.join(ROOT, "host", "sid")
+API_CHECK = os.path.join(ROOT, "host", "api_check")
+
+
+@pytest.fixture(scope="module")
+def sid_bin():
+    from sid_b200 import build
+    build.build_libsidgpu()
+    build.build_sid_cli()
+    return SID
+
+
+def run(binary, *args):
+    r = subprocess.run([binary] + list(args), stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    return r.returncode, r.stdout, r.stderr.decode()
+
+
+@pytest.mark.parametrize("case", [c for c in MANIFEST["cases"] if c["input"] in ("edge.plp", "depth30.plp", "edge_quality.plp", "depth5.plp")],
+                         ids=lambda c: c["csv"])
+def test_cli_matches_reference(sid_bin, case):
+    rc, out, err = run(sid_bin, *case["flags"], os.path.join(GOLDEN, case["input"]))
+    assert rc == 0, err
+    n, diffs = op.compare_csv(out, read(case["csv"]))
+    assert diffs <= max(2, n // 1000)
+    if "heterozygosity" in case:
+        # the reference's stderr lines, same format (std::scientific, 6 digits)
+        assert "# unique profiles: %d" % case["unique_profiles"] in err
+        m = re.search(r"# heterozygosity: (\S+)", err)
+        assert m and abs(float(m.group(1)) - case["heterozygosity"]) <= 2e-4 * case["heterozygosity"]
+        m = re.search(r"# error: (\S+)", err)
+        assert m and abs(float(m.group(1)) - case["error"]) <= 2e-4 * case["error"]
+        assert re.search(r"# GSL function minimization converged in \d+ iterations\.", err)
+
+
+def test_cli_error_behaviour(sid_bin):
+    # malformed line: the reference terminates on std::invalid_argument (SIGABRT), nothing on stdout
+    rc, out, err = run(sid_bin, os.path.join(GOLDEN, "malformed_too_few_columns.plp"))
+    assert rc == -6 and out == b"" and "Malformed pileup line" in err
+    rc, out, err = run(sid_bin, "-m", "quality", os.path.join(GOLDEN, "malformed_missing_mapq.plp"))
+    assert rc == -6 and "missing mapping qualities" in err
+    # sid.cpp:86-89, :106-109, :92-102
+    rc, out, err = run(sid_bin, "/nonexistent/file.plp")
+    assert rc == 1 and "Could not open file" in err
+    rc, out, err = run(sid_bin)
+    assert rc == 1 and "No file name given!" in err
+    rc, out, err = run(sid_bin, "-h")
+    assert rc == 1 and out.startswith(b"sid [flags] input_file") and "No file name given!" in err
+    rc, out, err = run(sid_bin, "-m", "nonsense", os.path.join(GOLDEN, "depth5.plp"))
+    assert rc == 0 and out == b"chrom,pos,label,gt,hom_conf,het_conf,conf_type\n"
+
+
+def test_cpp_api(sid_bin):
+    rc, out, err = run(API_CHECK, os.path.join(GOLDEN, "depth5.plp"))
+    assert rc == 0, out.decode() + err
+    assert out.strip().endswith(b"PASSED")
