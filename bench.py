@@ -113,7 +113,8 @@ def time_cpu(args, n_procs, sites_per_proc, repeats=1):
     paths = []
     try:
         for i in range(n_procs):
-            t = synth.generate(sites_per_proc, site_begin=i * sites_per_proc, seed=1, **synth.CONFIGS[args.depth])
+            t = synth.generate(sites_per_proc, site_begin=i * sites_per_proc, seed=1, seven_columns=args.method == "quality",
+                               **synth.CONFIGS[args.depth])
             p = os.path.join(tmp, "slice%d.plp" % i)
             t.tofile(p)
             paths.append(p)
@@ -196,10 +197,10 @@ def run_ours(args):
     # ---- synthetic text for this rank's shard, generated straight into pinned host memory
     n_sites = args.sites
     cfg = synth.CONFIGS[args.depth]
-    cap = int(n_sites * (16 + 2.7 * (cfg["lam"] + 1)) + (1 << 20))
+    cap = int(n_sites * (16 + 2.7 * (cfg["lam"] + 1)) * (1.5 if args.method == "quality" else 1.0) + (1 << 20))
     h_text_t = torch.empty(cap, dtype=torch.uint8, pin_memory=True)
     t0 = time.perf_counter()
-    h_text = synth.generate(n_sites, site_begin=rank * n_sites, seed=1, out=h_text_t.numpy(), **cfg)
+    h_text = synth.generate(n_sites, site_begin=rank * n_sites, seed=1, out=h_text_t.numpy(), seven_columns=args.method == "quality", **cfg)
     text_len = int(h_text.nbytes)
     gen_s = time.perf_counter() - t0
     d_text = torch.empty(((text_len + 15) // 16 + 1) * 16, dtype=torch.uint8, device="cuda")
@@ -211,11 +212,33 @@ def run_ours(args):
 
     ctx = sid_b200.Context(device=local_rank, stream=stream.cuda_stream, max_chunk_bytes=256 << 20)
     params = sid_b200.Context.make_params(args.method)
+    ctx_streams = args.method in ("local", "quality")       # rows can be emitted chunk by chunk, no global step
     state = {"csv_bytes": 0, "rows": 0}
+
+    needs_fit = args.method in ("bayes", "likelihood_ratio")
+    d_obj = torch.zeros(1, dtype=torch.float64, device="cuda")
 
     def step_resident():
         ctx.begin(params)
         n = ctx.feed(d_text.data_ptr(), text_len)
+        if needs_fit and world > 1:
+            # sharded Lynch fit: five integers once, then one double per optimiser evaluation (NCCL)
+            from sid_b200 import shard
+            ints, flt = shard.torch_collectives(dist, "cuda")
+            _, sums = ctx.histogram_sums(4)
+
+            def local_objective(nd, pi, eps):
+                ctx.lynch_objective_partial(nd, pi, eps, d_obj.data_ptr())
+                return d_obj
+
+            fit = shard.distributed_fit(lambda: sums, local_objective, ints, flt)
+            ctx.set_fit(fit["pi"], fit["eps"], fit["nd"])
+            state["fit"] = {k: fit[k] for k in ("pi", "eps", "iterations", "evaluations")}
+        if not ctx_streams:
+            ctx.finish()
+            if "fit" not in state:
+                f = ctx.session_fit()
+                state["fit"] = {k: f[k] for k in ("pi", "eps", "iterations", "evaluations")}
         b, r = ctx.emit_csv(0, n, d_csv.data_ptr(), csv_cap)
         state["csv_bytes"], state["rows"] = b, r
         return n
@@ -298,7 +321,7 @@ def run_ours(args):
                          "frac": achieved / hbm_peak if hbm_peak else None, "traffic": None, "peak_kind": peak_kind,
                          "algorithmic_bytes_per_launch": text_len, "avg_launch_ms": tok_avg_ms, "launches_timed": tok_n,
                          "kernel_ms_per_step": {k: v[0] / args.steps for k, v in ktimes.items()}},
-            "e2e": e2e, "cpu_baseline": cpu, "gpu_launches": launches, "clocks": clocks.summary(),
+            "e2e": e2e, "cpu_baseline": cpu, "gpu_launches": launches, "clocks": clocks.summary(), "lynch_fit": state.get("fit"),
         }
         print(json.dumps(line))
     ctx.close()

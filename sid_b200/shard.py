@@ -1,0 +1,102 @@
+"""Position sharding across the GPUs of one box.
+
+The pileup text is cut into contiguous byte ranges, one per rank.  A rank owns the lines whose FIRST
+byte lies in its range (the tokenizer kernel applies the rule itself, so ranges may cut lines
+anywhere); `local` and `quality` need no communication at all.  Methods with a Lynch fit exchange
+  * five integers once (the nucleotide-distribution sums), and
+  * one double per optimiser evaluation (each rank's partial of compoundLikelihood, lynch.cpp:37-61),
+both as NCCL all-reduces (gloo on CPU in the tests).  Every rank then runs the identical
+Nelder-Mead trajectory and classifies its own sites."""
+from . import nelder_mead
+
+
+def shard_ranges(text_len, world):
+    """Contiguous byte ranges [begin, end) of a text of text_len bytes, one per rank."""
+    base, rem = divmod(text_len, world)
+    out, pos = [], 0
+    for r in range(world):
+        n = base + (1 if r < rem else 0)
+        out.append((pos, pos + n))
+        pos += n
+    return out
+
+
+def owned_line_starts(text, begin, end):
+    """Host restatement of the ownership rule for tests: offsets p in [begin, end) with
+    text[p] != '\\n' and (p == 0 or text[p-1] == '\\n')."""
+    out = []
+    for p in range(begin, end):
+        if text[p] != 10 and (p == 0 or text[p - 1] == 10):
+            out.append(p)
+    return out
+
+
+def distributed_fit(local_sums, local_objective, all_reduce_ints, all_reduce_float):
+    """Lynch fit over sharded histograms.
+      local_sums()                 -> [A, C, G, T, total] integer sums of this rank's histogram
+      local_objective(nd, pi, eps) -> this rank's partial of the objective (a float, or an object the
+                                      all-reduce understands)
+      all_reduce_ints(list)        -> element-wise sum over ranks
+      all_reduce_float(x)          -> sum over ranks, as a Python float
+    Returns dict(pi, eps, nd, fval, iterations, evaluations, converged); identical on every rank."""
+    sums = all_reduce_ints(list(local_sums()))
+    if sums[4]:
+        nd = [sums[i] / sums[4] for i in range(4)]          # pileup.cpp:209-213
+    else:
+        nd = [0.25] * 4                                     # pileup.cpp:215
+
+    def f(pi, eps):
+        if pi < 0 or pi > 1 or eps < 0 or eps > 1:          # lynch.cpp:41-43, decided before any exchange
+            return 1.7976931348623157e308
+        return all_reduce_float(local_objective(nd, pi, eps))
+
+    r = nelder_mead.nelder_mead_2d(f)
+    return {"pi": r["x"][0], "eps": r["x"][1], "nd": nd, "fval": r["fval"], "iterations": r["iterations"],
+            "evaluations": r["evaluations"], "converged": r["converged"]}
+
+
+def torch_collectives(dist, device):
+    """(all_reduce_ints, all_reduce_float) over torch.distributed for distributed_fit."""
+    import torch
+
+    def ints(v):
+        t = torch.tensor(v, dtype=torch.int64, device=device)
+        dist.all_reduce(t)
+        return [int(x) for x in t.tolist()]
+
+    def flt(x):
+        t = x if isinstance(x, torch.Tensor) else torch.tensor([x], dtype=torch.float64, device=device)
+        dist.all_reduce(t)
+        return float(t.reshape(-1)[0].item())
+
+    return ints, flt
+
+
+def call_sharded(ctx, d_text, text_len, rank, world, params, dist=None, device=None):
+    """Runs one calling session on this rank's shard of a device-resident text that every rank
+    holds (or at least its own range plus the straddling line).  Returns (n_sites, fit or None);
+    rows are then available through ctx.emit_csv(0, n_sites, ...)."""
+    import torch
+    begin, end = shard_ranges(text_len, world)[rank]
+    ctx.begin(params)
+    n = ctx.feed(d_text, text_len, begin, end)
+    needs_fit = params.method in (1, 2) or params.estimate_prior
+    fit = None
+    if needs_fit and world > 1 and not params.fit_given:
+        if params.method == 2:
+            raise NotImplementedError("likelihood_ratio needs the merged unique-profile table (Benjamini-Hochberg "
+                                      "ranks over all profiles); run it on one GPU")
+        ints, flt = torch_collectives(dist, device)
+        obj = torch.zeros(1, dtype=torch.float64, device=device)
+        _, sums = ctx.histogram_sums(4)
+
+        def local_objective(nd, pi, eps):
+            ctx.lynch_objective_partial(nd, pi, eps, obj.data_ptr())
+            return obj
+
+        fit = distributed_fit(lambda: sums, local_objective, ints, flt)
+        ctx.set_fit(fit["pi"], fit["eps"], fit["nd"])
+    ctx.finish()
+    if needs_fit and fit is None:
+        fit = ctx.session_fit()
+    return n, fit

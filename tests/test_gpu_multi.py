@@ -1,0 +1,61 @@
+"""GPU: the sharded path on one device -- two contexts play two ranks (ranges of the same text), the
+"all-reduce" is a sum over the two contexts.  Checks sidgpu_set_fit / histogram sums / the partial
+objective and that concatenated shard output equals the single-context output."""
+import numpy as np
+import pytest
+
+import oracle_py as op
+from sid_b200 import shard
+from test_oracle import read
+
+pytestmark = pytest.mark.gpu
+
+
+def _emit(ctx, n):
+    cap = max(4096, n * 80)
+    buf = ctx.device_buffer(cap)
+    try:
+        nbytes, rows = ctx.emit_csv(0, n, buf, cap)
+        return buf.download(np.uint8, nbytes).tobytes(), rows
+    finally:
+        buf.free()
+
+
+@pytest.mark.parametrize("method", ["local", "bayes"])
+def test_two_shards_equal_one(native, gpu_ctx, method):
+    import sid_b200
+    text = read("depth30_two_chroms.plp")
+    params = sid_b200.Context.make_params(method)
+    whole_rows, _, _ = gpu_ctx.call_host(text, params)
+    whole_fit = gpu_ctx.session_fit() if method == "bayes" else None
+    ctxs = [sid_b200.Context(), sid_b200.Context()]
+    bufs = [c.upload_text(text) for c in ctxs]
+    try:
+        ranges = shard.shard_ranges(len(text), 2)
+        ns = []
+        for c, d, (b, e) in zip(ctxs, bufs, ranges):
+            c.begin(sid_b200.Context.make_params(method))
+            ns.append(c.feed(d, len(text), b, e))
+        if method == "bayes":
+            sums = [c.histogram_sums(4)[1] for c in ctxs]
+            fit = shard.distributed_fit(lambda: [sum(s[i] for s in sums) for i in range(5)],
+                                        lambda nd, pi, eps: sum(c.lynch_objective(nd, pi, eps) for c in ctxs),
+                                        lambda v: v, lambda x: x)
+            assert fit["converged"]
+            assert abs(fit["pi"] - whole_fit["pi"]) <= 1e-6 * whole_fit["pi"]
+            assert abs(fit["eps"] - whole_fit["eps"]) <= 1e-6 * whole_fit["eps"]
+            assert np.allclose(fit["nd"], whole_fit["nd"], rtol=0, atol=1e-15)
+            for c in ctxs:
+                c.set_fit(fit["pi"], fit["eps"], fit["nd"])
+        rows = b""
+        for c, n in zip(ctxs, ns):
+            c.finish()
+            r, _ = _emit(c, n)
+            rows += r
+        n, diffs = op.compare_csv(rows, whole_rows)
+        assert diffs <= 2
+    finally:
+        for b in bufs:
+            b.free()
+        for c in ctxs:
+            c.close()
