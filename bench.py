@@ -291,6 +291,19 @@ def run_ours(args):
     e2e = None
     if not args.no_e2e:
         step_e2e()
+        # the copy engine alone on the same buffers: what PCIe allows for this step's bytes
+        barrier()
+        e0.record(stream)
+        d_text[:text_len].copy_(h_text_t[:text_len], non_blocking=True)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        h2d_gbs = text_len / 1e9 / (e0.elapsed_time(e1) * 1e-3)
+        nb0 = max(1, int(state["csv_bytes"]))
+        e0.record(stream)
+        h_csv_t[:nb0].copy_(d_csv[:nb0], non_blocking=True)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        d2h_gbs = nb0 / 1e9 / (e0.elapsed_time(e1) * 1e-3)
         barrier()
         t0 = time.perf_counter()
         e0.record(stream)
@@ -301,7 +314,9 @@ def run_ours(args):
         wall_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
         e2e = {"value": world * n_sites / (wall_ms / args.steps * 1e-3), "unit": UNIT, "h2d_bytes_per_step": text_len,
                "d2h_bytes_per_step": int(nb), "ms_per_step": wall_ms / args.steps,
-               "timing": "host wall clock around sidgpu_call_host (it returns after its last D2H copy), max over ranks"}
+               "timing": "host wall clock around sidgpu_call_host (it returns after its last D2H copy), max over ranks",
+               "pcie": {"h2d_gbs": h2d_gbs, "d2h_gbs": d2h_gbs,
+                        "copy_bound_ms": max(text_len / h2d_gbs, int(nb) / d2h_gbs) * 1e-6}}
 
     # ---- the reference's CPU path on this box's host cores (rank 0, N=1 only)
     cpu = None

@@ -6,18 +6,13 @@
 
 namespace {
 
+// The staging buffers and events live in the ctx (sidgpu_ctx::hp_*) and are reused from call to call.
 struct HostPath {
     sidgpu_ctx* ctx;
-    DevBuf text[2], csv[2];
-    cudaEvent_t ev_in[2] {nullptr, nullptr}, ev_out[2] {nullptr, nullptr};
-    ~HostPath() {
-        for (int i = 0; i < 2; ++i) {
-            release(text[i]);
-            release(csv[i]);
-            if (ev_in[i]) cudaEventDestroy(ev_in[i]);
-            if (ev_out[i]) cudaEventDestroy(ev_out[i]);
-        }
-    }
+    DevBuf* text;
+    DevBuf* csv;
+    cudaEvent_t* ev_in;
+    cudaEvent_t* ev_out;
 };
 
 // End (exclusive) of the chunk starting at `start`: the last line end within max_chunk, or the
@@ -37,11 +32,10 @@ extern "C" int sidgpu_call_host(sidgpu_ctx* ctx, const sidgpu_params* params, co
                                 char* h_csv, size_t csv_cap, uint64_t* csv_bytes, uint64_t* n_sites, uint64_t* n_rows) {
     if (!ctx || !params || (text_len && !h_text)) return SIDGPU_EINVAL;
     CK(cudaSetDevice(ctx->device));
-    HostPath hp;
-    hp.ctx = ctx;
+    HostPath hp {ctx, ctx->hp_text, ctx->hp_csv, ctx->hp_ev_in, ctx->hp_ev_out};
     for (int i = 0; i < 2; ++i) {
-        CK(cudaEventCreateWithFlags(&hp.ev_in[i], cudaEventDisableTiming));
-        CK(cudaEventCreateWithFlags(&hp.ev_out[i], cudaEventDisableTiming));
+        if (!hp.ev_in[i]) CK(cudaEventCreateWithFlags(&hp.ev_in[i], cudaEventDisableTiming));
+        if (!hp.ev_out[i]) CK(cudaEventCreateWithFlags(&hp.ev_out[i], cudaEventDisableTiming));
     }
     TRY(sidgpu_begin(ctx, params));
     const size_t max_chunk = ctx->max_chunk;

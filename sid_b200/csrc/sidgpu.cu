@@ -103,6 +103,10 @@ struct sidgpu_ctx {
     DevBuf partials;
     DevBuf quality_lut;
 
+    // sidgpu_call_host staging (two text buffers, two CSV buffers, their events), kept across calls
+    DevBuf hp_text[2], hp_csv[2];
+    cudaEvent_t hp_ev_in[2] = {nullptr, nullptr}, hp_ev_out[2] = {nullptr, nullptr};
+
     // optional per-kernel timing (sidgpu_profile): event pairs recorded around launches, resolved lazily
     bool profiling = false;
     struct Pending { cudaEvent_t a, b; int which; };
@@ -743,6 +747,12 @@ void sidgpu_destroy(sidgpu_ctx* ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     resolve_profile(ctx);
     for (cudaEvent_t e : ctx->free_events) cudaEventDestroy(e);
+    for (int i = 0; i < 2; ++i) {
+        release(ctx->hp_text[i]);
+        release(ctx->hp_csv[i]);
+        if (ctx->hp_ev_in[i]) cudaEventDestroy(ctx->hp_ev_in[i]);
+        if (ctx->hp_ev_out[i]) cudaEventDestroy(ctx->hp_ev_out[i]);
+    }
     free_table(ctx->tab);
     cudaFree(ctx->names.slots);
     cudaFree(ctx->names.pool);
