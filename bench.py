@@ -286,6 +286,14 @@ def run_ours(args):
     tok_ms, tok_n = ktimes["tokenize"]
     tok_avg_ms = tok_ms / max(tok_n, 1)
     achieved = (text_len / 1e9) / (tok_avg_ms * 1e-3) if tok_ms > 0 else 0.0
+    # DRAM traffic of the dominant kernel per launch: ratio measured by one `ncu --set full` capture
+    # (profiles/), scaled to this launch's algorithmic bytes
+    traffic = None
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))["k_tokenize"]
+        traffic = int(text_len * (t["dram_bytes_read"] + t["dram_bytes_write"]) / t["algorithmic_bytes"])
+    except Exception:
+        pass
 
     # ---- end to end through the host-buffer entry point (pinned host text -> pinned host CSV)
     e2e = None
@@ -333,7 +341,7 @@ def run_ours(args):
                        "l2": "inputs larger than L2 (%.1f GB of text per step)" % (text_len / 1e9), "parallelism": "position-sharded x%d, no data-path collective" % world,
                        "generator_seconds": gen_s},
             "roofline": {"bound": "hbm", "kernel": "k_tokenize", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved / hbm_peak if hbm_peak else None, "traffic": None, "peak_kind": peak_kind,
+                         "frac": achieved / hbm_peak if hbm_peak else None, "traffic": traffic, "peak_kind": peak_kind,
                          "algorithmic_bytes_per_launch": text_len, "avg_launch_ms": tok_avg_ms, "launches_timed": tok_n,
                          "kernel_ms_per_step": {k: v[0] / args.steps for k, v in ktimes.items()}},
             "e2e": e2e, "cpu_baseline": cpu, "gpu_launches": launches, "clocks": clocks.summary(), "lynch_fit": state.get("fit"),
