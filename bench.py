@@ -197,10 +197,23 @@ def run_ours(args):
     # ---- synthetic text for this rank's shard, generated straight into pinned host memory
     n_sites = args.sites
     cfg = synth.CONFIGS[args.depth]
+    # host memory guard: every rank pins its text and its CSV; never ask for more than half of what is free
+    note = None
+    try:
+        avail = [int(l.split()[1]) * 1024 for l in open("/proc/meminfo") if l.startswith("MemAvailable")][0]
+        per_site = (16 + 2.7 * (cfg["lam"] + 1)) * (1.5 if args.method == "quality" else 1.0) + 56
+        fit = int(0.5 * avail / max(world, 1) / per_site)
+        if fit < n_sites:
+            note = "sites per GPU reduced from %d to %d to fit pinned host memory (%.0f GB available)" % (n_sites, fit, avail / 1e9)
+            n_sites = fit
+    except Exception:
+        pass
+    gen_threads = max(1, (os.cpu_count() or 1) // max(world, 1))
     cap = int(n_sites * (16 + 2.7 * (cfg["lam"] + 1)) * (1.5 if args.method == "quality" else 1.0) + (1 << 20))
     h_text_t = torch.empty(cap, dtype=torch.uint8, pin_memory=True)
     t0 = time.perf_counter()
-    h_text = synth.generate(n_sites, site_begin=rank * n_sites, seed=1, out=h_text_t.numpy(), seven_columns=args.method == "quality", **cfg)
+    h_text = synth.generate(n_sites, site_begin=rank * n_sites, seed=1, out=h_text_t.numpy(), seven_columns=args.method == "quality",
+                            threads=gen_threads, **cfg)
     text_len = int(h_text.nbytes)
     gen_s = time.perf_counter() - t0
     d_text = torch.empty(((text_len + 15) // 16 + 1) * 16, dtype=torch.uint8, device="cuda")
@@ -339,7 +352,7 @@ def run_ours(args):
             "data": "synthetic",
             "config": {"workload": workload_name(args), "text_bytes_per_gpu": text_len, "csv_bytes_per_gpu": state["csv_bytes"],
                        "l2": "inputs larger than L2 (%.1f GB of text per step)" % (text_len / 1e9), "parallelism": "position-sharded x%d, no data-path collective" % world,
-                       "generator_seconds": gen_s},
+                       "generator_seconds": gen_s, "sites_per_gpu": n_sites, "note": note},
             "roofline": {"bound": "hbm", "kernel": "k_tokenize", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                          "frac": achieved / hbm_peak if hbm_peak else None, "traffic": traffic, "peak_kind": peak_kind,
                          "algorithmic_bytes_per_launch": text_len, "avg_launch_ms": tok_avg_ms, "launches_timed": tok_n,
