@@ -15,6 +15,7 @@
 #pragma once
 #include "common.cuh"
 #include "parse.cuh"
+#include "parse_bits.cuh"
 #include "parse_fast.cuh"
 #include "ptx.cuh"
 #include "table.cuh"
@@ -25,7 +26,7 @@ constexpr int TOK_PARSE_WARPS = 8;
 constexpr int TOK_THREADS = 32 * (1 + TOK_PARSE_WARPS);
 constexpr int TOK_STAGES = 2;
 constexpr int SLICE_MAX = 4096;                   // bytes; slices are multiples of 16
-constexpr int SLICE_MIN = 256;
+constexpr int SLICE_MIN = 256;                    // slices are multiples of 32
 constexpr int TILE_TAIL = 2048;                   // staged past the tile end for straddling lines
 constexpr int TILE_PAD = 16;                      // staged before the tile begin (previous byte)
 constexpr int TILE_SMEM_MAX = TILE_PAD + TOK_PARSE_WARPS * SLICE_MAX + TILE_TAIL;
@@ -59,11 +60,17 @@ struct TokParams {
     uint32_t slice_bytes;           // multiple of 16 in [SLICE_MIN, SLICE_MAX]; a tile is 8 slices
     uint32_t text_stride;           // bytes of shared memory per staged tile (tile_smem rounded up to 128)
     uint32_t lines_cap;             // line-start slots per slice (slice_bytes / 8)
+    uint32_t ext_bytes;             // bytes past its slice a parse warp also classifies (multiple of 32, <= 2016)
+    uint32_t words_cap;             // 32-bit words per class bit array: (slice_bytes + ext_bytes) / 32 + 2
 };
 
 // Dynamic shared memory a launch with this slice length needs.
 inline uint32_t tok_text_stride(uint32_t slice) { return (16u + 8u * slice + 2048u + 127u) & ~127u; }
-inline uint32_t tok_dyn_smem(uint32_t slice) { return 2u * (tok_text_stride(slice) + 8u * (slice / 8u) * 2u); }
+inline uint32_t tok_words_cap(uint32_t slice, uint32_t ext) { return (slice + ext) / 32u + 2u; }
+// staged text (2 stages) + line starts (2 stages x 8 warps) + class bit arrays (8 warps x 8 classes)
+inline uint32_t tok_dyn_smem(uint32_t slice, uint32_t ext) {
+    return 2u * (tok_text_stride(slice) + 8u * (slice / 8u) * 2u) + 8u * 8u * tok_words_cap(slice, ext) * 4u;
+}
 
 #if defined(__CUDACC__)
 
@@ -315,29 +322,49 @@ __global__ void __launch_bounds__(TOK_THREADS) k_tokenize(const TokParams p) {
                            ((size_t)b * TOK_PARSE_WARPS + pw) * p.lines_cap;
         const uint64_t tb = s_meta[b].tb;
         const uint64_t abs0 = tb - TILE_PAD;              // wraps for a tile at offset 0; only differences are used
-        // ---- line starts of this warp's slice: byte q starts a line iff text[q] != '\n' and text[q-1] == '\n'.
-        // 16-byte unit u of the slice is scanned by lane u % 32 in round u / 32.
+        // ---- stage 1, flat over the slice (+ ext_bytes so that the last lines can be finished): every
+        //      32-byte unit is transposed into bit planes and classified (parse_bits.cuh); the class
+        //      words go to this warp's bit arrays; the '\n' word gives the line starts of the slice:
+        //      byte q starts a line iff text[q] != '\n' and text[q-1] == '\n'.
+        //      Unit u is handled by lane u % 32 in round u / 32.
         uint32_t n_lines = 0;
+        const uint32_t slice_off = (uint32_t)pw * slice;               // offset of the slice inside the tile
+        const uint32_t region_off = TILE_PAD + slice_off;              // offset in txt of bit 0 of the bit arrays
+        uint32_t* bits = reinterpret_cast<uint32_t*>(s_dyn + (size_t)TOK_STAGES * (p.text_stride + TOK_PARSE_WARPS * p.lines_cap * 2)) +
+                         (size_t)pw * 8 * p.words_cap;
         {
-            const uint32_t units = slice / 16;
-            const uint32_t slice_off = (uint32_t)pw * slice;           // offset of the slice inside the tile
+            const uint32_t own_units = slice / 32, units = (slice + p.ext_bytes) / 32;
             const bool inside = tb + slice_off >= p.range_begin && tb + slice_off + slice <= p.range_end;   // the usual case
             for (uint32_t u0 = 0; u0 < units; u0 += 32) {
                 const uint32_t u = u0 + lane;
                 uint32_t st = 0;
                 if (u < units) {
-                    const uint8_t* up = txt + TILE_PAD + slice_off + u * 16;
-                    const uint32_t nl = newline_mask16(*reinterpret_cast<const uint4*>(up));
-                    const uint32_t prev_nl = up[-1] == (uint8_t)'\n' ? 1u : 0u;
-                    st = ((nl << 1) | prev_nl) & ~nl & 0xFFFFu;
-                    if (!inside) {                                     // restrict to the owned range [range_begin, range_end)
-                        const uint64_t first = tb + slice_off + u * 16;
-                        if (first + 16 <= p.range_begin || first >= p.range_end) st = 0;
-                        else {
-                            if (first < p.range_begin) st &= 0xFFFFu << (uint32_t)(p.range_begin - first);
-                            if (first + 16 > p.range_end) st &= (1u << (uint32_t)(p.range_end - first)) - 1u;
+                    const uint8_t* up = txt + region_off + u * 32;
+                    const uint4 v0 = *reinterpret_cast<const uint4*>(up), v1 = *reinterpret_cast<const uint4*>(up + 16);
+                    const uint32_t w[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+                    const ClassWords k = classify32(w);
+                    bits[0 * p.words_cap + u] = k.term;
+                    bits[1 * p.words_cap + u] = k.a;
+                    bits[2 * p.words_cap + u] = k.c;
+                    bits[3 * p.words_cap + u] = k.g;
+                    bits[4 * p.words_cap + u] = k.t;
+                    bits[5 * p.words_cap + u] = k.dot;
+                    bits[6 * p.words_cap + u] = k.caret;
+                    bits[7 * p.words_cap + u] = k.pm;
+                    if (u < own_units) {
+                        const uint32_t prev_nl = up[-1] == (uint8_t)'\n' ? 1u : 0u;
+                        st = ((k.nl << 1) | prev_nl) & ~k.nl;
+                        if (!inside) {                                 // restrict to the owned range [range_begin, range_end)
+                            const uint64_t first = tb + slice_off + u * 32;
+                            if (first + 32 <= p.range_begin || first >= p.range_end) st = 0;
+                            else {
+                                if (first < p.range_begin) st &= 0xFFFFFFFFu << (uint32_t)(p.range_begin - first);
+                                if (first + 32 > p.range_end) st &= 0xFFFFFFFFu >> (32u - (uint32_t)(p.range_end - first));
+                            }
                         }
                     }
+                } else if (u < units + 2) {
+                    for (int c = 0; c < 8; ++c) bits[c * p.words_cap + u] = 0;      // padding words read by bits32()
                 }
                 const uint32_t my_count = __popc(st);
                 uint32_t incl = my_count;
@@ -350,10 +377,13 @@ __global__ void __launch_bounds__(TOK_THREADS) k_tokenize(const TokParams p) {
                 while (st) {
                     const int bit = __ffs((int)st) - 1;
                     st &= st - 1;
-                    if (idx < p.lines_cap) starts[idx] = (uint16_t)(slice_off + u * 16 + bit);
+                    if (idx < p.lines_cap) starts[idx] = (uint16_t)(slice_off + u * 32 + bit);
                     ++idx;
                 }
                 n_lines += __shfl_sync(0xFFFFFFFFu, incl, 31);
+            }
+            if (units % 32 >= 30 || units % 32 == 0) {                 // the padding words did not fit into the last round
+                if (lane < 2) for (int c = 0; c < 8; ++c) bits[c * p.words_cap + units + lane] = 0;
             }
             if (n_lines > p.lines_cap) {                   // only possible with lines shorter than 8 bytes
                 if (lane == 0) report_error(p, tb, LINE_MALFORMED);
@@ -366,6 +396,10 @@ __global__ void __launch_bounds__(TOK_THREADS) k_tokenize(const TokParams p) {
                 mbar_arrive(&s_counted[b]);
             }
         }
+        BitArrays B;
+        B.term = bits; B.a = bits + p.words_cap; B.c = bits + 2 * p.words_cap; B.g = bits + 3 * p.words_cap;
+        B.t = bits + 4 * p.words_cap; B.dot = bits + 5 * p.words_cap; B.caret = bits + 6 * p.words_cap; B.pm = bits + 7 * p.words_cap;
+        B.n_bits = slice + p.ext_bytes;
         // ---- the slice's first line: its name is shared by (almost) all lines of the slice
         uint32_t l0_off = 0, name0_ref = 0;
         uint2 first8 = make_uint2(0, 0);
@@ -388,7 +422,7 @@ __global__ void __launch_bounds__(TOK_THREADS) k_tokenize(const TokParams p) {
             bool fast = false;
             if (FAST && !p.want_qual) {
                 FastLine fl;
-                fast = parse_line_fast_smem(txt, abs0, tile_smem, line_abs, fl);
+                fast = parse_line_bits(txt, tile_smem, region_off, B, TILE_PAD + off, fl);
                 r.status = fl.status; r.pos = fl.pos; r.profile = fl.profile; r.chrom_off = fl.chrom_off; r.chrom_len = fl.chrom_len;
             }
             if (!fast && mine) {

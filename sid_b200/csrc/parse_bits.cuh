@@ -1,0 +1,268 @@
+// Bit-parallel form of the tokenizer.
+//
+// Stage 1 (flat, no per-line work): 32 bytes of text are transposed into their 8 bit planes (an
+// 8x8 bit-matrix transpose per 8 bytes, three mask-and-shift rounds, then byte permutes), and every
+// character class the grammar of parseReadBases (pileup.cpp:70-153) distinguishes becomes a boolean
+// function of the planes: one 32-bit word per class and 32 bytes of text.  The words go to bit
+// arrays in shared memory (bit i <-> byte i of the warp's slice).
+//
+// Stage 2 (one line per lane): the header separators come from the TERM bit array, the bases field
+// is walked 32 bytes per step: '^' masks its successor by a shift of the CARET word, the counts of
+// A/C/G/T/./, are population counts of class words under the step's mask, an indel reads its length
+// from the text and restarts the walk after the number with that many bytes to ignore.
+//
+// Same contract as parse_fast.cuh: a line outside the fast grammar is REFUSED (returns false) and
+// the caller re-parses it with the byte-wise state machine of parse.cuh.
+#pragma once
+#include "common.cuh"
+#include "parse.cuh"
+#include "parse_fast.cuh"
+
+namespace sid {
+
+SID_HD uint32_t byte_perm(uint32_t x, uint32_t y, uint32_t s) {
+#if defined(__CUDA_ARCH__)
+    return __byte_perm(x, y, s);
+#else
+    const uint64_t v = ((uint64_t)y << 32) | x;
+    uint32_t r = 0;
+    for (int i = 0; i < 4; ++i) r |= (uint32_t)((v >> (8 * ((s >> (4 * i)) & 7))) & 0xFF) << (8 * i);
+    return r;
+#endif
+}
+
+// 8x8 bit transpose of the 8 bytes (lo = bytes 0..3, hi = bytes 4..7): afterwards byte j of lo
+// (j = 0..3) / hi (j = 4..7) holds bit j of the eight input bytes, input byte i at bit i.
+SID_HD void transpose8(uint32_t& lo, uint32_t& hi) {
+    uint32_t t;
+    t = (lo ^ (lo >> 7)) & 0x00AA00AAu; lo = lo ^ t ^ (t << 7);
+    t = (hi ^ (hi >> 7)) & 0x00AA00AAu; hi = hi ^ t ^ (t << 7);
+    t = (lo ^ (lo >> 14)) & 0x0000CCCCu; lo = lo ^ t ^ (t << 14);
+    t = (hi ^ (hi >> 14)) & 0x0000CCCCu; hi = hi ^ t ^ (t << 14);
+    const uint32_t nl = (lo & 0x0F0F0F0Fu) | ((hi << 4) & 0xF0F0F0F0u);
+    const uint32_t nh = (hi & 0xF0F0F0F0u) | ((lo >> 4) & 0x0F0F0F0Fu);
+    lo = nl;
+    hi = nh;
+}
+
+struct ClassWords {     // bit i of each word <-> byte i of the 32-byte unit
+    uint32_t term;      // byte <= 0x20: field separators, line end, NUL and the other control bytes
+    uint32_t nl;        // '\n'
+    uint32_t a, c, g, t;    // A/a C/c G/g T/t
+    uint32_t dot;       // '.' or ','
+    uint32_t caret;     // '^'
+    uint32_t pm;        // '+' or '-'
+    uint32_t high;      // byte >= 0x80
+};
+
+// w[0..7]: the unit's 32 bytes as little-endian words.
+SID_HD ClassWords classify32(const uint32_t w[8]) {
+    uint32_t lo[4], hi[4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        lo[g] = w[2 * g];
+        hi[g] = w[2 * g + 1];
+        transpose8(lo[g], hi[g]);
+    }
+    // gather plane j: byte j of the four groups
+    const uint32_t t01 = byte_perm(lo[0], lo[1], 0x5140u), t23 = byte_perm(lo[2], lo[3], 0x5140u);
+    const uint32_t u01 = byte_perm(lo[0], lo[1], 0x7362u), u23 = byte_perm(lo[2], lo[3], 0x7362u);
+    const uint32_t v01 = byte_perm(hi[0], hi[1], 0x5140u), v23 = byte_perm(hi[2], hi[3], 0x5140u);
+    const uint32_t x01 = byte_perm(hi[0], hi[1], 0x7362u), x23 = byte_perm(hi[2], hi[3], 0x7362u);
+    const uint32_t p0 = byte_perm(t01, t23, 0x5410u), p1 = byte_perm(t01, t23, 0x7632u);
+    const uint32_t p2 = byte_perm(u01, u23, 0x5410u), p3 = byte_perm(u01, u23, 0x7632u);
+    const uint32_t p4 = byte_perm(v01, v23, 0x5410u), p5 = byte_perm(v01, v23, 0x7632u);
+    const uint32_t p6 = byte_perm(x01, x23, 0x5410u), p7 = byte_perm(x01, x23, 0x7632u);
+    ClassWords k;
+    k.high = p7;
+    const uint32_t n7 = ~p7;
+    const uint32_t lo_zero = ~(p3 | p2 | p1 | p0);
+    k.term = n7 & ~p6 & (~p5 | (~p4 & lo_zero));                    // 0x00..0x1f, 0x20
+    k.nl = n7 & ~p6 & ~p5 & ~p4 & p3 & ~p2 & p1 & ~p0;              // 0x0a
+    const uint32_t l46 = n7 & p6 & ~p4;                             // 0x4_, 0x6_
+    k.a = l46 & ~p3 & ~p2 & ~p1 & p0;                               // 0x41 0x61
+    k.c = l46 & ~p3 & ~p2 & p1 & p0;                                // 0x43 0x63
+    k.g = l46 & ~p3 & p2 & p1 & p0;                                 // 0x47 0x67
+    k.t = n7 & p6 & p4 & ~p3 & p2 & ~p1 & ~p0;                      // 0x54 0x74
+    const uint32_t h2 = n7 & ~p6 & p5 & ~p4;                        // 0x2_
+    k.dot = h2 & p3 & p2 & ~p0;                                     // 0x2c 0x2e
+    k.pm = h2 & p3 & p0 & (p2 ^ p1);                                // 0x2b 0x2d
+    k.caret = n7 & p6 & ~p5 & p4 & p3 & p2 & p1 & ~p0;              // 0x5e
+    return k;
+}
+
+// The class bit arrays of one region of staged text (bit i <-> byte region_off + i).  Each array
+// holds n_words valid words followed by at least one padding word.
+struct BitArrays {
+    const uint32_t* term;
+    const uint32_t* a;
+    const uint32_t* c;
+    const uint32_t* g;
+    const uint32_t* t;
+    const uint32_t* dot;
+    const uint32_t* caret;
+    const uint32_t* pm;
+    uint32_t n_bits;        // classified bytes
+};
+
+SID_HD uint32_t bits32(const uint32_t* arr, uint32_t pos) {        // 32 bits starting at bit `pos`
+    const uint32_t k = pos >> 5;
+    return funnel_r(arr[k], arr[k + 1], pos & 31);
+}
+
+// `s`: staged text (4-byte aligned, `avail` bytes, byte 0 at absolute offset abs0); the bit arrays
+// cover the bytes from offset region_off of s.  Same result contract as parse_line_fast_smem.
+SID_HD bool parse_line_bits(const uint8_t* s, uint32_t avail, uint32_t region_off, const BitArrays& B, uint32_t line_off,
+                            FastLine& o) {
+    const uint32_t* sw = reinterpret_cast<const uint32_t*>(s);
+    const uint32_t ls = line_off - region_off;                      // bit index of the line's first byte
+    bool ok = line_off >= region_off && ls + 96 <= B.n_bits && line_off + 64 <= avail && line_off >= 12;
+    const uint32_t l0 = ok ? ls : 0, h0 = ok ? line_off : 16;
+    // ---- header: the bytes <= 0x20 among the first 32 locate the four separators
+    const uint32_t sepmask = bits32(B.term, l0);
+    ok = ok && pop_count(sepmask) >= 4;
+    uint32_t m = sepmask;
+    const uint32_t p1 = first_bit(m); m &= m - 1;
+    const uint32_t p2 = first_bit(m); m &= m - 1;
+    const uint32_t p3 = first_bit(m); m &= m - 1;
+    const uint32_t p4 = first_bit(m);
+    const uint32_t nd = p2 - p1 - 1;
+    // chrom non-empty, 1..9 digits, one reference character, depth non-empty, bases non-empty within reach
+    ok = ok && p1 >= 1 && nd >= 1 && nd <= 9 && p3 == p2 + 2 && p4 > p3 + 1 && p4 <= 30 && ((sepmask >> (p4 + 1)) & 1u) == 0;
+    const uint32_t q1 = ok ? p1 : 1, q2 = ok ? p2 : 3, q3 = ok ? p3 : 5, q4 = ok ? p4 : 7;
+    {
+        const uint32_t c1 = s[h0 + q1], c2 = s[h0 + q2], c3 = s[h0 + q3], c4 = s[h0 + q4];
+        ok = ok && (c1 == '\t' || c1 == ' ') && (c2 == '\t' || c2 == ' ') && (c3 == '\t' || c3 == ' ') && (c4 == '\t' || c4 == ' ');
+    }
+    o.chrom_off = 0;
+    o.chrom_len = q1;
+    const uint32_t ref = s[h0 + q2 + 1];
+    // ---- position: the (up to) eight characters before the second separator, leading ones forced to '0'
+    uint32_t acc;
+    {
+        const uint32_t e = h0 + q2;
+        const uint32_t ndd = ok ? nd : 1;
+        const uint32_t* pw = sw + ((e - 8) >> 2);
+        const uint32_t ps = ((e - 8) & 3) * 8;
+        const uint32_t w0 = pw[0], w1 = pw[1], w2 = pw[2];
+        uint32_t lo = funnel_r(w0, w1, ps), hi = funnel_r(w1, w2, ps);
+        const uint32_t zero = ndd >= 8 ? 0u : 8u - ndd;
+        if (zero >= 4) {
+            lo = 0x30303030u;
+            const uint32_t mz = zero == 4 ? 0u : ((1u << (8 * (zero - 4))) - 1u);
+            hi = (hi & ~mz) | (0x30303030u & mz);
+        } else if (zero) {
+            const uint32_t mz = (1u << (8 * zero)) - 1u;
+            lo = (lo & ~mz) | (0x30303030u & mz);
+        }
+        const bool dig = ((lo & 0xF0F0F0F0u) == 0x30303030u) && ((hi & 0xF0F0F0F0u) == 0x30303030u) &&
+                         ((((lo & 0x0F0F0F0Fu) + 0x06060606u) | ((hi & 0x0F0F0F0Fu) + 0x06060606u)) & 0x10101010u) == 0;
+        ok = ok && dig;
+        const uint32_t xl = lo & 0x0F0F0F0Fu, xh = hi & 0x0F0F0F0Fu;
+        const uint32_t tl = xl * 10u + (xl >> 8), th = xh * 10u + (xh >> 8);
+        const uint32_t vl = (tl & 0xFFu) * 100u + ((tl >> 16) & 0xFFu), vh = (th & 0xFFu) * 100u + ((th >> 16) & 0xFFu);
+        acc = vl * 10000u + vh;
+        if (ndd == 9) {
+            const uint32_t d9 = (uint32_t)s[e - 9] - (uint32_t)'0';
+            ok = ok && d9 <= 9;
+            acc += d9 * 100000000u;
+        }
+    }
+    SID_SYNCWARP();
+    // ---- bases field: 32 bytes per step
+    uint32_t cur = l0 + q4 + 1;             // bit index of the next byte to look at
+    uint32_t na = 0, nc = 0, ng = 0, nt = 0, ndot = 0;
+    uint32_t skip = 0;                      // bytes at `cur` still covered by a '^' or an indel
+    bool running = ok;
+    while (running) {
+        if (cur + 64 > B.n_bits) { ok = false; break; }             // ran out of classified bytes
+        const uint32_t term = bits32(B.term, cur);
+        uint32_t vmask = 0xFFFFFFFFu;       // bytes of this step that belong to the field
+        bool last = false;
+        if (term) {
+            const uint32_t n = first_bit(term);
+            const uint32_t tb = s[region_off + cur + n];
+            if (tb != '\t' && tb != ' ' && tb != '\n' && tb != 0) { ok = false; break; }   // a control byte inside the field
+            vmask = n ? (0xFFFFFFFFu >> (32 - n)) : 0u;
+            last = true;
+        }
+        if (skip) {
+            const uint32_t sk = skip < 32 ? skip : 32;
+            vmask &= sk == 32 ? 0u : (0xFFFFFFFFu << sk);
+            skip -= sk;
+        }
+        const uint32_t car = bits32(B.caret, cur) & vmask;
+        if (car & (car << 1)) { ok = false; break; }                // "^^": leave the parity to the byte-wise path
+        const uint32_t live = vmask & ~(car << 1);                  // '^' hides the byte after it
+        const uint32_t pm = bits32(B.pm, cur) & live;
+        uint32_t cm = live;                 // the bytes to count in this step
+        uint32_t next = cur + 32;
+        if (pm) {
+            // everything before the sign counts; the indel length is read from the text
+            // (pileup.cpp:131-136) and the walk restarts right after the number
+            const uint32_t p = first_bit(pm);
+            cm = live & (p ? (0xFFFFFFFFu >> (32 - p)) : 0u);
+            uint32_t q = region_off + cur + p + 1;                  // first byte after the sign
+            uint32_t n = 0;
+            bool any = false;
+            while (q + 8 < avail) {
+                const uint32_t d = (uint32_t)s[q] - (uint32_t)'0';
+                if (d > 9) break;
+                if (n < (1u << 26)) n = n * 10 + d;
+                any = true;
+                ++q;
+            }
+            if (q + 8 >= avail) { ok = false; break; }
+            skip = any ? n : 0;             // a sign without digits is ignored (pileup.cpp:131-133)
+            next = q - region_off;
+            last = false;
+        } else if (car >> 31) {
+            skip = 1;                       // the hidden byte is the first of the next step
+        }
+        na += pop_count(bits32(B.a, cur) & cm);
+        nc += pop_count(bits32(B.c, cur) & cm);
+        ng += pop_count(bits32(B.g, cur) & cm);
+        nt += pop_count(bits32(B.t, cur) & cm);
+        ndot += pop_count(bits32(B.dot, cur) & cm);
+        cur = next;
+        if (last) running = false;
+    }
+    SID_SYNCWARP();
+    // '.' and ',' stand for the reference base (pileup.cpp:78-83); other reference characters drop them
+    const uint32_t rf = ref & 0xDFu;
+    o.profile = pack_profile(na + (rf == 'A' ? ndot : 0u), nc + (rf == 'C' ? ndot : 0u), ng + (rf == 'G' ? ndot : 0u),
+                             nt + (rf == 'T' ? ndot : 0u));
+    o.pos = (int32_t)acc;
+    o.status = LINE_OK;
+    return ok;
+}
+
+#if !defined(__CUDACC__)
+// Host check: classifies the whole line (plus slack) like the kernel's stage 1, then runs stage 2.
+inline bool parse_line_bits_host(const uint8_t* text, uint64_t len, uint64_t p, FastLine& o) {
+    const int64_t first = (int64_t)(p & ~(uint64_t)31) - 32;       // region and staging start (32-byte aligned, with lead-in)
+    uint64_t end = p;
+    while (end < len && text[end] != '\n') ++end;
+    const uint64_t avail64 = (((int64_t)end - first) + 256 + 31) & ~(uint64_t)31;
+    if (avail64 > (1u << 20)) return false;
+    static thread_local uint8_t scratch[(1u << 20) + 64] __attribute__((aligned(16)));
+    static thread_local uint32_t arr[8][(1u << 15) + 8];
+    for (uint64_t k = 0; k < avail64; ++k) {
+        const int64_t q = first + (int64_t)k;
+        scratch[k] = (q >= 0 && (uint64_t)q < len) ? text[q] : (uint8_t)'\n';
+    }
+    const uint32_t units = (uint32_t)(avail64 / 32);
+    for (uint32_t u = 0; u < units; ++u) {
+        uint32_t w[8];
+        memcpy(w, scratch + 32 * u, 32);
+        const ClassWords k = classify32(w);
+        arr[0][u] = k.term; arr[1][u] = k.a; arr[2][u] = k.c; arr[3][u] = k.g; arr[4][u] = k.t;
+        arr[5][u] = k.dot; arr[6][u] = k.caret; arr[7][u] = k.pm;
+    }
+    for (int i = 0; i < 8; ++i) arr[i][units] = arr[i][units + 1] = 0;
+    BitArrays B {arr[0], arr[1], arr[2], arr[3], arr[4], arr[5], arr[6], arr[7], units * 32};
+    return parse_line_bits(scratch, (uint32_t)avail64, 0, B, (uint32_t)((int64_t)p - first), o);
+}
+#endif
+
+}  // namespace sid

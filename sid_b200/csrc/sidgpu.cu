@@ -362,8 +362,11 @@ int run_tokenizer(sidgpu_ctx* ctx, const char* d_text, size_t text_len, size_t r
     const uint64_t tile0 = range_begin & ~(uint64_t)15;
     const uint64_t span = range_end - tile0;
     // a slice (one parse warp's share of a tile) should hold about 30 lines: 32 lanes, little overflow
-    uint32_t slice = (uint32_t)(ctx->avg_line_bytes * 29.5) & ~15u;
+    uint32_t slice = (uint32_t)(ctx->avg_line_bytes * 29.5) & ~31u;
     slice = std::max<uint32_t>(SLICE_MIN, std::min<uint32_t>(SLICE_MAX, slice));
+    // a parse warp also classifies the bytes after its slice that its last lines reach into
+    uint32_t ext = ((uint32_t)(ctx->avg_line_bytes * 1.25) + 31u) & ~31u;
+    ext = std::max<uint32_t>(128u, std::min<uint32_t>(2016u, ext));
     const uint64_t tile_bytes = (uint64_t)slice * TOK_PARSE_WARPS;
     const uint64_t n_tiles64 = (span + tile_bytes - 1) / tile_bytes;
     if (n_tiles64 > 0x7FFFFFFFull) return ctx->fail(SIDGPU_EINVAL, "range too large");
@@ -403,7 +406,9 @@ int run_tokenizer(sidgpu_ctx* ctx, const char* d_text, size_t text_len, size_t r
         p.slice_bytes = slice;
         p.text_stride = tok_text_stride(slice);
         p.lines_cap = slice / 8;
-        const uint32_t dyn_smem = tok_dyn_smem(slice);
+        p.ext_bytes = ext;
+        p.words_cap = tok_words_cap(slice, ext);
+        const uint32_t dyn_smem = tok_dyn_smem(slice, ext);
         int per_sm = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tokenize<true>, TOK_THREADS, dyn_smem) != cudaSuccess || per_sm < 1) per_sm = 1;
         const int max_ctas = ctx->sm_count * per_sm;
@@ -726,8 +731,8 @@ int sidgpu_create(const sidgpu_config* cfg, sidgpu_ctx** out) {
         cudaMemcpyAsync(ctx->quality_lut.p, lut.data(), lut.size() * 8, cudaMemcpyHostToDevice, ctx->stream);
         cudaStreamSynchronize(ctx->stream);
     }
-    if ((e = cudaFuncSetAttribute(k_tokenize<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tok_dyn_smem(SLICE_MAX))) != cudaSuccess ||
-        (e = cudaFuncSetAttribute(k_tokenize<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tok_dyn_smem(SLICE_MAX))) != cudaSuccess ||
+    if ((e = cudaFuncSetAttribute(k_tokenize<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tok_dyn_smem(SLICE_MAX, 2016))) != cudaSuccess ||
+        (e = cudaFuncSetAttribute(k_tokenize<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tok_dyn_smem(SLICE_MAX, 2016))) != cudaSuccess ||
         (e = cudaFuncSetAttribute(k_csv, cudaFuncAttributeMaxDynamicSharedMemorySize, CSV_STAGE)) != cudaSuccess) {
         ctx->err = std::string("shared memory opt-in: ") + cudaGetErrorString(e);
         return bail(SIDGPU_ECUDA);

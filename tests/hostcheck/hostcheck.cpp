@@ -10,6 +10,7 @@
 #include "../../sid_b200/csrc/parse.cuh"
 #ifdef SID_HAVE_FAST
 #include "../../sid_b200/csrc/parse_fast.cuh"
+#include "../../sid_b200/csrc/parse_bits.cuh"
 #endif
 
 using namespace sid;
@@ -67,6 +68,36 @@ int64_t hc_compare_parsers(const uint8_t* text, uint64_t len, uint64_t* n_fast) 
     }
     if (n_fast) *n_fast = fast;
     return k;
+}
+
+// Same comparison for the bit-parallel tokenizer (parse_bits.cuh).
+int64_t hc_compare_parsers_bits(const uint8_t* text, uint64_t len, uint64_t* n_fast) {
+    FlatSrc src {text, len};
+    int64_t k = 0;
+    uint64_t fast = 0;
+    for (uint64_t p = 0; p < len; ++p) {
+        if (text[p] == '\n' || (p > 0 && text[p - 1] != '\n')) continue;
+        ParsedLine a;
+        parse_line(src, p, false, a);
+        FastLine b;
+        if (parse_line_bits_host(text, len, p, b)) {
+            ++fast;
+            if (a.status != LINE_OK || b.status != LINE_OK || a.profile != b.profile || a.pos != b.pos ||
+                a.chrom_off != b.chrom_off || a.chrom_len != b.chrom_len) return -(k + 1);
+        }
+        ++k;
+    }
+    if (n_fast) *n_fast = fast;
+    return k;
+}
+
+// classify32 on one 32-byte unit: out[0..9] = term nl a c g t dot caret pm high
+void hc_classify32(const uint8_t* bytes, uint32_t* out) {
+    uint32_t w[8];
+    memcpy(w, bytes, 32);
+    const ClassWords k = classify32(w);
+    out[0] = k.term; out[1] = k.nl; out[2] = k.a; out[3] = k.c; out[4] = k.g; out[5] = k.t; out[6] = k.dot; out[7] = k.caret;
+    out[8] = k.pm; out[9] = k.high;
 }
 #endif
 

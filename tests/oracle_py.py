@@ -187,6 +187,9 @@ def hostcheck():
             h.hc_parse_line_fast.argtypes = [ctypes.c_char_p, ctypes.c_uint64, ctypes.c_uint64, ctypes.POINTER(HcLine)]
             h.hc_compare_parsers.restype = ctypes.c_int64
             h.hc_compare_parsers.argtypes = [ctypes.c_char_p, ctypes.c_uint64, ctypes.POINTER(ctypes.c_uint64)]
+            h.hc_compare_parsers_bits.restype = ctypes.c_int64
+            h.hc_compare_parsers_bits.argtypes = [ctypes.c_char_p, ctypes.c_uint64, ctypes.POINTER(ctypes.c_uint64)]
+            h.hc_classify32.argtypes = [ctypes.c_char_p, ctypes.POINTER(ctypes.c_uint32)]
         h.hc_fmt_g6.argtypes = [ctypes.c_double, ctypes.c_char_p]
         h.hc_fmt_i32.argtypes = [ctypes.c_int32, ctypes.c_char_p]
         h.hc_major_alleles.argtypes = [ctypes.c_uint64, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]

@@ -198,3 +198,42 @@ def test_fast_tokenizer_covers_normal_text(native, name):
     assert k > 0
     if name != "edge.plp":
         assert nf.value == k          # every ordinary line is handled without the byte-wise fallback
+
+
+def test_classify32_equals_per_byte_classes(native):
+    """The bit-plane classifier (transpose + boolean functions of the planes) against a plain
+    per-byte definition of every character class, on all byte values and random units."""
+    hc = op.hostcheck()
+    rnd = random.Random(9)
+    units = [bytes((32 * k + i) & 0xFF for i in range(32)) for k in range(8)]
+    units += [bytes(rnd.getrandbits(8) for _ in range(32)) for _ in range(2000)]
+    units += [bytes(rnd.choice(b".,ACGTacgtNn*$^+-0123456789\t\n ~") for _ in range(32)) for _ in range(2000)]
+    out = (ctypes.c_uint32 * 10)()
+    defs = [lambda b: b <= 0x20, lambda b: b == 10, lambda b: b in b"Aa", lambda b: b in b"Cc", lambda b: b in b"Gg",
+            lambda b: b in b"Tt", lambda b: b in b".,", lambda b: b == ord("^"), lambda b: b in b"+-", lambda b: b >= 0x80]
+    for u in units:
+        hc.hc_classify32(u, out)
+        for k, f in enumerate(defs):
+            want = sum(1 << i for i in range(32) if f(u[i]))
+            assert out[k] == want, (k, u)
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_bit_tokenizer_equals_scalar_on_adversarial_lines(native, seed):
+    hc = op.hostcheck()
+    text = _adversarial_text(seed, 20000)
+    nf = ctypes.c_uint64()
+    k = hc.hc_compare_parsers_bits(text, len(text), ctypes.byref(nf))
+    assert k > 0, text.split(b"\n")[-k - 1][:200] if k < 0 else None
+    assert nf.value > k // 100
+
+
+@pytest.mark.parametrize("name", ["depth30.plp", "depth500.plp", "depth5.plp", "quality30.plp", "edge.plp"])
+def test_bit_tokenizer_covers_normal_text(native, name):
+    hc = op.hostcheck()
+    text = read(name)
+    nf = ctypes.c_uint64()
+    k = hc.hc_compare_parsers_bits(text, len(text), ctypes.byref(nf))
+    assert k > 0
+    if name != "edge.plp":
+        assert nf.value == k
