@@ -18,10 +18,48 @@ SID_HD int fmt_i32(int32_t v, char* out) {
 }
 
 SID_HD int digits_i32(int32_t v) {
-    uint32_t u = v < 0 ? 0u - (uint32_t)v : (uint32_t)v;
+    const uint32_t u = v < 0 ? 0u - (uint32_t)v : (uint32_t)v;
     int n = v < 0 ? 2 : 1;
-    while (u >= 10) { u /= 10; ++n; }
+    n += u >= 10u;
+    n += u >= 100u;
+    n += u >= 1000u;
+    n += u >= 10000u;
+    n += u >= 100000u;
+    n += u >= 1000000u;
+    n += u >= 10000000u;
+    n += u >= 100000000u;
+    n += u >= 1000000000u;
     return n;
+}
+
+// Four decimal digits of x < 10000 as four bytes, most significant digit in the lowest byte
+// (multiply-shift divisions: x/100 == x*5243>>19 for x < 43699, a/10 == a*205>>11 for a < 1029).
+SID_HD uint32_t digits4(uint32_t x) {
+    const uint32_t a = (x * 5243u) >> 19, b = x - a * 100u;
+    const uint32_t d0 = (a * 205u) >> 11, d1 = a - d0 * 10u;
+    const uint32_t d2 = (b * 205u) >> 11, d3 = b - d2 * 10u;
+    return d0 | (d1 << 8) | (d2 << 16) | (d3 << 24);
+}
+
+// fmt_i32 without a division loop: the digits of |v| in three groups (2 + 4 + 4), then the
+// significant ones are written out.  Same text as fmt_i32.
+SID_HD int fmt_i32_fast(int32_t v, char* out) {
+    const uint32_t u = v < 0 ? 0u - (uint32_t)v : (uint32_t)v;
+    const uint32_t top = u / 100000000u;                   // 0..42
+    const uint32_t rest = u - top * 100000000u;
+    const uint32_t mid = rest / 10000u, low = rest - mid * 10000u;
+    const uint32_t g0 = digits4(top), g1 = digits4(mid), g2 = digits4(low);
+    // twelve digit bytes d[0..11]: g0 g1 g2, text order
+    const int nd = digits_i32(v < 0 ? (int32_t)(0u - u) : v) - (v < 0 ? 1 : 0);
+    int len = 0;
+    if (v < 0) out[len++] = '-';
+    const int skip = 12 - nd;
+#pragma unroll
+    for (int k = 0; k < 12; ++k) {
+        const uint32_t g = k < 4 ? g0 : (k < 8 ? g1 : g2);
+        if (k >= skip) out[len + k - skip] = (char)('0' + ((g >> (8 * (k & 3))) & 0xFFu));
+    }
+    return len + nd;
 }
 
 // round_half_even(m * 2^e2 * 10^j) for j >= 0, result known to be < 2^40.

@@ -90,7 +90,7 @@ struct CsvParams {
 // Rows of one tile are assembled in shared memory and copied out with aligned 16-byte stores.
 // The staging area starts at (global offset of the tile's first byte) mod 16, so 16-byte chunks of
 // shared memory line up with 16-byte chunks of the output buffer.
-constexpr int CSV_STAGE = 72 * 1024;          // bytes of rows one tile may stage (else: direct global writes)
+constexpr int CSV_STAGE = 52 * 1024;          // bytes of rows one tile may stage (else: direct global writes)
 
 __global__ void __launch_bounds__(CSV_THREADS) k_csv(const CsvParams p) {
     extern __shared__ __align__(16) char s_stage[];
@@ -187,7 +187,7 @@ __global__ void __launch_bounds__(CSV_THREADS) k_csv(const CsvParams p) {
             for (uint32_t i = 0; i < nlen[k]; ++i) w[i] = (char)nm[2 + i];
             w += nlen[k];
             *w++ = ',';
-            w += fmt_i32(pos[k], w);
+            w += fmt_i32_fast(pos[k], w);
             // suffix: three aligned 16-byte loads, copied byte-wise into the (unaligned) row
             const uint4* sv = reinterpret_cast<const uint4*>(sfxp[k]);
             const uint32_t sl = slen[k];

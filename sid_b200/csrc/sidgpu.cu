@@ -992,7 +992,9 @@ int sidgpu_emit_csv(sidgpu_ctx* ctx, uint64_t site_begin, uint64_t n_sites, char
     p.bytes_out = ctl_field(ctx, &Control::csv_bytes);
     p.rows_out = ctl_field(ctx, &Control::csv_rows);
     p.n_tiles = n_tiles;
-    const unsigned grid = (unsigned)std::min<uint64_t>(n_tiles, (uint64_t)ctx->sm_count * 3);
+    int csv_per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&csv_per_sm, k_csv, CSV_THREADS, CSV_STAGE) != cudaSuccess || csv_per_sm < 1) csv_per_sm = 1;
+    const unsigned grid = (unsigned)std::min<uint64_t>(n_tiles, (uint64_t)ctx->sm_count * csv_per_sm);
     {
         ProfScope prof(ctx, PROF_CSV);
         k_csv<<<grid, CSV_THREADS, CSV_STAGE, ctx->stream>>>(p);

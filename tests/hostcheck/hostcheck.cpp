@@ -103,6 +103,8 @@ void hc_classify32(const uint8_t* bytes, uint32_t* out) {
 
 int hc_fmt_g6(double x, char* out) { int n = fmt_g6(x, out); out[n] = 0; return n; }
 int hc_fmt_i32(int32_t v, char* out) { int n = fmt_i32(v, out); out[n] = 0; return n; }
+int hc_fmt_i32_fast(int32_t v, char* out) { int n = fmt_i32_fast(v, out); out[n] = 0; return n; }
+int hc_digits_i32(int32_t v) { return digits_i32(v); }
 
 void hc_major_alleles(uint64_t profile, int* f, int* s) { major_alleles(profile, *f, *s); }
 

@@ -78,9 +78,15 @@ def test_format_g_matches_printf(native):
 def test_format_int(native):
     hc = op.hostcheck()
     buf = ctypes.create_string_buffer(16)
-    for v in [0, 1, -1, 9, 10, 99, 100, 2147483647, -2147483648, 1337, -5]:
+    rnd = random.Random(3)
+    vals = [0, 1, -1, 9, 10, 99, 100, 2147483647, -2147483648, 1337, -5, 99999999, 100000000, 999999999, 1000000000, 9999, 10000]
+    vals += [rnd.randrange(-2**31, 2**31) for _ in range(20000)] + [rnd.randrange(0, 10 ** rnd.randrange(1, 10)) for _ in range(20000)]
+    hc.hc_fmt_i32_fast.argtypes = [ctypes.c_int32, ctypes.c_char_p]
+    for v in vals:
         hc.hc_fmt_i32(v, buf)
         assert buf.value.decode() == str(v)
+        n = hc.hc_fmt_i32_fast(v, buf)
+        assert buf.value.decode() == str(v) and n == len(str(v)) == hc.hc_digits_i32(v)
 
 
 @pytest.mark.parametrize("case", [c for c in MANIFEST["cases"] if "quality" not in c["flags"]], ids=lambda c: c["csv"])

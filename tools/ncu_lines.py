@@ -14,7 +14,7 @@ def sass_lines(lib, kernel):
     d = tempfile.mkdtemp()
     subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(lib)], cwd=d, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
     cub = [f for f in os.listdir(d) if f.endswith(".cubin")][0]
-    dis = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(d, cub)], stdout=subprocess.PIPE, text=True).stdout.splitlines()
+    dis = subprocess.run(["nvdisasm", "-gi", "-c", os.path.join(d, cub)], stdout=subprocess.PIPE, text=True).stdout.splitlines()
     out, inside, cur = [], False, ("?", 0)
     for ln in dis:
         if ln.startswith("\t.section\t.text."):
@@ -22,10 +22,14 @@ def sass_lines(lib, kernel):
             continue
         if not inside:
             continue
-        m = re.search(r'//## File "([^"]+)", line (\d+)', ln)
+        m = re.search(r'//## File "([^"]+)", line (\d+)(?: inlined at "([^"]+)", line (\d+))?', ln)
         if m:
-            # keep the outermost user line of an inlined chain: nvdisasm prints "inlined at" lines after
-            cur = (os.path.basename(m.group(1)), int(m.group(2)))
+            if OUTER and m.group(3):
+                # attribute to the call site: walk to the outermost frame (nvdisasm prints one level per line,
+                # innermost first; the next "//##" lines continue the chain)
+                cur = (os.path.basename(m.group(3)), int(m.group(4)))
+            elif not (OUTER and ln.lstrip().startswith("//## File") and "inlined at" not in ln and False):
+                cur = (os.path.basename(m.group(1)), int(m.group(2)))
             continue
         m = re.match(r"\s+/\*([0-9a-f]{4,})\*/\s+(.*?);", ln)
         if m:
@@ -33,6 +37,9 @@ def sass_lines(lib, kernel):
     return out
 
 
+OUTER = "--outer" in sys.argv
+if OUTER:
+    sys.argv.remove("--outer")
 SORT = 2 if "--by-samples" in sys.argv else 0
 if "--by-samples" in sys.argv:
     sys.argv.remove("--by-samples")
