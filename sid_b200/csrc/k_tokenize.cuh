@@ -420,7 +420,8 @@ __global__ void __launch_bounds__(TOK_THREADS) k_tokenize(const TokParams p) {
             LineResult r;
             r.status = LINE_MALFORMED;
             bool fast = false;
-            if (FAST && !p.want_qual) {
+            if (FAST) {
+                // (with want_qual the quality columns are validated by k_quality, which re-reads the line)
                 FastLine fl;
                 fast = parse_line_bits(txt, tile_smem, region_off, B, TILE_PAD + off, fl);
                 r.status = fl.status; r.pos = fl.pos; r.profile = fl.profile; r.chrom_off = fl.chrom_off; r.chrom_len = fl.chrom_len;

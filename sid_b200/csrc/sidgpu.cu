@@ -354,7 +354,7 @@ const char* status_text(int st) {
 // Runs K1 over [range_begin, range_end) writing sites from index site_base.  On return
 // *n_out holds the number of sites the range produced.
 int run_tokenizer(sidgpu_ctx* ctx, const char* d_text, size_t text_len, size_t range_begin, size_t range_end,
-                  bool want_qual, bool use_table, uint64_t site_base, bool keep_sites, uint64_t* n_out) {
+                  bool want_qual, bool use_table, uint64_t site_base, bool keep_sites, uint64_t* n_out, bool strict_qual = false) {
     if (((uintptr_t)d_text & 15) != 0) return ctx->fail(SIDGPU_EINVAL, "d_text must be 16-byte aligned");
     if (range_begin > range_end || range_end > text_len) return ctx->fail(SIDGPU_EINVAL, "bad range [%zu,%zu) for text of %zu bytes", range_begin, range_end, text_len);
     *n_out = 0;
@@ -415,7 +415,9 @@ int run_tokenizer(sidgpu_ctx* ctx, const char* d_text, size_t text_len, size_t r
         const unsigned grid = (unsigned)std::min<uint64_t>(n_tiles, (uint64_t)max_ctas);
         {
             ProfScope prof(ctx, PROF_TOKENIZE);
-            if (want_qual) k_tokenize<false><<<grid, TOK_THREADS, dyn_smem, ctx->stream>>>(p);
+            // strict_qual (sidgpu_tokenize with want_qual): the byte-wise grammar also validates the quality
+            // columns; inside a quality session k_quality re-reads every line and reports them itself
+            if (want_qual && strict_qual) k_tokenize<false><<<grid, TOK_THREADS, dyn_smem, ctx->stream>>>(p);
             else k_tokenize<true><<<grid, TOK_THREADS, dyn_smem, ctx->stream>>>(p);
         }
         TRY(check_launch(ctx, "k_tokenize"));
@@ -844,7 +846,7 @@ int sidgpu_tokenize(sidgpu_ctx* ctx, const char* d_text, size_t text_len, size_t
     ctx->want_line_off = want_qual != 0;
     TRY(reset_table(ctx));
     uint64_t n = 0;
-    TRY(run_tokenizer(ctx, d_text, text_len, range_begin, range_end, want_qual != 0, true, 0, false, &n));
+    TRY(run_tokenizer(ctx, d_text, text_len, range_begin, range_end, want_qual != 0, true, 0, false, &n, true));
     ctx->n_sites_total = n;
     ctx->chunk_begin = 0;
     ctx->chunk_sites = n;
@@ -1002,7 +1004,10 @@ int sidgpu_emit_csv(sidgpu_ctx* ctx, uint64_t site_begin, uint64_t n_sites, char
     TRY(check_launch(ctx, "k_csv"));
     TRY(sync_ctl(ctx));
     if (is_quality && ctx->h_ctl->error != ~0ull) {
-        return ctx->fail(SIDGPU_EQUAL_SHORT, "%s (line starting at byte %llu)", status_text((int)(ctx->h_ctl->error & 7)), ctx->h_ctl->error >> 3);
+        const int st = (int)(ctx->h_ctl->error & 7);
+        const int code = st == LINE_MISSING_MAPQ ? SIDGPU_EMISSING_MAPQ : st == LINE_QUAL_SHORT ? SIDGPU_EQUAL_SHORT
+                         : st == LINE_MALFORMED ? SIDGPU_EMALFORMED : SIDGPU_EINTERNAL;
+        return ctx->fail(code, "%s (line starting at byte %llu)", status_text(st), ctx->h_ctl->error >> 3);
     }
     if (bytes_out) *bytes_out = ctx->h_ctl->csv_bytes;
     if (rows_out) *rows_out = ctx->h_ctl->csv_rows;
