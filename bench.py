@@ -247,7 +247,15 @@ def run_ours(args):
             fit = shard.distributed_fit(lambda: sums, local_objective, ints, flt)
             ctx.set_fit(fit["pi"], fit["eps"], fit["nd"])
             state["fit"] = {k: fit[k] for k in ("pi", "eps", "iterations", "evaluations")}
-        if not ctx_streams:
+            if args.method == "likelihood_ratio":
+                # Benjamini-Hochberg needs the unique profiles of all shards: gather, merge, finish on the device
+                local = ctx.histogram(4)[:2]
+                gathered = [None] * world
+                dist.all_gather_object(gathered, (local[0], local[1]))
+                merged, _ = shard.merge_histograms(gathered)
+                ctx.finish_global(merged)
+                state["lr_global_unique"] = int(len(merged))
+        if not ctx_streams and not (needs_fit and world > 1 and args.method == "likelihood_ratio"):
             ctx.finish()
             if "fit" not in state:
                 f = ctx.session_fit()

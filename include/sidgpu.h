@@ -190,6 +190,12 @@ int sidgpu_lynch_fit(sidgpu_ctx* ctx, const double nd[4], sidgpu_fit* out);
  * of the local optimiser: a multi-GPU host fits on the all-reduced objective and hands every rank
  * the same result. */
 int sidgpu_set_fit(sidgpu_ctx* ctx, double pi, double eps, const double nd[4]);
+/* sidgpu_finish for a position-sharded `likelihood_ratio` session: Benjamini-Hochberg ranks over the
+ * unique profiles of ALL shards (call.cpp:105-106, m = number of unique profiles), so the host merges
+ * the shards' histograms (sidgpu_histogram) and hands every rank the merged profile list, sorted in
+ * the reference's lexicographic order (n_global packed profiles, host memory).  Requires sidgpu_set_fit.
+ * p-values, the BH adjustment and the classification of this rank's own profiles run on the device. */
+int sidgpu_finish_global(sidgpu_ctx* ctx, const uint64_t* h_profiles_sorted, uint64_t n_global);
 /* The fit the session used (after sidgpu_finish). */
 int sidgpu_session_fit(sidgpu_ctx* ctx, sidgpu_fit* out, double nd[4], uint64_t* n_unique);
 

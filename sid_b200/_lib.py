@@ -73,6 +73,7 @@ PROTOTYPES = {
                                                       ctypes.c_void_p]),
     "sidgpu_lynch_objective": (ctypes.c_int, [ctypes.c_void_p, c_double_p, ctypes.c_double, ctypes.c_double, c_double_p]),
     "sidgpu_lynch_fit": (ctypes.c_int, [ctypes.c_void_p, c_double_p, ctypes.POINTER(Fit)]),
+    "sidgpu_finish_global": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, c_u64]),
     "sidgpu_session_fit": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(Fit), c_double_p, c_u64_p]),
     "sidgpu_bh_adjust": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, c_u64, ctypes.c_void_p]),
     "sidgpu_format_g": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, c_u64, ctypes.c_void_p]),

@@ -250,6 +250,12 @@ class Context:
         a = (ctypes.c_double * 4)(*nd)
         self._ck(self.lib.sidgpu_set_fit(self.h, pi, eps, a))
 
+    def finish_global(self, profiles_sorted):
+        """sidgpu_finish for a sharded likelihood_ratio session: the merged unique profiles of all shards,
+        in the reference's lexicographic order."""
+        p = np.ascontiguousarray(profiles_sorted, dtype=np.uint64)
+        self._ck(self.lib.sidgpu_finish_global(self.h, p.ctypes.data if p.size else None, p.size))
+
     def lynch_objective_partial(self, nd, pi, eps, d_out):
         """Leaves this rank's -log likelihood sum at device pointer d_out (no host sync)."""
         a = (ctypes.c_double * 4)(*nd)

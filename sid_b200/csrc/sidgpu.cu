@@ -455,6 +455,20 @@ __global__ void k_insert_profiles(TableView t, const uint64_t* profiles, const u
     atomicAdd(&t.counts[slot], weights ? (unsigned long long)weights[i] : 1ull);
 }
 
+// For each local table entry: its row in a merged, lexicographically sorted profile list
+// (0xFFFFFFFF: not present there, i.e. coverage < 4 -> dropped, call.cpp:66-70,131-140).
+__global__ void k_map_entries(TableView t, uint32_t n_entries, const unsigned long long* sorted_profiles, uint32_t n, uint32_t* entry_to_unique) {
+    const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_entries) return;
+    const uint64_t key = profile_sort_key(t.keys[t.entry_list[e]]);
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (profile_sort_key(sorted_profiles[mid]) < key) lo = mid + 1; else hi = mid;
+    }
+    entry_to_unique[e] = (lo < n && profile_sort_key(sorted_profiles[lo]) == key) ? lo : 0xFFFFFFFFu;
+}
+
 __global__ void k_count_slots(const uint32_t* slot, uint64_t begin, uint64_t n, unsigned long long* counts) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) atomicAdd(&counts[slot[begin + i]], 1ull);
@@ -957,6 +971,50 @@ int sidgpu_finish(sidgpu_ctx* ctx) {
             ctx->classified = n_entries;
         }
     }
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->phase = PHASE_FINISHED;
+    return SIDGPU_OK;
+}
+
+int sidgpu_finish_global(sidgpu_ctx* ctx, const uint64_t* h_profiles_sorted, uint64_t n_global) {
+    if (!ctx || (n_global && !h_profiles_sorted)) return SIDGPU_EINVAL;
+    if (ctx->phase != PHASE_FEED) return ctx->fail(SIDGPU_ESTATE, "sidgpu_finish_global outside a session");
+    if (ctx->params.method != SIDGPU_METHOD_LIKELIHOOD_RATIO) return ctx->fail(SIDGPU_EINVAL, "sidgpu_finish_global is for likelihood_ratio sessions");
+    if (!ctx->params.fit_given) return ctx->fail(SIDGPU_ESTATE, "sidgpu_finish_global needs sidgpu_set_fit first");
+    if (n_global > 0x7FFFFFFFull) return ctx->fail(SIDGPU_EINVAL, "too many unique profiles");
+    CK(cudaSetDevice(ctx->device));
+    ctx->fit.pi = ctx->params.fit_pi;
+    ctx->fit.eps = ctx->params.fit_eps;
+    ctx->fit.converged = 1;
+    for (int i = 0; i < 4; ++i) ctx->fit_nd[i] = ctx->params.fit_nd[i];
+    ctx->fit_done = true;
+    TRY(sync_ctl(ctx));
+    const uint32_t n_entries = ctx->h_ctl->n_entries;
+    const uint32_t nu = (uint32_t)n_global;
+    TRY(ensure(ctx, ctx->u_profile, (size_t)std::max(nu, 1u) * 8));
+    TRY(ensure(ctx, ctx->p_hom, (size_t)std::max(nu, 1u) * 8));
+    TRY(ensure(ctx, ctx->p_het, (size_t)std::max(nu, 1u) * 8));
+    TRY(ensure(ctx, ctx->adj_hom, (size_t)std::max(nu, 1u) * 8));
+    TRY(ensure(ctx, ctx->adj_het, (size_t)std::max(nu, 1u) * 8));
+    TRY(ensure(ctx, ctx->entry_to_unique, (size_t)std::max<uint32_t>(n_entries, 1) * 4));
+    if (nu) {
+        CK(cudaMemcpyAsync(ctx->u_profile.p, h_profiles_sorted, (size_t)nu * 8, cudaMemcpyHostToDevice, ctx->stream));
+        k_lr_pvalues<<<(nu + 255) / 256, 256, 0, ctx->stream>>>((const unsigned long long*)ctx->u_profile.p, nu,
+                                                                host_lynch_consts(ctx->fit_nd, ctx->fit.eps),
+                                                                ctx->params.estimate_prior, ctx->fit.pi,
+                                                                (double*)ctx->p_hom.p, (double*)ctx->p_het.p);
+        TRY(check_launch(ctx, "k_lr_pvalues"));
+        TRY(bh_adjust(ctx, (const double*)ctx->p_hom.p, nu, (double*)ctx->adj_hom.p));
+        TRY(bh_adjust(ctx, (const double*)ctx->p_het.p, nu, (double*)ctx->adj_het.p));
+    }
+    if (n_entries) {
+        k_map_entries<<<(n_entries + 255) / 256, 256, 0, ctx->stream>>>(ctx->tab, n_entries, (const unsigned long long*)ctx->u_profile.p, nu,
+                                                                         (uint32_t*)ctx->entry_to_unique.p);
+        TRY(check_launch(ctx, "k_map_entries"));
+        TRY(classify_entries(ctx, 0, n_entries));
+        ctx->classified = n_entries;
+    }
+    ctx->n_unique = nu;
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->phase = PHASE_FINISHED;
     return SIDGPU_OK;

@@ -55,6 +55,29 @@ def distributed_fit(local_sums, local_objective, all_reduce_ints, all_reduce_flo
             "evaluations": r["evaluations"], "converged": r["converged"]}
 
 
+def profile_sort_key(p):
+    """Lexicographic order of std::array<uint16_t,4> (pileup.cpp:179-182) for packed profiles (numpy uint64)."""
+    import numpy as np
+    p = np.asarray(p, dtype=np.uint64)
+    m = np.uint64(0xFFFF)
+    return ((p & m) << np.uint64(48)) | (((p >> np.uint64(16)) & m) << np.uint64(32)) | (((p >> np.uint64(32)) & m) << np.uint64(16)) | (p >> np.uint64(48))
+
+
+def merge_histograms(tables):
+    """Merges per-rank (profiles, counts) histograms: one entry per profile, counts summed, in the
+    reference's lexicographic order (countUniqueProfiles over the whole genome)."""
+    import numpy as np
+    prof = np.concatenate([np.asarray(t[0], dtype=np.uint64) for t in tables]) if tables else np.zeros(0, np.uint64)
+    cnt = np.concatenate([np.asarray(t[1], dtype=np.uint64) for t in tables]) if tables else np.zeros(0, np.uint64)
+    if prof.size == 0:
+        return prof, cnt
+    u, inv = np.unique(prof, return_inverse=True)
+    c = np.zeros(len(u), dtype=np.uint64)
+    np.add.at(c, inv, cnt)
+    order = np.argsort(profile_sort_key(u), kind="stable")
+    return u[order], c[order]
+
+
 def torch_collectives(dist, device):
     """(all_reduce_ints, all_reduce_float) over torch.distributed for distributed_fit."""
     import torch
@@ -83,9 +106,6 @@ def call_sharded(ctx, d_text, text_len, rank, world, params, dist=None, device=N
     needs_fit = params.method in (1, 2) or params.estimate_prior
     fit = None
     if needs_fit and world > 1 and not params.fit_given:
-        if params.method == 2:
-            raise NotImplementedError("likelihood_ratio needs the merged unique-profile table (Benjamini-Hochberg "
-                                      "ranks over all profiles); run it on one GPU")
         ints, flt = torch_collectives(dist, device)
         obj = torch.zeros(1, dtype=torch.float64, device=device)
         _, sums = ctx.histogram_sums(4)
@@ -96,6 +116,15 @@ def call_sharded(ctx, d_text, text_len, rank, world, params, dist=None, device=N
 
         fit = distributed_fit(lambda: sums, local_objective, ints, flt)
         ctx.set_fit(fit["pi"], fit["eps"], fit["nd"])
+        if params.method == 2:
+            # Benjamini-Hochberg ranks over the unique profiles of the whole genome: gather the shards'
+            # histograms (a few thousand entries each), merge on the host, finish on the device
+            local = ctx.histogram(4)[:2]
+            gathered = [None] * world
+            dist.all_gather_object(gathered, (local[0], local[1]))
+            merged, _ = merge_histograms(gathered)
+            ctx.finish_global(merged)
+            return n, fit
     ctx.finish()
     if needs_fit and fit is None:
         fit = ctx.session_fit()

@@ -21,13 +21,13 @@ def _emit(ctx, n):
         buf.free()
 
 
-@pytest.mark.parametrize("method", ["local", "bayes"])
+@pytest.mark.parametrize("method", ["local", "bayes", "likelihood_ratio"])
 def test_two_shards_equal_one(native, gpu_ctx, method):
     import sid_b200
     text = read("depth30_two_chroms.plp")
     params = sid_b200.Context.make_params(method)
     whole_rows, _, _ = gpu_ctx.call_host(text, params)
-    whole_fit = gpu_ctx.session_fit() if method == "bayes" else None
+    whole_fit = gpu_ctx.session_fit() if method != "local" else None
     ctxs = [sid_b200.Context(), sid_b200.Context()]
     bufs = [c.upload_text(text) for c in ctxs]
     try:
@@ -36,7 +36,7 @@ def test_two_shards_equal_one(native, gpu_ctx, method):
         for c, d, (b, e) in zip(ctxs, bufs, ranges):
             c.begin(sid_b200.Context.make_params(method))
             ns.append(c.feed(d, len(text), b, e))
-        if method == "bayes":
+        if method != "local":
             sums = [c.histogram_sums(4)[1] for c in ctxs]
             fit = shard.distributed_fit(lambda: [sum(s[i] for s in sums) for i in range(5)],
                                         lambda nd, pi, eps: sum(c.lynch_objective(nd, pi, eps) for c in ctxs),
@@ -47,9 +47,20 @@ def test_two_shards_equal_one(native, gpu_ctx, method):
             assert np.allclose(fit["nd"], whole_fit["nd"], rtol=0, atol=1e-15)
             for c in ctxs:
                 c.set_fit(fit["pi"], fit["eps"], fit["nd"])
+        merged = None
+        if method == "likelihood_ratio":
+            merged, counts = shard.merge_histograms([c.histogram(4)[:2] for c in ctxs])
+            o = op.oracle_call(text, "likelihood_ratio")
+            prof = o["profiles"]
+            cov = op.unpack_profiles(prof).astype(np.int64).sum(axis=1)
+            wu, wc = op.oracle_unique(prof[cov >= 4])
+            assert np.array_equal(merged, wu) and np.array_equal(counts, wc)      # == countUniqueProfiles of the whole text
         rows = b""
         for c, n in zip(ctxs, ns):
-            c.finish()
+            if merged is not None:
+                c.finish_global(merged)
+            else:
+                c.finish()
             r, _ = _emit(c, n)
             rows += r
         n, diffs = op.compare_csv(rows, whole_rows)

@@ -104,3 +104,18 @@ def test_distributed_fit_two_ranks(native):
     assert f0["converged"]
     assert abs(f0["pi"] - want["pi"]) <= 1e-6 * want["pi"] and abs(f0["eps"] - want["eps"]) <= 1e-6 * want["eps"]
     assert f0["iterations"] == want["iterations"]
+
+
+def test_merge_histograms_equals_count_unique(native):
+    """Merging per-shard histograms gives countUniqueProfiles of the whole text (order included)."""
+    text = read("depth30.plp")
+    o = op.oracle_call(text, "local")
+    prof = o["profiles"]
+    wu, wc = op.oracle_unique(prof)
+    parts = np.array_split(prof, 3)
+    tables = []
+    for part in parts:
+        u, c = np.unique(part, return_counts=True)
+        tables.append((u, c.astype(np.uint64)))
+    mu, mc = shard.merge_histograms(tables)
+    assert np.array_equal(mu, wu) and np.array_equal(mc, wc)
