@@ -71,7 +71,8 @@ constexpr int CSV_PER_THREAD = 4;
 constexpr int CSV_TILE = CSV_THREADS * CSV_PER_THREAD;
 
 struct CsvParams {
-    uint64_t site_begin, n_sites;
+    uint64_t site_begin, n_sites;    // file-order range of the store
+    const uint32_t* order;           // file index -> storage index
     const int32_t* pos;
     const uint32_t* slot;
     const uint32_t* name_ref;
@@ -99,13 +100,29 @@ __global__ void __launch_bounds__(CSV_THREADS) k_csv(const CsvParams p) {
     __shared__ uint32_t s_warp_sums[CSV_THREADS / 32];
     __shared__ uint32_t s_warp_rows[CSV_THREADS / 32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // storage indices of this thread's four sites of a tile (0xFFFFFFFF past the end)
+    auto load_order = [&](uint32_t tile, uint32_t (&ord)[CSV_PER_THREAD]) {
+        const uint64_t first = (uint64_t)tile * CSV_TILE + (uint64_t)tid * CSV_PER_THREAD;
+#pragma unroll
+        for (int k = 0; k < CSV_PER_THREAD; ++k) ord[k] = 0xFFFFFFFFu;
+        if (tile >= p.n_tiles || first >= p.n_sites) return;
+        const uint32_t* src = p.order + p.site_begin + first;
+        if (first + CSV_PER_THREAD <= p.n_sites && ((uintptr_t)src & 15u) == 0) {
+            const uint4 v = __ldg(reinterpret_cast<const uint4*>(src));
+            ord[0] = v.x; ord[1] = v.y; ord[2] = v.z; ord[3] = v.w;
+        } else {
+#pragma unroll
+            for (int k = 0; k < CSV_PER_THREAD; ++k) if (first + k < p.n_sites) ord[k] = __ldg(src + k);
+        }
+    };
     for (;;) {
         __syncthreads();
-        if (tid == 0) s_tile = atomicAdd(p.ticket, 1u);
+        if (tid == 0) s_tile = atomicAdd(p.ticket, 1u);     // in order: the look-back below needs every earlier tile started
         __syncthreads();
         const uint32_t tile = s_tile;
         if (tile >= p.n_tiles) break;
-        const uint64_t first = (uint64_t)tile * CSV_TILE + (uint64_t)tid * CSV_PER_THREAD;
+        uint32_t ord[CSV_PER_THREAD];
+        load_order(tile, ord);
         uint32_t len[CSV_PER_THREAD], nlen[CSV_PER_THREAD], slen[CSV_PER_THREAD], nref[CSV_PER_THREAD];
         int32_t pos[CSV_PER_THREAD];
         const char* sfxp[CSV_PER_THREAD];
@@ -113,9 +130,8 @@ __global__ void __launch_bounds__(CSV_THREADS) k_csv(const CsvParams p) {
 #pragma unroll
         for (int k = 0; k < CSV_PER_THREAD; ++k) {
             len[k] = 0;
-            const uint64_t i = first + k;
-            if (i < p.n_sites) {
-                const uint64_t site = p.site_begin + i;
+            if (ord[k] != 0xFFFFFFFFu) {
+                const uint64_t site = ord[k];
                 const char* sfx = p.site_suffix ? p.site_suffix + site * SUFFIX_BYTES
                                                 : p.table.suffix + (size_t)p.slot[site] * SUFFIX_BYTES;
                 sfxp[k] = sfx;
@@ -223,6 +239,7 @@ __global__ void __launch_bounds__(CSV_THREADS) k_csv(const CsvParams p) {
 // Per-site records instead of text (OutputRecord, call.hpp:14-27).
 struct RecordParams {
     uint64_t site_begin, n_sites;
+    const uint32_t* order;
     const uint32_t* slot;
     TableView table;
     uint8_t* label;
@@ -234,7 +251,7 @@ struct RecordParams {
 __global__ void k_records(const RecordParams p) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= p.n_sites) return;
-    const uint32_t s = p.slot[p.site_begin + i];
+    const uint32_t s = p.slot[p.order[p.site_begin + i]];
     if (p.label) p.label[i] = p.table.label[s];
     if (p.gt) { p.gt[2 * i] = p.table.gt[2 * s]; p.gt[2 * i + 1] = p.table.gt[2 * s + 1]; }
     if (p.hom) p.hom[i] = p.table.hom[s];

@@ -22,6 +22,7 @@ struct QualityParams {
     const uint8_t* text;
     uint64_t text_len;
     const uint64_t* line_off;
+    const uint32_t* order;      // file index -> storage index
     uint64_t site_begin, n_sites;
     const double* lut;          // [0,256) log(1-e)  [256,512) log(e)  [512,768) log(1-2e/3)  [768,1024) log(2e/3)
     double prior, alpha;
@@ -78,7 +79,7 @@ SID_HD CallResult call_quality(const Src& src, uint64_t line_abs, const ParsedLi
 __global__ void __launch_bounds__(QUAL_THREADS) k_quality(const QualityParams p) {
     const uint64_t i = (uint64_t)blockIdx.x * QUAL_THREADS + threadIdx.x;
     if (i >= p.n_sites) return;
-    const uint64_t site = p.site_begin + i;
+    const uint64_t site = p.order[p.site_begin + i];
     const uint64_t line_abs = p.line_off[site];
     FlatSrc src {p.text, p.text_len};
     ParsedLine pl;

@@ -5,12 +5,16 @@
 // Layout: the text is cut into tiles of eight slices.  Each persistent CTA is warp specialised:
 //   * warp 0 (service) draws tiles in order from an atomic ticket and stages them (+ a tail for
 //     the line that straddles the end) in shared memory with one bulk asynchronous copy
-//     (cp.async.bulk -> mbarrier), one tile ahead of the parse warps; it sums the slices' line
-//     counts and obtains the global index of the tile's first line by a decoupled look-back over
-//     per-tile counts (single pass over the text, output dense and in file order).
+//     (cp.async.bulk -> mbarrier), one tile ahead of the parse warps.
 //   * warps 1..8 (parse) each own one slice of the staged tile: the warp finds the line starts of
-//     its slice with SWAR newline masks, then parses them one line per lane.  The slice length is
-//     chosen by the host so that a slice holds about 30 lines.
+//     its slice, then parses them one line per lane.  The slice length is chosen by the host so
+//     that a slice holds about 30 lines.
+// Site storage is dense but NOT in file order: a warp reserves room for the lines of its slice with
+// one atomicAdd and records (first storage index, count) in the block table entry of (tile, slice).
+// The block table is in file order; k_blk_sums/k_blk_order turn it into order[file index] = storage
+// index, and the consumers (CSV writer, records, quality, the ordered view) go through that.  A file-ordered store would
+// need every tile to wait for the line counts of all tiles before it (a look-back chain over some
+// 450 resident CTAs): measured 18 % of the kernel, see profiles/README.md.
 // Hand-over in both directions goes through mbarriers; there is no CTA-wide barrier in the loop.
 #pragma once
 #include "common.cuh"
@@ -32,6 +36,7 @@ constexpr int TILE_PAD = 16;                      // staged before the tile begi
 constexpr int TILE_SMEM_MAX = TILE_PAD + TOK_PARSE_WARPS * SLICE_MAX + TILE_TAIL;
 constexpr int SLICE_MAX_LINES = SLICE_MAX / 8;    // a valid line has >= 10 bytes
 
+// decoupled look-back status words (k_csv)
 constexpr unsigned long long LB_FLAG_AGG = 1ull << 62;
 constexpr unsigned long long LB_FLAG_PREFIX = 2ull << 62;
 constexpr unsigned long long LB_VALUE_MASK = (1ull << 62) - 1;
@@ -41,9 +46,9 @@ struct TokParams {
     uint64_t text_len, range_begin, range_end;
     uint64_t tile0;                 // absolute offset of tile 0 (range_begin rounded down to 16)
     uint32_t n_tiles;
-    // outputs, indexed by site (site_base + running index)
-    uint64_t site_base;
-    uint64_t site_cap;
+    // outputs, indexed by storage index (site_base + the room a warp reserved)
+    uint64_t site_base;             // first storage index of this call
+    uint64_t site_cap;              // capacity of the site arrays (storage indices, < 2^32)
     uint64_t* profile;              // optional
     int32_t* pos;
     uint32_t* slot;                 // optional (needs table)
@@ -51,8 +56,8 @@ struct TokParams {
     uint64_t* line_off;             // optional (quality path)
     // scheduling / look-back
     unsigned int* tile_ticket;
-    unsigned long long* tile_status;
-    unsigned long long* n_sites;    // out: sites produced by this call
+    unsigned long long* site_alloc; // storage indices handed out so far, relative to site_base (atomic)
+    unsigned long long* blk;        // block table of this call, entry (tile * 8 + slice): lines << 32 | first storage index
     unsigned long long* error;      // out: min over (line offset << 3 | LineStatus)
     TableView table;
     NameDict names;
@@ -141,9 +146,6 @@ __device__ __forceinline__ bool same_name_as_first(const uint8_t* s_text, uint32
 
 struct StageMeta {
     uint64_t tb;           // absolute offset of the tile
-    uint64_t base;         // global index of its first line
-    uint32_t prefix[TOK_PARSE_WARPS];   // lines in the slices before slice w
-    uint32_t count[TOK_PARSE_WARPS];    // lines that start in slice w
     int32_t tile;          // -1: no more tiles
     uint32_t smem_bytes;   // bytes staged for this tile
 };
@@ -159,7 +161,7 @@ template <bool FAST>
 __global__ void __launch_bounds__(TOK_THREADS) k_tokenize(const TokParams p) {
     extern __shared__ __align__(128) uint8_t s_dyn[];      // staged text per stage, then line starts per stage and warp
     __shared__ StageMeta s_meta[TOK_STAGES];
-    __shared__ __align__(8) uint64_t s_full[TOK_STAGES], s_counted[TOK_STAGES], s_ready[TOK_STAGES], s_done[TOK_STAGES];
+    __shared__ __align__(8) uint64_t s_full[TOK_STAGES], s_done[TOK_STAGES];
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
@@ -169,8 +171,6 @@ __global__ void __launch_bounds__(TOK_THREADS) k_tokenize(const TokParams p) {
     if (tid == 0) {
         for (int b = 0; b < TOK_STAGES; ++b) {
             mbar_init(&s_full[b], 1);
-            mbar_init(&s_counted[b], TOK_PARSE_WARPS);
-            mbar_init(&s_ready[b], 1);
             mbar_init(&s_done[b], TOK_PARSE_WARPS);
         }
         mbar_fence_init();
@@ -246,61 +246,6 @@ __global__ void __launch_bounds__(TOK_THREADS) k_tokenize(const TokParams p) {
                 next_tile = __shfl_sync(0xFFFFFFFFu, t, 0);
                 if (next_tile < p.n_tiles) issue_load(nb, next_tile);
             }
-            const uint64_t tb = p.tile0 + (uint64_t)tile * tile_bytes;
-            // ---- the parse warps have counted the lines of their slices
-            if (!mbar_wait(&s_counted[b], use & 1)) {
-                if (lane == 0) report_error(p, tb, LINE_MALFORMED + 4);
-                break;
-            }
-            uint32_t cnt = lane < TOK_PARSE_WARPS ? s_meta[b].count[lane] : 0u;
-            uint32_t incl = cnt;
-#pragma unroll
-            for (int d = 1; d < TOK_PARSE_WARPS; d <<= 1) {
-                const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-                if (lane >= d) incl += o;
-            }
-            if (lane < TOK_PARSE_WARPS) s_meta[b].prefix[lane] = incl - cnt;
-            const uint32_t n_lines = __shfl_sync(0xFFFFFFFFu, incl, TOK_PARSE_WARPS - 1);
-            // ---- decoupled look-back over the per-tile line counts, 32 predecessors per step
-            uint64_t base = 0;
-            bool lb_ok = true;
-            if (tile == 0) {
-                if (lane == 0) atomicExch(&p.tile_status[0], LB_FLAG_PREFIX | (unsigned long long)n_lines);
-            } else {
-                if (lane == 0) atomicExch(&p.tile_status[tile], LB_FLAG_AGG | (unsigned long long)n_lines);
-                int64_t look = (int64_t)tile - 1;
-                uint32_t polls = 0;
-                for (;;) {
-                    const int64_t i = look - lane;
-                    unsigned long long w = 2ull << 62;                                  // before tile 0: an empty prefix
-                    if (i >= 0) w = *((volatile unsigned long long*)&p.tile_status[i]);
-                    const uint32_t is_prefix = __ballot_sync(0xFFFFFFFFu, (w >> 63) != 0);
-                    const uint32_t is_empty = __ballot_sync(0xFFFFFFFFu, (w >> 62) == 0);
-                    const int fp = is_prefix ? __ffs((int)is_prefix) - 1 : 31;          // last lane that counts
-                    const uint32_t need = fp == 31 ? 0xFFFFFFFFu : ((2u << fp) - 1u);
-                    if (is_empty & need) {
-                        if (++polls > (1u << 22)) { lb_ok = false; break; }
-                        __nanosleep(100);
-                        continue;
-                    }
-                    unsigned long long v = lane <= fp ? (w & LB_VALUE_MASK) : 0ull;
-#pragma unroll
-                    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, d);
-                    base += v;
-                    if (is_prefix) break;
-                    look -= 32;
-                }
-                if (lane == 0) atomicExch(&p.tile_status[tile], LB_FLAG_PREFIX | (unsigned long long)(base + n_lines));
-            }
-            if (!lb_ok && lane == 0) report_error(p, tb, LINE_MALFORMED + 4);
-            if (tile == p.n_tiles - 1 && lane == 0) *p.n_sites = base + n_lines;
-            __syncwarp();
-            if (lane == 0) {
-                s_meta[b].base = base;
-                __threadfence_block();
-                mbar_arrive(&s_ready[b]);               // base and prefixes are published
-            }
-            __syncwarp();
         }
         return;
     }
@@ -390,11 +335,16 @@ __global__ void __launch_bounds__(TOK_THREADS) k_tokenize(const TokParams p) {
                 n_lines = p.lines_cap;
             }
             __syncwarp();
+        }
+        // ---- room for the lines of this slice: one atomicAdd, recorded in the (file-ordered) block table
+        uint64_t base = 0;
+        {
+            unsigned long long bb = 0;
             if (lane == 0) {
-                s_meta[b].count[pw] = n_lines;
-                __threadfence_block();
-                mbar_arrive(&s_counted[b]);
+                if (n_lines) bb = p.site_base + atomicAdd(p.site_alloc, (unsigned long long)n_lines);
+                p.blk[(uint64_t)s_meta[b].tile * TOK_PARSE_WARPS + pw] = ((unsigned long long)n_lines << 32) | (bb & 0xFFFFFFFFull);
             }
+            base = __shfl_sync(0xFFFFFFFFu, bb, 0);
         }
         BitArrays B;
         B.term = bits; B.a = bits + p.words_cap; B.c = bits + 2 * p.words_cap; B.g = bits + 3 * p.words_cap;
@@ -410,8 +360,6 @@ __global__ void __launch_bounds__(TOK_THREADS) k_tokenize(const TokParams p) {
         // ---- groups of 32 consecutive lines, one line per lane.  Every lane runs the tokenizer (lanes
         //      past the end re-parse the group's first line and drop the result) so that the warp
         //      reconverges inside it.
-        bool have_base = false;
-        uint64_t base = 0;
         for (uint32_t g = 0; g < n_lines; g += 32) {
             const uint32_t j = g + lane;
             const bool mine = j < n_lines;
@@ -469,16 +417,9 @@ __global__ void __launch_bounds__(TOK_THREADS) k_tokenize(const TokParams p) {
                 same = name0_ref && r.chrom_off == 0 && same_name_as_first(txt, TILE_PAD + off, r.chrom_len, l0_off, first8);
                 if (p.use_table) slot = table_find_or_insert(p.table, r.profile);
             }
-            if (!have_base) {                              // the service warp has usually long published it
-                if (!mbar_wait(&s_ready[b], use & 1)) {
-                    if (lane == 0) report_error(p, tb, LINE_MALFORMED + 4);
-                }
-                base = s_meta[b].base + s_meta[b].prefix[pw];
-                have_base = true;
-            }
             if (mine && r.status != LINE_OK) report_error(p, line_abs, r.status);
             if (good) {
-                const uint64_t site = p.site_base + base + j;
+                const uint64_t site = base + j;
                 if (site >= p.site_cap) { report_error(p, line_abs, LINE_MALFORMED + 5); }
                 else {
                     const uint32_t ref = same ? name0_ref : name_intern(p.names, gsrc, line_abs + r.chrom_off, r.chrom_len);
@@ -490,9 +431,84 @@ __global__ void __launch_bounds__(TOK_THREADS) k_tokenize(const TokParams p) {
                 }
             }
         }
-        if (!have_base) mbar_wait(&s_ready[b], use & 1);   // keep the phase of s_ready in step for every warp
         __syncwarp();
         if (lane == 0) mbar_arrive(&s_done[b]);            // this warp is finished with the stage
+    }
+}
+
+// ---- block table -> order[]: order[first_file_index + f] = storage index of the f-th line of the range.
+constexpr int BLK_THREADS = 256;
+constexpr int BLK_PER_THREAD = 8;
+constexpr int BLK_CHUNK = BLK_THREADS * BLK_PER_THREAD;
+
+__global__ void __launch_bounds__(BLK_THREADS) k_blk_sums(const unsigned long long* blk, uint32_t n_blocks, unsigned long long* part) {
+    __shared__ uint32_t s_w[BLK_THREADS / 32];
+    const uint32_t first = blockIdx.x * BLK_CHUNK + threadIdx.x;
+    uint32_t sum = 0;
+#pragma unroll
+    for (int k = 0; k < BLK_PER_THREAD; ++k) {
+        const uint32_t b = first + k * BLK_THREADS;
+        if (b < n_blocks) sum += (uint32_t)(blk[b] >> 32);
+    }
+#pragma unroll
+    for (int d = 16; d; d >>= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, d);
+    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+        for (int w = 0; w < BLK_THREADS / 32; ++w) t += s_w[w];
+        part[blockIdx.x] = t;
+    }
+}
+
+__global__ void __launch_bounds__(BLK_THREADS) k_blk_order(const unsigned long long* blk, uint32_t n_blocks, const unsigned long long* part,
+                                                           uint64_t file_base, uint32_t* order, uint64_t order_cap) {
+    __shared__ unsigned long long s_red[BLK_THREADS / 32];
+    __shared__ uint32_t s_first[BLK_CHUNK + 1];             // first file index (relative to the chunk) of each block
+    __shared__ uint32_t s_base[BLK_CHUNK];                  // first storage index of each block
+    __shared__ uint32_t s_wsum[BLK_THREADS / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // file index of the chunk's first line: the lines of all chunks before it
+    unsigned long long before = 0;
+    for (uint32_t c = tid; c < blockIdx.x; c += BLK_THREADS) before += part[c];
+#pragma unroll
+    for (int d = 16; d; d >>= 1) before += __shfl_xor_sync(0xFFFFFFFFu, before, d);
+    if (lane == 0) s_red[warp] = before;
+    // exclusive scan of the chunk's counts, thread t owning blocks [8t, 8t+8)
+    const uint32_t b0 = blockIdx.x * BLK_CHUNK + tid * BLK_PER_THREAD;
+    uint32_t cnt[BLK_PER_THREAD], mine = 0;
+#pragma unroll
+    for (int k = 0; k < BLK_PER_THREAD; ++k) {
+        const unsigned long long e = b0 + k < n_blocks ? blk[b0 + k] : 0ull;
+        cnt[k] = (uint32_t)(e >> 32);
+        s_base[tid * BLK_PER_THREAD + k] = (uint32_t)e;
+        mine += cnt[k];
+    }
+    uint32_t incl = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+        if (lane >= d) incl += o;
+    }
+    if (lane == 31) s_wsum[warp] = incl;
+    __syncthreads();
+    uint32_t off = incl - mine;
+    for (int w = 0; w < warp; ++w) off += s_wsum[w];
+    unsigned long long chunk_first = file_base;
+    for (int w = 0; w < BLK_THREADS / 32; ++w) chunk_first += s_red[w];
+#pragma unroll
+    for (int k = 0; k < BLK_PER_THREAD; ++k) {
+        s_first[tid * BLK_PER_THREAD + k] = off;
+        off += cnt[k];
+    }
+    if (tid == BLK_THREADS - 1) s_first[BLK_CHUNK] = off;
+    __syncthreads();
+    // one warp per block: consecutive lanes write consecutive entries
+    for (uint32_t j = warp; j < BLK_CHUNK; j += BLK_THREADS / 32) {
+        const uint32_t f = s_first[j], n = s_first[j + 1] - f, base = s_base[j];
+        const unsigned long long f0 = chunk_first + f;
+        for (uint32_t i = lane; i < n; i += 32)
+            if (f0 + i < order_cap) order[f0 + i] = base + i;
     }
 }
 

@@ -74,10 +74,12 @@ struct sidgpu_ctx {
     TableView tab {};
     // chromosome names
     NameDict names {};
-    // look-back status words
-    DevBuf tile_status, csv_status;
-    // site store
-    DevBuf pos, slot, name_ref, profile, line_off, site_suffix;
+    // look-back status words of the CSV writer
+    DevBuf csv_status;
+    // site store: arrays indexed by storage index (dense, not in file order) and order[file index] = storage index
+    DevBuf pos, slot, name_ref, profile, line_off, site_suffix, order;
+    DevBuf blk, blk_part;            // block table of the running tokenizer call and its per-chunk sums
+    DevBuf v_pos, v_slot, v_name_ref, v_profile, v_line_off;   // file-ordered copies behind sidgpu_sites_view
     uint64_t site_cap = 0;
     bool want_profile = false, want_line_off = false, want_site_suffix = false;
     uint64_t n_sites_total = 0;      // sites in the store (accumulate mode) or in the last chunk (streaming)
@@ -331,6 +333,8 @@ int ensure_sites(sidgpu_ctx* ctx, uint64_t n, bool keep) {
     if (n > ctx->site_cap || (ctx->want_profile && ctx->profile.cap < n * 8) || (ctx->want_line_off && ctx->line_off.cap < n * 8) ||
         (ctx->want_site_suffix && ctx->site_suffix.cap < n * SUFFIX_BYTES)) {
         const uint64_t cap = std::max<uint64_t>(n, ctx->site_cap);
+        if (cap >= 0xFFFFFFFFull) return ctx->fail(SIDGPU_ECAPACITY, "more than 2^32 sites in one store: feed smaller ranges");
+        TRY(ensure(ctx, ctx->order, cap * 4, keep));
         TRY(ensure(ctx, ctx->pos, cap * 4, keep));
         TRY(ensure(ctx, ctx->slot, cap * 4, keep));
         TRY(ensure(ctx, ctx->name_ref, cap * 4, keep));
@@ -351,8 +355,9 @@ const char* status_text(int st) {
     }
 }
 
-// Runs K1 over [range_begin, range_end) writing sites from index site_base.  On return
-// *n_out holds the number of sites the range produced.
+// Runs K1 over [range_begin, range_end): the sites go to storage indices [site_base, site_base + n) in
+// no particular order, and order[site_base + f] is the storage index of the f-th line of the range.
+// On return *n_out holds the number of sites the range produced.
 int run_tokenizer(sidgpu_ctx* ctx, const char* d_text, size_t text_len, size_t range_begin, size_t range_end,
                   bool want_qual, bool use_table, uint64_t site_base, bool keep_sites, uint64_t* n_out, bool strict_qual = false) {
     if (((uintptr_t)d_text & 15) != 0) return ctx->fail(SIDGPU_EINVAL, "d_text must be 16-byte aligned");
@@ -371,12 +376,16 @@ int run_tokenizer(sidgpu_ctx* ctx, const char* d_text, size_t text_len, size_t r
     const uint64_t n_tiles64 = (span + tile_bytes - 1) / tile_bytes;
     if (n_tiles64 > 0x7FFFFFFFull) return ctx->fail(SIDGPU_EINVAL, "range too large");
     const uint32_t n_tiles = (uint32_t)n_tiles64;
-    TRY(ensure(ctx, ctx->tile_status, (size_t)n_tiles * 8));
+    const uint32_t n_blocks = n_tiles * TOK_PARSE_WARPS;
+    if (n_tiles64 * TOK_PARSE_WARPS > 0x7FFFFFFFull) return ctx->fail(SIDGPU_EINVAL, "range too large");
+    const uint32_t n_chunks = (n_blocks + BLK_CHUNK - 1) / BLK_CHUNK;
+    TRY(ensure(ctx, ctx->blk, (size_t)n_blocks * 8));
+    TRY(ensure(ctx, ctx->blk_part, (size_t)n_chunks * 8));
 
     uint64_t guess = (range_end - range_begin) / 24 + 4096;
     for (int attempt = 0;; ++attempt) {
         TRY(ensure_sites(ctx, site_base + guess, keep_sites || attempt > 0 ? keep_sites : false));
-        CK(cudaMemsetAsync(ctx->tile_status.p, 0, (size_t)n_tiles * 8, ctx->stream));
+        CK(cudaMemsetAsync(ctx->blk.p, 0, (size_t)n_blocks * 8, ctx->stream));
         CK(cudaMemsetAsync(ctl_field(ctx, &Control::tok_ticket), 0, sizeof(unsigned int), ctx->stream));
         CK(cudaMemsetAsync(ctl_field(ctx, &Control::n_sites), 0, sizeof(unsigned long long), ctx->stream));
         CK(cudaMemsetAsync(ctl_field(ctx, &Control::error), 0xFF, sizeof(unsigned long long), ctx->stream));
@@ -395,8 +404,8 @@ int run_tokenizer(sidgpu_ctx* ctx, const char* d_text, size_t text_len, size_t r
         p.name_ref = (uint32_t*)ctx->name_ref.p;
         p.line_off = ctx->want_line_off ? (uint64_t*)ctx->line_off.p : nullptr;
         p.tile_ticket = ctl_field(ctx, &Control::tok_ticket);
-        p.tile_status = (unsigned long long*)ctx->tile_status.p;
-        p.n_sites = ctl_field(ctx, &Control::n_sites);
+        p.site_alloc = ctl_field(ctx, &Control::n_sites);
+        p.blk = (unsigned long long*)ctx->blk.p;
         p.error = ctl_field(ctx, &Control::error);
         p.table = ctx->tab;
         p.names = ctx->names;
@@ -419,8 +428,13 @@ int run_tokenizer(sidgpu_ctx* ctx, const char* d_text, size_t text_len, size_t r
             // columns; inside a quality session k_quality re-reads every line and reports them itself
             if (want_qual && strict_qual) k_tokenize<false><<<grid, TOK_THREADS, dyn_smem, ctx->stream>>>(p);
             else k_tokenize<true><<<grid, TOK_THREADS, dyn_smem, ctx->stream>>>(p);
+            TRY(check_launch(ctx, "k_tokenize"));
+            k_blk_sums<<<n_chunks, BLK_THREADS, 0, ctx->stream>>>((const unsigned long long*)ctx->blk.p, n_blocks, (unsigned long long*)ctx->blk_part.p);
+            TRY(check_launch(ctx, "k_blk_sums"));
+            k_blk_order<<<n_chunks, BLK_THREADS, 0, ctx->stream>>>((const unsigned long long*)ctx->blk.p, n_blocks, (const unsigned long long*)ctx->blk_part.p,
+                                                                   site_base, (uint32_t*)ctx->order.p, ctx->site_cap);
+            TRY(check_launch(ctx, "k_blk_order"));
         }
-        TRY(check_launch(ctx, "k_tokenize"));
         TRY(sync_ctl(ctx));
         const Control& c = *ctx->h_ctl;
         if (c.name_overflow) return ctx->fail(SIDGPU_ECAPACITY, c.name_overflow == 2 ? "chromosome name longer than 65535 bytes" : "chromosome name dictionary is full");
@@ -467,6 +481,12 @@ __global__ void k_map_entries(TableView t, uint32_t n_entries, const unsigned lo
         if (profile_sort_key(sorted_profiles[mid]) < key) lo = mid + 1; else hi = mid;
     }
     entry_to_unique[e] = (lo < n && profile_sort_key(sorted_profiles[lo]) == key) ? lo : 0xFFFFFFFFu;
+}
+
+template <class T>
+__global__ void k_gather(T* out, const T* in, const uint32_t* order, uint64_t n) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = in[order[i]];
 }
 
 __global__ void k_count_slots(const uint32_t* slot, uint64_t begin, uint64_t n, unsigned long long* counts) {
@@ -652,6 +672,7 @@ int quality_rows(sidgpu_ctx* ctx, uint64_t site_begin, uint64_t n) {
     q.text = (const uint8_t*)ctx->last_text;
     q.text_len = ctx->last_text_len;
     q.line_off = (const uint64_t*)ctx->line_off.p;
+    q.order = (const uint32_t*)ctx->order.p;
     q.site_begin = site_begin;
     q.n_sites = n;
     q.lut = (const double*)ctx->quality_lut.p;
@@ -777,7 +798,7 @@ void sidgpu_destroy(sidgpu_ctx* ctx) {
     free_table(ctx->tab);
     cudaFree(ctx->names.slots);
     cudaFree(ctx->names.pool);
-    for (DevBuf* b : {&ctx->tile_status, &ctx->csv_status, &ctx->pos, &ctx->slot, &ctx->name_ref, &ctx->profile, &ctx->line_off,
+    for (DevBuf* b : {&ctx->blk, &ctx->blk_part, &ctx->order, &ctx->v_pos, &ctx->v_slot, &ctx->v_name_ref, &ctx->v_profile, &ctx->v_line_off, &ctx->csv_status, &ctx->pos, &ctx->slot, &ctx->name_ref, &ctx->profile, &ctx->line_off,
                       &ctx->site_suffix, &ctx->sort_keys, &ctx->sort_vals, &ctx->u_profile, &ctx->u_count, &ctx->u_logM,
                       &ctx->entry_to_unique, &ctx->p_hom, &ctx->p_het, &ctx->adj_hom, &ctx->adj_het, &ctx->bh_c, &ctx->bh_block,
                       &ctx->partials, &ctx->quality_lut})
@@ -866,11 +887,29 @@ int sidgpu_tokenize(sidgpu_ctx* ctx, const char* d_text, size_t text_len, size_t
     ctx->chunk_sites = n;
     memset(out, 0, sizeof *out);
     out->n_sites = n;
-    out->d_profile = (const uint64_t*)ctx->profile.p;
-    out->d_pos = (const int32_t*)ctx->pos.p;
-    out->d_slot = (const uint32_t*)ctx->slot.p;
-    out->d_line_off = want_qual ? (const uint64_t*)ctx->line_off.p : nullptr;
-    out->d_name_ref = (const uint32_t*)ctx->name_ref.p;
+    // the view is in file order: gather the stored columns through order[]
+    const size_t nn = std::max<uint64_t>(n, 1);
+    TRY(ensure(ctx, ctx->v_profile, nn * 8));
+    TRY(ensure(ctx, ctx->v_pos, nn * 4));
+    TRY(ensure(ctx, ctx->v_slot, nn * 4));
+    TRY(ensure(ctx, ctx->v_name_ref, nn * 4));
+    if (want_qual) TRY(ensure(ctx, ctx->v_line_off, nn * 8));
+    if (n) {
+        const unsigned g = (unsigned)((n + 255) / 256);
+        const uint32_t* ord = (const uint32_t*)ctx->order.p;
+        k_gather<<<g, 256, 0, ctx->stream>>>((uint64_t*)ctx->v_profile.p, (const uint64_t*)ctx->profile.p, ord, n);
+        k_gather<<<g, 256, 0, ctx->stream>>>((int32_t*)ctx->v_pos.p, (const int32_t*)ctx->pos.p, ord, n);
+        k_gather<<<g, 256, 0, ctx->stream>>>((uint32_t*)ctx->v_slot.p, (const uint32_t*)ctx->slot.p, ord, n);
+        k_gather<<<g, 256, 0, ctx->stream>>>((uint32_t*)ctx->v_name_ref.p, (const uint32_t*)ctx->name_ref.p, ord, n);
+        if (want_qual) k_gather<<<g, 256, 0, ctx->stream>>>((uint64_t*)ctx->v_line_off.p, (const uint64_t*)ctx->line_off.p, ord, n);
+        TRY(check_launch(ctx, "k_gather"));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    out->d_profile = (const uint64_t*)ctx->v_profile.p;
+    out->d_pos = (const int32_t*)ctx->v_pos.p;
+    out->d_slot = (const uint32_t*)ctx->v_slot.p;
+    out->d_line_off = want_qual ? (const uint64_t*)ctx->v_line_off.p : nullptr;
+    out->d_name_ref = (const uint32_t*)ctx->v_name_ref.p;
     out->d_names = ctx->names.pool;
     out->names_bytes = ctx->h_ctl->name_cursor;
     return SIDGPU_OK;
@@ -1039,6 +1078,7 @@ int sidgpu_emit_csv(sidgpu_ctx* ctx, uint64_t site_begin, uint64_t n_sites, char
     CsvParams p {};
     p.site_begin = site_begin;
     p.n_sites = n_sites;
+    p.order = (const uint32_t*)ctx->order.p;
     p.pos = (const int32_t*)ctx->pos.p;
     p.slot = (const uint32_t*)ctx->slot.p;
     p.name_ref = (const uint32_t*)ctx->name_ref.p;
@@ -1081,7 +1121,7 @@ int sidgpu_emit_records(sidgpu_ctx* ctx, uint64_t site_begin, uint64_t n_sites, 
     if (site_begin + n_sites > ctx->n_sites_total) return ctx->fail(SIDGPU_EINVAL, "site range not in the store");
     if (n_sites == 0) return SIDGPU_OK;
     CK(cudaSetDevice(ctx->device));
-    RecordParams p {site_begin, n_sites, (const uint32_t*)ctx->slot.p, ctx->tab, d_label, d_gt, d_hom, d_het};
+    RecordParams p {site_begin, n_sites, (const uint32_t*)ctx->order.p, (const uint32_t*)ctx->slot.p, ctx->tab, d_label, d_gt, d_hom, d_het};
     k_records<<<(unsigned)((n_sites + 255) / 256), 256, 0, ctx->stream>>>(p);
     TRY(check_launch(ctx, "k_records"));
     CK(cudaStreamSynchronize(ctx->stream));
