@@ -29,6 +29,13 @@ namespace sid {
 constexpr int TOK_PARSE_WARPS = 8;
 constexpr int TOK_THREADS = 32 * (1 + TOK_PARSE_WARPS);
 constexpr int TOK_STAGES = 2;
+#ifndef SID_SVC_SLEEP
+#define SID_SVC_SLEEP 500
+#endif
+#ifndef SID_PARSE_SLEEP
+#define SID_PARSE_SLEEP 200
+#endif
+constexpr unsigned SVC_SLEEP = SID_SVC_SLEEP, PARSE_SLEEP = SID_PARSE_SLEEP;   // ns between polls of a waiting warp
 constexpr int SLICE_MAX = 4096;                   // bytes; slices are multiples of 16
 constexpr int SLICE_MIN = 256;                    // slices are multiples of 32
 constexpr int TILE_TAIL = 2048;                   // staged past the tile end for straddling lines
@@ -64,17 +71,19 @@ struct TokParams {
     int use_table, count_profiles, want_qual;
     uint32_t slice_bytes;           // multiple of 16 in [SLICE_MIN, SLICE_MAX]; a tile is 8 slices
     uint32_t text_stride;           // bytes of shared memory per staged tile (tile_smem rounded up to 128)
+    uint32_t tail_bytes;            // bytes staged past the tile end for the lines that straddle it (<= TILE_TAIL)
     uint32_t lines_cap;             // line-start slots per slice (slice_bytes / 8)
     uint32_t ext_bytes;             // bytes past its slice a parse warp also classifies (multiple of 32, <= 2016)
     uint32_t words_cap;             // 32-bit words per class bit array: (slice_bytes + ext_bytes) / 32 + 2
 };
 
 // Dynamic shared memory a launch with this slice length needs.
-inline uint32_t tok_text_stride(uint32_t slice) { return (16u + 8u * slice + 2048u + 127u) & ~127u; }
+inline uint32_t tok_tail_bytes(uint32_t ext) { return ext + 128u > 2048u ? 2048u : ext + 128u; }   // multiple of 32
+inline uint32_t tok_text_stride(uint32_t slice, uint32_t ext) { return (16u + 8u * slice + tok_tail_bytes(ext) + 127u) & ~127u; }
 inline uint32_t tok_words_cap(uint32_t slice, uint32_t ext) { return (slice + ext) / 32u + 2u; }
-// staged text (2 stages) + line starts (2 stages x 8 warps) + class bit arrays (8 warps x 8 classes)
+// staged text (2 stages) + line starts (8 warps) + class bit arrays (8 warps x 8 classes)
 inline uint32_t tok_dyn_smem(uint32_t slice, uint32_t ext) {
-    return 2u * (tok_text_stride(slice) + 8u * (slice / 8u) * 2u) + 8u * 8u * tok_words_cap(slice, ext) * 4u;
+    return 2u * tok_text_stride(slice, ext) + 8u * (slice / 8u) * 2u + 8u * 8u * tok_words_cap(slice, ext) * 4u;
 }
 
 #if defined(__CUDACC__)
@@ -167,7 +176,7 @@ __global__ void __launch_bounds__(TOK_THREADS) k_tokenize(const TokParams p) {
     const int lane = tid & 31, warp = tid >> 5;
     const uint32_t slice = p.slice_bytes;
     const uint32_t tile_bytes = slice * TOK_PARSE_WARPS;
-    const uint32_t tile_smem = TILE_PAD + tile_bytes + TILE_TAIL;
+    const uint32_t tile_smem = TILE_PAD + tile_bytes + p.tail_bytes;
     if (tid == 0) {
         for (int b = 0; b < TOK_STAGES; ++b) {
             mbar_init(&s_full[b], 1);
@@ -187,7 +196,7 @@ __global__ void __launch_bounds__(TOK_THREADS) k_tokenize(const TokParams p) {
                 s_meta[b].tb = tb;
                 s_meta[b].tile = (int32_t)tile;
             }
-            // stage [tb - 16, tb + tile_bytes + TILE_TAIL); bytes outside the text read as '\n'
+            // stage [tb - 16, tb + tile_bytes + tail_bytes); bytes outside the text read as '\n'
             const bool interior = tb >= TILE_PAD && tb - TILE_PAD + tile_smem <= p.text_len;
             if (interior) {
                 if (lane == 0) {
@@ -224,7 +233,6 @@ __global__ void __launch_bounds__(TOK_THREADS) k_tokenize(const TokParams p) {
         if (next_tile < p.n_tiles) issue_load(0, next_tile);
         for (uint32_t it = 0;; ++it) {
             const int b = it % TOK_STAGES;
-            const uint32_t use = it / TOK_STAGES;
             const uint32_t tile = next_tile;
             if (tile >= p.n_tiles) {
                 if (lane == 0) {
@@ -237,7 +245,7 @@ __global__ void __launch_bounds__(TOK_THREADS) k_tokenize(const TokParams p) {
             // ---- prefetch: free the next stage, draw the next ticket, start its copy
             {
                 const int nb = (it + 1) % TOK_STAGES;
-                if (it + 1 >= TOK_STAGES && !mbar_wait(&s_done[nb], ((it + 1) / TOK_STAGES - 1) & 1)) {
+                if (it + 1 >= TOK_STAGES && !mbar_wait<SVC_SLEEP>(&s_done[nb], ((it + 1) / TOK_STAGES - 1) & 1)) {
                     if (lane == 0) report_error(p, 0, LINE_MALFORMED + 4);
                     break;
                 }
@@ -257,14 +265,14 @@ __global__ void __launch_bounds__(TOK_THREADS) k_tokenize(const TokParams p) {
     for (uint32_t it = 0;; ++it) {
         const int b = it % TOK_STAGES;
         const uint32_t use = it / TOK_STAGES;
-        if (!mbar_wait(&s_full[b], use & 1)) {
+        if (!mbar_wait<PARSE_SLEEP>(&s_full[b], use & 1)) {
             if (lane == 0) report_error(p, 0, LINE_MALFORMED + 4);
             break;
         }
         if (s_meta[b].tile < 0) break;
         const uint8_t* txt = s_dyn + (size_t)b * p.text_stride;
         uint16_t* starts = reinterpret_cast<uint16_t*>(s_dyn + (size_t)TOK_STAGES * p.text_stride) +
-                           ((size_t)b * TOK_PARSE_WARPS + pw) * p.lines_cap;
+                           (size_t)pw * p.lines_cap;
         const uint64_t tb = s_meta[b].tb;
         const uint64_t abs0 = tb - TILE_PAD;              // wraps for a tile at offset 0; only differences are used
         // ---- stage 1, flat over the slice (+ ext_bytes so that the last lines can be finished): every
@@ -275,7 +283,7 @@ __global__ void __launch_bounds__(TOK_THREADS) k_tokenize(const TokParams p) {
         uint32_t n_lines = 0;
         const uint32_t slice_off = (uint32_t)pw * slice;               // offset of the slice inside the tile
         const uint32_t region_off = TILE_PAD + slice_off;              // offset in txt of bit 0 of the bit arrays
-        uint32_t* bits = reinterpret_cast<uint32_t*>(s_dyn + (size_t)TOK_STAGES * (p.text_stride + TOK_PARSE_WARPS * p.lines_cap * 2)) +
+        uint32_t* bits = reinterpret_cast<uint32_t*>(s_dyn + (size_t)TOK_STAGES * p.text_stride + (size_t)TOK_PARSE_WARPS * p.lines_cap * 2) +
                          (size_t)pw * 8 * p.words_cap;
         {
             const uint32_t own_units = slice / 32, units = (slice + p.ext_bytes) / 32;
@@ -414,7 +422,7 @@ __global__ void __launch_bounds__(TOK_THREADS) k_tokenize(const TokParams p) {
             bool same = false;
             uint32_t slot = 0;
             if (good) {
-                same = name0_ref && r.chrom_off == 0 && same_name_as_first(txt, TILE_PAD + off, r.chrom_len, l0_off, first8);
+                same = name0_ref && r.chrom_off == 0 && same_name_as_first(txt, TILE_PAD + off, r.chrom_len, l0_off, first8, tile_smem);
                 if (p.use_table) slot = table_find_or_insert(p.table, r.profile);
             }
             if (mine && r.status != LINE_OK) report_error(p, line_abs, r.status);

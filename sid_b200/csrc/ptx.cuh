@@ -33,10 +33,11 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 }
 // Bounded wait: returns false if the phase did not complete within ~2^22 polls (a lost arrival
 // would otherwise hang the GPU; callers turn it into an error code).
+template <unsigned SLEEP_NS = 100>
 __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return true;
     for (uint32_t i = 0; i < (1u << 22); ++i) {
-        __nanosleep(100);                       // waiting warps must not eat the issue slots of working ones
+        __nanosleep(SLEEP_NS);                  // waiting warps must not eat the issue slots of working ones
         if (mbar_try_wait(bar, parity)) return true;
     }
     return false;

@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <string>
@@ -367,7 +368,8 @@ int run_tokenizer(sidgpu_ctx* ctx, const char* d_text, size_t text_len, size_t r
     const uint64_t tile0 = range_begin & ~(uint64_t)15;
     const uint64_t span = range_end - tile0;
     // a slice (one parse warp's share of a tile) should hold about 30 lines: 32 lanes, little overflow
-    uint32_t slice = (uint32_t)(ctx->avg_line_bytes * 29.5) & ~31u;
+    static const double slice_lines = getenv("SIDGPU_SLICE_LINES") ? atof(getenv("SIDGPU_SLICE_LINES")) : 29.5;   // tuning knob
+    uint32_t slice = (uint32_t)(ctx->avg_line_bytes * slice_lines) & ~31u;
     slice = std::max<uint32_t>(SLICE_MIN, std::min<uint32_t>(SLICE_MAX, slice));
     // a parse warp also classifies the bytes after its slice that its last lines reach into
     uint32_t ext = ((uint32_t)(ctx->avg_line_bytes * 1.25) + 31u) & ~31u;
@@ -413,7 +415,8 @@ int run_tokenizer(sidgpu_ctx* ctx, const char* d_text, size_t text_len, size_t r
         p.count_profiles = 0;
         p.want_qual = want_qual ? 1 : 0;
         p.slice_bytes = slice;
-        p.text_stride = tok_text_stride(slice);
+        p.text_stride = tok_text_stride(slice, ext);
+        p.tail_bytes = tok_tail_bytes(ext);
         p.lines_cap = slice / 8;
         p.ext_bytes = ext;
         p.words_cap = tok_words_cap(slice, ext);
