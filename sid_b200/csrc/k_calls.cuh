@@ -66,9 +66,17 @@ __global__ void __launch_bounds__(128) k_classify(const ClassifyParams p) {
 }
 
 // ------------------------------------------------------------------------------------------- K6
+// CSV writer (operator<< call.hpp:29-38 + the print loop sid.cpp:102-106).  Every warp works on its own:
+// it draws a tile of 128 consecutive sites (file order), computes the row lengths, publishes their sum
+// and finds its byte offset with a warp-wide decoupled look-back, assembles the rows in its private
+// piece of shared memory and copies them out with aligned 16-byte stores.  No CTA-wide barrier: a warp
+// waiting for memory or for its predecessors does not hold up the others.
 constexpr int CSV_THREADS = 256;
+constexpr int CSV_WARPS = CSV_THREADS / 32;
 constexpr int CSV_PER_THREAD = 4;
-constexpr int CSV_TILE = CSV_THREADS * CSV_PER_THREAD;
+constexpr int CSV_TILE = 32 * CSV_PER_THREAD;     // sites per warp tile
+constexpr int CSV_WSTAGE = 6912;                  // bytes of rows a warp may stage (else: direct global writes)
+constexpr int CSV_STAGE = CSV_WARPS * CSV_WSTAGE;
 
 struct CsvParams {
     uint64_t site_begin, n_sites;    // file-order range of the store
@@ -82,47 +90,76 @@ struct CsvParams {
     char* out;
     uint64_t out_cap;
     unsigned int* ticket;
-    unsigned long long* status;
+    unsigned long long* status;  // one look-back word per tile, zeroed
     unsigned long long* bytes_out;
     unsigned long long* rows_out;
+    unsigned long long* error;   // atomicMin target; a look-back that never resolves reports LINE_MALFORMED + 4
     uint32_t n_tiles;
 };
 
-// Rows of one tile are assembled in shared memory and copied out with aligned 16-byte stores.
-// The staging area starts at (global offset of the tile's first byte) mod 16, so 16-byte chunks of
-// shared memory line up with 16-byte chunks of the output buffer.
-constexpr int CSV_STAGE = 52 * 1024;          // bytes of rows one tile may stage (else: direct global writes)
+__device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v) {
+#pragma unroll
+    for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, d);
+    return v;
+}
 
-__global__ void __launch_bounds__(CSV_THREADS) k_csv(const CsvParams p) {
-    extern __shared__ __align__(16) char s_stage[];
-    __shared__ uint32_t s_tile;
-    __shared__ uint64_t s_base;
-    __shared__ uint32_t s_warp_sums[CSV_THREADS / 32];
-    __shared__ uint32_t s_warp_rows[CSV_THREADS / 32];
+// Bytes before tile `tile`: sums the published aggregates of its predecessors, 32 at a time, back to the
+// first one whose inclusive prefix is known.
+__device__ __forceinline__ unsigned long long csv_look_back(const CsvParams& p, uint32_t tile, int lane, bool& ok) {
+    unsigned long long base = 0;
+    int64_t idx = (int64_t)tile - 1;
+    uint32_t idle = 0;
+    ok = true;
+    while (idx >= 0) {
+        const int64_t i = idx - lane;
+        unsigned long long w = LB_FLAG_PREFIX;                                   // before tile 0: prefix 0
+        if (i >= 0) w = *((volatile unsigned long long*)&p.status[i]);
+        const uint32_t flag = (uint32_t)(w >> 62);
+        const uint32_t not_ready = __ballot_sync(0xFFFFFFFFu, flag == 0);
+        const uint32_t usable = not_ready ? ((1u << (__ffs((int)not_ready) - 1)) - 1u) : 0xFFFFFFFFu;   // lanes before the first gap
+        const uint32_t pref = __ballot_sync(0xFFFFFFFFu, flag == 2) & usable;
+        if (pref) {
+            const int first = __ffs((int)pref) - 1;
+            base += warp_sum_u64(lane <= first ? (w & LB_VALUE_MASK) : 0ull);
+            return base;
+        }
+        if (usable) {
+            base += warp_sum_u64(((usable >> lane) & 1u) ? (w & LB_VALUE_MASK) : 0ull);
+            idx -= __popc(usable);
+            idle = 0;
+        } else {
+            if (++idle > (1u << 22)) { ok = false; return base; }
+            __nanosleep(40);
+        }
+    }
+    return base;
+}
+
+__global__ void __launch_bounds__(CSV_THREADS, 4) k_csv(const CsvParams p) {
+    extern __shared__ __align__(16) char s_stage_all[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    // storage indices of this thread's four sites of a tile (0xFFFFFFFF past the end)
-    auto load_order = [&](uint32_t tile, uint32_t (&ord)[CSV_PER_THREAD]) {
-        const uint64_t first = (uint64_t)tile * CSV_TILE + (uint64_t)tid * CSV_PER_THREAD;
+    char* s_stage = s_stage_all + warp * CSV_WSTAGE;
+    unsigned long long my_rows = 0;
+    for (;;) {
+        uint32_t tile = 0;
+        if (lane == 0) tile = atomicAdd(p.ticket, 1u);      // in order: the look-back needs every earlier tile started
+        tile = __shfl_sync(0xFFFFFFFFu, tile, 0);
+        if (tile >= p.n_tiles) break;
+        const uint64_t first = (uint64_t)tile * CSV_TILE + (uint64_t)lane * CSV_PER_THREAD;
+        // storage indices of this lane's four sites (0xFFFFFFFF past the end)
+        uint32_t ord[CSV_PER_THREAD];
 #pragma unroll
         for (int k = 0; k < CSV_PER_THREAD; ++k) ord[k] = 0xFFFFFFFFu;
-        if (tile >= p.n_tiles || first >= p.n_sites) return;
-        const uint32_t* src = p.order + p.site_begin + first;
-        if (first + CSV_PER_THREAD <= p.n_sites && ((uintptr_t)src & 15u) == 0) {
-            const uint4 v = __ldg(reinterpret_cast<const uint4*>(src));
-            ord[0] = v.x; ord[1] = v.y; ord[2] = v.z; ord[3] = v.w;
-        } else {
+        if (first < p.n_sites) {
+            const uint32_t* src = p.order + p.site_begin + first;
+            if (first + CSV_PER_THREAD <= p.n_sites && ((uintptr_t)src & 15u) == 0) {
+                const uint4 v = __ldg(reinterpret_cast<const uint4*>(src));
+                ord[0] = v.x; ord[1] = v.y; ord[2] = v.z; ord[3] = v.w;
+            } else {
 #pragma unroll
-            for (int k = 0; k < CSV_PER_THREAD; ++k) if (first + k < p.n_sites) ord[k] = __ldg(src + k);
+                for (int k = 0; k < CSV_PER_THREAD; ++k) if (first + k < p.n_sites) ord[k] = __ldg(src + k);
+            }
         }
-    };
-    for (;;) {
-        __syncthreads();
-        if (tid == 0) s_tile = atomicAdd(p.ticket, 1u);     // in order: the look-back below needs every earlier tile started
-        __syncthreads();
-        const uint32_t tile = s_tile;
-        if (tile >= p.n_tiles) break;
-        uint32_t ord[CSV_PER_THREAD];
-        load_order(tile, ord);
         uint32_t len[CSV_PER_THREAD], nlen[CSV_PER_THREAD], slen[CSV_PER_THREAD], nref[CSV_PER_THREAD];
         int32_t pos[CSV_PER_THREAD];
         const char* sfxp[CSV_PER_THREAD];
@@ -148,53 +185,29 @@ __global__ void __launch_bounds__(CSV_THREADS) k_csv(const CsvParams p) {
             }
             mine += len[k];
         }
-        uint32_t incl = mine, rincl = rows;
+        uint32_t incl = mine;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-            const uint32_t r = __shfl_up_sync(0xFFFFFFFFu, rincl, d);
-            if (lane >= d) { incl += o; rincl += r; }
+            if (lane >= d) incl += o;
         }
-        if (lane == 31) { s_warp_sums[warp] = incl; s_warp_rows[warp] = rincl; }
-        __syncthreads();
-        uint32_t warp_off = 0, total = 0, total_rows = 0;
-#pragma unroll
-        for (int w = 0; w < CSV_THREADS / 32; ++w) {
-            if (w < warp) warp_off += s_warp_sums[w];
-            total += s_warp_sums[w];
-            total_rows += s_warp_rows[w];
+        const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+        my_rows += rows;
+        // ---- byte offset of the tile
+        if (lane == 0) atomicExch(&p.status[tile], (tile == 0 ? LB_FLAG_PREFIX : LB_FLAG_AGG) | (unsigned long long)total);
+        unsigned long long tile_base = 0;
+        if (tile) {
+            bool ok;
+            tile_base = csv_look_back(p, tile, lane, ok);
+            if (!ok && lane == 0) atomicMin(p.error, (unsigned long long)(LINE_MALFORMED + 4));
+            if (lane == 0) atomicExch(&p.status[tile], LB_FLAG_PREFIX | (tile_base + total));
         }
-        if (tid == 0) {
-            uint64_t base = 0;
-            if (tile == 0) {
-                atomicExch(&p.status[0], LB_FLAG_PREFIX | (unsigned long long)total);
-            } else {
-                atomicExch(&p.status[tile], LB_FLAG_AGG | (unsigned long long)total);
-                uint32_t i = tile - 1;
-                for (;;) {
-                    unsigned long long w;
-                    unsigned int spins = 0;
-                    do {
-                        w = *((volatile unsigned long long*)&p.status[i]);
-                        if ((w >> 62) == 0 && ++spins > (1u << 24)) w = LB_FLAG_PREFIX;
-                    } while ((w >> 62) == 0);
-                    base += w & LB_VALUE_MASK;
-                    if (w & LB_FLAG_PREFIX) break;
-                    --i;
-                }
-                atomicExch(&p.status[tile], LB_FLAG_PREFIX | (unsigned long long)(base + total));
-            }
-            s_base = base;
-            if (tile == p.n_tiles - 1) *p.bytes_out = base + total;
-            if (total_rows) atomicAdd(p.rows_out, (unsigned long long)total_rows);
-        }
-        __syncthreads();
-        const uint64_t tile_base = s_base;
-        const uint32_t local = warp_off + incl - mine;                 // byte offset of this thread's rows inside the tile
+        if (tile == p.n_tiles - 1 && lane == 0) *p.bytes_out = tile_base + total;
         if (tile_base + total > p.out_cap) continue;                   // the host reports SIDGPU_ECAPACITY from bytes_out
+        // ---- rows: assembled in shared memory at (global offset mod 16), so that 16-byte chunks line up
         const uint32_t mis = (uint32_t)((uintptr_t)(p.out + tile_base) & 15u);
-        const bool staged = total + mis + 16 <= CSV_STAGE;
-        uint32_t o = local;
+        const bool staged = total + mis + 16 <= CSV_WSTAGE;
+        uint32_t o = incl - mine;
 #pragma unroll
         for (int k = 0; k < CSV_PER_THREAD; ++k) {
             if (!len[k]) continue;
@@ -221,19 +234,22 @@ __global__ void __launch_bounds__(CSV_THREADS) k_csv(const CsvParams p) {
             o += len[k];
         }
         if (staged) {
-            __syncthreads();
+            __syncwarp();
             char* g = p.out + tile_base;               // first byte of the tile in global memory
             // head: bytes up to the first 16-byte boundary; body: aligned vectors; tail: the rest
             const uint32_t head = mis ? min(16u - mis, total) : 0u;
-            if ((uint32_t)tid < head) g[tid] = s_stage[mis + tid];
+            if ((uint32_t)lane < head) g[lane] = s_stage[mis + lane];
             const uint32_t body = (total - head) >> 4;
             const uint4* sv = reinterpret_cast<const uint4*>(s_stage + mis + head);    // 16-byte aligned by construction
             uint4* gv = reinterpret_cast<uint4*>(g + head);
-            for (uint32_t i = tid; i < body; i += CSV_THREADS) gv[i] = sv[i];
+            for (uint32_t i = lane; i < body; i += 32) gv[i] = sv[i];
             const uint32_t done = head + (body << 4);
-            if (done + (uint32_t)tid < total) g[done + tid] = s_stage[mis + done + tid];
+            if (done + (uint32_t)lane < total) g[done + lane] = s_stage[mis + done + lane];
+            __syncwarp();
         }
     }
+    my_rows = warp_sum_u64(my_rows);
+    if (lane == 0 && my_rows) atomicAdd(p.rows_out, my_rows);
 }
 
 // Per-site records instead of text (OutputRecord, call.hpp:14-27).

@@ -1094,17 +1094,19 @@ int sidgpu_emit_csv(sidgpu_ctx* ctx, uint64_t site_begin, uint64_t n_sites, char
     p.status = (unsigned long long*)ctx->csv_status.p;
     p.bytes_out = ctl_field(ctx, &Control::csv_bytes);
     p.rows_out = ctl_field(ctx, &Control::csv_rows);
+    p.error = ctl_field(ctx, &Control::error);
+    if (!is_quality) CK(cudaMemsetAsync(ctl_field(ctx, &Control::error), 0xFF, sizeof(unsigned long long), ctx->stream));
     p.n_tiles = n_tiles;
     int csv_per_sm = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&csv_per_sm, k_csv, CSV_THREADS, CSV_STAGE) != cudaSuccess || csv_per_sm < 1) csv_per_sm = 1;
-    const unsigned grid = (unsigned)std::min<uint64_t>(n_tiles, (uint64_t)ctx->sm_count * csv_per_sm);
+    const unsigned grid = (unsigned)std::min<uint64_t>((n_tiles + CSV_WARPS - 1) / CSV_WARPS, (uint64_t)ctx->sm_count * csv_per_sm);
     {
         ProfScope prof(ctx, PROF_CSV);
         k_csv<<<grid, CSV_THREADS, CSV_STAGE, ctx->stream>>>(p);
     }
     TRY(check_launch(ctx, "k_csv"));
     TRY(sync_ctl(ctx));
-    if (is_quality && ctx->h_ctl->error != ~0ull) {
+    if (ctx->h_ctl->error != ~0ull) {
         const int st = (int)(ctx->h_ctl->error & 7);
         const int code = st == LINE_MISSING_MAPQ ? SIDGPU_EMISSING_MAPQ : st == LINE_QUAL_SHORT ? SIDGPU_EQUAL_SHORT
                          : st == LINE_MALFORMED ? SIDGPU_EMALFORMED : SIDGPU_EINTERNAL;
