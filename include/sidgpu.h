@@ -210,11 +210,12 @@ int sidgpu_format_g(sidgpu_ctx* ctx, const double* d_values, uint64_t n, char* d
 
 /* Counters for benchmarking: kernels launched by this ctx since creation; and, when enabled,
  * device time per kernel family measured with CUDA events on the ctx's stream around each launch:
- * ms[0]/launches[0] tokenizer (K1), [1] classification (K2), [2] CSV formatter (K6).
+ * ms[0]/launches[0] tokenizer (K1), [1] classification (K2), [2] CSV formatter (K6), [3] the two small
+ * kernels that turn the tokenizer's block table into the file order of the sites (one count per pair).
  * sidgpu_profile(ctx, enable) resets the accumulators. */
 uint64_t sidgpu_launch_count(const sidgpu_ctx* ctx);
 int sidgpu_profile(sidgpu_ctx* ctx, int enable);
-int sidgpu_kernel_times(sidgpu_ctx* ctx, double ms[3], uint64_t launches[3]);
+int sidgpu_kernel_times(sidgpu_ctx* ctx, double ms[4], uint64_t launches[4]);
 
 #ifdef __cplusplus
 }

@@ -123,11 +123,11 @@ class Context:
         self._ck(self.lib.sidgpu_profile(self.h, 1 if enable else 0))
 
     def kernel_times(self):
-        """{'tokenize': (ms, launches), 'classify': ..., 'csv': ...} since profile(True)."""
-        ms = (ctypes.c_double * 3)()
-        n = (ctypes.c_uint64 * 3)()
+        """{'tokenize': (ms, launches), 'classify': ..., 'csv': ..., 'order': ...} since profile(True)."""
+        ms = (ctypes.c_double * 4)()
+        n = (ctypes.c_uint64 * 4)()
         self._ck(self.lib.sidgpu_kernel_times(self.h, ms, n))
-        return {k: (ms[i], n[i]) for i, k in enumerate(("tokenize", "classify", "csv"))}
+        return {k: (ms[i], n[i]) for i, k in enumerate(("tokenize", "classify", "csv", "order"))}
 
     # ---- K1
     def tokenize(self, d_text, text_len, begin=0, end=None, want_qual=False):

@@ -187,7 +187,7 @@ int check_launch(sidgpu_ctx* ctx, const char* what) {
     return SIDGPU_OK;
 }
 
-enum { PROF_TOKENIZE = 0, PROF_CLASSIFY = 1, PROF_CSV = 2, PROF_OTHER = 3 };
+enum { PROF_TOKENIZE = 0, PROF_CLASSIFY = 1, PROF_CSV = 2, PROF_ORDER = 3 };
 
 cudaEvent_t take_event(sidgpu_ctx* ctx) {
     if (!ctx->free_events.empty()) { cudaEvent_t e = ctx->free_events.back(); ctx->free_events.pop_back(); return e; }
@@ -432,6 +432,9 @@ int run_tokenizer(sidgpu_ctx* ctx, const char* d_text, size_t text_len, size_t r
             if (want_qual && strict_qual) k_tokenize<false><<<grid, TOK_THREADS, dyn_smem, ctx->stream>>>(p);
             else k_tokenize<true><<<grid, TOK_THREADS, dyn_smem, ctx->stream>>>(p);
             TRY(check_launch(ctx, "k_tokenize"));
+        }
+        {
+            ProfScope prof(ctx, PROF_ORDER);
             k_blk_sums<<<n_chunks, BLK_THREADS, 0, ctx->stream>>>((const unsigned long long*)ctx->blk.p, n_blocks, (unsigned long long*)ctx->blk_part.p);
             TRY(check_launch(ctx, "k_blk_sums"));
             k_blk_order<<<n_chunks, BLK_THREADS, 0, ctx->stream>>>((const unsigned long long*)ctx->blk.p, n_blocks, (const unsigned long long*)ctx->blk_part.p,
@@ -822,11 +825,11 @@ int sidgpu_profile(sidgpu_ctx* ctx, int enable) {
     return SIDGPU_OK;
 }
 
-int sidgpu_kernel_times(sidgpu_ctx* ctx, double ms[3], uint64_t launches[3]) {
+int sidgpu_kernel_times(sidgpu_ctx* ctx, double ms[4], uint64_t launches[4]) {
     if (!ctx) return SIDGPU_EINVAL;
     CK(cudaStreamSynchronize(ctx->stream));
     resolve_profile(ctx);
-    for (int i = 0; i < 3; ++i) {
+    for (int i = 0; i < 4; ++i) {
         if (ms) ms[i] = ctx->kernel_ms[i];
         if (launches) launches[i] = ctx->kernel_launches[i];
     }
