@@ -38,6 +38,7 @@ def parse_args():
     ap.add_argument("--method", default="local")
     ap.add_argument("--depth", default="depth30", choices=["depth30", "depth60", "depth500"])
     ap.add_argument("--cpu-sample-sites", type=int, default=3_000_000)
+    ap.add_argument("--het-only", action="store_true", help="emit only rows labelled het (the pipeline's grep ',het,'); not the headline config")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -224,7 +225,7 @@ def run_ours(args):
     torch.cuda.synchronize()
 
     ctx = sid_b200.Context(device=local_rank, stream=stream.cuda_stream, max_chunk_bytes=256 << 20)
-    params = sid_b200.Context.make_params(args.method)
+    params = sid_b200.Context.make_params(args.method, het_only=args.het_only)
     ctx_streams = args.method in ("local", "quality")       # rows can be emitted chunk by chunk, no global step
     state = {"csv_bytes": 0, "rows": 0}
 
@@ -360,7 +361,8 @@ def run_ours(args):
             "data": "synthetic",
             "config": {"workload": workload_name(args), "text_bytes_per_gpu": text_len, "csv_bytes_per_gpu": state["csv_bytes"],
                        "l2": "inputs larger than L2 (%.1f GB of text per step)" % (text_len / 1e9), "parallelism": "position-sharded x%d, no data-path collective" % world,
-                       "generator_seconds": gen_s, "sites_per_gpu": n_sites, "note": note},
+                       "generator_seconds": gen_s, "sites_per_gpu": n_sites,
+                       "note": ("het rows only (--het-only); " + (note or "")) if args.het_only else note},
             "roofline": {"bound": "hbm", "kernel": "k_tokenize", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                          "frac": achieved / hbm_peak if hbm_peak else None, "traffic": traffic, "peak_kind": peak_kind,
                          "algorithmic_bytes_per_launch": text_len, "avg_launch_ms": tok_avg_ms, "launches_timed": tok_n,

@@ -60,3 +60,6 @@ SidRunInfo sidCallToStream(const std::string& method, const char* text, size_t l
                            const char* header = nullptr);
 // Selects the GPU (default 0) and the chunk size of the host path for subsequent calls.
 void sidSetDevice(int device, size_t max_chunk_bytes = 0);
+// Only rows labelled "het" from now on: the `grep ',het,'` of scripts/sid-pipeline/run-sid.sh:16-17 done
+// before the rows leave the GPU.  Applies to sidCallToStream and to the four call* functions.
+void sidSetHetOnly(bool het_only);

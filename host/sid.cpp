@@ -1,6 +1,8 @@
 // `sid [flags] input_file` -- the reference's command line (sid.cpp:11-110) over the GPU path.
 // Same flags and defaults (-m METHOD, -r PRIOR, -R, -p LEVEL, -E ERROR, -h), same CSV on stdout,
-// same `# ...` lines on stderr, same exit codes.  Extra long options: --device N, --chunk-mb N.
+// same `# ...` lines on stderr, same exit codes.  Extra long options: --device N, --chunk-mb N,
+// --het-only (rows labelled het only: the pipeline's `grep ',het,'`, scripts/sid-pipeline/run-sid.sh:16-17;
+// the header line is kept).
 #include <fcntl.h>
 #include <getopt.h>
 #include <sys/mman.h>
@@ -37,7 +39,8 @@ int main(int argc, char** argv) {
     GlobalOptions o;
     int device = 0;
     size_t chunk_mb = 0;
-    static const option LONG[] = {{"device", required_argument, nullptr, 1000}, {"chunk-mb", required_argument, nullptr, 1001}, {nullptr, 0, nullptr, 0}};
+    bool het_only = false;
+    static const option LONG[] = {{"device", required_argument, nullptr, 1000}, {"chunk-mb", required_argument, nullptr, 1001}, {"het-only", no_argument, nullptr, 1002}, {nullptr, 0, nullptr, 0}};
     int flag;
     while ((flag = getopt_long(argc, argv, "E:Rhm:p:r:", LONG, nullptr)) != -1) {      // optstring as built by sid.cpp:60-69
         switch (flag) {
@@ -49,6 +52,7 @@ int main(int argc, char** argv) {
             case 'E': o.site_error_threshold = atof(optarg); break;
             case 1000: device = atoi(optarg); break;
             case 1001: chunk_mb = (size_t)atol(optarg); break;
+            case 1002: het_only = true; break;
             default: exit(EXIT_FAILURE);             // sid.cpp:80-82
         }
     }
@@ -74,6 +78,7 @@ int main(int argc, char** argv) {
     std::ios::sync_with_stdio(false);
     try {
         sidSetDevice(device, chunk_mb << 20);
+        sidSetHetOnly(het_only);
         sidCallToStream(o.method, text, len, o.estimate_prior, o.snp_prior, o.site_error_threshold, o.significance_level,
                         std::cout, std::cerr, "chrom,pos,label,gt,hom_conf,het_conf,conf_type");          // sid.cpp:102
         std::cout.flush();

@@ -15,6 +15,7 @@ namespace {
 
 int g_device = 0;
 size_t g_chunk = 0;
+bool g_het_only = false;
 
 struct Ctx {
     sidgpu_ctx* h = nullptr;
@@ -91,6 +92,7 @@ void run(int method, const char* text, size_t len, bool estimate_prior, double p
     p.prior = prior;
     p.error_threshold = error_threshold;
     p.significance_level = significance_level;
+    p.het_only = g_het_only ? 1 : 0;
     out.csv.reserve(len + len / 2 + 4096);
     for (;;) {
         const int rc = sidgpu_call_host(ctx().h, &p, text, len, out.csv.p, out.csv.cap, &out.bytes, &out.sites, &out.rows);
@@ -208,6 +210,8 @@ void sidSetDevice(int device, size_t max_chunk_bytes) {
     g_device = device;
     g_chunk = max_chunk_bytes;
 }
+
+void sidSetHetOnly(bool het_only) { g_het_only = het_only; }
 
 // ---- call.hpp:40-43 ------------------------------------------------------------------------------
 std::vector<OutputRecord> callSiteMLError(std::istream& in, const bool estimate_prior, double prior, double error_threshold,

@@ -68,6 +68,10 @@ typedef struct {
      * (pi, eps, nucleotide distribution) instead of running the optimiser. */
     int fit_given;
     double fit_pi, fit_eps, fit_nd[4];
+    /* Emit only the rows whose label is "het": what the reference's pipeline keeps of the CSV
+     * (scripts/sid-pipeline/run-sid.sh:16-17 pipes it through grep ',het,').  Sites, fits and
+     * sidgpu_emit_records are unaffected; *rows_out counts the rows written. */
+    int het_only;
 } sidgpu_params;
 
 /* ------------------------------------------------------------------------------------------------

@@ -21,7 +21,7 @@ class Params(ctypes.Structure):
     _fields_ = [("method", ctypes.c_int), ("estimate_prior", ctypes.c_int), ("prior", ctypes.c_double),
                 ("error_threshold", ctypes.c_double), ("significance_level", ctypes.c_double),
                 ("fit_given", ctypes.c_int), ("fit_pi", ctypes.c_double), ("fit_eps", ctypes.c_double),
-                ("fit_nd", ctypes.c_double * 4)]
+                ("fit_nd", ctypes.c_double * 4), ("het_only", ctypes.c_int)]
 
 
 class SitesView(ctypes.Structure):

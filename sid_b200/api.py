@@ -158,13 +158,15 @@ class Context:
 
     # ---- sessions
     @staticmethod
-    def make_params(method, estimate_prior=False, prior=-1.0, error_threshold=0.1, significance_level=0.05, fit=None):
+    def make_params(method, estimate_prior=False, prior=-1.0, error_threshold=0.1, significance_level=0.05, fit=None,
+                    het_only=False):
         p = Params()
         p.method = METHODS[method] if isinstance(method, str) else int(method)
         p.estimate_prior = 1 if estimate_prior else 0
         p.prior = prior
         p.error_threshold = error_threshold
         p.significance_level = significance_level
+        p.het_only = 1 if het_only else 0
         if fit is not None:
             p.fit_given = 1
             p.fit_pi, p.fit_eps = fit[0], fit[1]
@@ -362,10 +364,13 @@ def callQualityBasedSimple(text, estimate_prior=False, prior=-1.0, significance_
     return _call(text, Context.make_params("quality", estimate_prior, prior, 0.1, significance_level), ctx)
 
 
-def sid_csv(text, method="local", estimate_prior=False, prior=-1.0, error_threshold=0.1, significance_level=0.05, ctx=None):
-    """What `sid -m METHOD file` prints on stdout (sid.cpp:92-105), as bytes."""
+def sid_csv(text, method="local", estimate_prior=False, prior=-1.0, error_threshold=0.1, significance_level=0.05, ctx=None,
+            het_only=False):
+    """What `sid -m METHOD file` prints on stdout (sid.cpp:92-105), as bytes; with het_only what is left of it
+    after the pipeline's `grep ',het,'` (scripts/sid-pipeline/run-sid.sh:16-17), header excluded."""
     if method not in METHODS:
         return CSV_HEADER                       # sid.cpp:92-100 has no else branch: header only
     ctx = ctx or default_context()
-    rows, _, _ = ctx.call_host(text, Context.make_params(method, estimate_prior, prior, error_threshold, significance_level))
-    return CSV_HEADER + rows
+    rows, _, _ = ctx.call_host(text, Context.make_params(method, estimate_prior, prior, error_threshold, significance_level,
+                                                         het_only=het_only))
+    return rows if het_only else CSV_HEADER + rows

@@ -21,19 +21,19 @@ struct ClassifyParams {
     const double* adj_hom;       // likelihood_ratio: BH-adjusted p-values per entry index (or NULL)
     const double* adj_het;
     const uint32_t* entry_to_unique;   // likelihood_ratio: entry index -> row of adj_* (0xFFFFFFFF: dropped)
+    int het_only;                // rows of hom profiles get length 0: the CSV writer skips them
 };
 
 #if defined(__CUDACC__)
 
-__device__ __forceinline__ void store_class(const TableView& t, uint32_t slot, const CallResult& r, bool probability) {
+__device__ __forceinline__ void store_class(const TableView& t, uint32_t slot, const CallResult& r, bool probability, bool het_only) {
     t.label[slot] = r.label;
     t.gt[2 * slot] = r.gt0;
     t.gt[2 * slot + 1] = r.gt1;
     t.hom[slot] = r.hom;
     t.het[slot] = r.het;
     char buf[SUFFIX_BYTES];
-    const int n = format_suffix(r, probability, buf);
-    buf[SUFFIX_BYTES - 1] = (char)n;
+    const int n = (het_only && r.label != 1) ? 0 : format_suffix(r, probability, buf);
     char* dst = t.suffix + (size_t)slot * SUFFIX_BYTES;
     for (int i = 0; i < n; ++i) dst[i] = buf[i];
     dst[SUFFIX_BYTES - 1] = (char)n;
@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(128) k_classify(const ClassifyParams p) {
             if (r.het < p.alpha) { r.label = 1; r.gt1 = base_char(s); }     // call.cpp:120-123
         }
     }
-    store_class(p.table, slot, r, p.method == 1);
+    store_class(p.table, slot, r, p.method == 1, p.het_only != 0);
 }
 
 // ------------------------------------------------------------------------------------------- K6

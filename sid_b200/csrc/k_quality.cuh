@@ -26,6 +26,7 @@ struct QualityParams {
     uint64_t site_begin, n_sites;
     const double* lut;          // [0,256) log(1-e)  [256,512) log(e)  [512,768) log(1-2e/3)  [768,1024) log(2e/3)
     double prior, alpha;
+    int het_only;               // rows of hom sites get length 0
     char* site_suffix;          // SUFFIX_BYTES per site
     unsigned long long* error;
 };
@@ -92,7 +93,7 @@ __global__ void __launch_bounds__(QUAL_THREADS) k_quality(const QualityParams p)
     }
     const CallResult r = call_quality(src, line_abs, pl, p.lut, p.prior, p.alpha);
     char buf[SUFFIX_BYTES];
-    const int n = format_suffix(r, false, buf);
+    const int n = (p.het_only && r.label != 1) ? 0 : format_suffix(r, false, buf);
     for (int k = 0; k < n; ++k) dst[k] = buf[k];
     dst[SUFFIX_BYTES - 1] = (char)n;
 }

@@ -512,6 +512,7 @@ int classify_entries(sidgpu_ctx* ctx, uint32_t first, uint32_t last) {
     p.prior = ctx->session_prior;
     p.error_threshold = ctx->params.error_threshold;
     p.alpha = ctx->params.significance_level;
+    p.het_only = ctx->params.het_only;
     if (p.method != 0) {
         p.lynch = host_lynch_consts(ctx->fit_nd, ctx->fit.eps);
         p.pi = ctx->fit.pi;
@@ -684,6 +685,7 @@ int quality_rows(sidgpu_ctx* ctx, uint64_t site_begin, uint64_t n) {
     q.lut = (const double*)ctx->quality_lut.p;
     q.prior = ctx->session_prior;
     q.alpha = ctx->params.significance_level;
+    q.het_only = ctx->params.het_only;
     q.site_suffix = (char*)ctx->site_suffix.p;
     q.error = ctl_field(ctx, &Control::error);
     CK(cudaMemsetAsync(ctl_field(ctx, &Control::error), 0xFF, sizeof(unsigned long long), ctx->stream));

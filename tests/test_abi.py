@@ -45,3 +45,24 @@ def test_no_gpu_means_loud_failure():
     with pytest.raises(sid_b200.SidGpuError) as e:
         sid_b200.Context()
     assert "no CPU fallback" in str(e.value)
+
+
+def test_ctypes_structs_match_the_header(tmp_path):
+    """The ctypes mirror of the ABI's structs has the C compiler's sizes and offsets."""
+    import ctypes
+    import subprocess
+    from sid_b200 import _lib
+    src = tmp_path / "layout.c"
+    src.write_text(
+        '#include <stddef.h>\n#include <stdio.h>\n#include "sidgpu.h"\n'
+        'int main(void) {\n'
+        '  printf("%zu %zu %zu %zu\\n", sizeof(sidgpu_params), offsetof(sidgpu_params, het_only), offsetof(sidgpu_params, fit_nd), sizeof(sidgpu_config));\n'
+        '  printf("%zu %zu %zu\\n", sizeof(sidgpu_sites_view), sizeof(sidgpu_unique_view), sizeof(sidgpu_fit));\n'
+        '  return 0;\n}\n')
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], stdout=subprocess.PIPE, check=True, text=True).stdout.split()
+    got = [int(x) for x in out]
+    want = [ctypes.sizeof(_lib.Params), _lib.Params.het_only.offset, _lib.Params.fit_nd.offset, ctypes.sizeof(_lib.Config),
+            ctypes.sizeof(_lib.SitesView), ctypes.sizeof(_lib.UniqueView), ctypes.sizeof(_lib.Fit)]
+    assert got == want

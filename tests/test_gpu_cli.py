@@ -46,6 +46,18 @@ def test_cli_matches_reference(sid_bin, case):
         assert re.search(r"# GSL function minimization converged in \d+ iterations\.", err)
 
 
+def test_cli_het_only(sid_bin):
+    """--het-only == the reference's output through grep ',het,' (header kept)."""
+    case = [c for c in MANIFEST["cases"] if c["input"] == "depth30.plp" and c["flags"][:2] == ["-m", "local"]][0]
+    rc, out, err = run(sid_bin, "--het-only", *case["flags"], os.path.join(GOLDEN, case["input"]))
+    assert rc == 0, err
+    ref = read(case["csv"]).splitlines(keepends=True)
+    want = b"".join(l for i, l in enumerate(ref) if i == 0 or b",het," in l)
+    assert want.count(b"\n") > 1
+    n, diffs = op.compare_csv(out, want)
+    assert diffs <= 2
+
+
 def test_cli_error_behaviour(sid_bin):
     # malformed line: the reference terminates on std::invalid_argument (SIGABRT), nothing on stdout
     rc, out, err = run(sid_bin, os.path.join(GOLDEN, "malformed_too_few_columns.plp"))

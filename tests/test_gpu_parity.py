@@ -78,6 +78,28 @@ def test_csv_matches_reference(native, gpu_ctx, case):
     assert diffs <= max(2, n // 1000), "too many last-digit differences: %d of %d" % (diffs, n)
 
 
+@pytest.mark.parametrize("case", MANIFEST["cases"], ids=lambda c: c["csv"])
+def test_het_only_is_grep_het(native, gpu_ctx, case):
+    """het_only leaves what the reference's pipeline keeps: its CSV through `grep ',het,'`
+    (scripts/sid-pipeline/run-sid.sh:16-17), filtered before the rows leave the GPU."""
+    text = read(case["input"])
+    kw = flags_to_kwargs(case["flags"])
+    fit = None
+    if "heterozygosity" in case or kw.get("estimate_prior"):
+        o = op.oracle_call(text, **kw)
+        prof = o["profiles"]
+        cov = op.unpack_profiles(prof).astype(np.int64).sum(axis=1)
+        u, c = op.oracle_unique(prof[cov >= 4])
+        fit = (o["pi"], o["eps"], op.oracle_nd(u, c))
+    p = params_from_flags(case["flags"], fit)
+    p.het_only = 1
+    rows, n_sites, n_rows = gpu_ctx.call_host(text, p)
+    want = b"".join(l for l in read(case["csv"]).splitlines(keepends=True) if b",het," in l)
+    n, diffs = op.compare_csv(rows, want)
+    assert n == n_rows == want.count(b"\n")
+    assert diffs <= max(2, n // 1000)
+
+
 @pytest.mark.parametrize("case", MANIFEST["malformed"], ids=lambda c: c["input"])
 def test_malformed_raises(native, gpu_ctx, case):
     import sid_b200
