@@ -100,6 +100,82 @@ def test_het_only_is_grep_het(native, gpu_ctx, case):
     assert diffs <= max(2, n // 1000)
 
 
+@pytest.fixture(scope="module")
+def tiny_chunk_ctx():
+    import sid_b200
+    ctx = sid_b200.Context(max_chunk_bytes=20000)          # every golden input becomes 4..18 chunks
+    yield ctx
+    ctx.close()
+
+
+@pytest.mark.parametrize("case", [c for c in MANIFEST["cases"] if c["input"] in ("depth30.plp", "depth30_two_chroms.plp", "quality30.plp",
+                                                                                  "depth500.plp", "edge.plp")], ids=lambda c: c["csv"])
+def test_csv_many_small_chunks(native, tiny_chunk_ctx, case):
+    """The same rows when the host path cuts the text into many chunks: sessions that keep their sites
+    (bayes, likelihood_ratio, -R) append to the store feed after feed, the others stream chunk by chunk."""
+    import sid_b200
+    text = read(case["input"])
+    kw = flags_to_kwargs(case["flags"])
+    fit = None
+    if "heterozygosity" in case or kw.get("estimate_prior"):
+        o = op.oracle_call(text, **kw)
+        prof = o["profiles"]
+        cov = op.unpack_profiles(prof).astype(np.int64).sum(axis=1)
+        u, c = op.oracle_unique(prof[cov >= 4])
+        fit = (o["pi"], o["eps"], op.oracle_nd(u, c))
+    rows, n_sites, n_rows = tiny_chunk_ctx.call_host(text, params_from_flags(case["flags"], fit))
+    n, diffs = op.compare_csv(sid_b200.CSV_HEADER + rows, read(case["csv"]))
+    assert n == n_rows
+    assert diffs <= max(2, n // 1000)
+
+
+def test_emit_sub_ranges_concatenate(native, gpu_ctx):
+    """sidgpu_emit_csv over odd-sized pieces of the store == one call over all of it (file order through order[])."""
+    import sid_b200
+    text = read("depth30_two_chroms.plp")
+    d = gpu_ctx.upload_text(text)
+    cap = 2 * len(text) + 4096
+    out = sid_b200.api.DeviceBuffer(gpu_ctx, cap)
+
+    def emit(begin, count):
+        nbytes, _ = gpu_ctx.emit_csv(begin, count, out, cap)
+        return out.download(np.uint8, nbytes).tobytes() if nbytes else b""
+
+    try:
+        for method in ("local", "bayes"):
+            o = op.oracle_call(text, method)
+            fit = None
+            if method == "bayes":
+                prof = o["profiles"]
+                cov = op.unpack_profiles(prof).astype(np.int64).sum(axis=1)
+                u, c = op.oracle_unique(prof[cov >= 4])
+                fit = (o["pi"], o["eps"], op.oracle_nd(u, c))
+            gpu_ctx.begin(sid_b200.Context.make_params(method, fit=fit))
+            # three feeds over byte ranges of the same text: the store is appended to (bayes) or replaced (local)
+            cuts = [0, len(text) // 3 + 7, 2 * len(text) // 3 + 1, len(text)]
+            if method == "bayes":
+                n = sum(gpu_ctx.feed(d, len(text), a, b) for a, b in zip(cuts[:-1], cuts[1:]))
+                gpu_ctx.finish()
+            else:
+                n = gpu_ctx.feed(d, len(text))
+            whole = emit(0, n)
+            pieces = b""
+            s = 0
+            for step in (1, 3, 127, 128, 129, 1001, 4099, n):
+                if s >= n:
+                    break
+                k = min(step, n - s)
+                pieces += emit(s, k)
+                s += k
+            if s < n:
+                pieces += emit(s, n - s)
+            assert pieces == whole
+            assert whole.count(b"\n") <= n
+    finally:
+        out.free()
+        d.free()
+
+
 @pytest.mark.parametrize("case", MANIFEST["malformed"], ids=lambda c: c["input"])
 def test_malformed_raises(native, gpu_ctx, case):
     import sid_b200
