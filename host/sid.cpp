@@ -2,18 +2,23 @@
 // Same flags and defaults (-m METHOD, -r PRIOR, -R, -p LEVEL, -E ERROR, -h), same CSV on stdout,
 // same `# ...` lines on stderr, same exit codes.  Extra long options: --device N, --chunk-mb N,
 // --het-only (rows labelled het only: the pipeline's `grep ',het,'`, scripts/sid-pipeline/run-sid.sh:16-17;
-// the header line is kept).
+// the header line is kept).  A gzip-compressed input (as the pipeline stores its pileups,
+// scripts/prepare-data.sh:14) is inflated in memory instead of `zcat` to a temporary file
+// (scripts/sid-pipeline/run-sid.sh:15).
 #include <fcntl.h>
 #include <getopt.h>
 #include <sys/mman.h>
 #include <sys/stat.h>
 #include <unistd.h>
+#include <zlib.h>
 
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 #include <iostream>
 #include <stdexcept>
 #include <string>
+#include <vector>
 
 #include "call.hpp"
 
@@ -67,10 +72,29 @@ int main(int argc, char** argv) {
         std::cerr << "Could not open file: " << path << std::endl;
         exit(EXIT_FAILURE);
     }
-    const size_t len = (size_t)st.st_size;
+    size_t len = (size_t)st.st_size;
     const char* text = "";
     void* map = nullptr;
-    if (len) {
+    std::vector<char> inflated;
+    unsigned char magic[2] = {0, 0};
+    const bool gz = len >= 18 && pread(fd, magic, 2, 0) == 2 && magic[0] == 0x1f && magic[1] == 0x8b;
+    if (gz) {
+        gzFile z = gzdopen(dup(fd), "rb");
+        if (!z) { std::cerr << "Could not open file: " << path << std::endl; exit(EXIT_FAILURE); }
+        gzbuffer(z, 1u << 20);
+        inflated.resize(std::max<size_t>(len * 4, (size_t)1 << 20));
+        size_t have = 0;
+        for (;;) {
+            if (have == inflated.size()) inflated.resize(inflated.size() * 2);
+            const int got = gzread(z, inflated.data() + have, (unsigned)std::min<size_t>(inflated.size() - have, (size_t)1 << 30));
+            if (got < 0) { std::cerr << "Could not inflate file: " << path << std::endl; exit(EXIT_FAILURE); }
+            if (got == 0) break;
+            have += (size_t)got;
+        }
+        gzclose(z);
+        len = have;
+        text = inflated.data();
+    } else if (len) {
         map = mmap(nullptr, len, PROT_READ, MAP_PRIVATE, fd, 0);
         if (map == MAP_FAILED) { std::cerr << "Could not open file: " << path << std::endl; exit(EXIT_FAILURE); }
         text = (const char*)map;

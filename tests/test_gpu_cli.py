@@ -58,6 +58,20 @@ def test_cli_het_only(sid_bin):
     assert diffs <= 2
 
 
+def test_cli_reads_gzip_input(sid_bin, tmp_path):
+    """`sid x.plp.gz` == `zcat x.plp.gz > tmp; sid tmp` (scripts/sid-pipeline/run-sid.sh:15-16), incl. two gzip members."""
+    import gzip
+    case = [c for c in MANIFEST["cases"] if c["input"] == "depth30_two_chroms.plp" and c["flags"][:2] == ["-m", "local"]][0]
+    text = read(case["input"])
+    cut = text.index(b"\n", len(text) // 2) + 1
+    gz = tmp_path / "input.plp.gz"
+    gz.write_bytes(gzip.compress(text[:cut]) + gzip.compress(text[cut:]))
+    rc, out, err = run(sid_bin, *case["flags"], str(gz))
+    assert rc == 0, err
+    n, diffs = op.compare_csv(out, read(case["csv"]))
+    assert diffs <= max(2, n // 1000)
+
+
 def test_cli_error_behaviour(sid_bin):
     # malformed line: the reference terminates on std::invalid_argument (SIGABRT), nothing on stdout
     rc, out, err = run(sid_bin, os.path.join(GOLDEN, "malformed_too_few_columns.plp"))
