@@ -31,16 +31,46 @@ SID_HD uint32_t byte_perm(uint32_t x, uint32_t y, uint32_t s) {
 #endif
 }
 
+// Three-input logic with the truth table spelled out (a = 0xF0, b = 0xCC, c = 0xAA): on the device one
+// LOP3 per call.  Stage 1 is bound by the integer ALU pipe, so the number of LOP3s is counted by hand.
+constexpr int TA = 0xF0, TB = 0xCC, TC = 0xAA;
+template <int LUT>
+SID_HD uint32_t lop3(uint32_t a, uint32_t b, uint32_t c) {
+#if defined(__CUDA_ARCH__)
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, %4;" : "=r"(d) : "r"(a), "r"(b), "r"(c), "n"(LUT & 0xFF));
+    return d;
+#else
+    uint32_t r = 0;
+    for (int i = 0; i < 8; ++i)
+        if ((LUT >> i) & 1) r |= ((i & 4) ? a : ~a) & ((i & 2) ? b : ~b) & ((i & 1) ? c : ~c);
+    return r;
+#endif
+}
+
+// x >> k for a constant k.  (The high half of x * 2^(32-k) would run on the FMA pipe instead of the
+// saturated ALU pipe, but IMAD.HI is slower: 1.256 vs 1.236 ms per 1.63 GB.  -DSID_SHR_FMA to try again.)
+template <int K>
+SID_HD uint32_t shr_fma(uint32_t x) {
+#if defined(__CUDA_ARCH__) && defined(SID_SHR_FMA)
+    return __umulhi(x, 1u << (32 - K));
+#else
+    return x >> K;
+#endif
+}
+
 // 8x8 bit transpose of the 8 bytes (lo = bytes 0..3, hi = bytes 4..7): afterwards byte j of lo
 // (j = 0..3) / hi (j = 4..7) holds bit j of the eight input bytes, input byte i at bit i.
 SID_HD void transpose8(uint32_t& lo, uint32_t& hi) {
+    // a delta swap is two LOP3s: t = (x ^ (x >> s)) & m, then x ^ t ^ (t << s)
+    constexpr int XOR_AND = (TA ^ TB) & TC, XOR3 = TA ^ TB ^ TC, SELECT = (TA & TC) | (TB & ~TC);
     uint32_t t;
-    t = (lo ^ (lo >> 7)) & 0x00AA00AAu; lo = lo ^ t ^ (t << 7);
-    t = (hi ^ (hi >> 7)) & 0x00AA00AAu; hi = hi ^ t ^ (t << 7);
-    t = (lo ^ (lo >> 14)) & 0x0000CCCCu; lo = lo ^ t ^ (t << 14);
-    t = (hi ^ (hi >> 14)) & 0x0000CCCCu; hi = hi ^ t ^ (t << 14);
-    const uint32_t nl = (lo & 0x0F0F0F0Fu) | ((hi << 4) & 0xF0F0F0F0u);
-    const uint32_t nh = (hi & 0xF0F0F0F0u) | ((lo >> 4) & 0x0F0F0F0Fu);
+    t = lop3<XOR_AND>(lo, shr_fma<7>(lo), 0x00AA00AAu); lo = lop3<XOR3>(lo, t, t << 7);
+    t = lop3<XOR_AND>(hi, shr_fma<7>(hi), 0x00AA00AAu); hi = lop3<XOR3>(hi, t, t << 7);
+    t = lop3<XOR_AND>(lo, shr_fma<14>(lo), 0x0000CCCCu); lo = lop3<XOR3>(lo, t, t << 14);
+    t = lop3<XOR_AND>(hi, shr_fma<14>(hi), 0x0000CCCCu); hi = lop3<XOR3>(hi, t, t << 14);
+    const uint32_t nl = lop3<SELECT>(lo, hi << 4, 0x0F0F0F0Fu);        // low nibbles of lo, high nibbles from hi
+    const uint32_t nh = lop3<SELECT>(shr_fma<4>(lo), hi, 0x0F0F0F0Fu);
     lo = nl;
     hi = nh;
 }
@@ -75,19 +105,28 @@ SID_HD ClassWords classify32(const uint32_t w[8]) {
     const uint32_t p6 = byte_perm(x01, x23, 0x5410u), p7 = byte_perm(x01, x23, 0x7632u);
     ClassWords k;
     k.high = p7;
-    const uint32_t n7 = ~p7;
-    const uint32_t lo_zero = ~(p3 | p2 | p1 | p0);
-    k.term = n7 & ~p6 & (~p5 | (~p4 & lo_zero));                    // 0x00..0x1f, 0x20
-    k.nl = n7 & ~p6 & ~p5 & ~p4 & p3 & ~p2 & p1 & ~p0;              // 0x0a
-    const uint32_t l46 = n7 & p6 & ~p4;                             // 0x4_, 0x6_
-    k.a = l46 & ~p3 & ~p2 & ~p1 & p0;                               // 0x41 0x61
-    k.c = l46 & ~p3 & ~p2 & p1 & p0;                                // 0x43 0x63
-    k.g = l46 & ~p3 & p2 & p1 & p0;                                 // 0x47 0x67
-    k.t = n7 & p6 & p4 & ~p3 & p2 & ~p1 & ~p0;                      // 0x54 0x74
-    const uint32_t h2 = n7 & ~p6 & p5 & ~p4;                        // 0x2_
-    k.dot = h2 & p3 & p2 & ~p0;                                     // 0x2c 0x2e
-    k.pm = h2 & p3 & p0 & (p2 ^ p1);                                // 0x2b 0x2d
-    k.caret = n7 & p6 & ~p5 & p4 & p3 & p2 & p1 & ~p0;              // 0x5e
+    // high nibbles (p7 p6 p5 p4)
+    const uint32_t h00 = lop3<~TA & ~TB & ~TC>(p7, p6, p5);            // 000x: 0x00..0x1f
+    const uint32_t h2 = lop3<~TA & ~TB & TC>(p7, p6, p5) & ~p4;        // 0010: 0x2_
+    const uint32_t h46 = lop3<~TA & TB & ~TC>(p7, p6, p4);             // 01x0: 0x4_ 0x6_
+    const uint32_t h57 = lop3<~TA & TB & TC>(p7, p6, p4);              // 01x1: 0x5_ 0x7_
+    // low nibbles (p3 p2 p1 p0), three planes first, then p0 together with the high-nibble term
+    const uint32_t l000 = lop3<~TA & ~TB & ~TC>(p3, p2, p1);
+    const uint32_t l001 = lop3<~TA & ~TB & TC>(p3, p2, p1);
+    const uint32_t l011 = lop3<~TA & TB & TC>(p3, p2, p1);
+    const uint32_t l010 = lop3<~TA & TB & ~TC>(p3, p2, p1);
+    const uint32_t l111 = lop3<TA & TB & TC>(p3, p2, p1);
+    const uint32_t l101 = lop3<TA & ~TB & TC>(p3, p2, p1);
+    const uint32_t l1x = lop3<TA & (TB ^ TC)>(p3, p2, p1);             // 101_ or 110_
+    k.a = lop3<TA & TB & TC>(l000, p0, h46);                           // 0x41 0x61
+    k.c = lop3<TA & TB & TC>(l001, p0, h46);                           // 0x43 0x63
+    k.g = lop3<TA & TB & TC>(l011, p0, h46);                           // 0x47 0x67
+    k.t = lop3<TA & ~TB & TC>(l010, p0, h57);                          // 0x54 0x74
+    k.dot = lop3<TA & ~TB & TC>(p3 & p2, p0, h2);                      // 0x2c 0x2e
+    k.pm = lop3<TA & TB & TC>(l1x, p0, h2);                            // 0x2b 0x2d
+    k.caret = lop3<TA & ~TB & TC>(l111, p0, h57) & ~p5;                // 0x5e
+    k.nl = lop3<TA & ~TB & TC>(l101, p0, h00) & ~p4;                   // 0x0a
+    k.term = h00 | lop3<TA & ~TB & TC>(l000, p0, h2);                  // 0x00..0x1f, 0x20
     return k;
 }
 
