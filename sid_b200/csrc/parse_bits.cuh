@@ -1,7 +1,7 @@
 // Bit-parallel form of the tokenizer.
 //
-// Stage 1 (flat, no per-line work): 32 bytes of text are transposed into their 8 bit planes (an
-// 8x8 bit-matrix transpose per 8 bytes, three mask-and-shift rounds, then byte permutes), and every
+// Stage 1 (flat, no per-line work): 32 bytes of text are transposed into their 8 bit planes (byte
+// permutes, then an 8x8 bit-matrix transpose across eight words: three rounds of block swaps), and every
 // character class the grammar of parseReadBases (pileup.cpp:70-153) distinguishes becomes a boolean
 // function of the planes: one 32-bit word per class and 32 bytes of text.  The words go to bit
 // arrays in shared memory (bit i <-> byte i of the warp's slice).
@@ -59,18 +59,13 @@ SID_HD uint32_t shr_fma(uint32_t x) {
 #endif
 }
 
-// 8x8 bit transpose of the 8 bytes (lo = bytes 0..3, hi = bytes 4..7): afterwards byte j of lo
-// (j = 0..3) / hi (j = 4..7) holds bit j of the eight input bytes, input byte i at bit i.
-SID_HD void transpose8(uint32_t& lo, uint32_t& hi) {
-    // a delta swap is two LOP3s: t = (x ^ (x >> s)) & m, then x ^ t ^ (t << s)
-    constexpr int XOR_AND = (TA ^ TB) & TC, XOR3 = TA ^ TB ^ TC, SELECT = (TA & TC) | (TB & ~TC);
-    uint32_t t;
-    t = lop3<XOR_AND>(lo, shr_fma<7>(lo), 0x00AA00AAu); lo = lop3<XOR3>(lo, t, t << 7);
-    t = lop3<XOR_AND>(hi, shr_fma<7>(hi), 0x00AA00AAu); hi = lop3<XOR3>(hi, t, t << 7);
-    t = lop3<XOR_AND>(lo, shr_fma<14>(lo), 0x0000CCCCu); lo = lop3<XOR3>(lo, t, t << 14);
-    t = lop3<XOR_AND>(hi, shr_fma<14>(hi), 0x0000CCCCu); hi = lop3<XOR3>(hi, t, t << 14);
-    const uint32_t nl = lop3<SELECT>(lo, hi << 4, 0x0F0F0F0Fu);        // low nibbles of lo, high nibbles from hi
-    const uint32_t nh = lop3<SELECT>(shr_fma<4>(lo), hi, 0x0F0F0F0Fu);
+// One step of an 8x8 bit-matrix transpose whose rows are eight words: rows lo and hi exchange the bit
+// blocks selected by M / S (two LOP3 selects, one shift each way).
+template <uint32_t M, int S>
+SID_HD void swap_blocks(uint32_t& lo, uint32_t& hi) {
+    constexpr int SELECT = (TA & TC) | (TB & ~TC);                     // c ? a : b, bit by bit
+    const uint32_t nl = lop3<SELECT>(lo, hi << S, M);
+    const uint32_t nh = lop3<SELECT>(shr_fma<S>(lo), hi, M);
     lo = nl;
     hi = nh;
 }
@@ -87,22 +82,28 @@ struct ClassWords {     // bit i of each word <-> byte i of the 32-byte unit
 
 // w[0..7]: the unit's 32 bytes as little-endian words.
 SID_HD ClassWords classify32(const uint32_t w[8]) {
-    uint32_t lo[4], hi[4];
+    // bytes: n[i] = text bytes (i, 8 + i, 16 + i, 24 + i), so that after the bit transpose across the eight
+    // words byte lane k of plane j holds bit j of bytes 8k .. 8k+7 in order
+    uint32_t n[8];
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {
-        lo[g] = w[2 * g];
-        hi[g] = w[2 * g + 1];
-        transpose8(lo[g], hi[g]);
+    for (int h = 0; h < 2; ++h) {
+        const uint32_t ab01 = byte_perm(w[h], w[2 + h], 0x5140u), ab23 = byte_perm(w[h], w[2 + h], 0x7362u);
+        const uint32_t cd01 = byte_perm(w[4 + h], w[6 + h], 0x5140u), cd23 = byte_perm(w[4 + h], w[6 + h], 0x7362u);
+        n[4 * h + 0] = byte_perm(ab01, cd01, 0x5410u);
+        n[4 * h + 1] = byte_perm(ab01, cd01, 0x7632u);
+        n[4 * h + 2] = byte_perm(ab23, cd23, 0x5410u);
+        n[4 * h + 3] = byte_perm(ab23, cd23, 0x7632u);
     }
-    // gather plane j: byte j of the four groups
-    const uint32_t t01 = byte_perm(lo[0], lo[1], 0x5140u), t23 = byte_perm(lo[2], lo[3], 0x5140u);
-    const uint32_t u01 = byte_perm(lo[0], lo[1], 0x7362u), u23 = byte_perm(lo[2], lo[3], 0x7362u);
-    const uint32_t v01 = byte_perm(hi[0], hi[1], 0x5140u), v23 = byte_perm(hi[2], hi[3], 0x5140u);
-    const uint32_t x01 = byte_perm(hi[0], hi[1], 0x7362u), x23 = byte_perm(hi[2], hi[3], 0x7362u);
-    const uint32_t p0 = byte_perm(t01, t23, 0x5410u), p1 = byte_perm(t01, t23, 0x7632u);
-    const uint32_t p2 = byte_perm(u01, u23, 0x5410u), p3 = byte_perm(u01, u23, 0x7632u);
-    const uint32_t p4 = byte_perm(v01, v23, 0x5410u), p5 = byte_perm(v01, v23, 0x7632u);
-    const uint32_t p6 = byte_perm(x01, x23, 0x5410u), p7 = byte_perm(x01, x23, 0x7632u);
+    // bits: 8x8 transpose (rows = words, columns = bit in byte), all four byte lanes at once
+#pragma unroll
+    for (int i = 0; i < 4; ++i) swap_blocks<0x0F0F0F0Fu, 4>(n[i], n[i + 4]);
+    swap_blocks<0x33333333u, 2>(n[0], n[2]);
+    swap_blocks<0x33333333u, 2>(n[1], n[3]);
+    swap_blocks<0x33333333u, 2>(n[4], n[6]);
+    swap_blocks<0x33333333u, 2>(n[5], n[7]);
+#pragma unroll
+    for (int i = 0; i < 8; i += 2) swap_blocks<0x55555555u, 1>(n[i], n[i + 1]);
+    const uint32_t p0 = n[0], p1 = n[1], p2 = n[2], p3 = n[3], p4 = n[4], p5 = n[5], p6 = n[6], p7 = n[7];
     ClassWords k;
     k.high = p7;
     // high nibbles (p7 p6 p5 p4)
