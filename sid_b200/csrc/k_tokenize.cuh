@@ -446,7 +446,7 @@ __global__ void __launch_bounds__(TOK_THREADS) k_tokenize(const TokParams p) {
 
 // ---- block table -> order[]: order[first_file_index + f] = storage index of the f-th line of the range.
 constexpr int BLK_THREADS = 256;
-constexpr int BLK_PER_THREAD = 8;
+constexpr int BLK_PER_THREAD = 2;
 constexpr int BLK_CHUNK = BLK_THREADS * BLK_PER_THREAD;
 
 __global__ void __launch_bounds__(BLK_THREADS) k_blk_sums(const unsigned long long* blk, uint32_t n_blocks, unsigned long long* part) {

@@ -16,6 +16,7 @@ def sass_lines(lib, kernel):
     cub = [f for f in os.listdir(d) if f.endswith(".cubin")][0]
     dis = subprocess.run(["nvdisasm", "-gi", "-c", os.path.join(d, cub)], stdout=subprocess.PIPE, text=True).stdout.splitlines()
     out, inside, cur = [], False, ("?", 0)
+    in_run = False          # inside a run of consecutive "//##" lines (one per inlining level, innermost first)
     for ln in dis:
         if ln.startswith("\t.section\t.text."):
             inside = kernel in ln
@@ -24,13 +25,14 @@ def sass_lines(lib, kernel):
             continue
         m = re.search(r'//## File "([^"]+)", line (\d+)(?: inlined at "([^"]+)", line (\d+))?', ln)
         if m:
-            if OUTER and m.group(3):
-                # attribute to the call site: walk to the outermost frame (nvdisasm prints one level per line,
-                # innermost first; the next "//##" lines continue the chain)
-                cur = (os.path.basename(m.group(3)), int(m.group(4)))
-            elif not (OUTER and ln.lstrip().startswith("//## File") and "inlined at" not in ln and False):
-                cur = (os.path.basename(m.group(1)), int(m.group(2)))
+            if OUTER:
+                # attribute to the call site: the last line of the run names the outermost frame
+                cur = (os.path.basename(m.group(3)), int(m.group(4))) if m.group(3) else (os.path.basename(m.group(1)), int(m.group(2)))
+            elif not in_run:
+                cur = (os.path.basename(m.group(1)), int(m.group(2)))        # innermost frame
+            in_run = True
             continue
+        in_run = False
         m = re.match(r"\s+/\*([0-9a-f]{4,})\*/\s+(.*?);", ln)
         if m:
             out.append((int(m.group(1), 16), m.group(2).strip(), cur))
