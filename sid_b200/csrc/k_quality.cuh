@@ -22,6 +22,7 @@ struct QualityParams {
     const uint8_t* text;
     uint64_t text_len;
     const uint64_t* line_off;
+    const uint64_t* profile;    // per site, as stored by the tokenizer
     const uint32_t* order;      // file index -> storage index
     uint64_t site_begin, n_sites;
     const double* lut;          // [0,256) log(1-e)  [256,512) log(e)  [512,768) log(1-2e/3)  [768,1024) log(2e/3)
@@ -84,7 +85,7 @@ __global__ void __launch_bounds__(QUAL_THREADS) k_quality(const QualityParams p)
     const uint64_t line_abs = p.line_off[site];
     FlatSrc src {p.text, p.text_len};
     ParsedLine pl;
-    parse_line(src, line_abs, true, pl);
+    quality_fields(src, line_abs, p.profile[site], pl);      // offsets, lengths and status of parse_line; the profile is known
     char* dst = p.site_suffix + site * SUFFIX_BYTES;
     if (pl.status != LINE_OK) {
         atomicMin(p.error, (unsigned long long)((line_abs << 3) | (uint64_t)pl.status));

@@ -171,4 +171,60 @@ SID_HD void parse_line(const Src& src, uint64_t p, bool want_qual, ParsedLine& o
     o.status = (o.n_bases > o.bq_len || o.n_bases > o.mq_len) ? LINE_QUAL_SHORT : LINE_OK;
 }
 
+// The fields of a line whose profile is already known (the tokenizer stored it): the same offsets,
+// lengths and status as parse_line(..., want_qual = true), without counting the bases again.  Only
+// for lines whose bases field is shorter than 65536 bytes (no 16-bit count can have wrapped, so the
+// number of counted bases is the sum of the profile); longer ones go through parse_line.
+template <class Src>
+SID_HD void quality_fields(const Src& src, uint64_t p, uint64_t profile, ParsedLine& o) {
+    o.status = LINE_MALFORMED;
+    o.pos = -1;
+    o.profile = profile;
+    o.n_bases = 0;
+    o.ref = 'N';
+    o.chrom_off = o.chrom_len = 0;
+    o.bases_off = o.bases_len = o.bq_off = o.bq_len = o.mq_off = o.mq_len = 0;
+    uint64_t q = p;
+    uint8_t c = src.at(q);
+    // tokens 0 and 1: chromosome name, position
+    for (int t = 0; t < 2; ++t) {
+        while (is_delim(c)) c = src.at(++q);
+        if (is_eol(c)) return;
+        if (t == 0) o.chrom_off = (uint32_t)(q - p);
+        while (!is_delim(c) && !is_eol(c)) c = src.at(++q);
+        if (t == 0) o.chrom_len = (uint32_t)(q - p) - o.chrom_off;
+    }
+    // token 2: reference base, exactly one character
+    while (is_delim(c)) c = src.at(++q);
+    if (is_eol(c)) return;
+    o.ref = (char)c;
+    c = src.at(++q);
+    if (!is_delim(c) && !is_eol(c)) return;
+    // token 3: coverage
+    while (is_delim(c)) c = src.at(++q);
+    if (is_eol(c)) return;
+    while (!is_delim(c) && !is_eol(c)) c = src.at(++q);
+    // token 4: read bases
+    while (is_delim(c)) c = src.at(++q);
+    if (is_eol(c)) return;
+    o.bases_off = (uint32_t)(q - p);
+    while (!is_delim(c) && !is_eol(c)) c = src.at(++q);
+    o.bases_len = (uint32_t)(q - p) - o.bases_off;
+    if (o.bases_len >= 65536u) { parse_line(src, p, true, o); return; }
+    o.n_bases = profile_count(profile, 0) + profile_count(profile, 1) + profile_count(profile, 2) + profile_count(profile, 3);
+    // token 5: base qualities
+    while (is_delim(c)) c = src.at(++q);
+    if (is_eol(c)) return;
+    o.bq_off = (uint32_t)(q - p);
+    while (!is_delim(c) && !is_eol(c)) c = src.at(++q);
+    o.bq_len = (uint32_t)(q - p) - o.bq_off;
+    // token 6: mapping qualities
+    while (is_delim(c)) c = src.at(++q);
+    if (is_eol(c)) { o.status = LINE_MISSING_MAPQ; return; }
+    o.mq_off = (uint32_t)(q - p);
+    while (!is_delim(c) && !is_eol(c)) c = src.at(++q);
+    o.mq_len = (uint32_t)(q - p) - o.mq_off;
+    o.status = (o.n_bases > o.bq_len || o.n_bases > o.mq_len) ? LINE_QUAL_SHORT : LINE_OK;
+}
+
 }  // namespace sid

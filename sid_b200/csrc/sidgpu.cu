@@ -679,6 +679,7 @@ int quality_rows(sidgpu_ctx* ctx, uint64_t site_begin, uint64_t n) {
     q.text = (const uint8_t*)ctx->last_text;
     q.text_len = ctx->last_text_len;
     q.line_off = (const uint64_t*)ctx->line_off.p;
+    q.profile = (const uint64_t*)ctx->profile.p;
     q.order = (const uint32_t*)ctx->order.p;
     q.site_begin = site_begin;
     q.n_sites = n;
@@ -931,7 +932,7 @@ int sidgpu_begin(sidgpu_ctx* ctx, const sidgpu_params* params) {
     ctx->params = *params;
     ctx->streaming = method_streams(*params);
     ctx->counting = !ctx->streaming;
-    ctx->want_profile = false;
+    ctx->want_profile = params->method == SIDGPU_METHOD_QUALITY;      // k_quality takes the counts from the tokenizer
     ctx->want_line_off = params->method == SIDGPU_METHOD_QUALITY;
     ctx->want_site_suffix = params->method == SIDGPU_METHOD_QUALITY;
     ctx->session_prior = params->prior;

@@ -37,6 +37,25 @@ void hc_parse_line(const uint8_t* text, uint64_t len, uint64_t p, int want_qual,
     fill(pl, out);
 }
 
+// quality_fields (the field scan k_quality uses once the tokenizer has stored the profile) against
+// parse_line(want_qual) on every line of a text.  Returns the number of lines, or -(k+1) when line k differs.
+int64_t hc_compare_quality_fields(const uint8_t* text, uint64_t len) {
+    FlatSrc src {text, len};
+    int64_t k = 0;
+    for (uint64_t p = 0; p < len; ++p) {
+        if (text[p] == '\n' || (p > 0 && text[p - 1] != '\n')) continue;
+        ParsedLine a, b;
+        parse_line(src, p, true, a);
+        quality_fields(src, p, a.profile, b);
+        const bool same = a.status == b.status && a.ref == b.ref && a.chrom_off == b.chrom_off && a.chrom_len == b.chrom_len &&
+                          a.bases_off == b.bases_off && a.bases_len == b.bases_len && a.bq_off == b.bq_off && a.bq_len == b.bq_len &&
+                          a.mq_off == b.mq_off && a.mq_len == b.mq_len && (a.status == LINE_MALFORMED || a.n_bases == b.n_bases);
+        if (!same) return -(k + 1);
+        ++k;
+    }
+    return k;
+}
+
 #ifdef SID_HAVE_FAST
 // The SWAR tokenizer the kernel uses.  Returns 1 when the fast grammar accepted the line.
 int hc_parse_line_fast(const uint8_t* text, uint64_t len, uint64_t p, hc_line* out) {

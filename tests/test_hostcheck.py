@@ -243,3 +243,22 @@ def test_bit_tokenizer_covers_normal_text(native, name):
     assert k > 0
     if name != "edge.plp":
         assert nf.value == k
+
+
+@pytest.mark.parametrize("name", ["quality30.plp", "edge_quality.plp", "depth30.plp", "depth500.plp", "edge.plp"])
+def test_quality_fields_equal_parse_line(native, name):
+    """The lean field scan of the quality kernel returns parse_line's offsets, lengths and status."""
+    hc = op.hostcheck()
+    hc.hc_compare_quality_fields.restype = ctypes.c_int64
+    text = read(name)
+    k = hc.hc_compare_quality_fields(text, len(text))
+    assert k > 0, text.split(b"\n")[-k - 1][:200] if k < 0 else None
+
+
+@pytest.mark.parametrize("seed", [4, 5])
+def test_quality_fields_on_adversarial_lines(native, seed):
+    hc = op.hostcheck()
+    hc.hc_compare_quality_fields.restype = ctypes.c_int64
+    text = _adversarial_text(seed, 20000)
+    k = hc.hc_compare_quality_fields(text, len(text))
+    assert k > 0, text.split(b"\n")[-k - 1][:200] if k < 0 else None
