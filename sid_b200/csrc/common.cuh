@@ -65,6 +65,14 @@ SID_HD int clz64(uint64_t x) {
 #endif
 }
 
+SID_HD int ctz64(uint64_t x) {              // x != 0
+#if defined(__CUDA_ARCH__)
+    return __ffsll((long long)x) - 1;
+#else
+    return __builtin_ctzll(x);
+#endif
+}
+
 SID_HD uint64_t mix64(uint64_t k) {
     k ^= k >> 33;
     k *= 0xFF51AFD7ED558CCDull;

@@ -25,7 +25,7 @@ struct QualityParams {
     const uint64_t* profile;    // per site, as stored by the tokenizer
     const uint32_t* order;      // file index -> storage index
     uint64_t site_begin, n_sites;
-    const double* lut;          // [0,256) log(1-e)  [256,512) log(e)  [512,768) log(1-2e/3)  [768,1024) log(2e/3)
+    const double* lut;          // [0,256) log(1-e)  [256,512) log(e)  [512,768) log(1-2e/3)  [768,1024) log(2e/3)  [1024,1280) lgamma(n+1)
     double prior, alpha;
     int het_only;               // rows of hom sites get length 0
     char* site_suffix;          // SUFFIX_BYTES per site
@@ -37,32 +37,73 @@ SID_HD uint32_t phred_of(uint8_t c) {                    // parseQualities pileu
     return q < 1 ? 1u : q;
 }
 
-template <class Src>
-SID_HD CallResult call_quality(const Src& src, uint64_t line_abs, const ParsedLine& pl, const double* lut, double prior,
+// The bases field walked once more for the order of the counted bases (parseReadBases pileup.cpp:70-153
+// without the counters): 0..3 = A C G T, 4 = '.' or ',', -1 = nothing counted.
+struct BasesWalk {
+    uint64_t skip, num;
+    int mode;                // 0 normal, 1 just saw '+'/'-', 2 reading the indel length
+    SID_HD void init() { skip = 0; num = 0; mode = 0; }
+    SID_HD int feed(uint8_t c) {
+        if (mode) {
+            const uint32_t d = (uint32_t)c - (uint32_t)'0';
+            if (d <= 9) {
+                if (mode == 1) { mode = 2; num = d; } else if (num < (1ull << 40)) num = num * 10 + d;
+                return -1;
+            }
+            if (mode == 2) skip = num;          // pileup.cpp:144
+            mode = 0;                           // pileup.cpp:131-133: a sign without digits is ignored
+        }
+        if (skip) { --skip; return -1; }
+        switch (c) {
+            case 'A': case 'a': return 0;
+            case 'C': case 'c': return 1;
+            case 'G': case 'g': return 2;
+            case 'T': case 't': return 3;
+            case '.': case ',': return 4;
+            case '^': skip = 1; return -1;
+            case '+': case '-': mode = 1; return -1;
+            default: return -1;
+        }
+    }
+};
+
+constexpr int LOG_FACT_N = 256;   // lut[1024 + n] = lgamma(n + 1) for n < LOG_FACT_N
+SID_HD double log_factorial(const double* lut, uint32_t n) { return n < (uint32_t)LOG_FACT_N ? lut[1024 + n] : lgamma((double)n + 1.0); }
+
+// `text` holds the whole line: every index below was validated by quality_fields (bq_len, mq_len >= counted bases).
+SID_HD CallResult call_quality(const uint8_t* text, uint64_t line_abs, const ParsedLine& pl, const double* lut, double prior,
                                double alpha) {
     int ref0, ref1;
     major_alleles(pl.profile, ref0, ref1);                // call.cpp:311-319
     const int ri = ref_index((uint8_t)pl.ref);
+    // sums of per-read terms: eight plain additions at a time, the blocks added with compensation (in place of
+    // the reference's x87 long double accumulation)
     CompSum lh, lt;
     lh.init();
     lt.init();
-    BasesState b;
+    double bh = 0, bt = 0;
+    BasesWalk b;
     b.init();
     uint32_t j = 0;
-    const uint64_t bases = line_abs + pl.bases_off, bq = line_abs + pl.bq_off, mq = line_abs + pl.mq_off;
+    const uint8_t* bases = text + line_abs + pl.bases_off;
+    const uint8_t* bq = text + line_abs + pl.bq_off;
+    const uint8_t* mq = text + line_abs + pl.mq_off;
     for (uint32_t i = 0; i < pl.bases_len; ++i) {
-        int r = b.feed(src.at(bases + i));
-        if (r >= 4) r = ri;                               // '.' / ',' stand for the reference base
+        int r = b.feed(bases[i]);
+        if (r == 4) r = ri;                               // '.' / ',' stand for the reference base
         if (r < 0) continue;
-        const uint32_t q1 = phred_of(src.at(bq + j)), q2 = phred_of(src.at(mq + j));
+        const uint32_t q1 = phred_of(bq[j]), q2 = phred_of(mq[j]);
         const uint32_t q = q1 < q2 ? q1 : q2;             // call.cpp:330
         ++j;
-        lh.add(r == ref0 ? lut[q] : lut[256 + q]);        // call.cpp:331-335
-        lt.add((r == ref0 || r == ref1) ? lut[512 + q] : lut[768 + q]);   // call.cpp:336-340
+        bh += r == ref0 ? lut[q] : lut[256 + q];          // call.cpp:331-335
+        bt += (r == ref0 || r == ref1) ? lut[512 + q] : lut[768 + q];   // call.cpp:336-340
+        if ((j & 7u) == 0) { lh.add(bh); lt.add(bt); bh = bt = 0; }
     }
+    lh.add(bh);
+    lt.add(bt);
     const uint32_t n = profile_count(pl.profile, ref0) + profile_count(pl.profile, ref1);   // call.cpp:347-349
     const uint32_t k = profile_count(pl.profile, ref1);
-    lt.add(lgamma((double)n + 1.0) - lgamma((double)(n - k) + 1.0) - lgamma((double)k + 1.0));
+    lt.add(log_factorial(lut, n) - log_factorial(lut, n - k) - log_factorial(lut, k));
     lt.add(-(double)n * 0.69314718055994530942);
     double l1 = lh.value(), l2 = lt.value();
     if (l1 < LOG_LDBL_ZERO) l1 = neg_inf();               // call.cpp:352-353 exp() underflow
@@ -85,14 +126,14 @@ __global__ void __launch_bounds__(QUAL_THREADS) k_quality(const QualityParams p)
     const uint64_t line_abs = p.line_off[site];
     FlatSrc src {p.text, p.text_len};
     ParsedLine pl;
-    quality_fields(src, line_abs, p.profile[site], pl);      // offsets, lengths and status of parse_line; the profile is known
+    quality_fields(WordSrc {p.text, p.text_len}, line_abs, p.profile[site], pl);      // parse_line's offsets, lengths, status
     char* dst = p.site_suffix + site * SUFFIX_BYTES;
     if (pl.status != LINE_OK) {
         atomicMin(p.error, (unsigned long long)((line_abs << 3) | (uint64_t)pl.status));
         dst[SUFFIX_BYTES - 1] = 0;
         return;
     }
-    const CallResult r = call_quality(src, line_abs, pl, p.lut, p.prior, p.alpha);
+    const CallResult r = call_quality(p.text, line_abs, pl, p.lut, p.prior, p.alpha);
     char buf[SUFFIX_BYTES];
     const int n = (p.het_only && r.label != 1) ? 0 : format_suffix(r, false, buf);
     for (int k = 0; k < n; ++k) dst[k] = buf[k];

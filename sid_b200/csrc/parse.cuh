@@ -171,12 +171,49 @@ SID_HD void parse_line(const Src& src, uint64_t p, bool want_qual, ParsedLine& o
     o.status = (o.n_bases > o.bq_len || o.n_bases > o.mq_len) ? LINE_QUAL_SHORT : LINE_OK;
 }
 
+// Flat text with word access for the field scan below: base is 8-byte aligned, reads at or past
+// `limit` look like '\n'.
+struct WordSrc {
+    const uint8_t* base;
+    uint64_t limit;
+    SID_HD uint8_t at(uint64_t off) const { return off < limit ? base[off] : (uint8_t)'\n'; }
+    SID_HD uint64_t word(uint64_t k) const {                    // bytes 8k .. 8k+7, little endian
+        if (8 * k + 8 <= limit) return *reinterpret_cast<const uint64_t*>(base + 8 * k);
+        uint64_t w = 0;
+        for (int i = 0; i < 8; ++i) w |= (uint64_t)at(8 * k + i) << (8 * i);
+        return w;
+    }
+    // smallest q >= from whose byte is <= 0x20 (every delimiter and line end is); the text ends with one
+    SID_HD uint64_t next_low(uint64_t from) const {
+        uint64_t k = from >> 3;
+        uint64_t keep = ~0ull << (8 * (from & 7));              // bytes of the first word at or after `from`
+        for (;;) {
+            const uint64_t w = word(k);
+            // bit 7 of a byte of `ge` is set iff the byte is >= 0x21
+            const uint64_t ge = (((w & 0x7F7F7F7F7F7F7F7Full) + 0x5F5F5F5F5F5F5F5Full) | w) & 0x8080808080808080ull;
+            const uint64_t low = (ge ^ 0x8080808080808080ull) & keep;
+            if (low) return 8 * k + (uint64_t)(ctz64(low) >> 3);
+            keep = ~0ull;
+            ++k;
+        }
+    }
+    // end of the token that contains `q`: the first delimiter or line end at or after q
+    SID_HD uint64_t token_end(uint64_t q) const {
+        for (;;) {
+            q = next_low(q);
+            const uint8_t c = at(q);
+            if (is_delim(c) || is_eol(c)) return q;
+            ++q;                                                // a control byte inside the token
+        }
+    }
+};
+
 // The fields of a line whose profile is already known (the tokenizer stored it): the same offsets,
-// lengths and status as parse_line(..., want_qual = true), without counting the bases again.  Only
-// for lines whose bases field is shorter than 65536 bytes (no 16-bit count can have wrapped, so the
-// number of counted bases is the sum of the profile); longer ones go through parse_line.
-template <class Src>
-SID_HD void quality_fields(const Src& src, uint64_t p, uint64_t profile, ParsedLine& o) {
+// lengths and status as parse_line(..., want_qual = true), without counting the bases again and with
+// the token ends found eight bytes at a time.  Only for lines whose bases field is shorter than 65536
+// bytes (no 16-bit count can have wrapped, so the number of counted bases is the sum of the profile);
+// longer ones go through parse_line.
+SID_HD void quality_fields(const WordSrc& src, uint64_t p, uint64_t profile, ParsedLine& o) {
     o.status = LINE_MALFORMED;
     o.pos = -1;
     o.profile = profile;
@@ -191,7 +228,8 @@ SID_HD void quality_fields(const Src& src, uint64_t p, uint64_t profile, ParsedL
         while (is_delim(c)) c = src.at(++q);
         if (is_eol(c)) return;
         if (t == 0) o.chrom_off = (uint32_t)(q - p);
-        while (!is_delim(c) && !is_eol(c)) c = src.at(++q);
+        q = src.token_end(q);
+        c = src.at(q);
         if (t == 0) o.chrom_len = (uint32_t)(q - p) - o.chrom_off;
     }
     // token 2: reference base, exactly one character
@@ -203,12 +241,14 @@ SID_HD void quality_fields(const Src& src, uint64_t p, uint64_t profile, ParsedL
     // token 3: coverage
     while (is_delim(c)) c = src.at(++q);
     if (is_eol(c)) return;
-    while (!is_delim(c) && !is_eol(c)) c = src.at(++q);
+    q = src.token_end(q);
+    c = src.at(q);
     // token 4: read bases
     while (is_delim(c)) c = src.at(++q);
     if (is_eol(c)) return;
     o.bases_off = (uint32_t)(q - p);
-    while (!is_delim(c) && !is_eol(c)) c = src.at(++q);
+    q = src.token_end(q);
+    c = src.at(q);
     o.bases_len = (uint32_t)(q - p) - o.bases_off;
     if (o.bases_len >= 65536u) { parse_line(src, p, true, o); return; }
     o.n_bases = profile_count(profile, 0) + profile_count(profile, 1) + profile_count(profile, 2) + profile_count(profile, 3);
@@ -216,13 +256,14 @@ SID_HD void quality_fields(const Src& src, uint64_t p, uint64_t profile, ParsedL
     while (is_delim(c)) c = src.at(++q);
     if (is_eol(c)) return;
     o.bq_off = (uint32_t)(q - p);
-    while (!is_delim(c) && !is_eol(c)) c = src.at(++q);
+    q = src.token_end(q);
+    c = src.at(q);
     o.bq_len = (uint32_t)(q - p) - o.bq_off;
     // token 6: mapping qualities
     while (is_delim(c)) c = src.at(++q);
     if (is_eol(c)) { o.status = LINE_MISSING_MAPQ; return; }
     o.mq_off = (uint32_t)(q - p);
-    while (!is_delim(c) && !is_eol(c)) c = src.at(++q);
+    q = src.token_end(q);
     o.mq_len = (uint32_t)(q - p) - o.mq_off;
     o.status = (o.n_bases > o.bq_len || o.n_bases > o.mq_len) ? LINE_QUAL_SHORT : LINE_OK;
 }

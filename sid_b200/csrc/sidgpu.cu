@@ -764,7 +764,7 @@ int sidgpu_create(const sidgpu_config* cfg, sidgpu_ctx** out) {
     cudaMemcpyAsync(ctx->names.cursor, &four, sizeof four, cudaMemcpyHostToDevice, ctx->stream);
     // quality lookup tables: log(1-e), log(e), log(1-2e/3), log(2e/3) with e = 10^(-q/10) (call.cpp:330-341)
     {
-        std::vector<double> lut(4 * 256);
+        std::vector<double> lut(4 * 256 + LOG_FACT_N);
         for (int q = 0; q < 256; ++q) {
             const double error = pow(10., q / -10.);
             lut[q] = log(1 - error);
@@ -772,6 +772,7 @@ int sidgpu_create(const sidgpu_config* cfg, sidgpu_ctx** out) {
             lut[512 + q] = log(1 - 2. / 3. * error);
             lut[768 + q] = log(2. / 3. * error);
         }
+        for (int n = 0; n < LOG_FACT_N; ++n) lut[1024 + n] = lgamma((double)n + 1.0);     // log n! for the binomial of call.cpp:347-349
         rc = ensure(ctx, ctx->quality_lut, lut.size() * 8);
         if (rc != SIDGPU_OK) return bail(rc);
         cudaMemcpyAsync(ctx->quality_lut.p, lut.data(), lut.size() * 8, cudaMemcpyHostToDevice, ctx->stream);

@@ -8,6 +8,9 @@
 #include "../../sid_b200/csrc/calls.cuh"
 #include "../../sid_b200/csrc/fmt.cuh"
 #include "../../sid_b200/csrc/parse.cuh"
+#include "../../sid_b200/csrc/k_quality.cuh"
+#include <cmath>
+#include <vector>
 #ifdef SID_HAVE_FAST
 #include "../../sid_b200/csrc/parse_fast.cuh"
 #include "../../sid_b200/csrc/parse_bits.cuh"
@@ -46,11 +49,38 @@ int64_t hc_compare_quality_fields(const uint8_t* text, uint64_t len) {
         if (text[p] == '\n' || (p > 0 && text[p - 1] != '\n')) continue;
         ParsedLine a, b;
         parse_line(src, p, true, a);
-        quality_fields(src, p, a.profile, b);
+        quality_fields(WordSrc {text, len}, p, a.profile, b);
         const bool same = a.status == b.status && a.ref == b.ref && a.chrom_off == b.chrom_off && a.chrom_len == b.chrom_len &&
                           a.bases_off == b.bases_off && a.bases_len == b.bases_len && a.bq_off == b.bq_off && a.bq_len == b.bq_len &&
                           a.mq_off == b.mq_off && a.mq_len == b.mq_len && (a.status == LINE_MALFORMED || a.n_bases == b.n_bases);
         if (!same) return -(k + 1);
+        ++k;
+    }
+    return k;
+}
+
+// call_quality exactly as k_quality runs it (field scan with the profile given, then the per-read sums)
+// over every line of a 7-column text.  Returns the number of lines, or -(k+1) when line k is not LINE_OK.
+int64_t hc_call_quality(const uint8_t* text, uint64_t len, double prior, double alpha, int32_t* label, char* gt, double* hom, double* het) {
+    std::vector<double> lut(4 * 256 + LOG_FACT_N);
+    for (int n = 0; n < LOG_FACT_N; ++n) lut[1024 + n] = lgamma((double)n + 1.0);
+    for (int q = 0; q < 256; ++q) {                       // same expressions as sidgpu_create (call.cpp:330-341)
+        const double error = pow(10., q / -10.);
+        lut[q] = log(1 - error);
+        lut[256 + q] = log(error);
+        lut[512 + q] = log(1 - 2. / 3. * error);
+        lut[768 + q] = log(2. / 3. * error);
+    }
+    FlatSrc src {text, len};
+    int64_t k = 0;
+    for (uint64_t p = 0; p < len; ++p) {
+        if (text[p] == '\n' || (p > 0 && text[p - 1] != '\n')) continue;
+        ParsedLine full, pl;
+        parse_line(src, p, true, full);
+        quality_fields(WordSrc {text, len}, p, full.profile, pl);
+        if (pl.status != LINE_OK) return -(k + 1);
+        const CallResult r = call_quality(text, p, pl, lut.data(), prior, alpha);
+        label[k] = r.label; gt[2 * k] = r.gt0; gt[2 * k + 1] = r.gt1; hom[k] = r.hom; het[k] = r.het;
         ++k;
     }
     return k;

@@ -262,3 +262,36 @@ def test_quality_fields_on_adversarial_lines(native, seed):
     text = _adversarial_text(seed, 20000)
     k = hc.hc_compare_quality_fields(text, len(text))
     assert k > 0, text.split(b"\n")[-k - 1][:200] if k < 0 else None
+
+
+def _quality_case(text, prior=-1.0, alpha=0.05):
+    hc = op.hostcheck()
+    hc.hc_call_quality.restype = ctypes.c_int64
+    hc.hc_call_quality.argtypes = [ctypes.c_char_p, ctypes.c_uint64, ctypes.c_double, ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p,
+                                   ctypes.c_void_p, ctypes.c_void_p]
+    want = op.oracle_call(text, "quality", prior=prior, alpha=alpha)
+    n = want["n"]
+    label = np.zeros(n + 1, dtype=np.int32)
+    gt = np.zeros((n + 1, 2), dtype=np.uint8)
+    hom = np.zeros(n + 1)
+    het = np.zeros(n + 1)
+    k = hc.hc_call_quality(text, len(text), prior, alpha, label.ctypes.data, gt.ctypes.data, hom.ctypes.data, het.ctypes.data)
+    assert k == n
+    assert np.array_equal(label[:n], want["label"]) and np.array_equal(gt[:n], want["gt"])
+    for a, b in ((hom[:n], want["hom"]), (het[:n], want["het"])):
+        for x, y in zip(a, b):
+            assert op.conf_close(x, y), (x, y)
+
+
+@pytest.mark.parametrize("name,prior", [("quality30.plp", -1.0), ("quality30.plp", 0.001), ("edge_quality.plp", -1.0)])
+def test_quality_call_matches_oracle(native, name, prior):
+    """The per-site arithmetic of k_quality (SID_HD call_quality) against the oracle: labels and genotypes
+    exact, confidences within REL_TOL."""
+    _quality_case(read(name), prior)
+
+
+def test_quality_call_matches_oracle_on_deep_pileups(native):
+    """2000x coverage: thousands of per-read terms per sum."""
+    from sid_b200 import synth
+    text = synth.generate(300, seed=7, lam=2000.0, het=0.02, err=0.02, start=0.05, indel=0.01, seven_columns=True)
+    _quality_case(bytes(text))
