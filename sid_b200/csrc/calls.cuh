@@ -201,9 +201,10 @@ SID_HD int format_suffix(const CallResult& r, bool probability, char* out) {
 struct CompSum {
     double s, c;
     SID_HD void init() { s = 0; c = 0; }
-    SID_HD void add(double x) {
+    SID_HD void add(double x) {               // Knuth's branch-free two-sum: t + e == s + x exactly
         const double t = s + x;
-        if (fabs(s) >= fabs(x)) c += (s - t) + x; else c += (x - t) + s;
+        const double z = t - s;
+        c += (s - (t - z)) + (x - z);
         s = t;
     }
     SID_HD double value() const { return s + c; }

@@ -54,16 +54,17 @@ struct BasesWalk {
             mode = 0;                           // pileup.cpp:131-133: a sign without digits is ignored
         }
         if (skip) { --skip; return -1; }
-        switch (c) {
-            case 'A': case 'a': return 0;
-            case 'C': case 'c': return 1;
-            case 'G': case 'g': return 2;
-            case 'T': case 't': return 3;
-            case '.': case ',': return 4;
-            case '^': skip = 1; return -1;
-            case '+': case '-': mode = 1; return -1;
-            default: return -1;
-        }
+        // no switch: the lanes of a warp look at different characters, selects keep them together
+        const uint32_t u = (uint32_t)c | 0x20u;                       // letters to lower case; '.' ',' '+' '-' unchanged
+        int r = -1;
+        r = u == 'a' ? 0 : r;
+        r = u == 'c' ? 1 : r;
+        r = u == 'g' ? 2 : r;
+        r = u == 't' ? 3 : r;
+        r = (c == '.' || c == ',') ? 4 : r;
+        skip = c == '^' ? 1 : 0;                                      // pileup.cpp:125-127 (skip was 0 here)
+        mode = (c == '+' || c == '-') ? 1 : 0;                        // (mode was 0 here)
+        return r;
     }
 };
 
