@@ -129,6 +129,22 @@ def test_csv_many_small_chunks(native, tiny_chunk_ctx, case):
     assert diffs <= max(2, n // 1000)
 
 
+@pytest.mark.parametrize("lam,n_sites", [(3000.0, 120), (20000.0, 24), (70000.0, 6)])
+@pytest.mark.parametrize("method", ["local", "quality"])
+def test_very_deep_pileups(native, gpu_ctx, lam, n_sites, method):
+    """Lines longer than a tokenizer slice (7 kB), than a whole tile (47 kB) and with 16-bit count wrap
+    (depth 70,000): same rows as the oracle."""
+    import sid_b200
+    from sid_b200 import synth
+    text = bytes(synth.generate(n_sites, seed=11, lam=lam, het=0.05, err=0.02, start=0.02, indel=0.005, seven_columns=True))
+    want = op.oracle_call(text, method)
+    rows, n, n_rows = gpu_ctx.call_host(text, sid_b200.Context.make_params(method))
+    assert n == n_sites
+    k, diffs = op.compare_csv(sid_b200.CSV_HEADER + rows, want["csv"])
+    assert k == n_rows == n_sites
+    assert diffs <= 2
+
+
 def test_emit_sub_ranges_concatenate(native, gpu_ctx):
     """sidgpu_emit_csv over odd-sized pieces of the store == one call over all of it (file order through order[])."""
     import sid_b200
