@@ -147,6 +147,23 @@ int sidgpu_emit_csv(sidgpu_ctx* ctx, uint64_t site_begin, uint64_t n_sites, char
 int sidgpu_emit_records(sidgpu_ctx* ctx, uint64_t site_begin, uint64_t n_sites, uint8_t* d_label,
                         char* d_gt, double* d_hom_conf, double* d_het_conf);
 
+/* The same per-site results as columns, with the position and the chromosome name of every site: the
+ * columnar form downstream consumers read (scripts/nonsynonymous.py:10-12,36 re-parses the CSV into
+ * exactly these fields).  Any pointer may be NULL; arrays of n_sites elements (d_gt: 2 per site), file
+ * order.  d_name_ref[i] is the byte offset of a record (uint16 length, then the bytes) in the names
+ * pool that sidgpu_names returns.  Not for `quality` sessions (their results exist as text only). */
+typedef struct {
+    int32_t* d_pos;
+    uint32_t* d_name_ref;
+    uint8_t* d_label;
+    char* d_gt;
+    double* d_hom_conf;
+    double* d_het_conf;
+} sidgpu_columns;
+int sidgpu_emit_columns(sidgpu_ctx* ctx, uint64_t site_begin, uint64_t n_sites, const sidgpu_columns* cols);
+/* The chromosome-name pool of the ctx (device memory, valid until the ctx is destroyed or grown). */
+int sidgpu_names(sidgpu_ctx* ctx, const char** d_names, uint64_t* names_bytes);
+
 /* One-call host-buffer path (what the `sid` binary and the call.hpp wrappers use): chunked,
  * double-buffered pinned H2D of `h_text`, the session above on the device, D2H of the CSV.
  * h_csv receives the rows (no header); *csv_bytes the size.  Returns SIDGPU_ECAPACITY (with the

@@ -24,6 +24,11 @@ class Params(ctypes.Structure):
                 ("fit_nd", ctypes.c_double * 4), ("het_only", ctypes.c_int)]
 
 
+class Columns(ctypes.Structure):
+    _fields_ = [("d_pos", ctypes.c_void_p), ("d_name_ref", ctypes.c_void_p), ("d_label", ctypes.c_void_p), ("d_gt", ctypes.c_void_p),
+                ("d_hom_conf", ctypes.c_void_p), ("d_het_conf", ctypes.c_void_p)]
+
+
 class SitesView(ctypes.Structure):
     _fields_ = [("n_sites", c_u64), ("d_profile", ctypes.c_void_p), ("d_pos", ctypes.c_void_p),
                 ("d_slot", ctypes.c_void_p), ("d_line_off", ctypes.c_void_p), ("d_name_ref", ctypes.c_void_p),
@@ -60,6 +65,8 @@ PROTOTYPES = {
                                    ctypes.c_size_t, c_u64_p]),
     "sidgpu_finish": (ctypes.c_int, [ctypes.c_void_p]),
     "sidgpu_emit_csv": (ctypes.c_int, [ctypes.c_void_p, c_u64, c_u64, ctypes.c_void_p, ctypes.c_size_t, c_u64_p, c_u64_p]),
+    "sidgpu_emit_columns": (ctypes.c_int, [ctypes.c_void_p, c_u64, c_u64, ctypes.POINTER(Columns)]),
+    "sidgpu_names": (ctypes.c_int, [ctypes.c_void_p, c_void_pp, ctypes.POINTER(c_u64)]),
     "sidgpu_emit_records": (ctypes.c_int, [ctypes.c_void_p, c_u64, c_u64, ctypes.c_void_p, ctypes.c_void_p,
                                            ctypes.c_void_p, ctypes.c_void_p]),
     "sidgpu_call_host": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(Params), ctypes.c_void_p, ctypes.c_size_t,

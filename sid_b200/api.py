@@ -11,7 +11,7 @@ import ctypes
 import numpy as np
 
 from . import _lib
-from ._lib import Config, Fit, Params, SitesView, UniqueView
+from ._lib import Columns, Config, Fit, Params, SitesView, UniqueView
 
 METHODS = {"local": 0, "bayes": 1, "likelihood_ratio": 2, "quality": 3}
 CSV_HEADER = b"chrom,pos,label,gt,hom_conf,het_conf,conf_type\n"      # sid.cpp:102
@@ -192,6 +192,41 @@ class Context:
         ptr = d_out.ptr if isinstance(d_out, DeviceBuffer) else d_out
         self._ck(self.lib.sidgpu_emit_csv(self.h, site_begin, n_sites, ptr, out_cap, ctypes.byref(b), ctypes.byref(r)))
         return b.value, r.value
+
+    def emit_columns(self, site_begin, n_sites, keep_dropped=False):
+        """sidgpu_emit_columns: the rows of the session as columns (numpy arrays) instead of CSV text.
+        'chrom' is dictionary encoded: chrom_codes index into chrom_names.  Sites the method drops
+        (coverage < 4 for bayes / likelihood_ratio, label 255) are filtered unless keep_dropped."""
+        n = int(n_sites)
+        bufs = {"pos": DeviceBuffer(self, max(4 * n, 4)), "name_ref": DeviceBuffer(self, max(4 * n, 4)), "label": DeviceBuffer(self, max(n, 1)),
+                "gt": DeviceBuffer(self, max(2 * n, 2)), "hom": DeviceBuffer(self, max(8 * n, 8)), "het": DeviceBuffer(self, max(8 * n, 8))}
+        try:
+            cols = Columns(bufs["pos"].ptr, bufs["name_ref"].ptr, bufs["label"].ptr, bufs["gt"].ptr, bufs["hom"].ptr, bufs["het"].ptr)
+            self._ck(self.lib.sidgpu_emit_columns(self.h, site_begin, n, ctypes.byref(cols)))
+            pos = bufs["pos"].download(np.int32, n)
+            refs = bufs["name_ref"].download(np.uint32, n)
+            label = bufs["label"].download(np.uint8, n)
+            gt = bufs["gt"].download(np.uint8, 2 * n).reshape(-1, 2)
+            hom = bufs["hom"].download(np.float64, n)
+            het = bufs["het"].download(np.float64, n)
+        finally:
+            for b in bufs.values():
+                b.free()
+        d_names, nbytes = ctypes.c_void_p(), ctypes.c_uint64()
+        self._ck(self.lib.sidgpu_names(self.h, ctypes.byref(d_names), ctypes.byref(nbytes)))
+        pool = self._download(d_names.value, np.uint8, nbytes.value).tobytes()
+        uniq, codes = np.unique(refs, return_inverse=True)
+        names = []
+        for r in uniq:
+            r = int(r)
+            ln = pool[r] | (pool[r + 1] << 8)
+            names.append(pool[r + 2:r + 2 + ln].decode("latin-1"))
+        out = {"chrom_codes": codes.astype(np.int32), "chrom_names": names, "pos": pos, "label": label, "gt": gt, "hom_conf": hom, "het_conf": het}
+        if not keep_dropped:
+            keep = label != 255
+            for k in ("chrom_codes", "pos", "label", "gt", "hom_conf", "het_conf"):
+                out[k] = out[k][keep]
+        return out
 
     def emit_records(self, site_begin, n_sites):
         lab = DeviceBuffer(self, max(n_sites, 1))
@@ -374,3 +409,33 @@ def sid_csv(text, method="local", estimate_prior=False, prior=-1.0, error_thresh
     rows, _, _ = ctx.call_host(text, Context.make_params(method, estimate_prior, prior, error_threshold, significance_level,
                                                          het_only=het_only))
     return rows if het_only else CSV_HEADER + rows
+
+
+def call_columns(text, method="local", estimate_prior=False, prior=-1.0, error_threshold=0.1, significance_level=0.05, ctx=None, fit=None):
+    """The rows `sid -m METHOD` prints, as columns: a dict of numpy arrays (see Context.emit_columns).
+    `local`, `bayes`, `likelihood_ratio`; the text is fed from device memory in one piece."""
+    ctx = ctx or default_context()
+    d = ctx.upload_text(text)
+    try:
+        ctx.begin(Context.make_params(method, estimate_prior, prior, error_threshold, significance_level, fit=fit))
+        n = ctx.feed(d, d.text_len)
+        if not ctx_streams(method, estimate_prior):
+            ctx.finish()
+        return ctx.emit_columns(0, n)
+    finally:
+        d.free()
+
+
+def ctx_streams(method, estimate_prior):
+    """Sessions that emit rows feed by feed (no genome-wide fit first)."""
+    return method in ("local", "quality") and not estimate_prior
+
+
+def columns_to_arrow(cols):
+    """pyarrow.Table of the columns: chrom (dictionary), pos, label ('hom'/'het'), gt, hom_conf, het_conf."""
+    import pyarrow as pa
+    gt = [bytes(g).decode("latin-1") for g in cols["gt"]]
+    chrom = pa.DictionaryArray.from_arrays(pa.array(cols["chrom_codes"], type=pa.int32()), pa.array(cols["chrom_names"], type=pa.string()))
+    label = pa.DictionaryArray.from_arrays(pa.array(cols["label"].astype(np.int8)), pa.array(["hom", "het"]))
+    return pa.table({"chrom": chrom, "pos": pa.array(cols["pos"]), "label": label, "gt": pa.array(gt), "hom_conf": pa.array(cols["hom_conf"]),
+                     "het_conf": pa.array(cols["het_conf"])})

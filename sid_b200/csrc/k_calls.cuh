@@ -262,12 +262,19 @@ struct RecordParams {
     char* gt;
     double* hom;
     double* het;
+    const int32_t* pos_in;          // columns of the site store, copied out in file order when asked for
+    const uint32_t* name_ref_in;
+    int32_t* pos;
+    uint32_t* name_ref;
 };
 
 __global__ void k_records(const RecordParams p) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= p.n_sites) return;
-    const uint32_t s = p.slot[p.order[p.site_begin + i]];
+    const uint32_t site = p.order[p.site_begin + i];
+    const uint32_t s = p.slot[site];
+    if (p.pos) p.pos[i] = p.pos_in[site];
+    if (p.name_ref) p.name_ref[i] = p.name_ref_in[site];
     if (p.label) p.label[i] = p.table.label[s];
     if (p.gt) { p.gt[2 * i] = p.table.gt[2 * s]; p.gt[2 * i + 1] = p.table.gt[2 * s + 1]; }
     if (p.hom) p.hom[i] = p.table.hom[s];

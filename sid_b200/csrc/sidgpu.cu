@@ -1133,10 +1133,37 @@ int sidgpu_emit_records(sidgpu_ctx* ctx, uint64_t site_begin, uint64_t n_sites, 
     if (site_begin + n_sites > ctx->n_sites_total) return ctx->fail(SIDGPU_EINVAL, "site range not in the store");
     if (n_sites == 0) return SIDGPU_OK;
     CK(cudaSetDevice(ctx->device));
-    RecordParams p {site_begin, n_sites, (const uint32_t*)ctx->order.p, (const uint32_t*)ctx->slot.p, ctx->tab, d_label, d_gt, d_hom, d_het};
+    RecordParams p {site_begin, n_sites, (const uint32_t*)ctx->order.p, (const uint32_t*)ctx->slot.p, ctx->tab, d_label, d_gt, d_hom, d_het,
+                    nullptr, nullptr, nullptr, nullptr};
     k_records<<<(unsigned)((n_sites + 255) / 256), 256, 0, ctx->stream>>>(p);
     TRY(check_launch(ctx, "k_records"));
     CK(cudaStreamSynchronize(ctx->stream));
+    return SIDGPU_OK;
+}
+
+int sidgpu_emit_columns(sidgpu_ctx* ctx, uint64_t site_begin, uint64_t n_sites, const sidgpu_columns* cols) {
+    if (!ctx || !cols) return SIDGPU_EINVAL;
+    if (ctx->phase == PHASE_IDLE) return ctx->fail(SIDGPU_ESTATE, "sidgpu_emit_columns outside a session");
+    if (!ctx->streaming && ctx->phase != PHASE_FINISHED) return ctx->fail(SIDGPU_ESTATE, "this method needs sidgpu_finish first");
+    if (ctx->params.method == SIDGPU_METHOD_QUALITY) return ctx->fail(SIDGPU_EINVAL, "quality results are per site: use sidgpu_emit_csv");
+    if (site_begin + n_sites > ctx->n_sites_total) return ctx->fail(SIDGPU_EINVAL, "site range not in the store");
+    if (n_sites == 0) return SIDGPU_OK;
+    CK(cudaSetDevice(ctx->device));
+    RecordParams p {site_begin, n_sites, (const uint32_t*)ctx->order.p, (const uint32_t*)ctx->slot.p, ctx->tab,
+                    cols->d_label, cols->d_gt, cols->d_hom_conf, cols->d_het_conf,
+                    (const int32_t*)ctx->pos.p, (const uint32_t*)ctx->name_ref.p, cols->d_pos, cols->d_name_ref};
+    k_records<<<(unsigned)((n_sites + 255) / 256), 256, 0, ctx->stream>>>(p);
+    TRY(check_launch(ctx, "k_records"));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return SIDGPU_OK;
+}
+
+int sidgpu_names(sidgpu_ctx* ctx, const char** d_names, uint64_t* names_bytes) {
+    if (!ctx || !d_names || !names_bytes) return SIDGPU_EINVAL;
+    CK(cudaSetDevice(ctx->device));
+    TRY(sync_ctl(ctx));
+    *d_names = ctx->names.pool;
+    *names_bytes = ctx->h_ctl->name_cursor;
     return SIDGPU_OK;
 }
 

@@ -145,6 +145,39 @@ def test_very_deep_pileups(native, gpu_ctx, lam, n_sites, method):
     assert diffs <= 2
 
 
+@pytest.mark.parametrize("case", [c for c in MANIFEST["cases"] if c["input"] in ("depth30_two_chroms.plp", "edge.plp", "depth5.plp")
+                                  and "quality" not in c["flags"]], ids=lambda c: c["csv"])
+def test_columns_match_reference_csv(native, gpu_ctx, case):
+    """sidgpu_emit_columns (chrom, pos, label, gt, confidences as arrays) row by row against
+    the reference's CSV, and as a pyarrow table."""
+    import sid_b200
+    text = read(case["input"])
+    kw = flags_to_kwargs(case["flags"])
+    fit = None
+    if "heterozygosity" in case or kw.get("estimate_prior"):
+        o = op.oracle_call(text, **kw)
+        prof = o["profiles"]
+        cov = op.unpack_profiles(prof).astype(np.int64).sum(axis=1)
+        u, c = op.oracle_unique(prof[cov >= 4])
+        fit = (o["pi"], o["eps"], op.oracle_nd(u, c))
+    cols = sid_b200.call_columns(text, kw["method"], kw.get("estimate_prior", False), kw.get("prior", -1.0), kw.get("error_threshold", 0.1),
+                                 kw.get("alpha", 0.05), ctx=gpu_ctx, fit=fit)
+    want = op.parse_rows(read(case["csv"]))
+    assert len(cols["pos"]) == len(want)
+    for i, w in enumerate(want):
+        assert cols["chrom_names"][cols["chrom_codes"][i]] == w[0]
+        assert int(cols["pos"][i]) == w[1]
+        assert ("hom", "het")[cols["label"][i]] == w[2]
+        assert bytes(cols["gt"][i]).decode("latin-1") == w[3]
+        # the CSV carries six significant digits
+        assert op.conf_close(cols["hom_conf"][i], w[4], 1e-5) and op.conf_close(cols["het_conf"][i], w[5], 1e-5)
+    pa = pytest.importorskip("pyarrow")
+    t = sid_b200.columns_to_arrow(cols)
+    assert t.num_rows == len(want) and t.column_names == ["chrom", "pos", "label", "gt", "hom_conf", "het_conf"]
+    if len(want):
+        assert t.column("chrom")[0].as_py() == want[0][0] and t.column("label")[0].as_py() == want[0][2]
+
+
 def test_emit_sub_ranges_concatenate(native, gpu_ctx):
     """sidgpu_emit_csv over odd-sized pieces of the store == one call over all of it (file order through order[])."""
     import sid_b200
