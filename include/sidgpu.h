@@ -57,7 +57,9 @@ typedef struct {
     void* stream;             /* cudaStream_t to run on (NULL: the ctx creates its own) */
 } sidgpu_config;
 
-/* Parameters of one calling session: GlobalOptions of sid.cpp:11-17. */
+/* Parameters of one calling session: GlobalOptions of sid.cpp:11-17.
+ * (Environment: SIDGPU_SLICE_LINES=<lines per tokenizer slice, default 29.5> is a tuning knob read once
+ * per process; results do not depend on it.) */
 typedef struct {
     int method;                 /* SIDGPU_METHOD_* */
     int estimate_prior;         /* -R */

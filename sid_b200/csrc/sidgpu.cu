@@ -31,7 +31,7 @@ std::string g_create_error;
 struct Control {
     unsigned int tok_ticket;
     unsigned int csv_ticket;
-    unsigned long long n_sites;
+    unsigned long long n_sites;      // storage indices the running tokenizer call has handed out (TokParams::site_alloc)
     unsigned long long error;
     unsigned long long csv_bytes;
     unsigned long long csv_rows;
