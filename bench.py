@@ -39,6 +39,7 @@ def parse_args():
     ap.add_argument("--depth", default="depth30", choices=["depth30", "depth60", "depth500"])
     ap.add_argument("--cpu-sample-sites", type=int, default=3_000_000)
     ap.add_argument("--het-only", action="store_true", help="emit only rows labelled het (the pipeline's grep ',het,'); not the headline config")
+    ap.add_argument("--chunk-mb", type=int, default=256, help="chunk size of the host-buffer path (sidgpu_config.max_chunk_bytes)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -224,7 +225,7 @@ def run_ours(args):
     h_csv_t = torch.empty(csv_cap, dtype=torch.uint8, pin_memory=True)
     torch.cuda.synchronize()
 
-    ctx = sid_b200.Context(device=local_rank, stream=stream.cuda_stream, max_chunk_bytes=256 << 20)
+    ctx = sid_b200.Context(device=local_rank, stream=stream.cuda_stream, max_chunk_bytes=args.chunk_mb << 20)
     params = sid_b200.Context.make_params(args.method, het_only=args.het_only)
     ctx_streams = args.method in ("local", "quality")       # rows can be emitted chunk by chunk, no global step
     state = {"csv_bytes": 0, "rows": 0}

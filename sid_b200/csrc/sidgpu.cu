@@ -68,7 +68,8 @@ struct sidgpu_ctx {
     double avg_line_bytes = 80.0;    // running estimate, sizes the tokenizer's slices
 
     Control* d_ctl = nullptr;
-    Control* h_ctl = nullptr;
+    Control* h_ctl = nullptr;          // mapped pinned memory: the device writes it directly (k_publish_ctl)
+    Control* h_ctl_dev = nullptr;      // its device-side address
 
     // unique-profile table
     int table_log2 = 0;
@@ -174,8 +175,20 @@ void release(DevBuf& b) {
 template <class T>
 T* ctl_field(sidgpu_ctx* ctx, T Control::*m) { return &(ctx->d_ctl->*m); }
 
+// The control block travels to the host by stores from a one-warp kernel into mapped pinned memory, not
+// by a cudaMemcpy: a copy would queue in the device-to-host copy engine behind the CSV chunks of the
+// host path (milliseconds each), and the host loop that keeps the uploads going waits on this.
+__global__ void k_publish_ctl(const Control* d, Control* h) {
+    static_assert(sizeof(Control) % 8 == 0, "Control is copied in 8-byte words");
+    const unsigned long long* s = reinterpret_cast<const unsigned long long*>(d);
+    volatile unsigned long long* t = reinterpret_cast<volatile unsigned long long*>(h);
+    for (unsigned i = threadIdx.x; i < sizeof(Control) / 8; i += blockDim.x) t[i] = s[i];
+    __threadfence_system();
+}
+
 int sync_ctl(sidgpu_ctx* ctx) {
-    CK(cudaMemcpyAsync(ctx->h_ctl, ctx->d_ctl, sizeof(Control), cudaMemcpyDeviceToHost, ctx->stream));
+    k_publish_ctl<<<1, 32, 0, ctx->stream>>>(ctx->d_ctl, ctx->h_ctl_dev);
+    CK(cudaGetLastError());
     CK(cudaStreamSynchronize(ctx->stream));
     return SIDGPU_OK;
 }
@@ -620,8 +633,7 @@ int objective_value(sidgpu_ctx* ctx, const double nd[4], double pi, double eps, 
     }
     double* d_obj = ctl_field(ctx, &Control::objective);
     TRY(launch_objective(ctx, nd, pi, eps, d_obj));
-    CK(cudaMemcpyAsync(&ctx->h_ctl->objective, d_obj, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    TRY(sync_ctl(ctx));
     *value = ctx->h_ctl->objective;
     return SIDGPU_OK;
 }
@@ -740,7 +752,9 @@ int sidgpu_create(const sidgpu_config* cfg, sidgpu_ctx** out) {
     }
     if (cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking) != cudaSuccess) { ctx->err = "stream creation failed"; return bail(SIDGPU_ECUDA); }
-    if (cudaMalloc((void**)&ctx->d_ctl, sizeof(Control)) != cudaSuccess || cudaMallocHost((void**)&ctx->h_ctl, sizeof(Control)) != cudaSuccess) {
+    if (cudaMalloc((void**)&ctx->d_ctl, sizeof(Control)) != cudaSuccess ||
+        cudaHostAlloc((void**)&ctx->h_ctl, sizeof(Control), cudaHostAllocMapped) != cudaSuccess ||
+        cudaHostGetDevicePointer((void**)&ctx->h_ctl_dev, ctx->h_ctl, 0) != cudaSuccess) {
         ctx->err = "control block allocation failed";
         return bail(SIDGPU_ENOMEM);
     }
