@@ -213,16 +213,18 @@ SID_HD bool parse_line_bits(const uint8_t* s, uint32_t avail, uint32_t region_of
     uint32_t cur = l0 + q4 + 1;             // bit index of the next byte to look at
     uint32_t na = 0, nc = 0, ng = 0, nt = 0, ndot = 0;
     uint32_t skip = 0;                      // bytes at `cur` still covered by a '^' or an indel
+    // The loop has one exit, at its bottom: a refusal clears `ok` and lets the step finish on harmless values
+    // (no `break`: the lanes of a warp leave together more often and the compiler emits no break blocks).
     bool running = ok;
     while (running) {
-        if (cur + 64 > B.n_bits) { ok = false; break; }             // ran out of classified bytes
+        if (cur + 64 > B.n_bits) { ok = false; cur = 0; running = false; }   // ran out of classified bytes
         const uint32_t term = bits32(B.term, cur);
         uint32_t vmask = 0xFFFFFFFFu;       // bytes of this step that belong to the field
         bool last = false;
         if (term) {
             const uint32_t n = first_bit(term);
             const uint32_t tb = s[region_off + cur + n];
-            if (tb != '\t' && tb != ' ' && tb != '\n' && tb != 0) { ok = false; break; }   // a control byte inside the field
+            if (tb != '\t' && tb != ' ' && tb != '\n' && tb != 0) ok = false;   // a control byte inside the field
             vmask = n ? (0xFFFFFFFFu >> (32 - n)) : 0u;
             last = true;
         }
@@ -232,7 +234,7 @@ SID_HD bool parse_line_bits(const uint8_t* s, uint32_t avail, uint32_t region_of
             skip -= sk;
         }
         const uint32_t car = bits32(B.caret, cur) & vmask;
-        if (car & (car << 1)) { ok = false; break; }                // "^^": leave the parity to the byte-wise path
+        if (car & (car << 1)) ok = false;                           // "^^": leave the parity to the byte-wise path
         const uint32_t live = vmask & ~(car << 1);                  // '^' hides the byte after it
         const uint32_t pm = bits32(B.pm, cur) & live;
         uint32_t cm = live;                 // the bytes to count in this step
@@ -252,10 +254,10 @@ SID_HD bool parse_line_bits(const uint8_t* s, uint32_t avail, uint32_t region_of
                 any = true;
                 ++q;
             }
-            if (q + 8 >= avail) { ok = false; break; }
             skip = any ? n : 0;             // a sign without digits is ignored (pileup.cpp:131-133)
             next = q - region_off;
             last = false;
+            if (q + 8 >= avail) { ok = false; last = true; }
         } else if (car >> 31) {
             skip = 1;                       // the hidden byte is the first of the next step
         }
@@ -265,7 +267,7 @@ SID_HD bool parse_line_bits(const uint8_t* s, uint32_t avail, uint32_t region_of
         nt += pop_count(bits32(B.t, cur) & cm);
         ndot += pop_count(bits32(B.dot, cur) & cm);
         cur = next;
-        if (last) running = false;
+        if (last || !ok) running = false;
     }
     SID_SYNCWARP();
     // '.' and ',' stand for the reference base (pileup.cpp:78-83); other reference characters drop them
