@@ -180,7 +180,13 @@ def _adversarial_text(seed, n_lines):
         pos = rnd.choice(["1", "123456789", "1234567890", "007", "-5", "+3", "12ab", "99999999999999999999", "4294967296"])
         ref = rnd.choice(list("ACGTNacgtn*") + ["AC", ""])
         tail = rnd.choice(["\tIIII", "", "\t", "\tII\tJJ", " II"])
-        lines.append(sep.join([chrom, pos, ref, str(ln), bases]) + tail)
+        fields = [chrom, pos, ref, str(ln), bases]
+        if rnd.random() < 0.08:                      # too few columns: the next line's separators must not be taken for this one's
+            fields = fields[:rnd.choice([1, 2, 3, 4])]
+            tail = ""
+        lines.append(sep.join(fields) + tail)
+        if rnd.random() < 0.03:
+            lines.extend([""] * rnd.choice([1, 2]))          # blank lines (readFile skips them, call.cpp:14)
     return ("\n".join(lines) + "\n").encode("latin-1")
 
 
