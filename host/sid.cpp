@@ -1,6 +1,7 @@
 // `sid [flags] input_file` -- the reference's command line (sid.cpp:11-110) over the GPU path.
 // Same flags and defaults (-m METHOD, -r PRIOR, -R, -p LEVEL, -E ERROR, -h), same CSV on stdout,
-// same `# ...` lines on stderr, same exit codes.  Extra long options: --device N, --chunk-mb N,
+// same `# ...` lines on stderr, same exit codes.  Extra long options: --device N, --devices A,B,.. (one
+// position shard per GPU; -m local / quality without -R), --chunk-mb N,
 // --het-only (rows labelled het only: the pipeline's `grep ',het,'`, scripts/sid-pipeline/run-sid.sh:16-17;
 // the header line is kept).  A gzip-compressed input (as the pipeline stores its pileups,
 // scripts/prepare-data.sh:14) is inflated in memory instead of `zcat` to a temporary file
@@ -45,7 +46,8 @@ int main(int argc, char** argv) {
     int device = 0;
     size_t chunk_mb = 0;
     bool het_only = false;
-    static const option LONG[] = {{"device", required_argument, nullptr, 1000}, {"chunk-mb", required_argument, nullptr, 1001}, {"het-only", no_argument, nullptr, 1002}, {nullptr, 0, nullptr, 0}};
+    std::vector<int> devices;
+    static const option LONG[] = {{"device", required_argument, nullptr, 1000}, {"chunk-mb", required_argument, nullptr, 1001}, {"het-only", no_argument, nullptr, 1002}, {"devices", required_argument, nullptr, 1003}, {nullptr, 0, nullptr, 0}};
     int flag;
     while ((flag = getopt_long(argc, argv, "E:Rhm:p:r:", LONG, nullptr)) != -1) {      // optstring as built by sid.cpp:60-69
         switch (flag) {
@@ -58,6 +60,13 @@ int main(int argc, char** argv) {
             case 1000: device = atoi(optarg); break;
             case 1001: chunk_mb = (size_t)atol(optarg); break;
             case 1002: het_only = true; break;
+            case 1003:
+                for (const char* q = optarg; *q;) {
+                    devices.push_back(atoi(q));
+                    while (*q && *q != ',') ++q;
+                    if (*q == ',') ++q;
+                }
+                break;
             default: exit(EXIT_FAILURE);             // sid.cpp:80-82
         }
     }
@@ -101,8 +110,13 @@ int main(int argc, char** argv) {
     }
     std::ios::sync_with_stdio(false);
     try {
+        if (devices.size() == 1) device = devices[0];
         sidSetDevice(device, chunk_mb << 20);
         sidSetHetOnly(het_only);
+        if (devices.size() > 1 && !o.estimate_prior && (o.method == "local" || o.method == "quality"))
+            sidCallToStreamSharded(o.method, text, len, o.snp_prior, o.site_error_threshold, o.significance_level, devices, std::cout,
+                                   "chrom,pos,label,gt,hom_conf,het_conf,conf_type");
+        else
         sidCallToStream(o.method, text, len, o.estimate_prior, o.snp_prior, o.site_error_threshold, o.significance_level,
                         std::cout, std::cerr, "chrom,pos,label,gt,hom_conf,het_conf,conf_type");          // sid.cpp:102
         std::cout.flush();

@@ -7,6 +7,7 @@
 #include <memory>
 #include <sstream>
 #include <stdexcept>
+#include <thread>
 
 #include "../include/sidgpu.h"
 #include "call.hpp"
@@ -243,6 +244,76 @@ SidRunInfo sidCallToStream(const std::string& method, const char* text, size_t l
     log_fit(m, info, log);
     if (header) out << header << std::endl;
     out.write(rows.csv.p, (std::streamsize)rows.bytes);
+    return info;
+}
+
+SidRunInfo sidCallToStreamSharded(const std::string& method, const char* text, size_t len, double prior, double error_threshold,
+                                  double significance_level, const std::vector<int>& devices, std::ostream& out, const char* header) {
+    SidRunInfo info;
+    const int m = method_id(method);
+    if (m != SIDGPU_METHOD_LOCAL && m != SIDGPU_METHOD_QUALITY)
+        throw std::runtime_error("several devices: only -m local / -m quality without -R (the methods without a genome-wide fit)");
+    const size_t n = devices.size();
+    if (n == 0) throw std::runtime_error("no devices given");
+    // shard k owns the lines whose first byte lies in [cut[k], cut[k+1]): cuts are moved to line starts
+    std::vector<size_t> cut(n + 1, len);
+    cut[0] = 0;
+    for (size_t k = 1; k < n; ++k) {
+        size_t c = std::max(cut[k - 1], len / n * k);
+        if (c > 0 && c < len && text[c - 1] != '\n') {
+            const void* nl = std::memchr(text + c, '\n', len - c);
+            c = nl ? (size_t)((const char*)nl - text) + 1 : len;
+        }
+        cut[k] = std::min(c, len);
+    }
+    struct Shard { sidgpu_ctx* h = nullptr; char* csv = nullptr; uint64_t bytes = 0, sites = 0, rows = 0; int rc = SIDGPU_OK; std::string err; };
+    std::vector<Shard> shard(n);
+    std::vector<std::thread> workers;
+    for (size_t k = 0; k < n; ++k) {
+        workers.emplace_back([&, k]() {
+            Shard& s = shard[k];
+            sidgpu_config cfg {};
+            cfg.device = devices[k];
+            cfg.max_chunk_bytes = g_chunk;
+            s.rc = sidgpu_create(&cfg, &s.h);
+            if (s.rc != SIDGPU_OK) { s.err = sidgpu_last_error(nullptr); return; }
+            sidgpu_params p {};
+            p.method = m;
+            p.prior = prior;
+            p.error_threshold = error_threshold;
+            p.significance_level = significance_level;
+            p.het_only = g_het_only ? 1 : 0;
+            const size_t bytes_in = cut[k + 1] - cut[k];
+            size_t cap = bytes_in + bytes_in / 2 + 4096;
+            for (;;) {
+                if ((s.rc = sidgpu_malloc_host(s.h, cap, (void**)&s.csv)) != SIDGPU_OK) break;
+                s.rc = sidgpu_call_host(s.h, &p, text + cut[k], bytes_in, s.csv, cap, &s.bytes, &s.sites, &s.rows);
+                if (s.rc == SIDGPU_ECAPACITY && s.bytes > cap) { sidgpu_free_host(s.h, s.csv); s.csv = nullptr; cap = s.bytes + 4096; continue; }
+                break;
+            }
+            if (s.rc != SIDGPU_OK) s.err = sidgpu_last_error(s.h);
+        });
+    }
+    for (auto& w : workers) w.join();
+    int rc = SIDGPU_OK;
+    std::string err;
+    for (auto& s : shard) if (s.rc != SIDGPU_OK && rc == SIDGPU_OK) { rc = s.rc; err = s.err; }      // first failing shard in file order
+    if (rc == SIDGPU_OK) {
+        if (header) out << header << std::endl;
+        for (auto& s : shard) {
+            out.write(s.csv, (std::streamsize)s.bytes);
+            info.n_sites += s.sites;
+            info.n_rows += s.rows;
+        }
+    }
+    for (auto& s : shard) {
+        if (s.h && s.csv) sidgpu_free_host(s.h, s.csv);
+        if (s.h) sidgpu_destroy(s.h);
+    }
+    if (rc == SIDGPU_EMALFORMED) throw std::invalid_argument("Malformed pileup line");
+    if (rc == SIDGPU_EMISSING_MAPQ) throw std::invalid_argument("Malformed pileup line or missing mapping qualities");
+    if (rc == SIDGPU_EQUAL_SHORT) throw std::invalid_argument("Malformed pileup line: " + err);
+    if (rc != SIDGPU_OK) throw std::runtime_error("sidgpu error " + std::to_string(rc) + ": " + err);
     return info;
 }
 

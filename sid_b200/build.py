@@ -52,9 +52,9 @@ def build_sid_cli(force=False):
         return None
     link = ["-Lsid_b200", "-lsidgpu", "-Wl,-rpath,$ORIGIN/../sid_b200"]
     if force or _newer(out, srcs + [os.path.join(ROOT, "sid_b200", "libsidgpu.so")]):
-        _run(["g++", "-O2", "-std=c++17", "-Wall", "-Iinclude", "-o", out, "host/sid.cpp", "host/sid_host.cpp"] + link + ["-lz"])
+        _run(["g++", "-O2", "-std=c++17", "-Wall", "-Iinclude", "-o", out, "host/sid.cpp", "host/sid_host.cpp"] + link + ["-lz", "-pthread"])
         _run(["g++", "-O2", "-std=c++17", "-Wall", "-Iinclude", "-o", os.path.join(ROOT, "host", "api_check"),
-              "host/api_check.cpp", "host/sid_host.cpp"] + link)
+              "host/api_check.cpp", "host/sid_host.cpp"] + link + ["-pthread"])
     return out
 
 

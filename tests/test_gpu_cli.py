@@ -72,6 +72,20 @@ def test_cli_reads_gzip_input(sid_bin, tmp_path):
     assert diffs <= max(2, n // 1000)
 
 
+@pytest.mark.parametrize("devices", ["0,0", "0,0,0,0,0"])
+def test_cli_position_shards(sid_bin, devices):
+    """--devices: one position shard per listed GPU (here the same GPU several times), rows in file order."""
+    for name, flags in (("depth30_two_chroms.plp", ["-m", "local"]), ("quality30.plp", ["-m", "quality"])):
+        case = [c for c in MANIFEST["cases"] if c["input"] == name and c["flags"] == flags][0]
+        rc, out, err = run(sid_bin, "--devices", devices, *flags, os.path.join(GOLDEN, name))
+        assert rc == 0, err
+        n, diffs = op.compare_csv(out, read(case["csv"]))
+        assert diffs <= max(2, n // 1000)
+    # a malformed line in any shard aborts like the reference
+    rc, out, err = run(sid_bin, "--devices", devices, os.path.join(GOLDEN, "malformed_second_line_bad.plp"))
+    assert rc in (-6, 134) and out == b"" and "Malformed pileup line" in err
+
+
 def test_cli_error_behaviour(sid_bin):
     # malformed line: the reference terminates on std::invalid_argument (SIGABRT), nothing on stdout
     rc, out, err = run(sid_bin, os.path.join(GOLDEN, "malformed_too_few_columns.plp"))
