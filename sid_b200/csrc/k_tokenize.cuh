@@ -28,7 +28,7 @@ namespace sid {
 
 constexpr int TOK_PARSE_WARPS = 8;
 constexpr int TOK_THREADS = 32 * (1 + TOK_PARSE_WARPS);
-constexpr int TOK_STAGES = 2;
+constexpr int TOK_STAGES_MAX = 2;                 // tiles staged per CTA: 2 (copy of tile n+1 under the parsing of n) or 1 (long lines)
 #ifndef SID_SVC_SLEEP
 #define SID_SVC_SLEEP 500
 #endif
@@ -81,9 +81,9 @@ struct TokParams {
 inline uint32_t tok_tail_bytes(uint32_t ext) { return ext + 128u > 2048u ? 2048u : ext + 128u; }   // multiple of 32
 inline uint32_t tok_text_stride(uint32_t slice, uint32_t ext) { return (16u + 8u * slice + tok_tail_bytes(ext) + 127u) & ~127u; }
 inline uint32_t tok_words_cap(uint32_t slice, uint32_t ext) { return (slice + ext) / 32u + 2u; }
-// staged text (2 stages) + line starts (8 warps) + class bit arrays (8 warps x 8 classes)
-inline uint32_t tok_dyn_smem(uint32_t slice, uint32_t ext) {
-    return 2u * tok_text_stride(slice, ext) + 8u * (slice / 8u) * 2u + 8u * 8u * tok_words_cap(slice, ext) * 4u;
+// staged text (1 or 2 stages) + line starts (8 warps) + class bit arrays (8 warps x 8 classes)
+inline uint32_t tok_dyn_smem(uint32_t slice, uint32_t ext, uint32_t stages = 2) {
+    return stages * tok_text_stride(slice, ext) + 8u * (slice / 8u) * 2u + 8u * 8u * tok_words_cap(slice, ext) * 4u;
 }
 
 #if defined(__CUDACC__)
@@ -166,7 +166,7 @@ struct SmemBytes {         // byte source over a staged tile for name_intern
 };
 
 
-template <bool FAST>
+template <bool FAST, int TOK_STAGES>
 __global__ void __launch_bounds__(TOK_THREADS) k_tokenize(const TokParams p) {
     extern __shared__ __align__(128) uint8_t s_dyn[];      // staged text per stage, then line starts per stage and warp
     __shared__ StageMeta s_meta[TOK_STAGES];

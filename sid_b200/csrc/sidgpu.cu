@@ -433,17 +433,28 @@ int run_tokenizer(sidgpu_ctx* ctx, const char* d_text, size_t text_len, size_t r
         p.lines_cap = slice / 8;
         p.ext_bytes = ext;
         p.words_cap = tok_words_cap(slice, ext);
-        const uint32_t dyn_smem = tok_dyn_smem(slice, ext);
-        int per_sm = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tokenize<true>, TOK_THREADS, dyn_smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+        // two staged tiles per CTA (the copy of the next tile runs under the parsing of this one) unless the
+        // slices are so long that a single stage doubles the CTAs an SM holds: then the CTAs cover each other's copies
+        static const int force_stages = getenv("SIDGPU_TOK_STAGES") ? atoi(getenv("SIDGPU_TOK_STAGES")) : 0;     // tuning knob
+        int per_sm2 = 0, per_sm1 = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm2, k_tokenize<true, 2>, TOK_THREADS, tok_dyn_smem(slice, ext, 2)) != cudaSuccess || per_sm2 < 1) per_sm2 = 1;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm1, k_tokenize<true, 1>, TOK_THREADS, tok_dyn_smem(slice, ext, 1)) != cudaSuccess || per_sm1 < 1) per_sm1 = 1;
+        const int stages = force_stages == 1 || force_stages == 2 ? force_stages : (per_sm1 >= 2 * per_sm2 ? 1 : 2);
+        const uint32_t dyn_smem = tok_dyn_smem(slice, ext, (uint32_t)stages);
+        const int per_sm = stages == 1 ? per_sm1 : per_sm2;
         const int max_ctas = ctx->sm_count * per_sm;
         const unsigned grid = (unsigned)std::min<uint64_t>(n_tiles, (uint64_t)max_ctas);
         {
             ProfScope prof(ctx, PROF_TOKENIZE);
             // strict_qual (sidgpu_tokenize with want_qual): the byte-wise grammar also validates the quality
             // columns; inside a quality session k_quality re-reads every line and reports them itself
-            if (want_qual && strict_qual) k_tokenize<false><<<grid, TOK_THREADS, dyn_smem, ctx->stream>>>(p);
-            else k_tokenize<true><<<grid, TOK_THREADS, dyn_smem, ctx->stream>>>(p);
+            if (want_qual && strict_qual) {
+                if (stages == 1) k_tokenize<false, 1><<<grid, TOK_THREADS, dyn_smem, ctx->stream>>>(p);
+                else k_tokenize<false, 2><<<grid, TOK_THREADS, dyn_smem, ctx->stream>>>(p);
+            } else {
+                if (stages == 1) k_tokenize<true, 1><<<grid, TOK_THREADS, dyn_smem, ctx->stream>>>(p);
+                else k_tokenize<true, 2><<<grid, TOK_THREADS, dyn_smem, ctx->stream>>>(p);
+            }
             TRY(check_launch(ctx, "k_tokenize"));
         }
         {
@@ -792,8 +803,10 @@ int sidgpu_create(const sidgpu_config* cfg, sidgpu_ctx** out) {
         cudaMemcpyAsync(ctx->quality_lut.p, lut.data(), lut.size() * 8, cudaMemcpyHostToDevice, ctx->stream);
         cudaStreamSynchronize(ctx->stream);
     }
-    if ((e = cudaFuncSetAttribute(k_tokenize<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tok_dyn_smem(SLICE_MAX, 2016))) != cudaSuccess ||
-        (e = cudaFuncSetAttribute(k_tokenize<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tok_dyn_smem(SLICE_MAX, 2016))) != cudaSuccess ||
+    if ((e = cudaFuncSetAttribute(k_tokenize<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tok_dyn_smem(SLICE_MAX, 2016))) != cudaSuccess ||
+        (e = cudaFuncSetAttribute(k_tokenize<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tok_dyn_smem(SLICE_MAX, 2016))) != cudaSuccess ||
+        (e = cudaFuncSetAttribute(k_tokenize<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tok_dyn_smem(SLICE_MAX, 2016))) != cudaSuccess ||
+        (e = cudaFuncSetAttribute(k_tokenize<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tok_dyn_smem(SLICE_MAX, 2016))) != cudaSuccess ||
         (e = cudaFuncSetAttribute(k_csv, cudaFuncAttributeMaxDynamicSharedMemorySize, CSV_STAGE)) != cudaSuccess) {
         ctx->err = std::string("shared memory opt-in: ") + cudaGetErrorString(e);
         return bail(SIDGPU_ECUDA);
