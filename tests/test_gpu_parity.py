@@ -37,6 +37,40 @@ def test_tokenizer_bit_exact(native, gpu_ctx, name):
     assert got["chrom"] == want["chrom"]
 
 
+@pytest.mark.parametrize("seed", [21, 22])
+def test_tokenizer_on_adversarial_valid_lines(native, gpu_ctx, seed):
+    """Odd but well-formed lines (control bytes and high bytes in names, doubled delimiters, '^^', signs without
+    digits, huge indel lengths, 5-column lines, 40-character names): the kernel's fast path, its fall-backs
+    and the name dictionary against the oracle, line by line."""
+    from test_hostcheck import _adversarial_text
+    hc = op.hostcheck()
+    raw = _adversarial_text(seed, 30000)
+    keep = []
+    line = op.HcLine()
+    for ln in raw.split(b"\n"):
+        if not ln or b"\0" in ln:
+            continue
+        buf = ln + b"\n"
+        hc.hc_parse_line(buf, len(buf), 0, 0, ctypes.byref(line))
+        if line.status == 0:
+            keep.append(buf)
+    assert len(keep) > 5000
+    text = b"".join(keep)
+    want = op.oracle_call(text, "local")
+    d = gpu_ctx.upload_text(text)
+    try:
+        got = gpu_ctx.tokenize(d, len(text))
+    finally:
+        d.free()
+    assert got["n_sites"] == want["n_sites"] == len(keep)
+    assert np.array_equal(got["profile"], want["profiles"])
+    assert np.array_equal(got["pos"], want["pos"])
+    assert got["chrom"] == want["chrom"]
+    rows, n, n_rows = gpu_ctx.call_host(text, __import__("sid_b200").Context.make_params("local"))
+    k, diffs = op.compare_csv(__import__("sid_b200").CSV_HEADER + rows, want["csv"])
+    assert k == n_rows and diffs <= max(2, k // 1000)
+
+
 def test_tokenizer_shard_ranges_concatenate(native, gpu_ctx):
     """Byte-range sharding: any split of the text into ranges yields the same sites."""
     text = read("depth30.plp")
