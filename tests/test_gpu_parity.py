@@ -74,6 +74,30 @@ def test_tokenizer_on_adversarial_valid_lines(native, gpu_ctx, seed):
     assert k == n_rows and diffs <= max(2, k // 1000)
 
 
+def test_quality_on_adversarial_valid_lines(native, gpu_ctx):
+    """The same kind of lines with both quality columns long enough for their counted bases, through -m quality."""
+    import sid_b200
+    from test_hostcheck import _adversarial_text
+    hc = op.hostcheck()
+    line = op.HcLine()
+    keep = []
+    for seed in (31, 32, 33):
+        for ln in _adversarial_text(seed, 30000).split(b"\n"):
+            if not ln:
+                continue
+            buf = ln + b"\n"
+            hc.hc_parse_line(buf, len(buf), 0, 1, ctypes.byref(line))
+            if line.status == 0:
+                keep.append(buf)
+    assert len(keep) > 1000
+    text = b"".join(keep)
+    want = op.oracle_call(text, "quality")
+    rows, n, n_rows = gpu_ctx.call_host(text, sid_b200.Context.make_params("quality"))
+    assert n == len(keep)
+    k, diffs = op.compare_csv(sid_b200.CSV_HEADER + rows, want["csv"])
+    assert k == n_rows and diffs <= max(2, k // 1000)
+
+
 def test_tokenizer_shard_ranges_concatenate(native, gpu_ctx):
     """Byte-range sharding: any split of the text into ranges yields the same sites."""
     text = read("depth30.plp")
