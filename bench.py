@@ -367,6 +367,8 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "kernel": "k_tokenize", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                          "frac": achieved / hbm_peak if hbm_peak else None, "traffic": traffic, "peak_kind": peak_kind,
                          "algorithmic_bytes_per_launch": text_len, "avg_launch_ms": tok_avg_ms, "launches_timed": tok_n,
+                         "limiter": "integer ALU pipe, 66 % of its peak in profiles/r1_ncu_full_tokenize_v19.txt (DRAM 18 %): "
+                                    "the HBM roofline is the contract's bound, not what this kernel runs into",
                          "kernel_ms_per_step": {k: v[0] / args.steps for k, v in ktimes.items()}},
             "e2e": e2e, "cpu_baseline": cpu, "gpu_launches": launches, "clocks": clocks.summary(), "lynch_fit": state.get("fit"),
         }
