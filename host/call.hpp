@@ -61,12 +61,13 @@ SidRunInfo sidCallToStream(const std::string& method, const char* text, size_t l
 // Selects the GPU (default 0) and the chunk size of the host path for subsequent calls.
 void sidSetDevice(int device, size_t max_chunk_bytes = 0);
 // The same over several GPUs of one node, one host thread and one position shard (a line-aligned byte range
-// of the text) per device, rows written in shard order: the data-parallel case, i.e. `local`
-// and `quality` without -R, which need no exchange between shards.  Methods with a genome-wide fit throw
-// std::runtime_error here: their sharded form lives in the Python host (sid_b200/shard.py, NCCL).
-SidRunInfo sidCallToStreamSharded(const std::string& method, const char* text, size_t len, double prior, double error_threshold,
-                                  double significance_level, const std::vector<int>& devices, std::ostream& out,
-                                  const char* header = nullptr);
+// of the text) per device, rows written in shard order.  `local` and `quality` without -R need
+// no exchange between shards.  The methods with a genome-wide fit share it: the host sums the shards' integer
+// nucleotide counts and, per optimiser step, their objective values (one double each), and merges their
+// unique-profile lists for the BH ranks of likelihood_ratio.  (`quality -R` is not sharded: two text passes.)
+SidRunInfo sidCallToStreamSharded(const std::string& method, const char* text, size_t len, bool estimate_prior, double prior,
+                                  double error_threshold, double significance_level, const std::vector<int>& devices, std::ostream& out,
+                                  std::ostream& log, const char* header = nullptr);
 // Only rows labelled "het" from now on: the `grep ',het,'` of scripts/sid-pipeline/run-sid.sh:16-17 done
 // before the rows leave the GPU.  Applies to sidCallToStream and to the four call* functions.
 void sidSetHetOnly(bool het_only);

@@ -1,7 +1,7 @@
 // `sid [flags] input_file` -- the reference's command line (sid.cpp:11-110) over the GPU path.
 // Same flags and defaults (-m METHOD, -r PRIOR, -R, -p LEVEL, -E ERROR, -h), same CSV on stdout,
 // same `# ...` lines on stderr, same exit codes.  Extra long options: --device N, --devices A,B,.. (one
-// position shard per GPU; -m local / quality without -R), --chunk-mb N,
+// position shard per GPU, one shared fit), --chunk-mb N,
 // --het-only (rows labelled het only: the pipeline's `grep ',het,'`, scripts/sid-pipeline/run-sid.sh:16-17;
 // the header line is kept).  A gzip-compressed input (as the pipeline stores its pileups,
 // scripts/prepare-data.sh:14) is inflated in memory instead of `zcat` to a temporary file
@@ -113,9 +113,9 @@ int main(int argc, char** argv) {
         if (devices.size() == 1) device = devices[0];
         sidSetDevice(device, chunk_mb << 20);
         sidSetHetOnly(het_only);
-        if (devices.size() > 1 && !o.estimate_prior && (o.method == "local" || o.method == "quality"))
-            sidCallToStreamSharded(o.method, text, len, o.snp_prior, o.site_error_threshold, o.significance_level, devices, std::cout,
-                                   "chrom,pos,label,gt,hom_conf,het_conf,conf_type");
+        if (devices.size() > 1)
+            sidCallToStreamSharded(o.method, text, len, o.estimate_prior, o.snp_prior, o.site_error_threshold, o.significance_level, devices,
+                                   std::cout, std::cerr, "chrom,pos,label,gt,hom_conf,het_conf,conf_type");
         else
         sidCallToStream(o.method, text, len, o.estimate_prior, o.snp_prior, o.site_error_threshold, o.significance_level,
                         std::cout, std::cerr, "chrom,pos,label,gt,hom_conf,het_conf,conf_type");          // sid.cpp:102

@@ -6,10 +6,13 @@
 #include <iterator>
 #include <memory>
 #include <sstream>
+#include <algorithm>
+#include <limits>
 #include <stdexcept>
 #include <thread>
 
 #include "../include/sidgpu.h"
+#include "../sid_b200/csrc/nelder_mead.hpp"      // the simplex driver the library itself uses (host code, header only)
 #include "call.hpp"
 
 namespace {
@@ -247,14 +250,46 @@ SidRunInfo sidCallToStream(const std::string& method, const char* text, size_t l
     return info;
 }
 
-SidRunInfo sidCallToStreamSharded(const std::string& method, const char* text, size_t len, double prior, double error_threshold,
-                                  double significance_level, const std::vector<int>& devices, std::ostream& out, const char* header) {
+namespace {
+
+// lexicographic order of std::array<uint16_t,4> (pileup.cpp:179-182) for a packed profile
+uint64_t profile_sort_key(uint64_t p) {
+    return ((p & 0xFFFFull) << 48) | (((p >> 16) & 0xFFFFull) << 32) | (((p >> 32) & 0xFFFFull) << 16) | (p >> 48);
+}
+
+struct Shard {
+    sidgpu_ctx* h = nullptr;
+    char* csv = nullptr;
+    size_t cap = 0;
+    uint64_t bytes = 0, sites = 0, rows = 0;
+    int rc = SIDGPU_OK;
+    std::string err;
+    void fail(int code) { rc = code; err = h ? sidgpu_last_error(h) : sidgpu_last_error(nullptr); }
+};
+
+template <class F>
+void on_every_shard(std::vector<Shard>& shard, F f) {
+    std::vector<std::thread> workers;
+    for (size_t k = 0; k < shard.size(); ++k) workers.emplace_back([&, k]() { if (shard[k].rc == SIDGPU_OK) f(k, shard[k]); });
+    for (auto& w : workers) w.join();
+}
+
+}  // namespace
+
+SidRunInfo sidCallToStreamSharded(const std::string& method, const char* text, size_t len, bool estimate_prior, double prior,
+                                  double error_threshold, double significance_level, const std::vector<int>& devices, std::ostream& out,
+                                  std::ostream& log, const char* header) {
     SidRunInfo info;
     const int m = method_id(method);
-    if (m != SIDGPU_METHOD_LOCAL && m != SIDGPU_METHOD_QUALITY)
-        throw std::runtime_error("several devices: only -m local / -m quality without -R (the methods without a genome-wide fit)");
+    if (m < 0) {                                    // sid.cpp:92-100: unknown methods print the header only
+        if (header) out << header << std::endl;
+        return info;
+    }
+    if (m == SIDGPU_METHOD_QUALITY && estimate_prior)
+        throw std::runtime_error("several devices: -m quality -R needs two passes over the text and is not sharded here");
     const size_t n = devices.size();
     if (n == 0) throw std::runtime_error("no devices given");
+    const bool streams = (m == SIDGPU_METHOD_LOCAL || m == SIDGPU_METHOD_QUALITY) && !estimate_prior;
     // shard k owns the lines whose first byte lies in [cut[k], cut[k+1]): cuts are moved to line starts
     std::vector<size_t> cut(n + 1, len);
     cut[0] = 0;
@@ -266,39 +301,114 @@ SidRunInfo sidCallToStreamSharded(const std::string& method, const char* text, s
         }
         cut[k] = std::min(c, len);
     }
-    struct Shard { sidgpu_ctx* h = nullptr; char* csv = nullptr; uint64_t bytes = 0, sites = 0, rows = 0; int rc = SIDGPU_OK; std::string err; };
+    sidgpu_params p {};
+    p.method = m;
+    p.estimate_prior = estimate_prior ? 1 : 0;
+    p.prior = prior;
+    p.error_threshold = error_threshold;
+    p.significance_level = significance_level;
+    p.het_only = g_het_only ? 1 : 0;
     std::vector<Shard> shard(n);
-    std::vector<std::thread> workers;
-    for (size_t k = 0; k < n; ++k) {
-        workers.emplace_back([&, k]() {
-            Shard& s = shard[k];
-            sidgpu_config cfg {};
-            cfg.device = devices[k];
-            cfg.max_chunk_bytes = g_chunk;
-            s.rc = sidgpu_create(&cfg, &s.h);
-            if (s.rc != SIDGPU_OK) { s.err = sidgpu_last_error(nullptr); return; }
-            sidgpu_params p {};
-            p.method = m;
-            p.prior = prior;
-            p.error_threshold = error_threshold;
-            p.significance_level = significance_level;
-            p.het_only = g_het_only ? 1 : 0;
-            const size_t bytes_in = cut[k + 1] - cut[k];
+    auto alloc_csv = [](Shard& s, size_t cap) {
+        if (s.csv) { sidgpu_free_host(s.h, s.csv); s.csv = nullptr; }
+        s.cap = cap;
+        const int rc = sidgpu_malloc_host(s.h, cap, (void**)&s.csv);
+        if (rc != SIDGPU_OK) s.fail(rc);
+        return rc == SIDGPU_OK;
+    };
+    // ---- every shard: its own ctx, its text in
+    on_every_shard(shard, [&](size_t k, Shard& s) {
+        sidgpu_config cfg {};
+        cfg.device = devices[k];
+        cfg.max_chunk_bytes = g_chunk;
+        int rc = sidgpu_create(&cfg, &s.h);
+        if (rc != SIDGPU_OK) { s.fail(rc); return; }
+        const size_t bytes_in = cut[k + 1] - cut[k];
+        if (streams) {                              // no exchange between shards: the whole call at once
             size_t cap = bytes_in + bytes_in / 2 + 4096;
             for (;;) {
-                if ((s.rc = sidgpu_malloc_host(s.h, cap, (void**)&s.csv)) != SIDGPU_OK) break;
-                s.rc = sidgpu_call_host(s.h, &p, text + cut[k], bytes_in, s.csv, cap, &s.bytes, &s.sites, &s.rows);
-                if (s.rc == SIDGPU_ECAPACITY && s.bytes > cap) { sidgpu_free_host(s.h, s.csv); s.csv = nullptr; cap = s.bytes + 4096; continue; }
+                if (!alloc_csv(s, cap)) return;
+                rc = sidgpu_call_host(s.h, &p, text + cut[k], bytes_in, s.csv, s.cap, &s.bytes, &s.sites, &s.rows);
+                if (rc == SIDGPU_ECAPACITY && s.bytes > s.cap) { cap = s.bytes + 4096; continue; }
                 break;
             }
-            if (s.rc != SIDGPU_OK) s.err = sidgpu_last_error(s.h);
+        } else {
+            rc = sidgpu_begin(s.h, &p);
+            if (rc == SIDGPU_OK) rc = sidgpu_feed_host(s.h, text + cut[k], bytes_in, &s.sites);
+        }
+        if (rc != SIDGPU_OK) s.fail(rc);
+    });
+    auto first_error = [&]() {
+        for (auto& s : shard) if (s.rc != SIDGPU_OK) return &s;      // first failing shard in file order
+        return (Shard*)nullptr;
+    };
+    if (!streams && !first_error()) {
+        // ---- one fit for all shards: integer nucleotide sums, then Nelder-Mead on the sum of the shards' objectives
+        //      (estimateProfileGenotypeLikelihoods lynch.cpp:17-35; the objective is linear in the profile counts)
+        std::vector<sidgpu_unique_view> view(n);
+        uint64_t sums[5] = {0, 0, 0, 0, 0};
+        for (size_t k = 0; k < n && !first_error(); ++k) {
+            const int rc = sidgpu_histogram(shard[k].h, 4, &view[k]);
+            if (rc != SIDGPU_OK) { shard[k].fail(rc); break; }
+            for (int i = 0; i < 5; ++i) sums[i] += view[k].nd_sums[i];
+        }
+        double nd[4] = {0.25, 0.25, 0.25, 0.25};                     // pileup.cpp:209-215
+        if (sums[4]) for (int i = 0; i < 4; ++i) nd[i] = (double)sums[i] / (double)sums[4];
+        // the merged unique profiles (countUniqueProfiles of the whole genome): BH of likelihood_ratio ranks over them
+        std::vector<uint64_t> merged;
+        for (size_t k = 0; k < n && !first_error(); ++k) {
+            std::vector<uint64_t> prof(view[k].n_unique);
+            if (!prof.empty()) {
+                const int rc = sidgpu_memcpy_d2h(shard[k].h, prof.data(), view[k].d_profile, prof.size() * 8);
+                if (rc != SIDGPU_OK) { shard[k].fail(rc); break; }
+            }
+            merged.insert(merged.end(), prof.begin(), prof.end());
+        }
+        std::sort(merged.begin(), merged.end(), [](uint64_t a, uint64_t b) { return profile_sort_key(a) < profile_sort_key(b); });
+        merged.erase(std::unique(merged.begin(), merged.end()), merged.end());
+        if (!first_error()) {
+            auto objective = [&](double pi, double eps) {
+                if (pi < 0 || pi > 1 || eps < 0 || eps > 1) return std::numeric_limits<double>::max();     // lynch.cpp:41-43
+                double f = 0;
+                for (size_t k = 0; k < n; ++k) {
+                    double fk = 0;
+                    const int rc = sidgpu_lynch_objective(shard[k].h, nd, pi, eps, &fk);
+                    if (rc != SIDGPU_OK) { shard[k].fail(rc); return std::numeric_limits<double>::max(); }
+                    f += fk;
+                }
+                return f;
+            };
+            const double x0[2] = {1e-3, 1e-3}, step[2] = {1e-4, 1e-4};                                    // lynch.cpp:8-10,20
+            const sid::NelderMeadResult r = sid::nelder_mead_2d(objective, x0, step);
+            info.has_fit = true;
+            info.heterozygosity = r.x[0];
+            info.error_rate = r.x[1];
+            info.iterations = r.iterations;
+            info.converged = r.converged;
+            info.unique_profiles = merged.size();
+            for (size_t k = 0; k < n && !first_error(); ++k) {
+                const int rc = sidgpu_set_fit(shard[k].h, r.x[0], r.x[1], nd);
+                if (rc != SIDGPU_OK) shard[k].fail(rc);
+            }
+        }
+        // ---- classification with the shared fit, rows out
+        on_every_shard(shard, [&](size_t, Shard& s) {
+            int rc = m == SIDGPU_METHOD_LIKELIHOOD_RATIO ? sidgpu_finish_global(s.h, merged.data(), merged.size()) : sidgpu_finish(s.h);
+            size_t cap = (size_t)s.sites * 48 + 4096;
+            while (rc == SIDGPU_OK) {
+                if (!alloc_csv(s, cap)) return;
+                rc = sidgpu_emit_host(s.h, s.csv, s.cap, &s.bytes, &s.rows);
+                if (rc == SIDGPU_ECAPACITY && s.bytes > s.cap) { cap = s.bytes + 4096; rc = SIDGPU_OK; continue; }
+                break;
+            }
+            if (rc != SIDGPU_OK) s.fail(rc);
         });
     }
-    for (auto& w : workers) w.join();
     int rc = SIDGPU_OK;
     std::string err;
-    for (auto& s : shard) if (s.rc != SIDGPU_OK && rc == SIDGPU_OK) { rc = s.rc; err = s.err; }      // first failing shard in file order
+    if (Shard* bad = first_error()) { rc = bad->rc; err = bad->err; }
     if (rc == SIDGPU_OK) {
+        log_fit(m, info, log);
         if (header) out << header << std::endl;
         for (auto& s : shard) {
             out.write(s.csv, (std::streamsize)s.bytes);

@@ -173,6 +173,14 @@ int sidgpu_names(sidgpu_ctx* ctx, const char** d_names, uint64_t* names_bytes);
 int sidgpu_call_host(sidgpu_ctx* ctx, const sidgpu_params* params, const char* h_text, size_t text_len,
                      char* h_csv, size_t csv_cap, uint64_t* csv_bytes, uint64_t* n_sites, uint64_t* n_rows);
 
+/* The two halves of sidgpu_call_host for sessions that keep their sites (bayes, likelihood_ratio, local -R)
+ * when something has to happen between them: several shards of one genome, one ctx each, that share one fit
+ * (sidgpu_histogram / sidgpu_lynch_objective per shard, summed by the host; sidgpu_set_fit; sidgpu_finish or
+ * sidgpu_finish_global).  sidgpu_feed_host: after sidgpu_begin, chunked upload + K1/K3 of a host text.
+ * sidgpu_emit_host: after the finish call, the rows of all stored sites into a host buffer. */
+int sidgpu_feed_host(sidgpu_ctx* ctx, const char* h_text, size_t text_len, uint64_t* n_sites);
+int sidgpu_emit_host(sidgpu_ctx* ctx, char* h_csv, size_t csv_cap, uint64_t* csv_bytes, uint64_t* n_rows);
+
 /* ------------------------------------------------------------------------------------------------
  * K3: unique-profile histogram   (countUniqueProfiles pileup.cpp:169-196,
  *                                 computeNucleotideDistribution pileup.cpp:198-217)

@@ -26,30 +26,34 @@ size_t chunk_end(const char* t, size_t len, size_t start, size_t max_chunk) {
     return fw ? (size_t)((const char*)fw - t) + 1 : len;
 }
 
-}  // namespace
-
-extern "C" int sidgpu_call_host(sidgpu_ctx* ctx, const sidgpu_params* params, const char* h_text, size_t text_len,
-                                char* h_csv, size_t csv_cap, uint64_t* csv_bytes, uint64_t* n_sites, uint64_t* n_rows) {
-    if (!ctx || !params || (text_len && !h_text)) return SIDGPU_EINVAL;
-    CK(cudaSetDevice(ctx->device));
-    HostPath hp {ctx, ctx->hp_text, ctx->hp_csv, ctx->hp_ev_in, ctx->hp_ev_out};
-    for (int i = 0; i < 2; ++i) {
-        if (!hp.ev_in[i]) CK(cudaEventCreateWithFlags(&hp.ev_in[i], cudaEventDisableTiming));
-        if (!hp.ev_out[i]) CK(cudaEventCreateWithFlags(&hp.ev_out[i], cudaEventDisableTiming));
-    }
-    TRY(sidgpu_begin(ctx, params));
-    const size_t max_chunk = ctx->max_chunk;
+// State of one pass of text in / rows out over the ctx's staging buffers.
+struct HostIo {
+    sidgpu_ctx* ctx;
+    HostPath hp;
+    const char* h_text = nullptr;
+    size_t text_len = 0;
+    char* h_csv = nullptr;
+    size_t csv_cap = 0;
     uint64_t total_sites = 0, total_rows = 0, out_off = 0;
     bool out_overflow = false;
 
-    auto upload = [&](int b, size_t start, size_t end) -> int {
+    explicit HostIo(sidgpu_ctx* c) : ctx(c), hp {c, c->hp_text, c->hp_csv, c->hp_ev_in, c->hp_ev_out} {}
+
+    int init() {
+        for (int i = 0; i < 2; ++i) {
+            if (!hp.ev_in[i]) CK(cudaEventCreateWithFlags(&hp.ev_in[i], cudaEventDisableTiming));
+            if (!hp.ev_out[i]) CK(cudaEventCreateWithFlags(&hp.ev_out[i], cudaEventDisableTiming));
+        }
+        return SIDGPU_OK;
+    }
+    int upload(int b, size_t start, size_t end) {
         const size_t n = end - start;
         TRY(ensure(ctx, hp.text[b], ((n + 15) & ~(size_t)15) + 16));
         CK(cudaMemcpyAsync(hp.text[b].p, h_text + start, n, cudaMemcpyHostToDevice, ctx->copy_in));
         CK(cudaEventRecord(hp.ev_in[b], ctx->copy_in));
         return SIDGPU_OK;
-    };
-    auto emit_range = [&](int b, uint64_t site_begin, uint64_t count) -> int {
+    }
+    int emit_range(int b, uint64_t site_begin, uint64_t count) {
         if (count == 0) return SIDGPU_OK;
         CK(cudaEventSynchronize(hp.ev_out[b]));                     // the previous D2H out of csv[b] is done
         uint64_t bytes = 0, rows = 0;
@@ -70,10 +74,11 @@ extern "C" int sidgpu_call_host(sidgpu_ctx* ctx, const sidgpu_params* params, co
         out_off += bytes;
         total_rows += rows;
         return SIDGPU_OK;
-    };
+    }
     // one streamed pass over the text; `emit` says whether rows are produced chunk by chunk
-    auto pass = [&](bool emit) -> int {
+    int pass(bool emit) {
         if (text_len == 0) return SIDGPU_OK;
+        const size_t max_chunk = ctx->max_chunk;
         size_t start = 0, end = chunk_end(h_text, text_len, 0, max_chunk);
         TRY(upload(0, start, end));
         for (int i = 0; start < text_len; ++i) {
@@ -93,30 +98,87 @@ extern "C" int sidgpu_call_host(sidgpu_ctx* ctx, const sidgpu_params* params, co
             end = next_end;
         }
         return SIDGPU_OK;
-    };
+    }
+    // the rows of every stored site, in blocks
+    int emit_store() {
+        const uint64_t step = (uint64_t)8 << 20;                    // sites per emitted block
+        int b = 0;
+        for (uint64_t s = 0; s < ctx->n_sites_total; s += step, b ^= 1) {
+            TRY(emit_range(b, s, std::min<uint64_t>(step, ctx->n_sites_total - s)));
+        }
+        return SIDGPU_OK;
+    }
+    int drain() {
+        CK(cudaStreamSynchronize(ctx->copy_out));
+        CK(cudaStreamSynchronize(ctx->stream));
+        return SIDGPU_OK;
+    }
+};
 
-    const bool streaming = ctx->streaming;
-    if (streaming) {
-        TRY(pass(true));
+}  // namespace
+
+extern "C" int sidgpu_call_host(sidgpu_ctx* ctx, const sidgpu_params* params, const char* h_text, size_t text_len,
+                                char* h_csv, size_t csv_cap, uint64_t* csv_bytes, uint64_t* n_sites, uint64_t* n_rows) {
+    if (!ctx || !params || (text_len && !h_text)) return SIDGPU_EINVAL;
+    CK(cudaSetDevice(ctx->device));
+    HostIo io(ctx);
+    TRY(io.init());
+    io.h_text = h_text;
+    io.text_len = text_len;
+    io.h_csv = h_csv;
+    io.csv_cap = csv_cap;
+    TRY(sidgpu_begin(ctx, params));
+    if (ctx->streaming) {
+        TRY(io.pass(true));
     } else {
-        TRY(pass(false));
+        TRY(io.pass(false));
         TRY(sidgpu_finish(ctx));
         if (params->method == SIDGPU_METHOD_QUALITY) {
-            total_sites = 0;
-            TRY(pass(true));                                        // second pass with the fitted prior
+            io.total_sites = 0;
+            TRY(io.pass(true));                                     // second pass with the fitted prior
         } else {
-            const uint64_t step = (uint64_t)8 << 20;                // sites per emitted block
-            int b = 0;
-            for (uint64_t s = 0; s < ctx->n_sites_total; s += step, b ^= 1) {
-                TRY(emit_range(b, s, std::min<uint64_t>(step, ctx->n_sites_total - s)));
-            }
+            TRY(io.emit_store());
         }
     }
-    CK(cudaStreamSynchronize(ctx->copy_out));
-    CK(cudaStreamSynchronize(ctx->stream));
-    if (csv_bytes) *csv_bytes = out_off;
-    if (n_sites) *n_sites = total_sites;
-    if (n_rows) *n_rows = total_rows;
-    if (out_overflow) return ctx->fail(SIDGPU_ECAPACITY, "CSV needs %llu bytes, buffer has %zu", (unsigned long long)out_off, csv_cap);
+    TRY(io.drain());
+    if (csv_bytes) *csv_bytes = io.out_off;
+    if (n_sites) *n_sites = io.total_sites;
+    if (n_rows) *n_rows = io.total_rows;
+    if (io.out_overflow) return ctx->fail(SIDGPU_ECAPACITY, "CSV needs %llu bytes, buffer has %zu", (unsigned long long)io.out_off, csv_cap);
+    return SIDGPU_OK;
+}
+
+// The two halves of the above for sessions that keep their sites (bayes, likelihood_ratio, local -R) and are
+// driven from outside between them: several shards of one genome that share a fit (host/sid_host.cpp).
+extern "C" int sidgpu_feed_host(sidgpu_ctx* ctx, const char* h_text, size_t text_len, uint64_t* n_sites) {
+    if (!ctx || (text_len && !h_text)) return SIDGPU_EINVAL;
+    if (ctx->phase != PHASE_FEED) return ctx->fail(SIDGPU_ESTATE, "sidgpu_feed_host outside a session");
+    if (ctx->streaming || ctx->params.method == SIDGPU_METHOD_QUALITY)
+        return ctx->fail(SIDGPU_EINVAL, "sidgpu_feed_host is for sessions that keep their sites; use sidgpu_call_host");
+    CK(cudaSetDevice(ctx->device));
+    HostIo io(ctx);
+    TRY(io.init());
+    io.h_text = h_text;
+    io.text_len = text_len;
+    TRY(io.pass(false));
+    TRY(io.drain());
+    if (n_sites) *n_sites = io.total_sites;
+    return SIDGPU_OK;
+}
+
+extern "C" int sidgpu_emit_host(sidgpu_ctx* ctx, char* h_csv, size_t csv_cap, uint64_t* csv_bytes, uint64_t* n_rows) {
+    if (!ctx) return SIDGPU_EINVAL;
+    if (ctx->phase != PHASE_FINISHED || ctx->streaming || ctx->params.method == SIDGPU_METHOD_QUALITY)
+        return ctx->fail(SIDGPU_ESTATE, "sidgpu_emit_host needs a finished session that kept its sites");
+    CK(cudaSetDevice(ctx->device));
+    HostIo io(ctx);
+    TRY(io.init());
+    io.h_csv = h_csv;
+    io.csv_cap = csv_cap;
+    TRY(io.emit_store());
+    TRY(io.drain());
+    if (csv_bytes) *csv_bytes = io.out_off;
+    if (n_rows) *n_rows = io.total_rows;
+    if (io.out_overflow) return ctx->fail(SIDGPU_ECAPACITY, "CSV needs %llu bytes, buffer has %zu", (unsigned long long)io.out_off, csv_cap);
     return SIDGPU_OK;
 }

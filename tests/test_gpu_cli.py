@@ -86,6 +86,25 @@ def test_cli_position_shards(sid_bin, devices):
     assert rc in (-6, 134) and out == b"" and "Malformed pileup line" in err
 
 
+@pytest.mark.parametrize("flags", [["-m", "bayes"], ["-m", "likelihood_ratio"], ["-m", "likelihood_ratio", "-R"], ["-m", "local", "-R"]],
+                         ids=lambda f: "_".join(f))
+def test_cli_position_shards_share_the_fit(sid_bin, flags):
+    """--devices with the methods that fit (pi, eps) genome-wide: three shards, one fit (the host sums the shards'
+    nucleotide counts and objective values), BH over the merged unique profiles; rows and stderr lines as the reference."""
+    for name in ("depth30.plp", "edge.plp"):
+        case = [c for c in MANIFEST["cases"] if c["input"] == name and c["flags"] == flags][0]
+        rc, out, err = run(sid_bin, "--devices", "0,0,0", *flags, os.path.join(GOLDEN, name))
+        assert rc == 0, err
+        n, diffs = op.compare_csv(out, read(case["csv"]))
+        assert diffs <= max(2, n // 1000)
+        if "heterozygosity" in case:
+            assert "# unique profiles: %d" % case["unique_profiles"] in err
+            m = re.search(r"# heterozygosity: (\S+)", err)
+            assert m and abs(float(m.group(1)) - case["heterozygosity"]) <= 2e-4 * case["heterozygosity"]
+            m = re.search(r"# error: (\S+)", err)
+            assert m and abs(float(m.group(1)) - case["error"]) <= 2e-4 * case["error"]
+
+
 def test_cli_error_behaviour(sid_bin):
     # malformed line: the reference terminates on std::invalid_argument (SIGABRT), nothing on stdout
     rc, out, err = run(sid_bin, os.path.join(GOLDEN, "malformed_too_few_columns.plp"))
