@@ -64,7 +64,7 @@ void sidSetDevice(int device, size_t max_chunk_bytes = 0);
 // of the text) per device, rows written in shard order.  `local` and `quality` without -R need
 // no exchange between shards.  The methods with a genome-wide fit share it: the host sums the shards' integer
 // nucleotide counts and, per optimiser step, their objective values (one double each), and merges their
-// unique-profile lists for the BH ranks of likelihood_ratio.  (`quality -R` is not sharded: two text passes.)
+// unique-profile lists for the BH ranks of likelihood_ratio.
 SidRunInfo sidCallToStreamSharded(const std::string& method, const char* text, size_t len, bool estimate_prior, double prior,
                                   double error_threshold, double significance_level, const std::vector<int>& devices, std::ostream& out,
                                   std::ostream& log, const char* header = nullptr);

@@ -285,8 +285,6 @@ SidRunInfo sidCallToStreamSharded(const std::string& method, const char* text, s
         if (header) out << header << std::endl;
         return info;
     }
-    if (m == SIDGPU_METHOD_QUALITY && estimate_prior)
-        throw std::runtime_error("several devices: -m quality -R needs two passes over the text and is not sharded here");
     const size_t n = devices.size();
     if (n == 0) throw std::runtime_error("no devices given");
     const bool streams = (m == SIDGPU_METHOD_LOCAL || m == SIDGPU_METHOD_QUALITY) && !estimate_prior;
@@ -392,11 +390,14 @@ SidRunInfo sidCallToStreamSharded(const std::string& method, const char* text, s
             }
         }
         // ---- classification with the shared fit, rows out
-        on_every_shard(shard, [&](size_t, Shard& s) {
+        on_every_shard(shard, [&](size_t k, Shard& s) {
             int rc = m == SIDGPU_METHOD_LIKELIHOOD_RATIO ? sidgpu_finish_global(s.h, merged.data(), merged.size()) : sidgpu_finish(s.h);
             size_t cap = (size_t)s.sites * 48 + 4096;
             while (rc == SIDGPU_OK) {
                 if (!alloc_csv(s, cap)) return;
+                if (m == SIDGPU_METHOD_QUALITY)     // quality -R keeps no sites: its second pass over the shard's text
+                    rc = sidgpu_stream_host(s.h, text + cut[k], cut[k + 1] - cut[k], s.csv, s.cap, &s.bytes, &s.sites, &s.rows);
+                else
                 rc = sidgpu_emit_host(s.h, s.csv, s.cap, &s.bytes, &s.rows);
                 if (rc == SIDGPU_ECAPACITY && s.bytes > s.cap) { cap = s.bytes + 4096; rc = SIDGPU_OK; continue; }
                 break;

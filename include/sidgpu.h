@@ -180,6 +180,10 @@ int sidgpu_call_host(sidgpu_ctx* ctx, const sidgpu_params* params, const char* h
  * sidgpu_emit_host: after the finish call, the rows of all stored sites into a host buffer. */
 int sidgpu_feed_host(sidgpu_ctx* ctx, const char* h_text, size_t text_len, uint64_t* n_sites);
 int sidgpu_emit_host(sidgpu_ctx* ctx, char* h_csv, size_t csv_cap, uint64_t* csv_bytes, uint64_t* n_rows);
+/* Text in, rows out chunk by chunk on an open session: the second pass of `quality -R` (its sites are not kept;
+ * call it with the same text after sidgpu_finish), or a streaming session (local / quality without -R). */
+int sidgpu_stream_host(sidgpu_ctx* ctx, const char* h_text, size_t text_len, char* h_csv, size_t csv_cap,
+                       uint64_t* csv_bytes, uint64_t* n_sites, uint64_t* n_rows);
 
 /* ------------------------------------------------------------------------------------------------
  * K3: unique-profile histogram   (countUniqueProfiles pileup.cpp:169-196,

@@ -67,6 +67,8 @@ PROTOTYPES = {
     "sidgpu_emit_csv": (ctypes.c_int, [ctypes.c_void_p, c_u64, c_u64, ctypes.c_void_p, ctypes.c_size_t, c_u64_p, c_u64_p]),
     "sidgpu_feed_host": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.POINTER(c_u64)]),
     "sidgpu_emit_host": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.POINTER(c_u64), ctypes.POINTER(c_u64)]),
+    "sidgpu_stream_host": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t,
+                                          ctypes.POINTER(c_u64), ctypes.POINTER(c_u64), ctypes.POINTER(c_u64)]),
     "sidgpu_emit_columns": (ctypes.c_int, [ctypes.c_void_p, c_u64, c_u64, ctypes.POINTER(Columns)]),
     "sidgpu_names": (ctypes.c_int, [ctypes.c_void_p, c_void_pp, ctypes.POINTER(c_u64)]),
     "sidgpu_emit_records": (ctypes.c_int, [ctypes.c_void_p, c_u64, c_u64, ctypes.c_void_p, ctypes.c_void_p,

@@ -153,8 +153,7 @@ extern "C" int sidgpu_call_host(sidgpu_ctx* ctx, const sidgpu_params* params, co
 extern "C" int sidgpu_feed_host(sidgpu_ctx* ctx, const char* h_text, size_t text_len, uint64_t* n_sites) {
     if (!ctx || (text_len && !h_text)) return SIDGPU_EINVAL;
     if (ctx->phase != PHASE_FEED) return ctx->fail(SIDGPU_ESTATE, "sidgpu_feed_host outside a session");
-    if (ctx->streaming || ctx->params.method == SIDGPU_METHOD_QUALITY)
-        return ctx->fail(SIDGPU_EINVAL, "sidgpu_feed_host is for sessions that keep their sites; use sidgpu_call_host");
+    if (ctx->streaming) return ctx->fail(SIDGPU_EINVAL, "sidgpu_feed_host is for sessions with a genome-wide fit; use sidgpu_call_host");
     CK(cudaSetDevice(ctx->device));
     HostIo io(ctx);
     TRY(io.init());
@@ -166,10 +165,34 @@ extern "C" int sidgpu_feed_host(sidgpu_ctx* ctx, const char* h_text, size_t text
     return SIDGPU_OK;
 }
 
+// Text in, rows out chunk by chunk on an open session: a streaming session (local / quality without -R), or the
+// second pass of `quality -R` after sidgpu_finish (the first pass, sidgpu_feed_host, only built the histogram).
+extern "C" int sidgpu_stream_host(sidgpu_ctx* ctx, const char* h_text, size_t text_len, char* h_csv, size_t csv_cap,
+                                  uint64_t* csv_bytes, uint64_t* n_sites, uint64_t* n_rows) {
+    if (!ctx || (text_len && !h_text)) return SIDGPU_EINVAL;
+    const bool second_pass = ctx->phase == PHASE_FINISHED && ctx->params.method == SIDGPU_METHOD_QUALITY;
+    if (!((ctx->streaming && ctx->phase == PHASE_FEED) || second_pass))
+        return ctx->fail(SIDGPU_ESTATE, "sidgpu_stream_host needs a streaming session or the second pass of quality -R");
+    CK(cudaSetDevice(ctx->device));
+    HostIo io(ctx);
+    TRY(io.init());
+    io.h_text = h_text;
+    io.text_len = text_len;
+    io.h_csv = h_csv;
+    io.csv_cap = csv_cap;
+    TRY(io.pass(true));
+    TRY(io.drain());
+    if (csv_bytes) *csv_bytes = io.out_off;
+    if (n_sites) *n_sites = io.total_sites;
+    if (n_rows) *n_rows = io.total_rows;
+    if (io.out_overflow) return ctx->fail(SIDGPU_ECAPACITY, "CSV needs %llu bytes, buffer has %zu", (unsigned long long)io.out_off, csv_cap);
+    return SIDGPU_OK;
+}
+
 extern "C" int sidgpu_emit_host(sidgpu_ctx* ctx, char* h_csv, size_t csv_cap, uint64_t* csv_bytes, uint64_t* n_rows) {
     if (!ctx) return SIDGPU_EINVAL;
     if (ctx->phase != PHASE_FINISHED || ctx->streaming || ctx->params.method == SIDGPU_METHOD_QUALITY)
-        return ctx->fail(SIDGPU_ESTATE, "sidgpu_emit_host needs a finished session that kept its sites");
+        return ctx->fail(SIDGPU_ESTATE, "sidgpu_emit_host needs a finished session that kept its sites (quality -R: sidgpu_stream_host)");
     CK(cudaSetDevice(ctx->device));
     HostIo io(ctx);
     TRY(io.init());

@@ -86,6 +86,15 @@ def test_cli_position_shards(sid_bin, devices):
     assert rc in (-6, 134) and out == b"" and "Malformed pileup line" in err
 
 
+def test_cli_position_shards_quality_with_estimated_prior(sid_bin):
+    """quality -R over three shards: first pass for the shared fit, second pass with the fitted prior."""
+    case = [c for c in MANIFEST["cases"] if c["input"] == "quality30.plp" and c["flags"] == ["-m", "quality", "-R"]][0]
+    rc, out, err = run(sid_bin, "--devices", "0,0,0", "-m", "quality", "-R", os.path.join(GOLDEN, "quality30.plp"))
+    assert rc == 0, err
+    n, diffs = op.compare_csv(out, read(case["csv"]))
+    assert diffs <= max(2, n // 1000)
+
+
 @pytest.mark.parametrize("flags", [["-m", "bayes"], ["-m", "likelihood_ratio"], ["-m", "likelihood_ratio", "-R"], ["-m", "local", "-R"]],
                          ids=lambda f: "_".join(f))
 def test_cli_position_shards_share_the_fit(sid_bin, flags):
