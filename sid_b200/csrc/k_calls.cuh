@@ -73,9 +73,12 @@ __global__ void __launch_bounds__(128) k_classify(const ClassifyParams p) {
 // waiting for memory or for its predecessors does not hold up the others.
 constexpr int CSV_THREADS = 256;
 constexpr int CSV_WARPS = CSV_THREADS / 32;
-constexpr int CSV_PER_THREAD = 4;
+#ifndef SID_CSV_PER_THREAD
+#define SID_CSV_PER_THREAD 4
+#endif
+constexpr int CSV_PER_THREAD = SID_CSV_PER_THREAD;
 constexpr int CSV_TILE = 32 * CSV_PER_THREAD;     // sites per warp tile
-constexpr int CSV_WSTAGE = 6912;                  // bytes of rows a warp may stage (else: direct global writes)
+constexpr int CSV_WSTAGE = 1728 * CSV_PER_THREAD; // bytes of rows a warp may stage (else: direct global writes)
 constexpr int CSV_STAGE = CSV_WARPS * CSV_WSTAGE;
 
 struct CsvParams {
@@ -135,7 +138,10 @@ __device__ __forceinline__ unsigned long long csv_look_back(const CsvParams& p, 
     return base;
 }
 
-__global__ void __launch_bounds__(CSV_THREADS, 4) k_csv(const CsvParams p) {
+#ifndef SID_CSV_CTAS
+#define SID_CSV_CTAS 3      // register budget: 3 CTAs per SM (72 registers used, 24 warps) beat 4 (64 registers, 32 warps): 0.65 vs 0.69 ms
+#endif
+__global__ void __launch_bounds__(CSV_THREADS, SID_CSV_CTAS) k_csv(const CsvParams p) {
     extern __shared__ __align__(16) char s_stage_all[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     char* s_stage = s_stage_all + warp * CSV_WSTAGE;
@@ -152,9 +158,12 @@ __global__ void __launch_bounds__(CSV_THREADS, 4) k_csv(const CsvParams p) {
         for (int k = 0; k < CSV_PER_THREAD; ++k) ord[k] = 0xFFFFFFFFu;
         if (first < p.n_sites) {
             const uint32_t* src = p.order + p.site_begin + first;
-            if (first + CSV_PER_THREAD <= p.n_sites && ((uintptr_t)src & 15u) == 0) {
-                const uint4 v = __ldg(reinterpret_cast<const uint4*>(src));
-                ord[0] = v.x; ord[1] = v.y; ord[2] = v.z; ord[3] = v.w;
+            if (CSV_PER_THREAD % 4 == 0 && first + CSV_PER_THREAD <= p.n_sites && ((uintptr_t)src & 15u) == 0) {
+#pragma unroll
+                for (int k = 0; k < CSV_PER_THREAD / 4; ++k) {
+                    const uint4 v = __ldg(reinterpret_cast<const uint4*>(src) + k);
+                    ord[4 * k] = v.x; ord[4 * k + 1] = v.y; ord[4 * k + 2] = v.z; ord[4 * k + 3] = v.w;
+                }
             } else {
 #pragma unroll
                 for (int k = 0; k < CSV_PER_THREAD; ++k) if (first + k < p.n_sites) ord[k] = __ldg(src + k);
