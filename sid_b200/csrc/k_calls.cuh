@@ -71,7 +71,10 @@ __global__ void __launch_bounds__(128) k_classify(const ClassifyParams p) {
 // and finds its byte offset with a warp-wide decoupled look-back, assembles the rows in its private
 // piece of shared memory and copies them out with aligned 16-byte stores.  No CTA-wide barrier: a warp
 // waiting for memory or for its predecessors does not hold up the others.
-constexpr int CSV_THREADS = 256;
+#ifndef SID_CSV_THREADS
+#define SID_CSV_THREADS 128     // 4 warps per CTA: at 72 registers 7 CTAs = 28 warps fit an SM (256 threads: 3 CTAs = 24 warps)
+#endif
+constexpr int CSV_THREADS = SID_CSV_THREADS;
 constexpr int CSV_WARPS = CSV_THREADS / 32;
 #ifndef SID_CSV_PER_THREAD
 #define SID_CSV_PER_THREAD 4
@@ -139,7 +142,8 @@ __device__ __forceinline__ unsigned long long csv_look_back(const CsvParams& p, 
 }
 
 #ifndef SID_CSV_CTAS
-#define SID_CSV_CTAS 3      // register budget: 3 CTAs per SM (72 registers used, 24 warps) beat 4 (64 registers, 32 warps): 0.65 vs 0.69 ms
+#define SID_CSV_CTAS 3      // minimum CTAs per SM for the register allocator: loose on purpose.  A 64-register cap (32 warps per
+                            // SM) costs more than the extra warps bring: 0.69 ms against 0.61 ms at 72 registers and 28 warps
 #endif
 __global__ void __launch_bounds__(CSV_THREADS, SID_CSV_CTAS) k_csv(const CsvParams p) {
     extern __shared__ __align__(16) char s_stage_all[];
