@@ -164,7 +164,9 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f80", "data": "synthetic",
-        "config": {"workload": workload_name(args), "note": "reference is single-threaded: one process per host core, one slice each"},
+        "config": {"workload": workload_name(args) + "; SAMPLED on %d x %d sites per step (one reference process per host core)" % (cores, per_proc),
+                   "note": "reference is single-threaded and needs 406 B of RAM per site: one process per host core, one slice each; "
+                           "the same host run at every --gpus N"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }

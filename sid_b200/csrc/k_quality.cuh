@@ -30,6 +30,11 @@ struct QualityParams {
     int het_only;               // rows of hom sites get length 0
     char* site_suffix;          // SUFFIX_BYTES per site
     unsigned long long* error;
+    // optional per-site records (OutputRecord, call.hpp:14-27) in file order, index i - site_begin
+    uint8_t* rec_label;
+    char* rec_gt;
+    double* rec_hom;
+    double* rec_het;
 };
 
 SID_HD uint32_t phred_of(uint8_t c) {                    // parseQualities pileup.cpp:158-163
@@ -38,11 +43,13 @@ SID_HD uint32_t phred_of(uint8_t c) {                    // parseQualities pileu
 }
 
 // The bases field walked once more for the order of the counted bases (parseReadBases pileup.cpp:70-153
-// without the counters): 0..3 = A C G T, 4 = '.' or ',', -1 = nothing counted.
+// without the counters): 0..3 = A C G T, -1 = nothing counted.  '.' / ',' are replaced by toupper / tolower of
+// the reference character before they are looked at (pileup.cpp:78-83).
 struct BasesWalk {
     uint64_t skip, num;
     int mode;                // 0 normal, 1 just saw '+'/'-', 2 reading the indel length
-    SID_HD void init() { skip = 0; num = 0; mode = 0; }
+    uint8_t dot_as, comma_as;
+    SID_HD void init(uint8_t ref) { skip = 0; num = 0; mode = 0; dot_as = ascii_upper(ref); comma_as = ascii_lower(ref); }
     SID_HD int feed(uint8_t c) {
         if (mode) {
             const uint32_t d = (uint32_t)c - (uint32_t)'0';
@@ -54,14 +61,15 @@ struct BasesWalk {
             mode = 0;                           // pileup.cpp:131-133: a sign without digits is ignored
         }
         if (skip) { --skip; return -1; }
+        c = c == '.' ? dot_as : c;
+        c = c == ',' ? comma_as : c;
         // no switch: the lanes of a warp look at different characters, selects keep them together
-        const uint32_t u = (uint32_t)c | 0x20u;                       // letters to lower case; '.' ',' '+' '-' unchanged
+        const uint32_t u = (uint32_t)c | 0x20u;                       // letters to lower case; '+' '-' unchanged, '^' -> '~'
         int r = -1;
         r = u == 'a' ? 0 : r;
         r = u == 'c' ? 1 : r;
         r = u == 'g' ? 2 : r;
         r = u == 't' ? 3 : r;
-        r = (c == '.' || c == ',') ? 4 : r;
         skip = c == '^' ? 1 : 0;                                      // pileup.cpp:125-127 (skip was 0 here)
         mode = (c == '+' || c == '-') ? 1 : 0;                        // (mode was 0 here)
         return r;
@@ -76,7 +84,6 @@ SID_HD CallResult call_quality(const uint8_t* text, uint64_t line_abs, const Par
                                double alpha) {
     int ref0, ref1;
     major_alleles(pl.profile, ref0, ref1);                // call.cpp:311-319
-    const int ri = ref_index((uint8_t)pl.ref);
     // sums of per-read terms: eight plain additions at a time, the blocks added with compensation (in place of
     // the reference's x87 long double accumulation)
     CompSum lh, lt;
@@ -84,14 +91,13 @@ SID_HD CallResult call_quality(const uint8_t* text, uint64_t line_abs, const Par
     lt.init();
     double bh = 0, bt = 0;
     BasesWalk b;
-    b.init();
+    b.init((uint8_t)pl.ref);
     uint32_t j = 0;
     const uint8_t* bases = text + line_abs + pl.bases_off;
     const uint8_t* bq = text + line_abs + pl.bq_off;
     const uint8_t* mq = text + line_abs + pl.mq_off;
     for (uint32_t i = 0; i < pl.bases_len; ++i) {
-        int r = b.feed(bases[i]);
-        if (r == 4) r = ri;                               // '.' / ',' stand for the reference base
+        const int r = b.feed(bases[i]);                  // '.' / ',' stand for the reference character
         if (r < 0) continue;
         const uint32_t q1 = phred_of(bq[j]), q2 = phred_of(mq[j]);
         const uint32_t q = q1 < q2 ? q1 : q2;             // call.cpp:330
@@ -135,6 +141,10 @@ __global__ void __launch_bounds__(QUAL_THREADS) k_quality(const QualityParams p)
         return;
     }
     const CallResult r = call_quality(p.text, line_abs, pl, p.lut, p.prior, p.alpha);
+    if (p.rec_label) p.rec_label[i] = r.label;
+    if (p.rec_gt) { p.rec_gt[2 * i] = r.gt0; p.rec_gt[2 * i + 1] = r.gt1; }
+    if (p.rec_hom) p.rec_hom[i] = r.hom;
+    if (p.rec_het) p.rec_het[i] = r.het;
     char buf[SUFFIX_BYTES];
     const int n = (p.het_only && r.label != 1) ? 0 : format_suffix(r, false, buf);
     for (int k = 0; k < n; ++k) dst[k] = buf[k];

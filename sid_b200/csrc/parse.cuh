@@ -61,15 +61,25 @@ struct AtoiState {
     }
 };
 
-// Bases state machine, one byte at a time (pileup.cpp:76-150).
+// toupper / tolower of the "C" locale (pileup.cpp:79,82 run under it: the reference never calls setlocale).
+SID_HD uint8_t ascii_upper(uint8_t c) { return (c >= 'a' && c <= 'z') ? (uint8_t)(c - 32) : c; }
+SID_HD uint8_t ascii_lower(uint8_t c) { return (c >= 'A' && c <= 'Z') ? (uint8_t)(c + 32) : c; }
+
+// Bases state machine, one byte at a time (pileup.cpp:76-150).  '.' and ',' are replaced by
+// toupper / tolower of the reference character BEFORE the switch (pileup.cpp:78-83), so a reference
+// column of '^', '+' or '-' turns every '.' into that control character; the digit look-ahead of an
+// indel (pileup.cpp:131,136) reads the raw text.
 struct BasesState {
     uint32_t cnt[4];
-    uint32_t dots, commas;   // '.' and ',' are attributed to the reference base at the end
     uint64_t skip;           // bytes still to be skipped ('^' -> 1, indel -> N)
     uint64_t num;            // indel length being read
     int mode;                // 0 normal, 1 just saw '+'/'-', 2 reading the indel length
-    SID_HD void init() { cnt[0] = cnt[1] = cnt[2] = cnt[3] = 0; dots = commas = 0; skip = 0; num = 0; mode = 0; }
-    // returns the index 0..3 of the counted base, 4 for '.', 5 for ',', -1 when nothing is counted
+    uint8_t dot_as, comma_as;
+    SID_HD void init(uint8_t ref) {
+        cnt[0] = cnt[1] = cnt[2] = cnt[3] = 0; skip = 0; num = 0; mode = 0;
+        dot_as = ascii_upper(ref); comma_as = ascii_lower(ref);
+    }
+    // returns the index 0..3 of the counted base, -1 when nothing is counted
     SID_HD int feed(uint8_t c) {
         if (mode == 1) {                        // pileup.cpp:131-133: sign not followed by a digit is ignored
             uint32_t d = (uint32_t)c - (uint32_t)'0';
@@ -82,19 +92,22 @@ struct BasesState {
             skip = num;                         // pileup.cpp:144: skip that many bytes after the number
         }
         if (skip) { --skip; return -1; }
+        if (c == '.') c = dot_as; else if (c == ',') c = comma_as;    // pileup.cpp:78-83
         switch (c) {
             case 'A': case 'a': ++cnt[0]; return 0;
             case 'C': case 'c': ++cnt[1]; return 1;
             case 'G': case 'g': ++cnt[2]; return 2;
             case 'T': case 't': ++cnt[3]; return 3;
-            case '.': ++dots; return 4;
-            case ',': ++commas; return 5;
             case '^': skip = 1; return -1;      // pileup.cpp:125-127
             case '+': case '-': mode = 1; return -1;
             default: return -1;
         }
     }
 };
+
+// Reference characters for which '.' / ',' become control characters of the bases grammar: the
+// bit-parallel tokenizer leaves such lines to the byte-wise state machine.
+SID_HD bool ref_is_control(uint8_t ref) { return ref == '^' || ref == '+' || ref == '-'; }
 
 // Index of the reference base for '.' (toupper) and ',' (tolower) substitution, or -1 when the
 // substituted character is not one of ACGTacgt (pileup.cpp:78-83 then the switch default).
@@ -147,14 +160,11 @@ SID_HD void parse_line(const Src& src, uint64_t p, bool want_qual, ParsedLine& o
     if (is_eol(c)) return;
     o.bases_off = (uint32_t)(q - p);
     BasesState b;
-    b.init();
+    b.init((uint8_t)o.ref);
     while (!is_delim(c) && !is_eol(c)) { b.feed(c); c = src.at(++q); }
     o.bases_len = (uint32_t)(q - p) - o.bases_off;
-    const int ri = ref_index((uint8_t)o.ref);
-    uint32_t cnt[4] = {b.cnt[0], b.cnt[1], b.cnt[2], b.cnt[3]};
-    if (ri >= 0) cnt[ri] += b.dots + b.commas;
-    o.profile = pack_profile(cnt[0], cnt[1], cnt[2], cnt[3]);
-    o.n_bases = b.cnt[0] + b.cnt[1] + b.cnt[2] + b.cnt[3] + (ri >= 0 ? b.dots + b.commas : 0);
+    o.profile = pack_profile(b.cnt[0], b.cnt[1], b.cnt[2], b.cnt[3]);
+    o.n_bases = b.cnt[0] + b.cnt[1] + b.cnt[2] + b.cnt[3];
     if (!want_qual) { o.status = LINE_OK; return; }
     // token 5: base qualities (pileup.cpp:49-57; the reference dereferences NULL when it is missing)
     while (is_delim(c)) c = src.at(++q);

@@ -177,6 +177,7 @@ SID_HD bool parse_line_bits(const uint8_t* s, uint32_t avail, uint32_t region_of
     o.chrom_off = 0;
     o.chrom_len = q1;
     const uint32_t ref = s[h0 + q2 + 1];
+    ok = ok && !ref_is_control((uint8_t)ref);               // '.' / ',' would become '^', '+' or '-' (pileup.cpp:78-83)
     // ---- position: the (up to) eight characters before the second separator, leading ones forced to '0'
     uint32_t acc;
     {

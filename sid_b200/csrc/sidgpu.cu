@@ -327,6 +327,15 @@ int grow_table(sidgpu_ctx* ctx, int shift, uint64_t stored_sites) {
     return SIDGPU_OK;
 }
 
+// Forgets the interned chromosome names (and a reported overflow): every session starts with an empty dictionary.
+int reset_names(sidgpu_ctx* ctx) {
+    CK(cudaMemsetAsync(ctx->names.slots, 0, ((size_t)ctx->names.mask + 1) * 8, ctx->stream));
+    const unsigned int four = 4;             // pool offsets start at 4: 0 means "no name"
+    CK(cudaMemcpyAsync(ctx->names.cursor, &four, sizeof four, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemsetAsync(ctx->names.overflow, 0, sizeof(unsigned int), ctx->stream));
+    return SIDGPU_OK;
+}
+
 int reset_table(sidgpu_ctx* ctx) {
     const size_t n = (size_t)ctx->tab.cap + 1;
     CK(cudaMemsetAsync(ctx->tab.keys, 0xFF, n * 8, ctx->stream));
@@ -377,7 +386,7 @@ int run_tokenizer(sidgpu_ctx* ctx, const char* d_text, size_t text_len, size_t r
     if (((uintptr_t)d_text & 15) != 0) return ctx->fail(SIDGPU_EINVAL, "d_text must be 16-byte aligned");
     if (range_begin > range_end || range_end > text_len) return ctx->fail(SIDGPU_EINVAL, "bad range [%zu,%zu) for text of %zu bytes", range_begin, range_end, text_len);
     *n_out = 0;
-    if (range_begin == range_end) return SIDGPU_OK;
+    if (range_begin == range_end) return sync_ctl(ctx);      // callers read the host mirror of the control block afterwards
     const uint64_t tile0 = range_begin & ~(uint64_t)15;
     const uint64_t span = range_end - tile0;
     // a slice (one parse warp's share of a tile) should hold about 30 lines: 32 lanes, little overflow
@@ -695,7 +704,8 @@ bool method_streams(const sidgpu_params& p) {
     return (p.method == SIDGPU_METHOD_LOCAL || p.method == SIDGPU_METHOD_QUALITY) && !p.estimate_prior;
 }
 
-int quality_rows(sidgpu_ctx* ctx, uint64_t site_begin, uint64_t n) {
+int quality_rows(sidgpu_ctx* ctx, uint64_t site_begin, uint64_t n, uint8_t* rec_label = nullptr, char* rec_gt = nullptr,
+                 double* rec_hom = nullptr, double* rec_het = nullptr) {
     if (!ctx->last_text) return ctx->fail(SIDGPU_ESTATE, "quality needs the text of the chunk: feed before emit");
     if (n == 0) return SIDGPU_OK;
     QualityParams q {};
@@ -712,6 +722,10 @@ int quality_rows(sidgpu_ctx* ctx, uint64_t site_begin, uint64_t n) {
     q.het_only = ctx->params.het_only;
     q.site_suffix = (char*)ctx->site_suffix.p;
     q.error = ctl_field(ctx, &Control::error);
+    q.rec_label = rec_label;
+    q.rec_gt = rec_gt;
+    q.rec_hom = rec_hom;
+    q.rec_het = rec_het;
     CK(cudaMemsetAsync(ctl_field(ctx, &Control::error), 0xFF, sizeof(unsigned long long), ctx->stream));
     k_quality<<<(unsigned)((n + QUAL_THREADS - 1) / QUAL_THREADS), QUAL_THREADS, 0, ctx->stream>>>(q);
     return check_launch(ctx, "k_quality");
@@ -917,6 +931,7 @@ int sidgpu_tokenize(sidgpu_ctx* ctx, const char* d_text, size_t text_len, size_t
     ctx->want_profile = true;
     ctx->want_line_off = want_qual != 0;
     TRY(reset_table(ctx));
+    TRY(reset_names(ctx));
     uint64_t n = 0;
     TRY(run_tokenizer(ctx, d_text, text_len, range_begin, range_end, want_qual != 0, true, 0, false, &n, true));
     ctx->n_sites_total = n;
@@ -970,6 +985,7 @@ int sidgpu_begin(sidgpu_ctx* ctx, const sidgpu_params* params) {
     ctx->chunk_begin = ctx->chunk_sites = 0;
     ctx->last_text = nullptr;
     TRY(reset_table(ctx));
+    TRY(reset_names(ctx));
     ctx->phase = PHASE_FEED;
     return SIDGPU_OK;
 }
@@ -1156,10 +1172,21 @@ int sidgpu_emit_records(sidgpu_ctx* ctx, uint64_t site_begin, uint64_t n_sites, 
     if (!ctx) return SIDGPU_EINVAL;
     if (ctx->phase == PHASE_IDLE) return ctx->fail(SIDGPU_ESTATE, "sidgpu_emit_records outside a session");
     if (!ctx->streaming && ctx->phase != PHASE_FINISHED) return ctx->fail(SIDGPU_ESTATE, "this method needs sidgpu_finish first");
-    if (ctx->params.method == SIDGPU_METHOD_QUALITY) return ctx->fail(SIDGPU_EINVAL, "quality results are per site: use sidgpu_emit_csv");
     if (site_begin + n_sites > ctx->n_sites_total) return ctx->fail(SIDGPU_EINVAL, "site range not in the store");
     if (n_sites == 0) return SIDGPU_OK;
     CK(cudaSetDevice(ctx->device));
+    if (ctx->params.method == SIDGPU_METHOD_QUALITY) {
+        // per-site results (call.cpp:309-370): the quality kernel writes them beside the row text
+        TRY(quality_rows(ctx, site_begin, n_sites, d_label, d_gt, d_hom, d_het));
+        TRY(sync_ctl(ctx));
+        if (ctx->h_ctl->error != ~0ull) {
+            const int st = (int)(ctx->h_ctl->error & 7);
+            const int code = st == LINE_MISSING_MAPQ ? SIDGPU_EMISSING_MAPQ : st == LINE_QUAL_SHORT ? SIDGPU_EQUAL_SHORT
+                             : st == LINE_MALFORMED ? SIDGPU_EMALFORMED : SIDGPU_EINTERNAL;
+            return ctx->fail(code, "%s (line starting at byte %llu)", status_text(st), ctx->h_ctl->error >> 3);
+        }
+        return SIDGPU_OK;
+    }
     RecordParams p {site_begin, n_sites, (const uint32_t*)ctx->order.p, (const uint32_t*)ctx->slot.p, ctx->tab, d_label, d_gt, d_hom, d_het,
                     nullptr, nullptr, nullptr, nullptr};
     k_records<<<(unsigned)((n_sites + 255) / 256), 256, 0, ctx->stream>>>(p);

@@ -104,6 +104,7 @@ __device__ __forceinline__ bool name_equals(const NameDict& d, uint32_t pool_off
 template <class Src>
 __device__ __forceinline__ uint32_t name_intern(const NameDict& d, const Src& src, uint64_t off, uint32_t len) {
     if (len > 0xFFFFu) { atomicExch(d.overflow, 2u); return 0; }
+    if (*((volatile unsigned int*)d.overflow)) return 0;      // full: the host reports it; do not advance the cursor further
     const uint64_t hv = name_hash(src, off, len);
     const uint32_t tag = (uint32_t)(hv >> 48) & 0xFFFFu;
     uint32_t h = (uint32_t)hv & d.mask;

@@ -112,6 +112,7 @@ def call_sharded(ctx, d_text, text_len, rank, world, params, dist=None, device=N
 
         def local_objective(nd, pi, eps):
             ctx.lynch_objective_partial(nd, pi, eps, obj.data_ptr())
+            ctx.synchronize()       # the kernel ran on the ctx's stream, the all-reduce runs on torch's: order them
             return obj
 
         fit = distributed_fit(lambda: sums, local_objective, ints, flt)

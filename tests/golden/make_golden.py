@@ -59,6 +59,14 @@ EDGE = [
     "chrX\t33\tA\t1\t*\tI",
     "chrX\t34\tA\t70000\t" + "." * 70000 + "\t" + "I" * 70000,
     "chrY\t35\tG\t7\t.,.,AAt\tIIIIIII",
+    # pileup.cpp:78-83 substitutes '.' / ',' by the reference character BEFORE the switch: with '^' every '.' eats
+    # the next byte, with '+' / '-' it starts an indel when a digit follows
+    "chrY\t36\t^\t4\t.A.C\tIIII",
+    "chrY\t37\t^\t6\t,AC.GT.\tIIIIII",
+    "chrY\t38\t+\t6\t.2ACGT,1AC\tIIIIII",
+    "chrY\t39\t-\t6\tA.1CG,TT.x\tIIIIII",
+    "chrY\t40\t+\t5\t..3ACGTA\tIIIII",
+    "chrY\t41\t-\t5\tAC,GT.\tIIIII",
 ]
 
 QUAL_EDGE = [
@@ -68,6 +76,9 @@ QUAL_EDGE = [
     "chr19\t1340\tA\t6\t^].,$.+2AC,-3acgT\tIIIIII\t]]]]]]",
     "chr19\t1341\tC\t0\t*\t*\t*",
     "chr19\t1342\tC\t8\tccccTTTT\t+5?I+5?I\t!!!!IIII",
+    "chr19\t1343\t^\t4\t.A.CGT\tIIII\t]]]]",
+    "chr19\t1344\t+\t4\t.1AC,GT\tIIII\t]]]]",
+    "chr19\t1345\t-\t4\tA.2CGTT\tIIII\t]]]]",
 ]
 
 
@@ -80,7 +91,7 @@ def main():
     if not os.path.exists(REF):
         sys.exit("oracle/_ref/sid_ref missing: run `make -C oracle ref` (needs /root/reference)")
     files = {}
-    files["edge"] = ("\n".join(EDGE) + "\n").encode() + b"chrY\t36\tT\t3\t..,\tIII"      # last line unterminated
+    files["edge"] = ("\n".join(EDGE) + "\n").encode() + b"chrY\t42\tT\t3\t..,\tIII"      # last line unterminated
     files["edge_quality"] = ("\n".join(QUAL_EDGE) + "\n").encode()
     files["depth30"] = synth.generate(4000, seed=11, **synth.CONFIGS["depth30"]).tobytes()
     files["depth30_two_chroms"] = synth.generate(3000, seed=12, chroms=("chr1", "chr2"), chrom_lengths=(1700, 1300),

@@ -12,7 +12,7 @@
 #include <cmath>
 #include <vector>
 #ifdef SID_HAVE_FAST
-#include "../../sid_b200/csrc/parse_fast.cuh"
+#include "parse_swar.hpp"
 #include "../../sid_b200/csrc/parse_bits.cuh"
 #endif
 

@@ -319,6 +319,91 @@ def test_records_match_oracle(native, gpu_ctx):
             assert op.conf_close(x, y)
 
 
+def _oracle_fit(text, kw):
+    o = op.oracle_call(text, **kw)
+    prof = o["profiles"]
+    cov = op.unpack_profiles(prof).astype(np.int64).sum(axis=1)
+    u, c = op.oracle_unique(prof[cov >= 4])
+    return o, (o["pi"], o["eps"], op.oracle_nd(u, c))
+
+
+RECORD_CASES = [c for c in MANIFEST["cases"] if c["flags"][1] in ("bayes", "likelihood_ratio", "quality")
+                or c["input"] in ("depth500.plp", "edge.plp", "depth5.plp")]
+
+
+@pytest.mark.parametrize("case", RECORD_CASES, ids=lambda c: c["csv"])
+def test_record_doubles_match_oracle(native, gpu_ctx, case):
+    """hom_conf / het_conf as DOUBLES from the CUDA path (sidgpu_emit_records) against the oracle's x87 values at the
+    stated tolerance (1e-9 relative), for every method on every golden input (bayes / likelihood_ratio with and without
+    -R, quality per site, depth 500); labels and genotypes exact.  The oracle's fit is injected (GSL is unpinned)."""
+    import sid_b200
+    text = read(case["input"])
+    kw = flags_to_kwargs(case["flags"])
+    method = kw["method"]
+    fit = None
+    if method in ("bayes", "likelihood_ratio") or kw.get("estimate_prior"):
+        want, fit = _oracle_fit(text, kw)
+    else:
+        want = op.oracle_call(text, **kw)
+    d = gpu_ctx.upload_text(text)
+    try:
+        gpu_ctx.begin(params_from_flags(case["flags"], fit))
+        n = gpu_ctx.feed(d, len(text))
+        if method in ("bayes", "likelihood_ratio") or kw.get("estimate_prior"):
+            gpu_ctx.finish()
+            if method == "quality":
+                n = gpu_ctx.feed(d, len(text))           # second pass of quality -R
+        lab, gt, hom, het = gpu_ctx.emit_records(0, n)
+    finally:
+        d.free()
+    assert n == want["n_sites"]
+    keep = lab != 255                                    # coverage < 4 under bayes / likelihood_ratio: no row (call.cpp:131-140)
+    assert int(keep.sum()) == want["n"]
+    assert np.array_equal(lab[keep], want["label"]) and np.array_equal(gt[keep], want["gt"])
+    for a, b in ((hom[keep], want["hom"]), (het[keep], want["het"])):
+        bad = [(x, y) for x, y in zip(a, b) if not op.conf_close(x, y)]
+        assert not bad, bad[:5]
+
+
+def test_reference_character_fuzz_on_device(native, gpu_ctx):
+    """The reference substitutes '.' / ',' by the reference character before its switch (pileup.cpp:78-83), so a
+    reference column of '^', '+' or '-' changes the grammar of the line.  40,000 random lines with the reference drawn
+    from letters, digits and those control characters: profiles bit-exact through the tokenizer, rows through
+    `local`, per-site records through `quality`."""
+    import random
+    import sid_b200
+    rnd = random.Random(12)
+    refs = "ACGTacgtNn*.,^+-$1x"
+    alphabet = ".,.,.,ACGTacgtNn*$^+-0123456789<>"
+    lines = []
+    for k in range(40000):
+        ln = rnd.choice([1, 2, 3, 4, 5, 8, 12, 20, 31, 32, 33, 40, 64, 70])
+        bases = "".join(rnd.choice(alphabet) for _ in range(ln))
+        q = "".join(chr(33 + rnd.randrange(0, 60)) for _ in range(ln))
+        lines.append("chr%d\t%d\t%s\t%d\t%s\t%s\t%s" % (1 + k // 20000, k + 1, rnd.choice(refs), ln, bases, q, q[::-1]))
+    text = ("\n".join(lines) + "\n").encode()
+    want = op.oracle_call(text, "local")
+    d = gpu_ctx.upload_text(text)
+    try:
+        got = gpu_ctx.tokenize(d, len(text))
+        assert got["n_sites"] == want["n_sites"] == 40000
+        assert int((got["profile"] != want["profiles"]).sum()) == 0
+        assert np.array_equal(got["pos"], want["pos"]) and got["chrom"] == want["chrom"]
+        wq = op.oracle_call(text, "quality")
+        gpu_ctx.begin(sid_b200.Context.make_params("quality"))
+        n = gpu_ctx.feed(d, len(text))
+        lab, gt, hom, het = gpu_ctx.emit_records(0, n)
+    finally:
+        d.free()
+    assert np.array_equal(lab, wq["label"]) and np.array_equal(gt, wq["gt"])
+    for a, b in ((hom, wq["hom"]), (het, wq["het"])):
+        bad = [(x, y) for x, y in zip(a, b) if not op.conf_close(x, y)]
+        assert not bad, bad[:5]
+    rows, n_sites, n_rows = gpu_ctx.call_host(text, sid_b200.Context.make_params("local"))
+    k, diffs = op.compare_csv(sid_b200.CSV_HEADER + rows, want["csv"])
+    assert k == n_rows == 40000 and diffs <= 40
+
+
 def test_histogram_and_objective(native, gpu_ctx):
     import sid_b200
     text = read("depth30.plp")

@@ -161,6 +161,39 @@ def test_lynch_objective_matches_oracle(native):
     assert hc.hc_lynch_objective(len(u), u.ctypes.data, c.ctypes.data, a, -0.1, 0.5) == 1.7976931348623157e308
 
 
+def test_reference_character_substitution_fuzz(native):
+    """pileup.cpp:78-83 replaces '.' / ',' by toupper / tolower(reference) BEFORE its switch: a reference column of
+    '^' makes every '.' eat the next byte, '+' / '-' make it start an indel.  40,000 random lines, reference drawn from
+    letters, digits and the grammar's own control characters: byte-wise and bit-parallel tokenizers against the oracle."""
+    hc = op.hostcheck()
+    o = op.oracle()
+    rnd = random.Random(11)
+    refs = "ACGTacgtNn*.,^+-$1x"
+    alphabet = ".,.,.,ACGTacgtNn*$^+-0123456789<>"
+    lines, want = [], []
+    counts = (ctypes.c_uint16 * 4)()
+    for k in range(40000):
+        ref = rnd.choice(refs)
+        ln = rnd.choice([1, 2, 3, 4, 5, 8, 12, 20, 31, 32, 33, 40, 64, 70])
+        bases = "".join(rnd.choice(alphabet) for _ in range(ln))
+        lines.append("chr1\t%d\t%s\t%d\t%s\t%s" % (k + 1, ref, ln, bases, "I" * ln))
+        o.orc_parse_read_bases(bases.encode(), ref.encode(), counts, None)
+        want.append(int(op.pack_profiles([list(counts)])[0]))
+    text = ("\n".join(lines) + "\n").encode()
+    hl = op.HcLine()
+    starts = line_starts(text)
+    assert len(starts) == len(want)
+    bad = 0
+    for k, s0 in enumerate(starts):
+        hc.hc_parse_line(text, len(text), s0, 0, ctypes.byref(hl))
+        assert hl.status == 0
+        bad += hl.profile != want[k]
+    assert bad == 0
+    nf = ctypes.c_uint64()
+    assert hc.hc_compare_parsers_bits(text, len(text), ctypes.byref(nf)) == len(want)
+    assert hc.hc_compare_parsers(text, len(text), ctypes.byref(nf)) == len(want)
+
+
 def _adversarial_text(seed, n_lines):
     rnd = random.Random(seed)
     alphabet = ".,ACGTacgtNn*$^+-0123456789<>#!~^^++--Rr \t]I"
@@ -178,7 +211,7 @@ def _adversarial_text(seed, n_lines):
         sep = rnd.choice(["\t", "\t", "\t", " ", "\t\t", " \t"])
         chrom = rnd.choice(["chr1", "c", "chromosome_with_a_long_name", "x" * 40, "chr\x01", "chr\xe9"])
         pos = rnd.choice(["1", "123456789", "1234567890", "007", "-5", "+3", "12ab", "99999999999999999999", "4294967296"])
-        ref = rnd.choice(list("ACGTNacgtn*") + ["AC", ""])
+        ref = rnd.choice(list("ACGTNacgtn*") + ["AC", "", "^", "+", "-", "$", "1", "x", "."])
         tail = rnd.choice(["\tIIII", "", "\t", "\tII\tJJ", " II"])
         fields = [chrom, pos, ref, str(ln), bases]
         if rnd.random() < 0.08:                      # too few columns: the next line's separators must not be taken for this one's
@@ -294,6 +327,19 @@ def test_quality_call_matches_oracle(native, name, prior):
     """The per-site arithmetic of k_quality (SID_HD call_quality) against the oracle: labels and genotypes
     exact, confidences within REL_TOL."""
     _quality_case(read(name), prior)
+
+
+def test_quality_call_with_control_reference_characters(native):
+    """`-m quality` pairs the j-th COUNTED base with the j-th quality characters (call.cpp:330-331); with a reference
+    column of '^', '+' or '-' the set of counted bases itself changes (pileup.cpp:78-83)."""
+    rnd = random.Random(13)
+    lines = []
+    for k in range(6000):
+        ln = rnd.choice([1, 2, 3, 5, 8, 12, 20, 31, 33, 40, 70])
+        bases = "".join(rnd.choice(".,.,.,ACGTacgtNn*$^+-0123456789<>") for _ in range(ln))
+        q = "".join(chr(33 + rnd.randrange(0, 60)) for _ in range(ln))
+        lines.append("chr1\t%d\t%s\t%d\t%s\t%s\t%s" % (k + 1, rnd.choice("ACGTacgtNn*.,^+-$1x"), ln, bases, q, q[::-1]))
+    _quality_case(("\n".join(lines) + "\n").encode())
 
 
 def test_quality_call_matches_oracle_on_deep_pileups(native):
