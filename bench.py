@@ -40,6 +40,7 @@ def parse_args():
     ap.add_argument("--cpu-sample-sites", type=int, default=3_000_000)
     ap.add_argument("--het-only", action="store_true", help="emit only rows labelled het (the pipeline's grep ',het,'); not the headline config")
     ap.add_argument("--chunk-mb", type=int, default=256, help="chunk size of the host-buffer path (sidgpu_config.max_chunk_bytes)")
+    ap.add_argument("--unfused", action="store_true", help="local: sidgpu_feed + sidgpu_emit_csv (site store + K6) instead of the one-pass sidgpu_feed_rows")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -235,8 +236,14 @@ def run_ours(args):
     needs_fit = args.method in ("bayes", "likelihood_ratio")
     d_obj = torch.zeros(1, dtype=torch.float64, device="cuda")
 
+    fused = args.method == "local" and not args.unfused
+
     def step_resident():
         ctx.begin(params)
+        if fused:                                   # one kernel from text to rows, then the regions laid end to end
+            b, r, n = ctx.feed_rows(d_text.data_ptr(), text_len, d_csv.data_ptr(), csv_cap)
+            state["csv_bytes"], state["rows"] = b, r
+            return n
         n = ctx.feed(d_text.data_ptr(), text_len)
         if needs_fit and world > 1:
             # sharded Lynch fit: five integers once, then one double per optimiser evaluation (NCCL)
@@ -366,7 +373,7 @@ def run_ours(args):
                        "l2": "inputs larger than L2 (%.1f GB of text per step)" % (text_len / 1e9), "parallelism": "position-sharded x%d, no data-path collective" % world,
                        "generator_seconds": gen_s, "sites_per_gpu": n_sites,
                        "note": ("het rows only (--het-only); " + (note or "")) if args.het_only else note},
-            "roofline": {"bound": "hbm", "kernel": "k_tokenize", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": "k_tok2<rows>" if fused else "k_tok2<sites>", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                          "frac": achieved / hbm_peak if hbm_peak else None, "traffic": traffic, "peak_kind": peak_kind,
                          "algorithmic_bytes_per_launch": text_len, "avg_launch_ms": tok_avg_ms, "launches_timed": tok_n,
                          "limiter": "integer ALU pipe, 66 % of its peak in profiles/r1_ncu_full_tokenize_v19.txt (DRAM 18 %): "

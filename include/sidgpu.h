@@ -92,6 +92,7 @@ int sidgpu_malloc_host(sidgpu_ctx* ctx, size_t bytes, void** h_ptr);
 int sidgpu_free_host(sidgpu_ctx* ctx, void* h_ptr);
 int sidgpu_memcpy_h2d(sidgpu_ctx* ctx, void* d_dst, const void* h_src, size_t bytes);
 int sidgpu_memcpy_d2h(sidgpu_ctx* ctx, void* h_dst, const void* d_src, size_t bytes);
+int sidgpu_memcpy_d2d(sidgpu_ctx* ctx, void* d_dst, const void* d_src, size_t bytes);
 
 /* ------------------------------------------------------------------------------------------------
  * K1: tokenizer + profile builder
@@ -139,6 +140,14 @@ int sidgpu_begin(sidgpu_ctx* ctx, const sidgpu_params* params);
 int sidgpu_feed(sidgpu_ctx* ctx, const char* d_text, size_t text_len, size_t range_begin,
                 size_t range_end, uint64_t* n_sites_out);
 int sidgpu_finish(sidgpu_ctx* ctx);
+/* Text in, CSV rows out in ONE pass for sessions whose rows need no genome-wide step (SIDGPU_METHOD_LOCAL without -R):
+ * readFile + callSiteMLError + operator<< (call.cpp:11-20,213-289; call.hpp:29-38) of the lines that start in
+ * [range_begin, range_end).  The tokenizer kernel classifies a profile when it first meets it and writes the rows
+ * itself; nothing is stored per site, so the rows exist only in d_out (sidgpu_emit_* address the sites of sidgpu_feed,
+ * not of this call).  *bytes_out: CSV bytes written (no header line); *rows_out: rows (fewer than sites with het_only);
+ * *n_sites_out: lines parsed.  SIDGPU_ECAPACITY (needed size in *bytes_out) when out_cap is too small. */
+int sidgpu_feed_rows(sidgpu_ctx* ctx, const char* d_text, size_t text_len, size_t range_begin, size_t range_end,
+                     char* d_out, size_t out_cap, uint64_t* bytes_out, uint64_t* rows_out, uint64_t* n_sites_out);
 /* Formats sites [site_begin, site_begin + n_sites) of the session into d_out (K2 for profiles not yet
  * classified + K6).  In streaming mode (local/quality without -R) only the sites of the most recent
  * feed are addressable.  *bytes_out receives the CSV bytes written (no header line). */
@@ -231,6 +240,13 @@ int sidgpu_set_fit(sidgpu_ctx* ctx, double pi, double eps, const double nd[4]);
  * the reference's lexicographic order (n_global packed profiles, host memory).  Requires sidgpu_set_fit.
  * p-values, the BH adjustment and the classification of this rank's own profiles run on the device. */
 int sidgpu_finish_global(sidgpu_ctx* ctx, const uint64_t* h_profiles_sorted, uint64_t n_global);
+/* Position shards with a genome-wide step, the collective form: every rank passes the histograms of ALL shards
+ * (device memory: n (profile, count) pairs, e.g. the all-gather of each rank's sidgpu_histogram, padded with
+ * count 0) before sidgpu_finish.  The device merges them (counts summed, lexicographic order = countUniqueProfiles of
+ * the whole genome, pileup.cpp:169-196), derives the nucleotide distribution from the merged integers and maps this
+ * rank's own profiles onto the merged list; sidgpu_finish then fits and classifies exactly as a single GPU holding
+ * the whole genome would, so every rank gets bit-identical (pi, eps) without any per-evaluation exchange. */
+int sidgpu_set_global_histogram(sidgpu_ctx* ctx, const uint64_t* d_profiles, const uint64_t* d_counts, uint64_t n);
 /* The fit the session used (after sidgpu_finish). */
 int sidgpu_session_fit(sidgpu_ctx* ctx, sidgpu_fit* out, double nd[4], uint64_t* n_unique);
 
@@ -245,12 +261,14 @@ int sidgpu_format_g(sidgpu_ctx* ctx, const double* d_values, uint64_t n, char* d
 
 /* Counters for benchmarking: kernels launched by this ctx since creation; and, when enabled,
  * device time per kernel family measured with CUDA events on the ctx's stream around each launch:
- * ms[0]/launches[0] tokenizer (K1), [1] classification (K2), [2] CSV formatter (K6), [3] the two small
- * kernels that turn the tokenizer's block table into the file order of the sites (one count per pair).
- * sidgpu_profile(ctx, enable) resets the accumulators. */
+ * ms[0]/launches[0] tokenizer (K1), [1] classification (K2), [2] CSV (K6, or the compaction of the fused row writer's
+ * regions), [3] the two small kernels that turn the tokenizer's block table into the file order of the sites,
+ * [4] Lynch fit (K4: one k_lynch_fit launch, or the objective evaluations of the host loop), [5] histogram (K3),
+ * [6] quality, [7] reserved.  sidgpu_profile(ctx, enable) resets the accumulators. */
+#define SIDGPU_N_TIMERS 8
 uint64_t sidgpu_launch_count(const sidgpu_ctx* ctx);
 int sidgpu_profile(sidgpu_ctx* ctx, int enable);
-int sidgpu_kernel_times(sidgpu_ctx* ctx, double ms[4], uint64_t launches[4]);
+int sidgpu_kernel_times(sidgpu_ctx* ctx, double ms[SIDGPU_N_TIMERS], uint64_t launches[SIDGPU_N_TIMERS]);
 
 #ifdef __cplusplus
 }

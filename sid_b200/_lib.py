@@ -58,11 +58,14 @@ PROTOTYPES = {
     "sidgpu_free_host": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     "sidgpu_memcpy_h2d": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]),
     "sidgpu_memcpy_d2h": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]),
+    "sidgpu_memcpy_d2d": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]),
     "sidgpu_tokenize": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t,
                                        ctypes.c_size_t, ctypes.c_int, ctypes.POINTER(SitesView)]),
     "sidgpu_begin": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(Params)]),
     "sidgpu_feed": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t,
                                    ctypes.c_size_t, c_u64_p]),
+    "sidgpu_feed_rows": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_size_t,
+                                        ctypes.c_void_p, ctypes.c_size_t, c_u64_p, c_u64_p, c_u64_p]),
     "sidgpu_finish": (ctypes.c_int, [ctypes.c_void_p]),
     "sidgpu_emit_csv": (ctypes.c_int, [ctypes.c_void_p, c_u64, c_u64, ctypes.c_void_p, ctypes.c_size_t, c_u64_p, c_u64_p]),
     "sidgpu_feed_host": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.POINTER(c_u64)]),
@@ -80,6 +83,7 @@ PROTOTYPES = {
     "sidgpu_count_unique_weighted": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, c_u64, ctypes.c_uint32,
                                                     ctypes.POINTER(UniqueView)]),
     "sidgpu_set_fit": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_double, ctypes.c_double, c_double_p]),
+    "sidgpu_set_global_histogram": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, c_u64]),
     "sidgpu_lynch_objective_partial": (ctypes.c_int, [ctypes.c_void_p, c_double_p, ctypes.c_double, ctypes.c_double,
                                                       ctypes.c_void_p]),
     "sidgpu_lynch_objective": (ctypes.c_int, [ctypes.c_void_p, c_double_p, ctypes.c_double, ctypes.c_double, c_double_p]),

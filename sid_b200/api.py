@@ -109,6 +109,10 @@ class Context:
         buf.text_len = a.nbytes
         return buf
 
+    def copy_d2d(self, dst_ptr, src_ptr, nbytes):
+        if nbytes:
+            self._ck(self.lib.sidgpu_memcpy_d2d(self.h, dst_ptr, src_ptr, nbytes))
+
     def _download(self, ptr, dtype, count):
         out = np.empty(int(count), dtype=dtype)
         if out.nbytes:
@@ -123,11 +127,12 @@ class Context:
         self._ck(self.lib.sidgpu_profile(self.h, 1 if enable else 0))
 
     def kernel_times(self):
-        """{'tokenize': (ms, launches), 'classify': ..., 'csv': ..., 'order': ...} since profile(True)."""
-        ms = (ctypes.c_double * 4)()
-        n = (ctypes.c_uint64 * 4)()
+        """{'tokenize': (ms, launches), 'classify': ..., 'csv': ..., 'order': ..., 'fit': ..., 'histogram': ..., 'quality': ...}
+        since profile(True)."""
+        ms = (ctypes.c_double * 8)()
+        n = (ctypes.c_uint64 * 8)()
         self._ck(self.lib.sidgpu_kernel_times(self.h, ms, n))
-        return {k: (ms[i], n[i]) for i, k in enumerate(("tokenize", "classify", "csv", "order"))}
+        return {k: (ms[i], n[i]) for i, k in enumerate(("tokenize", "classify", "csv", "order", "fit", "histogram", "quality"))}
 
     # ---- K1
     def tokenize(self, d_text, text_len, begin=0, end=None, want_qual=False):
@@ -183,6 +188,15 @@ class Context:
         ptr = d_text.ptr if isinstance(d_text, DeviceBuffer) else d_text
         self._ck(self.lib.sidgpu_feed(self.h, ptr, text_len, begin, end, ctypes.byref(n)))
         return n.value
+
+    def feed_rows(self, d_text, text_len, d_out, out_cap, begin=0, end=None):
+        """Text in, CSV rows out in one kernel pass (`local` without -R): returns (csv_bytes, rows, n_sites)."""
+        end = text_len if end is None else end
+        b, r, n = ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_uint64()
+        ptr = d_text.ptr if isinstance(d_text, DeviceBuffer) else d_text
+        out = d_out.ptr if isinstance(d_out, DeviceBuffer) else d_out
+        self._ck(self.lib.sidgpu_feed_rows(self.h, ptr, text_len, begin, end, out, out_cap, ctypes.byref(b), ctypes.byref(r), ctypes.byref(n)))
+        return b.value, r.value, n.value
 
     def finish(self):
         self._ck(self.lib.sidgpu_finish(self.h))
@@ -240,6 +254,17 @@ class Context:
         finally:
             for b in (lab, gt, hom, het):
                 b.free()
+
+    def set_global_histogram(self, d_profiles, d_counts, n):
+        """The histograms of all shards (device pointers, n (profile, count) pairs, count 0 = padding): merged on the
+        device; finish() then fits and classifies as one GPU holding the whole genome would."""
+        self._ck(self.lib.sidgpu_set_global_histogram(self.h, d_profiles, d_counts, n))
+
+    def histogram_device(self, min_coverage=4):
+        """(n_unique, device pointer of the profiles, device pointer of the counts) of the session's histogram."""
+        v = UniqueView()
+        self._ck(self.lib.sidgpu_histogram(self.h, min_coverage, ctypes.byref(v)))
+        return int(v.n_unique), v.d_profile, v.d_count
 
     def session_fit(self):
         f = Fit()

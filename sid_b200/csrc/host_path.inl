@@ -61,7 +61,29 @@ struct HostIo {
         for (;;) {
             TRY(ensure(ctx, hp.csv[b], want));
             const int rc = sidgpu_emit_csv(ctx, site_begin, count, (char*)hp.csv[b].p, hp.csv[b].cap, &bytes, &rows);
-            if (rc == SIDGPU_ECAPACITY) { want = (size_t)bytes + 4096; continue; }
+            if (rc == SIDGPU_ECAPACITY && bytes + 4096 > want) { want = (size_t)bytes + 4096; continue; }
+            if (rc != SIDGPU_OK) return rc;
+            break;
+        }
+        if (out_off + bytes <= csv_cap && h_csv) {
+            CK(cudaMemcpyAsync(h_csv + out_off, hp.csv[b].p, bytes, cudaMemcpyDeviceToHost, ctx->copy_out));
+            CK(cudaEventRecord(hp.ev_out[b], ctx->copy_out));
+        } else {
+            out_overflow = true;
+        }
+        out_off += bytes;
+        total_rows += rows;
+        return SIDGPU_OK;
+    }
+    // the fused form of feed + emit_range for `local` sessions: K1 writes the rows of the chunk itself
+    int rows_chunk(int b, const char* d_text, size_t len, uint64_t* n_sites) {
+        CK(cudaEventSynchronize(hp.ev_out[b]));                     // the previous D2H out of csv[b] is done
+        uint64_t bytes = 0, rows = 0;
+        size_t want = std::max<size_t>(hp.csv[b].cap, len + len / 2 + 4096);
+        for (;;) {
+            TRY(ensure(ctx, hp.csv[b], want));
+            const int rc = sidgpu_feed_rows(ctx, d_text, len, 0, len, (char*)hp.csv[b].p, hp.csv[b].cap, &bytes, &rows, n_sites);
+            if (rc == SIDGPU_ECAPACITY && bytes + 4096 > want) { want = (size_t)bytes + 4096; continue; }
             if (rc != SIDGPU_OK) return rc;
             break;
         }
@@ -91,9 +113,15 @@ struct HostIo {
             }
             CK(cudaStreamWaitEvent(ctx->stream, hp.ev_in[b], 0));
             uint64_t n = 0;
-            TRY(sidgpu_feed(ctx, (const char*)hp.text[b].p, end - start, 0, end - start, &n));
-            total_sites += n;
-            if (emit) TRY(emit_range(b, 0, n));
+            static const bool fused = !(getenv("SIDGPU_FUSED_ROWS") && atoi(getenv("SIDGPU_FUSED_ROWS")) == 0);   // 0: feed + K6 (A/B runs)
+            if (emit && fused && ctx->streaming && ctx->params.method == SIDGPU_METHOD_LOCAL && ctx->phase == PHASE_FEED) {
+                TRY(rows_chunk(b, (const char*)hp.text[b].p, end - start, &n));       // one kernel from text to rows
+                total_sites += n;
+            } else {
+                TRY(sidgpu_feed(ctx, (const char*)hp.text[b].p, end - start, 0, end - start, &n));
+                total_sites += n;
+                if (emit) TRY(emit_range(b, 0, n));
+            }
             start = next_start;
             end = next_end;
         }

@@ -36,7 +36,7 @@ __device__ __forceinline__ void store_class(const TableView& t, uint32_t slot, c
     const int n = (het_only && r.label != 1) ? 0 : format_suffix(r, probability, buf);
     char* dst = t.suffix + (size_t)slot * SUFFIX_BYTES;
     for (int i = 0; i < n; ++i) dst[i] = buf[i];
-    dst[SUFFIX_BYTES - 1] = (char)n;
+    dst[SUFFIX_BYTES - 1] = (char)(n | SUFFIX_READY);      // length + "record complete" (the fused row writer waits for it)
 }
 
 __global__ void __launch_bounds__(128) k_classify(const ClassifyParams p) {
@@ -185,7 +185,7 @@ __global__ void __launch_bounds__(CSV_THREADS, SID_CSV_CTAS) k_csv(const CsvPara
                 const char* sfx = p.site_suffix ? p.site_suffix + site * SUFFIX_BYTES
                                                 : p.table.suffix + (size_t)p.slot[site] * SUFFIX_BYTES;
                 sfxp[k] = sfx;
-                const uint32_t sl = (uint8_t)sfx[SUFFIX_BYTES - 1];
+                const uint32_t sl = (uint8_t)sfx[SUFFIX_BYTES - 1] & 0x7Fu;
                 slen[k] = sl;
                 if (sl) {
                     nref[k] = p.name_ref[site];

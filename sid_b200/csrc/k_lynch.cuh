@@ -5,6 +5,7 @@
 #pragma once
 #include "calls.cuh"
 #include "common.cuh"
+#include "nelder_mead.hpp"
 #include "table.cuh"
 
 namespace sid {
@@ -179,6 +180,102 @@ __global__ void __launch_bounds__(OBJ_THREADS) k_lynch_objective(const ObjParams
         }
         *p.out = -a.value();
         *p.done_blocks = 0;
+    }
+}
+
+// ---- K4, whole fit in one launch -----------------------------------------------------------------
+// estimateProfileGenotypeLikelihoods (lynch.cpp:17-35) + FunctionMinimizer<2>::run (optimization.hpp:51-89) as ONE
+// cooperative kernel: every thread walks the same Nelder-Mead trajectory (nelder_mead.hpp); an objective evaluation
+// (compoundLikelihood, lynch.cpp:37-61) is a grid-wide reduction: per-thread compensated sums over the histogram,
+// a fixed-order tree per block, one grid barrier, then every block adds the block partials in the same order.
+// No host round trip per evaluation; the result depends only on the histogram (its order included), so every rank
+// that holds the same merged histogram gets bit-identical (pi, eps).
+struct FitParams {
+    const unsigned long long* u_profile;
+    const unsigned long long* u_count;
+    const double* u_logM;
+    uint32_t n_unique;
+    double nd[4];
+    double x0[2], step[2];
+    double* partials;          // 2 buffers x 2 doubles per block
+    unsigned int* barrier;     // monotonic arrival counter, zero at launch
+    double* out;               // pi, eps, fval, iterations, evaluations, converged (as doubles)
+    unsigned long long* error;
+};
+
+struct FitEval {
+    const FitParams& p;
+    double* s_s;
+    double* s_c;
+    double* s_val;
+    uint32_t epoch;
+    bool dead;
+    __device__ double operator()(double pi, double eps) {
+        if (pi < 0 || pi > 1 || eps < 0 || eps > 1) return 1.7976931348623157e308;      // lynch.cpp:41-43
+        const LynchConsts k = lynch_consts(p.nd, eps);
+        const double log1m_pi = log1p(-pi), log_pi = log(pi);
+        CompSum acc;
+        acc.init();
+        for (uint32_t u = blockIdx.x * OBJ_THREADS + threadIdx.x; u < p.n_unique; u += gridDim.x * OBJ_THREADS) {
+            double t;
+            if (lynch_term(p.u_profile[u], p.u_logM[u], k, log1m_pi, log_pi, t)) acc.add(t * (double)p.u_count[u]);
+        }
+        s_s[threadIdx.x] = acc.s;
+        s_c[threadIdx.x] = acc.c;
+        __syncthreads();
+        for (int d = OBJ_THREADS / 2; d > 0; d >>= 1) {
+            if ((int)threadIdx.x < d) {
+                CompSum a;
+                a.s = s_s[threadIdx.x]; a.c = s_c[threadIdx.x];
+                a.add(s_s[threadIdx.x + d]);
+                a.c += s_c[threadIdx.x + d];
+                s_s[threadIdx.x] = a.s; s_c[threadIdx.x] = a.c;
+            }
+            __syncthreads();
+        }
+        double* buf = p.partials + (size_t)(epoch & 1u) * 2 * gridDim.x;
+        if (threadIdx.x == 0) {
+            buf[2 * blockIdx.x] = s_s[0];
+            buf[2 * blockIdx.x + 1] = s_c[0];
+            __threadfence();
+            atomicAdd(p.barrier, 1u);
+            // grid barrier: all blocks are resident (cooperative launch); bounded like every wait of this library
+            const unsigned int target = (epoch + 1u) * gridDim.x;
+            uint32_t spins = 0;
+            while (*((volatile unsigned int*)p.barrier) < target) {
+                if (++spins > (1u << 24)) { dead = true; break; }
+                __nanosleep(64);
+            }
+            __threadfence();
+            CompSum a;
+            a.init();
+            for (uint32_t b = 0; b < gridDim.x; ++b) {
+                a.add(__ldcg(&buf[2 * b]));
+                a.c += __ldcg(&buf[2 * b + 1]);
+            }
+            *s_val = dead ? 1.7976931348623157e308 : -a.value();
+        }
+        __syncthreads();
+        const double v = *s_val;
+        __syncthreads();
+        ++epoch;
+        return v;
+    }
+};
+
+__global__ void __launch_bounds__(OBJ_THREADS) k_lynch_fit(const FitParams p) {
+    __shared__ double s_s[OBJ_THREADS], s_c[OBJ_THREADS];
+    __shared__ double s_val;
+    FitEval f {p, s_s, s_c, &s_val, 0u, false};
+    const NelderMeadResult r = nelder_mead_2d(f, p.x0, p.step);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        p.out[0] = r.x[0];
+        p.out[1] = r.x[1];
+        p.out[2] = r.fval;
+        p.out[3] = (double)r.iterations;
+        p.out[4] = (double)r.evaluations;
+        p.out[5] = r.converged ? 1.0 : 0.0;
+        if (f.dead) atomicMin(p.error, (unsigned long long)(LINE_MALFORMED + 4));
     }
 }
 

@@ -123,6 +123,9 @@ __device__ __forceinline__ uint2 load8_unaligned(const uint8_t* s, uint32_t o) {
     return make_uint2(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh));
 }
 
+__device__ __forceinline__ void report_error_at(unsigned long long* error, uint64_t line_abs, int status) {
+    atomicMin(error, (unsigned long long)((line_abs << 3) | (uint64_t)status));
+}
 __device__ __forceinline__ void report_error(const TokParams& p, uint64_t line_abs, int status) {
     atomicMin(p.error, (unsigned long long)((line_abs << 3) | (uint64_t)status));
 }

@@ -5,9 +5,16 @@
 // update rules follow the published algorithm: reflect (-1), expand (-2), contract (0.5), shrink
 // towards the best corner (0.5), size = sqrt(mean squared distance to the centroid), maintained
 // incrementally.  Stop rule of the reference: size < 1e-5, at most 1000 iterations.
+// The same code runs on the host (one device reduction per evaluation, sidgpu_lynch_objective) and inside
+// k_lynch_fit, where every thread of a cooperative grid walks the identical trajectory and an evaluation is a
+// grid-wide reduction: the whole fit is then one kernel launch.
 #pragma once
 #include <cmath>
+#if !defined(__CUDACC__)
 #include <functional>
+#endif
+
+#include "common.cuh"
 
 namespace sid {
 
@@ -19,8 +26,14 @@ struct NelderMeadResult {
     bool converged;
 };
 
-inline NelderMeadResult nelder_mead_2d(const std::function<double(double, double)>& f, const double x0[2],
-                                       const double step[2], double size_eps = 1e-5, int max_iterations = 1000) {
+SID_HD bool nm_finite(double v) { return v - v == 0.0; }      // false for NaN and +-inf
+
+#if defined(__CUDACC__)
+#pragma nv_exec_check_disable       // F is a host lambda in the host instantiation, a device functor in the kernel's
+#endif
+template <class F>
+SID_HD NelderMeadResult nelder_mead_2d(F&& f, const double x0[2], const double step[2], double size_eps = 1e-5,
+                                       int max_iterations = 1000) {
     constexpr int P = 3;
     double X[P][2], Y[P], c[2], S2 = 0;
     int evals = 0;
@@ -36,7 +49,7 @@ inline NelderMeadResult nelder_mead_2d(const std::function<double(double, double
             ss += t;
         }
         S2 = ss / P;
-        return std::sqrt(S2);
+        return sqrt(S2);
     };
     auto move = [&](double coeff, int corner, double* xc) {
         const double alpha = (1 - coeff) * P / (P - 1.0);
@@ -52,7 +65,7 @@ inline NelderMeadResult nelder_mead_2d(const std::function<double(double, double
             d2 += delta * delta;
             xmcd += xmc * delta;
         }
-        const double d = std::sqrt(d2);
+        const double d = sqrt(d2);
         S2 += (2.0 / P) * xmcd + ((P - 1.0) / P) * (d * d / P);
         for (int j = 0; j < 2; ++j) {
             c[j] -= (1.0 / P) * X[i][j];
@@ -84,20 +97,20 @@ inline NelderMeadResult nelder_mead_2d(const std::function<double(double, double
         }
         double xc[2], xc2[2];
         const double val = move(-1.0, hi, xc);
-        if (std::isfinite(val) && val < Y[lo]) {
+        if (nm_finite(val) && val < Y[lo]) {
             const double val2 = move(-2.0, hi, xc2);
-            if (std::isfinite(val2) && val2 < Y[lo]) update(hi, xc2, val2); else update(hi, xc, val);
-        } else if (!std::isfinite(val) || val > Y[s_hi]) {
-            if (std::isfinite(val) && val <= Y[hi]) update(hi, xc, val);
+            if (nm_finite(val2) && val2 < Y[lo]) update(hi, xc2, val2); else update(hi, xc, val);
+        } else if (!nm_finite(val) || val > Y[s_hi]) {
+            if (nm_finite(val) && val <= Y[hi]) update(hi, xc, val);
             const double val2 = move(0.5, hi, xc2);
-            if (std::isfinite(val2) && val2 <= Y[hi]) {
+            if (nm_finite(val2) && val2 <= Y[hi]) {
                 update(hi, xc2, val2);
             } else {
                 for (int k = 0; k < P; ++k) {
                     if (k == lo) continue;
                     for (int j = 0; j < 2; ++j) X[k][j] = 0.5 * (X[k][j] + X[lo][j]);
                     Y[k] = eval(X[k]);
-                    if (!std::isfinite(Y[k])) failed = true;
+                    if (!nm_finite(Y[k])) failed = true;
                 }
                 center();
                 full_size();
@@ -111,7 +124,7 @@ inline NelderMeadResult nelder_mead_2d(const std::function<double(double, double
         r.x[0] = X[lo][0];
         r.x[1] = X[lo][1];
         r.fval = Y[lo];
-        size = S2 > 0 ? std::sqrt(S2) : full_size();
+        size = S2 > 0 ? sqrt(S2) : full_size();
         r.converged = size < size_eps;            // optimization.hpp:66-67
         go = !r.converged && it < max_iterations; // optimization.hpp:72
     }

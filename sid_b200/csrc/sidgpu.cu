@@ -19,6 +19,7 @@
 #include "k_lynch.cuh"
 #include "k_quality.cuh"
 #include "k_tokenize.cuh"
+#include "k_tok2.cuh"
 #include "nelder_mead.hpp"
 
 using namespace sid;
@@ -45,6 +46,12 @@ struct Control {
     unsigned int pad0;
     unsigned long long nd_acc[5];
     double objective;
+    // merged (all shards) histogram table: its own counters
+    unsigned int g_n_entries;
+    unsigned int g_special_used;
+    unsigned int g_overflow;
+    unsigned int fit_barrier;        // arrival counter of k_lynch_fit's grid barrier
+    double fit_out[6];               // pi, eps, fval, iterations, evaluations, converged
 };
 
 struct DevBuf {
@@ -81,6 +88,8 @@ struct sidgpu_ctx {
     // site store: arrays indexed by storage index (dense, not in file order) and order[file index] = storage index
     DevBuf pos, slot, name_ref, profile, line_off, site_suffix, order;
     DevBuf blk, blk_part;            // block table of the running tokenizer call and its per-chunk sums
+    DevBuf rows_scratch, rows_part, rows_part_rows;   // fused row writer: per-slice regions, per-chunk byte / row sums
+    double region_factor = 1.0;      // grows when a slice's rows did not fit its region
     DevBuf v_pos, v_slot, v_name_ref, v_profile, v_line_off;   // file-ordered copies behind sidgpu_sites_view
     uint64_t site_cap = 0;
     bool want_profile = false, want_line_off = false, want_site_suffix = false;
@@ -104,6 +113,8 @@ struct sidgpu_ctx {
     DevBuf sort_keys, sort_vals, u_profile, u_count, u_logM, entry_to_unique, p_hom, p_het, adj_hom, adj_het, bh_c, bh_block;
     uint64_t n_unique = 0;
     bool hist_valid = false;
+    bool global_hist = false;        // the histogram is the merged one of all shards (sidgpu_set_global_histogram)
+    DevBuf g_e2u;
     DevBuf partials;
     DevBuf quality_lut;
 
@@ -116,8 +127,8 @@ struct sidgpu_ctx {
     struct Pending { cudaEvent_t a, b; int which; };
     std::vector<Pending> pending;
     std::vector<cudaEvent_t> free_events;
-    double kernel_ms[4] = {0, 0, 0, 0};
-    uint64_t kernel_launches[4] = {0, 0, 0, 0};
+    double kernel_ms[SIDGPU_N_TIMERS] = {0};
+    uint64_t kernel_launches[SIDGPU_N_TIMERS] = {0};
 
     int fail(int code, const char* fmt, ...) {
         char buf[512];
@@ -200,7 +211,7 @@ int check_launch(sidgpu_ctx* ctx, const char* what) {
     return SIDGPU_OK;
 }
 
-enum { PROF_TOKENIZE = 0, PROF_CLASSIFY = 1, PROF_CSV = 2, PROF_ORDER = 3 };
+enum { PROF_TOKENIZE = 0, PROF_CLASSIFY = 1, PROF_CSV = 2, PROF_ORDER = 3, PROF_FIT = 4, PROF_HIST = 5, PROF_QUALITY = 6 };
 
 cudaEvent_t take_event(sidgpu_ctx* ctx) {
     if (!ctx->free_events.empty()) { cudaEvent_t e = ctx->free_events.back(); ctx->free_events.pop_back(); return e; }
@@ -242,29 +253,34 @@ void free_table(TableView& t) {
     t = TableView {};
 }
 
-int alloc_table(sidgpu_ctx* ctx, int log2cap, TableView& t) {
+// aux: a counting-only table (keys, counts, entry list) with its own counters: the merged histogram of all shards
+int alloc_table(sidgpu_ctx* ctx, int log2cap, TableView& t, bool aux = false) {
     t = TableView {};
     const size_t cap = (size_t)1 << log2cap, n = cap + 1;
     t.cap = (uint32_t)cap;
     t.mask = (uint32_t)(cap - 1);
-    t.n_entries = ctl_field(ctx, &Control::n_entries);
-    t.special_used = ctl_field(ctx, &Control::special_used);
-    t.overflow = ctl_field(ctx, &Control::table_overflow);
+    t.n_entries = ctl_field(ctx, aux ? &Control::g_n_entries : &Control::n_entries);
+    t.special_used = ctl_field(ctx, aux ? &Control::g_special_used : &Control::special_used);
+    t.overflow = ctl_field(ctx, aux ? &Control::g_overflow : &Control::table_overflow);
     cudaError_t e = cudaSuccess;
     auto A = [&](void** p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, bytes); };
     A((void**)&t.keys, n * 8);
     A((void**)&t.counts, n * 8);
     A((void**)&t.entry_list, n * 4);
-    A((void**)&t.suffix, n * SUFFIX_BYTES);
-    A((void**)&t.label, n);
-    A((void**)&t.gt, n * 2);
-    A((void**)&t.hom, n * 8);
-    A((void**)&t.het, n * 8);
+    if (!aux) {
+        A((void**)&t.suffix, n * SUFFIX_BYTES);
+        A((void**)&t.label, n);
+        A((void**)&t.gt, n * 2);
+        A((void**)&t.hom, n * 8);
+        A((void**)&t.het, n * 8);
+    }
     if (e != cudaSuccess) { free_table(t); return ctx->fail(SIDGPU_ENOMEM, "profile table of 2^%d slots: %s", log2cap, cudaGetErrorString(e)); }
     CK(cudaMemsetAsync(t.keys, 0xFF, n * 8, ctx->stream));
     CK(cudaMemsetAsync(t.counts, 0, n * 8, ctx->stream));
-    CK(cudaMemsetAsync(t.suffix, 0, n * SUFFIX_BYTES, ctx->stream));
-    CK(cudaMemsetAsync(t.label, 255, n, ctx->stream));
+    if (!aux) {
+        CK(cudaMemsetAsync(t.suffix, 0, n * SUFFIX_BYTES, ctx->stream));
+        CK(cudaMemsetAsync(t.label, 255, n, ctx->stream));
+    }
     return SIDGPU_OK;
 }
 
@@ -278,7 +294,7 @@ __global__ void k_rehash(TableView from, TableView to, uint32_t n_entries, uint3
         h = to.cap;
         to.keys[h] = key;
     } else {
-        h = (uint32_t)mix64(key) & to.mask;
+        h = table_hash(key) & to.mask;
         for (;;) {
             const unsigned long long old = atomicCAS(&to.keys[h], (unsigned long long)TABLE_EMPTY, (unsigned long long)key);
             if (old == TABLE_EMPTY) break;
@@ -445,6 +461,30 @@ int run_tokenizer(sidgpu_ctx* ctx, const char* d_text, size_t text_len, size_t r
         // two staged tiles per CTA (the copy of the next tile runs under the parsing of this one) unless the
         // slices are so long that a single stage doubles the CTAs an SM holds: then the CTAs cover each other's copies
         static const int force_stages = getenv("SIDGPU_TOK_STAGES") ? atoi(getenv("SIDGPU_TOK_STAGES")) : 0;     // tuning knob
+        static const int k1_version = getenv("SIDGPU_K1") ? atoi(getenv("SIDGPU_K1")) : 2;                       // 1: round-1 kernel (A/B runs)
+        if (k1_version != 1) {
+            Tok2Params q {};
+            q.text = p.text; q.text_len = p.text_len; q.range_begin = p.range_begin; q.range_end = p.range_end;
+            q.tile0 = p.tile0; q.n_tiles = p.n_tiles;
+            q.site_base = p.site_base; q.site_cap = p.site_cap; q.profile = p.profile; q.pos = p.pos; q.slot = p.slot;
+            q.name_ref = p.name_ref; q.line_off = p.line_off; q.site_alloc = p.site_alloc;
+            q.tile_ticket = p.tile_ticket; q.blk = p.blk; q.error = p.error; q.table = p.table; q.names = p.names;
+            q.use_table = p.use_table; q.want_qual = p.want_qual; q.bytewise = (want_qual && strict_qual) ? 1 : 0;
+            q.slice_bytes = slice; q.text_stride = p.text_stride; q.tail_bytes = p.tail_bytes; q.lines_cap = p.lines_cap;
+            q.ext_bytes = ext; q.units_cap = tok2_units(slice, ext) + CW_PAD_UNITS;
+            int s2 = 0, s1 = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s2, k_tok2<false, 2>, TOK_THREADS, tok2_dyn_smem(slice, ext, 2, false)) != cudaSuccess || s2 < 1) s2 = 1;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s1, k_tok2<false, 1>, TOK_THREADS, tok2_dyn_smem(slice, ext, 1, false)) != cudaSuccess || s1 < 1) s1 = 1;
+            const int stages = force_stages == 1 || force_stages == 2 ? force_stages : (s1 > s2 ? 1 : 2);
+            const unsigned grid = (unsigned)std::min<uint64_t>(n_tiles, (uint64_t)ctx->sm_count * (stages == 1 ? s1 : s2));
+            const uint32_t dyn = tok2_dyn_smem(slice, ext, (uint32_t)stages, false);
+            {
+                ProfScope prof(ctx, PROF_TOKENIZE);
+                if (stages == 1) k_tok2<false, 1><<<grid, TOK_THREADS, dyn, ctx->stream>>>(q);
+                else k_tok2<false, 2><<<grid, TOK_THREADS, dyn, ctx->stream>>>(q);
+                TRY(check_launch(ctx, "k_tok2"));
+            }
+        } else {
         int per_sm2 = 0, per_sm1 = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm2, k_tokenize<true, 2>, TOK_THREADS, tok_dyn_smem(slice, ext, 2)) != cudaSuccess || per_sm2 < 1) per_sm2 = 1;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm1, k_tokenize<true, 1>, TOK_THREADS, tok_dyn_smem(slice, ext, 1)) != cudaSuccess || per_sm1 < 1) per_sm1 = 1;
@@ -465,6 +505,7 @@ int run_tokenizer(sidgpu_ctx* ctx, const char* d_text, size_t text_len, size_t r
                 else k_tokenize<true, 2><<<grid, TOK_THREADS, dyn_smem, ctx->stream>>>(p);
             }
             TRY(check_launch(ctx, "k_tokenize"));
+        }
         }
         {
             ProfScope prof(ctx, PROF_ORDER);
@@ -497,6 +538,107 @@ int run_tokenizer(sidgpu_ctx* ctx, const char* d_text, size_t text_len, size_t r
         if (c.n_sites >= 64) ctx->avg_line_bytes = (double)(range_end - range_begin) / (double)c.n_sites;   // sizes the slices of the next call
         // keep the load factor below one half for the next chunk
         while ((uint64_t)c.n_entries * 2 > ctx->tab.cap) TRY(grow_table(ctx, 2, site_base + c.n_sites));
+        return SIDGPU_OK;
+    }
+}
+
+// K1 in its ROWS form over [range_begin, range_end) of a streaming `local` session, then the compaction of the
+// slices' regions into d_out: text in, CSV rows out, nothing stored per site.
+int run_tok2_rows(sidgpu_ctx* ctx, const char* d_text, size_t text_len, size_t range_begin, size_t range_end, char* d_out, size_t out_cap,
+                  uint64_t* bytes_out, uint64_t* rows_out, uint64_t* n_out) {
+    if (((uintptr_t)d_text & 15) != 0) return ctx->fail(SIDGPU_EINVAL, "d_text must be 16-byte aligned");
+    if (range_begin > range_end || range_end > text_len) return ctx->fail(SIDGPU_EINVAL, "bad range [%zu,%zu) for text of %zu bytes", range_begin, range_end, text_len);
+    *bytes_out = *rows_out = *n_out = 0;
+    if (range_begin == range_end) return sync_ctl(ctx);
+    const uint64_t tile0 = range_begin & ~(uint64_t)15;
+    const uint64_t span = range_end - tile0;
+    static const double slice_lines = getenv("SIDGPU_SLICE_LINES") ? atof(getenv("SIDGPU_SLICE_LINES")) : 29.5;
+    static const int force_stages = getenv("SIDGPU_TOK_STAGES") ? atoi(getenv("SIDGPU_TOK_STAGES")) : 0;
+    uint32_t slice = (uint32_t)(ctx->avg_line_bytes * slice_lines) & ~31u;
+    slice = std::max<uint32_t>(SLICE_MIN, std::min<uint32_t>(SLICE_MAX, slice));
+    uint32_t ext = ((uint32_t)(ctx->avg_line_bytes * 1.25) + 31u) & ~31u;
+    ext = std::max<uint32_t>(128u, std::min<uint32_t>(2016u, ext));
+    const uint64_t tile_bytes = (uint64_t)slice * TOK_PARSE_WARPS;
+    const uint64_t n_tiles64 = (span + tile_bytes - 1) / tile_bytes;
+    if (n_tiles64 * TOK_PARSE_WARPS > 0x7FFFFFFFull) return ctx->fail(SIDGPU_EINVAL, "range too large");
+    const uint32_t n_tiles = (uint32_t)n_tiles64, n_regions = n_tiles * TOK_PARSE_WARPS;
+    const uint32_t n_chunks = (n_regions + RC_REGIONS - 1) / RC_REGIONS;
+    TRY(ensure(ctx, ctx->blk, (size_t)n_regions * 8));
+    TRY(ensure(ctx, ctx->rows_part, (size_t)n_chunks * 8));
+    TRY(ensure(ctx, ctx->rows_part_rows, (size_t)n_chunks * 8));
+    for (int attempt = 0;; ++attempt) {
+        // a region holds the rows of one slice: about 30 rows of up to 30 + 46 bytes when the slice was sized for 29.5 lines
+        const double lines_per_slice = (double)slice / std::max(8.0, ctx->avg_line_bytes);
+        uint64_t region_cap64 = (uint64_t)((lines_per_slice * 80.0 + 512.0) * ctx->region_factor);
+        region_cap64 = std::min<uint64_t>((region_cap64 + 15) & ~(uint64_t)15, (uint64_t)1 << 24);
+        const uint32_t region_cap = (uint32_t)region_cap64;
+        TRY(ensure(ctx, ctx->rows_scratch, (size_t)n_regions * region_cap));
+        CK(cudaMemsetAsync(ctl_field(ctx, &Control::tok_ticket), 0, sizeof(unsigned int), ctx->stream));
+        CK(cudaMemsetAsync(ctl_field(ctx, &Control::n_sites), 0, sizeof(unsigned long long), ctx->stream));
+        CK(cudaMemsetAsync(ctl_field(ctx, &Control::error), 0xFF, sizeof(unsigned long long), ctx->stream));
+        CK(cudaMemsetAsync(ctl_field(ctx, &Control::csv_bytes), 0, 2 * sizeof(unsigned long long), ctx->stream));
+        Tok2Params q {};
+        q.text = (const uint8_t*)d_text; q.text_len = text_len; q.range_begin = range_begin; q.range_end = range_end;
+        q.tile0 = tile0; q.n_tiles = n_tiles;
+        q.site_alloc = ctl_field(ctx, &Control::n_sites);
+        q.rows = (uint8_t*)ctx->rows_scratch.p; q.region_cap = region_cap;
+        q.prior = ctx->session_prior; q.error_threshold = ctx->params.error_threshold; q.alpha = ctx->params.significance_level;
+        q.het_only = ctx->params.het_only;
+        q.tile_ticket = ctl_field(ctx, &Control::tok_ticket);
+        q.blk = (unsigned long long*)ctx->blk.p;
+        q.error = ctl_field(ctx, &Control::error);
+        q.table = ctx->tab; q.names = ctx->names; q.use_table = 1;
+        q.slice_bytes = slice; q.text_stride = tok_text_stride(slice, ext); q.tail_bytes = tok_tail_bytes(ext); q.lines_cap = slice / 8;
+        q.ext_bytes = ext; q.units_cap = tok2_units(slice, ext) + CW_PAD_UNITS;
+        int s2 = 0, s1 = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s2, k_tok2<true, 2>, TOK_THREADS, tok2_dyn_smem(slice, ext, 2, true)) != cudaSuccess || s2 < 1) s2 = 1;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s1, k_tok2<true, 1>, TOK_THREADS, tok2_dyn_smem(slice, ext, 1, true)) != cudaSuccess || s1 < 1) s1 = 1;
+        const int stages = force_stages == 1 || force_stages == 2 ? force_stages : (s1 > s2 ? 1 : 2);
+        const unsigned grid = (unsigned)std::min<uint64_t>(n_tiles, (uint64_t)ctx->sm_count * (stages == 1 ? s1 : s2));
+        const uint32_t dyn = tok2_dyn_smem(slice, ext, (uint32_t)stages, true);
+        {
+            ProfScope prof(ctx, PROF_TOKENIZE);
+            if (stages == 1) k_tok2<true, 1><<<grid, TOK_THREADS, dyn, ctx->stream>>>(q);
+            else k_tok2<true, 2><<<grid, TOK_THREADS, dyn, ctx->stream>>>(q);
+            TRY(check_launch(ctx, "k_tok2 (rows)"));
+        }
+        {
+            ProfScope prof(ctx, PROF_CSV);
+            k_rows_sums<<<n_chunks, 256, 0, ctx->stream>>>((const unsigned long long*)ctx->blk.p, n_regions, (unsigned long long*)ctx->rows_part.p,
+                                                          (unsigned long long*)ctx->rows_part_rows.p);
+            TRY(check_launch(ctx, "k_rows_sums"));
+            k_rows_scan<<<1, 1024, 0, ctx->stream>>>((unsigned long long*)ctx->rows_part.p, (const unsigned long long*)ctx->rows_part_rows.p, n_chunks,
+                                                     ctl_field(ctx, &Control::csv_bytes), ctl_field(ctx, &Control::csv_rows));
+            TRY(check_launch(ctx, "k_rows_scan"));
+            k_rows_compact<<<n_chunks, RC_THREADS, (RC_THREADS / 32) * RC_STAGE, ctx->stream>>>(
+                (const uint8_t*)ctx->rows_scratch.p, region_cap, (const unsigned long long*)ctx->blk.p, n_regions,
+                (const unsigned long long*)ctx->rows_part.p, (uint8_t*)d_out, out_cap);
+            TRY(check_launch(ctx, "k_rows_compact"));
+        }
+        TRY(sync_ctl(ctx));
+        const Control& c = *ctx->h_ctl;
+        if (c.error != ~0ull) {
+            const int st = (int)(c.error & 7);
+            const unsigned long long off = c.error >> 3;
+            if (st == LINE_ROWS_OVERFLOW) {
+                if (attempt >= 6) return ctx->fail(SIDGPU_EINTERNAL, "row region sizing failed");
+                ctx->region_factor *= 2.0;
+                continue;
+            }
+            const int code = st == LINE_MALFORMED ? SIDGPU_EMALFORMED : SIDGPU_EINTERNAL;
+            return ctx->fail(code, "%s (line starting at byte %llu)", status_text(st), off);
+        }
+        if (c.table_overflow) {
+            TRY(grow_table(ctx, 2, 0));
+            continue;
+        }
+        *n_out = c.n_sites;
+        *bytes_out = c.csv_bytes;
+        *rows_out = c.csv_rows;
+        if (c.n_sites >= 64) ctx->avg_line_bytes = (double)(range_end - range_begin) / (double)c.n_sites;
+        while ((uint64_t)c.n_entries * 2 > ctx->tab.cap) TRY(grow_table(ctx, 2, 0));
+        ctx->classified = c.n_entries;                       // every entry was classified by the lane that inserted it
+        if (c.csv_bytes > out_cap) return ctx->fail(SIDGPU_ECAPACITY, "CSV needs %llu bytes, buffer has %zu", c.csv_bytes, out_cap);
         return SIDGPU_OK;
     }
 }
@@ -582,20 +724,21 @@ uint32_t pow2_at_least(uint64_t n) {
     return p;
 }
 
-int build_histogram(sidgpu_ctx* ctx, uint32_t min_cov) {
-    TRY(sync_ctl(ctx));
-    const uint32_t n_entries = ctx->h_ctl->n_entries;
+// The histogram of table `tab` (its first n_entries entries): unique arrays in lexicographic order, logM, integer
+// nucleotide sums; e2u[entry] = row of the entry in the unique arrays.
+int build_histogram_of(sidgpu_ctx* ctx, const TableView& tab, uint32_t n_entries, uint32_t min_cov, DevBuf& e2u) {
+    ProfScope prof(ctx, PROF_HIST);
     const uint32_t np2 = pow2_at_least(n_entries);
     TRY(ensure(ctx, ctx->sort_keys, (size_t)np2 * 8));
     TRY(ensure(ctx, ctx->sort_vals, (size_t)np2 * 4));
-    TRY(ensure(ctx, ctx->entry_to_unique, (size_t)std::max<uint32_t>(n_entries, 1) * 4));
+    TRY(ensure(ctx, e2u, (size_t)std::max<uint32_t>(n_entries, 1) * 4));
     CK(cudaMemsetAsync(ctl_field(ctx, &Control::n_selected), 0, sizeof(unsigned int), ctx->stream));
     CK(cudaMemsetAsync(ctl_field(ctx, &Control::nd_acc), 0, 5 * sizeof(unsigned long long), ctx->stream));
     ctx->n_unique = 0;
     if (n_entries) {
-        k_fill_u32<<<(n_entries + 255) / 256, 256, 0, ctx->stream>>>((uint32_t*)ctx->entry_to_unique.p, n_entries, 0xFFFFFFFFu);
+        k_fill_u32<<<(n_entries + 255) / 256, 256, 0, ctx->stream>>>((uint32_t*)e2u.p, n_entries, 0xFFFFFFFFu);
         TRY(check_launch(ctx, "k_fill_u32"));
-        k_hist_select<<<(n_entries + 255) / 256, 256, 0, ctx->stream>>>(ctx->tab, n_entries, min_cov, (unsigned long long*)ctx->sort_keys.p,
+        k_hist_select<<<(n_entries + 255) / 256, 256, 0, ctx->stream>>>(tab, n_entries, min_cov, (unsigned long long*)ctx->sort_keys.p,
                                                                          (uint32_t*)ctx->sort_vals.p, ctl_field(ctx, &Control::n_selected));
         TRY(check_launch(ctx, "k_hist_select"));
         TRY(sync_ctl(ctx));
@@ -608,9 +751,9 @@ int build_histogram(sidgpu_ctx* ctx, uint32_t min_cov) {
             TRY(ensure(ctx, ctx->u_profile, (size_t)n_sel * 8));
             TRY(ensure(ctx, ctx->u_count, (size_t)n_sel * 8));
             TRY(ensure(ctx, ctx->u_logM, (size_t)n_sel * 8));
-            k_hist_gather<<<(n_sel + 255) / 256, 256, 0, ctx->stream>>>(ctx->tab, (const uint32_t*)ctx->sort_vals.p, n_sel,
+            k_hist_gather<<<(n_sel + 255) / 256, 256, 0, ctx->stream>>>(tab, (const uint32_t*)ctx->sort_vals.p, n_sel,
                                                                          (unsigned long long*)ctx->u_profile.p, (unsigned long long*)ctx->u_count.p,
-                                                                         (double*)ctx->u_logM.p, (uint32_t*)ctx->entry_to_unique.p,
+                                                                         (double*)ctx->u_logM.p, (uint32_t*)e2u.p,
                                                                          ctl_field(ctx, &Control::nd_acc)[0]);
             TRY(check_launch(ctx, "k_hist_gather"));
             TRY(sync_ctl(ctx));
@@ -625,6 +768,12 @@ int build_histogram(sidgpu_ctx* ctx, uint32_t min_cov) {
     }
     ctx->hist_valid = true;
     return SIDGPU_OK;
+}
+
+int build_histogram(sidgpu_ctx* ctx, uint32_t min_cov) {
+    TRY(sync_ctl(ctx));
+    ctx->global_hist = false;
+    return build_histogram_of(ctx, ctx->tab, ctx->h_ctl->n_entries, min_cov, ctx->entry_to_unique);
 }
 
 int launch_objective(sidgpu_ctx* ctx, const double nd[4], double pi, double eps, double* d_out) {
@@ -658,13 +807,68 @@ int objective_value(sidgpu_ctx* ctx, const double nd[4], double pi, double eps, 
     return SIDGPU_OK;
 }
 
+int run_fit_host(sidgpu_ctx* ctx, const double nd[4], sidgpu_fit* out);
+
+// The whole Nelder-Mead fit as one cooperative kernel (k_lynch_fit); SIDGPU_FIT=host: the round-1 form, the simplex
+// on the host and one launch + read-back per objective evaluation.
 int run_fit(sidgpu_ctx* ctx, const double nd[4], sidgpu_fit* out) {
-    int rc = SIDGPU_OK;
-    auto f = [&](double pi, double eps) {
-        double v = std::numeric_limits<double>::quiet_NaN();
-        if (rc == SIDGPU_OK) rc = objective_value(ctx, nd, pi, eps, &v);
+    static const bool host_loop = getenv("SIDGPU_FIT") && strcmp(getenv("SIDGPU_FIT"), "host") == 0;
+    if (host_loop) return run_fit_host(ctx, nd, out);
+    if (!ctx->hist_valid) return ctx->fail(SIDGPU_ESTATE, "no histogram: call sidgpu_histogram or sidgpu_finish first");
+    ProfScope prof(ctx, PROF_FIT);
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_lynch_fit, OBJ_THREADS, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+    // one profile per thread while that fits on a quarter of the SMs (a small grid keeps the barrier cheap), then grid-stride
+    const uint64_t want = (ctx->n_unique + OBJ_THREADS - 1) / OBJ_THREADS;
+    const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(want, (uint64_t)ctx->sm_count * std::min(per_sm, 2)));
+    TRY(ensure(ctx, ctx->partials, (size_t)std::max<unsigned>(grid, (unsigned)ctx->sm_count * 4) * 4 * sizeof(double)));
+    CK(cudaMemsetAsync(ctl_field(ctx, &Control::fit_barrier), 0, sizeof(unsigned int), ctx->stream));
+    CK(cudaMemsetAsync(ctl_field(ctx, &Control::error), 0xFF, sizeof(unsigned long long), ctx->stream));
+    FitParams p {};
+    p.u_profile = (const unsigned long long*)ctx->u_profile.p;
+    p.u_count = (const unsigned long long*)ctx->u_count.p;
+    p.u_logM = (const double*)ctx->u_logM.p;
+    p.n_unique = (uint32_t)ctx->n_unique;
+    for (int i = 0; i < 4; ++i) p.nd[i] = nd[i];
+    p.x0[0] = p.x0[1] = 1e-3;                                        // lynch.cpp:8-10,20
+    p.step[0] = p.step[1] = 1e-4;
+    p.partials = (double*)ctx->partials.p;
+    p.barrier = ctl_field(ctx, &Control::fit_barrier);
+    p.out = ctl_field(ctx, &Control::fit_out)[0];
+    p.error = ctl_field(ctx, &Control::error);
+    void* args[] = {&p};
+    CK(cudaLaunchCooperativeKernel((const void*)k_lynch_fit, dim3(grid), dim3(OBJ_THREADS), args, 0, ctx->stream));
+    TRY(check_launch(ctx, "k_lynch_fit"));
+    TRY(sync_ctl(ctx));
+    if (ctx->h_ctl->error != ~0ull) return ctx->fail(SIDGPU_EINTERNAL, "k_lynch_fit: grid barrier timed out");
+    const double* r = ctx->h_ctl->fit_out;
+    out->pi = r[0];
+    out->eps = r[1];
+    out->fval = r[2];
+    out->iterations = (int)r[3];
+    out->evaluations = (int)r[4];
+    out->converged = r[5] != 0.0;
+    return SIDGPU_OK;
+}
+
+struct HostObjective {           // one device reduction + read-back per evaluation
+    sidgpu_ctx* ctx;
+    const double* nd;
+    int* rc;
+    SID_HD double operator()(double pi, double eps) {
+        double v = 0;
+#if !defined(__CUDA_ARCH__)
+        v = std::numeric_limits<double>::quiet_NaN();
+        if (*rc == SIDGPU_OK) *rc = objective_value(ctx, nd, pi, eps, &v);
+#endif
         return v;
-    };
+    }
+};
+
+int run_fit_host(sidgpu_ctx* ctx, const double nd[4], sidgpu_fit* out) {
+    ProfScope prof(ctx, PROF_FIT);
+    int rc = SIDGPU_OK;
+    HostObjective f {ctx, nd, &rc};
     const double x0[2] = {1e-3, 1e-3}, step[2] = {1e-4, 1e-4};       // lynch.cpp:8-10,20
     NelderMeadResult r = nelder_mead_2d(f, x0, step);
     if (rc != SIDGPU_OK) return rc;
@@ -821,6 +1025,11 @@ int sidgpu_create(const sidgpu_config* cfg, sidgpu_ctx** out) {
         (e = cudaFuncSetAttribute(k_tokenize<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tok_dyn_smem(SLICE_MAX, 2016))) != cudaSuccess ||
         (e = cudaFuncSetAttribute(k_tokenize<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tok_dyn_smem(SLICE_MAX, 2016))) != cudaSuccess ||
         (e = cudaFuncSetAttribute(k_tokenize<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tok_dyn_smem(SLICE_MAX, 2016))) != cudaSuccess ||
+        (e = cudaFuncSetAttribute(k_tok2<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tok2_dyn_smem(SLICE_MAX, 2016, 1, false))) != cudaSuccess ||
+        (e = cudaFuncSetAttribute(k_tok2<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::min<uint32_t>(227u << 10, tok2_dyn_smem(SLICE_MAX, 2016, 2, false)))) != cudaSuccess ||
+        (e = cudaFuncSetAttribute(k_tok2<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tok2_dyn_smem(SLICE_MAX, 2016, 1, true))) != cudaSuccess ||
+        (e = cudaFuncSetAttribute(k_tok2<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::min<uint32_t>(227u << 10, tok2_dyn_smem(SLICE_MAX, 2016, 2, true)))) != cudaSuccess ||
+        (e = cudaFuncSetAttribute(k_rows_compact, cudaFuncAttributeMaxDynamicSharedMemorySize, (RC_THREADS / 32) * RC_STAGE)) != cudaSuccess ||
         (e = cudaFuncSetAttribute(k_csv, cudaFuncAttributeMaxDynamicSharedMemorySize, CSV_STAGE)) != cudaSuccess) {
         ctx->err = std::string("shared memory opt-in: ") + cudaGetErrorString(e);
         return bail(SIDGPU_ECUDA);
@@ -850,8 +1059,8 @@ void sidgpu_destroy(sidgpu_ctx* ctx) {
     cudaFree(ctx->names.slots);
     cudaFree(ctx->names.pool);
     for (DevBuf* b : {&ctx->blk, &ctx->blk_part, &ctx->order, &ctx->v_pos, &ctx->v_slot, &ctx->v_name_ref, &ctx->v_profile, &ctx->v_line_off, &ctx->csv_status, &ctx->pos, &ctx->slot, &ctx->name_ref, &ctx->profile, &ctx->line_off,
-                      &ctx->site_suffix, &ctx->sort_keys, &ctx->sort_vals, &ctx->u_profile, &ctx->u_count, &ctx->u_logM,
-                      &ctx->entry_to_unique, &ctx->p_hom, &ctx->p_het, &ctx->adj_hom, &ctx->adj_het, &ctx->bh_c, &ctx->bh_block,
+                      &ctx->site_suffix, &ctx->rows_scratch, &ctx->rows_part, &ctx->rows_part_rows, &ctx->sort_keys, &ctx->sort_vals, &ctx->u_profile, &ctx->u_count, &ctx->u_logM,
+                      &ctx->entry_to_unique, &ctx->g_e2u, &ctx->p_hom, &ctx->p_het, &ctx->adj_hom, &ctx->adj_het, &ctx->bh_c, &ctx->bh_block,
                       &ctx->partials, &ctx->quality_lut})
         release(*b);
     if (ctx->d_ctl) cudaFree(ctx->d_ctl);
@@ -866,15 +1075,15 @@ int sidgpu_profile(sidgpu_ctx* ctx, int enable) {
     if (!ctx) return SIDGPU_EINVAL;
     resolve_profile(ctx);
     ctx->profiling = enable != 0;
-    for (int i = 0; i < 4; ++i) { ctx->kernel_ms[i] = 0; ctx->kernel_launches[i] = 0; }
+    for (int i = 0; i < SIDGPU_N_TIMERS; ++i) { ctx->kernel_ms[i] = 0; ctx->kernel_launches[i] = 0; }
     return SIDGPU_OK;
 }
 
-int sidgpu_kernel_times(sidgpu_ctx* ctx, double ms[4], uint64_t launches[4]) {
+int sidgpu_kernel_times(sidgpu_ctx* ctx, double ms[SIDGPU_N_TIMERS], uint64_t launches[SIDGPU_N_TIMERS]) {
     if (!ctx) return SIDGPU_EINVAL;
     CK(cudaStreamSynchronize(ctx->stream));
     resolve_profile(ctx);
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < SIDGPU_N_TIMERS; ++i) {
         if (ms) ms[i] = ctx->kernel_ms[i];
         if (launches) launches[i] = ctx->kernel_launches[i];
     }
@@ -912,6 +1121,12 @@ int sidgpu_free_host(sidgpu_ctx* ctx, void* h_ptr) {
 int sidgpu_memcpy_h2d(sidgpu_ctx* ctx, void* d_dst, const void* h_src, size_t bytes) {
     if (!ctx) return SIDGPU_EINVAL;
     CK(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return SIDGPU_OK;
+}
+int sidgpu_memcpy_d2d(sidgpu_ctx* ctx, void* d_dst, const void* d_src, size_t bytes) {
+    if (!ctx) return SIDGPU_EINVAL;
+    CK(cudaMemcpyAsync(d_dst, d_src, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return SIDGPU_OK;
 }
@@ -980,6 +1195,7 @@ int sidgpu_begin(sidgpu_ctx* ctx, const sidgpu_params* params) {
     ctx->want_site_suffix = params->method == SIDGPU_METHOD_QUALITY;
     ctx->session_prior = params->prior;
     ctx->fit_done = false;
+    ctx->global_hist = false;
     ctx->fit = sidgpu_fit {};
     ctx->n_sites_total = 0;
     ctx->chunk_begin = ctx->chunk_sites = 0;
@@ -1021,12 +1237,34 @@ int sidgpu_feed(sidgpu_ctx* ctx, const char* d_text, size_t text_len, size_t ran
     return SIDGPU_OK;
 }
 
+int sidgpu_feed_rows(sidgpu_ctx* ctx, const char* d_text, size_t text_len, size_t range_begin, size_t range_end, char* d_out, size_t out_cap,
+                     uint64_t* bytes_out, uint64_t* rows_out, uint64_t* n_sites_out) {
+    if (!ctx || (out_cap && !d_out)) return SIDGPU_EINVAL;
+    if (ctx->phase != PHASE_FEED) return ctx->fail(SIDGPU_ESTATE, "sidgpu_feed_rows outside a session");
+    if (!(ctx->streaming && ctx->params.method == SIDGPU_METHOD_LOCAL))
+        return ctx->fail(SIDGPU_EINVAL, "sidgpu_feed_rows is for `local` sessions without -R (rows need no genome-wide step); use sidgpu_feed + sidgpu_emit_csv");
+    CK(cudaSetDevice(ctx->device));
+    uint64_t bytes = 0, rows = 0, n = 0;
+    const int rc = run_tok2_rows(ctx, d_text, text_len, range_begin, range_end, d_out, out_cap, &bytes, &rows, &n);
+    if (rc == SIDGPU_ECAPACITY && bytes_out) *bytes_out = bytes;       // the size the caller has to offer
+    if (rc != SIDGPU_OK) return rc;
+    ctx->last_text = d_text;
+    ctx->last_text_len = text_len;
+    ctx->chunk_begin = 0;
+    ctx->chunk_sites = 0;
+    ctx->n_sites_total = 0;                 // no site store: rows of this chunk exist only in d_out
+    if (bytes_out) *bytes_out = bytes;
+    if (rows_out) *rows_out = rows;
+    if (n_sites_out) *n_sites_out = n;
+    return SIDGPU_OK;
+}
+
 int sidgpu_finish(sidgpu_ctx* ctx) {
     if (!ctx) return SIDGPU_EINVAL;
     if (ctx->phase != PHASE_FEED) return ctx->fail(SIDGPU_ESTATE, "sidgpu_finish outside a session");
     CK(cudaSetDevice(ctx->device));
     if (!ctx->streaming) {
-        TRY(build_histogram(ctx, 4));                                   // call.cpp:66-70,149-153,224-229,296-301
+        if (!ctx->global_hist) TRY(build_histogram(ctx, 4));            // call.cpp:66-70,149-153,224-229,296-301
         if (ctx->params.fit_given) {
             ctx->fit.pi = ctx->params.fit_pi;
             ctx->fit.eps = ctx->params.fit_eps;
@@ -1263,6 +1501,41 @@ int sidgpu_count_unique_weighted(sidgpu_ctx* ctx, const uint64_t* d_profiles, co
                                  uint32_t min_coverage, sidgpu_unique_view* out) {
     if (n && !d_counts) return SIDGPU_EINVAL;
     return count_unique_impl(ctx, d_profiles, d_counts, n, min_coverage, out);
+}
+
+int sidgpu_set_global_histogram(sidgpu_ctx* ctx, const uint64_t* d_profiles, const uint64_t* d_counts, uint64_t n) {
+    if (!ctx || (n && (!d_profiles || !d_counts))) return SIDGPU_EINVAL;
+    if (ctx->phase != PHASE_FEED || ctx->streaming) return ctx->fail(SIDGPU_ESTATE, "sidgpu_set_global_histogram needs an open session with a genome-wide step");
+    if (n > 0x3FFFFFFFull) return ctx->fail(SIDGPU_EINVAL, "too many histogram entries");
+    CK(cudaSetDevice(ctx->device));
+    int log2cap = 12;
+    while (((uint64_t)1 << log2cap) < 2 * n + 2) ++log2cap;
+    TableView g;
+    CK(cudaMemsetAsync(ctl_field(ctx, &Control::g_n_entries), 0, 3 * sizeof(unsigned int), ctx->stream));
+    TRY(alloc_table(ctx, log2cap, g, true));
+    int rc = SIDGPU_OK;
+    if (n) {
+        k_insert_profiles<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(g, d_profiles, d_counts, n);
+        rc = check_launch(ctx, "k_insert_profiles");
+    }
+    if (rc == SIDGPU_OK) rc = sync_ctl(ctx);
+    if (rc == SIDGPU_OK && ctx->h_ctl->g_overflow) rc = ctx->fail(SIDGPU_EINTERNAL, "merged histogram table overflow");
+    // entries with count 0 (padding of the all-gather) and coverage < 4 (call.cpp:66-70) are left out by the selection
+    if (rc == SIDGPU_OK) rc = build_histogram_of(ctx, g, ctx->h_ctl->g_n_entries, 4, ctx->g_e2u);
+    if (rc == SIDGPU_OK) {
+        const uint32_t n_entries = ctx->h_ctl->n_entries;
+        rc = ensure(ctx, ctx->entry_to_unique, (size_t)std::max<uint32_t>(n_entries, 1) * 4);
+        if (rc == SIDGPU_OK && n_entries) {
+            // this rank's own profiles -> their rows in the merged list
+            k_map_entries<<<(n_entries + 255) / 256, 256, 0, ctx->stream>>>(ctx->tab, n_entries, (const unsigned long long*)ctx->u_profile.p,
+                                                                             (uint32_t)ctx->n_unique, (uint32_t*)ctx->entry_to_unique.p);
+            rc = check_launch(ctx, "k_map_entries");
+        }
+    }
+    cudaStreamSynchronize(ctx->stream);
+    free_table(g);
+    if (rc == SIDGPU_OK) ctx->global_hist = true;
+    return rc;
 }
 
 int sidgpu_set_fit(sidgpu_ctx* ctx, double pi, double eps, const double nd[4]) {

@@ -27,6 +27,18 @@ struct TableView {
     double* het;
 };
 
+// Hash of a packed profile: two 32-bit multiplies and a finaliser (the FMA pipe; the 64-bit mix64 costs three times
+// as many instructions on the tokenizer's critical pipe).
+SID_HD uint32_t table_hash(uint64_t key) {
+    uint32_t h = ((uint32_t)key * 0x9E3779B1u) ^ ((uint32_t)(key >> 32) * 0x85EBCA77u);
+    h ^= h >> 15;
+    h *= 0x2C1B3C6Du;
+    h ^= h >> 13;
+    return h;
+}
+
+constexpr uint32_t SUFFIX_READY = 0x80u;   // bit 7 of a suffix record's last byte: the record is complete (low bits: length)
+
 #if defined(__CUDACC__)
 
 __device__ __forceinline__ uint32_t table_find_or_insert(const TableView& t, uint64_t key) {
@@ -37,7 +49,7 @@ __device__ __forceinline__ uint32_t table_find_or_insert(const TableView& t, uin
         }
         return t.cap;
     }
-    uint32_t h = (uint32_t)mix64(key) & t.mask;
+    uint32_t h = table_hash(key) & t.mask;
     for (uint32_t probes = 0; probes <= t.mask; ++probes) {
         unsigned long long k = *((volatile unsigned long long*)&t.keys[h]);
         if (k == key) return h;
@@ -57,7 +69,7 @@ __device__ __forceinline__ uint32_t table_find_or_insert(const TableView& t, uin
 
 __device__ __forceinline__ uint32_t table_find(const TableView& t, uint64_t key) {
     if (key == TABLE_EMPTY) return t.cap;
-    uint32_t h = (uint32_t)mix64(key) & t.mask;
+    uint32_t h = table_hash(key) & t.mask;
     for (uint32_t probes = 0; probes <= t.mask; ++probes) {
         const unsigned long long k = t.keys[h];
         if (k == key) return h;

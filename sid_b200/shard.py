@@ -3,10 +3,16 @@
 The pileup text is cut into contiguous byte ranges, one per rank.  A rank owns the lines whose FIRST
 byte lies in its range (the tokenizer kernel applies the rule itself, so ranges may cut lines
 anywhere); `local` and `quality` need no communication at all.  Methods with a Lynch fit exchange
-  * five integers once (the nucleotide-distribution sums), and
-  * one double per optimiser evaluation (each rank's partial of compoundLikelihood, lynch.cpp:37-61),
-both as NCCL all-reduces (gloo on CPU in the tests).  Every rank then runs the identical
-Nelder-Mead trajectory and classifies its own sites."""
+their unique-profile histograms ONCE: an NCCL all-gather of (profile, count) pairs, a few thousand per
+rank.  Every rank merges them on its device (sidgpu_set_global_histogram: counts summed, lexicographic
+order = countUniqueProfiles of the whole genome) and runs the whole Nelder-Mead fit as one kernel on
+the merged histogram: identical input, identical code, so (pi, eps) are bit-identical on every rank and
+for every number of ranks, with no traffic per optimiser step.  likelihood_ratio's Benjamini-Hochberg
+ranks (m = unique profiles of the whole genome) come from the same merged list.
+
+The literal north_star form -- each rank reduces its own histogram and the ranks all-reduce ONE double
+per objective evaluation (lynch.cpp:37-61) -- is kept as `per_evaluation_allreduce=True` (and as the
+gloo-tested distributed_fit); bench.py times both."""
 from . import nelder_mead
 
 
@@ -95,7 +101,41 @@ def torch_collectives(dist, device):
     return ints, flt
 
 
-def call_sharded(ctx, d_text, text_len, rank, world, params, dist=None, device=None):
+def all_gather_histograms(dist, prof, cnt):
+    """All-gather of every rank's (profiles, counts) histogram (int64 tensors of any, rank-dependent, length on the
+    collective's device).  Returns (profiles, counts) of world * max_length entries; the padding has count 0."""
+    import torch
+    world = dist.get_world_size()
+    n = torch.tensor([prof.numel()], dtype=torch.int64, device=prof.device)
+    dist.all_reduce(n, op=dist.ReduceOp.MAX)
+    m = max(1, int(n.item()))
+    p = torch.zeros(m, dtype=torch.int64, device=prof.device)
+    c = torch.zeros(m, dtype=torch.int64, device=prof.device)
+    p[:prof.numel()] = prof
+    c[:cnt.numel()] = cnt
+    gp = torch.empty(world * m, dtype=torch.int64, device=prof.device)
+    gc = torch.empty(world * m, dtype=torch.int64, device=prof.device)
+    dist.all_gather_into_tensor(gp, p)
+    dist.all_gather_into_tensor(gc, c)
+    return gp, gc
+
+
+def exchange_histograms(ctx, dist, device):
+    """The collective step of a sharded session with a genome-wide fit: all-gather of the ranks' histograms (NCCL),
+    merge on this rank's device.  Returns the number of gathered entries."""
+    import torch
+    n_u, d_prof, d_cnt = ctx.histogram_device(4)
+    prof = torch.empty(n_u, dtype=torch.int64, device=device)
+    cnt = torch.empty(n_u, dtype=torch.int64, device=device)
+    ctx.copy_d2d(prof.data_ptr(), d_prof, 8 * n_u)          # synchronises the ctx's stream: ordered before the collective
+    ctx.copy_d2d(cnt.data_ptr(), d_cnt, 8 * n_u)
+    gp, gc = all_gather_histograms(dist, prof, cnt)
+    torch.cuda.current_stream().synchronize()               # the collective ran on torch's stream, the merge runs on the ctx's
+    ctx.set_global_histogram(gp.data_ptr(), gc.data_ptr(), gp.numel())
+    return gp.numel()
+
+
+def call_sharded(ctx, d_text, text_len, rank, world, params, dist=None, device=None, per_evaluation_allreduce=False):
     """Runs one calling session on this rank's shard of a device-resident text that every rank
     holds (or at least its own range plus the straddling line).  Returns (n_sites, fit or None);
     rows are then available through ctx.emit_csv(0, n_sites, ...)."""
@@ -105,6 +145,10 @@ def call_sharded(ctx, d_text, text_len, rank, world, params, dist=None, device=N
     n = ctx.feed(d_text, text_len, begin, end)
     needs_fit = params.method in (1, 2) or params.estimate_prior
     fit = None
+    if needs_fit and world > 1 and not params.fit_given and not per_evaluation_allreduce:
+        exchange_histograms(ctx, dist, device)
+        ctx.finish()
+        return n, ctx.session_fit()
     if needs_fit and world > 1 and not params.fit_given:
         ints, flt = torch_collectives(dist, device)
         obj = torch.zeros(1, dtype=torch.float64, device=device)
@@ -120,10 +164,14 @@ def call_sharded(ctx, d_text, text_len, rank, world, params, dist=None, device=N
         if params.method == 2:
             # Benjamini-Hochberg ranks over the unique profiles of the whole genome: gather the shards'
             # histograms (a few thousand entries each), merge on the host, finish on the device
-            local = ctx.histogram(4)[:2]
-            gathered = [None] * world
-            dist.all_gather_object(gathered, (local[0], local[1]))
-            merged, _ = merge_histograms(gathered)
+            n_u, d_prof, d_cnt = ctx.histogram_device(4)
+            prof = torch.empty(n_u, dtype=torch.int64, device=device)
+            cnt = torch.empty(n_u, dtype=torch.int64, device=device)
+            ctx.copy_d2d(prof.data_ptr(), d_prof, 8 * n_u)
+            ctx.copy_d2d(cnt.data_ptr(), d_cnt, 8 * n_u)
+            gp, gc = all_gather_histograms(dist, prof, cnt)
+            keep = gc.cpu().numpy() > 0
+            merged, _ = merge_histograms([(gp.cpu().numpy().view("uint64")[keep], gc.cpu().numpy().view("uint64")[keep])])
             ctx.finish_global(merged)
             return n, fit
     ctx.finish()

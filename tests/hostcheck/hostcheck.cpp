@@ -14,6 +14,8 @@
 #ifdef SID_HAVE_FAST
 #include "parse_swar.hpp"
 #include "../../sid_b200/csrc/parse_bits.cuh"
+#include "../../sid_b200/csrc/parse_win.cuh"
+#include "../../sid_b200/csrc/row_assemble.cuh"
 #endif
 
 using namespace sid;
@@ -147,6 +149,78 @@ void hc_classify32(const uint8_t* bytes, uint32_t* out) {
     const ClassWords k = classify32(w);
     out[0] = k.term; out[1] = k.nl; out[2] = k.a; out[3] = k.c; out[4] = k.g; out[5] = k.t; out[6] = k.dot; out[7] = k.caret;
     out[8] = k.pm; out[9] = k.high;
+}
+#endif
+
+#ifdef SID_HAVE_FAST
+// The window tokenizer (parse_win.cuh) against the byte-wise one on every line of a text.  Returns the number of
+// lines, or -(k+1) when line k differs; *n_fast receives how many lines the fast grammar accepted.  Checks the
+// profile, the name, the position (WANT_POS form) and, for the row writer, that "canonical" means exactly that the
+// digits in the text are what printf("%d") prints for the position.
+int64_t hc_compare_parsers_win(const uint8_t* text, uint64_t len, uint64_t* n_fast) {
+    FlatSrc src {text, len};
+    int64_t k = 0;
+    uint64_t fast = 0;
+    for (uint64_t p = 0; p < len; ++p) {
+        if (text[p] == '\n' || (p > 0 && text[p - 1] != '\n')) continue;
+        ParsedLine a;
+        parse_line(src, p, false, a);
+        WinLine b, c;
+        const bool fb = parse_line_win_host<true>(text, len, p, b), fc = parse_line_win_host<false>(text, len, p, c);
+        if (fb != fc) return -(k + 1);
+        if (fb) {
+            ++fast;
+            if (a.status != LINE_OK || b.status != LINE_OK || a.profile != b.profile || a.pos != b.pos || c.profile != a.profile ||
+                a.chrom_off != 0 || a.chrom_len != b.name_len || c.name_len != b.name_len || b.hdr_len != c.hdr_len ||
+                b.pos_canonical != c.pos_canonical) return -(k + 1);
+            char digits[16];
+            const int nd = fmt_i32(a.pos, digits);
+            const bool same_text = b.hdr_len == a.chrom_len + 1 + (uint32_t)nd && memcmp(text + p + a.chrom_len + 1, digits, nd) == 0;
+            if (same_text != b.pos_canonical) return -(k + 1);
+        }
+        ++k;
+    }
+    if (n_fast) *n_fast = fast;
+    return k;
+}
+
+// The two-phase row assembly of the fused CSV writer, as a warp would run it: phase A of all `n` lanes in the order
+// `order` gives (a warp-wide store with overlapping words has no defined winner), then phase B.  text: staged text
+// (4-byte aligned), line_off/hdr_len/name_len/sfx_len per lane, sfx 48 bytes per lane; rows are laid end to end from
+// offset d0 of `stage`.  Returns the offset after the last row.
+uint32_t hc_assemble_rows(const uint8_t* text, uint8_t* stage, uint32_t d0, uint32_t n, const uint32_t* order, const uint32_t* line_off,
+                          const uint32_t* hdr_len, const uint32_t* name_len, const uint8_t* sfx, const uint32_t* sfx_len) {
+    RowSrc rows[32];
+    uint32_t d[33], first[32], hw = 0, sxw = 0;
+    d[0] = d0;
+    for (uint32_t j = 0; j < n; ++j) {
+        rows[j].line_off = line_off[j]; rows[j].hdr_len = hdr_len[j]; rows[j].name_len = name_len[j]; rows[j].sfx_len = sfx_len[j];
+        memcpy(rows[j].sfx, sfx + 48 * j, 48);
+        const uint32_t len = sfx_len[j] ? hdr_len[j] + sfx_len[j] : 0;
+        d[j + 1] = d[j] + len;
+        if (len) {
+            const uint32_t a = d[j] & 3u, a2 = (d[j] + hdr_len[j]) & 3u;
+            hw = hw > ((a + hdr_len[j] + 3) >> 2) ? hw : ((a + hdr_len[j] + 3) >> 2);
+            sxw = sxw > ((a2 + sfx_len[j] + 3) >> 2) ? sxw : ((a2 + sfx_len[j] + 3) >> 2);
+        }
+    }
+    for (uint32_t i = 0; i < n; ++i) {
+        const uint32_t j = order[i];
+        if (d[j + 1] > d[j]) first[j] = row_phase_a(text, stage, d[j], rows[j], hw, sxw);
+    }
+    for (uint32_t j = 0; j < n; ++j)
+        if (d[j + 1] > d[j]) row_phase_b(stage, d[j], rows[j], first[j]);
+    return d[n];
+}
+
+// classify_unit on one 32-byte unit: out[0..9] = term base p1 p2 dot caret pm digit nl bad
+void hc_classify_unit(const uint8_t* bytes, uint32_t* out) {
+    uint32_t w[8];
+    memcpy(w, bytes, 32);
+    const UnitClasses k = classify_unit(w);
+    for (int c = 0; c < CW_WORDS; ++c) out[c] = k.w[c];
+    out[8] = k.nl;
+    out[9] = k.bad;
 }
 #endif
 

@@ -190,6 +190,9 @@ def hostcheck():
             h.hc_compare_parsers_bits.restype = ctypes.c_int64
             h.hc_compare_parsers_bits.argtypes = [ctypes.c_char_p, ctypes.c_uint64, ctypes.POINTER(ctypes.c_uint64)]
             h.hc_classify32.argtypes = [ctypes.c_char_p, ctypes.POINTER(ctypes.c_uint32)]
+            h.hc_compare_parsers_win.restype = ctypes.c_int64
+            h.hc_compare_parsers_win.argtypes = [ctypes.c_char_p, ctypes.c_uint64, ctypes.POINTER(ctypes.c_uint64)]
+            h.hc_classify_unit.argtypes = [ctypes.c_char_p, ctypes.POINTER(ctypes.c_uint32)]
         h.hc_fmt_g6.argtypes = [ctypes.c_double, ctypes.c_char_p]
         h.hc_fmt_i32.argtypes = [ctypes.c_int32, ctypes.c_char_p]
         h.hc_major_alleles.argtypes = [ctypes.c_uint64, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]

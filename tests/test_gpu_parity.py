@@ -286,6 +286,61 @@ def test_emit_sub_ranges_concatenate(native, gpu_ctx):
         d.free()
 
 
+@pytest.mark.parametrize("name", ["edge.plp", "depth30.plp", "depth500.plp", "depth5.plp", "depth30_two_chroms.plp", "quality30.plp"])
+@pytest.mark.parametrize("het_only", [0, 1])
+def test_feed_rows_matches_reference(native, gpu_ctx, name, het_only):
+    """sidgpu_feed_rows (the tokenizer kernel classifies new profiles and writes the rows itself) against the reference's
+    CSV: whole text, and byte ranges cut anywhere whose rows must concatenate to the same bytes."""
+    import sid_b200
+    text = read(name)
+    o = op.oracle_call(text, "local")
+    want = o["csv"].split(b"\n", 1)[1]
+    if het_only:
+        want = b"".join(l for l in want.splitlines(keepends=True) if b",het," in l)
+    d = gpu_ctx.upload_text(text)
+    cap = 2 * len(text) + 4096
+    out = sid_b200.api.DeviceBuffer(gpu_ctx, cap)
+    try:
+        p = sid_b200.Context.make_params("local", het_only=bool(het_only))
+        gpu_ctx.begin(p)
+        nbytes, rows, n = gpu_ctx.feed_rows(d, len(text), out, cap)
+        got = out.download(np.uint8, nbytes).tobytes()
+        assert n == o["n_sites"]
+        assert rows == want.count(b"\n")
+        k, diffs = op.compare_csv(got, want)
+        assert k == rows and diffs <= max(2, k // 1000)
+        # ranges: a fresh session (the table starts empty again), cuts in the middle of lines
+        gpu_ctx.begin(p)
+        cuts = [0, 1, len(text) // 5, len(text) // 5 + 1, len(text) // 2 + 3, len(text) - 1, len(text)]
+        pieces, total_sites = b"", 0
+        for a, b in zip(cuts[:-1], cuts[1:]):
+            nb, r, ns = gpu_ctx.feed_rows(d, len(text), out, cap, a, b)
+            pieces += out.download(np.uint8, nb).tobytes() if nb else b""
+            total_sites += ns
+        assert total_sites == n and pieces == got
+    finally:
+        out.free()
+        d.free()
+
+
+def test_feed_rows_tiny_output_buffer(native, gpu_ctx):
+    import sid_b200
+    text = read("depth30.plp")
+    d = gpu_ctx.upload_text(text)
+    out = sid_b200.api.DeviceBuffer(gpu_ctx, 1024)
+    try:
+        gpu_ctx.begin(sid_b200.Context.make_params("local"))
+        with pytest.raises(sid_b200.SidGpuError) as e:
+            gpu_ctx.feed_rows(d, len(text), out, 1024)
+        assert e.value.code == 6
+        with pytest.raises(sid_b200.SidGpuError):
+            gpu_ctx.begin(sid_b200.Context.make_params("bayes"))
+            gpu_ctx.feed_rows(d, len(text), out, 1024)
+    finally:
+        out.free()
+        d.free()
+
+
 @pytest.mark.parametrize("case", MANIFEST["malformed"], ids=lambda c: c["input"])
 def test_malformed_raises(native, gpu_ctx, case):
     import sid_b200

@@ -284,6 +284,115 @@ def test_bit_tokenizer_covers_normal_text(native, name):
         assert nf.value == k
 
 
+def test_classify_unit_equals_per_byte_classes(native):
+    """Round-2 classifier (one BASE class + raw bit planes 1 and 2, digits, control bytes) against per-byte definitions."""
+    hc = op.hostcheck()
+    rnd = random.Random(19)
+    units = [bytes((32 * k + i) & 0xFF for i in range(32)) for k in range(8)]
+    units += [bytes(rnd.getrandbits(8) for _ in range(32)) for _ in range(2000)]
+    units += [bytes(rnd.choice(b".,ACGTacgtNn*$^+-0123456789\t\n ~") for _ in range(32)) for _ in range(2000)]
+    out = (ctypes.c_uint32 * 10)()
+    defs = [lambda b: b <= 0x20, lambda b: b in b"AaCcGgTt", lambda b: (b >> 1) & 1, lambda b: (b >> 2) & 1, lambda b: b in b".,",
+            lambda b: b == ord("^"), lambda b: b in b"+-", lambda b: 48 <= b <= 57, lambda b: b == 10,
+            lambda b: b < 0x20 and b not in (9, 10)]
+    for u in units:
+        hc.hc_classify_unit(u, out)
+        for k, f in enumerate(defs):
+            want = sum(1 << i for i in range(32) if f(u[i]))
+            assert out[k] == want, (k, u)
+    # the letter code the counts rest on: (p2, p1) = A 00, C 01, G 11, T 10
+    for ch, code in ((b"A", 0), (b"a", 0), (b"C", 1), (b"c", 1), (b"G", 3), (b"g", 3), (b"T", 2), (b"t", 2)):
+        assert ((ch[0] >> 1) & 1) | (((ch[0] >> 2) & 1) << 1) == code
+
+
+def test_row_assembly_two_phases(native):
+    """The fused CSV writer's row assembly (word moves with funnel shifts, shared words settled in a second phase):
+    groups of up to 32 rows with every alignment of source line, header length and destination offset, lanes of
+    phase A in random order, rows of length 0 (het-only) in between."""
+    hc = op.hostcheck()
+    hc.hc_assemble_rows.restype = ctypes.c_uint32
+    hc.hc_assemble_rows.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32] + [ctypes.c_void_p] * 6
+    rnd = random.Random(29)
+    for trial in range(600):
+        n = rnd.choice([1, 2, 5, 31, 32])
+        lines, want = [], b""
+        text = bytearray(b"\n" * 16)
+        line_off, hdr_len, name_len, sfx, sfx_len = [], [], [], bytearray(), []
+        for j in range(n):
+            name = "".join(rnd.choice("chrXY1234_") for _ in range(rnd.choice([1, 2, 4, 5, 12, 20])))
+            pos = str(rnd.choice([1, 12, 123, 99999, 123456789, rnd.randrange(1, 10 ** 9)]))
+            while len(name) + 1 + len(pos) > 26:
+                name = name[:-1]
+            rest = "\tA\t3\t" + "".join(rnd.choice(".,ACGT") for _ in range(rnd.randrange(1, 40))) + "\tIII\n"
+            line_off.append(len(text))
+            text += (name + "\t" + pos + rest).encode()
+            hdr_len.append(len(name) + 1 + len(pos))
+            name_len.append(len(name))
+            sx = rnd.choice([b",hom,AA,0.000196638,1,p_value\n", b",het,CA,1,4.13196e-06,p_value\n", b",hom,TT,1,1,p_value\n", b"",
+                             b",het,AC,1.23457e-308,1.23457e-308,probability\n"])
+            sfx += sx + bytes(48 - len(sx))
+            sfx_len.append(len(sx))
+            if sx:
+                want += (name + "," + pos).encode() + sx
+        text += b"\n" * 64
+        while len(text) % 4:
+            text += b"\n"
+        d0 = rnd.randrange(0, 16)
+        stage = bytearray(b"\xAA" * (d0 + len(want) + 64))
+        order = list(range(n))
+        rnd.shuffle(order)
+        A = lambda v: (ctypes.c_uint32 * len(v))(*v)
+        tb = (ctypes.c_uint8 * len(text)).from_buffer(text)
+        sb = (ctypes.c_uint8 * len(stage)).from_buffer(stage)
+        xb = (ctypes.c_uint8 * len(sfx)).from_buffer(sfx)
+        end = hc.hc_assemble_rows(ctypes.addressof(tb), ctypes.addressof(sb), d0, n, A(order), A(line_off), A(hdr_len), A(name_len),
+                                  ctypes.addressof(xb), A(sfx_len))
+        assert end == d0 + len(want)
+        assert bytes(stage[:d0]) == b"\xAA" * d0, "bytes before the first row were touched"
+        assert bytes(stage[d0:end]) == want, (trial, bytes(stage[d0:end]), want)
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3, 6, 7])
+def test_window_tokenizer_equals_scalar_on_adversarial_lines(native, seed):
+    hc = op.hostcheck()
+    text = _adversarial_text(seed, 20000)
+    nf = ctypes.c_uint64()
+    k = hc.hc_compare_parsers_win(text, len(text), ctypes.byref(nf))
+    assert k > 0, text.split(b"\n")[-k - 1][:200] if k < 0 else None
+    assert nf.value > k // 100
+
+
+@pytest.mark.parametrize("name", ["depth30.plp", "depth500.plp", "depth5.plp", "quality30.plp", "edge.plp", "depth30_two_chroms.plp"])
+def test_window_tokenizer_covers_normal_text(native, name):
+    hc = op.hostcheck()
+    text = read(name)
+    nf = ctypes.c_uint64()
+    k = hc.hc_compare_parsers_win(text, len(text), ctypes.byref(nf))
+    assert k > 0, text.split(b"\n")[-k - 1][:200] if k < 0 else None
+    if name != "edge.plp":
+        assert nf.value == k          # every ordinary line is handled without the byte-wise fallback
+
+
+def test_window_tokenizer_long_fields_and_indels_at_window_ends(native):
+    """Signs, numbers, '^' and skipped stretches placed at every offset around the 64-byte window boundaries."""
+    hc = op.hostcheck()
+    rnd = random.Random(23)
+    lines = []
+    for k in range(6000):
+        pre = rnd.randrange(0, 140)
+        mid = rnd.choice(["+3ACG", "-12ACGTACGTACGT", "^+", "^1", "+", "-", "+0", "-1a", "^~", "+25" + "acgtn" * 5, "$", "^]", "+100" + "A" * 100,
+                          "-70" + "c" * 70, "^-", "+9", "+3ac"])
+        post = rnd.randrange(0, 90)
+        bases = "".join(rnd.choice(".,ACGTacgt") for _ in range(pre)) + mid + "".join(rnd.choice(".,ACGTacgt*") for _ in range(post))
+        lines.append("%s\t%d\t%s\t%d\t%s\t%s" % (rnd.choice(["chr1", "c", "chr12_random"]), rnd.choice([1, 99, 123456789, 10 ** rnd.randrange(0, 9)]),
+                                                   rnd.choice("ACGTNacgt"), len(bases), bases, "I" * rnd.randrange(1, 50)))
+    text = ("\n".join(lines) + "\n").encode()
+    nf = ctypes.c_uint64()
+    k = hc.hc_compare_parsers_win(text, len(text), ctypes.byref(nf))
+    assert k == len(lines), text.split(b"\n")[-k - 1][:300] if k < 0 else None
+    assert nf.value == k
+
+
 @pytest.mark.parametrize("name", ["quality30.plp", "edge_quality.plp", "depth30.plp", "depth500.plp", "edge.plp"])
 def test_quality_fields_equal_parse_line(native, name):
     """The lean field scan of the quality kernel returns parse_line's offsets, lengths and status."""
