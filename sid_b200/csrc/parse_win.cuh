@@ -102,19 +102,25 @@ struct Win64 {              // one 64-bit window of every class
 };
 
 // The classes of the 64 bytes starting at bit `pos` of the class arrays (pos + 64 must lie within the padded arrays).
+// RING_UNITS != 0: the class arrays are a ring of that many units (a power of two); unit indices wrap.
+template <uint32_t RING_UNITS = 0>
 SID_HD Win64 load_window(const uint32_t* cw, uint32_t pos) {
     const uint32_t u = pos >> 5, sh = pos & 31;
     uint32_t a[3][CW_WORDS];
 #if defined(__CUDA_ARCH__)
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-        const uint4 lo = *reinterpret_cast<const uint4*>(cw + (size_t)(u + k) * CW_WORDS);
-        const uint4 hi = *reinterpret_cast<const uint4*>(cw + (size_t)(u + k) * CW_WORDS + 4);
+        const uint32_t uu = RING_UNITS ? ((u + k) & (RING_UNITS - 1u)) : (u + k);
+        const uint4 lo = *reinterpret_cast<const uint4*>(cw + (size_t)uu * CW_WORDS);
+        const uint4 hi = *reinterpret_cast<const uint4*>(cw + (size_t)uu * CW_WORDS + 4);
         a[k][0] = lo.x; a[k][1] = lo.y; a[k][2] = lo.z; a[k][3] = lo.w;
         a[k][4] = hi.x; a[k][5] = hi.y; a[k][6] = hi.z; a[k][7] = hi.w;
     }
 #else
-    for (int k = 0; k < 3; ++k) for (int c = 0; c < CW_WORDS; ++c) a[k][c] = cw[(size_t)(u + k) * CW_WORDS + c];
+    for (int k = 0; k < 3; ++k) {
+        const uint32_t uu = RING_UNITS ? ((u + k) & (RING_UNITS - 1u)) : (u + k);
+        for (int c = 0; c < CW_WORDS; ++c) a[k][c] = cw[(size_t)uu * CW_WORDS + c];
+    }
 #endif
     uint64_t v[CW_WORDS];
 #pragma unroll
@@ -131,13 +137,18 @@ SID_HD uint64_t low_bits64(uint32_t n) { return n >= 64 ? ~0ull : ((1ull << n) -
 // `s`: staged text (4-byte aligned, byte 0 of the class arrays is s[region_off]); `cw`: class words (array of
 // structures) of n_bits classified bytes followed by CW_PAD_UNITS zero units; `nlw`: the '\n' words (same padding).
 // WANT_POS: also convert the position (the row writer copies its digits from the text instead).
-template <bool WANT_POS>
+// RING_UNITS != 0 (the streaming tokenizer, k_tok3.cuh): text and class arrays are rings of RING_UNITS * 32 bytes /
+// RING_UNITS units that hold the WHOLE line (its '\n' included, which ends every scan below); region_off is 0,
+// line_off the ring offset of the line's first byte, n_bits unused; every index wraps.
+template <bool WANT_POS, uint32_t RING_UNITS = 0>
 SID_HD bool parse_line_win(const uint8_t* s, uint32_t region_off, const uint32_t* cw, const uint32_t* nlw, uint32_t n_bits,
                            uint32_t line_off, WinLine& o) {
+    constexpr uint32_t RB = RING_UNITS ? RING_UNITS * 32u - 1u : 0xFFFFFFFFu;     // byte index mask
+    constexpr uint32_t RU = RING_UNITS ? RING_UNITS - 1u : 0xFFFFFFFFu;           // unit index mask
     const uint32_t ls = line_off - region_off;                      // bit index of the line's first byte
-    bool ok = line_off >= region_off && ls + 64 <= n_bits && line_off >= 12;
+    bool ok = RING_UNITS ? true : (line_off >= region_off && ls + 64 <= n_bits && line_off >= 12);
     const uint32_t l0 = ok ? ls : 0, h0 = ok ? line_off : region_off + 16;
-    Win64 w = load_window(cw, l0);
+    Win64 w = load_window<RING_UNITS>(cw, l0);
     // ---- header: the bytes <= 0x20 among the first 32 locate the four separators (pileup.cpp:17-36)
     const uint32_t sepmask = (uint32_t)w.term;
     ok = ok && pop_count(sepmask) >= 4;
@@ -153,7 +164,7 @@ SID_HD bool parse_line_win(const uint8_t* s, uint32_t region_off, const uint32_t
     {
         // none of the four is a line end (fewer than five columns: the reference throws, pileup.cpp:22-40); other
         // control bytes are the caller's business (UnitClasses::bad)
-        const uint32_t nl32 = funnel_r(nlw[l0 >> 5], nlw[(l0 >> 5) + 1], l0 & 31);
+        const uint32_t nl32 = funnel_r(nlw[(l0 >> 5) & RU], nlw[((l0 >> 5) + 1) & RU], l0 & 31);
         ok = ok && (nl32 & (0xFFFFFFFFu >> (31 - q4))) == 0;
         // the position is all digits
         const uint32_t dm = (0xFFFFFFFFu >> (32 - q2)) & ~(0xFFFFFFFFu >> (31 - q1));       // bits (q1, q2)
@@ -168,15 +179,15 @@ SID_HD bool parse_line_win(const uint8_t* s, uint32_t region_off, const uint32_t
     o.name_len = q1;
     o.hdr_len = q2;
     o.pos = 0;
-    o.pos_canonical = s[h0 + q1 + 1] != (uint8_t)'0' || nd == 1;
+    o.pos_canonical = s[(h0 + q1 + 1) & RB] != (uint8_t)'0' || nd == 1;
     if (WANT_POS) {
         // the (up to) eight characters before the second separator, leading ones forced to '0' (digits checked above)
         const uint32_t* sw = reinterpret_cast<const uint32_t*>(s);
         const uint32_t e = h0 + q2;
         const uint32_t ndd = ok ? nd : 1;
-        const uint32_t* pw = sw + ((e - 8) >> 2);
+        const uint32_t pw = (e - 8) >> 2;
         const uint32_t ps = ((e - 8) & 3) * 8;
-        const uint32_t w0 = pw[0], w1 = pw[1], w2 = pw[2];
+        const uint32_t w0 = sw[pw & (RB >> 2)], w1 = sw[(pw + 1) & (RB >> 2)], w2 = sw[(pw + 2) & (RB >> 2)];
         uint32_t lo = funnel_r(w0, w1, ps), hi = funnel_r(w1, w2, ps);
         const uint32_t zero = ndd >= 8 ? 0u : 8u - ndd;
         if (zero >= 4) {
@@ -191,7 +202,7 @@ SID_HD bool parse_line_win(const uint8_t* s, uint32_t region_off, const uint32_t
         const uint32_t tl = xl * 10u + (xl >> 8), th = xh * 10u + (xh >> 8);
         const uint32_t vl = (tl & 0xFFu) * 100u + ((tl >> 16) & 0xFFu), vh = (th & 0xFFu) * 100u + ((th >> 16) & 0xFFu);
         uint32_t acc = vl * 10000u + vh;
-        if (ndd == 9) acc += ((uint32_t)s[e - 9] - (uint32_t)'0') * 100000000u;
+        if (ndd == 9) acc += ((uint32_t)s[(e - 9) & RB] - (uint32_t)'0') * 100000000u;
         o.pos = (int32_t)acc;
     }
     SID_SYNCWARP();
@@ -235,9 +246,9 @@ SID_HD bool parse_line_win(const uint8_t* s, uint32_t region_off, const uint32_t
             }
             if (ndig == 0) continue;                            // a sign without a digit is ignored (pileup.cpp:131-133)
             uint32_t n = 0;
-            const uint8_t* q = s + region_off + cur + p + 1;
+            const uint32_t q = region_off + cur + p + 1;
             for (uint32_t i = 0; i < ndig; ++i)
-                if (n < (1u << 26)) n = n * 10 + ((uint32_t)q[i] - (uint32_t)'0');
+                if (n < (1u << 26)) n = n * 10 + ((uint32_t)s[(q + i) & RB] - (uint32_t)'0');
             const uint64_t to = (uint64_t)p + 1 + ndig + n;     // first byte after the skipped ones (pileup.cpp:144)
             live_all &= ~(low_bits64(to >= 64 ? 64u : (uint32_t)to) & ~low_bits64(p + 1));
             if (to > 64 && !last) skip = (uint32_t)(to - 64 > (1u << 27) ? (1u << 27) : to - 64);
@@ -254,8 +265,8 @@ SID_HD bool parse_line_win(const uint8_t* s, uint32_t region_off, const uint32_t
         } else {
             cur = next;
             below = 0;
-            if (cur + 64 > n_bits) { ok = false; running = false; }        // ran out of classified bytes
-            else w = load_window(cw, cur);
+            if (!RING_UNITS && cur + 64 > n_bits) { ok = false; running = false; }        // ran out of classified bytes
+            else w = load_window<RING_UNITS>(cw, cur);
         }
     }
     SID_SYNCWARP();
