@@ -40,7 +40,14 @@ def parse_args():
     ap.add_argument("--cpu-sample-sites", type=int, default=3_000_000)
     ap.add_argument("--het-only", action="store_true", help="emit only rows labelled het (the pipeline's grep ',het,'); not the headline config")
     ap.add_argument("--chunk-mb", type=int, default=256, help="chunk size of the host-buffer path (sidgpu_config.max_chunk_bytes)")
-    ap.add_argument("--unfused", action="store_true", help="local: sidgpu_feed + sidgpu_emit_csv (site store + K6) instead of the one-pass sidgpu_feed_rows")
+    ap.add_argument("--fused", action="store_true", help="local: the one-pass sidgpu_feed_rows (K1 writes the rows itself) instead of site store + K6; measured slower")
+    ap.add_argument("--lynch", default="merged", choices=["merged", "per_evaluation"],
+                    help="sharded bayes / likelihood_ratio: histograms all-gathered once and the fit as one kernel (default), or one all-reduce per objective evaluation")
+    ap.add_argument("--lynch-sites", type=int, default=250_000_000, help="other_configs: sites of the depth-60 Lynch run, whole job (configs[2]: 250 Mb)")
+    ap.add_argument("--deep-sites", type=int, default=2_000_000, help="other_configs: sites per GPU of the depth-500 run (configs[4])")
+    ap.add_argument("--quality-sites", type=int, default=20_000_000, help="other_configs: sites per GPU of the `quality` run")
+    ap.add_argument("--no-other", action="store_true", help="skip other_configs (Lynch depth 60, depth 500, quality)")
+    ap.add_argument("--no-affinity", action="store_true", help="do not pin the rank's threads next to its GPU")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -175,38 +182,237 @@ def run_reference(args):
 
 
 # ---------------------------------------------------------------------------------------------
+class Env:
+    """What every measurement of this rank shares: the process group, the stream, the peaks."""
+
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device (this path has no CPU fallback; see --impl reference)")
+        torch.cuda.set_device(self.local_rank)
+        # pin this rank's threads next to its GPU BEFORE any pinned buffer is allocated and touched
+        self.placement = None
+        if not args.no_affinity:
+            try:
+                from sid_b200 import affinity
+                self.placement = affinity.bind_to_gpu(self.local_rank)
+            except Exception as e:          # placement is an optimisation, never a reason to fail
+                self.placement = {"error": str(e)}
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
+        self.stream = torch.cuda.current_stream()
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        self.hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        self.peak_kind = "measured" if "hbm_gbs" in peaks else "fallback"
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, x):
+        if self.world == 1:
+            return x
+        t = self.torch.tensor([x], dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+
+def text_bytes_bound(n_sites, cfg, seven):
+    return int(n_sites * (16 + 2.7 * (cfg["lam"] + 1)) * (1.5 if seven else 1.0) + (1 << 20))
+
+
+def generate_to_device(env, n_sites, depth, seven, bounce, site_begin):
+    """Synthetic text of n_sites sites straight into device memory, through a pinned bounce buffer (pieces of a few
+    million sites), so that configurations larger than the host's pinned budget still fit.  Returns (d_text, len)."""
+    from sid_b200 import synth
+    torch = env.torch
+    cfg = synth.CONFIGS[depth]
+    d_text = torch.empty((text_bytes_bound(n_sites, cfg, seven) // 16 + 2) * 16, dtype=torch.uint8, device="cuda")
+    per_piece = max(10_000, int(bounce.numel() / ((16 + 2.7 * (cfg["lam"] + 1)) * (1.5 if seven else 1.0)) * 0.9))
+    threads = max(1, (os.cpu_count() or 1) // max(env.world, 1))
+    off, done = 0, 0
+    while done < n_sites:
+        n = min(per_piece, n_sites - done)
+        h = synth.generate(n, site_begin=site_begin + done, seed=1, out=bounce.numpy(), seven_columns=seven, threads=threads, **cfg)
+        src = bounce[:h.nbytes] if h.ctypes.data == bounce.data_ptr() else torch.from_numpy(h)     # (the generator outgrew the bounce buffer)
+        d_text[off:off + h.nbytes].copy_(src, non_blocking=True)
+        torch.cuda.synchronize()            # the bounce buffer is reused by the next piece
+        off += int(h.nbytes)
+        done += n
+    return d_text, off
+
+
+class Resident:
+    """One method over one device-resident text: the whole path per step, CUDA-event timing, per-kernel times."""
+
+    def __init__(self, env, ctx, method, d_text, text_len, n_sites, het_only=False, lynch_variant="merged"):
+        import sid_b200
+        self.env, self.ctx, self.method = env, ctx, method
+        self.d_text, self.text_len, self.n_sites = d_text, text_len, n_sites
+        self.params = sid_b200.Context.make_params(method, het_only=het_only)
+        self.csv_cap = int(n_sites * 56 + (1 << 20))
+        self.d_csv = env.torch.empty(self.csv_cap, dtype=env.torch.uint8, device="cuda")
+        self.d_obj = env.torch.zeros(1, dtype=env.torch.float64, device="cuda")
+        self.lynch_variant = lynch_variant          # "merged": histograms all-gathered once; "per_evaluation": one all-reduce per step
+        self.state = {"csv_bytes": 0, "rows": 0}
+        self.exchange_ms = 0.0
+        self.exchanges = 0
+
+    def step(self, fused=False):
+        env, ctx, torch = self.env, self.ctx, self.env.torch
+        from sid_b200 import shard
+        ctx.begin(self.params)
+        if fused:                                   # K1 writes the rows itself, then the regions are laid end to end
+            b, r, n = ctx.feed_rows(self.d_text.data_ptr(), self.text_len, self.d_csv.data_ptr(), self.csv_cap)
+            self.state["csv_bytes"], self.state["rows"] = b, r
+            return n
+        n = ctx.feed(self.d_text.data_ptr(), self.text_len)
+        if self.method in ("bayes", "likelihood_ratio"):
+            if env.world > 1 and self.lynch_variant == "merged":
+                # the shards' histograms are exchanged ONCE (NCCL all-gather), merged on every device, and the whole
+                # Nelder-Mead fit runs there as one kernel: identical on every rank, no traffic per optimiser step
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(env.stream)
+                self.state["gathered_entries"] = shard.exchange_histograms(ctx, env.dist, "cuda")
+                e1.record(env.stream)
+                torch.cuda.synchronize()
+                self.exchange_ms += e0.elapsed_time(e1)
+                self.exchanges += 1
+                ctx.finish()
+            elif env.world > 1:
+                # the literal north_star form: every rank reduces its own histogram, one 8-byte all-reduce per evaluation
+                ints, flt = shard.torch_collectives(env.dist, "cuda")
+                _, sums = ctx.histogram_sums(4)
+
+                def local_objective(nd, pi, eps):
+                    ctx.lynch_objective_partial(nd, pi, eps, self.d_obj.data_ptr())
+                    return self.d_obj
+
+                fit = shard.distributed_fit(lambda: sums, local_objective, ints, flt)
+                ctx.set_fit(fit["pi"], fit["eps"], fit["nd"])
+                self.state["fit"] = {k: fit[k] for k in ("pi", "eps", "iterations", "evaluations")}
+                if self.method == "likelihood_ratio":
+                    n_u, d_prof, d_cnt = ctx.histogram_device(4)
+                    prof = torch.empty(n_u, dtype=torch.int64, device="cuda")
+                    cnt = torch.empty(n_u, dtype=torch.int64, device="cuda")
+                    ctx.copy_d2d(prof.data_ptr(), d_prof, 8 * n_u)
+                    ctx.copy_d2d(cnt.data_ptr(), d_cnt, 8 * n_u)
+                    gp, gc = shard.all_gather_histograms(env.dist, prof, cnt)
+                    keep = gc.cpu().numpy() > 0
+                    merged, _ = shard.merge_histograms([(gp.cpu().numpy().view("uint64")[keep], gc.cpu().numpy().view("uint64")[keep])])
+                    ctx.finish_global(merged)
+                else:
+                    ctx.finish()
+            else:
+                ctx.finish()
+            if "fit" not in self.state or self.lynch_variant == "merged" or env.world == 1:
+                f = ctx.session_fit()
+                self.state["fit"] = {k: f[k] for k in ("pi", "eps", "iterations", "evaluations")}
+        b, r = ctx.emit_csv(0, n, self.d_csv.data_ptr(), self.csv_cap)
+        self.state["csv_bytes"], self.state["rows"] = b, r
+        return n
+
+    def timed(self, steps, warmup, fused=False, clocks=None):
+        env, ctx, torch = self.env, self.ctx, self.env.torch
+        n = 0
+        for _ in range(warmup):
+            n = self.step(fused)
+        assert n == self.n_sites, (n, self.n_sites)
+        self.exchange_ms, self.exchanges = 0.0, 0
+        ctx.profile(True)
+        launches0 = ctx.launch_count
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        env.barrier()
+        e0.record(env.stream)
+        for _ in range(steps):
+            self.step(fused)
+        e1.record(env.stream)
+        env.barrier()
+        ms_total = env.max_over_ranks(e0.elapsed_time(e1))
+        launches = ctx.launch_count - launches0
+        ktimes = ctx.kernel_times()
+        ctx.profile(False)
+        ms = ms_total / steps
+        tok_ms, tok_n = ktimes["tokenize"]
+        tok_avg = tok_ms / max(tok_n, 1)
+        return {"ms_per_step": ms, "sites_per_s": env.world * self.n_sites / (ms * 1e-3), "launches": launches,
+                "kernel_ms_per_step": {k: v[0] / steps for k, v in ktimes.items() if v[0]},
+                "k1_avg_launch_ms": tok_avg, "k1_launches": tok_n,
+                "k1_gbs": (self.text_len / 1e9) / (tok_avg * 1e-3) if tok_avg > 0 else 0.0,
+                "fit_evaluations": (self.state.get("fit") or {}).get("evaluations"),
+                "exchange_ms_per_step": self.exchange_ms / max(self.exchanges, 1) if self.exchanges else None}
+
+
+def time_cli(args, h_text, text_len, n_sites):
+    """`host/sid -m local file > /dev/null` on the same text, file in /dev/shm: what a user of the command line gets
+    (process start, CUDA context, file read, rows written), timed like the reference arm."""
+    sid = os.path.join(ROOT, "host", "sid")
+    if not os.path.exists(sid) or not os.path.isdir("/dev/shm"):
+        return None
+    st = os.statvfs("/dev/shm")
+    room = st.f_bavail * st.f_frsize
+    use = text_len
+    try:
+        avail = [int(l.split()[1]) * 1024 for l in open("/proc/meminfo") if l.startswith("MemAvailable")][0]
+    except Exception:
+        avail = room
+    if min(room, avail // 2) < text_len + (64 << 20):
+        return {"skipped": "/dev/shm has %.1f GB free (%.1f GB of RAM available), the text is %.1f GB" % (room / 1e9, avail / 1e9, text_len / 1e9)}
+    path = os.path.join("/dev/shm", "sidbench_cli_%d.plp" % os.getpid())
+    tiny = path + ".tiny"
+    try:
+        h_text[:use].tofile(path)
+        nl = int(h_text[:4096].tobytes().rfind(b"\n")) + 1
+        h_text[:nl].tofile(tiny)
+        t0 = time.perf_counter()
+        subprocess.run([sid, "-m", "local", tiny], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, check=True)
+        startup = time.perf_counter() - t0
+        best = None
+        for _ in range(2):
+            t0 = time.perf_counter()
+            with open(os.devnull, "wb") as null:
+                subprocess.run([sid, "-m", "local", path], stdout=null, stderr=subprocess.DEVNULL, check=True)
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+        return {"value": n_sites / best, "unit": UNIT, "seconds": best, "startup_seconds": startup,
+                "value_without_startup": n_sites / max(best - startup, 1e-9),
+                "what": "host/sid -m local /dev/shm/file > /dev/null, wall clock of the whole process (best of 2); startup = the same on a 4 KB file"}
+    except Exception as e:
+        return {"error": str(e)}
+    finally:
+        for q in (path, tiny):
+            try:
+                os.remove(q)
+            except OSError:
+                pass
+
+
 def run_ours(args):
-    import numpy as np
-    import torch
-    import torch.distributed as dist
+    import numpy as np  # noqa: F401
     import sid_b200
     from sid_b200 import synth
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device (this path has no CPU fallback; see --impl reference)")
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    stream = torch.cuda.current_stream()
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    peak_kind = "measured" if "hbm_gbs" in peaks else "fallback"
+    env = Env(args)
+    torch, world, rank, local_rank = env.torch, env.world, env.rank, env.local_rank
 
     # ---- synthetic text for this rank's shard, generated straight into pinned host memory
     n_sites = args.sites
     cfg = synth.CONFIGS[args.depth]
+    seven = args.method == "quality"
     # host memory guard: every rank pins its text and its CSV; never ask for more than half of what is free
     note = None
     try:
         avail = [int(l.split()[1]) * 1024 for l in open("/proc/meminfo") if l.startswith("MemAvailable")][0]
-        per_site = (16 + 2.7 * (cfg["lam"] + 1)) * (1.5 if args.method == "quality" else 1.0) + 56
+        per_site = (16 + 2.7 * (cfg["lam"] + 1)) * (1.5 if seven else 1.0) + 56
         fit = int(0.5 * avail / max(world, 1) / per_site)
         if fit < n_sites:
             note = "sites per GPU reduced from %d to %d to fit pinned host memory (%.0f GB available)" % (n_sites, fit, avail / 1e9)
@@ -214,177 +420,184 @@ def run_ours(args):
     except Exception:
         pass
     gen_threads = max(1, (os.cpu_count() or 1) // max(world, 1))
-    cap = int(n_sites * (16 + 2.7 * (cfg["lam"] + 1)) * (1.5 if args.method == "quality" else 1.0) + (1 << 20))
-    h_text_t = torch.empty(cap, dtype=torch.uint8, pin_memory=True)
+    h_text_t = torch.empty(text_bytes_bound(n_sites, cfg, seven), dtype=torch.uint8, pin_memory=True)
     t0 = time.perf_counter()
-    h_text = synth.generate(n_sites, site_begin=rank * n_sites, seed=1, out=h_text_t.numpy(), seven_columns=args.method == "quality",
-                            threads=gen_threads, **cfg)
+    h_text = synth.generate(n_sites, site_begin=rank * n_sites, seed=1, out=h_text_t.numpy(), seven_columns=seven, threads=gen_threads, **cfg)
     text_len = int(h_text.nbytes)
     gen_s = time.perf_counter() - t0
     d_text = torch.empty(((text_len + 15) // 16 + 1) * 16, dtype=torch.uint8, device="cuda")
     d_text[:text_len].copy_(h_text_t[:text_len], non_blocking=True)
-    csv_cap = int(n_sites * 56 + (1 << 20))
-    d_csv = torch.empty(csv_cap, dtype=torch.uint8, device="cuda")
-    h_csv_t = torch.empty(csv_cap, dtype=torch.uint8, pin_memory=True)
     torch.cuda.synchronize()
 
-    ctx = sid_b200.Context(device=local_rank, stream=stream.cuda_stream, max_chunk_bytes=args.chunk_mb << 20)
-    params = sid_b200.Context.make_params(args.method, het_only=args.het_only)
-    ctx_streams = args.method in ("local", "quality")       # rows can be emitted chunk by chunk, no global step
-    state = {"csv_bytes": 0, "rows": 0}
-
-    needs_fit = args.method in ("bayes", "likelihood_ratio")
-    d_obj = torch.zeros(1, dtype=torch.float64, device="cuda")
-
-    fused = args.method == "local" and not args.unfused
-
-    def step_resident():
-        ctx.begin(params)
-        if fused:                                   # one kernel from text to rows, then the regions laid end to end
-            b, r, n = ctx.feed_rows(d_text.data_ptr(), text_len, d_csv.data_ptr(), csv_cap)
-            state["csv_bytes"], state["rows"] = b, r
-            return n
-        n = ctx.feed(d_text.data_ptr(), text_len)
-        if needs_fit and world > 1:
-            # sharded Lynch fit: five integers once, then one double per optimiser evaluation (NCCL)
-            from sid_b200 import shard
-            ints, flt = shard.torch_collectives(dist, "cuda")
-            _, sums = ctx.histogram_sums(4)
-
-            def local_objective(nd, pi, eps):
-                ctx.lynch_objective_partial(nd, pi, eps, d_obj.data_ptr())
-                return d_obj
-
-            fit = shard.distributed_fit(lambda: sums, local_objective, ints, flt)
-            ctx.set_fit(fit["pi"], fit["eps"], fit["nd"])
-            state["fit"] = {k: fit[k] for k in ("pi", "eps", "iterations", "evaluations")}
-            if args.method == "likelihood_ratio":
-                # Benjamini-Hochberg needs the unique profiles of all shards: gather, merge, finish on the device
-                local = ctx.histogram(4)[:2]
-                gathered = [None] * world
-                dist.all_gather_object(gathered, (local[0], local[1]))
-                merged, _ = shard.merge_histograms(gathered)
-                ctx.finish_global(merged)
-                state["lr_global_unique"] = int(len(merged))
-        if not ctx_streams and not (needs_fit and world > 1 and args.method == "likelihood_ratio"):
-            ctx.finish()
-            if "fit" not in state:
-                f = ctx.session_fit()
-                state["fit"] = {k: f[k] for k in ("pi", "eps", "iterations", "evaluations")}
-        b, r = ctx.emit_csv(0, n, d_csv.data_ptr(), csv_cap)
-        state["csv_bytes"], state["rows"] = b, r
-        return n
-
-    def step_e2e():
-        import ctypes
-        nb, ns, nr = ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_uint64()
-        rc = ctx.lib.sidgpu_call_host(ctx.h, ctypes.byref(params), h_text_t.data_ptr(), text_len, h_csv_t.data_ptr(), csv_cap,
-                                      ctypes.byref(nb), ctypes.byref(ns), ctypes.byref(nr))
-        ctx._ck(rc)
-        return ns.value, nb.value
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+    ctx = sid_b200.Context(device=local_rank, stream=env.stream.cuda_stream, max_chunk_bytes=args.chunk_mb << 20)
+    head = Resident(env, ctx, args.method, d_text, text_len, n_sites, het_only=args.het_only, lynch_variant=args.lynch)
+    fused = args.method == "local" and args.fused
+    csv_cap = head.csv_cap
+    h_csv_t = torch.empty(csv_cap, dtype=torch.uint8, pin_memory=True)
 
     # ---- kernel-only: text resident in HBM
-    for _ in range(args.warmup):
-        n = step_resident()
-    assert n == n_sites, (n, n_sites)
-    ctx.profile(True)
-    launches0 = ctx.launch_count
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local_rank) as clocks:
-        barrier()
-        e0.record(stream)
-        for _ in range(args.steps):
-            step_resident()
-        e1.record(stream)
-        barrier()
-    ms_total = max_over_ranks(e0.elapsed_time(e1))
-    launches = ctx.launch_count - launches0
-    ktimes = ctx.kernel_times()
-    ctx.profile(False)
-    ms_per_step = ms_total / args.steps
-    value = world * n_sites / (ms_per_step * 1e-3)
-    tok_ms, tok_n = ktimes["tokenize"]
-    tok_avg_ms = tok_ms / max(tok_n, 1)
-    achieved = (text_len / 1e9) / (tok_avg_ms * 1e-3) if tok_ms > 0 else 0.0
+        r = head.timed(args.steps, args.warmup, fused)
+    ms_per_step, value, launches = r["ms_per_step"], r["sites_per_s"], r["launches"]
+    achieved, tok_avg_ms, tok_n = r["k1_gbs"], r["k1_avg_launch_ms"], r["k1_launches"]
+    state = head.state
     # DRAM traffic of the dominant kernel per launch: ratio measured by one `ncu --set full` capture
     # (profiles/), scaled to this launch's algorithmic bytes
     traffic = None
     try:
-        t = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))["k_tokenize"]
+        t = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))["k_tok2<sites>"]
         traffic = int(text_len * (t["dram_bytes_read"] + t["dram_bytes_write"]) / t["algorithmic_bytes"])
     except Exception:
         pass
 
     # ---- end to end through the host-buffer entry point (pinned host text -> pinned host CSV)
-    e2e = None
-    if not args.no_e2e:
-        step_e2e()
-        # the copy engine alone on the same buffers: what PCIe allows for this step's bytes
-        barrier()
-        e0.record(stream)
-        d_text[:text_len].copy_(h_text_t[:text_len], non_blocking=True)
-        e1.record(stream)
-        torch.cuda.synchronize()
-        h2d_gbs = text_len / 1e9 / (e0.elapsed_time(e1) * 1e-3)
-        nb0 = max(1, int(state["csv_bytes"]))
-        e0.record(stream)
-        h_csv_t[:nb0].copy_(d_csv[:nb0], non_blocking=True)
-        e1.record(stream)
-        torch.cuda.synchronize()
-        d2h_gbs = nb0 / 1e9 / (e0.elapsed_time(e1) * 1e-3)
-        barrier()
+    def e2e_leg(params):
+        import ctypes
+        nb, ns, nr = ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_uint64()
+
+        def one():
+            rc = ctx.lib.sidgpu_call_host(ctx.h, ctypes.byref(params), h_text_t.data_ptr(), text_len, h_csv_t.data_ptr(), csv_cap,
+                                          ctypes.byref(nb), ctypes.byref(ns), ctypes.byref(nr))
+            ctx._ck(rc)
+        one()
+        env.barrier()
         t0 = time.perf_counter()
-        e0.record(stream)
         for _ in range(args.steps):
-            ns, nb = step_e2e()
-        e1.record(stream)
-        barrier()
-        wall_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
-        e2e = {"value": world * n_sites / (wall_ms / args.steps * 1e-3), "unit": UNIT, "h2d_bytes_per_step": text_len,
-               "d2h_bytes_per_step": int(nb), "ms_per_step": wall_ms / args.steps,
-               "timing": "host wall clock around sidgpu_call_host (it returns after its last D2H copy), max over ranks",
-               "pcie": {"h2d_gbs": h2d_gbs, "d2h_gbs": d2h_gbs,
-                        "copy_bound_ms": max(text_len / h2d_gbs, int(nb) / d2h_gbs) * 1e-6}}
+            one()
+        env.barrier()
+        wall_ms = env.max_over_ranks((time.perf_counter() - t0) * 1e3)
+        return wall_ms / args.steps, int(nb.value)
+
+    e2e = e2e_het = None
+    if not args.no_e2e:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        # the copy engines alone on the same buffers, every rank at once: what the links allow for this step's bytes
+        nb0 = max(1, int(state["csv_bytes"]))
+        s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+
+        def copies(h2d, d2h):
+            env.barrier()
+            e0.record(env.stream)
+            s_in.wait_stream(env.stream)
+            s_out.wait_stream(env.stream)
+            if h2d:
+                with torch.cuda.stream(s_in):
+                    d_text[:text_len].copy_(h_text_t[:text_len], non_blocking=True)
+            if d2h:
+                with torch.cuda.stream(s_out):
+                    h_csv_t[:nb0].copy_(head.d_csv[:nb0], non_blocking=True)
+            env.stream.wait_stream(s_in)
+            env.stream.wait_stream(s_out)
+            e1.record(env.stream)
+            env.barrier()
+            return env.max_over_ranks(e0.elapsed_time(e1))
+        copies(True, True)
+        h2d_ms, d2h_ms, both_ms = copies(True, False), copies(False, True), copies(True, True)
+        ms, nb = e2e_leg(head.params)
+        e2e = {"value": world * n_sites / (ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": text_len, "d2h_bytes_per_step": nb,
+               "ms_per_step": ms, "timing": "host wall clock around sidgpu_call_host (it returns after its last D2H copy), max over ranks",
+               "pcie": {"h2d_gbs": text_len / 1e6 / h2d_ms, "d2h_gbs": nb0 / 1e6 / d2h_ms, "h2d_alone_ms": h2d_ms, "d2h_alone_ms": d2h_ms,
+                        "copy_bound_ms": both_ms, "frac_of_copy_bound": both_ms / ms,
+                        "how": "the step's text H2D and CSV D2H as two plain pinned copies on two streams, all ranks between the same "
+                               "barriers, CUDA events, max over ranks: the concurrent copy bound of this box at this N"}}
+        if args.method == "local" and not args.het_only:
+            # the pipeline keeps `grep ',het,'` of the CSV (run-sid.sh:16-17): the same step with only those rows coming back
+            ms2, nb2 = e2e_leg(sid_b200.Context.make_params("local", het_only=True))
+            e2e_het = {"value": world * n_sites / (ms2 * 1e-3), "unit": UNIT, "h2d_bytes_per_step": text_len, "d2h_bytes_per_step": nb2,
+                       "ms_per_step": ms2, "frac_of_h2d_bound": h2d_ms / ms2}
 
     # ---- the reference's CPU path on this box's host cores (rank 0, N=1 only)
-    cpu = None
+    cpu = cli = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         v, kind, sample, dt = time_cpu(args, 1, min(args.cpu_sample_sites, n_sites))
         cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": kind, "sample": sample, "seconds": dt}
+    if rank == 0 and world == 1 and not args.no_e2e and args.method == "local":
+        cli = time_cli(args, h_text, text_len, n_sites)
+
+    # ---- the other BASELINE configurations, outside the headline's timed region
+    other = None
+    if not args.no_other:
+        del head.d_csv, d_text
+        head.d_text = None
+        torch.cuda.empty_cache()
+        other = {}
+        steps, warm = 3, 2
+
+        def guarded(name, fn):
+            try:
+                other[name] = fn()
+            except Exception as e:              # a side measurement never takes the headline line down
+                other[name] = {"error": "%s: %s" % (type(e).__name__, e)}
+            env.barrier()
+            torch.cuda.empty_cache()
+
+        def lynch(method):
+            # BASELINE configs[2]: Lynch fit on a 250 Mb depth-60 chromosome, position-sharded over the GPUs of the run
+            def run():
+                total = args.lynch_sites
+                per = total // world
+                dt, tl = generate_to_device(env, per, "depth60", False, h_text_t, rank * per)
+                res = {"sites_per_gpu": per, "n_gpus": world, "text_bytes_per_gpu": tl}
+                for variant in (("merged", "per_evaluation") if world > 1 else ("merged",)):
+                    w = Resident(env, ctx, method, dt, tl, per, lynch_variant=variant)
+                    m = w.timed(steps, warm)
+                    fit_ms = m["kernel_ms_per_step"].get("fit", 0.0)
+                    ev = m["fit_evaluations"] or 0
+                    entry = {"sites_per_s": m["sites_per_s"], "ms_per_step": m["ms_per_step"], "kernel_ms_per_step": m["kernel_ms_per_step"],
+                             "k1_gbs": m["k1_gbs"], "k1_frac_of_hbm": m["k1_gbs"] / env.hbm_peak, "fit": w.state.get("fit"),
+                             "fit_kernel_ms": fit_ms, "us_per_objective_evaluation": 1e3 * fit_ms / ev if ev else None,
+                             "fit_share_of_step": fit_ms / m["ms_per_step"], "exchange_ms_per_step": m["exchange_ms_per_step"]}
+                    if variant == "per_evaluation":
+                        entry["note"] = "one NCCL all-reduce of 8 bytes per objective evaluation, host-driven simplex (sid_b200/shard.py distributed_fit)"
+                    res["histograms_merged_once" if variant == "merged" else "allreduce_per_evaluation"] = entry
+                    del w
+                return res
+            return run
+
+        def deep():
+            per = args.deep_sites
+            dt, tl = generate_to_device(env, per, "depth500", False, h_text_t, rank * per)
+            w = Resident(env, ctx, "local", dt, tl, per)
+            m = w.timed(steps, warm)
+            return {"sites_per_gpu": per, "text_bytes_per_gpu": tl, "sites_per_s": m["sites_per_s"], "ms_per_step": m["ms_per_step"],
+                    "k1_gbs": m["k1_gbs"], "k1_frac_of_hbm": m["k1_gbs"] / env.hbm_peak, "kernel_ms_per_step": m["kernel_ms_per_step"]}
+
+        def quality():
+            per = args.quality_sites
+            dt, tl = generate_to_device(env, per, "depth30", True, h_text_t, rank * per)
+            w = Resident(env, ctx, "quality", dt, tl, per)
+            m = w.timed(steps, warm)
+            return {"sites_per_gpu": per, "text_bytes_per_gpu": tl, "sites_per_s": m["sites_per_s"], "ms_per_step": m["ms_per_step"],
+                    "bytes_per_s": world * tl / (m["ms_per_step"] * 1e-3), "kernel_ms_per_step": m["kernel_ms_per_step"]}
+
+        guarded("lynch_bayes_depth60_250Mb", lynch("bayes"))
+        guarded("lynch_likelihood_ratio_depth60_250Mb", lynch("likelihood_ratio"))
+        guarded("depth500_local", deep)
+        guarded("quality_depth30_7col", quality)
 
     if rank == 0:
+        kernel_name = "k_tok2<rows>" if fused else "k_tok2<sites>"
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/f64",
             "data": "synthetic",
             "config": {"workload": workload_name(args), "text_bytes_per_gpu": text_len, "csv_bytes_per_gpu": state["csv_bytes"],
                        "l2": "inputs larger than L2 (%.1f GB of text per step)" % (text_len / 1e9), "parallelism": "position-sharded x%d, no data-path collective" % world,
-                       "generator_seconds": gen_s, "sites_per_gpu": n_sites,
+                       "generator_seconds": gen_s, "sites_per_gpu": n_sites, "host_placement": env.placement,
                        "note": ("het rows only (--het-only); " + (note or "")) if args.het_only else note},
-            "roofline": {"bound": "hbm", "kernel": "k_tok2<rows>" if fused else "k_tok2<sites>", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved / hbm_peak if hbm_peak else None, "traffic": traffic, "peak_kind": peak_kind,
+            "roofline": {"bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": env.hbm_peak, "unit": "GB/s",
+                         "frac": achieved / env.hbm_peak if env.hbm_peak else None, "traffic": traffic, "peak_kind": env.peak_kind,
                          "algorithmic_bytes_per_launch": text_len, "avg_launch_ms": tok_avg_ms, "launches_timed": tok_n,
-                         "limiter": "integer ALU pipe, 66 % of its peak in profiles/r1_ncu_full_tokenize_v19.txt (DRAM 18 %): "
+                         "limiter": "integer ALU pipe, 71 % of its peak in profiles/r2_ncu_full_sites.txt (DRAM 18 %): "
                                     "the HBM roofline is the contract's bound, not what this kernel runs into",
-                         "kernel_ms_per_step": {k: v[0] / args.steps for k, v in ktimes.items()}},
-            "e2e": e2e, "cpu_baseline": cpu, "gpu_launches": launches, "clocks": clocks.summary(), "lynch_fit": state.get("fit"),
+                         "kernel_ms_per_step": r["kernel_ms_per_step"]},
+            "e2e": e2e, "e2e_het_only": e2e_het, "cli_e2e": cli, "cpu_baseline": cpu, "gpu_launches": launches, "clocks": clocks.summary(),
+            "lynch_fit": state.get("fit"), "other_configs": other,
         }
         print(json.dumps(line))
     ctx.close()
     if world > 1:
-        dist.destroy_process_group()
+        env.dist.destroy_process_group()
 
 
 def main():

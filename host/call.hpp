@@ -58,6 +58,14 @@ struct SidRunInfo {
 SidRunInfo sidCallToStream(const std::string& method, const char* text, size_t len, bool estimate_prior, double prior,
                            double error_threshold, double significance_level, std::ostream& out, std::ostream& log,
                            const char* header = nullptr);
+// The streaming form the `sid` binary uses for one GPU (sid.cpp:85-105 without the whole file and the whole result
+// in memory): text is pulled from `fd_in` chunk by chunk (a gzip stream is inflated on the fly), rows are written to
+// `fd_out` as they come back from the device.  The header line goes out with the first rows, so an input that fails
+// within its first chunk prints nothing, like the reference; a later failure leaves the rows of the chunks before
+// it on fd_out (the exit status and the message are the reference's).  read_threads > 1 reads a regular file with
+// that many parallel preads per chunk.
+SidRunInfo sidCallFile(const std::string& method, int fd_in, bool gzip, bool estimate_prior, double prior, double error_threshold,
+                       double significance_level, int fd_out, std::ostream& log, const char* header = nullptr, int read_threads = 1);
 // Selects the GPU (default 0) and the chunk size of the host path for subsequent calls.
 void sidSetDevice(int device, size_t max_chunk_bytes = 0);
 // The same over several GPUs of one node, one host thread and one position shard (a line-aligned byte range

@@ -11,6 +11,9 @@
 #include <stdexcept>
 #include <thread>
 
+#include <unistd.h>
+#include <zlib.h>
+
 #include "../include/sidgpu.h"
 #include "../sid_b200/csrc/nelder_mead.hpp"      // the simplex driver the library itself uses (host code, header only)
 #include "call.hpp"
@@ -252,6 +255,84 @@ SidRunInfo sidCallToStream(const std::string& method, const char* text, size_t l
 
 namespace {
 
+// ---- callbacks of sidgpu_call_io over file descriptors
+struct FileIo {
+    int fd_in = -1, fd_out = -1;
+    bool gzip = false;
+    gzFile gz = nullptr;
+    off_t offset = 0;                   // next byte of a regular file
+    bool seekable = false;
+    int threads = 1;
+    const char* header = nullptr;
+    bool header_done = false;
+    bool write_failed = false;
+
+    static int64_t read_cb(void* user, char* dst, size_t cap) {
+        FileIo& f = *(FileIo*)user;
+        if (f.gzip) {
+            const int got = gzread(f.gz, dst, (unsigned)std::min<size_t>(cap, (size_t)1 << 30));
+            return got < 0 ? -1 : got;
+        }
+        if (!f.seekable || f.threads <= 1 || cap < ((size_t)8 << 20)) {
+            const ssize_t got = f.seekable ? pread(f.fd_in, dst, cap, f.offset) : read(f.fd_in, dst, cap);
+            if (got > 0) f.offset += got;
+            return got < 0 ? -1 : (int64_t)got;
+        }
+        // a regular file: the slot is filled by parallel preads (one kernel copy per thread)
+        const size_t part = (cap / (size_t)f.threads + 4095) & ~(size_t)4095;
+        std::vector<ssize_t> got((size_t)f.threads, 0);
+        std::vector<std::thread> workers;
+        for (int t = 0; t < f.threads; ++t) {
+            const size_t lo = std::min(cap, part * (size_t)t), hi = std::min(cap, part * (size_t)(t + 1));
+            workers.emplace_back([&, t, lo, hi]() {
+                size_t done = 0;
+                while (lo + done < hi) {
+                    const ssize_t g = pread(f.fd_in, dst + lo + done, hi - lo - done, f.offset + (off_t)(lo + done));
+                    if (g < 0) { got[(size_t)t] = -1; return; }
+                    if (g == 0) break;
+                    done += (size_t)g;
+                }
+                got[(size_t)t] = (ssize_t)done;
+            });
+        }
+        for (auto& w : workers) w.join();
+        size_t total = 0;
+        for (int t = 0; t < f.threads; ++t) {
+            if (got[(size_t)t] < 0) return -1;
+            total += (size_t)got[(size_t)t];
+            const size_t lo = std::min(cap, part * (size_t)t), hi = std::min(cap, part * (size_t)(t + 1));
+            if ((size_t)got[(size_t)t] < hi - lo) break;       // end of the file inside this part
+        }
+        f.offset += (off_t)total;
+        return (int64_t)total;
+    }
+    bool put(const char* p, size_t n) {
+        while (n) {
+            const ssize_t w = write(fd_out, p, n);
+            if (w < 0) { write_failed = true; return false; }
+            p += w;
+            n -= (size_t)w;
+        }
+        return true;
+    }
+    bool put_header() {
+        if (header_done || !header) return true;
+        header_done = true;
+        return put(header, std::strlen(header)) && put("\n", 1);
+    }
+    static int write_cb(void* user, const char* rows, size_t n) {
+        FileIo& f = *(FileIo*)user;
+        return f.put_header() && f.put(rows, n) ? 0 : 1;
+    }
+    static int rewind_cb(void* user) {
+        FileIo& f = *(FileIo*)user;
+        if (f.gzip) return gzrewind(f.gz) == 0 ? 0 : 1;
+        if (!f.seekable) return 1;
+        f.offset = 0;
+        return 0;
+    }
+};
+
 // lexicographic order of std::array<uint16_t,4> (pileup.cpp:179-182) for a packed profile
 uint64_t profile_sort_key(uint64_t p) {
     return ((p & 0xFFFFull) << 48) | (((p >> 16) & 0xFFFFull) << 32) | (((p >> 32) & 0xFFFFull) << 16) | (p >> 48);
@@ -425,6 +506,57 @@ SidRunInfo sidCallToStreamSharded(const std::string& method, const char* text, s
     if (rc == SIDGPU_EMISSING_MAPQ) throw std::invalid_argument("Malformed pileup line or missing mapping qualities");
     if (rc == SIDGPU_EQUAL_SHORT) throw std::invalid_argument("Malformed pileup line: " + err);
     if (rc != SIDGPU_OK) throw std::runtime_error("sidgpu error " + std::to_string(rc) + ": " + err);
+    return info;
+}
+
+SidRunInfo sidCallFile(const std::string& method, int fd_in, bool gzip, bool estimate_prior, double prior, double error_threshold,
+                       double significance_level, int fd_out, std::ostream& log, const char* header, int read_threads) {
+    SidRunInfo info;
+    FileIo f;
+    f.fd_in = fd_in;
+    f.fd_out = fd_out;
+    f.gzip = gzip;
+    f.header = header;
+    f.threads = std::max(1, read_threads);
+    f.seekable = !gzip && lseek(fd_in, 0, SEEK_CUR) != (off_t)-1;
+    const int m = method_id(method);
+    if (m < 0) {                                    // sid.cpp:92-100: unknown methods print the header only
+        f.put_header();
+        return info;
+    }
+    if (gzip) {
+        f.gz = gzdopen(dup(fd_in), "rb");
+        if (!f.gz) throw std::runtime_error("could not open the gzip stream");
+        gzbuffer(f.gz, 1u << 20);
+    }
+    sidgpu_params p {};
+    p.method = m;
+    p.estimate_prior = estimate_prior ? 1 : 0;
+    p.prior = prior;
+    p.error_threshold = error_threshold;
+    p.significance_level = significance_level;
+    p.het_only = g_het_only ? 1 : 0;
+    sidgpu_io io {FileIo::read_cb, FileIo::write_cb, FileIo::rewind_cb, &f};
+    uint64_t bytes = 0;
+    const int rc = sidgpu_call_io(ctx().h, &p, &io, &bytes, &info.n_sites, &info.n_rows);
+    if (f.gz) gzclose(f.gz);
+    if (rc != SIDGPU_OK) {
+        if (f.write_failed) throw std::runtime_error("could not write the rows");
+        raise(rc);
+    }
+    sidgpu_fit fit {};
+    double nd[4];
+    uint64_t nu = 0;
+    if (sidgpu_session_fit(ctx().h, &fit, nd, &nu) == SIDGPU_OK) {
+        info.has_fit = true;
+        info.heterozygosity = fit.pi;
+        info.error_rate = fit.eps;
+        info.iterations = fit.iterations;
+        info.converged = fit.converged != 0;
+        info.unique_profiles = nu;
+    }
+    log_fit(m, info, log);
+    f.put_header();                                 // an input without a single row still prints the header (sid.cpp:102)
     return info;
 }
 

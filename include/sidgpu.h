@@ -194,6 +194,27 @@ int sidgpu_emit_host(sidgpu_ctx* ctx, char* h_csv, size_t csv_cap, uint64_t* csv
 int sidgpu_stream_host(sidgpu_ctx* ctx, const char* h_text, size_t text_len, char* h_csv, size_t csv_cap,
                        uint64_t* csv_bytes, uint64_t* n_sites, uint64_t* n_rows);
 
+/* The same session for inputs and outputs of any size (what the `sid` binary uses: sid.cpp:85-105 reads the whole
+ * file into a vector of lines and prints a vector of records; here neither exists).  The ctx owns a ring of pinned
+ * text slots (max_chunk_bytes each, 64 MiB at most) and a ring of pinned CSV slots; an internal reader thread fills
+ * the text slots through `read` and cuts them at line ends, the calling thread keeps the copies and kernels going,
+ * an internal writer thread hands finished rows to `write` in file order.  Methods with a genome-wide step read the
+ * whole input first (their sites stay in device memory) and emit afterwards; `quality` with -R reads the input
+ * twice and needs `rewind`.
+ *   read(user, dst, cap)  up to cap bytes of text into dst; returns the count, 0 at the end of the input, < 0 on error.
+ *   write(user, rows, n)  n bytes of CSV rows (whole lines, no header); returns 0, anything else aborts the call.
+ *   rewind(user)          restarts the input; may be NULL; returns 0 on success.
+ * read and rewind are called from one thread, write from another, never concurrently with themselves.
+ * *csv_bytes / *n_sites / *n_rows (optional) receive the totals. */
+typedef struct {
+    int64_t (*read)(void* user, char* dst, size_t cap);
+    int (*write)(void* user, const char* rows, size_t n);
+    int (*rewind)(void* user);
+    void* user;
+} sidgpu_io;
+int sidgpu_call_io(sidgpu_ctx* ctx, const sidgpu_params* params, const sidgpu_io* io, uint64_t* csv_bytes,
+                   uint64_t* n_sites, uint64_t* n_rows);
+
 /* ------------------------------------------------------------------------------------------------
  * K3: unique-profile histogram   (countUniqueProfiles pileup.cpp:169-196,
  *                                 computeNucleotideDistribution pileup.cpp:198-217)

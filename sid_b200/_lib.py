@@ -46,6 +46,15 @@ class Fit(ctypes.Structure):
 
 
 # name -> (restype, argtypes); every symbol include/sidgpu.h declares
+IO_READ = ctypes.CFUNCTYPE(ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t)
+IO_WRITE = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t)
+IO_REWIND = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p)
+
+
+class Io(ctypes.Structure):                  # sidgpu_io
+    _fields_ = [("read", IO_READ), ("write", IO_WRITE), ("rewind", IO_REWIND), ("user", ctypes.c_void_p)]
+
+
 PROTOTYPES = {
     "sidgpu_create": (ctypes.c_int, [ctypes.POINTER(Config), c_void_pp]),
     "sidgpu_destroy": (None, [ctypes.c_void_p]),
@@ -78,6 +87,7 @@ PROTOTYPES = {
                                            ctypes.c_void_p, ctypes.c_void_p]),
     "sidgpu_call_host": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(Params), ctypes.c_void_p, ctypes.c_size_t,
                                         ctypes.c_void_p, ctypes.c_size_t, c_u64_p, c_u64_p, c_u64_p]),
+    "sidgpu_call_io": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(Params), ctypes.POINTER(Io), c_u64_p, c_u64_p, c_u64_p]),
     "sidgpu_histogram": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint32, ctypes.POINTER(UniqueView)]),
     "sidgpu_count_unique": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, c_u64, ctypes.c_uint32, ctypes.POINTER(UniqueView)]),
     "sidgpu_count_unique_weighted": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, c_u64, ctypes.c_uint32,

@@ -380,6 +380,47 @@ class Context:
             return out[:nb.value].tobytes(), ns.value, nr.value
 
 
+    def call_io(self, reader, writer, params, rewind=None):
+        """The streaming host path (sidgpu_call_io): `reader(n)` returns up to n bytes of pileup text (b"" at the
+        end), `writer(rows)` receives CSV rows in file order, `rewind()` restarts the input (quality with -R).
+        Returns (csv_bytes, n_sites, n_rows)."""
+        failure = []
+
+        def c_read(user, dst, cap):
+            try:
+                data = reader(min(cap, 1 << 24))
+                if data:
+                    ctypes.memmove(dst, data, len(data))
+                return len(data)
+            except Exception as e:          # an exception must not cross the C frame
+                failure.append(e)
+                return -1
+
+        def c_write(user, rows, n):
+            try:
+                writer(ctypes.string_at(rows, n))
+                return 0
+            except Exception as e:
+                failure.append(e)
+                return 1
+
+        def c_rewind(user):
+            try:
+                rewind()
+                return 0
+            except Exception as e:
+                failure.append(e)
+                return 1
+
+        io = _lib.Io(_lib.IO_READ(c_read), _lib.IO_WRITE(c_write), _lib.IO_REWIND(c_rewind) if rewind else _lib.IO_REWIND(), None)
+        nb, ns, nr = ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_uint64()
+        rc = self.lib.sidgpu_call_io(self.h, ctypes.byref(params), ctypes.byref(io), ctypes.byref(nb), ctypes.byref(ns), ctypes.byref(nr))
+        if failure:
+            raise failure[0]
+        self._ck(rc)
+        return nb.value, ns.value, nr.value
+
+
 def parse_csv_rows(rows):
     """CSV rows (no header) -> list of OutputRecord (call.hpp:23-27)."""
     out = []

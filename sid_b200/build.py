@@ -40,7 +40,7 @@ def build_libsidgpu(force=False):
     out = os.path.join(ROOT, "sid_b200", "libsidgpu.so")
     srcs = _glob("sid_b200/csrc", (".cu", ".cuh", ".hpp", ".inl")) + [os.path.join(ROOT, "include", "sidgpu.h")]
     if force or _newer(out, srcs):
-        _run([NVCC] + ARCH + ["-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-shared",
+        _run([NVCC] + ARCH + ["-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC,-pthread", "-shared",
                               "sid_b200/csrc/sidgpu.cu", "-o", out])
     return out
 
@@ -51,10 +51,12 @@ def build_sid_cli(force=False):
     if not os.path.exists(os.path.join(ROOT, "host", "sid.cpp")):
         return None
     link = ["-Lsid_b200", "-lsidgpu", "-Wl,-rpath,$ORIGIN/../sid_b200"]
-    if force or _newer(out, srcs + [os.path.join(ROOT, "sid_b200", "libsidgpu.so")]):
+    check = os.path.join(ROOT, "host", "api_check")
+    deps = srcs + [os.path.join(ROOT, "sid_b200", "libsidgpu.so")]
+    if force or _newer(out, deps) or _newer(check, deps):
         _run(["g++", "-O2", "-std=c++17", "-Wall", "-Iinclude", "-o", out, "host/sid.cpp", "host/sid_host.cpp"] + link + ["-lz", "-pthread"])
         _run(["g++", "-O2", "-std=c++17", "-Wall", "-Iinclude", "-o", os.path.join(ROOT, "host", "api_check"),
-              "host/api_check.cpp", "host/sid_host.cpp"] + link + ["-pthread"])
+              "host/api_check.cpp", "host/sid_host.cpp"] + link + ["-lz", "-pthread"])
     return out
 
 

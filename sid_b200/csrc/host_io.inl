@@ -166,17 +166,15 @@ struct IoPipe {
         return SIDGPU_OK;
     }
 
-    // rows of chunk (d_text, len) of a streaming session, or of stored sites [site_begin, +count), into hp_csv[b]
+    // rows of the chunk (d_text, len) of a streaming session (or of the second pass of quality -R) into hp_csv[b]
     int rows_of_chunk(int b, const char* d_text, size_t len, uint64_t* n_sites) {
+        TRY(sidgpu_feed(ctx, d_text, len, 0, len, n_sites));
         CK(cudaEventSynchronize(ev_out[b]));                        // the previous copy out of hp_csv[b] is done
         uint64_t bytes = 0, rows = 0;
-        const bool fused = ctx->params.method == SIDGPU_METHOD_LOCAL && ctx->phase == PHASE_FEED;
-        size_t want = std::max<size_t>(ctx->hp_csv[b].cap, len + len / 2 + 4096);
-        if (!fused) TRY(sidgpu_feed(ctx, d_text, len, 0, len, n_sites));
+        size_t want = std::max<size_t>(ctx->hp_csv[b].cap, (size_t)*n_sites * 48 + 4096);
         for (;;) {
             TRY(ensure(ctx, ctx->hp_csv[b], want));
-            const int rc = fused ? sidgpu_feed_rows(ctx, d_text, len, 0, len, (char*)ctx->hp_csv[b].p, ctx->hp_csv[b].cap, &bytes, &rows, n_sites)
-                                 : sidgpu_emit_csv(ctx, 0, *n_sites, (char*)ctx->hp_csv[b].p, ctx->hp_csv[b].cap, &bytes, &rows);
+            const int rc = sidgpu_emit_csv(ctx, 0, *n_sites, (char*)ctx->hp_csv[b].p, ctx->hp_csv[b].cap, &bytes, &rows);
             if (rc == SIDGPU_ECAPACITY && bytes + 4096 > want) { want = (size_t)bytes + 4096; continue; }
             if (rc != SIDGPU_OK) return rc;
             break;

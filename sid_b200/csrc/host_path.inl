@@ -113,7 +113,9 @@ struct HostIo {
             }
             CK(cudaStreamWaitEvent(ctx->stream, hp.ev_in[b], 0));
             uint64_t n = 0;
-            static const bool fused = !(getenv("SIDGPU_FUSED_ROWS") && atoi(getenv("SIDGPU_FUSED_ROWS")) == 0);   // 0: feed + K6 (A/B runs)
+            // K1 can write the rows of a `local` chunk itself (sidgpu_feed_rows); measured slower than site store + K6
+            // (2.93 vs 1.97 ms per 20 M sites, profiles/README.md), so it is opt-in: SIDGPU_FUSED_ROWS=1
+            static const bool fused = getenv("SIDGPU_FUSED_ROWS") && atoi(getenv("SIDGPU_FUSED_ROWS")) != 0;
             if (emit && fused && ctx->streaming && ctx->params.method == SIDGPU_METHOD_LOCAL && ctx->phase == PHASE_FEED) {
                 TRY(rows_chunk(b, (const char*)hp.text[b].p, end - start, &n));       // one kernel from text to rows
                 total_sites += n;

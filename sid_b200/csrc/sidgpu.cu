@@ -20,7 +20,6 @@
 #include "k_quality.cuh"
 #include "k_tokenize.cuh"
 #include "k_tok2.cuh"
-#include "k_tok3.cuh"
 #include "nelder_mead.hpp"
 
 using namespace sid;
@@ -644,100 +643,6 @@ int run_tok2_rows(sidgpu_ctx* ctx, const char* d_text, size_t text_len, size_t r
     }
 }
 
-// K1 in its streaming form (k_tok3.cuh) over [range_begin, range_end) of a streaming `local` session: every warp
-// streams chunks of the text through its own ring and writes the rows of a chunk into the chunk's region;
-// k_rows3_scan / k_rows3_copy lay the regions end to end in d_out.
-int run_tok3_rows(sidgpu_ctx* ctx, const char* d_text, size_t text_len, size_t range_begin, size_t range_end, char* d_out, size_t out_cap,
-                  uint64_t* bytes_out, uint64_t* rows_out, uint64_t* n_out) {
-    if (((uintptr_t)d_text & 15) != 0) return ctx->fail(SIDGPU_EINVAL, "d_text must be 16-byte aligned");
-    if (range_begin > range_end || range_end > text_len) return ctx->fail(SIDGPU_EINVAL, "bad range [%zu,%zu) for text of %zu bytes", range_begin, range_end, text_len);
-    *bytes_out = *rows_out = *n_out = 0;
-    if (range_begin == range_end) return sync_ctl(ctx);
-    static const uint32_t chunk_kb = getenv("SIDGPU_CHUNK_KB") ? (uint32_t)atoi(getenv("SIDGPU_CHUNK_KB")) : 64u;     // tuning knob
-    const uint64_t origin = range_begin & ~(uint64_t)15;
-    const uint64_t span = range_end - origin;
-    // chunks of chunk_kb KiB; small inputs get smaller chunks so that every SM has work (never below 4 KiB)
-    uint64_t chunk_bytes = (uint64_t)std::max(1u, std::min(chunk_kb, 1024u)) << 10;
-    const uint64_t want_chunks = (uint64_t)ctx->sm_count * 18 * 4;
-    while (chunk_bytes > 4096 && span / chunk_bytes < want_chunks) chunk_bytes >>= 1;
-    const uint64_t n_chunks64 = (span + chunk_bytes - 1) / chunk_bytes;
-    if (n_chunks64 > 0x7FFFFFFFull) return ctx->fail(SIDGPU_EINVAL, "range too large");
-    const uint32_t n_chunks = (uint32_t)n_chunks64;
-    TRY(ensure(ctx, ctx->blk, (size_t)n_chunks * 8));
-    TRY(ensure(ctx, ctx->rows_part, (size_t)n_chunks * 8));
-    for (int attempt = 0;; ++attempt) {
-        // a region holds the rows of one chunk: a row is at most 30 + 46 bytes of a line of about avg_line_bytes
-        const double lines_per_chunk = (double)chunk_bytes / std::max(8.0, ctx->avg_line_bytes);
-        uint64_t region_cap64 = (uint64_t)((lines_per_chunk * 56.0 + 4096.0) * ctx->region_factor);
-        region_cap64 = std::min<uint64_t>((region_cap64 + 15) & ~(uint64_t)15, (uint64_t)1 << 30);
-        const uint32_t region_cap = (uint32_t)region_cap64;
-        TRY(ensure(ctx, ctx->rows_scratch, (size_t)n_chunks * region_cap));
-        CK(cudaMemsetAsync(ctx->blk.p, 0, (size_t)n_chunks * 8, ctx->stream));
-        CK(cudaMemsetAsync(ctl_field(ctx, &Control::tok_ticket), 0, sizeof(unsigned int), ctx->stream));
-        CK(cudaMemsetAsync(ctl_field(ctx, &Control::n_sites), 0, sizeof(unsigned long long), ctx->stream));
-        CK(cudaMemsetAsync(ctl_field(ctx, &Control::error), 0xFF, sizeof(unsigned long long), ctx->stream));
-        CK(cudaMemsetAsync(ctl_field(ctx, &Control::csv_bytes), 0, 2 * sizeof(unsigned long long), ctx->stream));
-        Tok3Params q {};
-        q.text = (const uint8_t*)d_text; q.text_len = text_len; q.range_begin = range_begin; q.range_end = range_end;
-        q.origin = origin; q.n_chunks = n_chunks; q.chunk_bytes = (uint32_t)chunk_bytes;
-        q.rows = (uint8_t*)ctx->rows_scratch.p; q.region_cap = region_cap;
-        q.prior = ctx->session_prior; q.error_threshold = ctx->params.error_threshold; q.alpha = ctx->params.significance_level;
-        q.het_only = ctx->params.het_only;
-        q.ticket = ctl_field(ctx, &Control::tok_ticket);
-        q.site_alloc = ctl_field(ctx, &Control::n_sites);
-        q.blk = (unsigned long long*)ctx->blk.p;
-        q.error = ctl_field(ctx, &Control::error);
-        q.table = ctx->tab;
-        const uint32_t dyn = (uint32_t)(T3_WARPS * sizeof(Tok3Warp));
-        int per_sm = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tok3_rows, T3_THREADS, dyn) != cudaSuccess || per_sm < 1) per_sm = 1;
-        const unsigned grid = (unsigned)std::min<uint64_t>((n_chunks + T3_WARPS - 1) / T3_WARPS, (uint64_t)ctx->sm_count * per_sm);
-        {
-            ProfScope prof(ctx, PROF_TOKENIZE);
-            k_tok3_rows<<<grid, T3_THREADS, dyn, ctx->stream>>>(q);
-            TRY(check_launch(ctx, "k_tok3_rows"));
-        }
-        {
-            ProfScope prof(ctx, PROF_CSV);
-            k_rows3_scan<<<1, 1024, 0, ctx->stream>>>((const unsigned long long*)ctx->blk.p, n_chunks, (unsigned long long*)ctx->rows_part.p,
-                                                      ctl_field(ctx, &Control::csv_bytes), ctl_field(ctx, &Control::csv_rows));
-            TRY(check_launch(ctx, "k_rows3_scan"));
-            const uint32_t ppr = (region_cap + RC3_PIECE - 1) / RC3_PIECE;
-            const uint64_t items = (uint64_t)n_chunks * ppr;
-            const unsigned cgrid = (unsigned)std::min<uint64_t>((items + RC3_THREADS / 32 - 1) / (RC3_THREADS / 32), (uint64_t)ctx->sm_count * 6);
-            k_rows3_copy<<<cgrid, RC3_THREADS, (RC3_THREADS / 32) * RC3_STAGE, ctx->stream>>>(
-                (const uint8_t*)ctx->rows_scratch.p, region_cap, (const unsigned long long*)ctx->blk.p, (const unsigned long long*)ctx->rows_part.p,
-                n_chunks, ppr, (uint8_t*)d_out, out_cap);
-            TRY(check_launch(ctx, "k_rows3_copy"));
-        }
-        TRY(sync_ctl(ctx));
-        const Control& c = *ctx->h_ctl;
-        if (c.error != ~0ull) {
-            const int st = (int)(c.error & 7);
-            const unsigned long long off = c.error >> 3;
-            if (st == LINE_ROWS_OVERFLOW) {
-                if (attempt >= 6) return ctx->fail(SIDGPU_EINTERNAL, "row region sizing failed");
-                ctx->region_factor *= 2.0;
-                continue;
-            }
-            const int code = st == LINE_MALFORMED ? SIDGPU_EMALFORMED : SIDGPU_EINTERNAL;
-            return ctx->fail(code, "%s (line starting at byte %llu)", status_text(st), off);
-        }
-        if (c.table_overflow) {
-            TRY(grow_table(ctx, 2, 0));
-            continue;
-        }
-        *n_out = c.n_sites;
-        *bytes_out = c.csv_bytes;
-        *rows_out = c.csv_rows;
-        if (c.n_sites >= 64) ctx->avg_line_bytes = (double)(range_end - range_begin) / (double)c.n_sites;
-        while ((uint64_t)c.n_entries * 2 > ctx->tab.cap) TRY(grow_table(ctx, 2, 0));
-        ctx->classified = c.n_entries;                       // every entry was classified by the lane that inserted it
-        if (c.csv_bytes > out_cap) return ctx->fail(SIDGPU_ECAPACITY, "CSV needs %llu bytes, buffer has %zu", c.csv_bytes, out_cap);
-        return SIDGPU_OK;
-    }
-}
-
 __global__ void k_insert_profiles(TableView t, const uint64_t* profiles, const uint64_t* weights, uint64_t n) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -1125,8 +1030,6 @@ int sidgpu_create(const sidgpu_config* cfg, sidgpu_ctx** out) {
         (e = cudaFuncSetAttribute(k_tok2<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tok2_dyn_smem(SLICE_MAX, 2016, 1, true))) != cudaSuccess ||
         (e = cudaFuncSetAttribute(k_tok2<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::min<uint32_t>(227u << 10, tok2_dyn_smem(SLICE_MAX, 2016, 2, true)))) != cudaSuccess ||
         (e = cudaFuncSetAttribute(k_rows_compact, cudaFuncAttributeMaxDynamicSharedMemorySize, (RC_THREADS / 32) * RC_STAGE)) != cudaSuccess ||
-        (e = cudaFuncSetAttribute(k_tok3_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(T3_WARPS * sizeof(Tok3Warp)))) != cudaSuccess ||
-        (e = cudaFuncSetAttribute(k_tok3_rows, cudaFuncAttributePreferredSharedMemoryCarveout, 100)) != cudaSuccess ||
         (e = cudaFuncSetAttribute(k_csv, cudaFuncAttributeMaxDynamicSharedMemorySize, CSV_STAGE)) != cudaSuccess) {
         ctx->err = std::string("shared memory opt-in: ") + cudaGetErrorString(e);
         return bail(SIDGPU_ECUDA);
@@ -1342,9 +1245,7 @@ int sidgpu_feed_rows(sidgpu_ctx* ctx, const char* d_text, size_t text_len, size_
         return ctx->fail(SIDGPU_EINVAL, "sidgpu_feed_rows is for `local` sessions without -R (rows need no genome-wide step); use sidgpu_feed + sidgpu_emit_csv");
     CK(cudaSetDevice(ctx->device));
     uint64_t bytes = 0, rows = 0, n = 0;
-    static const int rows_version = getenv("SIDGPU_ROWS_K1") ? atoi(getenv("SIDGPU_ROWS_K1")) : 3;     // 2: k_tok2<rows> (A/B runs)
-    const int rc = rows_version == 2 ? run_tok2_rows(ctx, d_text, text_len, range_begin, range_end, d_out, out_cap, &bytes, &rows, &n)
-                                     : run_tok3_rows(ctx, d_text, text_len, range_begin, range_end, d_out, out_cap, &bytes, &rows, &n);
+    const int rc = run_tok2_rows(ctx, d_text, text_len, range_begin, range_end, d_out, out_cap, &bytes, &rows, &n);
     if (rc == SIDGPU_ECAPACITY && bytes_out) *bytes_out = bytes;       // the size the caller has to offer
     if (rc != SIDGPU_OK) return rc;
     ctx->last_text = d_text;
@@ -1702,3 +1603,4 @@ int sidgpu_format_g(sidgpu_ctx* ctx, const double* d_values, uint64_t n, char* d
 }  // extern "C"
 
 #include "host_path.inl"
+#include "host_io.inl"

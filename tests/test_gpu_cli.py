@@ -46,6 +46,18 @@ def test_cli_matches_reference(sid_bin, case):
         assert re.search(r"# GSL function minimization converged in \d+ iterations\.", err)
 
 
+def test_cli_reads_a_pipe(sid_bin):
+    """No seekable file, no size: the streaming host reads whatever the descriptor delivers (zcat x.gz | sid /dev/stdin)."""
+    import subprocess
+    text = open(os.path.join(GOLDEN, "depth30.plp"), "rb").read()
+    for extra in ([], ["-m", "bayes"], ["--chunk-mb", "1"]):
+        r = subprocess.run([sid_bin] + extra + ["/dev/stdin"], input=text, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+        assert r.returncode == 0, r.stderr
+        want = open(os.path.join(GOLDEN, "depth30.m_bayes.csv" if "bayes" in extra else "depth30.m_local.csv"), "rb").read()
+        n, diffs = op.compare_csv(r.stdout, want)
+        assert diffs <= max(2, n // 1000)
+
+
 def test_cli_het_only(sid_bin):
     """--het-only == the reference's output through grep ',het,' (header kept)."""
     case = [c for c in MANIFEST["cases"] if c["input"] == "depth30.plp" and c["flags"][:2] == ["-m", "local"]][0]

@@ -190,6 +190,59 @@ def test_csv_many_small_chunks(native, tiny_chunk_ctx, case):
     assert diffs <= max(2, n // 1000)
 
 
+@pytest.mark.parametrize("case", [c for c in MANIFEST["cases"] if c["input"] in ("depth30.plp", "depth30_two_chroms.plp", "quality30.plp",
+                                                                                  "depth500.plp", "edge.plp")], ids=lambda c: c["csv"])
+def test_call_io_streams_the_same_rows(native, tiny_chunk_ctx, case):
+    """sidgpu_call_io (what the `sid` binary uses): text pulled through a read callback in odd pieces, rows pushed to a
+    write callback chunk by chunk, the input rewound for the second pass of quality -R."""
+    import io
+    import sid_b200
+    text = read(case["input"])
+    kw = flags_to_kwargs(case["flags"])
+    fit = None
+    if "heterozygosity" in case or kw.get("estimate_prior"):
+        o = op.oracle_call(text, **kw)
+        prof = o["profiles"]
+        cov = op.unpack_profiles(prof).astype(np.int64).sum(axis=1)
+        u, c = op.oracle_unique(prof[cov >= 4])
+        fit = (o["pi"], o["eps"], op.oracle_nd(u, c))
+    src = io.BytesIO(text)
+    pieces = []
+    nb, n_sites, n_rows = tiny_chunk_ctx.call_io(lambda n: src.read(min(n, 7001)), pieces.append, params_from_flags(case["flags"], fit),
+                                                 rewind=lambda: src.seek(0))
+    rows = b"".join(pieces)
+    assert nb == len(rows) and len(pieces) >= 2
+    n, diffs = op.compare_csv(sid_b200.CSV_HEADER + rows, read(case["csv"]))
+    assert n == n_rows
+    assert diffs <= max(2, n // 1000)
+
+
+def test_call_io_errors(native, tiny_chunk_ctx):
+    import io
+    import sid_b200
+    p = sid_b200.Context.make_params("local")
+    # a malformed line: the reference's error, whatever was streamed before it
+    bad = read("malformed_second_line_bad.plp")
+    src = io.BytesIO(bad)
+    with pytest.raises(sid_b200.MalformedPileup):
+        tiny_chunk_ctx.call_io(lambda n: src.read(n), lambda rows: None, p)
+    # a failing callback surfaces as the callback's own exception, and the ctx stays usable
+    def boom(n):
+        raise OSError("disk on fire")
+    with pytest.raises(OSError):
+        tiny_chunk_ctx.call_io(boom, lambda rows: None, p)
+    text = read("depth30.plp")
+    src = io.BytesIO(text)
+    out = []
+    tiny_chunk_ctx.call_io(lambda n: src.read(n), out.append, p)
+    n, diffs = op.compare_csv(sid_b200.CSV_HEADER + b"".join(out), read("depth30.m_local.csv"))
+    assert diffs <= max(2, n // 1000)
+    # quality with -R needs a rewindable input
+    src = io.BytesIO(read("quality30.plp"))
+    with pytest.raises(sid_b200.SidGpuError):
+        tiny_chunk_ctx.call_io(lambda n: src.read(n), lambda rows: None, sid_b200.Context.make_params("quality", estimate_prior=True))
+
+
 @pytest.mark.parametrize("lam,n_sites", [(3000.0, 120), (20000.0, 24), (70000.0, 6)])
 @pytest.mark.parametrize("method", ["local", "quality"])
 def test_very_deep_pileups(native, gpu_ctx, lam, n_sites, method):
