@@ -15,9 +15,9 @@ typedef struct {                                      // pileup.hpp:9-18
     int position {-1};
     char reference_base {'N'};
     profile_t base_counts;
-    // The reference also materialises per-read vectors (bases, strands, base/mapping qualities).
-    // They only feed `-m quality`, which here consumes the text directly on the device
-    // (k_quality.cuh), so they are never built; the members exist for source compatibility.
+    // Per-read vectors (pileup.hpp:14-17).  The calling path never needs them (`-m quality` consumes the text on
+    // the device, k_quality.cuh); parsePileupLine / readFile fill bases and strands always, like the reference, and
+    // the two quality vectors when asked (sidgpu_read_counts / sidgpu_read_fill).
     std::vector<char> bases;
     std::vector<bool> strands;
     std::vector<uint8_t> base_qualities;
@@ -34,8 +34,11 @@ typedef struct {                                      // pileup.hpp:22-26
     profile_t counts;
 } ReadStack;
 
-// pileup.cpp:70-153: counts of a bases string against a reference base.
+// pileup.cpp:70-153: counts, letters and strands of a bases string against a reference base.
 ReadStack parseReadBases(const char* read_bases, char reference, int coverage);
+
+// pileup.cpp:155-167: character - 33, at least 1, up to the first NUL, tab or line end.
+std::vector<uint8_t> parseQualities(const char* base_qualities, int coverage);
 
 typedef struct UniqueProfile {                        // pileup.hpp:32-40
     profile_t profile;

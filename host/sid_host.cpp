@@ -7,6 +7,7 @@
 #include <memory>
 #include <sstream>
 #include <algorithm>
+#include <chrono>
 #include <limits>
 #include <stdexcept>
 #include <thread>
@@ -17,6 +18,8 @@
 #include "../include/sidgpu.h"
 #include "../sid_b200/csrc/nelder_mead.hpp"      // the simplex driver the library itself uses (host code, header only)
 #include "call.hpp"
+#include "lynch.hpp"
+#include "stats.hpp"
 
 namespace {
 
@@ -538,7 +541,14 @@ SidRunInfo sidCallFile(const std::string& method, int fd_in, bool gzip, bool est
     p.het_only = g_het_only ? 1 : 0;
     sidgpu_io io {FileIo::read_cb, FileIo::write_cb, FileIo::rewind_cb, &f};
     uint64_t bytes = 0;
-    const int rc = sidgpu_call_io(ctx().h, &p, &io, &bytes, &info.n_sites, &info.n_rows);
+    const auto t0 = std::chrono::steady_clock::now();
+    sidgpu_ctx* h = ctx().h;                        // creates the ctx on first use: CUDA context, kernels, tables
+    const auto t1 = std::chrono::steady_clock::now();
+    const int rc = sidgpu_call_io(h, &p, &io, &bytes, &info.n_sites, &info.n_rows);
+    const auto t2 = std::chrono::steady_clock::now();
+    if (getenv("SID_TIMING"))                       // where the wall clock of a run goes (bench.py cli_e2e)
+        log << "# timing: device setup " << std::chrono::duration<double>(t1 - t0).count() << " s, streaming " << bytes << " CSV bytes "
+            << std::chrono::duration<double>(t2 - t1).count() << " s" << std::endl;
     if (f.gz) gzclose(f.gz);
     if (rc != SIDGPU_OK) {
         if (f.write_failed) throw std::runtime_error("could not write the rows");
@@ -561,9 +571,14 @@ SidRunInfo sidCallFile(const std::string& method, int fd_in, bool gzip, bool est
 }
 
 // ---- pileup.hpp / call.hpp:12 ----------------------------------------------------------------------
+void fillReadVectors(std::vector<PileupLine>& lines, const char* text, size_t len, const std::vector<uint64_t>& starts,
+                     bool parse_base_qualities, bool parse_mapping_qualities);
+
 std::vector<PileupLine> parsePileupText(const char* text, size_t len, bool parse_base_qualities, bool parse_mapping_qualities) {
-    const Parsed p = tokenize(text, len, parse_base_qualities || parse_mapping_qualities);
+    const Parsed p = tokenize(text, len, false);
     std::vector<PileupLine> out(p.pos.size());
+    std::vector<uint64_t> starts;
+    starts.reserve(out.size());
     // reference base: the third column; recovered from the text only to fill the struct (1 byte per line)
     size_t line = 0, i = 0;
     while (i < len && line < out.size()) {
@@ -583,10 +598,13 @@ std::vector<PileupLine> parsePileupText(const char* text, size_t len, bool parse
             }
             while (q < e && (text[q] == ' ' || text[q] == '\t')) ++q;
             if (q < e) l.reference_base = text[q];
+            starts.push_back(i);
             ++line;
         }
         i = e + 1;
     }
+    // the per-read vectors (pileup.cpp:42-44: bases and strands always; :53-66: the qualities when asked)
+    fillReadVectors(out, text, len, starts, parse_base_qualities, parse_mapping_qualities);
     return out;
 }
 
@@ -604,12 +622,16 @@ PileupLine parsePileupLine(char* line, bool parse_base_qualities, bool parse_map
 
 ReadStack parseReadBases(const char* read_bases, char reference, int coverage) {
     (void)coverage;                                 // the reference only uses it as a reserve() hint (pileup.cpp:72-73)
-    std::string line = std::string("x\t1\t") + reference + "\t0\t" + read_bases + "\n";
     ReadStack r;
     r.counts = {0, 0, 0, 0};
     if (read_bases[0] == '\0') return r;            // an empty bases string is not a valid column; counts are zero
-    const Parsed p = tokenize(line.data(), line.size(), false);
-    if (!p.profile.empty()) r.counts = unpack(p.profile[0]);
+    const std::string line = std::string("x\t1\t") + reference + "\t0\t" + read_bases + "\n";
+    const std::vector<PileupLine> v = parsePileupText(line.data(), line.size(), false, false);
+    if (!v.empty()) {
+        r.counts = v[0].base_counts;
+        r.bases = v[0].bases;
+        r.strands = v[0].strands;
+    }
     return r;
 }
 
@@ -655,4 +677,155 @@ std::array<double, 4> computeNucleotideDistribution(const std::vector<UniqueProf
     sidgpu_unique_view v {};
     check(sidgpu_count_unique_weighted(ctx().h, dp, dc, prof.size(), 0, &v));
     return {v.nd[0], v.nd[1], v.nd[2], v.nd[3]};
+}
+
+// ---- the per-read vectors and the Lynch / statistics mirrors ---------------------------------------------------------
+namespace {
+
+struct Dev {                                        // a device allocation that goes away with the scope
+    void* p = nullptr;
+    explicit Dev(size_t bytes) { check(sidgpu_malloc(ctx().h, std::max<size_t>(bytes, 16), &p)); }
+    ~Dev() { sidgpu_free(ctx().h, p); }
+    Dev(const Dev&) = delete;
+    Dev& operator=(const Dev&) = delete;
+    template <class T> T* as() const { return (T*)p; }
+};
+
+template <class T>
+std::vector<uint64_t> offsets_of(const std::vector<T>& counts) {          // exclusive prefix sums (index arithmetic)
+    std::vector<uint64_t> off(counts.size() + 1, 0);
+    for (size_t i = 0; i < counts.size(); ++i) off[i + 1] = off[i] + counts[i];
+    return off;
+}
+
+std::vector<uint64_t> pack_profiles(const std::vector<UniqueProfile>& profiles) {
+    std::vector<uint64_t> p(profiles.size());
+    for (size_t i = 0; i < profiles.size(); ++i) {
+        const profile_t& c = profiles[i].profile;
+        p[i] = (uint64_t)c[0] | ((uint64_t)c[1] << 16) | ((uint64_t)c[2] << 32) | ((uint64_t)c[3] << 48);
+    }
+    return p;
+}
+
+}  // namespace
+
+// Fills bases / strands (always) and the quality vectors (when asked) of the lines of `text`; starts[i] = offset of line i.
+void fillReadVectors(std::vector<PileupLine>& lines, const char* text, size_t len, const std::vector<uint64_t>& starts,
+                     bool parse_base_qualities, bool parse_mapping_qualities) {
+    const size_t n = lines.size();
+    if (n == 0) return;
+    Dev d_text(((len + 15) & ~(size_t)15) + 16), d_off(n * 8), d_nb(n * 4), d_nq(n * 4), d_nm(n * 4);
+    check(sidgpu_memcpy_h2d(ctx().h, d_text.p, text, len));
+    check(sidgpu_memcpy_h2d(ctx().h, d_off.p, starts.data(), n * 8));
+    check(sidgpu_read_counts(ctx().h, d_text.as<char>(), len, d_off.as<uint64_t>(), n, parse_base_qualities ? 1 : 0, parse_mapping_qualities ? 1 : 0,
+                             d_nb.as<uint32_t>(), d_nq.as<uint32_t>(), d_nm.as<uint32_t>()));
+    std::vector<uint32_t> nb(n), nq(n), nm(n);
+    check(sidgpu_memcpy_d2h(ctx().h, nb.data(), d_nb.p, n * 4));
+    check(sidgpu_memcpy_d2h(ctx().h, nq.data(), d_nq.p, n * 4));
+    check(sidgpu_memcpy_d2h(ctx().h, nm.data(), d_nm.p, n * 4));
+    const std::vector<uint64_t> ob = offsets_of(nb), oq = offsets_of(nq), om = offsets_of(nm);
+    Dev d_ob(n * 8), d_oq(n * 8), d_om(n * 8), d_bases(ob[n]), d_str(ob[n]), d_bq(oq[n]), d_mq(om[n]);
+    check(sidgpu_memcpy_h2d(ctx().h, d_ob.p, ob.data(), n * 8));
+    check(sidgpu_memcpy_h2d(ctx().h, d_oq.p, oq.data(), n * 8));
+    check(sidgpu_memcpy_h2d(ctx().h, d_om.p, om.data(), n * 8));
+    check(sidgpu_read_fill(ctx().h, d_text.as<char>(), len, d_off.as<uint64_t>(), n, d_ob.as<uint64_t>(), d_oq.as<uint64_t>(), d_om.as<uint64_t>(),
+                           d_bases.as<char>(), d_str.as<uint8_t>(), parse_base_qualities ? d_bq.as<uint8_t>() : nullptr,
+                           parse_mapping_qualities ? d_mq.as<uint8_t>() : nullptr));
+    std::vector<char> bases(ob[n]);
+    std::vector<uint8_t> str(ob[n]), bq(parse_base_qualities ? oq[n] : 0), mq(parse_mapping_qualities ? om[n] : 0);
+    if (ob[n]) {
+        check(sidgpu_memcpy_d2h(ctx().h, bases.data(), d_bases.p, ob[n]));
+        check(sidgpu_memcpy_d2h(ctx().h, str.data(), d_str.p, ob[n]));
+    }
+    if (!bq.empty()) check(sidgpu_memcpy_d2h(ctx().h, bq.data(), d_bq.p, bq.size()));
+    if (!mq.empty()) check(sidgpu_memcpy_d2h(ctx().h, mq.data(), d_mq.p, mq.size()));
+    for (size_t i = 0; i < n; ++i) {
+        PileupLine& l = lines[i];
+        l.bases.assign(bases.begin() + (ptrdiff_t)ob[i], bases.begin() + (ptrdiff_t)ob[i + 1]);
+        l.strands.resize(nb[i]);
+        for (uint32_t k = 0; k < nb[i]; ++k) l.strands[k] = str[ob[i] + k] != 0;
+        if (parse_base_qualities) l.base_qualities.assign(bq.begin() + (ptrdiff_t)oq[i], bq.begin() + (ptrdiff_t)oq[i + 1]);
+        if (parse_mapping_qualities) l.mapping_qualities.assign(mq.begin() + (ptrdiff_t)om[i], mq.begin() + (ptrdiff_t)om[i + 1]);
+    }
+}
+
+std::vector<uint8_t> parseQualities(const char* base_qualities, int coverage) {
+    (void)coverage;                                 // a reserve() hint in the reference (pileup.cpp:157)
+    const size_t n = std::strlen(base_qualities);
+    std::vector<uint8_t> out;
+    if (n == 0) return out;
+    Dev d_in(n), d_out(n);
+    check(sidgpu_memcpy_h2d(ctx().h, d_in.p, base_qualities, n));
+    uint64_t m = 0;
+    check(sidgpu_qualities(ctx().h, d_in.as<char>(), n, d_out.as<uint8_t>(), &m));
+    out.resize(m);
+    if (m) check(sidgpu_memcpy_d2h(ctx().h, out.data(), d_out.p, m));
+    return out;
+}
+
+// ---- lynch.hpp:44-46 ---------------------------------------------------------------------------------------------------
+ProfileGenotypeLikelihoods estimateProfileGenotypeLikelihoods(const std::vector<UniqueProfile>& profiles, const std::array<double, 4> nd) {
+    ProfileGenotypeLikelihoods r {0, 0, {}};
+    const size_t n = profiles.size();
+    if (n == 0) return r;
+    const std::vector<uint64_t> prof = pack_profiles(profiles);
+    std::vector<uint64_t> cnt(n);
+    for (size_t i = 0; i < n; ++i) cnt[i] = profiles[i].count;
+    Dev d_p(n * 8), d_c(n * 8), d_h(n * 8), d_t(n * 8);
+    check(sidgpu_memcpy_h2d(ctx().h, d_p.p, prof.data(), n * 8));
+    check(sidgpu_memcpy_h2d(ctx().h, d_c.p, cnt.data(), n * 8));
+    sidgpu_unique_view v {};
+    check(sidgpu_count_unique_weighted(ctx().h, d_p.as<uint64_t>(), d_c.as<uint64_t>(), n, 0, &v));     // the histogram the fit runs on
+    sidgpu_fit fit {};
+    check(sidgpu_lynch_fit(ctx().h, nd.data(), &fit));
+    r.heterozygosity = fit.pi;
+    r.error_rate = fit.eps;
+    check(sidgpu_profile_loglik(ctx().h, d_p.as<uint64_t>(), n, nd.data(), fit.eps, d_h.as<double>(), d_t.as<double>()));
+    std::vector<double> lh(n), lt(n);
+    check(sidgpu_memcpy_d2h(ctx().h, lh.data(), d_h.p, n * 8));
+    check(sidgpu_memcpy_d2h(ctx().h, lt.data(), d_t.p, n * 8));
+    r.profile_likelihoods.resize(n);
+    for (size_t i = 0; i < n; ++i) r.profile_likelihoods[i] = {expl((long double)lh[i]), expl((long double)lt[i])};
+    return r;
+}
+
+double compoundLikelihood(double pi, double epsilon, const std::vector<UniqueProfile>& profiles, const std::array<double, 4> nd) {
+    const size_t n = profiles.size();
+    if (n == 0) return (pi < 0 || pi > 1 || epsilon < 0 || epsilon > 1) ? std::numeric_limits<double>::max() : 0.0;
+    const std::vector<uint64_t> prof = pack_profiles(profiles);
+    std::vector<uint64_t> cnt(n);
+    for (size_t i = 0; i < n; ++i) cnt[i] = profiles[i].count;
+    Dev d_p(n * 8), d_c(n * 8);
+    check(sidgpu_memcpy_h2d(ctx().h, d_p.p, prof.data(), n * 8));
+    check(sidgpu_memcpy_h2d(ctx().h, d_c.p, cnt.data(), n * 8));
+    sidgpu_unique_view v {};
+    check(sidgpu_count_unique_weighted(ctx().h, d_p.as<uint64_t>(), d_c.as<uint64_t>(), n, 0, &v));
+    double f = 0;
+    check(sidgpu_lynch_objective(ctx().h, nd.data(), pi, epsilon, &f));
+    return f;
+}
+
+// ---- stats.hpp:8,11 ----------------------------------------------------------------------------------------------------
+double likelihoodRatioTest(long double l_H0, long double l_H1) {
+    // the device works on log-likelihoods (-inf: l == 0)
+    const double a = l_H0 > 0 ? (double)logl(l_H0) : -std::numeric_limits<double>::infinity();
+    const double b = l_H1 > 0 ? (double)logl(l_H1) : -std::numeric_limits<double>::infinity();
+    Dev d_a(8), d_b(8), d_p(8);
+    check(sidgpu_memcpy_h2d(ctx().h, d_a.p, &a, 8));
+    check(sidgpu_memcpy_h2d(ctx().h, d_b.p, &b, 8));
+    check(sidgpu_lr_test(ctx().h, d_a.as<double>(), d_b.as<double>(), 1, d_p.as<double>()));
+    double p = 0;
+    check(sidgpu_memcpy_d2h(ctx().h, &p, d_p.p, 8));
+    return p;
+}
+
+std::vector<double> adjustBenjaminiHochberg(const std::vector<double>& p_values) {
+    std::vector<double> out(p_values.size());
+    if (p_values.empty()) return out;
+    const size_t n = p_values.size();
+    Dev d_p(n * 8), d_a(n * 8);
+    check(sidgpu_memcpy_h2d(ctx().h, d_p.p, p_values.data(), n * 8));
+    check(sidgpu_bh_adjust(ctx().h, d_p.as<double>(), n, d_a.as<double>()));
+    check(sidgpu_memcpy_d2h(ctx().h, out.data(), d_a.p, n * 8));
+    return out;
 }

@@ -93,6 +93,8 @@ int sidgpu_free_host(sidgpu_ctx* ctx, void* h_ptr);
 int sidgpu_memcpy_h2d(sidgpu_ctx* ctx, void* d_dst, const void* h_src, size_t bytes);
 int sidgpu_memcpy_d2h(sidgpu_ctx* ctx, void* h_dst, const void* d_src, size_t bytes);
 int sidgpu_memcpy_d2d(sidgpu_ctx* ctx, void* d_dst, const void* d_src, size_t bytes);
+/* The same, only enqueued on the ctx's stream (for hosts that run their own work on that stream). */
+int sidgpu_memcpy_d2d_async(sidgpu_ctx* ctx, void* d_dst, const void* d_src, size_t bytes);
 
 /* ------------------------------------------------------------------------------------------------
  * K1: tokenizer + profile builder
@@ -119,6 +121,25 @@ typedef struct {
 
 int sidgpu_tokenize(sidgpu_ctx* ctx, const char* d_text, size_t text_len, size_t range_begin,
                     size_t range_end, int want_qual, sidgpu_sites_view* out);
+
+/* The per-read side of the parser interface, for hosts that ask for it (readFile(in, true, true), call.cpp:11-20;
+ * PileupLine::bases / strands / base_qualities / mapping_qualities, pileup.hpp:14-17).  The calling path never builds
+ * these vectors (`quality` consumes the text on the device); they exist for inspection and for the reference's tests.
+ *   sidgpu_qualities    parseQualities (pileup.cpp:155-167) of one string: character - 33, at least 1, up to the first
+ *                       NUL, tab or line end; *n_out = number of qualities written to d_out.
+ *   sidgpu_read_counts  per line (d_line_off[i] = offset of its first byte in d_text): the lengths of its three vectors.
+ *                       A line with fewer than five columns is SIDGPU_EMALFORMED.  The quality columns matter only
+ *                       when asked for: a missing sixth column is SIDGPU_EMALFORMED with want_baseq != 0, a missing
+ *                       seventh SIDGPU_EMISSING_MAPQ with want_mapq != 0 (pileup.cpp:60-66); else their counts are 0.
+ *   sidgpu_read_fill    the vectors themselves at the offsets the caller derived from the counts (exclusive prefix sums):
+ *                       bases as upper-case letters, strands 1 = upper case / forward (pileup.cpp:84-123), qualities
+ *                       as numbers.  Any output pointer may be NULL. */
+int sidgpu_qualities(sidgpu_ctx* ctx, const char* d_quals, size_t n, uint8_t* d_out, uint64_t* n_out);
+int sidgpu_read_counts(sidgpu_ctx* ctx, const char* d_text, size_t text_len, const uint64_t* d_line_off, uint64_t n_lines,
+                       int want_baseq, int want_mapq, uint32_t* d_n_bases, uint32_t* d_n_bq, uint32_t* d_n_mq);
+int sidgpu_read_fill(sidgpu_ctx* ctx, const char* d_text, size_t text_len, const uint64_t* d_line_off, uint64_t n_lines,
+                     const uint64_t* d_base_off, const uint64_t* d_bq_off, const uint64_t* d_mq_off, char* d_bases,
+                     uint8_t* d_strands, uint8_t* d_bq, uint8_t* d_mq);
 
 /* ------------------------------------------------------------------------------------------------
  * Calling sessions: the four functions of call.hpp:40-43, streamed.
@@ -277,6 +298,13 @@ int sidgpu_session_fit(sidgpu_ctx* ctx, sidgpu_fit* out, double nd[4], uint64_t*
  *   `%g` formatting of operator<< call.hpp:29-38.
  * --------------------------------------------------------------------------------------------- */
 int sidgpu_bh_adjust(sidgpu_ctx* ctx, const double* d_p, uint64_t n, double* d_adjusted);
+/* likelihoodRatioTest (stats.cpp:29-37) on n pairs of LOG likelihoods (-inf stands for l == 0): p-values out. */
+int sidgpu_lr_test(sidgpu_ctx* ctx, const double* d_log_h0, const double* d_log_h1, uint64_t n, double* d_p);
+/* log homozygousLikelihood / log heterozygousLikelihood (lynch.hpp:57-74,82-90, multinomial coefficient included) of n
+ * packed profiles under (nucleotide distribution, eps): what estimateProfileGenotypeLikelihoods returns per profile
+ * (lynch.cpp:27-34), in log space. */
+int sidgpu_profile_loglik(sidgpu_ctx* ctx, const uint64_t* d_profiles, uint64_t n, const double nd[4], double eps,
+                          double* d_log_hom, double* d_log_het);
 /* Formats n doubles like printf("%g"); out is n fixed 16-byte cells, NUL padded. */
 int sidgpu_format_g(sidgpu_ctx* ctx, const double* d_values, uint64_t n, char* d_out16);
 

@@ -68,6 +68,7 @@ PROTOTYPES = {
     "sidgpu_memcpy_h2d": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]),
     "sidgpu_memcpy_d2h": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]),
     "sidgpu_memcpy_d2d": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]),
+    "sidgpu_memcpy_d2d_async": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]),
     "sidgpu_tokenize": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t,
                                        ctypes.c_size_t, ctypes.c_int, ctypes.POINTER(SitesView)]),
     "sidgpu_begin": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(Params)]),
@@ -101,6 +102,13 @@ PROTOTYPES = {
     "sidgpu_finish_global": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, c_u64]),
     "sidgpu_session_fit": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(Fit), c_double_p, c_u64_p]),
     "sidgpu_bh_adjust": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, c_u64, ctypes.c_void_p]),
+    "sidgpu_lr_test": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, c_u64, ctypes.c_void_p]),
+    "sidgpu_profile_loglik": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, c_u64, c_double_p, ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p]),
+    "sidgpu_qualities": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, c_u64_p]),
+    "sidgpu_read_counts": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, c_u64, ctypes.c_int, ctypes.c_int,
+                                          ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "sidgpu_read_fill": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, c_u64, ctypes.c_void_p,
+                                        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "sidgpu_format_g": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, c_u64, ctypes.c_void_p]),
     "sidgpu_launch_count": (c_u64, [ctypes.c_void_p]),
     "sidgpu_profile": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),

@@ -109,9 +109,10 @@ class Context:
         buf.text_len = a.nbytes
         return buf
 
-    def copy_d2d(self, dst_ptr, src_ptr, nbytes):
+    def copy_d2d(self, dst_ptr, src_ptr, nbytes, sync=True):
         if nbytes:
-            self._ck(self.lib.sidgpu_memcpy_d2d(self.h, dst_ptr, src_ptr, nbytes))
+            f = self.lib.sidgpu_memcpy_d2d if sync else self.lib.sidgpu_memcpy_d2d_async
+            self._ck(f(self.h, dst_ptr, src_ptr, nbytes))
 
     def _download(self, ptr, dtype, count):
         out = np.empty(int(count), dtype=dtype)

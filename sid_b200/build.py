@@ -41,7 +41,7 @@ def build_libsidgpu(force=False):
     srcs = _glob("sid_b200/csrc", (".cu", ".cuh", ".hpp", ".inl")) + [os.path.join(ROOT, "include", "sidgpu.h")]
     if force or _newer(out, srcs):
         _run([NVCC] + ARCH + ["-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC,-pthread", "-shared",
-                              "sid_b200/csrc/sidgpu.cu", "-o", out])
+                              "sid_b200/csrc/sidgpu.cu", "-o", out, "-ldl"])
     return out
 
 

@@ -269,6 +269,7 @@ struct IoPipe {
 extern "C" int sidgpu_call_io(sidgpu_ctx* ctx, const sidgpu_params* params, const sidgpu_io* io, uint64_t* csv_bytes, uint64_t* n_sites,
                               uint64_t* n_rows) {
     if (!ctx || !params || !io || !io->read || !io->write) return SIDGPU_EINVAL;
+    Range nvtx_range("sidgpu_call_io");
     CK(cudaSetDevice(ctx->device));
     IoPipe pipe;
     pipe.ctx = ctx;

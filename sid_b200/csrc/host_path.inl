@@ -150,6 +150,7 @@ struct HostIo {
 extern "C" int sidgpu_call_host(sidgpu_ctx* ctx, const sidgpu_params* params, const char* h_text, size_t text_len,
                                 char* h_csv, size_t csv_cap, uint64_t* csv_bytes, uint64_t* n_sites, uint64_t* n_rows) {
     if (!ctx || !params || (text_len && !h_text)) return SIDGPU_EINVAL;
+    Range nvtx_range("sidgpu_call_host");
     CK(cudaSetDevice(ctx->device));
     HostIo io(ctx);
     TRY(io.init());

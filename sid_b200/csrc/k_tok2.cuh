@@ -140,14 +140,120 @@ __device__ __noinline__ void parse_line_slow(const uint8_t* txt, uint64_t abs0, 
     }
 }
 
+// Stage 2 of a slice of LONG lines, warp-collective: the lines of the slice one per lane (line_off; `mine` false on
+// the lanes without one), their bases fields cut into 64-byte windows, one window per lane and pass (parse_win.cuh:
+// win_window).  Returns per lane whether its line stayed within the fast grammar; wl as parse_line_win<true>.
+__device__ __forceinline__ bool parse_lines_by_windows(const uint8_t* txt, uint32_t region_off, const uint32_t* cw, const uint32_t* nlw,
+                                                    const uint32_t* term_groups, uint32_t n_bits, uint32_t line_off, bool mine, WinLine& wl) {
+    constexpr uint32_t FULL = 0xFFFFFFFFu;
+    const uint32_t lane = threadIdx.x & 31u;
+    WinHeader hd;
+    Win64 w0;
+    bool ok = win_header<true>(txt, region_off, cw, nlw, n_bits, line_off, wl, hd, w0) && mine;
+    const uint32_t a = hd.l0 + hd.q4 + 1;                        // first byte of the bases field
+    uint32_t b = ok ? win_field_end(cw, n_bits, a, term_groups) : 0u;     // its end
+    if (b == 0xFFFFFFFFu || b <= a) { ok = false; b = 0; }
+    const uint32_t nw = ok ? (b - a + 63u) >> 6 : 0u;            // windows of this lane's line
+    const uint32_t refbits = (hd.ref_base ? 1u : 0u) | (hd.ref_p1 ? 2u : 0u) | (hd.ref_p2 ? 4u : 0u);
+    uint32_t incl = nw;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t o = __shfl_up_sync(FULL, incl, d);
+        if (lane >= (uint32_t)d) incl += o;
+    }
+    const uint32_t excl = incl - nw;
+    const uint32_t total = __shfl_sync(FULL, incl, 31);
+    uint64_t acc = 0;                                            // packed profile of this lane's line
+    uint32_t pass_carry = 0;                                     // skip_out of the last window of the pass before
+    for (uint32_t g0 = 0; g0 < total; g0 += 32) {
+        const uint32_t g = g0 + lane;                            // this lane's window, counted over all lines
+        const bool active = g < total;
+        // its line: the first j with incl_j > g
+        uint32_t j = 0;
+#pragma unroll
+        for (int step = 16; step; step >>= 1) {
+            const uint32_t v = __shfl_sync(FULL, incl, (int)(j + step - 1));
+            if (v <= g) j += step;
+        }
+        j = j < 31u ? j : 31u;
+        const uint32_t aj = __shfl_sync(FULL, a, (int)j), bj = __shfl_sync(FULL, b, (int)j), ej = __shfl_sync(FULL, excl, (int)j);
+        const uint32_t rj = __shfl_sync(FULL, refbits, (int)j);
+        const uint32_t k = g - ej;                               // window k of line j
+        const uint32_t pos = aj + 64u * k;
+        const bool cont = active && k > 0;                       // the window before it belongs to the same line
+        uint32_t skip_in = (cont && lane == 0) ? pass_carry : 0u;
+        // every lane evaluates its window as if nothing reached into it (r0), then takes what its predecessor reports;
+        // a skip that lands on plain letters only takes their counts off again (win_window_patch), anything else is a
+        // second evaluation.  A lane is final one round after the lane before it: one or two rounds in practice.
+        const bool in_reach = active && pos + 64u <= n_bits;
+        const Win64 w = load_window(cw, in_reach ? pos : 0u);
+        WinPart r0;
+        r0.cn = r0.c1 = r0.c2 = r0.c12 = r0.cd = 0;
+        r0.skip_out = 0;
+        r0.ok = true;
+        if (active) r0 = win_window_of(w, in_reach, txt, region_off, pos, bj, 0u);
+        WinPart r = r0;
+        if (skip_in) {                                           // lane 0 continuing a line from the pass before
+            if (!win_window_patch(w, pos, bj, r0, skip_in, r)) r = win_window_of(w, in_reach, txt, region_off, pos, bj, skip_in);
+        }
+        for (int round = 0; round < 34; ++round) {
+            const uint32_t up = __shfl_up_sync(FULL, r.skip_out, 1);
+            const uint32_t want = (cont && lane > 0) ? up : skip_in;
+            const bool redo = active && want != skip_in;
+            skip_in = want;
+            if (!__any_sync(FULL, redo)) break;
+            bool full = false;
+            if (redo) {
+                if (skip_in == 0) r = r0;
+                else full = !win_window_patch(w, pos, bj, r0, skip_in, r);
+            }
+            if (__any_sync(FULL, full)) {
+                if (full) r = win_window_of(w, in_reach, txt, region_off, pos, bj, skip_in);
+            }
+        }
+        pass_carry = __shfl_sync(FULL, r.skip_out, 31);
+        // the window's share of its line's profile, summed over the lanes of the line (runs of consecutive lanes)
+        WinHeader hj;
+        hj.l0 = 0; hj.q4 = 0;
+        hj.ref_base = (rj & 1u) != 0; hj.ref_p1 = (rj & 2u) != 0; hj.ref_p2 = (rj & 4u) != 0;
+        uint64_t v = active ? win_profile(r.cn, r.c1, r.c2, r.c12, r.cd, hj) : 0ull;
+        const uint32_t seg = active ? j : 0xFFFFFFFFu;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint64_t o = __shfl_down_sync(FULL, v, d);
+            const uint32_t os = __shfl_down_sync(FULL, seg, d);
+            if (lane + (uint32_t)d < 32u && active && os == seg) v += o;
+        }
+        // line `lane` collects from the first lane of its run in this pass
+        const uint32_t s0 = excl > g0 ? excl : g0;
+        const bool hit = nw != 0 && s0 < incl && s0 < g0 + 32u;
+        const uint32_t src = hit ? s0 - g0 : 0u;
+        const uint64_t part = __shfl_sync(FULL, v, (int)src);
+        const uint32_t refused = __ballot_sync(FULL, active && !r.ok);
+        if (hit) {
+            acc += part;
+            const uint32_t e0 = (incl < g0 + 32u ? incl : g0 + 32u) - g0;          // lanes [src, e0) hold this line's windows
+            const uint32_t m = (e0 >= 32u ? FULL : ((1u << e0) - 1u)) & ~((1u << src) - 1u);
+            if (refused & m) ok = false;
+        }
+    }
+    wl.profile = acc;
+    wl.status = LINE_OK;
+    return ok;
+}
+
 #ifndef SID_TOK2_CTAS
 #define SID_TOK2_CTAS 3         // CTAs per SM the register allocator must leave room for (288 threads each: 72 registers)
 #endif
-template <bool ROWS, int TOK_STAGES>
-__global__ void __launch_bounds__(TOK_THREADS, SID_TOK2_CTAS) k_tok2(const Tok2Params p) {
+// DEEP: the instantiation for long lines (hundreds of bytes): slices of a few lines run stage 2 one window per lane
+// (parse_lines_by_windows).  Its own kernel so that the code and the registers of that path stay out of the ordinary one
+// (folded into one kernel behind a flag it cost the depth-30 path 30 %); shared memory holds two such CTAs per SM anyway.
+template <bool ROWS, int TOK_STAGES, bool DEEP = false>
+__global__ void __launch_bounds__(TOK_THREADS, DEEP ? 2 : SID_TOK2_CTAS) k_tok2(const Tok2Params p) {
     extern __shared__ __align__(128) uint8_t s_dyn[];
     __shared__ StageMeta s_meta[TOK_STAGES];
     __shared__ __align__(8) uint64_t s_full[TOK_STAGES], s_done[TOK_STAGES];
+    __shared__ uint32_t s_term_groups[DEEP ? TOK_PARSE_WARPS : 1][(SLICE_MAX + 2016) / 1024 + 2];     // DEEP, per warp: which units hold a byte <= 0x20
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
@@ -264,7 +370,7 @@ __global__ void __launch_bounds__(TOK_THREADS, SID_TOK2_CTAS) k_tok2(const Tok2P
             uint32_t carry_nl = txt[region_off - 1] == (uint8_t)'\n' ? 1u : 0u;
             for (uint32_t u0 = 0; u0 < units; u0 += 32) {
                 const uint32_t u = u0 + lane;
-                uint32_t st = 0, nl = 0;
+                uint32_t st = 0, nl = 0, tw = 0;
                 if (u < units) {
                     const uint8_t* up = txt + region_off + u * 32;
                     const uint4 v0 = *reinterpret_cast<const uint4*>(up), v1 = *reinterpret_cast<const uint4*>(up + 16);
@@ -276,6 +382,11 @@ __global__ void __launch_bounds__(TOK_THREADS, SID_TOK2_CTAS) k_tok2(const Tok2P
                     nlw[u] = k.nl;
                     nl = k.nl;
                     bad |= k.bad;
+                    if (DEEP) tw = k.w[CW_TERM];
+                }
+                if (DEEP) {
+                    const uint32_t tg = __ballot_sync(0xFFFFFFFFu, tw != 0);
+                    if (lane == 0) s_term_groups[pw][u0 >> 5] = tg;
                 }
                 uint32_t prev = __shfl_up_sync(0xFFFFFFFFu, nl >> 31, 1);
                 if (lane == 0) prev = carry_nl;
@@ -341,6 +452,7 @@ __global__ void __launch_bounds__(TOK_THREADS, SID_TOK2_CTAS) k_tok2(const Tok2P
                 l0_off = TILE_PAD + starts[0];
                 first8 = load8_unaligned(txt, l0_off);
             }
+            const bool by_windows = DEEP && n_lines <= 10u;
             for (uint32_t g = 0; g < n_lines; g += 32) {
                 const uint32_t j = g + lane;
                 const bool mine = j < n_lines;
@@ -351,7 +463,9 @@ __global__ void __launch_bounds__(TOK_THREADS, SID_TOK2_CTAS) k_tok2(const Tok2P
                 bool fast = false;
                 if (win_ok) {
                     WinLine wl;
-                    fast = parse_line_win<true>(txt, region_off, cw, nlw, n_bits, TILE_PAD + off, wl);
+                    // a handful of long lines: one 64-byte window of a bases field per lane instead of one line per lane
+                    if (DEEP && by_windows) fast = parse_lines_by_windows(txt, region_off, cw, nlw, s_term_groups[pw], n_bits, TILE_PAD + off, mine, wl);
+                    else fast = parse_line_win<true>(txt, region_off, cw, nlw, n_bits, TILE_PAD + off, wl);
                     r.status = wl.status; r.pos = wl.pos; r.profile = wl.profile; r.chrom_off = 0; r.chrom_len = wl.name_len;
                 }
                 if (!fast && mine) {

@@ -102,25 +102,19 @@ struct Win64 {              // one 64-bit window of every class
 };
 
 // The classes of the 64 bytes starting at bit `pos` of the class arrays (pos + 64 must lie within the padded arrays).
-// RING_UNITS != 0: the class arrays are a ring of that many units (a power of two); unit indices wrap.
-template <uint32_t RING_UNITS = 0>
 SID_HD Win64 load_window(const uint32_t* cw, uint32_t pos) {
     const uint32_t u = pos >> 5, sh = pos & 31;
     uint32_t a[3][CW_WORDS];
 #if defined(__CUDA_ARCH__)
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-        const uint32_t uu = RING_UNITS ? ((u + k) & (RING_UNITS - 1u)) : (u + k);
-        const uint4 lo = *reinterpret_cast<const uint4*>(cw + (size_t)uu * CW_WORDS);
-        const uint4 hi = *reinterpret_cast<const uint4*>(cw + (size_t)uu * CW_WORDS + 4);
+        const uint4 lo = *reinterpret_cast<const uint4*>(cw + (size_t)(u + k) * CW_WORDS);
+        const uint4 hi = *reinterpret_cast<const uint4*>(cw + (size_t)(u + k) * CW_WORDS + 4);
         a[k][0] = lo.x; a[k][1] = lo.y; a[k][2] = lo.z; a[k][3] = lo.w;
         a[k][4] = hi.x; a[k][5] = hi.y; a[k][6] = hi.z; a[k][7] = hi.w;
     }
 #else
-    for (int k = 0; k < 3; ++k) {
-        const uint32_t uu = RING_UNITS ? ((u + k) & (RING_UNITS - 1u)) : (u + k);
-        for (int c = 0; c < CW_WORDS; ++c) a[k][c] = cw[(size_t)uu * CW_WORDS + c];
-    }
+    for (int k = 0; k < 3; ++k) for (int c = 0; c < CW_WORDS; ++c) a[k][c] = cw[(size_t)(u + k) * CW_WORDS + c];
 #endif
     uint64_t v[CW_WORDS];
 #pragma unroll
@@ -134,21 +128,25 @@ SID_HD Win64 load_window(const uint32_t* cw, uint32_t pos) {
 
 SID_HD uint64_t low_bits64(uint32_t n) { return n >= 64 ? ~0ull : ((1ull << n) - 1ull); }      // bits [0, n)
 
+// What the header of a line leaves for the bases field.
+struct WinHeader {
+    uint32_t l0;            // bit index (byte offset from region_off) of the line's first byte
+    uint32_t q4;            // offset of the fourth separator from there: the bases field starts at l0 + q4 + 1
+    bool ref_base, ref_p1, ref_p2;     // the reference character is A/C/G/T (any case) and its two telling bit planes
+};
+
 // `s`: staged text (4-byte aligned, byte 0 of the class arrays is s[region_off]); `cw`: class words (array of
 // structures) of n_bits classified bytes followed by CW_PAD_UNITS zero units; `nlw`: the '\n' words (same padding).
 // WANT_POS: also convert the position (the row writer copies its digits from the text instead).
-// RING_UNITS != 0 (the streaming tokenizer, k_tok3.cuh): text and class arrays are rings of RING_UNITS * 32 bytes /
-// RING_UNITS units that hold the WHOLE line (its '\n' included, which ends every scan below); region_off is 0,
-// line_off the ring offset of the line's first byte, n_bits unused; every index wraps.
-template <bool WANT_POS, uint32_t RING_UNITS = 0>
-SID_HD bool parse_line_win(const uint8_t* s, uint32_t region_off, const uint32_t* cw, const uint32_t* nlw, uint32_t n_bits,
-                           uint32_t line_off, WinLine& o) {
-    constexpr uint32_t RB = RING_UNITS ? RING_UNITS * 32u - 1u : 0xFFFFFFFFu;     // byte index mask
-    constexpr uint32_t RU = RING_UNITS ? RING_UNITS - 1u : 0xFFFFFFFFu;           // unit index mask
+// Header of the line at line_off (parsePileupLine, pileup.cpp:13-40): separators, position, reference character.
+// `w` receives the class window of the line's first 64 bytes.  Returns false when the line leaves the fast grammar.
+template <bool WANT_POS>
+SID_HD bool win_header(const uint8_t* s, uint32_t region_off, const uint32_t* cw, const uint32_t* nlw, uint32_t n_bits,
+                       uint32_t line_off, WinLine& o, WinHeader& hd, Win64& w) {
     const uint32_t ls = line_off - region_off;                      // bit index of the line's first byte
-    bool ok = RING_UNITS ? true : (line_off >= region_off && ls + 64 <= n_bits && line_off >= 12);
+    bool ok = line_off >= region_off && ls + 64 <= n_bits && line_off >= 12;
     const uint32_t l0 = ok ? ls : 0, h0 = ok ? line_off : region_off + 16;
-    Win64 w = load_window<RING_UNITS>(cw, l0);
+    w = load_window(cw, l0);
     // ---- header: the bytes <= 0x20 among the first 32 locate the four separators (pileup.cpp:17-36)
     const uint32_t sepmask = (uint32_t)w.term;
     ok = ok && pop_count(sepmask) >= 4;
@@ -164,7 +162,7 @@ SID_HD bool parse_line_win(const uint8_t* s, uint32_t region_off, const uint32_t
     {
         // none of the four is a line end (fewer than five columns: the reference throws, pileup.cpp:22-40); other
         // control bytes are the caller's business (UnitClasses::bad)
-        const uint32_t nl32 = funnel_r(nlw[(l0 >> 5) & RU], nlw[((l0 >> 5) + 1) & RU], l0 & 31);
+        const uint32_t nl32 = funnel_r(nlw[l0 >> 5], nlw[(l0 >> 5) + 1], l0 & 31);
         ok = ok && (nl32 & (0xFFFFFFFFu >> (31 - q4))) == 0;
         // the position is all digits
         const uint32_t dm = (0xFFFFFFFFu >> (32 - q2)) & ~(0xFFFFFFFFu >> (31 - q1));       // bits (q1, q2)
@@ -174,20 +172,23 @@ SID_HD bool parse_line_win(const uint8_t* s, uint32_t region_off, const uint32_t
     // characters of the bases grammar -> byte-wise path
     const uint32_t rbit = q2 + 1;
     ok = ok && (((uint32_t)(w.caret | w.pm) >> rbit) & 1u) == 0;
-    const bool ref_base = (((uint32_t)w.base >> rbit) & 1u) != 0;
-    const bool ref_p1 = (((uint32_t)w.p1 >> rbit) & 1u) != 0, ref_p2 = (((uint32_t)w.p2 >> rbit) & 1u) != 0;
+    hd.l0 = l0;
+    hd.q4 = q4;
+    hd.ref_base = (((uint32_t)w.base >> rbit) & 1u) != 0;
+    hd.ref_p1 = (((uint32_t)w.p1 >> rbit) & 1u) != 0;
+    hd.ref_p2 = (((uint32_t)w.p2 >> rbit) & 1u) != 0;
     o.name_len = q1;
     o.hdr_len = q2;
     o.pos = 0;
-    o.pos_canonical = s[(h0 + q1 + 1) & RB] != (uint8_t)'0' || nd == 1;
+    o.pos_canonical = s[h0 + q1 + 1] != (uint8_t)'0' || nd == 1;
     if (WANT_POS) {
         // the (up to) eight characters before the second separator, leading ones forced to '0' (digits checked above)
         const uint32_t* sw = reinterpret_cast<const uint32_t*>(s);
         const uint32_t e = h0 + q2;
         const uint32_t ndd = ok ? nd : 1;
-        const uint32_t pw = (e - 8) >> 2;
+        const uint32_t* pw = sw + ((e - 8) >> 2);
         const uint32_t ps = ((e - 8) & 3) * 8;
-        const uint32_t w0 = sw[pw & (RB >> 2)], w1 = sw[(pw + 1) & (RB >> 2)], w2 = sw[(pw + 2) & (RB >> 2)];
+        const uint32_t w0 = pw[0], w1 = pw[1], w2 = pw[2];
         uint32_t lo = funnel_r(w0, w1, ps), hi = funnel_r(w1, w2, ps);
         const uint32_t zero = ndd >= 8 ? 0u : 8u - ndd;
         if (zero >= 4) {
@@ -202,14 +203,35 @@ SID_HD bool parse_line_win(const uint8_t* s, uint32_t region_off, const uint32_t
         const uint32_t tl = xl * 10u + (xl >> 8), th = xh * 10u + (xh >> 8);
         const uint32_t vl = (tl & 0xFFu) * 100u + ((tl >> 16) & 0xFFu), vh = (th & 0xFFu) * 100u + ((th >> 16) & 0xFFu);
         uint32_t acc = vl * 10000u + vh;
-        if (ndd == 9) acc += ((uint32_t)s[(e - 9) & RB] - (uint32_t)'0') * 100000000u;
+        if (ndd == 9) acc += ((uint32_t)s[e - 9] - (uint32_t)'0') * 100000000u;
         o.pos = (int32_t)acc;
     }
+    return ok;
+}
+
+// The counts of a bases field as the packed profile; '.' and ',' stand for the reference base (pileup.cpp:78-83).
+SID_HD uint64_t win_profile(uint32_t cn, uint32_t c1, uint32_t c2, uint32_t c12, uint32_t cd, const WinHeader& hd) {
+    if (hd.ref_base) {
+        cn += cd;
+        c1 += hd.ref_p1 ? cd : 0u;
+        c2 += hd.ref_p2 ? cd : 0u;
+        c12 += (hd.ref_p1 && hd.ref_p2) ? cd : 0u;
+    }
+    return pack_profile(cn - c1 - c2 + c12, c1 - c12, c12, c2 - c12);
+}
+
+// One line per lane: header, then the bases field window by window (a loop of ceil(field / 64) steps).
+template <bool WANT_POS>
+SID_HD bool parse_line_win(const uint8_t* s, uint32_t region_off, const uint32_t* cw, const uint32_t* nlw, uint32_t n_bits,
+                           uint32_t line_off, WinLine& o) {
+    WinHeader hd;
+    Win64 w;
+    bool ok = win_header<WANT_POS>(s, region_off, cw, nlw, n_bits, line_off, o, hd, w);
     SID_SYNCWARP();
     // ---- bases field: 64 bytes per window; the first window is the one that holds the header
     uint32_t cn = 0, c1 = 0, c2 = 0, c12 = 0, cd = 0;
-    uint32_t cur = l0;                          // bit index of the window
-    uint64_t below = (2ull << q4) - 1ull;       // bits of the window that precede the field
+    uint32_t cur = hd.l0;                       // bit index of the window
+    uint64_t below = (2ull << hd.q4) - 1ull;    // bits of the window that precede the field
     uint32_t skip = 0;                          // bytes at the start of the next window still covered by a '^' or an indel
     bool running = ok;
     while (running) {
@@ -246,9 +268,9 @@ SID_HD bool parse_line_win(const uint8_t* s, uint32_t region_off, const uint32_t
             }
             if (ndig == 0) continue;                            // a sign without a digit is ignored (pileup.cpp:131-133)
             uint32_t n = 0;
-            const uint32_t q = region_off + cur + p + 1;
+            const uint8_t* q = s + region_off + cur + p + 1;
             for (uint32_t i = 0; i < ndig; ++i)
-                if (n < (1u << 26)) n = n * 10 + ((uint32_t)s[(q + i) & RB] - (uint32_t)'0');
+                if (n < (1u << 26)) n = n * 10 + ((uint32_t)q[i] - (uint32_t)'0');
             const uint64_t to = (uint64_t)p + 1 + ndig + n;     // first byte after the skipped ones (pileup.cpp:144)
             live_all &= ~(low_bits64(to >= 64 ? 64u : (uint32_t)to) & ~low_bits64(p + 1));
             if (to > 64 && !last) skip = (uint32_t)(to - 64 > (1u << 27) ? (1u << 27) : to - 64);
@@ -265,26 +287,142 @@ SID_HD bool parse_line_win(const uint8_t* s, uint32_t region_off, const uint32_t
         } else {
             cur = next;
             below = 0;
-            if (!RING_UNITS && cur + 64 > n_bits) { ok = false; running = false; }        // ran out of classified bytes
-            else w = load_window<RING_UNITS>(cw, cur);
+            if (cur + 64 > n_bits) { ok = false; running = false; }        // ran out of classified bytes
+            else w = load_window(cw, cur);
         }
     }
     SID_SYNCWARP();
-    if (ref_base) {                             // '.' and ',' stand for the reference base
-        cn += cd;
-        c1 += ref_p1 ? cd : 0u;
-        c2 += ref_p2 ? cd : 0u;
-        c12 += (ref_p1 && ref_p2) ? cd : 0u;
-    }
-    o.profile = pack_profile(cn - c1 - c2 + c12, c1 - c12, c12, c2 - c12);
+    o.profile = win_profile(cn, c1, c2, c12, cd, hd);
     o.status = LINE_OK;
     return ok;
+}
+
+// ---- long lines: one WINDOW per lane ----------------------------------------------------------------------------
+// A deep pileup (depth 500: 1.2 KB per line) leaves the loop above on three or four lanes for nineteen steps.  The
+// kernel then turns the field into windows of 64 bytes on a fixed grid from the field's first byte and gives every
+// window its own lane (win_window), all lines of the slice at once.  What a window needs from its predecessor is one
+// number: how many of its first bytes a '^' or an indel that began earlier still covers (skip_in).  Lanes start with
+// skip_in = 0, compare with what the lane before them reports (skip_out) and redo their window when it differs; a
+// lane is final one round after its predecessor, in practice after one or two rounds.
+
+// First byte <= 0x20 at or after bit `from` (the end of the bases field that starts there); 0xFFFFFFFF when the
+// classified bytes end first.
+// term_groups (optional): bit i of word g says that unit 32 g + i holds such a byte (stage 1 has them as ballots);
+// with it the search skips 32 units at a time.
+SID_HD uint32_t win_field_end(const uint32_t* cw, uint32_t n_bits, uint32_t from, const uint32_t* term_groups = nullptr) {
+    uint32_t u = from >> 5;
+    uint32_t t = cw[(size_t)u * CW_WORDS + CW_TERM] & (0xFFFFFFFFu << (from & 31));
+    const uint32_t n_units = n_bits >> 5;
+    if (t == 0 && term_groups) {
+        ++u;
+        if (u >= n_units) return 0xFFFFFFFFu;
+        uint32_t g = u >> 5;
+        uint32_t m = term_groups[g] & (0xFFFFFFFFu << (u & 31));
+        const uint32_t n_groups = (n_units + 31) >> 5;
+        while (m == 0) {
+            if (++g >= n_groups) return 0xFFFFFFFFu;
+            m = term_groups[g];
+        }
+        u = g * 32 + first_bit(m);
+        if (u >= n_units) return 0xFFFFFFFFu;
+        t = cw[(size_t)u * CW_WORDS + CW_TERM];
+    }
+    while (t == 0) {
+        if (++u >= n_units) return 0xFFFFFFFFu;
+        t = cw[(size_t)u * CW_WORDS + CW_TERM];
+    }
+    return u * 32 + first_bit(t);
+}
+
+struct WinPart {
+    uint32_t cn, c1, c2, c12, cd;   // counted bases of the window, by the bit planes that tell them apart, and '.'/','
+    uint32_t skip_out;              // bytes at the start of the next window that this one's '^' / indels cover
+    bool ok;
+};
+
+// The window [pos, pos + 64) of a bases field that ends at bit `end` (> pos); skip_in: bytes at its start covered
+// from before.  Numbers that run past the window's end are read from the text.
+SID_HD WinPart win_window_of(const Win64& w, bool in_reach, const uint8_t* s, uint32_t region_off, uint32_t pos, uint32_t end, uint32_t skip_in) {
+    WinPart r;
+    r.cn = r.c1 = r.c2 = r.c12 = r.cd = 0;
+    r.skip_out = 0;
+    r.ok = in_reach;
+    const uint32_t len = end - pos < 64 ? end - pos : 64;
+    uint64_t live_all = low_bits64(len);
+    if (skip_in) {
+        live_all &= ~low_bits64(skip_in < 64 ? skip_in : 64);
+        if (skip_in > 64) r.skip_out = skip_in - 64;
+    }
+    uint64_t pmw = w.pm, live;
+    for (;;) {
+        const uint64_t car = w.caret & live_all;                // pileup.cpp:125-127
+        if (car & (car << 1)) r.ok = false;                     // "^^": the byte-wise path keeps the parity
+        live = live_all & ~(car << 1);
+        const uint64_t pv = pmw & live;
+        if (!pv || !r.ok) break;
+        const uint32_t p = (uint32_t)ctz64(pv);                 // '+' / '-' (pileup.cpp:128-147)
+        pmw &= ~(1ull << p);
+        const uint64_t dg = p == 63 ? 0ull : (w.digit >> (p + 1));
+        uint32_t ndig = dg == ~0ull ? 64u : (uint32_t)ctz64(~dg);
+        if (p + 1 + ndig >= 64) {
+            // the digits reach the end of the window: the number continues in the text (if the field does)
+            ndig = 63 - p;
+            uint32_t extra = 0;
+            while (pos + 64 + extra < end && extra < 12 && (uint32_t)s[region_off + pos + 64 + extra] - (uint32_t)'0' <= 9u) ++extra;
+            ndig += extra;
+        }
+        if (ndig == 0) continue;                                // a sign without a digit is ignored (pileup.cpp:131-133)
+        if (ndig > 10) { r.ok = false; break; }
+        uint32_t n = 0;
+        const uint8_t* q = s + region_off + pos + p + 1;
+        for (uint32_t i = 0; i < ndig; ++i)
+            if (n < (1u << 26)) n = n * 10 + ((uint32_t)q[i] - (uint32_t)'0');
+        const uint64_t to = (uint64_t)p + 1 + ndig + n;         // first byte after the skipped ones (pileup.cpp:144)
+        live_all &= ~(low_bits64(to >= 64 ? 64u : (uint32_t)to) & ~low_bits64(p + 1));
+        if (to > 64) {
+            const uint32_t over = (uint32_t)(to - 64 > (1u << 27) ? (1u << 27) : to - 64);
+            if (over > r.skip_out) r.skip_out = over;
+        }
+    }
+    if (((w.caret & live_all) >> 63) && r.skip_out == 0) r.skip_out = 1;       // the hidden byte opens the next window
+    const uint64_t b = w.base & live;
+    r.cn = popc64(b);
+    r.c1 = popc64(b & w.p1);
+    r.c2 = popc64(b & w.p2);
+    r.c12 = popc64(b & w.p1 & w.p2);
+    r.cd = popc64(w.dot & live);
+    return r;
+}
+
+SID_HD WinPart win_window(const uint8_t* s, uint32_t region_off, const uint32_t* cw, uint32_t n_bits, uint32_t pos, uint32_t end,
+                          uint32_t skip_in) {
+    const bool in_reach = pos + 64 <= n_bits;
+    const Win64 w = load_window(cw, in_reach ? pos : 0);
+    return win_window_of(w, in_reach, s, region_off, pos, end, skip_in);
+}
+
+// The result for skip_in = s from the result r0 for skip_in = 0 of the same window, when the first s bytes hold neither
+// a '^' nor a sign (then they only ever contributed counts, and nothing after them changes).  Returns false when the
+// window has to be evaluated again.
+SID_HD bool win_window_patch(const Win64& w, uint32_t pos, uint32_t end, const WinPart& r0, uint32_t s, WinPart& r) {
+    const uint32_t len = end - pos < 64 ? end - pos : 64;
+    if (s >= len) return false;
+    const uint64_t low = low_bits64(s);
+    if ((w.caret | w.pm) & low) return false;
+    const uint64_t b = w.base & low;
+    r = r0;
+    r.cn -= popc64(b);
+    r.c1 -= popc64(b & w.p1);
+    r.c2 -= popc64(b & w.p2);
+    r.c12 -= popc64(b & w.p1 & w.p2);
+    r.cd -= popc64(w.dot & low);
+    return true;
 }
 
 #if !defined(__CUDACC__)
 // Host check: classifies the whole line (plus slack) like the kernel's stage 1, then runs stage 2.  A line with a
 // control byte (UnitClasses::bad) is refused here as the kernel refuses its whole slice.
-template <bool WANT_POS>
+template <bool WANT_POS, bool COOP = false>
 inline bool parse_line_win_host(const uint8_t* text, uint64_t len, uint64_t p, WinLine& o) {
     const int64_t first = (int64_t)(p & ~(uint64_t)31) - 32;
     uint64_t end = p;
@@ -316,7 +454,32 @@ inline bool parse_line_win_host(const uint8_t* text, uint64_t len, uint64_t p, W
         nlw[u] = 0;
     }
     if (bad) return false;
-    return parse_line_win<WANT_POS>(scratch, 0, cw, nlw, units * 32, (uint32_t)((int64_t)p - first), o);
+    if (!COOP) return parse_line_win<WANT_POS>(scratch, 0, cw, nlw, units * 32, (uint32_t)((int64_t)p - first), o);
+    // the window-per-lane form, windows in order: skip_in of a window is the final skip_out of the one before it,
+    // which is the fixed point the lanes of the kernel converge to
+    WinHeader hd;
+    Win64 w0;
+    if (!win_header<WANT_POS>(scratch, 0, cw, nlw, units * 32, (uint32_t)((int64_t)p - first), o, hd, w0)) return false;
+    const uint32_t a = hd.l0 + hd.q4 + 1;
+    static thread_local uint32_t groups[((1u << 15) + 8) / 32 + 2];
+    for (uint32_t g = 0; g < (units + 31) / 32; ++g) {
+        groups[g] = 0;
+        for (uint32_t i = 0; i < 32 && g * 32 + i < units; ++i)
+            if (cw[(size_t)(g * 32 + i) * CW_WORDS + CW_TERM]) groups[g] |= 1u << i;
+    }
+    const uint32_t b = win_field_end(cw, units * 32, a, groups);
+    if (b != win_field_end(cw, units * 32, a)) return false;            // the two searches agree (the caller counts this as a failure)
+    if (b == 0xFFFFFFFFu || b <= a) return false;
+    uint32_t cn = 0, c1 = 0, c2 = 0, c12 = 0, cd = 0, skip = 0;
+    for (uint32_t pos = a; pos < b; pos += 64) {
+        const WinPart r = win_window(scratch, 0, cw, units * 32, pos, b, skip);
+        if (!r.ok) return false;
+        cn += r.cn; c1 += r.c1; c2 += r.c2; c12 += r.c12; cd += r.cd;
+        skip = r.skip_out;
+    }
+    o.profile = win_profile(cn, c1, c2, c12, cd, hd);
+    o.status = LINE_OK;
+    return true;
 }
 #endif
 

@@ -40,23 +40,21 @@ struct RowSrc {
 
 // Phase A.  `text`: staged text; `stage`: the warp's staging buffer (both 4-byte aligned); d: offset of the row in
 // it.  hdr_words / sfx_words: warp-uniform upper bounds of the words any lane needs (the loops leave early together).
-// Returns the shared first word for phase B.  WMASK: mask applied to every word index of `text` (a ring of WMASK + 1
-// words in the streaming tokenizer; all ones for a linear buffer).
-template <uint32_t WMASK = 0xFFFFFFFFu>
+// Returns the shared first word for phase B.
 SID_HD uint32_t row_phase_a(const uint8_t* text, uint8_t* stage, uint32_t d, const RowSrc& r, uint32_t hdr_words, uint32_t sfx_words) {
     const uint32_t* tw = reinterpret_cast<const uint32_t*>(text);
     uint32_t* sw = reinterpret_cast<uint32_t*>(stage);
     const uint32_t a = d & 3u, dw = d >> 2;
     // ---- header: dest word q holds the text bytes [line_off - a + 4q, +4)
     const uint32_t base = r.line_off - a;
-    const uint32_t tp = base >> 2;
+    const uint32_t* tp = tw + (base >> 2);
     const uint32_t sh = (base & 3u) * 8u;
     const uint32_t nh = (a + r.hdr_len + 3u) >> 2;          // words that hold header bytes
-    uint32_t prev = tw[tp & WMASK], first = 0;
+    uint32_t prev = tp[0], first = 0;
 #pragma unroll
     for (int q = 0; q < ROW_HDR_WORDS; ++q) {
         if ((uint32_t)q >= hdr_words) break;
-        const uint32_t next = tw[(tp + q + 1) & WMASK];
+        const uint32_t next = tp[q + 1];
         const uint32_t v = funnel_r(prev, next, sh);
         prev = next;
         if (q == 0) first = v;
@@ -65,7 +63,7 @@ SID_HD uint32_t row_phase_a(const uint8_t* text, uint8_t* stage, uint32_t d, con
     // ---- suffix, from byte d + hdr_len on; the word at the junction takes its low bytes from the end of the header
     const uint32_t ds = d + r.hdr_len, a2 = ds & 3u, dw2 = ds >> 2;
     const uint32_t xb = r.line_off + r.hdr_len - 4u;
-    const uint32_t x = funnel_r(tw[(xb >> 2) & WMASK], tw[((xb >> 2) + 1) & WMASK], (xb & 3u) * 8u);   // header bytes [hdr_len - 4, hdr_len)
+    const uint32_t x = funnel_r(tw[xb >> 2], tw[(xb >> 2) + 1], (xb & 3u) * 8u);          // header bytes [hdr_len - 4, hdr_len)
     const uint32_t sh2 = 8u * (4u - a2);
     const uint32_t ns = (a2 + r.sfx_len + 3u) >> 2;
     uint32_t lo = x;

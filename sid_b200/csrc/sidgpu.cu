@@ -3,6 +3,7 @@
 // parsing, profile building, likelihoods, p-values, histogramming and CSV formatting run in the
 // kernels of k_*.cuh; there is no CPU implementation of any of them in this library.
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 
 #include <algorithm>
 #include <cmath>
@@ -20,6 +21,7 @@
 #include "k_quality.cuh"
 #include "k_tokenize.cuh"
 #include "k_tok2.cuh"
+#include "k_reads.cuh"
 #include "nelder_mead.hpp"
 
 using namespace sid;
@@ -115,6 +117,8 @@ struct sidgpu_ctx {
     bool hist_valid = false;
     bool global_hist = false;        // the histogram is the merged one of all shards (sidgpu_set_global_histogram)
     DevBuf g_e2u;
+    TableView g_tab {};               // counting table of the merged histogram, kept from call to call
+    int g_log2 = 0;
     DevBuf partials;
     DevBuf quality_lut;
 
@@ -210,6 +214,12 @@ int check_launch(sidgpu_ctx* ctx, const char* what) {
     ctx->launches++;
     return SIDGPU_OK;
 }
+
+// NVTX range around an ABI call: shows up as a named span in Nsight Systems timelines
+struct Range {
+    explicit Range(const char* name) { nvtxRangePushA(name); }
+    ~Range() { nvtxRangePop(); }
+};
 
 enum { PROF_TOKENIZE = 0, PROF_CLASSIFY = 1, PROF_CSV = 2, PROF_ORDER = 3, PROF_FIT = 4, PROF_HIST = 5, PROF_QUALITY = 6 };
 
@@ -472,16 +482,29 @@ int run_tokenizer(sidgpu_ctx* ctx, const char* d_text, size_t text_len, size_t r
             q.use_table = p.use_table; q.want_qual = p.want_qual; q.bytewise = (want_qual && strict_qual) ? 1 : 0;
             q.slice_bytes = slice; q.text_stride = p.text_stride; q.tail_bytes = p.tail_bytes; q.lines_cap = p.lines_cap;
             q.ext_bytes = ext; q.units_cap = tok2_units(slice, ext) + CW_PAD_UNITS;
+            static const int deep_knob = getenv("SIDGPU_DEEP_LINES") ? atoi(getenv("SIDGPU_DEEP_LINES")) : -1;     // A/B knob: 0 off, 1 on
+            const bool deep = deep_knob >= 0 ? deep_knob != 0 : ctx->avg_line_bytes >= 256.0;
             int s2 = 0, s1 = 0;
-            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s2, k_tok2<false, 2>, TOK_THREADS, tok2_dyn_smem(slice, ext, 2, false)) != cudaSuccess || s2 < 1) s2 = 1;
-            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s1, k_tok2<false, 1>, TOK_THREADS, tok2_dyn_smem(slice, ext, 1, false)) != cudaSuccess || s1 < 1) s1 = 1;
+            if (deep) {
+                // long lines: the instantiation whose stage 2 gives every 64-byte window of a bases field its own lane
+                if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s2, k_tok2<false, 2, true>, TOK_THREADS, tok2_dyn_smem(slice, ext, 2, false)) != cudaSuccess || s2 < 1) s2 = 1;
+                if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s1, k_tok2<false, 1, true>, TOK_THREADS, tok2_dyn_smem(slice, ext, 1, false)) != cudaSuccess || s1 < 1) s1 = 1;
+            } else {
+                if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s2, k_tok2<false, 2>, TOK_THREADS, tok2_dyn_smem(slice, ext, 2, false)) != cudaSuccess || s2 < 1) s2 = 1;
+                if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s1, k_tok2<false, 1>, TOK_THREADS, tok2_dyn_smem(slice, ext, 1, false)) != cudaSuccess || s1 < 1) s1 = 1;
+            }
             const int stages = force_stages == 1 || force_stages == 2 ? force_stages : (s1 > s2 ? 1 : 2);
             const unsigned grid = (unsigned)std::min<uint64_t>(n_tiles, (uint64_t)ctx->sm_count * (stages == 1 ? s1 : s2));
             const uint32_t dyn = tok2_dyn_smem(slice, ext, (uint32_t)stages, false);
             {
                 ProfScope prof(ctx, PROF_TOKENIZE);
-                if (stages == 1) k_tok2<false, 1><<<grid, TOK_THREADS, dyn, ctx->stream>>>(q);
-                else k_tok2<false, 2><<<grid, TOK_THREADS, dyn, ctx->stream>>>(q);
+                if (deep) {
+                    if (stages == 1) k_tok2<false, 1, true><<<grid, TOK_THREADS, dyn, ctx->stream>>>(q);
+                    else k_tok2<false, 2, true><<<grid, TOK_THREADS, dyn, ctx->stream>>>(q);
+                } else {
+                    if (stages == 1) k_tok2<false, 1><<<grid, TOK_THREADS, dyn, ctx->stream>>>(q);
+                    else k_tok2<false, 2><<<grid, TOK_THREADS, dyn, ctx->stream>>>(q);
+                }
                 TRY(check_launch(ctx, "k_tok2"));
             }
         } else {
@@ -946,6 +969,73 @@ const char* sidgpu_last_error(const sidgpu_ctx* ctx) { return ctx ? ctx->err.c_s
 
 uint64_t sidgpu_launch_count(const sidgpu_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
+// ---- the per-read side of pileup.hpp and the per-profile side of lynch.hpp / stats.hpp (k_reads.cuh)
+int sidgpu_qualities(sidgpu_ctx* ctx, const char* d_quals, size_t n, uint8_t* d_out, uint64_t* n_out) {
+    if (!ctx || !n_out || (n && (!d_quals || !d_out))) return SIDGPU_EINVAL;
+    CK(cudaSetDevice(ctx->device));
+    *n_out = 0;
+    if (n == 0) return SIDGPU_OK;
+    k_qualities<<<1, 256, 0, ctx->stream>>>((const uint8_t*)d_quals, n, d_out, ctl_field(ctx, &Control::csv_bytes));
+    TRY(check_launch(ctx, "k_qualities"));
+    TRY(sync_ctl(ctx));
+    *n_out = ctx->h_ctl->csv_bytes;
+    return SIDGPU_OK;
+}
+
+int sidgpu_read_counts(sidgpu_ctx* ctx, const char* d_text, size_t text_len, const uint64_t* d_line_off, uint64_t n_lines, int want_baseq,
+                       int want_mapq, uint32_t* d_n_bases, uint32_t* d_n_bq, uint32_t* d_n_mq) {
+    if (!ctx || (n_lines && (!d_text || !d_line_off || !d_n_bases || !d_n_bq || !d_n_mq))) return SIDGPU_EINVAL;
+    CK(cudaSetDevice(ctx->device));
+    if (n_lines == 0) return SIDGPU_OK;
+    CK(cudaMemsetAsync(ctl_field(ctx, &Control::error), 0xFF, sizeof(unsigned long long), ctx->stream));
+    k_read_counts<<<(unsigned)((n_lines + 127) / 128), 128, 0, ctx->stream>>>((const uint8_t*)d_text, text_len, d_line_off, n_lines, want_baseq,
+                                                                              want_mapq, d_n_bases, d_n_bq, d_n_mq, ctl_field(ctx, &Control::error));
+    TRY(check_launch(ctx, "k_read_counts"));
+    TRY(sync_ctl(ctx));
+    if (ctx->h_ctl->error != ~0ull) {
+        const int st = (int)(ctx->h_ctl->error & 7);
+        return ctx->fail(st == LINE_MISSING_MAPQ ? SIDGPU_EMISSING_MAPQ : SIDGPU_EMALFORMED, "%s (line starting at byte %llu)", status_text(st),
+                         ctx->h_ctl->error >> 3);
+    }
+    return SIDGPU_OK;
+}
+
+int sidgpu_read_fill(sidgpu_ctx* ctx, const char* d_text, size_t text_len, const uint64_t* d_line_off, uint64_t n_lines,
+                     const uint64_t* d_base_off, const uint64_t* d_bq_off, const uint64_t* d_mq_off, char* d_bases, uint8_t* d_strands,
+                     uint8_t* d_bq, uint8_t* d_mq) {
+    if (!ctx || (n_lines && (!d_text || !d_line_off))) return SIDGPU_EINVAL;
+    if (((d_bases || d_strands) && !d_base_off) || (d_bq && !d_bq_off) || (d_mq && !d_mq_off)) return SIDGPU_EINVAL;
+    CK(cudaSetDevice(ctx->device));
+    if (n_lines == 0) return SIDGPU_OK;
+    k_read_fill<<<(unsigned)((n_lines + 127) / 128), 128, 0, ctx->stream>>>((const uint8_t*)d_text, text_len, d_line_off, n_lines, d_base_off,
+                                                                            d_bq_off, d_mq_off, d_bases, d_strands, d_bq, d_mq);
+    TRY(check_launch(ctx, "k_read_fill"));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return SIDGPU_OK;
+}
+
+int sidgpu_profile_loglik(sidgpu_ctx* ctx, const uint64_t* d_profiles, uint64_t n, const double nd[4], double eps, double* d_log_hom,
+                          double* d_log_het) {
+    if (!ctx || !nd || (n && (!d_profiles || !d_log_hom || !d_log_het))) return SIDGPU_EINVAL;
+    CK(cudaSetDevice(ctx->device));
+    if (n == 0) return SIDGPU_OK;
+    k_profile_loglik<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>((const unsigned long long*)d_profiles, n, host_lynch_consts(nd, eps),
+                                                                           d_log_hom, d_log_het);
+    TRY(check_launch(ctx, "k_profile_loglik"));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return SIDGPU_OK;
+}
+
+int sidgpu_lr_test(sidgpu_ctx* ctx, const double* d_log_h0, const double* d_log_h1, uint64_t n, double* d_p) {
+    if (!ctx || (n && (!d_log_h0 || !d_log_h1 || !d_p))) return SIDGPU_EINVAL;
+    CK(cudaSetDevice(ctx->device));
+    if (n == 0) return SIDGPU_OK;
+    k_lr_test<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(d_log_h0, d_log_h1, n, d_p);
+    TRY(check_launch(ctx, "k_lr_test"));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return SIDGPU_OK;
+}
+
 int sidgpu_create(const sidgpu_config* cfg, sidgpu_ctx** out) {
     if (!out) return SIDGPU_EINVAL;
     *out = nullptr;
@@ -1027,6 +1117,8 @@ int sidgpu_create(const sidgpu_config* cfg, sidgpu_ctx** out) {
         (e = cudaFuncSetAttribute(k_tokenize<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tok_dyn_smem(SLICE_MAX, 2016))) != cudaSuccess ||
         (e = cudaFuncSetAttribute(k_tok2<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tok2_dyn_smem(SLICE_MAX, 2016, 1, false))) != cudaSuccess ||
         (e = cudaFuncSetAttribute(k_tok2<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::min<uint32_t>(227u << 10, tok2_dyn_smem(SLICE_MAX, 2016, 2, false)))) != cudaSuccess ||
+        (e = cudaFuncSetAttribute(k_tok2<false, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tok2_dyn_smem(SLICE_MAX, 2016, 1, false))) != cudaSuccess ||
+        (e = cudaFuncSetAttribute(k_tok2<false, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::min<uint32_t>(227u << 10, tok2_dyn_smem(SLICE_MAX, 2016, 2, false)))) != cudaSuccess ||
         (e = cudaFuncSetAttribute(k_tok2<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tok2_dyn_smem(SLICE_MAX, 2016, 1, true))) != cudaSuccess ||
         (e = cudaFuncSetAttribute(k_tok2<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::min<uint32_t>(227u << 10, tok2_dyn_smem(SLICE_MAX, 2016, 2, true)))) != cudaSuccess ||
         (e = cudaFuncSetAttribute(k_rows_compact, cudaFuncAttributeMaxDynamicSharedMemorySize, (RC_THREADS / 32) * RC_STAGE)) != cudaSuccess ||
@@ -1056,6 +1148,7 @@ void sidgpu_destroy(sidgpu_ctx* ctx) {
         if (ctx->hp_ev_out[i]) cudaEventDestroy(ctx->hp_ev_out[i]);
     }
     free_table(ctx->tab);
+    if (ctx->g_log2) free_table(ctx->g_tab);
     cudaFree(ctx->names.slots);
     cudaFree(ctx->names.pool);
     for (DevBuf* b : {&ctx->blk, &ctx->blk_part, &ctx->order, &ctx->v_pos, &ctx->v_slot, &ctx->v_name_ref, &ctx->v_profile, &ctx->v_line_off, &ctx->csv_status, &ctx->pos, &ctx->slot, &ctx->name_ref, &ctx->profile, &ctx->line_off,
@@ -1130,6 +1223,11 @@ int sidgpu_memcpy_d2d(sidgpu_ctx* ctx, void* d_dst, const void* d_src, size_t by
     CK(cudaStreamSynchronize(ctx->stream));
     return SIDGPU_OK;
 }
+int sidgpu_memcpy_d2d_async(sidgpu_ctx* ctx, void* d_dst, const void* d_src, size_t bytes) {
+    if (!ctx) return SIDGPU_EINVAL;
+    CK(cudaMemcpyAsync(d_dst, d_src, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    return SIDGPU_OK;
+}
 int sidgpu_memcpy_d2h(sidgpu_ctx* ctx, void* h_dst, const void* d_src, size_t bytes) {
     if (!ctx) return SIDGPU_EINVAL;
     CK(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1140,6 +1238,7 @@ int sidgpu_memcpy_d2h(sidgpu_ctx* ctx, void* h_dst, const void* d_src, size_t by
 // ------------------------------------------------------------------------------------------- K1
 int sidgpu_tokenize(sidgpu_ctx* ctx, const char* d_text, size_t text_len, size_t range_begin, size_t range_end,
                     int want_qual, sidgpu_sites_view* out) {
+    Range nvtx_range("sidgpu_tokenize");
     if (!ctx || !out) return SIDGPU_EINVAL;
     CK(cudaSetDevice(ctx->device));
     ctx->phase = PHASE_IDLE;
@@ -1207,6 +1306,7 @@ int sidgpu_begin(sidgpu_ctx* ctx, const sidgpu_params* params) {
 }
 
 int sidgpu_feed(sidgpu_ctx* ctx, const char* d_text, size_t text_len, size_t range_begin, size_t range_end, uint64_t* n_sites_out) {
+    Range nvtx_range("sidgpu_feed");
     if (!ctx) return SIDGPU_EINVAL;
     const bool second_pass = ctx->phase == PHASE_FINISHED && ctx->params.method == SIDGPU_METHOD_QUALITY;
     if (ctx->phase != PHASE_FEED && !second_pass) return ctx->fail(SIDGPU_ESTATE, "sidgpu_feed outside a session");
@@ -1239,6 +1339,7 @@ int sidgpu_feed(sidgpu_ctx* ctx, const char* d_text, size_t text_len, size_t ran
 
 int sidgpu_feed_rows(sidgpu_ctx* ctx, const char* d_text, size_t text_len, size_t range_begin, size_t range_end, char* d_out, size_t out_cap,
                      uint64_t* bytes_out, uint64_t* rows_out, uint64_t* n_sites_out) {
+    Range nvtx_range("sidgpu_feed_rows");
     if (!ctx || (out_cap && !d_out)) return SIDGPU_EINVAL;
     if (ctx->phase != PHASE_FEED) return ctx->fail(SIDGPU_ESTATE, "sidgpu_feed_rows outside a session");
     if (!(ctx->streaming && ctx->params.method == SIDGPU_METHOD_LOCAL))
@@ -1260,6 +1361,7 @@ int sidgpu_feed_rows(sidgpu_ctx* ctx, const char* d_text, size_t text_len, size_
 }
 
 int sidgpu_finish(sidgpu_ctx* ctx) {
+    Range nvtx_range("sidgpu_finish");
     if (!ctx) return SIDGPU_EINVAL;
     if (ctx->phase != PHASE_FEED) return ctx->fail(SIDGPU_ESTATE, "sidgpu_finish outside a session");
     CK(cudaSetDevice(ctx->device));
@@ -1307,6 +1409,7 @@ int sidgpu_finish(sidgpu_ctx* ctx) {
 }
 
 int sidgpu_finish_global(sidgpu_ctx* ctx, const uint64_t* h_profiles_sorted, uint64_t n_global) {
+    Range nvtx_range("sidgpu_finish_global");
     if (!ctx || (n_global && !h_profiles_sorted)) return SIDGPU_EINVAL;
     if (ctx->phase != PHASE_FEED) return ctx->fail(SIDGPU_ESTATE, "sidgpu_finish_global outside a session");
     if (ctx->params.method != SIDGPU_METHOD_LIKELIHOOD_RATIO) return ctx->fail(SIDGPU_EINVAL, "sidgpu_finish_global is for likelihood_ratio sessions");
@@ -1351,6 +1454,7 @@ int sidgpu_finish_global(sidgpu_ctx* ctx, const uint64_t* h_profiles_sorted, uin
 }
 
 int sidgpu_emit_csv(sidgpu_ctx* ctx, uint64_t site_begin, uint64_t n_sites, char* d_out, size_t out_cap, uint64_t* bytes_out, uint64_t* rows_out) {
+    Range nvtx_range("sidgpu_emit_csv");
     if (!ctx) return SIDGPU_EINVAL;
     if (ctx->phase == PHASE_IDLE) return ctx->fail(SIDGPU_ESTATE, "sidgpu_emit_csv outside a session");
     if (!ctx->streaming && ctx->phase != PHASE_FINISHED) return ctx->fail(SIDGPU_ESTATE, "this method needs sidgpu_finish before rows can be emitted");
@@ -1407,6 +1511,7 @@ int sidgpu_emit_csv(sidgpu_ctx* ctx, uint64_t site_begin, uint64_t n_sites, char
 }
 
 int sidgpu_emit_records(sidgpu_ctx* ctx, uint64_t site_begin, uint64_t n_sites, uint8_t* d_label, char* d_gt, double* d_hom, double* d_het) {
+    Range nvtx_range("sidgpu_emit_records");
     if (!ctx) return SIDGPU_EINVAL;
     if (ctx->phase == PHASE_IDLE) return ctx->fail(SIDGPU_ESTATE, "sidgpu_emit_records outside a session");
     if (!ctx->streaming && ctx->phase != PHASE_FINISHED) return ctx->fail(SIDGPU_ESTATE, "this method needs sidgpu_finish first");
@@ -1461,6 +1566,7 @@ int sidgpu_names(sidgpu_ctx* ctx, const char** d_names, uint64_t* names_bytes) {
 
 // ------------------------------------------------------------------------------------------- K3/K4
 int sidgpu_histogram(sidgpu_ctx* ctx, uint32_t min_coverage, sidgpu_unique_view* out) {
+    Range nvtx_range("sidgpu_histogram");
     if (!ctx || !out) return SIDGPU_EINVAL;
     CK(cudaSetDevice(ctx->device));
     TRY(build_histogram(ctx, min_coverage));
@@ -1504,15 +1610,26 @@ int sidgpu_count_unique_weighted(sidgpu_ctx* ctx, const uint64_t* d_profiles, co
 }
 
 int sidgpu_set_global_histogram(sidgpu_ctx* ctx, const uint64_t* d_profiles, const uint64_t* d_counts, uint64_t n) {
+    Range nvtx_range("sidgpu_set_global_histogram");
     if (!ctx || (n && (!d_profiles || !d_counts))) return SIDGPU_EINVAL;
     if (ctx->phase != PHASE_FEED || ctx->streaming) return ctx->fail(SIDGPU_ESTATE, "sidgpu_set_global_histogram needs an open session with a genome-wide step");
     if (n > 0x3FFFFFFFull) return ctx->fail(SIDGPU_EINVAL, "too many histogram entries");
     CK(cudaSetDevice(ctx->device));
     int log2cap = 12;
     while (((uint64_t)1 << log2cap) < 2 * n + 2) ++log2cap;
-    TableView g;
     CK(cudaMemsetAsync(ctl_field(ctx, &Control::g_n_entries), 0, 3 * sizeof(unsigned int), ctx->stream));
-    TRY(alloc_table(ctx, log2cap, g, true));
+    if (log2cap > ctx->g_log2) {
+        if (ctx->g_log2) free_table(ctx->g_tab);
+        ctx->g_log2 = 0;
+        TRY(alloc_table(ctx, log2cap, ctx->g_tab, true));
+        ctx->g_log2 = log2cap;
+    } else {
+        // the table of the previous exchange: only the slots that can be probed need clearing
+        log2cap = ctx->g_log2;
+        CK(cudaMemsetAsync(ctx->g_tab.keys, 0xFF, ((size_t)ctx->g_tab.cap + 1) * 8, ctx->stream));
+        CK(cudaMemsetAsync(ctx->g_tab.counts, 0, ((size_t)ctx->g_tab.cap + 1) * 8, ctx->stream));
+    }
+    const TableView& g = ctx->g_tab;
     int rc = SIDGPU_OK;
     if (n) {
         k_insert_profiles<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(g, d_profiles, d_counts, n);
@@ -1532,8 +1649,6 @@ int sidgpu_set_global_histogram(sidgpu_ctx* ctx, const uint64_t* d_profiles, con
             rc = check_launch(ctx, "k_map_entries");
         }
     }
-    cudaStreamSynchronize(ctx->stream);
-    free_table(g);
     if (rc == SIDGPU_OK) ctx->global_hist = true;
     return rc;
 }
@@ -1567,6 +1682,7 @@ int sidgpu_lynch_objective(sidgpu_ctx* ctx, const double nd[4], double pi, doubl
 }
 
 int sidgpu_lynch_fit(sidgpu_ctx* ctx, const double nd[4], sidgpu_fit* out) {
+    Range nvtx_range("sidgpu_lynch_fit");
     if (!ctx || !nd || !out) return SIDGPU_EINVAL;
     CK(cudaSetDevice(ctx->device));
     return run_fit(ctx, nd, out);

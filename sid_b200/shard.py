@@ -120,19 +120,44 @@ def all_gather_histograms(dist, prof, cnt):
     return gp, gc
 
 
-def exchange_histograms(ctx, dist, device):
-    """The collective step of a sharded session with a genome-wide fit: all-gather of the ranks' histograms (NCCL),
-    merge on this rank's device.  Returns the number of gathered entries."""
+_exchange_buffers = {}
+
+
+def exchange_histograms(ctx, dist, device, shared_stream=False):
+    """The collective step of a sharded session with a genome-wide fit: ONE all-gather of the ranks' histograms
+    (NCCL; profiles and counts in one buffer), merged on this rank's device.  Returns the number of gathered entries.
+    shared_stream: the ctx was created on torch's current stream, so its kernels, the copies and the collective are
+    already in order and nothing has to be synchronised in between."""
     import torch
+    world = dist.get_world_size()
     n_u, d_prof, d_cnt = ctx.histogram_device(4)
-    prof = torch.empty(n_u, dtype=torch.int64, device=device)
-    cnt = torch.empty(n_u, dtype=torch.int64, device=device)
-    ctx.copy_d2d(prof.data_ptr(), d_prof, 8 * n_u)          # synchronises the ctx's stream: ordered before the collective
-    ctx.copy_d2d(cnt.data_ptr(), d_cnt, 8 * n_u)
-    gp, gc = all_gather_histograms(dist, prof, cnt)
-    torch.cuda.current_stream().synchronize()               # the collective ran on torch's stream, the merge runs on the ctx's
-    ctx.set_global_histogram(gp.data_ptr(), gc.data_ptr(), gp.numel())
-    return gp.numel()
+    n = torch.tensor([n_u], dtype=torch.int64, device=device)
+    dist.all_reduce(n, op=dist.ReduceOp.MAX)
+    m = max(1, int(n.item()))
+    cap = 1 << (m - 1).bit_length()                         # buffers are kept and only grow
+    key = (str(device), world)
+    buf = _exchange_buffers.get(key)
+    if buf is None or buf[0].numel() < 2 * cap:
+        buf = (torch.zeros(2 * cap, dtype=torch.int64, device=device), torch.empty(world * 2 * cap, dtype=torch.int64, device=device))
+        _exchange_buffers[key] = buf
+    mine, gathered = buf
+    cap = mine.numel() // 2
+    # layout per rank: cap profiles, then cap counts; a count of 0 marks padding
+    mine[cap:].zero_()
+    if not shared_stream:
+        torch.cuda.current_stream().synchronize()           # the clearing ran on torch's stream, the copies run on the ctx's
+    if n_u:
+        ctx.copy_d2d(mine.data_ptr(), d_prof, 8 * n_u, sync=not shared_stream)
+        ctx.copy_d2d(mine.data_ptr() + 8 * cap, d_cnt, 8 * n_u, sync=not shared_stream)
+    dist.all_gather_into_tensor(gathered, mine)
+    if not shared_stream:
+        torch.cuda.current_stream().synchronize()           # the collective ran on torch's stream, the merge runs on the ctx's
+    g = gathered.view(world, 2, cap)
+    prof = g[:, 0, :].contiguous()
+    cnt = g[:, 1, :].contiguous()
+    ctx.set_global_histogram(prof.data_ptr(), cnt.data_ptr(), world * cap)
+    _exchange_buffers[key + ("keep",)] = (prof, cnt)        # alive until the merge kernels have run
+    return world * cap
 
 
 def call_sharded(ctx, d_text, text_len, rank, world, params, dist=None, device=None, per_evaluation_allreduce=False):

@@ -184,6 +184,28 @@ int64_t hc_compare_parsers_win(const uint8_t* text, uint64_t len, uint64_t* n_fa
     return k;
 }
 
+// The window-per-lane form of the window tokenizer (win_header + win_field_end + win_window, what the kernel runs on
+// deep pileups) against the byte-wise one on every line of a text.  Same return convention; *n_fast counts accepted lines.
+int64_t hc_compare_parsers_coop(const uint8_t* text, uint64_t len, uint64_t* n_fast) {
+    FlatSrc src {text, len};
+    int64_t k = 0;
+    uint64_t fast = 0;
+    for (uint64_t p = 0; p < len; ++p) {
+        if (text[p] == '\n' || (p > 0 && text[p - 1] != '\n')) continue;
+        ParsedLine a;
+        parse_line(src, p, false, a);
+        WinLine b;
+        if (parse_line_win_host<true, true>(text, len, p, b)) {
+            ++fast;
+            if (a.status != LINE_OK || b.status != LINE_OK || a.profile != b.profile || a.pos != b.pos || a.chrom_off != 0 ||
+                a.chrom_len != b.name_len) return -(k + 1);
+        }
+        ++k;
+    }
+    if (n_fast) *n_fast = fast;
+    return k;
+}
+
 // The two-phase row assembly of the fused CSV writer, as a warp would run it: phase A of all `n` lanes in the order
 // `order` gives (a warp-wide store with overlapping words has no defined winner), then phase B.  text: staged text
 // (4-byte aligned), line_off/hdr_len/name_len/sfx_len per lane, sfx 48 bytes per lane; rows are laid end to end from

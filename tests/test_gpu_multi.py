@@ -70,3 +70,50 @@ def test_two_shards_equal_one(native, gpu_ctx, method):
             b.free()
         for c in ctxs:
             c.close()
+
+
+@pytest.mark.parametrize("method", ["bayes", "likelihood_ratio"])
+@pytest.mark.parametrize("n_shards", [2, 3, 8])
+def test_merged_histograms_give_the_single_gpu_fit_bit_for_bit(native, gpu_ctx, method, n_shards):
+    """The collective form (sidgpu_set_global_histogram): every shard gets the histograms of all shards (here the
+    "all-gather" is a concatenation), merges them on the device and runs the whole fit there.  The merged histogram is
+    countUniqueProfiles of the whole text, so (pi, eps, iterations) are EQUAL to the single-GPU fit for any number of
+    shards, and the concatenated rows are the single-GPU rows."""
+    import sid_b200
+    text = read("depth30_two_chroms.plp")
+    whole_rows, _, _ = gpu_ctx.call_host(text, sid_b200.Context.make_params(method))
+    whole_fit = gpu_ctx.session_fit()
+    ctxs = [sid_b200.Context() for _ in range(n_shards)]
+    bufs = [c.upload_text(text) for c in ctxs]
+    try:
+        ns = []
+        for c, d, (b, e) in zip(ctxs, bufs, shard.shard_ranges(len(text), n_shards)):
+            c.begin(sid_b200.Context.make_params(method))
+            ns.append(c.feed(d, len(text), b, e))
+        hists = [c.histogram(4)[:2] for c in ctxs]
+        m = max(1, max(len(h[0]) for h in hists))
+        prof = np.zeros(n_shards * m, dtype=np.uint64)
+        cnt = np.zeros(n_shards * m, dtype=np.uint64)                  # padding: count 0, as the all-gather pads
+        for k, (p, c) in enumerate(hists):
+            prof[k * m:k * m + len(p)] = p
+            cnt[k * m:k * m + len(c)] = c
+        rows = b""
+        for c, n in zip(ctxs, ns):
+            dp, dc = c.device_buffer(prof.nbytes).upload(prof), c.device_buffer(cnt.nbytes).upload(cnt)
+            try:
+                c.set_global_histogram(dp.ptr, dc.ptr, len(prof))
+                c.finish()
+            finally:
+                dp.free()
+                dc.free()
+            f = c.session_fit()
+            assert (f["pi"], f["eps"], f["iterations"], f["evaluations"]) == (whole_fit["pi"], whole_fit["eps"], whole_fit["iterations"], whole_fit["evaluations"])
+            assert f["nd"] == whole_fit["nd"] and f["n_unique"] == whole_fit["n_unique"]
+            r, _ = _emit(c, n)
+            rows += r
+        assert rows == whole_rows
+    finally:
+        for b in bufs:
+            b.free()
+        for c in ctxs:
+            c.close()

@@ -393,6 +393,63 @@ def test_window_tokenizer_long_fields_and_indels_at_window_ends(native):
     assert nf.value == k
 
 
+def _deep_indel_lines(seed, n):
+    """Deep lines (hundreds to thousands of bases) dense with read starts, indels of every length and numbers, carets
+    and signs that straddle the 64-byte windows of the window-per-lane tokenizer."""
+    rnd = random.Random(seed)
+    lines = []
+    for k in range(n):
+        parts = []
+        for _ in range(rnd.randrange(20, 900)):
+            r = rnd.random()
+            if r < 0.05:
+                parts.append("^" + chr(33 + rnd.randrange(0, 61)))
+            elif r < 0.09:
+                m = rnd.choice([1, 2, 3, 9, 10, 11, 25, 63, 64, 65, 127, 130])
+                parts.append(rnd.choice("+-") + str(m) + "".join(rnd.choice("ACGTNacgtn") for _ in range(m)))
+            elif r < 0.10:
+                parts.append(rnd.choice(["+", "-", "$", "*", "+0", "-0A", "^+", "^-", "^^x"[:2], "<", ">"]))
+            parts.append(rnd.choice(".,.,.,ACGTacgt"))
+        bases = "".join(parts)
+        lines.append("%s\t%d\t%s\t%d\t%s\t%s" % (rnd.choice(["chr1", "c", "chr12_random"]), rnd.randrange(1, 10 ** 9), rnd.choice("ACGTNacgt"),
+                                                   len(bases), bases, "I" * rnd.randrange(1, 300)))
+    return ("\n".join(lines) + "\n").encode()
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3, 6, 7])
+def test_window_per_lane_tokenizer_equals_scalar_on_adversarial_lines(native, seed):
+    hc = op.hostcheck()
+    hc.hc_compare_parsers_coop.restype = ctypes.c_int64
+    text = _adversarial_text(seed, 20000)
+    nf = ctypes.c_uint64()
+    k = hc.hc_compare_parsers_coop(text, len(text), ctypes.byref(nf))
+    assert k > 0, text.split(b"\n")[-k - 1][:200] if k < 0 else None
+    assert nf.value > k // 100
+
+
+@pytest.mark.parametrize("name", ["depth30.plp", "depth500.plp", "depth5.plp", "quality30.plp", "edge.plp", "depth30_two_chroms.plp"])
+def test_window_per_lane_tokenizer_covers_normal_text(native, name):
+    hc = op.hostcheck()
+    hc.hc_compare_parsers_coop.restype = ctypes.c_int64
+    text = read(name)
+    nf = ctypes.c_uint64()
+    k = hc.hc_compare_parsers_coop(text, len(text), ctypes.byref(nf))
+    assert k > 0, text.split(b"\n")[-k - 1][:200] if k < 0 else None
+    if name != "edge.plp":
+        assert nf.value == k
+
+
+@pytest.mark.parametrize("seed", [11, 12, 13])
+def test_window_per_lane_tokenizer_on_deep_lines(native, seed):
+    hc = op.hostcheck()
+    hc.hc_compare_parsers_coop.restype = ctypes.c_int64
+    text = _deep_indel_lines(seed, 1500)
+    nf = ctypes.c_uint64()
+    k = hc.hc_compare_parsers_coop(text, len(text), ctypes.byref(nf))
+    assert k == text.count(b"\n"), text.split(b"\n")[-k - 1][:300] if k < 0 else None
+    assert nf.value > k * 0.5           # only the lines with "^^" (a third of them here) leave the fast grammar
+
+
 @pytest.mark.parametrize("name", ["quality30.plp", "edge_quality.plp", "depth30.plp", "depth500.plp", "edge.plp"])
 def test_quality_fields_equal_parse_line(native, name):
     """The lean field scan of the quality kernel returns parse_line's offsets, lengths and status."""

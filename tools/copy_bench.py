@@ -120,6 +120,10 @@ def main():
                              if l.startswith(("Model name", "Socket", "NUMA", "CPU(s):", "Hypervisor"))]
         except Exception:
             pass
+        try:
+            host["nvidia_smi_topo"] = subprocess.run(["nvidia-smi", "topo", "-m"], stdout=subprocess.PIPE, text=True, timeout=20).stdout.splitlines()
+        except Exception:
+            pass
         print(json.dumps({"n_gpus": world, "text_mb": args.text_mb, "csv_mb": args.csv_mb, "chunk_mb": args.chunk_mb, "summary": summary,
                           "per_rank": results, "topology": topos, "host": host}))
     if world > 1:
