@@ -1,7 +1,7 @@
 // `sid [flags] input_file` -- the reference's command line (sid.cpp:11-110) over the GPU path.
 // Same flags and defaults (-m METHOD, -r PRIOR, -R, -p LEVEL, -E ERROR, -h), same CSV on stdout,
 // same `# ...` lines on stderr, same exit codes.  Extra long options: --device N, --devices A,B,.. (one
-// position shard per GPU, one shared fit), --chunk-mb N, --read-threads N (parallel preads per chunk, default min(8, cores)),
+// position shard per GPU, one shared fit), --chunk-mb N, --read-threads N (parallel preads per chunk, default min(16, cores)),
 // --het-only (rows labelled het only: the pipeline's `grep ',het,'`, scripts/sid-pipeline/run-sid.sh:16-17;
 // the header line is kept).  With one GPU the input streams through pinned chunks and the rows are written as they
 // arrive (sidCallFile): memory use does not grow with the file.  A gzip-compressed input (as the pipeline stores its
@@ -49,7 +49,7 @@ int main(int argc, char** argv) {
     size_t chunk_mb = 0;
     bool het_only = false;
     std::vector<int> devices;
-    int read_threads = (int)std::min(8u, std::max(1u, std::thread::hardware_concurrency()));
+    int read_threads = (int)std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
     static const option LONG[] = {{"device", required_argument, nullptr, 1000}, {"chunk-mb", required_argument, nullptr, 1001}, {"het-only", no_argument, nullptr, 1002}, {"devices", required_argument, nullptr, 1003}, {"read-threads", required_argument, nullptr, 1004}, {nullptr, 0, nullptr, 0}};
     int flag;
     while ((flag = getopt_long(argc, argv, "E:Rhm:p:r:", LONG, nullptr)) != -1) {      // optstring as built by sid.cpp:60-69

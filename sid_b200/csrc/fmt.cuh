@@ -109,6 +109,44 @@ SID_HD uint64_t scaled_round(uint64_t m, int e2, int j) {
     return lo;
 }
 
+// 10^k, k = 0..300, as double-double (tools/gen_pow10_dd.py)
+#if defined(__CUDA_ARCH__)
+__device__ const double POW10_DD[301][2] = {
+#include "pow10_dd.inc"
+};
+#else
+static const double POW10_DD[301][2] = {
+#include "pow10_dd.inc"
+};
+#endif
+
+// The fast way to round_half_even(x * 10^k): the product in double-double arithmetic (x * hi error-free through an
+// FMA, plus x * lo): about 104 correct bits of a value below 2^20, so the integer part and which side of one half the
+// fraction lies on are certain unless the fraction is within 1e-9 of one half.  Then -- and for powers or values
+// outside the table's comfortable range -- the caller takes the exact big-integer path.  Returns false for "not sure".
+SID_HD bool scaled_round_fast(double x, int k, uint64_t& d) {
+    if (k < 0 || k > 300 || !(x >= 1e-290) || !(x < 1e300)) return false;
+    const double hi = POW10_DD[k][0], lo = POW10_DD[k][1];
+    const double p = x * hi;
+    if (!(p < 4.0e15)) return false;
+#if defined(__CUDA_ARCH__)
+    const double e = __fma_rn(x, hi, -p);
+#else
+    const double e = __builtin_fma(x, hi, -p);
+#endif
+    const double t = e + x * lo;
+    const double yh = p + t;
+    const double yl = t - (yh - p);                  // fast two-sum: |p| >= |t|
+    double f = floor(yh);
+    double s = (yh - f) + yl;                        // the fraction, in (-tiny, 1 + tiny)
+    if (s < 0) { f -= 1.0; s += 1.0; }
+    else if (s >= 1.0) { f += 1.0; s -= 1.0; }
+    const double off = s - 0.5;
+    if (off < 1e-9 && off > -1e-9) return false;     // too close to a tie to call
+    d = (uint64_t)f + (off > 0 ? 1u : 0u);
+    return true;
+}
+
 // printf("%g", x).  out needs 16 bytes; returns the length (no terminator written).
 SID_HD int fmt_g6(double x, char* out) {
     const uint64_t bits = double_bits(x);
@@ -139,8 +177,9 @@ SID_HD int fmt_g6(double x, char* out) {
         if (d >= 1000000) { d /= 10; ++e; }
         e10 = e;
     } else {
+        const double ax = neg ? -x : x;
         for (int it = 0; it < 4; ++it) {
-            d = scaled_round(m, e2, 5 - e10);
+            if (!scaled_round_fast(ax, 5 - e10, d)) d = scaled_round(m, e2, 5 - e10);
             if (d >= 1000000) { ++e10; if (e10 > 5) { d = 100000; break; } continue; }
             if (d < 100000) { --e10; continue; }
             break;

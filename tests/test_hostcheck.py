@@ -67,9 +67,15 @@ def test_format_g_matches_printf(native):
             vals.append(math.exp(-rnd.random() * 745))
         else:
             vals.append(struct.unpack("<d", struct.pack("<Q", rnd.getrandbits(62) % (0x3FF0000000000000 + 1)))[0])
-    for m in range(1, 40):                  # exact decimal ties: k * 2^-m
+    for m in range(1, 40):                  # exact decimal ties: k * 2^-m, and their neighbours one ulp away
         for k in range(1, 400, 2):
-            vals.append(k * 2.0 ** -m)
+            v = k * 2.0 ** -m
+            vals += [v, math.nextafter(v, 0.0), math.nextafter(v, 2.0)]
+    for e in range(-300, 6):                # six-digit boundaries d.ddddd5 * 10^e: a fast product must not guess them
+        for _ in range(20):
+            d = rnd.randrange(100000, 1000000)
+            v = float("%d.5e%d" % (d, e - 5))
+            vals += [v, math.nextafter(v, 0.0), math.nextafter(v, math.inf)]
     for x in vals:
         hc.hc_fmt_g6(x, buf)
         assert buf.value.decode() == "%g" % x, repr(x)
