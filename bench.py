@@ -394,7 +394,10 @@ def time_cli(args, h_text, text_len, n_sites):
             streaming = float(phases.split("bytes")[1].split("s")[0])
         except Exception:
             pass
-        return {"value": n_sites / best, "unit": UNIT, "seconds": best, "startup_seconds": startup, "phases": phases,
+        import resource
+        rss_mb = resource.getrusage(resource.RUSAGE_CHILDREN).ru_maxrss / 1024.0          # the largest child so far: the run on the full file
+        return {"value": n_sites / best, "unit": UNIT, "seconds": best, "startup_seconds": startup, "phases": phases, "max_rss_mb": rss_mb,
+                "file_bytes": int(text_len),
                 "streaming_seconds": streaming, "value_streaming_only": n_sites / streaming if streaming else None,
                 "what": "host/sid -m local /dev/shm/file > /dev/null, wall clock of the whole process (best of 3); startup = the same on a "
                         "4 KB file (process start, CUDA context, kernel image, tables, pinned rings); streaming = sidgpu_call_io alone"}
@@ -519,11 +522,11 @@ def run_ours(args):
 
     # ---- the reference's CPU path on this box's host cores (rank 0, N=1 only)
     cpu = cli = None
+    if rank == 0 and world == 1 and not args.no_e2e and args.method == "local":
+        cli = time_cli(args, h_text, text_len, n_sites)          # before the reference runs: max_rss_mb is the largest child so far
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         v, kind, sample, dt = time_cpu(args, 1, min(args.cpu_sample_sites, n_sites))
         cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": kind, "sample": sample, "seconds": dt}
-    if rank == 0 and world == 1 and not args.no_e2e and args.method == "local":
-        cli = time_cli(args, h_text, text_len, n_sites)
 
     # ---- the other BASELINE configurations, outside the headline's timed region
     other = None

@@ -17,6 +17,7 @@
 //     region; k_rows_compact lays the regions end to end in file order.  No site store, no order[], no K6.
 #pragma once
 #include "calls.cuh"
+#include "k_quality.cuh"
 #include "k_tokenize.cuh"
 #include "parse_win.cuh"
 #include "row_assemble.cuh"
@@ -38,6 +39,8 @@ struct Tok2Params {
     uint32_t* slot;
     uint32_t* name_ref;
     uint64_t* line_off;
+    double* qual_l;                 // QUAL: two doubles per site, the log-likelihood sums of `-m quality` (+inf: not formed here)
+    const double* qual_lut;         // QUAL: the per-read term tables (k_quality.cuh)
     unsigned long long* site_alloc;
     // ROWS form
     uint8_t* rows;                  // scratch: region of (tile, slice) at rows + (tile * 8 + slice) * region_cap
@@ -248,8 +251,13 @@ __device__ __forceinline__ bool parse_lines_by_windows(const uint8_t* txt, uint3
 // DEEP: the instantiation for long lines (hundreds of bytes): slices of a few lines run stage 2 one window per lane
 // (parse_lines_by_windows).  Its own kernel so that the code and the registers of that path stay out of the ordinary one
 // (folded into one kernel behind a flag it cost the depth-30 path 30 %); shared memory holds two such CTAs per SM anyway.
-template <bool ROWS, int TOK_STAGES, bool DEEP = false>
-__global__ void __launch_bounds__(TOK_THREADS, DEEP ? 2 : SID_TOK2_CTAS) k_tok2(const Tok2Params p) {
+#ifndef SID_TOK2_QUAL_CTAS
+#define SID_TOK2_QUAL_CTAS 2      // CTAs per SM the register allocator leaves room for in the QUAL instantiation
+#endif
+// QUAL: the instantiation of quality sessions: the per-read sums of callQualityBasedSimple are formed right here, from the
+// class windows of the line (k_quality.cuh: quality_sums_win), instead of a second byte-wise walk over the text in k_quality.
+template <bool ROWS, int TOK_STAGES, bool DEEP = false, bool QUAL = false>
+__global__ void __launch_bounds__(TOK_THREADS, DEEP ? 2 : (QUAL ? SID_TOK2_QUAL_CTAS : SID_TOK2_CTAS)) k_tok2(const Tok2Params p) {
     extern __shared__ __align__(128) uint8_t s_dyn[];
     __shared__ StageMeta s_meta[TOK_STAGES];
     __shared__ __align__(8) uint64_t s_full[TOK_STAGES], s_done[TOK_STAGES];
@@ -461,10 +469,21 @@ __global__ void __launch_bounds__(TOK_THREADS, DEEP ? 2 : SID_TOK2_CTAS) k_tok2(
                 LineResult r;
                 r.status = LINE_MALFORMED;
                 bool fast = false;
+                double ql1 = bits_double(0x7FF0000000000000ull), ql2 = 0;     // QUAL: +inf = "k_quality walks this line itself"
                 if (win_ok) {
                     WinLine wl;
                     // a handful of long lines: one 64-byte window of a bases field per lane instead of one line per lane
                     if (DEEP && by_windows) fast = parse_lines_by_windows(txt, region_off, cw, nlw, s_term_groups[pw], n_bits, TILE_PAD + off, mine, wl);
+                    else if (QUAL) {
+                        WinHeader hd;
+                        uint32_t end_bit = 0;
+                        fast = parse_line_win<true>(txt, region_off, cw, nlw, n_bits, TILE_PAD + off, wl, &hd, &end_bit);
+                        if (fast && mine) {
+                            double a, b;
+                            if (quality_sums_win(txt, region_off, cw, nlw, n_bits, hd, end_bit, wl.profile, p.qual_lut, a, b)) { ql1 = a; ql2 = b; }
+                        }
+                        __syncwarp();
+                    }
                     else fast = parse_line_win<true>(txt, region_off, cw, nlw, n_bits, TILE_PAD + off, wl);
                     r.status = wl.status; r.pos = wl.pos; r.profile = wl.profile; r.chrom_off = 0; r.chrom_len = wl.name_len;
                 }
@@ -517,6 +536,7 @@ __global__ void __launch_bounds__(TOK_THREADS, DEEP ? 2 : SID_TOK2_CTAS) k_tok2(
                         p.name_ref[site] = ref;
                         if (p.profile) p.profile[site] = r.profile;
                         if (p.line_off) p.line_off[site] = line_abs;
+                        if (QUAL) { p.qual_l[2 * site] = fast ? ql1 : bits_double(0x7FF0000000000000ull); p.qual_l[2 * site + 1] = ql2; }
                         if (p.use_table) p.slot[site] = slot;
                     }
                 }

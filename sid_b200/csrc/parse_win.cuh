@@ -220,16 +220,12 @@ SID_HD uint64_t win_profile(uint32_t cn, uint32_t c1, uint32_t c2, uint32_t c12,
     return pack_profile(cn - c1 - c2 + c12, c1 - c12, c12, c2 - c12);
 }
 
-// One line per lane: header, then the bases field window by window (a loop of ceil(field / 64) steps).
-template <bool WANT_POS>
-SID_HD bool parse_line_win(const uint8_t* s, uint32_t region_off, const uint32_t* cw, const uint32_t* nlw, uint32_t n_bits,
-                           uint32_t line_off, WinLine& o) {
-    WinHeader hd;
-    Win64 w;
-    bool ok = win_header<WANT_POS>(s, region_off, cw, nlw, n_bits, line_off, o, hd, w);
-    SID_SYNCWARP();
-    // ---- bases field: 64 bytes per window; the first window is the one that holds the header
-    uint32_t cn = 0, c1 = 0, c2 = 0, c12 = 0, cd = 0;
+// The bases field of a line window by window (a loop of ceil(field / 64) steps; the first window is the one that holds
+// the header).  visit(w, live) sees every window once, in text order, with the bytes of the field that the grammar
+// looks at ('^'-hidden and indel-skipped bytes removed).  *end_bit receives the bit index of the byte that ends the field.
+template <class Visit>
+SID_HD bool win_bases_walk(const uint8_t* s, uint32_t region_off, const uint32_t* cw, uint32_t n_bits, const WinHeader& hd, Win64 w, bool ok,
+                           Visit& visit, uint32_t* end_bit) {
     uint32_t cur = hd.l0;                       // bit index of the window
     uint64_t below = (2ull << hd.q4) - 1ull;    // bits of the window that precede the field
     uint32_t skip = 0;                          // bytes at the start of the next window still covered by a '^' or an indel
@@ -276,14 +272,10 @@ SID_HD bool parse_line_win(const uint8_t* s, uint32_t region_off, const uint32_t
             if (to > 64 && !last) skip = (uint32_t)(to - 64 > (1u << 27) ? (1u << 27) : to - 64);
         }
         if (!last && next == cur + 64 && ((w.caret & live_all) >> 63)) skip = 1;   // the hidden byte opens the next window
-        const uint64_t b = w.base & live;
-        cn += popc64(b);
-        c1 += popc64(b & w.p1);
-        c2 += popc64(b & w.p2);
-        c12 += popc64(b & w.p1 & w.p2);
-        cd += popc64(w.dot & live);
+        visit(w, live);
         if (last || !ok) {
             running = false;
+            if (end_bit) *end_bit = cur + e;
         } else {
             cur = next;
             below = 0;
@@ -291,9 +283,36 @@ SID_HD bool parse_line_win(const uint8_t* s, uint32_t region_off, const uint32_t
             else w = load_window(cw, cur);
         }
     }
+    return ok;
+}
+
+// The tokenizer's visitor: counts by the bit planes that tell A/C/G/T apart, and '.'/','.
+struct WinCounts {
+    uint32_t cn = 0, c1 = 0, c2 = 0, c12 = 0, cd = 0;
+    SID_HD void operator()(const Win64& w, uint64_t live) {
+        const uint64_t b = w.base & live;
+        cn += popc64(b);
+        c1 += popc64(b & w.p1);
+        c2 += popc64(b & w.p2);
+        c12 += popc64(b & w.p1 & w.p2);
+        cd += popc64(w.dot & live);
+    }
+};
+
+// One line per lane: header, then the bases field.
+template <bool WANT_POS>
+SID_HD bool parse_line_win(const uint8_t* s, uint32_t region_off, const uint32_t* cw, const uint32_t* nlw, uint32_t n_bits,
+                           uint32_t line_off, WinLine& o, WinHeader* hd_out = nullptr, uint32_t* end_bit = nullptr) {
+    WinHeader hd;
+    Win64 w;
+    bool ok = win_header<WANT_POS>(s, region_off, cw, nlw, n_bits, line_off, o, hd, w);
     SID_SYNCWARP();
-    o.profile = win_profile(cn, c1, c2, c12, cd, hd);
+    WinCounts c;
+    ok = win_bases_walk(s, region_off, cw, n_bits, hd, w, ok, c, end_bit);
+    SID_SYNCWARP();
+    o.profile = win_profile(c.cn, c.c1, c.c2, c.c12, c.cd, hd);
     o.status = LINE_OK;
+    if (hd_out) *hd_out = hd;
     return ok;
 }
 
@@ -420,15 +439,22 @@ SID_HD bool win_window_patch(const Win64& w, uint32_t pos, uint32_t end, const W
 }
 
 #if !defined(__CUDACC__)
-// Host check: classifies the whole line (plus slack) like the kernel's stage 1, then runs stage 2.  A line with a
-// control byte (UnitClasses::bad) is refused here as the kernel refuses its whole slice.
-template <bool WANT_POS, bool COOP = false>
-inline bool parse_line_win_host(const uint8_t* text, uint64_t len, uint64_t p, WinLine& o) {
+// Host check: the line at p (plus slack) classified like the kernel's stage 1.
+struct HostLineClasses {
+    const uint8_t* scratch;     // the bytes that were classified; scratch[0] is 32..63 bytes before the line
+    const uint32_t* cw;
+    const uint32_t* nlw;
+    uint32_t units;
+    uint32_t line_off;          // offset of the line in scratch
+    bool usable;                // false: the line is too long for the scratch arrays or holds a control byte
+};
+inline HostLineClasses classify_line_host(const uint8_t* text, uint64_t len, uint64_t p) {
+    HostLineClasses h {nullptr, nullptr, nullptr, 0, 0, false};
     const int64_t first = (int64_t)(p & ~(uint64_t)31) - 32;
     uint64_t end = p;
     while (end < len && text[end] != '\n') ++end;
     const uint64_t avail64 = (((int64_t)end - first) + 256 + 31) & ~(uint64_t)31;
-    if (avail64 > (1u << 20)) return false;
+    if (avail64 > (1u << 20)) return h;
     static thread_local uint8_t scratch[(1u << 20) + 64] __attribute__((aligned(16)));
     static thread_local uint32_t cw[((1u << 15) + 8) * CW_WORDS], nlw[(1u << 15) + 8];
     for (uint64_t k = 0; k < avail64; ++k) {
@@ -453,7 +479,23 @@ inline bool parse_line_win_host(const uint8_t* text, uint64_t len, uint64_t p, W
         for (int c = 0; c < CW_WORDS; ++c) cw[(size_t)u * CW_WORDS + c] = 0;
         nlw[u] = 0;
     }
-    if (bad) return false;
+    h.scratch = scratch; h.cw = cw; h.nlw = nlw; h.units = units;
+    h.line_off = (uint32_t)((int64_t)p - first);
+    h.usable = bad == 0;
+    return h;
+}
+
+// Runs stage 2 on the classified line.  A line with a control byte (UnitClasses::bad) is refused here as the kernel
+// refuses its whole slice.
+template <bool WANT_POS, bool COOP = false>
+inline bool parse_line_win_host(const uint8_t* text, uint64_t len, uint64_t p, WinLine& o) {
+    const HostLineClasses h = classify_line_host(text, len, p);
+    if (!h.usable) return false;
+    const uint8_t* scratch = h.scratch;
+    const uint32_t* cw = h.cw;
+    const uint32_t* nlw = h.nlw;
+    const uint32_t units = h.units;
+    const int64_t first = (int64_t)p - (int64_t)h.line_off;
     if (!COOP) return parse_line_win<WANT_POS>(scratch, 0, cw, nlw, units * 32, (uint32_t)((int64_t)p - first), o);
     // the window-per-lane form, windows in order: skip_in of a window is the final skip_out of the one before it,
     // which is the fixed point the lanes of the kernel converge to

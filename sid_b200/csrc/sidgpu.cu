@@ -89,12 +89,14 @@ struct sidgpu_ctx {
     DevBuf csv_status;
     // site store: arrays indexed by storage index (dense, not in file order) and order[file index] = storage index
     DevBuf pos, slot, name_ref, profile, line_off, site_suffix, order;
+    DevBuf qual_l;                   // quality sessions: two doubles per site from the tokenizer (k_tok2<..., QUAL>)
     DevBuf blk, blk_part;            // block table of the running tokenizer call and its per-chunk sums
     DevBuf rows_scratch, rows_part, rows_part_rows;   // fused row writer: per-slice regions, per-chunk byte / row sums
     double region_factor = 1.0;      // grows when a slice's rows did not fit its region
     DevBuf v_pos, v_slot, v_name_ref, v_profile, v_line_off;   // file-ordered copies behind sidgpu_sites_view
     uint64_t site_cap = 0;
     bool want_profile = false, want_line_off = false, want_site_suffix = false;
+    bool qual_sums_valid = false;    // the last tokenizer call left the log-likelihood sums of `-m quality` in qual_l
     uint64_t n_sites_total = 0;      // sites in the store (accumulate mode) or in the last chunk (streaming)
     uint64_t chunk_begin = 0, chunk_sites = 0;
 
@@ -380,7 +382,7 @@ int reset_table(sidgpu_ctx* ctx) {
 
 int ensure_sites(sidgpu_ctx* ctx, uint64_t n, bool keep) {
     if (n > ctx->site_cap || (ctx->want_profile && ctx->profile.cap < n * 8) || (ctx->want_line_off && ctx->line_off.cap < n * 8) ||
-        (ctx->want_site_suffix && ctx->site_suffix.cap < n * SUFFIX_BYTES)) {
+        (ctx->want_site_suffix && (ctx->site_suffix.cap < n * SUFFIX_BYTES || ctx->qual_l.cap < n * 16))) {
         const uint64_t cap = std::max<uint64_t>(n, ctx->site_cap);
         if (cap >= 0xFFFFFFFFull) return ctx->fail(SIDGPU_ECAPACITY, "more than 2^32 sites in one store: feed smaller ranges");
         TRY(ensure(ctx, ctx->order, cap * 4, keep));
@@ -390,6 +392,7 @@ int ensure_sites(sidgpu_ctx* ctx, uint64_t n, bool keep) {
         if (ctx->want_profile) TRY(ensure(ctx, ctx->profile, cap * 8, keep));
         if (ctx->want_line_off) TRY(ensure(ctx, ctx->line_off, cap * 8, keep));
         if (ctx->want_site_suffix) TRY(ensure(ctx, ctx->site_suffix, cap * SUFFIX_BYTES, keep));
+        if (ctx->want_site_suffix) TRY(ensure(ctx, ctx->qual_l, cap * 16, keep));
         ctx->site_cap = cap;
     }
     return SIDGPU_OK;
@@ -484,8 +487,17 @@ int run_tokenizer(sidgpu_ctx* ctx, const char* d_text, size_t text_len, size_t r
             q.ext_bytes = ext; q.units_cap = tok2_units(slice, ext) + CW_PAD_UNITS;
             static const int deep_knob = getenv("SIDGPU_DEEP_LINES") ? atoi(getenv("SIDGPU_DEEP_LINES")) : -1;     // A/B knob: 0 off, 1 on
             const bool deep = deep_knob >= 0 ? deep_knob != 0 : ctx->avg_line_bytes >= 256.0;
+            // quality sessions: the per-read sums are formed by the tokenizer (A/B knob: SIDGPU_QUALITY_K1=0 leaves them to k_quality)
+            static const bool qual_knob = !(getenv("SIDGPU_QUALITY_K1") && atoi(getenv("SIDGPU_QUALITY_K1")) == 0);
+            const bool qual = qual_knob && want_qual && !strict_qual && !deep && ctx->want_site_suffix && ctx->qual_l.p;
+            q.qual_l = qual ? (double*)ctx->qual_l.p : nullptr;
+            q.qual_lut = (const double*)ctx->quality_lut.p;
+            ctx->qual_sums_valid = qual;
             int s2 = 0, s1 = 0;
-            if (deep) {
+            if (qual) {
+                if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s2, k_tok2<false, 2, false, true>, TOK_THREADS, tok2_dyn_smem(slice, ext, 2, false)) != cudaSuccess || s2 < 1) s2 = 1;
+                if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s1, k_tok2<false, 1, false, true>, TOK_THREADS, tok2_dyn_smem(slice, ext, 1, false)) != cudaSuccess || s1 < 1) s1 = 1;
+            } else if (deep) {
                 // long lines: the instantiation whose stage 2 gives every 64-byte window of a bases field its own lane
                 if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s2, k_tok2<false, 2, true>, TOK_THREADS, tok2_dyn_smem(slice, ext, 2, false)) != cudaSuccess || s2 < 1) s2 = 1;
                 if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s1, k_tok2<false, 1, true>, TOK_THREADS, tok2_dyn_smem(slice, ext, 1, false)) != cudaSuccess || s1 < 1) s1 = 1;
@@ -498,7 +510,10 @@ int run_tokenizer(sidgpu_ctx* ctx, const char* d_text, size_t text_len, size_t r
             const uint32_t dyn = tok2_dyn_smem(slice, ext, (uint32_t)stages, false);
             {
                 ProfScope prof(ctx, PROF_TOKENIZE);
-                if (deep) {
+                if (qual) {
+                    if (stages == 1) k_tok2<false, 1, false, true><<<grid, TOK_THREADS, dyn, ctx->stream>>>(q);
+                    else k_tok2<false, 2, false, true><<<grid, TOK_THREADS, dyn, ctx->stream>>>(q);
+                } else if (deep) {
                     if (stages == 1) k_tok2<false, 1, true><<<grid, TOK_THREADS, dyn, ctx->stream>>>(q);
                     else k_tok2<false, 2, true><<<grid, TOK_THREADS, dyn, ctx->stream>>>(q);
                 } else {
@@ -940,6 +955,7 @@ int quality_rows(sidgpu_ctx* ctx, uint64_t site_begin, uint64_t n, uint8_t* rec_
     q.text_len = ctx->last_text_len;
     q.line_off = (const uint64_t*)ctx->line_off.p;
     q.profile = (const uint64_t*)ctx->profile.p;
+    q.qual_l = ctx->qual_sums_valid ? (const double*)ctx->qual_l.p : nullptr;
     q.order = (const uint32_t*)ctx->order.p;
     q.site_begin = site_begin;
     q.n_sites = n;
@@ -1119,6 +1135,8 @@ int sidgpu_create(const sidgpu_config* cfg, sidgpu_ctx** out) {
         (e = cudaFuncSetAttribute(k_tok2<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::min<uint32_t>(227u << 10, tok2_dyn_smem(SLICE_MAX, 2016, 2, false)))) != cudaSuccess ||
         (e = cudaFuncSetAttribute(k_tok2<false, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tok2_dyn_smem(SLICE_MAX, 2016, 1, false))) != cudaSuccess ||
         (e = cudaFuncSetAttribute(k_tok2<false, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::min<uint32_t>(227u << 10, tok2_dyn_smem(SLICE_MAX, 2016, 2, false)))) != cudaSuccess ||
+        (e = cudaFuncSetAttribute(k_tok2<false, 1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tok2_dyn_smem(SLICE_MAX, 2016, 1, false))) != cudaSuccess ||
+        (e = cudaFuncSetAttribute(k_tok2<false, 2, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::min<uint32_t>(227u << 10, tok2_dyn_smem(SLICE_MAX, 2016, 2, false)))) != cudaSuccess ||
         (e = cudaFuncSetAttribute(k_tok2<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tok2_dyn_smem(SLICE_MAX, 2016, 1, true))) != cudaSuccess ||
         (e = cudaFuncSetAttribute(k_tok2<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::min<uint32_t>(227u << 10, tok2_dyn_smem(SLICE_MAX, 2016, 2, true)))) != cudaSuccess ||
         (e = cudaFuncSetAttribute(k_rows_compact, cudaFuncAttributeMaxDynamicSharedMemorySize, (RC_THREADS / 32) * RC_STAGE)) != cudaSuccess ||

@@ -88,6 +88,42 @@ int64_t hc_call_quality(const uint8_t* text, uint64_t len, double prior, double 
     return k;
 }
 
+// The same calls formed the way a quality session forms them on the device now: the tokenizer's window walk sums the
+// per-read terms (quality_sums_win), k_quality only finishes.  Every line the window path accepts must give
+// BIT-IDENTICAL doubles to call_quality (same terms, same order).  Returns the number of lines, or -(k+1) when line k
+// differs; *n_win counts the lines the window path took.
+int64_t hc_call_quality_win(const uint8_t* text, uint64_t len, double prior, double alpha, uint64_t* n_win) {
+    std::vector<double> lut(4 * 256 + LOG_FACT_N);
+    for (int n = 0; n < LOG_FACT_N; ++n) lut[1024 + n] = lgamma((double)n + 1.0);
+    for (int q = 0; q < 256; ++q) {
+        const double error = pow(10., q / -10.);
+        lut[q] = log(1 - error);
+        lut[256 + q] = log(error);
+        lut[512 + q] = log(1 - 2. / 3. * error);
+        lut[768 + q] = log(2. / 3. * error);
+    }
+    FlatSrc src {text, len};
+    int64_t k = 0;
+    uint64_t taken = 0;
+    for (uint64_t p = 0; p < len; ++p) {
+        if (text[p] == '\n' || (p > 0 && text[p - 1] != '\n')) continue;
+        CallResult w;
+        if (quality_line_win_host(text, len, p, lut.data(), prior, alpha, w)) {
+            ++taken;
+            ParsedLine full, pl;
+            parse_line(src, p, true, full);
+            quality_fields(WordSrc {text, len}, p, full.profile, pl);
+            if (pl.status != LINE_OK) return -(k + 1);                  // the window path must refuse what the byte-wise code reports
+            const CallResult r = call_quality(text, p, pl, lut.data(), prior, alpha);
+            if (double_bits(r.hom) != double_bits(w.hom) || double_bits(r.het) != double_bits(w.het) || r.label != w.label ||
+                r.gt0 != w.gt0 || r.gt1 != w.gt1) return -(k + 1);
+        }
+        ++k;
+    }
+    if (n_win) *n_win = taken;
+    return k;
+}
+
 #ifdef SID_HAVE_FAST
 // The SWAR tokenizer the kernel uses.  Returns 1 when the fast grammar accepted the line.
 int hc_parse_line_fast(const uint8_t* text, uint64_t len, uint64_t p, hc_line* out) {

@@ -514,6 +514,44 @@ def test_quality_call_with_control_reference_characters(native):
     _quality_case(("\n".join(lines) + "\n").encode())
 
 
+def _quality_win_case(text, expect_all=False, prior=-1.0):
+    hc = op.hostcheck()
+    hc.hc_call_quality_win.restype = ctypes.c_int64
+    hc.hc_call_quality_win.argtypes = [ctypes.c_char_p, ctypes.c_uint64, ctypes.c_double, ctypes.c_double, ctypes.c_void_p]
+    taken = ctypes.c_uint64()
+    k = hc.hc_call_quality_win(text, len(text), prior, 0.05, ctypes.byref(taken))
+    assert k > 0, text.split(b"\n")[-k - 1][:300] if k < 0 else None
+    if expect_all:
+        assert taken.value == k
+    return k, taken.value
+
+
+@pytest.mark.parametrize("name,prior", [("quality30.plp", -1.0), ("quality30.plp", 0.001), ("edge_quality.plp", -1.0)])
+def test_quality_sums_in_the_tokenizer_are_bit_identical(native, name, prior):
+    """A quality session sums the per-read terms inside the tokenizer (WinQuality over the class windows); k_quality
+    then only finishes.  Same terms in the same order as call_quality: the doubles must be EQUAL, and every ordinary
+    line must take that path."""
+    _quality_win_case(read(name), expect_all=name == "quality30.plp", prior=prior)
+
+
+def test_quality_sums_in_the_tokenizer_on_odd_lines(native):
+    rnd = random.Random(17)
+    lines = []
+    for k in range(8000):
+        ln = rnd.choice([1, 2, 3, 5, 8, 12, 20, 31, 33, 40, 63, 64, 65, 70, 130])
+        bases = "".join(rnd.choice(".,.,.,.,ACGTacgtNn*$^+-0123456789<>") for _ in range(ln))
+        nq = ln + rnd.choice([0, 0, 0, 1, 5])
+        q = "".join(chr(33 + rnd.randrange(0, 60)) for _ in range(nq))
+        sep = rnd.choice(["\t", "\t", "\t", " ", "\t\t"])
+        lines.append("chr1\t%d\t%s\t%d\t%s%s%s\t%s" % (k + 1, rnd.choice("ACGTacgtNn*.,"), ln, bases, sep, q, q[::-1]))
+    k, taken = _quality_win_case(("\n".join(lines) + "\n").encode())
+    assert taken > k // 4
+    from sid_b200 import synth
+    deep = synth.generate(300, seed=7, lam=600.0, het=0.02, err=0.02, start=0.05, indel=0.01, seven_columns=True)
+    k, taken = _quality_win_case(bytes(deep))
+    assert taken > k // 2
+
+
 def test_quality_call_matches_oracle_on_deep_pileups(native):
     """2000x coverage: thousands of per-read terms per sum."""
     from sid_b200 import synth
