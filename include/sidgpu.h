@@ -157,7 +157,10 @@ int sidgpu_read_fill(sidgpu_ctx* ctx, const char* d_text, size_t text_len, const
  * --------------------------------------------------------------------------------------------- */
 int sidgpu_begin(sidgpu_ctx* ctx, const sidgpu_params* params);
 /* Tokenizes one chunk and joins its sites against the unique-profile table (K1 + K3).
- * n_sites_out (optional) receives the number of sites the chunk added. */
+ * n_sites_out (optional) receives the number of sites the chunk added.
+ * Limits: sessions that keep their sites (bayes, likelihood_ratio, -R) index them with 32 bits: at most 2^32 - 2 sites
+ * per ctx (SIDGPU_ECAPACITY beyond; shard larger genomes over several GPUs or sessions).  One call takes at most
+ * 2^31 tokenizer slices (about 5 TB of text). */
 int sidgpu_feed(sidgpu_ctx* ctx, const char* d_text, size_t text_len, size_t range_begin,
                 size_t range_end, uint64_t* n_sites_out);
 int sidgpu_finish(sidgpu_ctx* ctx);

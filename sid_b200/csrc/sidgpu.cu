@@ -956,7 +956,9 @@ int quality_rows(sidgpu_ctx* ctx, uint64_t site_begin, uint64_t n, uint8_t* rec_
     q.line_off = (const uint64_t*)ctx->line_off.p;
     q.profile = (const uint64_t*)ctx->profile.p;
     q.qual_l = ctx->qual_sums_valid ? (const double*)ctx->qual_l.p : nullptr;
-    q.order = (const uint32_t*)ctx->order.p;
+    // the rows of a whole chunk need no particular order here (K6 reads the suffixes through order[] afterwards)
+    const bool whole = !rec_label && !rec_gt && !rec_hom && !rec_het && site_begin == 0 && n == ctx->n_sites_total;
+    q.order = whole ? nullptr : (const uint32_t*)ctx->order.p;
     q.site_begin = site_begin;
     q.n_sites = n;
     q.lut = (const double*)ctx->quality_lut.p;
