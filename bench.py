@@ -375,27 +375,35 @@ def time_cli(args, h_text, text_len, n_sites):
         nl = int(h_text[:4096].tobytes().rfind(b"\n")) + 1
         h_text[:nl].tofile(tiny)
         env = dict(os.environ, SID_TIMING="1")
-        best, phases = None, ""
-        for _ in range(3):
+
+        def run_sid(file_path):
+            """(wall seconds, stderr text, peak RSS in MB) of one `sid -m local file > /dev/null`."""
             t0 = time.perf_counter()
             with open(os.devnull, "wb") as null:
-                r = subprocess.run([sid, "-m", "local", path], stdout=null, stderr=subprocess.PIPE, check=True, env=env)
-            dt = time.perf_counter() - t0
+                pr = subprocess.Popen([sid, "-m", "local", file_path], stdout=null, stderr=subprocess.PIPE, env=env)
+                err = pr.stderr.read()
+                _, status, ru = os.wait4(pr.pid, 0)
+            pr.returncode = os.waitstatus_to_exitcode(status)
+            if pr.returncode != 0:
+                raise RuntimeError("sid exited with %d: %s" % (pr.returncode, err.decode()[-300:]))
+            return time.perf_counter() - t0, err.decode().strip(), ru.ru_maxrss / 1024.0
+
+        best, phases, rss_mb = None, "", None
+        for _ in range(3):
+            dt, text_err, rss = run_sid(path)
             if best is None or dt < best:
-                best, phases = dt, r.stderr.decode().strip()
-        startup = None
+                best, phases, rss_mb = dt, text_err, rss
+        startup, rss_tiny = None, None
         for _ in range(3):                          # the same process on a 4 KB file: what is not streaming
-            t0 = time.perf_counter()
-            subprocess.run([sid, "-m", "local", tiny], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, check=True)
-            dt = time.perf_counter() - t0
-            startup = dt if startup is None else min(startup, dt)
+            dt, _, rss = run_sid(tiny)
+            if startup is None or dt < startup:
+                startup, rss_tiny = dt, rss
         streaming = None
         try:
             streaming = float(phases.split("bytes")[1].split("s")[0])
-        except Exception:
+            rss_mb = float(phases.split("peak RSS")[1].split("MB")[0])       # VmHWM as sid reads it itself: ru_maxrss of a child
+        except Exception:                                                  # still carries this process's peak from before exec
             pass
-        import resource
-        rss_mb = resource.getrusage(resource.RUSAGE_CHILDREN).ru_maxrss / 1024.0          # the largest child so far: the run on the full file
         return {"value": n_sites / best, "unit": UNIT, "seconds": best, "startup_seconds": startup, "phases": phases, "max_rss_mb": rss_mb,
                 "file_bytes": int(text_len),
                 "streaming_seconds": streaming, "value_streaming_only": n_sites / streaming if streaming else None,

@@ -1,6 +1,7 @@
 // Host side of the drop-in: the reference's free functions (call.hpp / pileup.hpp) implemented over
 // the C ABI of libsidgpu.so.  No parsing, likelihood or formatting code lives here -- this file only
 // moves bytes: istream -> pinned host buffer -> sidgpu_call_host -> CSV rows -> OutputRecord.
+#include <cstdio>
 #include <cstring>
 #include <iomanip>
 #include <iterator>
@@ -546,9 +547,16 @@ SidRunInfo sidCallFile(const std::string& method, int fd_in, bool gzip, bool est
     const auto t1 = std::chrono::steady_clock::now();
     const int rc = sidgpu_call_io(h, &p, &io, &bytes, &info.n_sites, &info.n_rows);
     const auto t2 = std::chrono::steady_clock::now();
-    if (getenv("SID_TIMING"))                       // where the wall clock of a run goes (bench.py cli_e2e)
+    if (getenv("SID_TIMING")) {                     // where the wall clock and the memory of a run go (bench.py cli_e2e)
+        long hwm_kb = -1;                           // VmHWM of this process image (ru_maxrss would carry the parent's peak over fork)
+        if (FILE* st = std::fopen("/proc/self/status", "r")) {
+            char line[256];
+            while (std::fgets(line, sizeof line, st)) if (std::sscanf(line, "VmHWM: %ld kB", &hwm_kb) == 1) break;
+            std::fclose(st);
+        }
         log << "# timing: device setup " << std::chrono::duration<double>(t1 - t0).count() << " s, streaming " << bytes << " CSV bytes "
-            << std::chrono::duration<double>(t2 - t1).count() << " s" << std::endl;
+            << std::chrono::duration<double>(t2 - t1).count() << " s, peak RSS " << hwm_kb / 1024 << " MB" << std::endl;
+    }
     if (f.gz) gzclose(f.gz);
     if (rc != SIDGPU_OK) {
         if (f.write_failed) throw std::runtime_error("could not write the rows");

@@ -186,7 +186,7 @@ int sidgpu_emit_records(sidgpu_ctx* ctx, uint64_t site_begin, uint64_t n_sites, 
  * columnar form downstream consumers read (scripts/nonsynonymous.py:10-12,36 re-parses the CSV into
  * exactly these fields).  Any pointer may be NULL; arrays of n_sites elements (d_gt: 2 per site), file
  * order.  d_name_ref[i] is the byte offset of a record (uint16 length, then the bytes) in the names
- * pool that sidgpu_names returns.  Not for `quality` sessions (their results exist as text only). */
+ * pool that sidgpu_names returns.  (`quality` sessions: the per-site call runs for the range, as for sidgpu_emit_records.) */
 typedef struct {
     int32_t* d_pos;
     uint32_t* d_name_ref;

@@ -480,7 +480,7 @@ def sid_csv(text, method="local", estimate_prior=False, prior=-1.0, error_thresh
 
 def call_columns(text, method="local", estimate_prior=False, prior=-1.0, error_threshold=0.1, significance_level=0.05, ctx=None, fit=None):
     """The rows `sid -m METHOD` prints, as columns: a dict of numpy arrays (see Context.emit_columns).
-    `local`, `bayes`, `likelihood_ratio`; the text is fed from device memory in one piece."""
+    All four methods (`quality` without -R: the text is fed once); the text is fed from device memory in one piece."""
     ctx = ctx or default_context()
     d = ctx.upload_text(text)
     try:

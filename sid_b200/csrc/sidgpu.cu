@@ -1562,12 +1562,15 @@ int sidgpu_emit_columns(sidgpu_ctx* ctx, uint64_t site_begin, uint64_t n_sites, 
     if (!ctx || !cols) return SIDGPU_EINVAL;
     if (ctx->phase == PHASE_IDLE) return ctx->fail(SIDGPU_ESTATE, "sidgpu_emit_columns outside a session");
     if (!ctx->streaming && ctx->phase != PHASE_FINISHED) return ctx->fail(SIDGPU_ESTATE, "this method needs sidgpu_finish first");
-    if (ctx->params.method == SIDGPU_METHOD_QUALITY) return ctx->fail(SIDGPU_EINVAL, "quality results are per site: use sidgpu_emit_csv");
     if (site_begin + n_sites > ctx->n_sites_total) return ctx->fail(SIDGPU_EINVAL, "site range not in the store");
     if (n_sites == 0) return SIDGPU_OK;
     CK(cudaSetDevice(ctx->device));
+    const bool is_quality = ctx->params.method == SIDGPU_METHOD_QUALITY;
+    // quality: the call is per site, not per profile: k_quality writes label / genotype / confidences itself
+    if (is_quality) TRY(sidgpu_emit_records(ctx, site_begin, n_sites, cols->d_label, cols->d_gt, cols->d_hom_conf, cols->d_het_conf));
     RecordParams p {site_begin, n_sites, (const uint32_t*)ctx->order.p, (const uint32_t*)ctx->slot.p, ctx->tab,
-                    cols->d_label, cols->d_gt, cols->d_hom_conf, cols->d_het_conf,
+                    is_quality ? nullptr : cols->d_label, is_quality ? nullptr : cols->d_gt, is_quality ? nullptr : cols->d_hom_conf,
+                    is_quality ? nullptr : cols->d_het_conf,
                     (const int32_t*)ctx->pos.p, (const uint32_t*)ctx->name_ref.p, cols->d_pos, cols->d_name_ref};
     k_records<<<(unsigned)((n_sites + 255) / 256), 256, 0, ctx->stream>>>(p);
     TRY(check_launch(ctx, "k_records"));

@@ -284,8 +284,10 @@ def test_very_deep_pileups(native, gpu_ctx, lam, n_sites, method):
     assert diffs <= 2
 
 
-@pytest.mark.parametrize("case", [c for c in MANIFEST["cases"] if c["input"] in ("depth30_two_chroms.plp", "edge.plp", "depth5.plp")
-                                  and "quality" not in c["flags"]], ids=lambda c: c["csv"])
+@pytest.mark.parametrize("case", [c for c in MANIFEST["cases"] if (c["input"] in ("depth30_two_chroms.plp", "edge.plp", "depth5.plp")
+                                                                    and "quality" not in c["flags"])
+                                  or (c["input"] in ("quality30.plp", "edge_quality.plp") and "quality" in c["flags"] and "-R" not in c["flags"])],
+                         ids=lambda c: c["csv"])
 def test_columns_match_reference_csv(native, gpu_ctx, case):
     """sidgpu_emit_columns (chrom, pos, label, gt, confidences as arrays) row by row against
     the reference's CSV, and as a pyarrow table."""
