@@ -56,6 +56,14 @@ def test_cli_reads_a_pipe(sid_bin):
         want = open(os.path.join(GOLDEN, "depth30.m_bayes.csv" if "bayes" in extra else "depth30.m_local.csv"), "rb").read()
         n, diffs = op.compare_csv(r.stdout, want)
         assert diffs <= max(2, n // 1000)
+    # nothing at all on the pipe: the header alone, like the reference on an empty file (sid.cpp:102)
+    r = subprocess.run([sid_bin, "/dev/stdin"], input=b"", stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert r.returncode == 0 and r.stdout == b"chrom,pos,label,gt,hom_conf,het_conf,conf_type\n"
+    # a last line without its line end, and chunks that cut lines anywhere
+    want = open(os.path.join(GOLDEN, "depth30.m_local.csv"), "rb").read()
+    r = subprocess.run([sid_bin, "--chunk-mb", "1", "/dev/stdin"], input=text.rstrip(b"\n"), stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    n, diffs = op.compare_csv(r.stdout, want)
+    assert r.returncode == 0 and diffs <= max(2, n // 1000)
 
 
 def test_cli_streams_with_bounded_memory(sid_bin, tmp_path):
