@@ -16,6 +16,8 @@
 #include <unistd.h>
 #include <zlib.h>
 
+#include "bgzf.hpp"
+
 #include "../include/sidgpu.h"
 #include "../sid_b200/csrc/nelder_mead.hpp"      // the simplex driver the library itself uses (host code, header only)
 #include "call.hpp"
@@ -264,6 +266,7 @@ struct FileIo {
     int fd_in = -1, fd_out = -1;
     bool gzip = false;
     gzFile gz = nullptr;
+    bgzf::Reader* blocks = nullptr;     // a BGZF file: its blocks are inflated side by side (bgzf.hpp)
     off_t offset = 0;                   // next byte of a regular file
     bool seekable = false;
     int threads = 1;
@@ -273,6 +276,7 @@ struct FileIo {
 
     static int64_t read_cb(void* user, char* dst, size_t cap) {
         FileIo& f = *(FileIo*)user;
+        if (f.blocks) return f.blocks->read(dst, cap);
         if (f.gzip) {
             const int got = gzread(f.gz, dst, (unsigned)std::min<size_t>(cap, (size_t)1 << 30));
             return got < 0 ? -1 : got;
@@ -330,6 +334,7 @@ struct FileIo {
     }
     static int rewind_cb(void* user) {
         FileIo& f = *(FileIo*)user;
+        if (f.blocks) { f.blocks->rewind(); return 0; }
         if (f.gzip) return gzrewind(f.gz) == 0 ? 0 : 1;
         if (!f.seekable) return 1;
         f.offset = 0;
@@ -528,10 +533,18 @@ SidRunInfo sidCallFile(const std::string& method, int fd_in, bool gzip, bool est
         f.put_header();
         return info;
     }
+    std::unique_ptr<bgzf::Reader> blocks;
     if (gzip) {
-        f.gz = gzdopen(dup(fd_in), "rb");
-        if (!f.gz) throw std::runtime_error("could not open the gzip stream");
-        gzbuffer(f.gz, 1u << 20);
+        unsigned char head[64];
+        const ssize_t got = pread(fd_in, head, sizeof head, 0);       // fails on a pipe: plain gzip stream then
+        if (got >= 18 && bgzf::looks_like(head, (size_t)got)) {
+            blocks.reset(new bgzf::Reader(fd_in, f.threads));
+            f.blocks = blocks.get();
+        } else {
+            f.gz = gzdopen(dup(fd_in), "rb");
+            if (!f.gz) throw std::runtime_error("could not open the gzip stream");
+            gzbuffer(f.gz, 1u << 20);
+        }
     }
     sidgpu_params p {};
     p.method = m;
@@ -560,6 +573,7 @@ SidRunInfo sidCallFile(const std::string& method, int fd_in, bool gzip, bool est
     if (f.gz) gzclose(f.gz);
     if (rc != SIDGPU_OK) {
         if (f.write_failed) throw std::runtime_error("could not write the rows");
+        if (f.blocks && !f.blocks->error().empty()) throw std::runtime_error("could not inflate the file: " + f.blocks->error());
         raise(rc);
     }
     sidgpu_fit fit {};

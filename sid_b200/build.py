@@ -57,6 +57,16 @@ def build_sid_cli(force=False):
         _run(["g++", "-O2", "-std=c++17", "-Wall", "-Iinclude", "-o", out, "host/sid.cpp", "host/sid_host.cpp"] + link + ["-lz", "-pthread"])
         _run(["g++", "-O2", "-std=c++17", "-Wall", "-Iinclude", "-o", os.path.join(ROOT, "host", "api_check"),
               "host/api_check.cpp", "host/sid_host.cpp"] + link + ["-lz", "-pthread"])
+    build_bgzf_cat(force)
+    return out
+
+
+def build_bgzf_cat(force=False):
+    """host/bgzf_cat: the block-parallel BGZF reader of `sid` on its own (no GPU, no libsidgpu)."""
+    out = os.path.join(ROOT, "host", "bgzf_cat")
+    srcs = [os.path.join(ROOT, "host", "bgzf_cat.cpp"), os.path.join(ROOT, "host", "bgzf.hpp")]
+    if force or _newer(out, srcs):
+        _run(["g++", "-O2", "-std=c++17", "-Wall", "-o", out, "host/bgzf_cat.cpp", "-lz", "-pthread"])
     return out
 
 
