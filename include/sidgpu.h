@@ -105,13 +105,15 @@ int sidgpu_memcpy_d2d_async(sidgpu_ctx* ctx, void* d_dst, const void* d_src, siz
  * line iff text[p] != '\n' and (p == 0 or text[p-1] == '\n') -- the sharding rule of SURVEY.md 8(e);
  * a line that straddles range_end is read to its end (up to text_len).  Empty lines are skipped
  * (call.cpp:14).  d_text must be 16-byte aligned.
+ * want_qual: 0 = five columns suffice; 1 = the quality columns are required as `quality` requires them (pileup.cpp:42-66)
+ * and d_line_off is filled; 2 = d_line_off is filled, the quality columns are not looked at.
  * --------------------------------------------------------------------------------------------- */
 typedef struct {
     uint64_t n_sites;          /* lines parsed by the call */
     const uint64_t* d_profile; /* per site: A | C<<16 | G<<32 | T<<48, each count mod 65536 (pileup.hpp:7) */
     const int32_t* d_pos;      /* per site: atoi(position column) */
     const uint32_t* d_slot;    /* per site: slot of its profile in the unique-profile table */
-    const uint64_t* d_line_off;/* per site: byte offset of the line in d_text (only with want_qual) */
+    const uint64_t* d_line_off;/* per site: byte offset of the line in d_text (only with want_qual != 0) */
     /* chromosome names are interned on the device: d_name_ref[i] is a byte offset into d_names,
      * where a 2-byte little-endian length is followed by the name bytes */
     const uint32_t* d_name_ref;
@@ -133,8 +135,15 @@ int sidgpu_tokenize(sidgpu_ctx* ctx, const char* d_text, size_t text_len, size_t
  *                       seventh SIDGPU_EMISSING_MAPQ with want_mapq != 0 (pileup.cpp:60-66); else their counts are 0.
  *   sidgpu_read_fill    the vectors themselves at the offsets the caller derived from the counts (exclusive prefix sums):
  *                       bases as upper-case letters, strands 1 = upper case / forward (pileup.cpp:84-123), qualities
- *                       as numbers.  Any output pointer may be NULL. */
+ *                       as numbers.  Any output pointer may be NULL.
+ *   sidgpu_strand_counts   the strands the reference parses and never reads (pileup.hpp:15,
+ *                       pileup.cpp:87-123), summed per line: d_fwd[i] / d_rev[i] = the counted bases of line i read on the
+ *                       forward strand (upper-case characters and '.') / the reverse strand (lower case and ','), packed
+ *                       like a profile (A | C<<16 | G<<32 | T<<48, each mod 65536); d_fwd[i] + d_rev[i] is the profile,
+ *                       count by count.  Either pointer may be NULL.  Line offsets: sidgpu_tokenize(..., want_qual = 2). */
 int sidgpu_qualities(sidgpu_ctx* ctx, const char* d_quals, size_t n, uint8_t* d_out, uint64_t* n_out);
+int sidgpu_strand_counts(sidgpu_ctx* ctx, const char* d_text, size_t text_len, const uint64_t* d_line_off, uint64_t n_lines,
+                         uint64_t* d_fwd, uint64_t* d_rev);
 int sidgpu_read_counts(sidgpu_ctx* ctx, const char* d_text, size_t text_len, const uint64_t* d_line_off, uint64_t n_lines,
                        int want_baseq, int want_mapq, uint32_t* d_n_bases, uint32_t* d_n_bq, uint32_t* d_n_mq);
 int sidgpu_read_fill(sidgpu_ctx* ctx, const char* d_text, size_t text_len, const uint64_t* d_line_off, uint64_t n_lines,

@@ -12,8 +12,29 @@
 
 /* ---------------------------------------------------------------- pileup.cpp */
 
-/* pileup.cpp:70-153 parseReadBases */
+/* pileup.cpp:70-153 parseReadBases; strands_out (optional): 1 for an upper-case character, 0 for a lower-case one (:85-124) */
+static size_t read_bases(const char* s, char reference, uint16_t counts[4], char* bases_out, uint8_t* strands_out);
 size_t orc_parse_read_bases(const char* s, char reference, uint16_t counts[4], char* bases_out) {
+    return read_bases(s, reference, counts, bases_out, NULL);
+}
+/* ReadStack::strands (pileup.hpp:15) summed by letter: fwd[i] / rev[i] = counted bases i on the forward / reverse strand */
+size_t orc_strand_counts(const char* s, char reference, uint16_t fwd[4], uint16_t rev[4]) {
+    uint16_t counts[4];
+    size_t cap = strlen(s) + 1;
+    char* b = (char*)malloc(cap);
+    uint8_t* st = (uint8_t*)malloc(cap);
+    size_t nb = read_bases(s, reference, counts, b, st);
+    memset(fwd, 0, 8);
+    memset(rev, 0, 8);
+    for (size_t k = 0; k < nb; ++k) {
+        int idx = b[k] == 'A' ? 0 : b[k] == 'C' ? 1 : b[k] == 'G' ? 2 : 3;
+        if (st[k]) ++fwd[idx]; else ++rev[idx];
+    }
+    free(b);
+    free(st);
+    return nb;
+}
+static size_t read_bases(const char* s, char reference, uint16_t counts[4], char* bases_out, uint8_t* strands_out) {
     size_t nb = 0;
     counts[0] = counts[1] = counts[2] = counts[3] = 0;
     size_t len = strlen(s);
@@ -48,6 +69,7 @@ size_t orc_parse_read_bases(const char* s, char reference, uint16_t counts[4], c
         }
         if (idx >= 0) {
             if (bases_out) bases_out[nb] = "ACGT"[idx];
+            if (strands_out) strands_out[nb] = (base >= 'A' && base <= 'Z') ? 1 : 0;     /* :85-124: the upper-case cases push 1 */
             ++nb;
             ++counts[idx];                       /* uint16_t: wraps mod 65536 like the reference */
         }

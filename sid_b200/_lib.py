@@ -105,6 +105,7 @@ PROTOTYPES = {
     "sidgpu_lr_test": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, c_u64, ctypes.c_void_p]),
     "sidgpu_profile_loglik": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, c_u64, c_double_p, ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p]),
     "sidgpu_qualities": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, c_u64_p]),
+    "sidgpu_strand_counts": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, c_u64, ctypes.c_void_p, ctypes.c_void_p]),
     "sidgpu_read_counts": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, c_u64, ctypes.c_int, ctypes.c_int,
                                           ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "sidgpu_read_fill": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, c_u64, ctypes.c_void_p,

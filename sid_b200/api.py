@@ -136,13 +136,24 @@ class Context:
         return {k: (ms[i], n[i]) for i, k in enumerate(("tokenize", "classify", "csv", "order", "fit", "histogram", "quality"))}
 
     # ---- K1
-    def tokenize(self, d_text, text_len, begin=0, end=None, want_qual=False):
-        """parsePileupLine/parseReadBases over device text; results copied back as numpy arrays."""
+    def tokenize(self, d_text, text_len, begin=0, end=None, want_qual=False, strands=False):
+        """parsePileupLine/parseReadBases over device text; results copied back as numpy arrays.
+        strands: also the per-strand profiles of every site ("fwd", "rev": packed like "profile", fwd + rev == profile;
+        the strands of pileup.hpp:15 summed per site)."""
         end = text_len if end is None else end
         v = SitesView()
         ptr = d_text.ptr if isinstance(d_text, DeviceBuffer) else d_text
-        self._ck(self.lib.sidgpu_tokenize(self.h, ptr, text_len, begin, end, 1 if want_qual else 0, ctypes.byref(v)))
+        self._ck(self.lib.sidgpu_tokenize(self.h, ptr, text_len, begin, end, 1 if want_qual else (2 if strands else 0), ctypes.byref(v)))
         n = v.n_sites
+        fwd = rev = None
+        if strands:
+            buf = DeviceBuffer(self, max(16, 16 * n))
+            try:
+                self._ck(self.lib.sidgpu_strand_counts(self.h, ptr, text_len, v.d_line_off, n, buf.ptr, buf.ptr + 8 * n))
+                both = buf.download(np.uint64, 2 * n)
+                fwd, rev = both[:n].copy(), both[n:].copy()
+            finally:
+                buf.free()
         names_pool = self._download(v.d_names, np.uint8, v.names_bytes).tobytes()
         refs = self._download(v.d_name_ref, np.uint32, n)
         cache = {}
@@ -158,7 +169,9 @@ class Context:
             "profile": self._download(v.d_profile, np.uint64, n),
             "pos": self._download(v.d_pos, np.int32, n),
             "slot": self._download(v.d_slot, np.uint32, n),
-            "line_off": self._download(v.d_line_off, np.uint64, n) if want_qual else None,
+            "line_off": self._download(v.d_line_off, np.uint64, n) if (want_qual or strands) else None,
+            "fwd": fwd,
+            "rev": rev,
             "chrom": [name_of(int(r)) for r in refs],
         }
 

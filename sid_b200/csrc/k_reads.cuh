@@ -76,6 +76,34 @@ __global__ void k_read_fill(const uint8_t* text, uint64_t text_len, const uint64
     if (mq && pl.status != LINE_MISSING_MAPQ) for (uint32_t k = 0; k < pl.mq_len; ++k) mq[mq_off[i] + k] = (uint8_t)phred_of(src.at(p + pl.mq_off + k));
 }
 
+// Per-strand profiles of every line (the strands parseReadBases derives and nobody reads, pileup.hpp:15,
+// pileup.cpp:87-123): the counted bases of the upper-case characters ('.' included) and of the lower-case ones (',' included),
+// packed like the profile (A | C<<16 | G<<32 | T<<48, each count mod 65536); fwd + rev is the line's profile, lane by lane.
+__global__ void k_strand_counts(const uint8_t* text, uint64_t text_len, const uint64_t* line_off, uint64_t n, unsigned long long* fwd,
+                                unsigned long long* rev, unsigned long long* error) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    FlatSrc src {text, text_len};
+    ParsedLine pl;
+    const uint64_t p = line_off[i];
+    parse_line(src, p, false, pl);
+    uint32_t c[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+    if (pl.status != LINE_OK) atomicMin(error, (unsigned long long)((p << 3) | (uint64_t)LINE_MALFORMED));
+    else {
+        BasesState st;
+        st.init((uint8_t)pl.ref);
+        for (uint32_t k = 0; k < pl.bases_len; ++k) {
+            const uint8_t ch = src.at(p + pl.bases_off + k);
+            const int idx = st.feed(ch);
+            if (idx < 0) continue;
+            const uint8_t seen = ch == '.' ? st.dot_as : ch == ',' ? st.comma_as : ch;      // pileup.cpp:78-83
+            ++c[(seen & 0x20u) ? 1 : 0][idx];
+        }
+    }
+    if (fwd) fwd[i] = pack_profile(c[0][0], c[0][1], c[0][2], c[0][3]);
+    if (rev) rev[i] = pack_profile(c[1][0], c[1][1], c[1][2], c[1][3]);
+}
+
 // parseQualities of one string: stops at NUL, tab or line end (pileup.cpp:158).  One block.
 __global__ void __launch_bounds__(256) k_qualities(const uint8_t* q, uint64_t n, uint8_t* out, unsigned long long* n_out) {
     __shared__ unsigned long long s_end;

@@ -1032,6 +1032,22 @@ int sidgpu_read_fill(sidgpu_ctx* ctx, const char* d_text, size_t text_len, const
     return SIDGPU_OK;
 }
 
+int sidgpu_strand_counts(sidgpu_ctx* ctx, const char* d_text, size_t text_len, const uint64_t* d_line_off, uint64_t n_lines, uint64_t* d_fwd,
+                         uint64_t* d_rev) {
+    if (!ctx || (n_lines && (!d_text || !d_line_off))) return SIDGPU_EINVAL;
+    CK(cudaSetDevice(ctx->device));
+    if (n_lines == 0) return SIDGPU_OK;
+    CK(cudaMemsetAsync(ctl_field(ctx, &Control::error), 0xFF, sizeof(unsigned long long), ctx->stream));
+    k_strand_counts<<<(unsigned)((n_lines + 127) / 128), 128, 0, ctx->stream>>>((const uint8_t*)d_text, text_len, d_line_off, n_lines,
+                                                                                (unsigned long long*)d_fwd, (unsigned long long*)d_rev,
+                                                                                ctl_field(ctx, &Control::error));
+    TRY(check_launch(ctx, "k_strand_counts"));
+    TRY(sync_ctl(ctx));
+    if (ctx->h_ctl->error != ~0ull)
+        return ctx->fail(SIDGPU_EMALFORMED, "%s (line starting at byte %llu)", status_text((int)(ctx->h_ctl->error & 7)), ctx->h_ctl->error >> 3);
+    return SIDGPU_OK;
+}
+
 int sidgpu_profile_loglik(sidgpu_ctx* ctx, const uint64_t* d_profiles, uint64_t n, const double nd[4], double eps, double* d_log_hom,
                           double* d_log_het) {
     if (!ctx || !nd || (n && (!d_profiles || !d_log_hom || !d_log_het))) return SIDGPU_EINVAL;
@@ -1267,7 +1283,8 @@ int sidgpu_tokenize(sidgpu_ctx* ctx, const char* d_text, size_t text_len, size_t
     TRY(reset_table(ctx));
     TRY(reset_names(ctx));
     uint64_t n = 0;
-    TRY(run_tokenizer(ctx, d_text, text_len, range_begin, range_end, want_qual != 0, true, 0, false, &n, true));
+    // want_qual 2: the line offsets without the quality columns (a six-column file stays valid)
+    TRY(run_tokenizer(ctx, d_text, text_len, range_begin, range_end, want_qual == 1, true, 0, false, &n, true));
     ctx->n_sites_total = n;
     ctx->chunk_begin = 0;
     ctx->chunk_sites = n;

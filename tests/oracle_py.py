@@ -45,6 +45,8 @@ def oracle():
         o.orc_free_result.argtypes = [ctypes.POINTER(_Res)]
         o.orc_parse_read_bases.restype = ctypes.c_size_t
         o.orc_parse_read_bases.argtypes = [ctypes.c_char_p, ctypes.c_char, ctypes.POINTER(ctypes.c_uint16), ctypes.c_char_p]
+        o.orc_strand_counts.restype = ctypes.c_size_t
+        o.orc_strand_counts.argtypes = [ctypes.c_char_p, ctypes.c_char, ctypes.POINTER(ctypes.c_uint16), ctypes.POINTER(ctypes.c_uint16)]
         o.orc_parse_qualities.restype = ctypes.c_size_t
         o.orc_parse_qualities.argtypes = [ctypes.c_char_p, ctypes.c_char_p]
         o.orc_lrt.restype = ctypes.c_double
@@ -109,6 +111,23 @@ def oracle_call(text, method="local", estimate_prior=False, prior=-1.0, error_th
         }
     finally:
         o.orc_free_result(ctypes.byref(r))
+
+
+def oracle_strand_counts(text):
+    """Per line of a well-formed pileup text: (fwd, rev) packed like profiles (ReadStack::strands summed by letter)."""
+    o = oracle()
+    fwd, rev = [], []
+    f4, r4 = (ctypes.c_uint16 * 4)(), (ctypes.c_uint16 * 4)()
+    for line in text.split(b"\n"):
+        if not line:
+            continue
+        col = line.replace(b" ", b"\t").split(b"\t")
+        col = [c for c in col if c]
+        o.orc_strand_counts(col[4], col[2][:1], f4, r4)
+        fwd.append(list(f4))
+        rev.append(list(r4))
+    n = len(fwd)
+    return (pack_profiles(np.array(fwd, dtype=np.uint16).reshape(n, 4)), pack_profiles(np.array(rev, dtype=np.uint16).reshape(n, 4)))
 
 
 def make_unique(profiles_packed, counts):

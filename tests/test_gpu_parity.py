@@ -37,6 +37,34 @@ def test_tokenizer_bit_exact(native, gpu_ctx, name):
     assert got["chrom"] == want["chrom"]
 
 
+@pytest.mark.parametrize("name", ["edge.plp", "depth30.plp", "depth500.plp", "depth5.plp", "quality30.plp", "fuzz"])
+def test_strand_counts(native, gpu_ctx, name):
+    """SURVEY.md 8f row 4: ReadStack::strands (pileup.hpp:15, pileup.cpp:87-123) summed per site and letter; six-column
+    files included (the quality columns are not looked at), and the reference-character substitution of pileup.cpp:78-83."""
+    if name == "fuzz":
+        import random
+        rnd = random.Random(5)
+        lines = []
+        for k in range(5000):
+            ln = rnd.choice([1, 2, 5, 12, 31, 32, 33, 64, 70, 300])
+            bases = "".join(rnd.choice(".,.,.,ACGTacgtNn*$^+-0123456789<>") for _ in range(ln))
+            lines.append("c\t%d\t%s\t%d\t%s\t%s" % (k + 1, rnd.choice("ACGTacgtNn*.,^+-$1x"), ln, bases, "I" * ln))
+        text = ("\n".join(lines) + "\n").encode()
+    else:
+        text = read(name)
+    want_fwd, want_rev = op.oracle_strand_counts(text)
+    d = gpu_ctx.upload_text(text)
+    try:
+        got = gpu_ctx.tokenize(d, len(text), strands=True)
+    finally:
+        d.free()
+    assert got["n_sites"] == len(want_fwd)
+    assert np.array_equal(got["fwd"], want_fwd) and np.array_equal(got["rev"], want_rev)
+    # fwd + rev is the profile, count by count (mod 65536 like profile_t)
+    f, r, p = op.unpack_profiles(got["fwd"]), op.unpack_profiles(got["rev"]), op.unpack_profiles(got["profile"])
+    assert np.array_equal((f + r).astype(np.uint16), p)
+
+
 @pytest.mark.parametrize("seed", [21, 22])
 def test_tokenizer_on_adversarial_valid_lines(native, gpu_ctx, seed):
     """Odd but well-formed lines (control bytes and high bytes in names, doubled delimiters, '^^', signs without

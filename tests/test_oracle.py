@@ -43,6 +43,16 @@ def counts(bases, ref):
     return list(c)
 
 
+def test_strands_reference_vector():
+    """test/test-pileup_parser.cpp:23-35: "AgACgt" has strands 1,0,1,1,0,0."""
+    o = op.oracle()
+    f, r = (ctypes.c_uint16 * 4)(), (ctypes.c_uint16 * 4)()
+    assert o.orc_strand_counts(b"AgACgt", b"N", f, r) == 6
+    assert list(f) == [2, 1, 0, 0] and list(r) == [0, 0, 2, 1]
+    assert o.orc_strand_counts(b".,.,^,.-2aa,", b"t", f, r) == 6              # '.' forward, ',' reverse; "^," and the deletion skipped
+    assert list(f) == [0, 0, 0, 3] and list(r) == [0, 0, 0, 3]
+
+
 # test/test-profiles.cpp:16-55
 @pytest.mark.parametrize("bases,ref,want", [
     ("aA", "n", [2, 0, 0, 0]), ("cC", "n", [0, 2, 0, 0]), ("gG", "n", [0, 0, 2, 0]), ("tT", "n", [0, 0, 0, 2]),
