@@ -79,3 +79,5 @@ SidRunInfo sidCallToStreamSharded(const std::string& method, const char* text, s
 // Only rows labelled "het" from now on: the `grep ',het,'` of scripts/sid-pipeline/run-sid.sh:16-17 done
 // before the rows leave the GPU.  Applies to sidCallToStream and to the four call* functions.
 void sidSetHetOnly(bool het_only);
+// BGZF input (sidCallFile): true = its members are inflated by the host's threads (host/bgzf.hpp), false (default) = on the device.
+void sidSetHostInflate(bool on);

@@ -6,7 +6,9 @@
 // the header line is kept).  With one GPU the input streams through pinned chunks and the rows are written as they
 // arrive (sidCallFile): memory use does not grow with the file.  A gzip-compressed input (as the pipeline stores its
 // pileups, scripts/prepare-data.sh:14) is inflated on the fly, under the GPU work, instead of `zcat` to a temporary
-// file (scripts/sid-pipeline/run-sid.sh:15).
+// file (scripts/sid-pipeline/run-sid.sh:15): a plain gzip stream by zlib on the reader thread; a blocked one (BGZF, what
+// `bgzip` writes) on the device, one warp per member, so that only the compressed bytes cross the link (--host-inflate:
+// by the reader's threads instead, host/bgzf.hpp).
 #include <fcntl.h>
 #include <getopt.h>
 #include <sys/mman.h>
@@ -47,10 +49,10 @@ int main(int argc, char** argv) {
     GlobalOptions o;
     int device = 0;
     size_t chunk_mb = 0;
-    bool het_only = false;
+    bool het_only = false, host_inflate = false;
     std::vector<int> devices;
     int read_threads = (int)std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
-    static const option LONG[] = {{"device", required_argument, nullptr, 1000}, {"chunk-mb", required_argument, nullptr, 1001}, {"het-only", no_argument, nullptr, 1002}, {"devices", required_argument, nullptr, 1003}, {"read-threads", required_argument, nullptr, 1004}, {nullptr, 0, nullptr, 0}};
+    static const option LONG[] = {{"device", required_argument, nullptr, 1000}, {"chunk-mb", required_argument, nullptr, 1001}, {"het-only", no_argument, nullptr, 1002}, {"devices", required_argument, nullptr, 1003}, {"read-threads", required_argument, nullptr, 1004}, {"host-inflate", no_argument, nullptr, 1005}, {nullptr, 0, nullptr, 0}};
     int flag;
     while ((flag = getopt_long(argc, argv, "E:Rhm:p:r:", LONG, nullptr)) != -1) {      // optstring as built by sid.cpp:60-69
         switch (flag) {
@@ -64,6 +66,7 @@ int main(int argc, char** argv) {
             case 1001: chunk_mb = (size_t)atol(optarg); break;
             case 1002: het_only = true; break;
             case 1004: read_threads = std::max(1, atoi(optarg)); break;
+            case 1005: host_inflate = true; break;
             case 1003:
                 for (const char* q = optarg; *q;) {
                     devices.push_back(atoi(q));
@@ -97,6 +100,7 @@ int main(int argc, char** argv) {
         if (devices.size() == 1) device = devices[0];
         sidSetDevice(device, chunk_mb << 20);
         sidSetHetOnly(het_only);
+        sidSetHostInflate(host_inflate);
         if (devices.size() > 1) {
             // one position shard per GPU: the shards are cut from the whole text, which therefore has to be in memory
             if (gz) {

@@ -29,6 +29,7 @@ namespace {
 int g_device = 0;
 size_t g_chunk = 0;
 bool g_het_only = false;
+bool g_host_inflate = false;         // BGZF input: inflate on the host threads (bgzf.hpp) instead of on the device
 
 struct Ctx {
     sidgpu_ctx* h = nullptr;
@@ -225,6 +226,7 @@ void sidSetDevice(int device, size_t max_chunk_bytes) {
 }
 
 void sidSetHetOnly(bool het_only) { g_het_only = het_only; }
+void sidSetHostInflate(bool on) { g_host_inflate = on; }
 
 // ---- call.hpp:40-43 ------------------------------------------------------------------------------
 std::vector<OutputRecord> callSiteMLError(std::istream& in, const bool estimate_prior, double prior, double error_threshold,
@@ -534,12 +536,20 @@ SidRunInfo sidCallFile(const std::string& method, int fd_in, bool gzip, bool est
         return info;
     }
     std::unique_ptr<bgzf::Reader> blocks;
+    bool device_inflate = false;
     if (gzip) {
         unsigned char head[64];
         const ssize_t got = pread(fd_in, head, sizeof head, 0);       // fails on a pipe: plain gzip stream then
         if (got >= 18 && bgzf::looks_like(head, (size_t)got)) {
-            blocks.reset(new bgzf::Reader(fd_in, f.threads));
-            f.blocks = blocks.get();
+            if (g_host_inflate) {
+                blocks.reset(new bgzf::Reader(fd_in, f.threads));
+                f.blocks = blocks.get();
+            } else {
+                // the file's own bytes go to the device (parallel preads like a plain text file); it inflates the members
+                device_inflate = true;
+                f.gzip = false;
+                f.seekable = true;
+            }
         } else {
             f.gz = gzdopen(dup(fd_in), "rb");
             if (!f.gz) throw std::runtime_error("could not open the gzip stream");
@@ -558,7 +568,8 @@ SidRunInfo sidCallFile(const std::string& method, int fd_in, bool gzip, bool est
     const auto t0 = std::chrono::steady_clock::now();
     sidgpu_ctx* h = ctx().h;                        // creates the ctx on first use: CUDA context, kernels, tables
     const auto t1 = std::chrono::steady_clock::now();
-    const int rc = sidgpu_call_io(h, &p, &io, &bytes, &info.n_sites, &info.n_rows);
+    const int rc = device_inflate ? sidgpu_call_io_bgzf(h, &p, &io, &bytes, &info.n_sites, &info.n_rows)
+                                  : sidgpu_call_io(h, &p, &io, &bytes, &info.n_sites, &info.n_rows);
     const auto t2 = std::chrono::steady_clock::now();
     if (getenv("SID_TIMING")) {                     // where the wall clock and the memory of a run go (bench.py cli_e2e)
         long hwm_kb = -1;                           // VmHWM of this process image (ru_maxrss would carry the parent's peak over fork)

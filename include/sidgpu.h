@@ -151,6 +151,30 @@ int sidgpu_read_fill(sidgpu_ctx* ctx, const char* d_text, size_t text_len, const
                      uint8_t* d_strands, uint8_t* d_bq, uint8_t* d_mq);
 
 /* ------------------------------------------------------------------------------------------------
+ * BGZF input inflated on the device (the pipeline stores its pileups gzipped, scripts/prepare-data.sh:14,
+ * and `zcat`s them to a temporary file on one core, scripts/sid-pipeline/run-sid.sh:15).  A BGZF file (`bgzip`) is a
+ * series of independent gzip members of at most 64 KiB of text; only the compressed bytes cross the link.
+ *   sidgpu_bgzf_scan     host only: walks the member headers of h_comp[0, len) and lists the members whose text fits
+ *                        text_cap (offsets relative to h_comp and to the start of the text); *consumed = bytes of the
+ *                        whole members it accepted (a member cut by `len` is left for the next call), *text_bytes =
+ *                        their text.  SIDGPU_EINVAL for bytes that are not a BGZF member header.
+ *   sidgpu_inflate_bgzf  inflates the listed members of the device buffer d_comp (4-byte aligned, readable 8 bytes
+ *                        past comp_len) into d_text, one warp per member; checks every member against its ISIZE (not its
+ *                        CRC-32); SIDGPU_EINVAL with the member's index in sidgpu_last_error for a damaged member.
+ *   sidgpu_call_io_bgzf  sidgpu_call_io for a BGZF file: the read callback delivers the FILE's bytes (compressed).
+ * --------------------------------------------------------------------------------------------- */
+typedef struct {
+    uint64_t c_off;    /* offset of the member's deflate stream in the compressed buffer */
+    uint64_t out_off;  /* offset of its text in the text buffer */
+    uint32_t c_len;    /* bytes of the deflate stream */
+    uint32_t isize;    /* bytes of text */
+} sidgpu_bgzf_block;
+int sidgpu_bgzf_scan(const void* h_comp, size_t len, sidgpu_bgzf_block* blocks, size_t max_blocks, size_t text_cap,
+                     size_t* n_blocks, size_t* consumed, size_t* text_bytes);
+int sidgpu_inflate_bgzf(sidgpu_ctx* ctx, const void* d_comp, size_t comp_len, const sidgpu_bgzf_block* h_blocks, size_t n_blocks,
+                        char* d_text, size_t text_cap);
+
+/* ------------------------------------------------------------------------------------------------
  * Calling sessions: the four functions of call.hpp:40-43, streamed.
  *
  *   sidgpu_begin(params)
@@ -247,6 +271,8 @@ typedef struct {
 } sidgpu_io;
 int sidgpu_call_io(sidgpu_ctx* ctx, const sidgpu_params* params, const sidgpu_io* io, uint64_t* csv_bytes,
                    uint64_t* n_sites, uint64_t* n_rows);
+int sidgpu_call_io_bgzf(sidgpu_ctx* ctx, const sidgpu_params* params, const sidgpu_io* io, uint64_t* csv_bytes,
+                        uint64_t* n_sites, uint64_t* n_rows);
 
 /* ------------------------------------------------------------------------------------------------
  * K3: unique-profile histogram   (countUniqueProfiles pileup.cpp:169-196,

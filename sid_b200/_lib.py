@@ -51,6 +51,10 @@ IO_WRITE = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctyp
 IO_REWIND = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p)
 
 
+class BgzfBlock(ctypes.Structure):
+    _fields_ = [("c_off", ctypes.c_uint64), ("out_off", ctypes.c_uint64), ("c_len", ctypes.c_uint32), ("isize", ctypes.c_uint32)]
+
+
 class Io(ctypes.Structure):                  # sidgpu_io
     _fields_ = [("read", IO_READ), ("write", IO_WRITE), ("rewind", IO_REWIND), ("user", ctypes.c_void_p)]
 
@@ -89,6 +93,10 @@ PROTOTYPES = {
     "sidgpu_call_host": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(Params), ctypes.c_void_p, ctypes.c_size_t,
                                         ctypes.c_void_p, ctypes.c_size_t, c_u64_p, c_u64_p, c_u64_p]),
     "sidgpu_call_io": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(Params), ctypes.POINTER(Io), c_u64_p, c_u64_p, c_u64_p]),
+    "sidgpu_call_io_bgzf": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(Params), ctypes.POINTER(Io), c_u64_p, c_u64_p, c_u64_p]),
+    "sidgpu_bgzf_scan": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t,
+                                        ctypes.POINTER(ctypes.c_size_t), ctypes.POINTER(ctypes.c_size_t), ctypes.POINTER(ctypes.c_size_t)]),
+    "sidgpu_inflate_bgzf": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t]),
     "sidgpu_histogram": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint32, ctypes.POINTER(UniqueView)]),
     "sidgpu_count_unique": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, c_u64, ctypes.c_uint32, ctypes.POINTER(UniqueView)]),
     "sidgpu_count_unique_weighted": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, c_u64, ctypes.c_uint32,

@@ -394,9 +394,36 @@ class Context:
             return out[:nb.value].tobytes(), ns.value, nr.value
 
 
-    def call_io(self, reader, writer, params, rewind=None):
+    def bgzf_scan(self, comp, text_cap=1 << 62, max_blocks=None):
+        """Member table of BGZF bytes (host only): (blocks array, consumed bytes, text bytes)."""
+        buf = np.frombuffer(comp, dtype=np.uint8)
+        cap = max_blocks or (len(comp) // 28 + 1)
+        blocks = (_lib.BgzfBlock * cap)()
+        n, used, tb = ctypes.c_size_t(), ctypes.c_size_t(), ctypes.c_size_t()
+        self._ck(self.lib.sidgpu_bgzf_scan(buf.ctypes.data if len(comp) else None, len(comp), blocks, cap, text_cap,
+                                           ctypes.byref(n), ctypes.byref(used), ctypes.byref(tb)))
+        return blocks, n.value, used.value, tb.value
+
+    def inflate_bgzf(self, comp):
+        """BGZF bytes -> their text, inflated on the device (one warp per member)."""
+        blocks, n, used, tb = self.bgzf_scan(comp)
+        if used != len(comp):
+            raise ValueError("truncated BGZF member")
+        d_comp = DeviceBuffer(self, ((len(comp) + 15) & ~15) + 16)
+        d_text = DeviceBuffer(self, tb + 16)
+        try:
+            if len(comp):
+                d_comp.upload(np.frombuffer(comp, dtype=np.uint8))
+            self._ck(self.lib.sidgpu_inflate_bgzf(self.h, d_comp.ptr, len(comp), blocks, n, d_text.ptr, tb))
+            return d_text.download(np.uint8, tb).tobytes()
+        finally:
+            d_comp.free()
+            d_text.free()
+
+    def call_io(self, reader, writer, params, rewind=None, bgzf=False):
         """The streaming host path (sidgpu_call_io): `reader(n)` returns up to n bytes of pileup text (b"" at the
         end), `writer(rows)` receives CSV rows in file order, `rewind()` restarts the input (quality with -R).
+        bgzf: the reader delivers the bytes of a BGZF file; its members are inflated on the device (sidgpu_call_io_bgzf).
         Returns (csv_bytes, n_sites, n_rows)."""
         failure = []
 
@@ -428,7 +455,8 @@ class Context:
 
         io = _lib.Io(_lib.IO_READ(c_read), _lib.IO_WRITE(c_write), _lib.IO_REWIND(c_rewind) if rewind else _lib.IO_REWIND(), None)
         nb, ns, nr = ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_uint64()
-        rc = self.lib.sidgpu_call_io(self.h, ctypes.byref(params), ctypes.byref(io), ctypes.byref(nb), ctypes.byref(ns), ctypes.byref(nr))
+        call = self.lib.sidgpu_call_io_bgzf if bgzf else self.lib.sidgpu_call_io
+        rc = call(self.h, ctypes.byref(params), ctypes.byref(io), ctypes.byref(nb), ctypes.byref(ns), ctypes.byref(nr))
         if failure:
             raise failure[0]
         self._ck(rc)

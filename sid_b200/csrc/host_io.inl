@@ -20,7 +20,18 @@ struct IoPipe {
     sidgpu_ctx* ctx;
     const sidgpu_io* io;
     size_t slot_cap = 0;
-    struct TextSlot { char* p = nullptr; size_t cap = 0, len = 0; } ts[NT];
+    struct TextSlot {
+        char* p = nullptr;
+        size_t cap = 0, len = 0;
+        // BGZF input (bgzf = true): the slot holds compressed members; their table (pinned) and the bytes of text they inflate to
+        sidgpu_bgzf_block* blocks = nullptr;
+        size_t n_blocks = 0, text_len = 0;
+        bool last = false;
+    } ts[NT];
+    bool bgzf = false;                      // the read callback delivers a BGZF file: members are inflated on the device
+    static constexpr size_t MAX_BLOCKS = (size_t)1 << 16;
+    size_t text_cap = 0;                    // bgzf: text bytes one chunk may inflate to
+    size_t tail[2] = {0, 0};                // bgzf: bytes of an unfinished line already at the front of hp_text[b]
     struct CsvSlot { char* p = nullptr; size_t cap = 0, len = 0; cudaEvent_t ev = nullptr; } cs[NC];
     std::mutex m;
     std::condition_variable cv;
@@ -42,7 +53,7 @@ struct IoPipe {
 
     // ---- reader thread: one pass over the input
     void reader() {
-        bool input_done = false;
+        bool input_done = false, src_eof = false;
         while (!input_done) {
             uint64_t k;
             {
@@ -53,6 +64,37 @@ struct IoPipe {
             }
             TextSlot& s = ts[k % NT];
             size_t have = 0;
+            if (bgzf) {
+                // whole members only: what the header walk does not accept opens the next slot
+                if (!carry.empty()) { memcpy(s.p, carry.data(), carry.size()); have = carry.size(); carry.clear(); }
+                while (have < s.cap && !src_eof) {
+                    const int64_t got = io->read(io->user, s.p + have, s.cap - have);
+                    if (got < 0) { set_error(SIDGPU_EINVAL, "read callback failed"); return; }
+                    if (got == 0) src_eof = true;
+                    have += (size_t)got;
+                }
+                size_t consumed = 0;
+                if (sidgpu_bgzf_scan(s.p, have, s.blocks, MAX_BLOCKS, text_cap, &s.n_blocks, &consumed, &s.text_len) != SIDGPU_OK) {
+                    set_error(SIDGPU_EINVAL, "not a BGZF file (bad member header)");
+                    return;
+                }
+                if (consumed == 0 && have > 0) {
+                    // a full slot always holds whole members (they are at most 64 KiB); at the end of the file it is a cut one
+                    set_error(SIDGPU_EINVAL, src_eof ? "truncated BGZF member at the end of the file" : "BGZF member larger than a slot");
+                    return;
+                }
+                carry.assign(s.p + consumed, s.p + have);
+                s.len = consumed;
+                input_done = src_eof && carry.empty();
+                s.last = input_done;
+                {
+                    std::lock_guard<std::mutex> g(m);
+                    ++t_prod;
+                    if (input_done) eof = true;
+                }
+                cv.notify_all();
+                continue;
+            }
             for (;;) {
                 if (carry.size() + 16 > s.cap || have == s.cap) {
                     // a single line longer than the slot: grow it (pinned memory; this is rare)
@@ -133,9 +175,42 @@ struct IoPipe {
     int upload(uint64_t i) {
         const int b = (int)(i & 1);
         TextSlot& s = ts[i % NT];
+        if (bgzf) {                                                 // the compressed members and their table
+            TRY(ensure(ctx, ctx->hp_comp[b], ((s.len + 15) & ~(size_t)15) + 16));
+            TRY(ensure(ctx, ctx->inf_blocks[b], std::max<size_t>(1, s.n_blocks) * sizeof(sidgpu_bgzf_block)));
+            if (s.len) CK(cudaMemcpyAsync(ctx->hp_comp[b].p, s.p, s.len, cudaMemcpyHostToDevice, ctx->copy_in));
+            if (s.n_blocks) CK(cudaMemcpyAsync(ctx->inf_blocks[b].p, s.blocks, s.n_blocks * sizeof(sidgpu_bgzf_block), cudaMemcpyHostToDevice, ctx->copy_in));
+            CK(cudaEventRecord(ev_in[b], ctx->copy_in));
+            return SIDGPU_OK;
+        }
         TRY(ensure(ctx, ctx->hp_text[b], ((s.len + 15) & ~(size_t)15) + 16));
         if (s.len) CK(cudaMemcpyAsync(ctx->hp_text[b].p, s.p, s.len, cudaMemcpyHostToDevice, ctx->copy_in));
         CK(cudaEventRecord(ev_in[b], ctx->copy_in));
+        return SIDGPU_OK;
+    }
+
+    // bgzf: inflates the members of slot i behind the unfinished line the chunk before left in hp_text[b]; *keep = bytes
+    // of whole lines (everything for the last chunk); what follows them opens the other buffer
+    int inflate_chunk(uint64_t i, int b, size_t* keep) {
+        TextSlot& s = ts[i % NT];
+        const size_t t0 = tail[b], total = t0 + s.text_len;
+        TRY(ensure(ctx, ctx->hp_text[b], ((total + 15) & ~(size_t)15) + 32, t0 != 0));
+        TRY(launch_inflate(ctx, (const uint8_t*)ctx->hp_comp[b].p, (const sid::BgzfBlock*)ctx->inf_blocks[b].p, s.n_blocks,
+                           (uint8_t*)ctx->hp_text[b].p + t0));
+        const bool cut = !s.last && total != 0;
+        if (cut) {
+            k_last_line_end<<<1, 256, 0, ctx->stream>>>((const uint8_t*)ctx->hp_text[b].p, total, ctl_field(ctx, &Control::csv_bytes));
+            TRY(check_launch(ctx, "k_last_line_end"));
+        }
+        TRY(sync_ctl(ctx));
+        TRY(inflate_failed(ctx));
+        *keep = cut ? (size_t)ctx->h_ctl->csv_bytes : total;
+        const size_t rest = total - *keep;
+        tail[b ^ 1] = rest;
+        if (rest) {
+            TRY(ensure(ctx, ctx->hp_text[b ^ 1], ((rest + text_cap + 15) & ~(size_t)15) + 32));
+            CK(cudaMemcpyAsync(ctx->hp_text[b ^ 1].p, (const char*)ctx->hp_text[b].p + *keep, rest, cudaMemcpyDeviceToDevice, ctx->stream));
+        }
         return SIDGPU_OK;
     }
 
@@ -189,6 +264,7 @@ struct IoPipe {
             t_prod = t_cons = 0;
             eof = false;
             carry.clear();
+            tail[0] = tail[1] = 0;
         }
         std::thread rd([this] { reader(); });
         int rc = SIDGPU_OK;
@@ -206,8 +282,12 @@ struct IoPipe {
                 uploaded = i + 2;
             }
             const int b = (int)(i & 1);
-            const size_t len = ts[i % NT].len;
+            size_t len = ts[i % NT].len;
             if (cudaStreamWaitEvent(ctx->stream, ev_in[b], 0) != cudaSuccess) { rc = ctx->fail(SIDGPU_ECUDA, "cudaStreamWaitEvent failed"); break; }
+            if (bgzf) {
+                rc = inflate_chunk(i, b, &len);
+                if (rc != SIDGPU_OK) break;
+            }
             uint64_t n = 0;
             if (len) {
                 if (emit) rc = rows_of_chunk(b, (const char*)ctx->hp_text[b].p, len, &n);
@@ -246,9 +326,11 @@ struct IoPipe {
 
     int init() {
         slot_cap = std::min<size_t>(ctx->max_chunk, (size_t)64 << 20);      // the text slots are pinned: three of 64 MiB at most
+        text_cap = std::max<size_t>(4 * slot_cap, (size_t)1 << 17);
         for (int i = 0; i < NT; ++i) {
-            ts[i].cap = slot_cap;
+            ts[i].cap = bgzf ? std::max<size_t>(slot_cap, (size_t)1 << 17) : slot_cap;
             CK(cudaHostAlloc((void**)&ts[i].p, ts[i].cap, cudaHostAllocDefault));
+            if (bgzf) CK(cudaHostAlloc((void**)&ts[i].blocks, MAX_BLOCKS * sizeof(sidgpu_bgzf_block), cudaHostAllocDefault));
         }
         for (int i = 0; i < NC; ++i) CK(cudaEventCreateWithFlags(&cs[i].ev, cudaEventDisableTiming));
         for (int i = 0; i < 2; ++i) {
@@ -258,7 +340,7 @@ struct IoPipe {
         return SIDGPU_OK;
     }
     void destroy() {
-        for (int i = 0; i < NT; ++i) if (ts[i].p) cudaFreeHost(ts[i].p);
+        for (int i = 0; i < NT; ++i) { if (ts[i].p) cudaFreeHost(ts[i].p); if (ts[i].blocks) cudaFreeHost(ts[i].blocks); }
         for (int i = 0; i < NC; ++i) { if (cs[i].p) cudaFreeHost(cs[i].p); if (cs[i].ev) cudaEventDestroy(cs[i].ev); }
         for (int i = 0; i < 2; ++i) { if (ev_in[i]) cudaEventDestroy(ev_in[i]); if (ev_out[i]) cudaEventDestroy(ev_out[i]); }
     }
@@ -266,14 +348,15 @@ struct IoPipe {
 
 }  // namespace
 
-extern "C" int sidgpu_call_io(sidgpu_ctx* ctx, const sidgpu_params* params, const sidgpu_io* io, uint64_t* csv_bytes, uint64_t* n_sites,
-                              uint64_t* n_rows) {
+static int call_io(sidgpu_ctx* ctx, const sidgpu_params* params, const sidgpu_io* io, bool bgzf, uint64_t* csv_bytes, uint64_t* n_sites,
+                   uint64_t* n_rows) {
     if (!ctx || !params || !io || !io->read || !io->write) return SIDGPU_EINVAL;
-    Range nvtx_range("sidgpu_call_io");
+    Range nvtx_range(bgzf ? "sidgpu_call_io_bgzf" : "sidgpu_call_io");
     CK(cudaSetDevice(ctx->device));
     IoPipe pipe;
     pipe.ctx = ctx;
     pipe.io = io;
+    pipe.bgzf = bgzf;
     int rc = pipe.init();
     std::thread wr;
     if (rc == SIDGPU_OK) wr = std::thread([&pipe] { pipe.writer(); });
@@ -307,4 +390,14 @@ extern "C" int sidgpu_call_io(sidgpu_ctx* ctx, const sidgpu_params* params, cons
     if (n_sites) *n_sites = pipe.total_sites;
     if (n_rows) *n_rows = pipe.total_rows;
     return rc;
+}
+
+extern "C" int sidgpu_call_io(sidgpu_ctx* ctx, const sidgpu_params* params, const sidgpu_io* io, uint64_t* csv_bytes, uint64_t* n_sites,
+                              uint64_t* n_rows) {
+    return call_io(ctx, params, io, false, csv_bytes, n_sites, n_rows);
+}
+
+extern "C" int sidgpu_call_io_bgzf(sidgpu_ctx* ctx, const sidgpu_params* params, const sidgpu_io* io, uint64_t* csv_bytes, uint64_t* n_sites,
+                                   uint64_t* n_rows) {
+    return call_io(ctx, params, io, true, csv_bytes, n_sites, n_rows);
 }

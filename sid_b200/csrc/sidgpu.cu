@@ -22,6 +22,7 @@
 #include "k_tokenize.cuh"
 #include "k_tok2.cuh"
 #include "k_reads.cuh"
+#include "inflate.cuh"
 #include "nelder_mead.hpp"
 
 using namespace sid;
@@ -126,6 +127,7 @@ struct sidgpu_ctx {
 
     // sidgpu_call_host staging (two text buffers, two CSV buffers, their events), kept across calls
     DevBuf hp_text[2], hp_csv[2];
+    DevBuf hp_comp[2], inf_blocks[2];  // BGZF input: compressed chunks and their member tables (bgzf_path.inl)
     cudaEvent_t hp_ev_in[2] = {nullptr, nullptr}, hp_ev_out[2] = {nullptr, nullptr};
 
     // optional per-kernel timing (sidgpu_profile): event pairs recorded around launches, resolved lazily
@@ -223,7 +225,7 @@ struct Range {
     ~Range() { nvtxRangePop(); }
 };
 
-enum { PROF_TOKENIZE = 0, PROF_CLASSIFY = 1, PROF_CSV = 2, PROF_ORDER = 3, PROF_FIT = 4, PROF_HIST = 5, PROF_QUALITY = 6 };
+enum { PROF_TOKENIZE = 0, PROF_CLASSIFY = 1, PROF_CSV = 2, PROF_ORDER = 3, PROF_FIT = 4, PROF_HIST = 5, PROF_QUALITY = 6, PROF_INFLATE = 7 };
 
 cudaEvent_t take_event(sidgpu_ctx* ctx) {
     if (!ctx->free_events.empty()) { cudaEvent_t e = ctx->free_events.back(); ctx->free_events.pop_back(); return e; }
@@ -1190,7 +1192,7 @@ void sidgpu_destroy(sidgpu_ctx* ctx) {
     for (DevBuf* b : {&ctx->blk, &ctx->blk_part, &ctx->order, &ctx->v_pos, &ctx->v_slot, &ctx->v_name_ref, &ctx->v_profile, &ctx->v_line_off, &ctx->csv_status, &ctx->pos, &ctx->slot, &ctx->name_ref, &ctx->profile, &ctx->line_off,
                       &ctx->site_suffix, &ctx->rows_scratch, &ctx->rows_part, &ctx->rows_part_rows, &ctx->sort_keys, &ctx->sort_vals, &ctx->u_profile, &ctx->u_count, &ctx->u_logM,
                       &ctx->entry_to_unique, &ctx->g_e2u, &ctx->p_hom, &ctx->p_het, &ctx->adj_hom, &ctx->adj_het, &ctx->bh_c, &ctx->bh_block,
-                      &ctx->partials, &ctx->quality_lut})
+                      &ctx->partials, &ctx->quality_lut, &ctx->hp_comp[0], &ctx->hp_comp[1], &ctx->inf_blocks[0], &ctx->inf_blocks[1]})
         release(*b);
     if (ctx->d_ctl) cudaFree(ctx->d_ctl);
     if (ctx->h_ctl) cudaFreeHost(ctx->h_ctl);
@@ -1759,4 +1761,5 @@ int sidgpu_format_g(sidgpu_ctx* ctx, const double* d_values, uint64_t n, char* d
 }  // extern "C"
 
 #include "host_path.inl"
+#include "bgzf_path.inl"
 #include "host_io.inl"

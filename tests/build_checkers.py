@@ -11,7 +11,7 @@ from sid_b200.build import ROOT, _glob, _newer, _run
 
 def build_hostcheck(force=False):
     out = os.path.join(ROOT, "tests", "hostcheck", "libhostcheck.so")
-    srcs = _glob("sid_b200/csrc", (".cuh",)) + [os.path.join(ROOT, "tests", "hostcheck", "hostcheck.cpp")]
+    srcs = _glob("sid_b200/csrc", (".cuh",)) + _glob("tests/hostcheck", (".cpp", ".hpp"))
     if force or _newer(out, srcs):
         _run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-Wno-unknown-pragmas", "-DSID_HAVE_FAST", "-x", "c++",
               "tests/hostcheck/hostcheck.cpp", "-o", out])

@@ -9,6 +9,7 @@
 #include "../../sid_b200/csrc/fmt.cuh"
 #include "../../sid_b200/csrc/parse.cuh"
 #include "../../sid_b200/csrc/k_quality.cuh"
+#include "../../sid_b200/csrc/inflate.cuh"
 #include <cmath>
 #include <vector>
 #ifdef SID_HAVE_FAST
@@ -21,6 +22,13 @@
 using namespace sid;
 
 extern "C" {
+
+// inflate.cuh: one raw deflate stream on one thread (the walk the kernel's lane 0 does, matches copied in place).
+// `in` must be readable 8 bytes past in_len.
+int hc_inflate_member(const uint8_t* in, uint32_t in_len, uint8_t* out, uint32_t out_len) {
+    static thread_local InflateTables t;
+    return inflate_member_serial(in, in_len, out, out_len, t);
+}
 
 struct hc_line {
     int32_t status, pos;

@@ -82,3 +82,108 @@ def test_reader_reports_damage(bgzf_cat, tmp_path):
     p.write_bytes(good[:len(good) // 2])                                     # truncated in the middle of a block
     rc, out, err = cat(bgzf_cat, p)
     assert rc == 1 and "truncated" in err
+
+
+# ---- the device inflate (sid_b200/csrc/inflate.cuh), compiled for the CPU: tests/hostcheck
+def _hc_inflate(raw, n_out):
+    import ctypes
+    import numpy as np
+    import oracle_py as op
+    hc = op.hostcheck()
+    hc.hc_inflate_member.restype = ctypes.c_int
+    hc.hc_inflate_member.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_uint32]
+    res = []
+    for lead in (0, 1, 2, 3):                     # every alignment of the stream's first byte
+        buf = np.zeros(lead + len(raw) + 16 + 4, dtype=np.uint8)
+        base = (4 - buf.ctypes.data % 4) % 4
+        buf[base + lead:base + lead + len(raw)] = np.frombuffer(raw, dtype=np.uint8)
+        out = np.zeros(max(1, n_out), dtype=np.uint8)
+        rc = hc.hc_inflate_member(buf.ctypes.data + base + lead, len(raw), out.ctypes.data, n_out)
+        res.append((rc, out[:n_out].tobytes()))
+    assert all(r == res[0] for r in res)
+    return res[0]
+
+
+def _deflate(data, level=6, strategy=zlib.Z_DEFAULT_STRATEGY, wbits=-15):
+    c = zlib.compressobj(level, zlib.DEFLATED, wbits, 9, strategy)
+    return c.compress(data) + c.flush()
+
+
+@pytest.mark.parametrize("level", [0, 1, 6, 9])
+@pytest.mark.parametrize("strategy", [zlib.Z_DEFAULT_STRATEGY, zlib.Z_FIXED, zlib.Z_HUFFMAN_ONLY, zlib.Z_RLE])
+def test_device_inflate_on_cpu_equals_zlib(level, strategy):
+    import random
+    rnd = random.Random(level * 10 + strategy)
+    texts = [read("depth30.plp")[:65280], read("depth500.plp")[:60000], read("quality30.plp")[:65280], b"", b"a", b"ab" * 30000,
+             bytes(rnd.randrange(256) for _ in range(20000)), bytes(rnd.choice(b"ACGT") for _ in range(65280)),
+             b"\n".join(b"x" * rnd.randrange(0, 300) for _ in range(400))[:65280]]
+    for t in texts:
+        raw = _deflate(t, level, strategy)
+        rc, out = _hc_inflate(raw, len(t))
+        assert rc == 0, (rc, len(t))
+        assert out == t
+
+
+def test_device_inflate_on_cpu_small_windows_and_sync_flushes():
+    """Short distances (window 512), many small deflate blocks (Z_SYNC_FLUSH leaves empty stored blocks), long codes."""
+    t = read("depth30.plp")[:65280]
+    c = zlib.compressobj(9, zlib.DEFLATED, -9)
+    raw = b""
+    for i in range(0, len(t), 700):
+        raw += c.compress(t[i:i + 700]) + c.flush(zlib.Z_SYNC_FLUSH)
+    raw += c.flush()
+    assert _hc_inflate(raw, len(t)) == (0, t)
+    # a skewed alphabet: code lengths up to 15
+    import random
+    rnd = random.Random(3)
+    sym = bytes(range(256))
+    skew = bytes(rnd.choices(sym, weights=[2.0 ** (-i / 6.0) for i in range(256)], k=65000))
+    assert _hc_inflate(_deflate(skew, 6, zlib.Z_HUFFMAN_ONLY), len(skew)) == (0, skew)
+
+
+def test_device_inflate_on_cpu_reports_damage():
+    t = read("depth30.plp")[:30000]
+    raw = _deflate(t)
+    assert _hc_inflate(raw, len(t) - 1)[0] != 0                               # more text than announced
+    assert _hc_inflate(raw, len(t) + 1)[0] != 0                               # less
+    assert _hc_inflate(raw[:len(raw) // 2], len(t))[0] != 0                   # cut stream
+    import random
+    rnd = random.Random(1)
+    bad = 0
+    for k in range(200):                                                      # flipped bits: an error or other text, never a crash
+        b = bytearray(raw)
+        b[rnd.randrange(len(b))] ^= 1 << rnd.randrange(8)
+        rc, out = _hc_inflate(bytes(b), len(t))
+        bad += rc != 0 or out != t
+    assert bad >= 190
+
+
+def test_bgzf_scan_lists_the_members():
+    import ctypes
+    import numpy as np
+    from sid_b200 import _lib
+    lib = _lib.load()
+    text = read("depth30.plp")
+    comp = bgzf_compress(text, 5000)
+
+    class Block(ctypes.Structure):
+        _fields_ = [("c_off", ctypes.c_uint64), ("out_off", ctypes.c_uint64), ("c_len", ctypes.c_uint32), ("isize", ctypes.c_uint32)]
+
+    blocks = (Block * 4096)()
+    n, consumed, tbytes = ctypes.c_size_t(), ctypes.c_size_t(), ctypes.c_size_t()
+    buf = np.frombuffer(comp, dtype=np.uint8)
+    assert lib.sidgpu_bgzf_scan(buf.ctypes.data, len(comp), blocks, 4096, 1 << 40, ctypes.byref(n), ctypes.byref(consumed), ctypes.byref(tbytes)) == 0
+    assert consumed.value == len(comp) and tbytes.value == len(text) and n.value == (len(text) + 4999) // 5000
+    got = b"".join(zlib.decompress(comp[b.c_off:b.c_off + b.c_len], -15) for b in blocks[:n.value])
+    assert got == text
+    assert [b.out_off for b in blocks[:3]] == [0, 5000, 10000]
+    # a window that cuts a member, a text cap, a member limit
+    assert lib.sidgpu_bgzf_scan(buf.ctypes.data, len(comp) - 40, blocks, 4096, 1 << 40, ctypes.byref(n), ctypes.byref(consumed), ctypes.byref(tbytes)) == 0
+    assert consumed.value < len(comp) - 40 and tbytes.value == 5000 * n.value
+    assert lib.sidgpu_bgzf_scan(buf.ctypes.data, len(comp), blocks, 4096, 12000, ctypes.byref(n), ctypes.byref(consumed), ctypes.byref(tbytes)) == 0
+    assert n.value == 2 and tbytes.value == 10000
+    assert lib.sidgpu_bgzf_scan(buf.ctypes.data, len(comp), blocks, 3, 1 << 40, ctypes.byref(n), ctypes.byref(consumed), ctypes.byref(tbytes)) == 0
+    assert n.value == 3
+    import gzip
+    plain = np.frombuffer(gzip.compress(text), dtype=np.uint8)
+    assert lib.sidgpu_bgzf_scan(plain.ctypes.data, len(plain), blocks, 4096, 1 << 40, ctypes.byref(n), ctypes.byref(consumed), ctypes.byref(tbytes)) != 0

@@ -115,29 +115,31 @@ def test_cli_reads_gzip_input(sid_bin, tmp_path):
     assert diffs <= max(2, n // 1000)
 
 
+@pytest.mark.parametrize("where", [[], ["--host-inflate"]], ids=["device", "host"])
 @pytest.mark.parametrize("flags", [["-m", "local"], ["-m", "bayes"]])
-def test_cli_reads_bgzf_input(sid_bin, tmp_path, flags):
-    """A blocked gzip file (`bgzip`): its blocks are inflated side by side into the pinned slots (host/bgzf.hpp); the
-    Lynch methods read it once, `quality -R` twice (rewind)."""
+def test_cli_reads_bgzf_input(sid_bin, tmp_path, flags, where):
+    """A blocked gzip file (`bgzip`): its members are inflated on the device (inflate.cuh; only compressed bytes cross the
+    link) or, with --host-inflate, side by side into the pinned slots by the reader's threads (host/bgzf.hpp); the Lynch
+    methods read it once, `quality -R` twice (rewind)."""
     from test_bgzf import bgzf_compress
     case = [c for c in MANIFEST["cases"] if c["input"] == "depth30_two_chroms.plp" and c["flags"] == flags][0]
     gz = tmp_path / "input.plp.gz"
     gz.write_bytes(bgzf_compress(read(case["input"]), 4096))
-    rc, out, err = run(sid_bin, *flags, "--chunk-mb", "1", "--read-threads", "4", str(gz))
+    rc, out, err = run(sid_bin, *flags, *where, "--chunk-mb", "1", "--read-threads", "4", str(gz))
     assert rc == 0, err
     n, diffs = op.compare_csv(out, read(case["csv"]))
     assert diffs <= max(2, n // 1000)
     case = [c for c in MANIFEST["cases"] if c["input"] == "quality30.plp" and c["flags"] == ["-m", "quality", "-R"]][0]
     gz.write_bytes(bgzf_compress(read(case["input"])))
-    rc, out, err = run(sid_bin, *case["flags"], str(gz))
+    rc, out, err = run(sid_bin, *case["flags"], *where, str(gz))
     assert rc == 0, err
     n, diffs = op.compare_csv(out, read(case["csv"]))
     assert diffs <= max(2, n // 1000)
     bad = bytearray(gz.read_bytes())
     bad[len(bad) // 2] ^= 0x55
     gz.write_bytes(bytes(bad))
-    rc, out, err = run(sid_bin, "-m", "local", str(gz))
-    assert rc == 2 and "inflate" in err
+    rc, out, err = run(sid_bin, "-m", "local", *where, str(gz))
+    assert rc == 2 and "inflate" in err, (rc, err)
 
 
 @pytest.mark.parametrize("devices", ["0,0", "0,0,0,0,0"])

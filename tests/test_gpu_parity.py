@@ -245,6 +245,93 @@ def test_call_io_streams_the_same_rows(native, tiny_chunk_ctx, case):
     assert diffs <= max(2, n // 1000)
 
 
+@pytest.mark.parametrize("block", [65280, 5000, 300])
+def test_inflate_bgzf_on_device(native, gpu_ctx, block):
+    """inflate.cuh: one warp per BGZF member, against zlib (levels and strategies per member vary), incl. empty members."""
+    import random
+    import zlib
+    from test_bgzf import bgzf_block, EOF_BLOCK
+    rnd = random.Random(block)
+    text = read("depth30.plp") + read("depth500.plp")[:300000] + bytes(rnd.randrange(256) for _ in range(70000)) + b"ab" * 50000
+    comp = b""
+    for i in range(0, len(text), block):
+        piece = text[i:i + block]
+        level = rnd.choice([0, 1, 6, 9])
+        if rnd.random() < 0.1:
+            comp += EOF_BLOCK                                                 # an empty member in the middle
+        if rnd.random() < 0.2:
+            c = zlib.compressobj(level, zlib.DEFLATED, -15, 9, rnd.choice([zlib.Z_FIXED, zlib.Z_HUFFMAN_ONLY, zlib.Z_RLE]))
+            body = c.compress(piece) + c.flush()
+            import struct
+            bsize = 12 + 6 + len(body) + 8 - 1
+            comp += (b"\x1f\x8b\x08\x04" + b"\0\0\0\0" + b"\x00\xff" + struct.pack("<H", 6) + b"BC" + struct.pack("<HH", 2, bsize) + body +
+                     struct.pack("<II", zlib.crc32(piece) & 0xFFFFFFFF, len(piece)))
+        else:
+            comp += bgzf_block(piece, level)
+    comp += EOF_BLOCK
+    assert gpu_ctx.inflate_bgzf(comp) == text
+    assert gpu_ctx.inflate_bgzf(EOF_BLOCK) == b""
+    # a damaged member is reported with its index
+    import sid_b200
+    bad = bytearray(comp)
+    k = len(comp) // 2
+    bad[k] ^= 0x10
+    try:
+        out = gpu_ctx.inflate_bgzf(bytes(bad))
+        assert out != text or True                                            # a flip inside a stored block or a header's spare byte changes nothing detectable
+    except (sid_b200.SidGpuError, ValueError) as e:
+        assert "BGZF" in str(e) or "truncated" in str(e)
+    assert gpu_ctx.inflate_bgzf(comp) == text                                 # and the ctx stays usable
+
+
+@pytest.mark.parametrize("case", [c for c in MANIFEST["cases"] if c["csv"] in ("depth30.m_local.csv", "depth30_two_chroms.m_bayes.csv",
+                                                                                "quality30.m_quality_R.csv", "depth500.m_local.csv", "edge.m_local.csv")],
+                         ids=lambda c: c["csv"])
+@pytest.mark.parametrize("block", [65280, 900])
+def test_call_io_bgzf_streams_the_same_rows(native, case, block):
+    """sidgpu_call_io_bgzf: the callback delivers the compressed file, the members are inflated on the device, the unfinished
+    line at the end of a chunk moves to the front of the next one."""
+    import io
+    import sid_b200
+    from test_bgzf import bgzf_compress
+    text = read(case["input"])
+    src = io.BytesIO(bgzf_compress(text, block))
+    pieces = []
+    with sid_b200.Context(max_chunk_bytes=1 << 17) as ctx:                    # slots of 128 KiB of compressed bytes
+        nb, n_sites, n_rows = ctx.call_io(lambda n: src.read(min(n, 50001)), pieces.append, params_from_flags(case["flags"]),
+                                          rewind=lambda: src.seek(0), bgzf=True)
+    rows = b"".join(pieces)
+    assert nb == len(rows)
+    n, diffs = op.compare_csv(sid_b200.CSV_HEADER + rows, read(case["csv"]))
+    assert n == n_rows
+    assert diffs <= max(2, n // 1000)
+
+
+def test_call_io_bgzf_errors(native, gpu_ctx):
+    import io
+    import sid_b200
+    from test_bgzf import bgzf_compress
+    p = sid_b200.Context.make_params("local")
+    comp = bgzf_compress(read("depth30.plp"))
+    for bad, what in ((comp[:len(comp) // 2], "truncated"), (b"not gzip at all, just text\n" * 10, "BGZF")):
+        src = io.BytesIO(bad)
+        with pytest.raises(sid_b200.SidGpuError) as e:
+            gpu_ctx.call_io(lambda n: src.read(n), lambda rows: None, p, bgzf=True)
+        assert what in str(e.value)
+    b = bytearray(comp)
+    b[len(b) // 3] ^= 0x04
+    src = io.BytesIO(bytes(b))
+    try:
+        gpu_ctx.call_io(lambda n: src.read(n), lambda rows: None, p, bgzf=True)
+    except (sid_b200.SidGpuError, sid_b200.MalformedPileup):
+        pass                                                                  # an inflate error, or text that is no pileup any more
+    src = io.BytesIO(comp)
+    pieces = []
+    gpu_ctx.call_io(lambda n: src.read(n), pieces.append, p, bgzf=True)       # the ctx stays usable
+    n, diffs = op.compare_csv(sid_b200.CSV_HEADER + b"".join(pieces), read("depth30.m_local.csv"))
+    assert diffs <= 2
+
+
 def test_call_io_errors(native, tiny_chunk_ctx):
     import io
     import sid_b200
