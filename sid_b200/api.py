@@ -128,12 +128,13 @@ class Context:
         self._ck(self.lib.sidgpu_profile(self.h, 1 if enable else 0))
 
     def kernel_times(self):
-        """{'tokenize': (ms, launches), 'classify': ..., 'csv': ..., 'order': ..., 'fit': ..., 'histogram': ..., 'quality': ...}
+        """{'tokenize': (ms, launches), 'classify': ..., 'csv': ..., 'order': ..., 'fit': ..., 'histogram': ..., 'quality': ...,
+        'inflate': ...}
         since profile(True)."""
         ms = (ctypes.c_double * 8)()
         n = (ctypes.c_uint64 * 8)()
         self._ck(self.lib.sidgpu_kernel_times(self.h, ms, n))
-        return {k: (ms[i], n[i]) for i, k in enumerate(("tokenize", "classify", "csv", "order", "fit", "histogram", "quality"))}
+        return {k: (ms[i], n[i]) for i, k in enumerate(("tokenize", "classify", "csv", "order", "fit", "histogram", "quality", "inflate"))}
 
     # ---- K1
     def tokenize(self, d_text, text_len, begin=0, end=None, want_qual=False, strands=False):

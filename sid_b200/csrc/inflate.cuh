@@ -35,34 +35,52 @@ struct InflateTables {
     uint16_t lit_cnt[16], dist_cnt[16];     // codes per length
 };
 
-// The input as a little-endian bit stream.  The buffer must be readable up to 8 bytes past its end (the callers pad).
+// The input as a little-endian bit stream: two consecutive aligned words and a bit offset; the next 32 bits of the stream are
+// one funnel shift away at any time.  The buffer must be readable up to 8 bytes past its end (the callers pad).
 struct BitReader {
-    const uint32_t* wp;     // next aligned word
-    uint64_t bb;            // bit buffer, next bit at bit 0
-    uint32_t bc;            // valid bits in bb
-    uint64_t taken;         // bits consumed so far
-    uint64_t limit;         // bits of the stream
+    const uint32_t* wp;     // the word after `hi`
+    const uint32_t* end;    // first word that holds no byte of the stream
+    uint32_t lo, hi;        // the words that hold the next bits
+    uint32_t p;             // offset of the next bit in `lo` (0..31)
+    bool over;              // the stream was read past its end
 
     SID_HD void init(const uint8_t* in, uint32_t len) {
         const uintptr_t a = (uintptr_t)in;
         wp = (const uint32_t*)(a & ~(uintptr_t)3);
-        const uint32_t skip = (uint32_t)(a & 3) * 8;
-        bb = (uint64_t)(*wp++) >> skip;
-        bc = 32 - skip;
-        taken = 0;
-        limit = (uint64_t)len * 8;
-        refill();
+        end = (const uint32_t*)(((a + len) + 3) & ~(uintptr_t)3);
+        p = (uint32_t)(a & 3) * 8;
+        lo = *wp++;
+        hi = *wp++;
+        over = false;
     }
-    SID_HD void refill() {                  // at least 33 valid bits afterwards
-        if (bc <= 32) {
-            bb |= (uint64_t)(*wp++) << bc;
-            bc += 32;
+    SID_HD uint32_t window() const {        // the next 32 bits
+#if defined(__CUDA_ARCH__)
+        return __funnelshift_r(lo, hi, p);
+#else
+        return (uint32_t)((((uint64_t)hi << 32) | lo) >> p);
+#endif
+    }
+    SID_HD uint32_t peek(uint32_t n) const { return window() & ((1u << n) - 1u); }
+    SID_HD void drop(uint32_t n) {          // n <= 32
+        p += n;
+        if (p >= 32) {
+            p -= 32;
+            lo = hi;
+            if (wp > end) {                             // `hi` may be the word after the stream, never a later one
+                hi = 0;
+                if (wp > end + 1) over = true;          // `lo` now lies wholly beyond the stream
+                ++wp;
+            } else hi = *wp++;
         }
     }
-    SID_HD uint32_t peek(uint32_t n) const { return (uint32_t)bb & ((1u << n) - 1u); }
-    SID_HD void drop(uint32_t n) { bb >>= n; bc -= n; taken += n; }
-    SID_HD uint32_t take(uint32_t n) { const uint32_t v = peek(n); drop(n); return v; }     // n <= 16, after a refill
-    SID_HD bool overrun() const { return taken > limit; }
+    SID_HD uint32_t take(uint32_t n) { const uint32_t v = peek(n); drop(n); return v; }     // n <= 16
+    SID_HD void to_byte_boundary() { drop((8u - (p & 7u)) & 7u); }
+    // bits consumed beyond the stream's last byte?  (exact: position of the next bit against the stream's length)
+    SID_HD bool overrun(const uint8_t* in, uint32_t len) const {
+        const uintptr_t first = (uintptr_t)in & ~(uintptr_t)3;
+        const uint64_t pos = ((uint64_t)((uintptr_t)wp - first) - 8) * 8 + p;       // bit offset of the next bit from `first`
+        return over || pos > ((uint64_t)((uintptr_t)in - first) + len) * 8;
+    }
 };
 
 SID_HD uint32_t bit_reverse(uint32_t v, uint32_t n) {      // the low n bits of v, reversed
@@ -111,17 +129,20 @@ SID_HD bool build_huffman(const uint8_t* lengths, uint32_t n, uint16_t* fast, ui
 
 // Next symbol of the alphabet (fast, bits, cnt, sym); -1 for a code that is not in it.
 SID_HD int decode_symbol(BitReader& br, const uint16_t* fast, uint32_t bits, const uint16_t* cnt, const uint16_t* sym) {
-    br.refill();
-    const uint32_t e = fast[br.peek(bits)];
+    const uint32_t w = br.window();
+    const uint32_t e = fast[w & ((1u << bits) - 1u)];
     if (e) {
         br.drop(e & 15u);
         return (int)(e >> 4);
     }
     int code = 0, first = 0, index = 0;
     for (int l = 1; l < 16; ++l) {
-        code |= (int)br.take(1);
+        code |= (int)((w >> (l - 1)) & 1u);
         const int count = cnt[l];
-        if (code - count < first) return sym[index + (code - first)];
+        if (code - count < first) {
+            br.drop((uint32_t)l);
+            return sym[index + (code - first)];
+        }
         index += count;
         first += count;
         first <<= 1;
@@ -150,7 +171,6 @@ SID_HD int read_block_tables(BitReader& br, bool fixed, InflateTables& t) {
         for (int s = 280; s < 288; ++s) lengths[s] = 8;
         for (int s = 0; s < 30; ++s) lengths[288 + s] = 5;
     } else {
-        br.refill();
         nlen = br.take(5) + 257;
         ndist = br.take(5) + 1;
         const uint32_t ncode = br.take(4) + 4;
@@ -158,8 +178,7 @@ SID_HD int read_block_tables(BitReader& br, bool fixed, InflateTables& t) {
         uint8_t cl[19];
         for (int i = 0; i < 19; ++i) cl[i] = 0;
         for (uint32_t i = 0; i < ncode; ++i) {
-            br.refill();
-            // order of the code length code lengths: 16 17 18 0 8 7 9 6 10 5 11 4 12 3 13 2 14 1 15
+                // order of the code length code lengths: 16 17 18 0 8 7 9 6 10 5 11 4 12 3 13 2 14 1 15
             const uint32_t pos = i < 3 ? 16 + i : i == 3 ? 0 : (i & 1) ? (19 - i) / 2 : 6 + i / 2;
             cl[pos] = (uint8_t)br.take(3);
         }
@@ -169,10 +188,9 @@ SID_HD int read_block_tables(BitReader& br, bool fixed, InflateTables& t) {
         while (i < nlen + ndist) {
             const int s = decode_symbol(br, t.dist_fast, 7, t.dist_cnt, t.dist_sym);
             if (s < 0) return INF_BAD_LENGTHS;
-            if (br.overrun()) return INF_INPUT_OVERRUN;
+            if (br.over) return INF_INPUT_OVERRUN;
             if (s < 16) { lengths[i++] = (uint8_t)s; continue; }
-            br.refill();
-            uint32_t rep, val = 0;
+                uint32_t rep, val = 0;
             if (s == 16) {
                 if (i == 0) return INF_BAD_LENGTHS;
                 val = lengths[i - 1];
@@ -200,7 +218,7 @@ SID_HD uint32_t decode_run(BitReader& br, const InflateTables& t, uint8_t* out, 
     for (;;) {
         const int s = decode_symbol(br, t.lit_fast, INF_LIT_BITS, t.lit_cnt, t.lit_sym);
         if (s < 0) { *n_lit = n; *len = INF_BAD_SYMBOL; return EV_ERROR; }
-        if (br.overrun()) { *n_lit = n; *len = INF_INPUT_OVERRUN; return EV_ERROR; }
+        if (br.over) { *n_lit = n; *len = INF_INPUT_OVERRUN; return EV_ERROR; }
         if (s < 256) {
             if (pos + n >= out_len) { *n_lit = n; *len = INF_OUTPUT_OVERRUN; return EV_ERROR; }
             out[pos + n] = (uint8_t)s;
@@ -211,11 +229,9 @@ SID_HD uint32_t decode_run(BitReader& br, const InflateTables& t, uint8_t* out, 
         if (s == 256) return EV_END;
         const uint32_t li = (uint32_t)s - 257;
         if (li > 28) { *len = INF_BAD_SYMBOL; return EV_ERROR; }
-        br.refill();
         const uint32_t l = length_base(li) + br.take(length_extra(li));
         const int d = decode_symbol(br, t.dist_fast, INF_DIST_BITS, t.dist_cnt, t.dist_sym);
         if (d < 0 || d > 29) { *len = INF_BAD_DISTANCE; return EV_ERROR; }
-        br.refill();
         const uint32_t dd = dist_base((uint32_t)d) + br.take(dist_extra((uint32_t)d));
         if (dd > pos + n) { *len = INF_BAD_DISTANCE; return EV_ERROR; }
         if (pos + n + l > out_len) { *len = INF_OUTPUT_OVERRUN; return EV_ERROR; }
@@ -225,31 +241,75 @@ SID_HD uint32_t decode_run(BitReader& br, const InflateTables& t, uint8_t* out, 
     }
 }
 
+// One symbol.  Returns STEP_LITERAL (stored at out[pos]), STEP_MATCH (*len, *dist set, nothing copied yet), STEP_END (end of
+// block) or STEP_ERROR (*len = code).
+enum : uint32_t { STEP_LITERAL = 0, STEP_MATCH = 1, STEP_END = 2, STEP_ERROR = 3 };
+SID_HD uint32_t decode_step(BitReader& br, const InflateTables& t, uint8_t* out, uint32_t pos, uint32_t out_len, uint32_t* len, uint32_t* dist) {
+    const int s = decode_symbol(br, t.lit_fast, INF_LIT_BITS, t.lit_cnt, t.lit_sym);
+    if (s < 0 || br.over) { *len = s < 0 ? INF_BAD_SYMBOL : INF_INPUT_OVERRUN; return STEP_ERROR; }
+    if (s < 256) {
+        if (pos >= out_len) { *len = INF_OUTPUT_OVERRUN; return STEP_ERROR; }
+        out[pos] = (uint8_t)s;
+        return STEP_LITERAL;
+    }
+    if (s == 256) return STEP_END;
+    const uint32_t li = (uint32_t)s - 257;
+    if (li > 28) { *len = INF_BAD_SYMBOL; return STEP_ERROR; }
+    const uint32_t l = length_base(li) + br.take(length_extra(li));
+    const int d = decode_symbol(br, t.dist_fast, INF_DIST_BITS, t.dist_cnt, t.dist_sym);
+    if (d < 0 || d > 29) { *len = INF_BAD_DISTANCE; return STEP_ERROR; }
+    const uint32_t dd = dist_base((uint32_t)d) + br.take(dist_extra((uint32_t)d));
+    if (dd > pos) { *len = INF_BAD_DISTANCE; return STEP_ERROR; }
+    if (pos + l > out_len) { *len = INF_OUTPUT_OVERRUN; return STEP_ERROR; }
+    *len = l;
+    *dist = dd;
+    return STEP_MATCH;
+}
+
 // Block header: BFINAL, BTYPE; a stored block is copied right here.  *final_block, *kind (0 stored: done, 1/2: tables built).
 SID_HD int begin_block(BitReader& br, InflateTables& t, uint8_t* out, uint32_t* pos, uint32_t out_len, bool* final_block, uint32_t* kind) {
-    br.refill();
     *final_block = br.take(1) != 0;
     *kind = br.take(2);
     if (*kind == 3) return INF_BAD_BLOCK_TYPE;
     if (*kind == 0) {
-        br.drop(br.bc & 7u);                                    // to the next byte boundary
-        br.refill();
+        br.to_byte_boundary();
         const uint32_t n = br.take(16);
-        br.refill();
         const uint32_t nn = br.take(16);
         if ((n ^ nn) != 0xFFFFu) return INF_BAD_STORED;
         if (*pos + n > out_len) return INF_OUTPUT_OVERRUN;
-        for (uint32_t i = 0; i < n; ++i) {
-            br.refill();
-            out[*pos + i] = (uint8_t)br.take(8);
-        }
+        for (uint32_t i = 0; i < n; ++i) out[*pos + i] = (uint8_t)br.take(8);
         *pos += n;
-        return br.overrun() ? INF_INPUT_OVERRUN : INF_OK;
+        return br.over ? INF_INPUT_OVERRUN : INF_OK;
     }
     return read_block_tables(br, *kind == 1, t);
 }
 
 // One member on one thread (tests/hostcheck; the kernel below is the same walk with the matches copied by the warp).
+SID_HD int inflate_member_steps(const uint8_t* in, uint32_t in_len, uint8_t* out, uint32_t out_len, InflateTables& t) {
+    BitReader br;
+    br.init(in, in_len);
+    uint32_t pos = 0;
+    for (uint32_t guard = 0; guard < (1u << 20); ++guard) {
+        bool final_block;
+        uint32_t kind;
+        const int rc = begin_block(br, t, out, &pos, out_len, &final_block, &kind);
+        if (rc != INF_OK) return rc;
+        if (kind != 0) {
+            for (;;) {
+                uint32_t len = 0, dist = 0;
+                const uint32_t ev = decode_step(br, t, out, pos, out_len, &len, &dist);
+                if (ev == STEP_ERROR) return (int)len;
+                if (ev == STEP_END) break;
+                if (ev == STEP_LITERAL) { ++pos; continue; }
+                for (uint32_t k = 0; k < len; ++k) out[pos + k] = (out + pos - dist)[dist >= len ? k : k % dist];
+                pos += len;
+            }
+        }
+        if (final_block) return pos == out_len ? (br.overrun(in, in_len) ? INF_INPUT_OVERRUN : INF_OK) : INF_SIZE_MISMATCH;
+    }
+    return INF_BAD_BLOCK_TYPE;
+}
+
 SID_HD int inflate_member_serial(const uint8_t* in, uint32_t in_len, uint8_t* out, uint32_t out_len, InflateTables& t) {
     BitReader br;
     br.init(in, in_len);
@@ -270,7 +330,7 @@ SID_HD int inflate_member_serial(const uint8_t* in, uint32_t in_len, uint8_t* ou
                 pos += len;
             }
         }
-        if (final_block) return pos == out_len ? (br.overrun() ? INF_INPUT_OVERRUN : INF_OK) : INF_SIZE_MISMATCH;
+        if (final_block) return pos == out_len ? (br.overrun(in, in_len) ? INF_INPUT_OVERRUN : INF_OK) : INF_SIZE_MISMATCH;
     }
     return INF_BAD_BLOCK_TYPE;
 }
@@ -330,7 +390,7 @@ __global__ void __launch_bounds__(INF_WARPS * 32) k_inflate_bgzf(const uint8_t* 
             }
             if (final_block) {
                 int over = 0;
-                if (lane == 0) over = br.overrun() ? 1 : 0;
+                if (lane == 0) over = br.overrun(comp + b.c_off, b.c_len) ? 1 : 0;
                 over = __shfl_sync(0xFFFFFFFFu, over, 0);
                 rc = pos != out_len ? INF_SIZE_MISMATCH : over ? INF_INPUT_OVERRUN : INF_OK;
                 done = true;
@@ -339,6 +399,100 @@ __global__ void __launch_bounds__(INF_WARPS * 32) k_inflate_bgzf(const uint8_t* 
         if (!done && rc == INF_OK) rc = INF_BAD_BLOCK_TYPE;
         if (rc != INF_OK && lane == 0) atomicMin(error, ((unsigned long long)m << 4) | (unsigned long long)rc);
         __syncwarp();
+    }
+}
+
+// Lockstep form: a warp inflates 32 / SW members at once.  Lane 0 of every group of SW lanes (the leader) owns one member's
+// bit reader; every trip of the warp's loop each leader decodes ONE symbol -- the same instructions for all of them --
+// and the groups that met a match copy it with their SW lanes.  Block headers (table building) run on the leaders that
+// need them while the others wait; members are dealt group by group, a group that is done with its member takes the
+// next one of its warp's share.
+constexpr int INF2_WARPS = 4;
+template <int SW>
+__global__ void __launch_bounds__(INF2_WARPS * 32) k_inflate_bgzf_lockstep(const uint8_t* comp, const BgzfBlock* blocks, uint32_t n_blocks, uint8_t* text,
+                                                                            unsigned long long* error) {
+    constexpr int G = 32 / SW;
+    extern __shared__ __align__(16) uint8_t s_inf[];
+    InflateTables* const tables = reinterpret_cast<InflateTables*>(s_inf);
+    constexpr uint32_t FULL = 0xFFFFFFFFu;
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t sub = lane / SW, sl = lane % SW;
+    const bool leader = sl == 0;
+    InflateTables& t = tables[warp * G + sub];
+    enum : int { ST_NEXT = 0, ST_HEADER = 1, ST_SYMBOLS = 2, ST_DONE = 3 };
+    // members: decoder d of the grid takes d, d + D, d + 2 D, ...
+    const uint32_t n_dec = gridDim.x * INF2_WARPS * G;
+    uint32_t m = (blockIdx.x * INF2_WARPS + warp) * G + sub;
+    int st = ST_NEXT;
+    BitReader br;
+    br.wp = br.end = nullptr; br.lo = br.hi = br.p = 0; br.over = false;
+    uint8_t* out = text;
+    uint32_t out_len = 0, pos = 0, c_len = 0;
+    const uint8_t* in = comp;
+    bool final_block = false;
+    bool first = true;
+    for (uint32_t guard = 0; guard < 0x7FFFFFF0u; ++guard) {
+        uint32_t ev = STEP_LITERAL, len = 0, dist = 0;
+        int rc = INF_OK;
+        if (leader) {
+            if (st == ST_NEXT) {
+                if (!first) m += n_dec;
+                first = false;
+                if (m >= n_blocks) st = ST_DONE;
+                else {
+                    const BgzfBlock b = blocks[m];
+                    in = comp + b.c_off;
+                    c_len = b.c_len;
+                    out = text + b.out_off;
+                    out_len = b.isize;
+                    pos = 0;
+                    br.init(in, c_len);
+                    st = ST_HEADER;
+                }
+            }
+            if (st == ST_HEADER) {
+                uint32_t kind = 0;
+                rc = begin_block(br, t, out, &pos, out_len, &final_block, &kind);
+                if (rc == INF_OK) {
+                    if (kind != 0) st = ST_SYMBOLS;
+                    else if (final_block) {
+                        rc = pos != out_len ? INF_SIZE_MISMATCH : br.overrun(in, c_len) ? INF_INPUT_OVERRUN : INF_OK;
+                        st = ST_NEXT;
+                    }
+                }
+            } else if (st == ST_SYMBOLS) {
+                ev = decode_step(br, t, out, pos, out_len, &len, &dist);
+                if (ev == STEP_LITERAL) ++pos;
+                else if (ev == STEP_END) {
+                    if (final_block) {
+                        rc = pos != out_len ? INF_SIZE_MISMATCH : br.overrun(in, c_len) ? INF_INPUT_OVERRUN : INF_OK;
+                        st = ST_NEXT;
+                    } else st = ST_HEADER;
+                } else if (ev == STEP_ERROR) rc = (int)len;
+            }
+            if (rc != INF_OK) {
+                atomicMin(error, ((unsigned long long)m << 4) | (unsigned long long)rc);
+                st = ST_NEXT;                                   // give the member up, go on with the next one
+                ev = STEP_LITERAL;
+            }
+        }
+        // ---- matches: copied by the lanes of the group
+        const bool match = leader && ev == STEP_MATCH;
+        if (__any_sync(FULL, match)) {
+            const uint32_t ld = __shfl_sync(FULL, match ? (len | (dist << 16)) : 0u, 0, SW);      // dist <= 32768, len <= 258
+            const unsigned long long dst = __shfl_sync(FULL, (unsigned long long)(uintptr_t)(out + pos), 0, SW);
+            __syncwarp();                                       // the leaders' literals are visible to the lanes that copy
+            const uint32_t l = ld & 0xFFFFu, d = ld >> 16;
+            if (l) {
+                uint8_t* q = (uint8_t*)(uintptr_t)dst;
+                const uint8_t* src = q - d;
+                if (d >= l) for (uint32_t k = sl; k < l; k += SW) q[k] = src[k];
+                else for (uint32_t k = sl; k < l; k += SW) q[k] = src[k % d];
+            }
+            __syncwarp();
+            if (match) pos += len;
+        }
+        if (__all_sync(FULL, !leader || st == ST_DONE)) break;
     }
 }
 

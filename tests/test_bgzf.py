@@ -90,17 +90,21 @@ def _hc_inflate(raw, n_out):
     import numpy as np
     import oracle_py as op
     hc = op.hostcheck()
-    hc.hc_inflate_member.restype = ctypes.c_int
-    hc.hc_inflate_member.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_uint32]
     res = []
-    for lead in (0, 1, 2, 3):                     # every alignment of the stream's first byte
-        buf = np.zeros(lead + len(raw) + 16 + 4, dtype=np.uint8)
-        base = (4 - buf.ctypes.data % 4) % 4
-        buf[base + lead:base + lead + len(raw)] = np.frombuffer(raw, dtype=np.uint8)
-        out = np.zeros(max(1, n_out), dtype=np.uint8)
-        rc = hc.hc_inflate_member(buf.ctypes.data + base + lead, len(raw), out.ctypes.data, n_out)
-        res.append((rc, out[:n_out].tobytes()))
-    assert all(r == res[0] for r in res)
+    for fn in (hc.hc_inflate_member, hc.hc_inflate_member_steps):        # literal runs (one warp per member) / one symbol per step (lockstep)
+        fn.restype = ctypes.c_int
+        fn.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_uint32]
+        for lead in (0, 1, 2, 3):                     # every alignment of the stream's first byte
+            buf = np.zeros(lead + len(raw) + 16 + 4, dtype=np.uint8)
+            base = (4 - buf.ctypes.data % 4) % 4
+            buf[base + lead:base + lead + len(raw)] = np.frombuffer(raw, dtype=np.uint8)
+            out = np.zeros(max(1, n_out), dtype=np.uint8)
+            rc = fn(buf.ctypes.data + base + lead, len(raw), out.ctypes.data, n_out)
+            res.append((rc, out[:n_out].tobytes()))
+    # the same text at every alignment; a damaged stream is an error at every alignment (how far the walk got may differ)
+    assert all((r[0] == 0) == (res[0][0] == 0) for r in res)
+    if res[0][0] == 0:
+        assert all(r == res[0] for r in res)
     return res[0]
 
 
