@@ -62,42 +62,14 @@ const char* inflate_error_text(int code) {
 int launch_inflate(sidgpu_ctx* ctx, const uint8_t* d_comp, const sid::BgzfBlock* d_blocks, size_t n, uint8_t* d_text) {
     CK(cudaMemsetAsync(ctl_field(ctx, &Control::error), 0xFF, sizeof(unsigned long long), ctx->stream));
     if (n == 0) return SIDGPU_OK;
-    // SID_INFLATE = 0: one warp per member; 4 / 8 / 16: lockstep, that many lanes per member (default 4)
-    static int variant = -1;
-    if (variant < 0) {
-        const char* e = getenv("SID_INFLATE");
-        variant = e ? atoi(e) : 4;
-        if (variant != 0 && variant != 4 && variant != 8 && variant != 16) variant = 4;
+    static int per_sm = 0;
+    if (per_sm == 0) {
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_inflate_bgzf, INF_WARPS * 32, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
     }
+    const size_t ctas = (n + INF_WARPS - 1) / INF_WARPS;
+    const unsigned grid = (unsigned)std::min<size_t>(ctas, (size_t)ctx->sm_count * (size_t)per_sm);
     ProfScope prof(ctx, PROF_INFLATE);
-    if (variant == 0) {
-        static int per_sm = 0;
-        if (per_sm == 0) {
-            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_inflate_bgzf, INF_WARPS * 32, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
-        }
-        const size_t ctas = (n + INF_WARPS - 1) / INF_WARPS;
-        const unsigned grid = (unsigned)std::min<size_t>(ctas, (size_t)ctx->sm_count * (size_t)per_sm);
-        k_inflate_bgzf<<<grid, INF_WARPS * 32, 0, ctx->stream>>>(d_comp, d_blocks, (uint32_t)n, d_text, ctl_field(ctx, &Control::error));
-    } else {
-        auto launch = [&](auto kernel, int sw) -> int {
-            const int g = 32 / sw;
-            const size_t smem = (size_t)INF2_WARPS * g * sizeof(sid::InflateTables);
-            static int per_sm_of[17] = {0};
-            if (per_sm_of[sw] == 0) {
-                CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                int v = 0;
-                if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, kernel, INF2_WARPS * 32, smem) != cudaSuccess || v < 1) v = 1;
-                per_sm_of[sw] = v;
-            }
-            const size_t per_cta = (size_t)INF2_WARPS * g;
-            const unsigned grid = (unsigned)std::min<size_t>((n + per_cta - 1) / per_cta, (size_t)ctx->sm_count * (size_t)per_sm_of[sw]);
-            kernel<<<grid, INF2_WARPS * 32, smem, ctx->stream>>>(d_comp, d_blocks, (uint32_t)n, d_text, ctl_field(ctx, &Control::error));
-            return SIDGPU_OK;
-        };
-        if (variant == 4) TRY(launch(k_inflate_bgzf_lockstep<4>, 4));
-        else if (variant == 8) TRY(launch(k_inflate_bgzf_lockstep<8>, 8));
-        else TRY(launch(k_inflate_bgzf_lockstep<16>, 16));
-    }
+    k_inflate_bgzf<<<grid, INF_WARPS * 32, 0, ctx->stream>>>(d_comp, d_blocks, (uint32_t)n, d_text, ctl_field(ctx, &Control::error));
     return check_launch(ctx, "k_inflate_bgzf");
 }
 

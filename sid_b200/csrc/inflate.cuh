@@ -28,10 +28,18 @@ enum : int { INF_OK = 0, INF_BAD_BLOCK_TYPE = 1, INF_BAD_STORED = 2, INF_BAD_LEN
 
 constexpr int INF_LIT_BITS = 10, INF_DIST_BITS = 8;
 
+// A table entry says everything the walk needs about a symbol: bits 0-3 the length of its code (0: not in the fast table),
+// bits 4-7 the number of extra bits that follow it, bits 8-9 what it is, bits 16-31 its value (the literal, the base of
+// the match length or of the distance).
+enum : uint32_t { K_LITERAL = 0, K_LENGTH = 1, K_END = 2, K_INVALID = 3 };
+SID_HD uint32_t make_entry(uint32_t kind, uint32_t extra, uint32_t value) { return (extra << 4) | (kind << 8) | (value << 16); }
+SID_HD uint32_t entry_kind(uint32_t e) { return (e >> 8) & 3u; }
+SID_HD uint32_t entry_value(uint32_t e) { return e >> 16; }
+
 struct InflateTables {
-    uint16_t lit_fast[1 << INF_LIT_BITS];   // (symbol << 4) | length for codes of at most INF_LIT_BITS bits, else 0
-    uint16_t dist_fast[1 << INF_DIST_BITS];
-    uint16_t lit_sym[288], dist_sym[32];    // symbols in canonical order (by length, then by value)
+    uint32_t lit_fast[1 << INF_LIT_BITS];   // entries of the codes of at most INF_LIT_BITS bits, by the next bits of the stream
+    uint32_t dist_fast[1 << INF_DIST_BITS];
+    uint16_t lit_sym[288], dist_sym[32];    // symbols in canonical order (by length, then by value): the longer codes
     uint16_t lit_cnt[16], dist_cnt[16];     // codes per length
 };
 
@@ -93,10 +101,32 @@ SID_HD uint32_t bit_reverse(uint32_t v, uint32_t n) {      // the low n bits of 
 #endif
 }
 
+SID_HD uint32_t length_base(uint32_t i) {       // length symbols 257..285 -> i = 0..28
+    return i < 8 ? 3 + i : i == 28 ? 258 : ((4 + (i & 3)) << ((i >> 2) - 1)) + 3;
+}
+SID_HD uint32_t length_extra(uint32_t i) { return i < 8 || i == 28 ? 0 : (i >> 2) - 1; }
+SID_HD uint32_t dist_base(uint32_t i) {         // distance symbols 0..29
+    return i < 4 ? 1 + i : ((2 + (i & 1)) << ((i >> 1) - 1)) + 1;
+}
+SID_HD uint32_t dist_extra(uint32_t i) { return i < 4 ? 0 : (i >> 1) - 1; }
+
+// The three alphabets of a block: literals / lengths, distances, and the code lengths of its header.
+enum : int { ALPHA_LITLEN = 0, ALPHA_DIST = 1, ALPHA_PLAIN = 2 };
+SID_HD uint32_t symbol_entry(int alphabet, uint32_t s) {
+    if (alphabet == ALPHA_LITLEN) {
+        if (s < 256) return make_entry(K_LITERAL, 0, s);
+        if (s == 256) return make_entry(K_END, 0, 0);
+        if (s > 285) return make_entry(K_INVALID, 0, 0);
+        return make_entry(K_LENGTH, length_extra(s - 257), length_base(s - 257));
+    }
+    if (alphabet == ALPHA_DIST) return s > 29 ? make_entry(K_INVALID, 0, 0) : make_entry(K_LITERAL, dist_extra(s), dist_base(s));
+    return make_entry(K_LITERAL, 0, s);
+}
+
 // Canonical Huffman code of `n` symbols with the given lengths (0 = unused): fast table of `bits` index bits, symbols in
 // canonical order, codes per length.  Returns false for an over-subscribed set of lengths (an incomplete one is accepted
-// like zlib accepts a single distance code; its unused codes decode to "bad symbol").
-SID_HD bool build_huffman(const uint8_t* lengths, uint32_t n, uint16_t* fast, uint32_t bits, uint16_t* sym, uint16_t* cnt) {
+// like zlib accepts a single distance code; its unused codes decode to K_INVALID).
+SID_HD bool build_huffman(int alphabet, const uint8_t* lengths, uint32_t n, uint32_t* fast, uint32_t bits, uint16_t* sym, uint16_t* cnt) {
     for (int l = 0; l < 16; ++l) cnt[l] = 0;
     for (uint32_t s = 0; s < n; ++s) ++cnt[lengths[s]];
     cnt[0] = 0;
@@ -120,45 +150,40 @@ SID_HD bool build_huffman(const uint8_t* lengths, uint32_t n, uint16_t* fast, ui
         sym[offs[l]++] = (uint16_t)s;
         const uint32_t c = next[l]++;
         if (l <= bits) {
-            const uint16_t e = (uint16_t)((s << 4) | l);
+            const uint32_t e = symbol_entry(alphabet, s) | l;
             for (uint32_t i = bit_reverse(c, l); i < (1u << bits); i += 1u << l) fast[i] = e;
         }
     }
     return true;
 }
 
-// Next symbol of the alphabet (fast, bits, cnt, sym); -1 for a code that is not in it.
-SID_HD int decode_symbol(BitReader& br, const uint16_t* fast, uint32_t bits, const uint16_t* cnt, const uint16_t* sym) {
+// Next symbol with its extra bits: its entry with the value completed (base + extra bits) in bits 16-31; code and extra
+// bits are consumed.  K_INVALID for a code that is not in the alphabet.
+SID_HD uint32_t decode_entry(BitReader& br, int alphabet, const uint32_t* fast, uint32_t bits, const uint16_t* cnt, const uint16_t* sym) {
     const uint32_t w = br.window();
-    const uint32_t e = fast[w & ((1u << bits) - 1u)];
-    if (e) {
-        br.drop(e & 15u);
-        return (int)(e >> 4);
-    }
-    int code = 0, first = 0, index = 0;
-    for (int l = 1; l < 16; ++l) {
-        code |= (int)((w >> (l - 1)) & 1u);
-        const int count = cnt[l];
-        if (code - count < first) {
-            br.drop((uint32_t)l);
-            return sym[index + (code - first)];
+    uint32_t e = fast[w & ((1u << bits) - 1u)];
+    if ((e & 15u) == 0) {
+        // a code longer than the table's index: the count/offset walk of the canonical order
+        int code = 0, first = 0, index = 0;
+        e = make_entry(K_INVALID, 0, 0) | 15u;
+        for (int l = 1; l < 16; ++l) {
+            code |= (int)((w >> (l - 1)) & 1u);
+            const int count = cnt[l];
+            if (code - count < first) {
+                e = symbol_entry(alphabet, sym[index + (code - first)]) | (uint32_t)l;
+                break;
+            }
+            index += count;
+            first += count;
+            first <<= 1;
+            code <<= 1;
         }
-        index += count;
-        first += count;
-        first <<= 1;
-        code <<= 1;
     }
-    return -1;
+    const uint32_t cl = e & 15u, xb = (e >> 4) & 15u;
+    const uint32_t extra = (w >> cl) & ((1u << xb) - 1u);          // cl + xb <= 28: all of it is in this window
+    br.drop(cl + xb);
+    return e + (extra << 16);
 }
-
-SID_HD uint32_t length_base(uint32_t i) {       // length symbols 257..285 -> i = 0..28
-    return i < 8 ? 3 + i : i == 28 ? 258 : ((4 + (i & 3)) << ((i >> 2) - 1)) + 3;
-}
-SID_HD uint32_t length_extra(uint32_t i) { return i < 8 || i == 28 ? 0 : (i >> 2) - 1; }
-SID_HD uint32_t dist_base(uint32_t i) {         // distance symbols 0..29
-    return i < 4 ? 1 + i : ((2 + (i & 1)) << ((i >> 1) - 1)) + 1;
-}
-SID_HD uint32_t dist_extra(uint32_t i) { return i < 4 ? 0 : (i >> 1) - 1; }
 
 // Header of a dynamic block (RFC 1951 3.2.7) or the fixed code (3.2.6) -> the two decoding tables.
 SID_HD int read_block_tables(BitReader& br, bool fixed, InflateTables& t) {
@@ -178,19 +203,20 @@ SID_HD int read_block_tables(BitReader& br, bool fixed, InflateTables& t) {
         uint8_t cl[19];
         for (int i = 0; i < 19; ++i) cl[i] = 0;
         for (uint32_t i = 0; i < ncode; ++i) {
-                // order of the code length code lengths: 16 17 18 0 8 7 9 6 10 5 11 4 12 3 13 2 14 1 15
+            // order of the code length code lengths: 16 17 18 0 8 7 9 6 10 5 11 4 12 3 13 2 14 1 15
             const uint32_t pos = i < 3 ? 16 + i : i == 3 ? 0 : (i & 1) ? (19 - i) / 2 : 6 + i / 2;
             cl[pos] = (uint8_t)br.take(3);
         }
-        // the code length alphabet reuses the distance arrays (they are rebuilt right after)
-        if (!build_huffman(cl, 19, t.dist_fast, 7, t.dist_sym, t.dist_cnt)) return INF_BAD_LENGTHS;
+        // the code length alphabet borrows the distance arrays (they are rebuilt right after)
+        if (!build_huffman(ALPHA_PLAIN, cl, 19, t.dist_fast, 7, t.dist_sym, t.dist_cnt)) return INF_BAD_LENGTHS;
         uint32_t i = 0;
         while (i < nlen + ndist) {
-            const int s = decode_symbol(br, t.dist_fast, 7, t.dist_cnt, t.dist_sym);
-            if (s < 0) return INF_BAD_LENGTHS;
+            const uint32_t e = decode_entry(br, ALPHA_PLAIN, t.dist_fast, 7, t.dist_cnt, t.dist_sym);
+            if (entry_kind(e) == K_INVALID) return INF_BAD_LENGTHS;
             if (br.over) return INF_INPUT_OVERRUN;
+            const uint32_t s = entry_value(e);
             if (s < 16) { lengths[i++] = (uint8_t)s; continue; }
-                uint32_t rep, val = 0;
+            uint32_t rep, val = 0;
             if (s == 16) {
                 if (i == 0) return INF_BAD_LENGTHS;
                 val = lengths[i - 1];
@@ -202,8 +228,8 @@ SID_HD int read_block_tables(BitReader& br, bool fixed, InflateTables& t) {
         }
         if (lengths[256] == 0) return INF_BAD_LENGTHS;          // no end-of-block code
     }
-    if (!build_huffman(lengths, nlen, t.lit_fast, INF_LIT_BITS, t.lit_sym, t.lit_cnt)) return INF_BAD_LENGTHS;
-    if (!build_huffman(lengths + nlen, ndist, t.dist_fast, INF_DIST_BITS, t.dist_sym, t.dist_cnt)) return INF_BAD_LENGTHS;
+    if (!build_huffman(ALPHA_LITLEN, lengths, nlen, t.lit_fast, INF_LIT_BITS, t.lit_sym, t.lit_cnt)) return INF_BAD_LENGTHS;
+    if (!build_huffman(ALPHA_DIST, lengths + nlen, ndist, t.dist_fast, INF_DIST_BITS, t.dist_sym, t.dist_cnt)) return INF_BAD_LENGTHS;
     return INF_OK;
 }
 
@@ -214,56 +240,28 @@ enum : uint32_t { EV_MATCH = 0, EV_END = 1, EV_ERROR = 2 };
 // *n_lit literals were stored, for EV_MATCH *len and *dist are set, for EV_ERROR *len is the code.
 SID_HD uint32_t decode_run(BitReader& br, const InflateTables& t, uint8_t* out, uint32_t pos, uint32_t out_len, uint32_t* n_lit,
                            uint32_t* len, uint32_t* dist) {
-    uint32_t n = 0;
+    uint32_t q = pos;
     for (;;) {
-        const int s = decode_symbol(br, t.lit_fast, INF_LIT_BITS, t.lit_cnt, t.lit_sym);
-        if (s < 0) { *n_lit = n; *len = INF_BAD_SYMBOL; return EV_ERROR; }
-        if (br.over) { *n_lit = n; *len = INF_INPUT_OVERRUN; return EV_ERROR; }
-        if (s < 256) {
-            if (pos + n >= out_len) { *n_lit = n; *len = INF_OUTPUT_OVERRUN; return EV_ERROR; }
-            out[pos + n] = (uint8_t)s;
-            ++n;
+        const uint32_t e = decode_entry(br, ALPHA_LITLEN, t.lit_fast, INF_LIT_BITS, t.lit_cnt, t.lit_sym);
+        const uint32_t kind = entry_kind(e);
+        if (kind == K_LITERAL) {
+            if (q >= out_len || br.over) { *n_lit = q - pos; *len = br.over ? INF_INPUT_OVERRUN : INF_OUTPUT_OVERRUN; return EV_ERROR; }
+            out[q++] = (uint8_t)entry_value(e);
             continue;
         }
-        *n_lit = n;
-        if (s == 256) return EV_END;
-        const uint32_t li = (uint32_t)s - 257;
-        if (li > 28) { *len = INF_BAD_SYMBOL; return EV_ERROR; }
-        const uint32_t l = length_base(li) + br.take(length_extra(li));
-        const int d = decode_symbol(br, t.dist_fast, INF_DIST_BITS, t.dist_cnt, t.dist_sym);
-        if (d < 0 || d > 29) { *len = INF_BAD_DISTANCE; return EV_ERROR; }
-        const uint32_t dd = dist_base((uint32_t)d) + br.take(dist_extra((uint32_t)d));
-        if (dd > pos + n) { *len = INF_BAD_DISTANCE; return EV_ERROR; }
-        if (pos + n + l > out_len) { *len = INF_OUTPUT_OVERRUN; return EV_ERROR; }
+        *n_lit = q - pos;
+        if (kind == K_END) return EV_END;
+        if (kind == K_INVALID) { *len = INF_BAD_SYMBOL; return EV_ERROR; }
+        const uint32_t l = entry_value(e);
+        const uint32_t d = decode_entry(br, ALPHA_DIST, t.dist_fast, INF_DIST_BITS, t.dist_cnt, t.dist_sym);
+        const uint32_t dd = entry_value(d);
+        if (entry_kind(d) == K_INVALID || dd > q) { *len = INF_BAD_DISTANCE; return EV_ERROR; }
+        if (q + l > out_len) { *len = INF_OUTPUT_OVERRUN; return EV_ERROR; }
+        if (br.over) { *len = INF_INPUT_OVERRUN; return EV_ERROR; }
         *len = l;
         *dist = dd;
         return EV_MATCH;
     }
-}
-
-// One symbol.  Returns STEP_LITERAL (stored at out[pos]), STEP_MATCH (*len, *dist set, nothing copied yet), STEP_END (end of
-// block) or STEP_ERROR (*len = code).
-enum : uint32_t { STEP_LITERAL = 0, STEP_MATCH = 1, STEP_END = 2, STEP_ERROR = 3 };
-SID_HD uint32_t decode_step(BitReader& br, const InflateTables& t, uint8_t* out, uint32_t pos, uint32_t out_len, uint32_t* len, uint32_t* dist) {
-    const int s = decode_symbol(br, t.lit_fast, INF_LIT_BITS, t.lit_cnt, t.lit_sym);
-    if (s < 0 || br.over) { *len = s < 0 ? INF_BAD_SYMBOL : INF_INPUT_OVERRUN; return STEP_ERROR; }
-    if (s < 256) {
-        if (pos >= out_len) { *len = INF_OUTPUT_OVERRUN; return STEP_ERROR; }
-        out[pos] = (uint8_t)s;
-        return STEP_LITERAL;
-    }
-    if (s == 256) return STEP_END;
-    const uint32_t li = (uint32_t)s - 257;
-    if (li > 28) { *len = INF_BAD_SYMBOL; return STEP_ERROR; }
-    const uint32_t l = length_base(li) + br.take(length_extra(li));
-    const int d = decode_symbol(br, t.dist_fast, INF_DIST_BITS, t.dist_cnt, t.dist_sym);
-    if (d < 0 || d > 29) { *len = INF_BAD_DISTANCE; return STEP_ERROR; }
-    const uint32_t dd = dist_base((uint32_t)d) + br.take(dist_extra((uint32_t)d));
-    if (dd > pos) { *len = INF_BAD_DISTANCE; return STEP_ERROR; }
-    if (pos + l > out_len) { *len = INF_OUTPUT_OVERRUN; return STEP_ERROR; }
-    *len = l;
-    *dist = dd;
-    return STEP_MATCH;
 }
 
 // Block header: BFINAL, BTYPE; a stored block is copied right here.  *final_block, *kind (0 stored: done, 1/2: tables built).
@@ -285,31 +283,6 @@ SID_HD int begin_block(BitReader& br, InflateTables& t, uint8_t* out, uint32_t* 
 }
 
 // One member on one thread (tests/hostcheck; the kernel below is the same walk with the matches copied by the warp).
-SID_HD int inflate_member_steps(const uint8_t* in, uint32_t in_len, uint8_t* out, uint32_t out_len, InflateTables& t) {
-    BitReader br;
-    br.init(in, in_len);
-    uint32_t pos = 0;
-    for (uint32_t guard = 0; guard < (1u << 20); ++guard) {
-        bool final_block;
-        uint32_t kind;
-        const int rc = begin_block(br, t, out, &pos, out_len, &final_block, &kind);
-        if (rc != INF_OK) return rc;
-        if (kind != 0) {
-            for (;;) {
-                uint32_t len = 0, dist = 0;
-                const uint32_t ev = decode_step(br, t, out, pos, out_len, &len, &dist);
-                if (ev == STEP_ERROR) return (int)len;
-                if (ev == STEP_END) break;
-                if (ev == STEP_LITERAL) { ++pos; continue; }
-                for (uint32_t k = 0; k < len; ++k) out[pos + k] = (out + pos - dist)[dist >= len ? k : k % dist];
-                pos += len;
-            }
-        }
-        if (final_block) return pos == out_len ? (br.overrun(in, in_len) ? INF_INPUT_OVERRUN : INF_OK) : INF_SIZE_MISMATCH;
-    }
-    return INF_BAD_BLOCK_TYPE;
-}
-
 SID_HD int inflate_member_serial(const uint8_t* in, uint32_t in_len, uint8_t* out, uint32_t out_len, InflateTables& t) {
     BitReader br;
     br.init(in, in_len);
@@ -337,7 +310,7 @@ SID_HD int inflate_member_serial(const uint8_t* in, uint32_t in_len, uint8_t* ou
 
 #if defined(__CUDACC__)
 
-constexpr int INF_WARPS = 8;        // members per CTA (one warp each; 3.3 KB of tables per warp)
+constexpr int INF_WARPS = 8;        // members per CTA (one warp each; 5.8 KB of tables per warp)
 
 // One warp per member, members dealt round robin.  error: (member index << 4 | code), the smallest wins.
 __global__ void __launch_bounds__(INF_WARPS * 32) k_inflate_bgzf(const uint8_t* comp, const BgzfBlock* blocks, uint32_t n_blocks, uint8_t* text,
@@ -399,100 +372,6 @@ __global__ void __launch_bounds__(INF_WARPS * 32) k_inflate_bgzf(const uint8_t* 
         if (!done && rc == INF_OK) rc = INF_BAD_BLOCK_TYPE;
         if (rc != INF_OK && lane == 0) atomicMin(error, ((unsigned long long)m << 4) | (unsigned long long)rc);
         __syncwarp();
-    }
-}
-
-// Lockstep form: a warp inflates 32 / SW members at once.  Lane 0 of every group of SW lanes (the leader) owns one member's
-// bit reader; every trip of the warp's loop each leader decodes ONE symbol -- the same instructions for all of them --
-// and the groups that met a match copy it with their SW lanes.  Block headers (table building) run on the leaders that
-// need them while the others wait; members are dealt group by group, a group that is done with its member takes the
-// next one of its warp's share.
-constexpr int INF2_WARPS = 4;
-template <int SW>
-__global__ void __launch_bounds__(INF2_WARPS * 32) k_inflate_bgzf_lockstep(const uint8_t* comp, const BgzfBlock* blocks, uint32_t n_blocks, uint8_t* text,
-                                                                            unsigned long long* error) {
-    constexpr int G = 32 / SW;
-    extern __shared__ __align__(16) uint8_t s_inf[];
-    InflateTables* const tables = reinterpret_cast<InflateTables*>(s_inf);
-    constexpr uint32_t FULL = 0xFFFFFFFFu;
-    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    const uint32_t sub = lane / SW, sl = lane % SW;
-    const bool leader = sl == 0;
-    InflateTables& t = tables[warp * G + sub];
-    enum : int { ST_NEXT = 0, ST_HEADER = 1, ST_SYMBOLS = 2, ST_DONE = 3 };
-    // members: decoder d of the grid takes d, d + D, d + 2 D, ...
-    const uint32_t n_dec = gridDim.x * INF2_WARPS * G;
-    uint32_t m = (blockIdx.x * INF2_WARPS + warp) * G + sub;
-    int st = ST_NEXT;
-    BitReader br;
-    br.wp = br.end = nullptr; br.lo = br.hi = br.p = 0; br.over = false;
-    uint8_t* out = text;
-    uint32_t out_len = 0, pos = 0, c_len = 0;
-    const uint8_t* in = comp;
-    bool final_block = false;
-    bool first = true;
-    for (uint32_t guard = 0; guard < 0x7FFFFFF0u; ++guard) {
-        uint32_t ev = STEP_LITERAL, len = 0, dist = 0;
-        int rc = INF_OK;
-        if (leader) {
-            if (st == ST_NEXT) {
-                if (!first) m += n_dec;
-                first = false;
-                if (m >= n_blocks) st = ST_DONE;
-                else {
-                    const BgzfBlock b = blocks[m];
-                    in = comp + b.c_off;
-                    c_len = b.c_len;
-                    out = text + b.out_off;
-                    out_len = b.isize;
-                    pos = 0;
-                    br.init(in, c_len);
-                    st = ST_HEADER;
-                }
-            }
-            if (st == ST_HEADER) {
-                uint32_t kind = 0;
-                rc = begin_block(br, t, out, &pos, out_len, &final_block, &kind);
-                if (rc == INF_OK) {
-                    if (kind != 0) st = ST_SYMBOLS;
-                    else if (final_block) {
-                        rc = pos != out_len ? INF_SIZE_MISMATCH : br.overrun(in, c_len) ? INF_INPUT_OVERRUN : INF_OK;
-                        st = ST_NEXT;
-                    }
-                }
-            } else if (st == ST_SYMBOLS) {
-                ev = decode_step(br, t, out, pos, out_len, &len, &dist);
-                if (ev == STEP_LITERAL) ++pos;
-                else if (ev == STEP_END) {
-                    if (final_block) {
-                        rc = pos != out_len ? INF_SIZE_MISMATCH : br.overrun(in, c_len) ? INF_INPUT_OVERRUN : INF_OK;
-                        st = ST_NEXT;
-                    } else st = ST_HEADER;
-                } else if (ev == STEP_ERROR) rc = (int)len;
-            }
-            if (rc != INF_OK) {
-                atomicMin(error, ((unsigned long long)m << 4) | (unsigned long long)rc);
-                st = ST_NEXT;                                   // give the member up, go on with the next one
-                ev = STEP_LITERAL;
-            }
-        }
-        // ---- matches: copied by the lanes of the group
-        const bool match = leader && ev == STEP_MATCH;
-        if (__any_sync(FULL, match)) {
-            const uint32_t ld = __shfl_sync(FULL, match ? (len | (dist << 16)) : 0u, 0, SW);      // dist <= 32768, len <= 258
-            const unsigned long long dst = __shfl_sync(FULL, (unsigned long long)(uintptr_t)(out + pos), 0, SW);
-            __syncwarp();                                       // the leaders' literals are visible to the lanes that copy
-            const uint32_t l = ld & 0xFFFFu, d = ld >> 16;
-            if (l) {
-                uint8_t* q = (uint8_t*)(uintptr_t)dst;
-                const uint8_t* src = q - d;
-                if (d >= l) for (uint32_t k = sl; k < l; k += SW) q[k] = src[k];
-                else for (uint32_t k = sl; k < l; k += SW) q[k] = src[k % d];
-            }
-            __syncwarp();
-            if (match) pos += len;
-        }
-        if (__all_sync(FULL, !leader || st == ST_DONE)) break;
     }
 }
 

@@ -29,11 +29,6 @@ int hc_inflate_member(const uint8_t* in, uint32_t in_len, uint8_t* out, uint32_t
     static thread_local InflateTables t;
     return inflate_member_serial(in, in_len, out, out_len, t);
 }
-// the same through the one-symbol step of the lockstep kernel
-int hc_inflate_member_steps(const uint8_t* in, uint32_t in_len, uint8_t* out, uint32_t out_len) {
-    static thread_local InflateTables t;
-    return inflate_member_steps(in, in_len, out, out_len, t);
-}
 
 struct hc_line {
     int32_t status, pos;

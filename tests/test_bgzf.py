@@ -91,7 +91,7 @@ def _hc_inflate(raw, n_out):
     import oracle_py as op
     hc = op.hostcheck()
     res = []
-    for fn in (hc.hc_inflate_member, hc.hc_inflate_member_steps):        # literal runs (one warp per member) / one symbol per step (lockstep)
+    for fn in (hc.hc_inflate_member,):
         fn.restype = ctypes.c_int
         fn.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_uint32]
         for lead in (0, 1, 2, 3):                     # every alignment of the stream's first byte
