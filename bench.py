@@ -49,6 +49,8 @@ def parse_args():
     ap.add_argument("--no-other", action="store_true", help="skip other_configs (Lynch depth 60, depth 500, quality)")
     ap.add_argument("--no-affinity", action="store_true", help="do not pin the rank's threads next to its GPU")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-bgzf", action="store_true", help="skip the compressed-input leg of cli_e2e")
+    ap.add_argument("--bgzf-sites", type=int, default=25000000, help="sites of the text that the compressed-input leg writes as a BGZF file")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -353,6 +355,94 @@ class Resident:
                 "exchange_ms_per_step": self.exchange_ms / max(self.exchanges, 1) if self.exchanges else None}
 
 
+def _bgzf_member(data):
+    import struct
+    import zlib
+    c = zlib.compressobj(6, zlib.DEFLATED, -15)
+    body = c.compress(data) + c.flush()
+    return (b"\x1f\x8b\x08\x04\0\0\0\0\x00\xff" + struct.pack("<H", 6) + b"BC" + struct.pack("<HH", 2, 12 + 6 + len(body) + 8 - 1) + body +
+            struct.pack("<II", zlib.crc32(data) & 0xFFFFFFFF, len(data)))
+
+
+def time_bgzf(args, h_text, text_len, n_sites):
+    """the same text as a BGZF file (what `bgzip` writes: gzip members of 65,280 bytes of text, zlib level 6).
+    The inflate kernel alone (all members in one launch), and `host/sid -m local file.plp.gz > /dev/null` with the members
+    inflated on the device against --host-inflate (the reader's threads) and against `zcat file > tmp` alone, the step the
+    reference's pipeline runs before sid sees a byte (scripts/sid-pipeline/run-sid.sh:15).  On a prefix of the text (the
+    file is written by Python's zlib here)."""
+    from concurrent.futures import ProcessPoolExecutor
+    import numpy as np
+    import torch
+    import sid_b200
+    sid = os.path.join(ROOT, "host", "sid")
+    if not os.path.exists(sid) or not os.path.isdir("/dev/shm"):
+        return None
+    sites = min(n_sites, args.bgzf_sites)
+    cut = text_len if sites == n_sites else int(text_len * (sites / n_sites))
+    raw = h_text[:cut].tobytes()
+    cut = raw.rfind(b"\n") + 1
+    raw = raw[:cut]
+    sites = raw.count(b"\n")
+    t0 = time.perf_counter()
+    with ProcessPoolExecutor(max_workers=os.cpu_count()) as ex:
+        members = list(ex.map(_bgzf_member, [raw[i:i + 65280] for i in range(0, len(raw), 65280)], chunksize=64))
+    comp = b"".join(members) + bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000")
+    res = {"sites": sites, "text_bytes": len(raw), "file_bytes": len(comp), "ratio": len(raw) / len(comp), "members": len(members),
+           "written_in_seconds": time.perf_counter() - t0}
+    path = os.path.join("/dev/shm", "sidbench_bgzf_%d.plp.gz" % os.getpid())
+    try:
+        with open(path, "wb") as f:
+            f.write(comp)
+        with sid_b200.Context(device=torch.cuda.current_device()) as ctx:
+            blocks, n, used, tb = ctx.bgzf_scan(comp)
+            d_comp = ctx.device_buffer(len(comp) + 32)
+            d_text = ctx.device_buffer(tb + 32)
+            d_comp.upload(np.frombuffer(comp, dtype=np.uint8))
+            ctx._ck(ctx.lib.sidgpu_inflate_bgzf(ctx.h, d_comp.ptr, len(comp), blocks, n, d_text.ptr, tb))
+            ctx.profile(True)
+            for _ in range(3):
+                ctx._ck(ctx.lib.sidgpu_inflate_bgzf(ctx.h, d_comp.ptr, len(comp), blocks, n, d_text.ptr, tb))
+            ms, launches = ctx.kernel_times()["inflate"]
+            same = d_text.download(np.uint8, tb).tobytes() == raw
+            d_comp.free()
+            d_text.free()
+        res["kernel"] = {"ms": ms / launches, "text_GBps": tb / (ms / launches) / 1e6, "compressed_GBps": len(comp) / (ms / launches) / 1e6,
+                         "equals_text": same, "what": "k_inflate_bgzf, one warp per member, all members in one launch (CUDA events)"}
+        env = dict(os.environ, SID_TIMING="1")
+
+        def run_sid(extra):
+            t0 = time.perf_counter()
+            pr = subprocess.run([sid, "-m", "local"] + extra + [path], stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, env=env)
+            dt = time.perf_counter() - t0
+            if pr.returncode != 0:
+                raise RuntimeError("sid exited with %d: %s" % (pr.returncode, pr.stderr.decode()[-300:]))
+            phases = [ln for ln in pr.stderr.decode().splitlines() if ln.startswith("# timing")]
+            streaming = None
+            try:
+                streaming = float(phases[-1].split("bytes")[1].split("s")[0])
+            except Exception:
+                pass
+            return dt, streaming
+
+        for name, extra in (("cli_device_inflate", []), ("cli_host_inflate", ["--host-inflate"])):
+            runs = [run_sid(extra) for _ in range(2)]
+            dt, streaming = min(runs)
+            res[name] = {"seconds": dt, "streaming_seconds": streaming, "value": sites / dt, "unit": UNIT,
+                         "text_GBps_streaming": len(raw) / streaming / 1e9 if streaming else None}
+        t0 = time.perf_counter()
+        subprocess.run("zcat %s > %s.tmp" % (path, path), shell=True, check=True)
+        res["zcat_to_tmp_seconds"] = time.perf_counter() - t0
+    except Exception as e:
+        res["error"] = "%s: %s" % (type(e).__name__, e)
+    finally:
+        for q in (path, path + ".tmp"):
+            try:
+                os.remove(q)
+            except OSError:
+                pass
+    return res
+
+
 def time_cli(args, h_text, text_len, n_sites):
     """`host/sid -m local file > /dev/null` on the same text, file in /dev/shm: what a user of the command line gets
     (process start, CUDA context, file read, rows written), timed like the reference arm."""
@@ -532,6 +622,8 @@ def run_ours(args):
     cpu = cli = None
     if rank == 0 and world == 1 and not args.no_e2e and args.method == "local":
         cli = time_cli(args, h_text, text_len, n_sites)          # before the reference runs: max_rss_mb is the largest child so far
+        if cli is not None and not args.no_bgzf:
+            cli["bgzf"] = time_bgzf(args, h_text, text_len, n_sites)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         v, kind, sample, dt = time_cpu(args, 1, min(args.cpu_sample_sites, n_sites))
         cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": kind, "sample": sample, "seconds": dt}
