@@ -50,7 +50,7 @@ def parse_args():
     ap.add_argument("--no-affinity", action="store_true", help="do not pin the rank's threads next to its GPU")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-bgzf", action="store_true", help="skip the compressed-input leg of cli_e2e")
-    ap.add_argument("--bgzf-sites", type=int, default=25000000, help="sites of the text that the compressed-input leg writes as a BGZF file")
+    ap.add_argument("--bgzf-sites", type=int, default=50000000, help="sites of the text that the compressed-input leg writes as a BGZF file")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 

@@ -9,6 +9,7 @@
 // fit, and then stream the rows of the site store out the same way; `quality -R` reads the text a second time
 // (rewind callback).
 
+#include <chrono>
 #include <condition_variable>
 #include <mutex>
 #include <thread>
@@ -44,6 +45,9 @@ struct IoPipe {
     std::vector<char> carry;                // the unfinished line at the end of the previous slot
     cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
     uint64_t total_sites = 0, total_rows = 0, total_bytes = 0;
+    // SIDGPU_IO_TIMING=1: where the caller's thread spends its time (seconds), printed to stderr at the end of the call
+    double t_wait_text = 0, t_upload = 0, t_inflate = 0, t_feed = 0, t_rows = 0, t_queue = 0, t_init = 0;
+    static double now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
     void set_error(int code, const std::string& msg) {
         std::lock_guard<std::mutex> g(m);
@@ -241,20 +245,32 @@ struct IoPipe {
         return SIDGPU_OK;
     }
 
-    // rows of the chunk (d_text, len) of a streaming session (or of the second pass of quality -R) into hp_csv[b]
-    int rows_of_chunk(int b, const char* d_text, size_t len, uint64_t* n_sites) {
+    // rows of the chunk (d_text, len) of a streaming session (or of the second pass of quality -R): fed at once, written
+    // in pieces of at most ROW_STEP sites through the two device buffers (a chunk of inflated BGZF members is several
+    // times the size of a text slot; the pinned CSV slots stay the size of a piece)
+    static constexpr uint64_t ROW_STEP = (uint64_t)1 << 20;
+    int rows_of_chunk(int b0, const char* d_text, size_t len, uint64_t* n_sites) {
         TRY(sidgpu_feed(ctx, d_text, len, 0, len, n_sites));
-        CK(cudaEventSynchronize(ev_out[b]));                        // the previous copy out of hp_csv[b] is done
-        uint64_t bytes = 0, rows = 0;
-        size_t want = std::max<size_t>(ctx->hp_csv[b].cap, (size_t)*n_sites * 48 + 4096);
-        for (;;) {
-            TRY(ensure(ctx, ctx->hp_csv[b], want));
-            const int rc = sidgpu_emit_csv(ctx, 0, *n_sites, (char*)ctx->hp_csv[b].p, ctx->hp_csv[b].cap, &bytes, &rows);
-            if (rc == SIDGPU_ECAPACITY && bytes + 4096 > want) { want = (size_t)bytes + 4096; continue; }
+        int b = b0;
+        for (uint64_t s0 = 0; s0 < *n_sites || s0 == 0; s0 += ROW_STEP, b ^= 1) {
+            const uint64_t count = std::min<uint64_t>(ROW_STEP, *n_sites - s0);
+            CK(cudaEventSynchronize(ev_out[b]));                    // the previous copy out of hp_csv[b] is done
+            uint64_t bytes = 0, rows = 0;
+            size_t want = std::max<size_t>(ctx->hp_csv[b].cap, (size_t)count * 48 + 4096);
+            for (;;) {
+                TRY(ensure(ctx, ctx->hp_csv[b], want));
+                const int rc = sidgpu_emit_csv(ctx, s0, count, (char*)ctx->hp_csv[b].p, ctx->hp_csv[b].cap, &bytes, &rows);
+                if (rc == SIDGPU_ECAPACITY && bytes + 4096 > want) { want = (size_t)bytes + 4096; continue; }
+                if (rc != SIDGPU_OK) return rc;
+                break;
+            }
+            const double q0 = now();
+            const int rc = queue_rows(b, bytes, rows);
+            t_queue += now() - q0;
             if (rc != SIDGPU_OK) return rc;
-            break;
+            if (*n_sites == 0) break;
         }
-        return queue_rows(b, bytes, rows);
+        return SIDGPU_OK;
     }
 
     // one pass over the input; emit: rows per chunk (streaming session / second pass), else the chunks are only fed
@@ -271,8 +287,13 @@ struct IoPipe {
         uint64_t uploaded = 0;
         for (uint64_t i = 0; rc == SIDGPU_OK; ++i) {
             if (uploaded <= i) {
-                if (!wait_text(i, true)) break;
+                const double w0 = now();
+                const bool have = wait_text(i, true);
+                t_wait_text += now() - w0;
+                if (!have) break;
+                const double u0 = now();
                 rc = upload(i);
+                t_upload += now() - u0;
                 if (rc != SIDGPU_OK) break;
                 uploaded = i + 1;
             }
@@ -285,13 +306,17 @@ struct IoPipe {
             size_t len = ts[i % NT].len;
             if (cudaStreamWaitEvent(ctx->stream, ev_in[b], 0) != cudaSuccess) { rc = ctx->fail(SIDGPU_ECUDA, "cudaStreamWaitEvent failed"); break; }
             if (bgzf) {
+                const double f0 = now();
                 rc = inflate_chunk(i, b, &len);
+                t_inflate += now() - f0;
                 if (rc != SIDGPU_OK) break;
             }
             uint64_t n = 0;
             if (len) {
+                const double f0 = now();
                 if (emit) rc = rows_of_chunk(b, (const char*)ctx->hp_text[b].p, len, &n);
                 else rc = sidgpu_feed(ctx, (const char*)ctx->hp_text[b].p, len, 0, len, &n);
+                t_feed += now() - f0;
                 total_sites += n;
             }
             release_text();                                         // the kernels are done with it (both calls synchronise), so is the copy
@@ -357,7 +382,9 @@ static int call_io(sidgpu_ctx* ctx, const sidgpu_params* params, const sidgpu_io
     pipe.ctx = ctx;
     pipe.io = io;
     pipe.bgzf = bgzf;
+    const double i0 = IoPipe::now();
     int rc = pipe.init();
+    pipe.t_init = IoPipe::now() - i0;
     std::thread wr;
     if (rc == SIDGPU_OK) wr = std::thread([&pipe] { pipe.writer(); });
     if (rc == SIDGPU_OK) rc = sidgpu_begin(ctx, params);
@@ -386,6 +413,9 @@ static int call_io(sidgpu_ctx* ctx, const sidgpu_params* params, const sidgpu_io
     cudaStreamSynchronize(ctx->stream);
     if (rc == SIDGPU_OK && pipe.error != SIDGPU_OK) { rc = pipe.error; ctx->err = pipe.errmsg; }
     pipe.destroy();
+    if (getenv("SIDGPU_IO_TIMING"))
+        fprintf(stderr, "# sidgpu_call_io: init %.3f, wait for text %.3f, upload %.3f, inflate %.3f, feed+rows %.3f (of which queueing rows %.3f) s\n",
+                pipe.t_init, pipe.t_wait_text, pipe.t_upload, pipe.t_inflate, pipe.t_feed, pipe.t_queue);
     if (csv_bytes) *csv_bytes = pipe.total_bytes;
     if (n_sites) *n_sites = pipe.total_sites;
     if (n_rows) *n_rows = pipe.total_rows;
