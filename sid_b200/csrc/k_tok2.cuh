@@ -20,6 +20,7 @@
 #include "k_quality.cuh"
 #include "k_tokenize.cuh"
 #include "parse_win.cuh"
+#include "parse_units.cuh"
 #include "row_assemble.cuh"
 
 namespace sid {
@@ -245,6 +246,9 @@ __device__ __forceinline__ bool parse_lines_by_windows(const uint8_t* txt, uint3
     return ok;
 }
 
+#ifndef SID_STAGE2_UNITS
+#define SID_STAGE2_UNITS 1      // stage 2 of ordinary lines: 1 = unit by unit (parse_units.cuh), 0 = 64-bit windows (parse_win.cuh)
+#endif
 #ifndef SID_TOK2_CTAS
 #define SID_TOK2_CTAS 3         // CTAs per SM the register allocator must leave room for (288 threads each: 72 registers)
 #endif
@@ -484,7 +488,11 @@ __global__ void __launch_bounds__(TOK_THREADS, DEEP ? 2 : (QUAL ? SID_TOK2_QUAL_
                         }
                         __syncwarp();
                     }
+#if SID_STAGE2_UNITS
+                    else fast = parse_line_units<true>(txt, region_off, cw, nlw, n_bits, TILE_PAD + off, wl);
+#else
                     else fast = parse_line_win<true>(txt, region_off, cw, nlw, n_bits, TILE_PAD + off, wl);
+#endif
                     r.status = wl.status; r.pos = wl.pos; r.profile = wl.profile; r.chrom_off = 0; r.chrom_len = wl.name_len;
                 }
                 if (!fast && mine) {

@@ -16,6 +16,7 @@
 #include "parse_swar.hpp"
 #include "../../sid_b200/csrc/parse_bits.cuh"
 #include "../../sid_b200/csrc/parse_win.cuh"
+#include "../../sid_b200/csrc/parse_units.cuh"
 #include "../../sid_b200/csrc/row_assemble.cuh"
 #endif
 
@@ -221,6 +222,33 @@ int64_t hc_compare_parsers_win(const uint8_t* text, uint64_t len, uint64_t* n_fa
             const int nd = fmt_i32(a.pos, digits);
             const bool same_text = b.hdr_len == a.chrom_len + 1 + (uint32_t)nd && memcmp(text + p + a.chrom_len + 1, digits, nd) == 0;
             if (same_text != b.pos_canonical) return -(k + 1);
+        }
+        ++k;
+    }
+    if (n_fast) *n_fast = fast;
+    return k;
+}
+
+// Stage 2 by units (parse_units.cuh: what the kernel runs on ordinary lines) against the byte-wise parser and against the
+// window form: the same lines accepted, the same results.  Same return convention.
+int64_t hc_compare_parsers_units(const uint8_t* text, uint64_t len, uint64_t* n_fast) {
+    FlatSrc src {text, len};
+    int64_t k = 0;
+    uint64_t fast = 0;
+    for (uint64_t p = 0; p < len; ++p) {
+        if (text[p] == '\n' || (p > 0 && text[p - 1] != '\n')) continue;
+        ParsedLine a;
+        parse_line(src, p, false, a);
+        WinLine b, c, w;
+        const bool fb = parse_line_units_host<true>(text, len, p, b), fc = parse_line_units_host<false>(text, len, p, c);
+        const bool fw = parse_line_win_host<true>(text, len, p, w);
+        if (fb != fc) return -(k + 1);
+        if (fb) {
+            ++fast;
+            if (a.status != LINE_OK || b.status != LINE_OK || a.profile != b.profile || a.pos != b.pos || c.profile != a.profile ||
+                a.chrom_off != 0 || a.chrom_len != b.name_len || c.name_len != b.name_len || b.hdr_len != c.hdr_len ||
+                b.pos_canonical != c.pos_canonical) return -(k + 1);
+            if (fw && (w.hdr_len != b.hdr_len || w.pos_canonical != b.pos_canonical)) return -(k + 1);
         }
         ++k;
     }

@@ -558,3 +558,50 @@ def test_quality_call_matches_oracle_on_deep_pileups(native):
     from sid_b200 import synth
     text = synth.generate(300, seed=7, lam=2000.0, het=0.02, err=0.02, start=0.05, indel=0.01, seven_columns=True)
     _quality_case(bytes(text))
+
+
+# ---- stage 2 by units (parse_units.cuh): the same three batteries as the window form, plus deep lines
+def _units(hc, text):
+    hc.hc_compare_parsers_units.restype = ctypes.c_int64
+    hc.hc_compare_parsers_units.argtypes = [ctypes.c_char_p, ctypes.c_uint64, ctypes.POINTER(ctypes.c_uint64)]
+    nf = ctypes.c_uint64()
+    k = hc.hc_compare_parsers_units(text, len(text), ctypes.byref(nf))
+    return k, nf.value
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3, 6, 7])
+def test_unit_tokenizer_equals_scalar_on_adversarial_lines(native, seed):
+    text = _adversarial_text(seed, 20000)
+    k, nf = _units(op.hostcheck(), text)
+    assert k > 0, text.split(b"\n")[-k - 1][:200] if k < 0 else None
+    assert nf > k // 100
+
+
+@pytest.mark.parametrize("name", ["depth30.plp", "depth500.plp", "depth5.plp", "quality30.plp", "edge.plp", "depth30_two_chroms.plp"])
+def test_unit_tokenizer_covers_normal_text(native, name):
+    text = read(name)
+    k, nf = _units(op.hostcheck(), text)
+    assert k > 0, text.split(b"\n")[-k - 1][:200] if k < 0 else None
+    if name != "edge.plp":
+        assert nf == k                # every ordinary line is handled without the byte-wise fallback
+
+
+def test_unit_tokenizer_long_fields_and_indels_at_unit_ends(native):
+    """Signs, numbers, '^' and skipped stretches at every offset around the 32-byte unit boundaries, and deep lines."""
+    rnd = random.Random(29)
+    lines = []
+    for k in range(8000):
+        pre = rnd.randrange(0, 140)
+        mid = rnd.choice(["+3ACG", "-12ACGTACGTACGT", "^+", "^1", "+", "-", "+0", "-1a", "^~", "+25" + "acgtn" * 5, "$", "^]", "+100" + "A" * 100,
+                          "-70" + "c" * 70, "^-", "+9", "+3ac", "+1234567890" + "a" * 40, "-00003acg", "^.", "^,", "+2^^", "-31" + "N" * 31, "+32" + "t" * 32])
+        post = rnd.randrange(0, 90)
+        bases = "".join(rnd.choice(".,ACGTacgt") for _ in range(pre)) + mid + "".join(rnd.choice(".,ACGTacgt*") for _ in range(post))
+        lines.append("%s\t%d\t%s\t%d\t%s\t%s" % (rnd.choice(["chr1", "c", "chr12_random", "x" * 17]), rnd.choice([1, 99, 123456789, 10 ** rnd.randrange(0, 9)]),
+                                                   rnd.choice("ACGTNacgt"), len(bases), bases, "I" * rnd.randrange(1, 50)))
+    text = ("\n".join(lines) + "\n").encode()
+    k, nf = _units(op.hostcheck(), text)
+    assert k == len(lines), text.split(b"\n")[-k - 1][:300] if k < 0 else None
+    assert nf >= k * 8 // 10          # "^^" and headers longer than 31 bytes leave the fast grammar, the rest stays
+    text = _deep_indel_lines(4, 400)
+    k, nf = _units(op.hostcheck(), text)
+    assert k == 400, text.split(b"\n")[-k - 1][:300] if k < 0 else None
