@@ -159,15 +159,18 @@ int sidgpu_read_fill(sidgpu_ctx* ctx, const char* d_text, size_t text_len, const
  *                        whole members it accepted (a member cut by `len` is left for the next call), *text_bytes =
  *                        their text.  SIDGPU_EINVAL for bytes that are not a BGZF member header.
  *   sidgpu_inflate_bgzf  inflates the listed members of the device buffer d_comp (4-byte aligned, readable 8 bytes
- *                        past comp_len) into d_text, one warp per member; checks every member against its ISIZE (not its
- *                        CRC-32); SIDGPU_EINVAL with the member's index in sidgpu_last_error for a damaged member.
+ *                        past comp_len) into d_text, one warp per member; checks every member's text against the ISIZE and
+ *                        the CRC-32 of its trailer; SIDGPU_EINVAL with the member's index in sidgpu_last_error for a
+ *                        damaged member.
  *   sidgpu_call_io_bgzf  sidgpu_call_io for a BGZF file: the read callback delivers the FILE's bytes (compressed).
  * --------------------------------------------------------------------------------------------- */
 typedef struct {
     uint64_t c_off;    /* offset of the member's deflate stream in the compressed buffer */
     uint64_t out_off;  /* offset of its text in the text buffer */
     uint32_t c_len;    /* bytes of the deflate stream */
-    uint32_t isize;    /* bytes of text */
+    uint32_t isize;    /* bytes of text (trailer) */
+    uint32_t crc;      /* CRC-32 of the text (trailer) */
+    uint32_t reserved;
 } sidgpu_bgzf_block;
 int sidgpu_bgzf_scan(const void* h_comp, size_t len, sidgpu_bgzf_block* blocks, size_t max_blocks, size_t text_cap,
                      size_t* n_blocks, size_t* consumed, size_t* text_bytes);

@@ -52,7 +52,8 @@ IO_REWIND = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p)
 
 
 class BgzfBlock(ctypes.Structure):
-    _fields_ = [("c_off", ctypes.c_uint64), ("out_off", ctypes.c_uint64), ("c_len", ctypes.c_uint32), ("isize", ctypes.c_uint32)]
+    _fields_ = [("c_off", ctypes.c_uint64), ("out_off", ctypes.c_uint64), ("c_len", ctypes.c_uint32), ("isize", ctypes.c_uint32),
+                ("crc", ctypes.c_uint32), ("reserved", ctypes.c_uint32)]
 
 
 class Io(ctypes.Structure):                  # sidgpu_io

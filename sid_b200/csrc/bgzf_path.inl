@@ -24,6 +24,7 @@ extern "C" int sidgpu_bgzf_scan(const void* h_comp, size_t len, sidgpu_bgzf_bloc
         if (q + block_len > len) break;                                 // block cut by the window
         const unsigned char* t = h + block_len - 4;
         const uint32_t isize = (uint32_t)t[0] | ((uint32_t)t[1] << 8) | ((uint32_t)t[2] << 16) | ((uint32_t)t[3] << 24);
+        const uint32_t crc = (uint32_t)t[-4] | ((uint32_t)t[-3] << 8) | ((uint32_t)t[-2] << 16) | ((uint32_t)t[-1] << 24);
         if (isize > 65536) return SIDGPU_EINVAL;
         if (out + isize > text_cap) break;
         if (isize) {                                                    // the end-of-file marker and other empty members carry no text
@@ -31,6 +32,8 @@ extern "C" int sidgpu_bgzf_scan(const void* h_comp, size_t len, sidgpu_bgzf_bloc
             blocks[n].out_off = out;
             blocks[n].c_len = (uint32_t)(block_len - 12 - xlen - 8);
             blocks[n].isize = isize;
+            blocks[n].crc = crc;
+            blocks[n].reserved = 0;
             ++n;
             out += isize;
         }
@@ -54,14 +57,36 @@ const char* inflate_error_text(int code) {
         case sid::INF_OUTPUT_OVERRUN: return "more text than the member's trailer says";
         case sid::INF_INPUT_OVERRUN: return "deflate stream runs past the member";
         case sid::INF_SIZE_MISMATCH: return "less text than the member's trailer says";
+        case sid::INF_CRC_MISMATCH: return "the text does not have the CRC-32 of the member's trailer";
         default: return "damaged member";
     }
+}
+
+// The tables of k_crc32_members, built once per ctx.
+int ensure_crc_tables(sidgpu_ctx* ctx) {
+    if (ctx->crc_tables.p) return SIDGPU_OK;
+    sid::CrcTables h;
+    for (uint32_t i = 0; i < 256; ++i) {
+        uint32_t c = i;
+        for (int k = 0; k < 8; ++k) c = (c & 1u) ? 0xEDB88320u ^ (c >> 1) : c >> 1;
+        h.byte_table[i] = c;
+    }
+    for (int j = 0; j < 32; ++j) {
+        uint32_t r = 1u << j;
+        for (uint32_t k = 0; k < sid::CRC_PIECE; ++k) r = h.byte_table[r & 0xFFu] ^ (r >> 8);
+        h.advance_2k[j] = r;
+    }
+    TRY(ensure(ctx, ctx->crc_tables, sizeof h));
+    CK(cudaMemcpyAsync(ctx->crc_tables.p, &h, sizeof h, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));          // `h` lives on this stack frame
+    return SIDGPU_OK;
 }
 
 // Queues the inflation of n members (table on the device) on ctx->stream; the error word is Control::error (reset here).
 int launch_inflate(sidgpu_ctx* ctx, const uint8_t* d_comp, const sid::BgzfBlock* d_blocks, size_t n, uint8_t* d_text) {
     CK(cudaMemsetAsync(ctl_field(ctx, &Control::error), 0xFF, sizeof(unsigned long long), ctx->stream));
     if (n == 0) return SIDGPU_OK;
+    TRY(ensure_crc_tables(ctx));
     static int per_sm = 0;
     if (per_sm == 0) {
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_inflate_bgzf, INF_WARPS * 32, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
@@ -70,7 +95,12 @@ int launch_inflate(sidgpu_ctx* ctx, const uint8_t* d_comp, const sid::BgzfBlock*
     const unsigned grid = (unsigned)std::min<size_t>(ctas, (size_t)ctx->sm_count * (size_t)per_sm);
     ProfScope prof(ctx, PROF_INFLATE);
     k_inflate_bgzf<<<grid, INF_WARPS * 32, 0, ctx->stream>>>(d_comp, d_blocks, (uint32_t)n, d_text, ctl_field(ctx, &Control::error));
-    return check_launch(ctx, "k_inflate_bgzf");
+    TRY(check_launch(ctx, "k_inflate_bgzf"));
+    // every member's text against the CRC-32 of its trailer (what zcat checks)
+    const unsigned crc_grid = (unsigned)std::min<size_t>((n + CRC_WARPS - 1) / CRC_WARPS, (size_t)ctx->sm_count * 8);
+    k_crc32_members<<<crc_grid, CRC_WARPS * 32, 0, ctx->stream>>>(d_text, d_blocks, (uint32_t)n, (const sid::CrcTables*)ctx->crc_tables.p,
+                                                                  ctl_field(ctx, &Control::error));
+    return check_launch(ctx, "k_crc32_members");
 }
 
 int inflate_failed(sidgpu_ctx* ctx) {        // after sync_ctl

@@ -8,7 +8,7 @@
 //   * runs of literals are stored by lane 0 as it decodes them; a match is broadcast and copied by all 32 lanes
 //     (out[p + k] = out[p - dist + k mod dist]: every byte comes from text that existed before the match began);
 //   * stored and fixed-Huffman blocks included; every loop is bounded by the member's compressed and inflated sizes
-//     (a damaged member is an error code, never a hang); ISIZE is checked, the CRC-32 is not (documented in DESIGN.md).
+//     (a damaged member is an error code, never a hang); ISIZE is checked by the decoder, the CRC-32 by k_crc32_members.
 // The table builder and the symbol decoder are SID_HD: tests/hostcheck inflates whole files with them on the CPU and
 // compares with zlib byte for byte.
 #pragma once
@@ -21,10 +21,12 @@ struct BgzfBlock {          // one gzip member of a BGZF file (filled by bgzf_sc
     uint64_t out_off;       // offset of its text in the output buffer
     uint32_t c_len;         // bytes of the deflate stream
     uint32_t isize;         // bytes of text (ISIZE of the trailer)
+    uint32_t crc;           // CRC-32 of the text (trailer)
+    uint32_t reserved;
 };
 
 enum : int { INF_OK = 0, INF_BAD_BLOCK_TYPE = 1, INF_BAD_STORED = 2, INF_BAD_LENGTHS = 3, INF_BAD_SYMBOL = 4, INF_BAD_DISTANCE = 5,
-             INF_OUTPUT_OVERRUN = 6, INF_INPUT_OVERRUN = 7, INF_SIZE_MISMATCH = 8 };
+             INF_OUTPUT_OVERRUN = 6, INF_INPUT_OVERRUN = 7, INF_SIZE_MISMATCH = 8, INF_CRC_MISMATCH = 9 };
 
 constexpr int INF_LIT_BITS = 10, INF_DIST_BITS = 8;
 
@@ -372,6 +374,47 @@ __global__ void __launch_bounds__(INF_WARPS * 32) k_inflate_bgzf(const uint8_t* 
         if (!done && rc == INF_OK) rc = INF_BAD_BLOCK_TYPE;
         if (rc != INF_OK && lane == 0) atomicMin(error, ((unsigned long long)m << 4) | (unsigned long long)rc);
         __syncwarp();
+    }
+}
+
+// ---- CRC-32 (the gzip trailer's, polynomial 0xEDB88320 reflected) of every member's text, one warp per member.
+// The register after a message is linear in (message, start value): lane i runs the byte-wise table walk over its 2 KiB
+// piece COUNTED FROM THE END of the text (the lane that holds byte 0 starts from 0xFFFFFFFF, the others from 0), so lane i's
+// register has to be advanced by exactly i * 2048 zero bytes; Horner over the lanes with the one operator "advance by 2048
+// zero bytes" (a 32 x 32 bit matrix, column `lane` in lane `lane`; a matrix-vector product is one select and an
+// exclusive-or reduction over the warp) gives the register of the whole text.
+struct CrcTables {
+    uint32_t byte_table[256];       // the usual table of the byte-wise walk
+    uint32_t advance_2k[32];        // column j: register 1 << j advanced by 2048 zero bytes
+};
+constexpr uint32_t CRC_PIECE = 2048;
+constexpr int CRC_WARPS = 8;
+
+__global__ void __launch_bounds__(CRC_WARPS * 32) k_crc32_members(const uint8_t* text, const BgzfBlock* blocks, uint32_t n_blocks, const CrcTables* tables,
+                                                                    unsigned long long* error) {
+    __shared__ uint32_t s_table[256];
+    for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) s_table[i] = tables->byte_table[i];
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t column = tables->advance_2k[lane];
+    for (uint32_t m = blockIdx.x * CRC_WARPS + warp; m < n_blocks; m += gridDim.x * CRC_WARPS) {
+        const BgzfBlock b = blocks[m];
+        const uint8_t* p = text + b.out_off;
+        const uint32_t n = b.isize;
+        // lane i: bytes [n - (i + 1) * 2048, n - i * 2048) cut at 0
+        const uint32_t hi = n > lane * CRC_PIECE ? n - lane * CRC_PIECE : 0u;
+        const uint32_t lo = hi > CRC_PIECE ? hi - CRC_PIECE : 0u;
+        uint32_t reg = (hi > 0 && lo == 0) ? 0xFFFFFFFFu : 0u;
+        for (uint32_t k = lo; k < hi; ++k) reg = s_table[(reg ^ p[k]) & 0xFFu] ^ (reg >> 8);
+        // Horner from the lane farthest from the end: acc = advance(acc) ^ reg_i, i = 31 .. 0
+        uint32_t acc = 0;
+        for (int i = 31; i >= 0; --i) {
+            uint32_t v = ((acc >> lane) & 1u) ? column : 0u;        // advance: exclusive-or of the columns of the set bits
+#pragma unroll
+            for (int d = 16; d; d >>= 1) v ^= __shfl_xor_sync(0xFFFFFFFFu, v, d);
+            acc = v ^ __shfl_sync(0xFFFFFFFFu, reg, i);
+        }
+        if (lane == 0 && (acc ^ 0xFFFFFFFFu) != b.crc) atomicMin(error, ((unsigned long long)m << 4) | (unsigned long long)INF_CRC_MISMATCH);
     }
 }
 

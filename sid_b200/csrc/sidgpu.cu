@@ -128,6 +128,7 @@ struct sidgpu_ctx {
     // sidgpu_call_host staging (two text buffers, two CSV buffers, their events), kept across calls
     DevBuf hp_text[2], hp_csv[2];
     DevBuf hp_comp[2], inf_blocks[2];  // BGZF input: compressed chunks and their member tables (bgzf_path.inl)
+    DevBuf crc_tables;                 // k_crc32_members
     cudaEvent_t hp_ev_in[2] = {nullptr, nullptr}, hp_ev_out[2] = {nullptr, nullptr};
 
     // optional per-kernel timing (sidgpu_profile): event pairs recorded around launches, resolved lazily
@@ -1192,7 +1193,7 @@ void sidgpu_destroy(sidgpu_ctx* ctx) {
     for (DevBuf* b : {&ctx->blk, &ctx->blk_part, &ctx->order, &ctx->v_pos, &ctx->v_slot, &ctx->v_name_ref, &ctx->v_profile, &ctx->v_line_off, &ctx->csv_status, &ctx->pos, &ctx->slot, &ctx->name_ref, &ctx->profile, &ctx->line_off,
                       &ctx->site_suffix, &ctx->rows_scratch, &ctx->rows_part, &ctx->rows_part_rows, &ctx->sort_keys, &ctx->sort_vals, &ctx->u_profile, &ctx->u_count, &ctx->u_logM,
                       &ctx->entry_to_unique, &ctx->g_e2u, &ctx->p_hom, &ctx->p_het, &ctx->adj_hom, &ctx->adj_het, &ctx->bh_c, &ctx->bh_block,
-                      &ctx->partials, &ctx->quality_lut, &ctx->hp_comp[0], &ctx->hp_comp[1], &ctx->inf_blocks[0], &ctx->inf_blocks[1]})
+                      &ctx->partials, &ctx->quality_lut, &ctx->hp_comp[0], &ctx->hp_comp[1], &ctx->inf_blocks[0], &ctx->inf_blocks[1], &ctx->crc_tables})
         release(*b);
     if (ctx->d_ctl) cudaFree(ctx->d_ctl);
     if (ctx->h_ctl) cudaFreeHost(ctx->h_ctl);

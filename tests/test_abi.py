@@ -58,11 +58,13 @@ def test_ctypes_structs_match_the_header(tmp_path):
         'int main(void) {\n'
         '  printf("%zu %zu %zu %zu\\n", sizeof(sidgpu_params), offsetof(sidgpu_params, het_only), offsetof(sidgpu_params, fit_nd), sizeof(sidgpu_config));\n'
         '  printf("%zu %zu %zu\\n", sizeof(sidgpu_sites_view), sizeof(sidgpu_unique_view), sizeof(sidgpu_fit));\n'
+        '  printf("%zu %zu %zu\\n", sizeof(sidgpu_bgzf_block), offsetof(sidgpu_bgzf_block, isize), offsetof(sidgpu_bgzf_block, crc));\n'
         '  return 0;\n}\n')
     exe = tmp_path / "layout"
     subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
     out = subprocess.run([str(exe)], stdout=subprocess.PIPE, check=True, text=True).stdout.split()
     got = [int(x) for x in out]
     want = [ctypes.sizeof(_lib.Params), _lib.Params.het_only.offset, _lib.Params.fit_nd.offset, ctypes.sizeof(_lib.Config),
-            ctypes.sizeof(_lib.SitesView), ctypes.sizeof(_lib.UniqueView), ctypes.sizeof(_lib.Fit)]
+            ctypes.sizeof(_lib.SitesView), ctypes.sizeof(_lib.UniqueView), ctypes.sizeof(_lib.Fit),
+            ctypes.sizeof(_lib.BgzfBlock), _lib.BgzfBlock.isize.offset, _lib.BgzfBlock.crc.offset]
     assert got == want

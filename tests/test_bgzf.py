@@ -171,7 +171,8 @@ def test_bgzf_scan_lists_the_members():
     comp = bgzf_compress(text, 5000)
 
     class Block(ctypes.Structure):
-        _fields_ = [("c_off", ctypes.c_uint64), ("out_off", ctypes.c_uint64), ("c_len", ctypes.c_uint32), ("isize", ctypes.c_uint32)]
+        _fields_ = [("c_off", ctypes.c_uint64), ("out_off", ctypes.c_uint64), ("c_len", ctypes.c_uint32), ("isize", ctypes.c_uint32),
+                    ("crc", ctypes.c_uint32), ("reserved", ctypes.c_uint32)]
 
     blocks = (Block * 4096)()
     n, consumed, tbytes = ctypes.c_size_t(), ctypes.c_size_t(), ctypes.c_size_t()
@@ -181,6 +182,7 @@ def test_bgzf_scan_lists_the_members():
     got = b"".join(zlib.decompress(comp[b.c_off:b.c_off + b.c_len], -15) for b in blocks[:n.value])
     assert got == text
     assert [b.out_off for b in blocks[:3]] == [0, 5000, 10000]
+    assert [b.crc for b in blocks[:3]] == [zlib.crc32(text[i:i + 5000]) for i in (0, 5000, 10000)]
     # a window that cuts a member, a text cap, a member limit
     assert lib.sidgpu_bgzf_scan(buf.ctypes.data, len(comp) - 40, blocks, 4096, 1 << 40, ctypes.byref(n), ctypes.byref(consumed), ctypes.byref(tbytes)) == 0
     assert consumed.value < len(comp) - 40 and tbytes.value == 5000 * n.value

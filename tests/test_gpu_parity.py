@@ -282,6 +282,15 @@ def test_inflate_bgzf_on_device(native, gpu_ctx, block):
     except (sid_b200.SidGpuError, ValueError) as e:
         assert "BGZF" in str(e) or "truncated" in str(e)
     assert gpu_ctx.inflate_bgzf(comp) == text                                 # and the ctx stays usable
+    # a member whose deflate stream is intact but whose text is not what its trailer's CRC-32 says (zcat: "crc error")
+    blocks, n, used, tb = gpu_ctx.bgzf_scan(comp)
+    k = n // 2
+    t_off = blocks[k].c_off + blocks[k].c_len                                 # the trailer follows the deflate stream
+    wrong = bytearray(comp)
+    wrong[t_off] ^= 0x01
+    with pytest.raises(sid_b200.SidGpuError) as e:
+        gpu_ctx.inflate_bgzf(bytes(wrong))
+    assert "member %d" % k in str(e.value) and "CRC-32" in str(e.value)
 
 
 @pytest.mark.parametrize("case", [c for c in MANIFEST["cases"] if c["csv"] in ("depth30.m_local.csv", "depth30_two_chroms.m_bayes.csv",
