@@ -50,6 +50,7 @@ def parse_args():
     ap.add_argument("--no-affinity", action="store_true", help="do not pin the rank's threads next to its GPU")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-bgzf", action="store_true", help="skip the compressed-input leg of cli_e2e")
+    ap.add_argument("--bgzf-sample-sites", type=int, default=6250000, help="sites of the sample that e2e_bgzf compresses and repeats")
     ap.add_argument("--bgzf-sites", type=int, default=50000000, help="sites of the text that the compressed-input leg writes as a BGZF file")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -364,6 +365,53 @@ def _bgzf_member(data):
             struct.pack("<II", zlib.crc32(data) & 0xFFFFFFFF, len(data)))
 
 
+def bgzf_e2e_leg(args, env, ctx, h_text, text_len, n_sites, h_csv_t, csv_cap, world):
+    """sidgpu_call_host_bgzf on pinned host buffers: the rank's text as a BGZF file (zlib level 6, members of 65,280 bytes).
+    Python's zlib writes a sample of the text once; the file is that sample's members repeated until it holds the step's
+    number of sites (the calling path does not care that positions repeat)."""
+    import ctypes
+    from concurrent.futures import ProcessPoolExecutor
+    import numpy as np
+    import torch
+    import sid_b200
+    sample_sites = min(n_sites, args.bgzf_sample_sites)
+    cut = int(text_len * (sample_sites / n_sites))
+    raw = h_text[:cut].tobytes()
+    raw = raw[:raw.rfind(b"\n") + 1]
+    sample_sites = raw.count(b"\n")
+    workers = max(1, (os.cpu_count() or 1) // max(1, world))
+    with ProcessPoolExecutor(max_workers=workers) as ex:
+        members = b"".join(ex.map(_bgzf_member, [raw[i:i + 65280] for i in range(0, len(raw), 65280)], chunksize=64))
+    reps = max(1, n_sites // sample_sites)
+    sites = reps * sample_sites
+    comp_len = reps * len(members)
+    h_comp = torch.empty(comp_len + 64, dtype=torch.uint8, pin_memory=True)
+    view = h_comp.numpy()
+    one = np.frombuffer(members, dtype=np.uint8)
+    for r in range(reps):
+        view[r * len(members):(r + 1) * len(members)] = one
+    p = sid_b200.Context.make_params("local")
+    nb, ns, nr = ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_uint64()
+
+    def one_step():
+        ctx._ck(ctx.lib.sidgpu_call_host_bgzf(ctx.h, ctypes.byref(p), h_comp.data_ptr(), comp_len, h_csv_t.data_ptr(), csv_cap,
+                                              ctypes.byref(nb), ctypes.byref(ns), ctypes.byref(nr)))
+    one_step()
+    assert ns.value == sites, (ns.value, sites)
+    env.barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        one_step()
+    env.barrier()
+    ms = env.max_over_ranks((time.perf_counter() - t0) * 1e3) / args.steps
+    del h_comp
+    return {"value": world * sites / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "sites_per_gpu": sites,
+            "h2d_bytes_per_step": comp_len, "d2h_bytes_per_step": int(nb.value), "text_bytes_per_step": reps * len(raw),
+            "ratio": len(raw) / len(members),
+            "what": "sidgpu_call_host_bgzf, pinned BGZF bytes -> pinned CSV, host wall clock, max over ranks; the file is a "
+                    "%d-site sample of the step's text (zlib level 6) repeated %d times" % (sample_sites, reps)}
+
+
 def time_bgzf(args, h_text, text_len, n_sites):
     """the same text as a BGZF file (what `bgzip` writes: gzip members of 65,280 bytes of text, zlib level 6).
     The inflate kernel alone (all members in one launch), and `host/sid -m local file.plp.gz > /dev/null` with the members
@@ -618,6 +666,16 @@ def run_ours(args):
             e2e_het = {"value": world * n_sites / (ms2 * 1e-3), "unit": UNIT, "h2d_bytes_per_step": text_len, "d2h_bytes_per_step": nb2,
                        "ms_per_step": ms2, "frac_of_h2d_bound": h2d_ms / ms2}
 
+    # ---- the same step from COMPRESSED input in host memory: a BGZF file of the step's text, its members
+    #      inflated on the device; only the compressed bytes cross the host link (which all ranks of a box share)
+    e2e_bgzf = None
+    if not args.no_e2e and not args.no_bgzf and args.method == "local" and not args.het_only:
+        try:
+            e2e_bgzf = bgzf_e2e_leg(args, env, ctx, h_text, text_len, n_sites, h_csv_t, csv_cap, world)
+        except Exception as e:                  # a side measurement never takes the headline line down
+            e2e_bgzf = {"error": "%s: %s" % (type(e).__name__, e)}
+        env.barrier()
+
     # ---- the reference's CPU path on this box's host cores (rank 0, N=1 only)
     cpu = cli = None
     if rank == 0 and world == 1 and not args.no_e2e and args.method == "local":
@@ -705,7 +763,7 @@ def run_ours(args):
                          "limiter": "integer ALU pipe, 71 % of its peak in profiles/r2_ncu_full_sites.txt (DRAM 18 %): "
                                     "the HBM roofline is the contract's bound, not what this kernel runs into",
                          "kernel_ms_per_step": r["kernel_ms_per_step"]},
-            "e2e": e2e, "e2e_het_only": e2e_het, "cli_e2e": cli, "cpu_baseline": cpu, "gpu_launches": launches, "clocks": clocks.summary(),
+            "e2e": e2e, "e2e_het_only": e2e_het, "e2e_bgzf": e2e_bgzf, "cli_e2e": cli, "cpu_baseline": cpu, "gpu_launches": launches, "clocks": clocks.summary(),
             "lynch_fit": state.get("fit"), "other_configs": other,
         }
         print(json.dumps(line))

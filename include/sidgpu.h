@@ -163,6 +163,7 @@ int sidgpu_read_fill(sidgpu_ctx* ctx, const char* d_text, size_t text_len, const
  *                        the CRC-32 of its trailer; SIDGPU_EINVAL with the member's index in sidgpu_last_error for a
  *                        damaged member.
  *   sidgpu_call_io_bgzf  sidgpu_call_io for a BGZF file: the read callback delivers the FILE's bytes (compressed).
+ *   sidgpu_call_host_bgzf  the same from a host buffer to a host buffer.
  * --------------------------------------------------------------------------------------------- */
 typedef struct {
     uint64_t c_off;    /* offset of the member's deflate stream in the compressed buffer */
@@ -176,6 +177,10 @@ int sidgpu_bgzf_scan(const void* h_comp, size_t len, sidgpu_bgzf_block* blocks, 
                      size_t* n_blocks, size_t* consumed, size_t* text_bytes);
 int sidgpu_inflate_bgzf(sidgpu_ctx* ctx, const void* d_comp, size_t comp_len, const sidgpu_bgzf_block* h_blocks, size_t n_blocks,
                         char* d_text, size_t text_cap);
+/* sidgpu_call_host (below) for a BGZF file that lies in host memory: h_comp holds the FILE's bytes (pin it for speed), the
+ * members are inflated on the device chunk by chunk; everything else as sidgpu_call_host. */
+int sidgpu_call_host_bgzf(sidgpu_ctx* ctx, const sidgpu_params* params, const void* h_comp, size_t comp_len, char* h_csv,
+                          size_t csv_cap, uint64_t* csv_bytes, uint64_t* n_sites, uint64_t* n_rows);
 
 /* ------------------------------------------------------------------------------------------------
  * Calling sessions: the four functions of call.hpp:40-43, streamed.

@@ -95,6 +95,8 @@ PROTOTYPES = {
                                         ctypes.c_void_p, ctypes.c_size_t, c_u64_p, c_u64_p, c_u64_p]),
     "sidgpu_call_io": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(Params), ctypes.POINTER(Io), c_u64_p, c_u64_p, c_u64_p]),
     "sidgpu_call_io_bgzf": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(Params), ctypes.POINTER(Io), c_u64_p, c_u64_p, c_u64_p]),
+    "sidgpu_call_host_bgzf": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(Params), ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t,
+                                             c_u64_p, c_u64_p, c_u64_p]),
     "sidgpu_bgzf_scan": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t,
                                         ctypes.POINTER(ctypes.c_size_t), ctypes.POINTER(ctypes.c_size_t), ctypes.POINTER(ctypes.c_size_t)]),
     "sidgpu_inflate_bgzf": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t]),

@@ -394,6 +394,20 @@ class Context:
             self._ck(rc)
             return out[:nb.value].tobytes(), ns.value, nr.value
 
+    def call_host_bgzf(self, comp, params, csv_capacity=None):
+        """call_host for the bytes of a BGZF file (its members are inflated on the device): (csv_rows_bytes, n_sites, n_rows)."""
+        a = _as_u8(comp)
+        cap = int(csv_capacity) if csv_capacity else max(4096, 6 * a.nbytes)
+        while True:
+            out = np.empty(cap, dtype=np.uint8)
+            nb, ns, nr = ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_uint64()
+            rc = self.lib.sidgpu_call_host_bgzf(self.h, ctypes.byref(params), a.ctypes.data if a.nbytes else None, a.nbytes,
+                                                out.ctypes.data, cap, ctypes.byref(nb), ctypes.byref(ns), ctypes.byref(nr))
+            if rc == 6 and nb.value > cap:
+                cap = nb.value + 4096
+                continue
+            self._ck(rc)
+            return out[:nb.value].tobytes(), ns.value, nr.value
 
     def bgzf_scan(self, comp, text_cap=1 << 62, max_blocks=None):
         """Member table of BGZF bytes (host only): (blocks array, consumed bytes, text bytes)."""

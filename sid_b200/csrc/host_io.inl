@@ -32,7 +32,7 @@ struct IoPipe {
     bool bgzf = false;                      // the read callback delivers a BGZF file: members are inflated on the device
     static constexpr size_t MAX_BLOCKS = (size_t)1 << 16;
     size_t text_cap = 0;                    // bgzf: text bytes one chunk may inflate to
-    size_t tail[2] = {0, 0};                // bgzf: bytes of an unfinished line already at the front of hp_text[b]
+    BgzfChunks chunks {nullptr, 0};         // bgzf: the inflate chains of the two text buffers (bgzf_path.inl)
     struct CsvSlot { char* p = nullptr; size_t cap = 0, len = 0; cudaEvent_t ev = nullptr; } cs[NC];
     std::mutex m;
     std::condition_variable cv;
@@ -193,31 +193,6 @@ struct IoPipe {
         return SIDGPU_OK;
     }
 
-    // bgzf: inflates the members of slot i behind the unfinished line the chunk before left in hp_text[b]; *keep = bytes
-    // of whole lines (everything for the last chunk); what follows them opens the other buffer
-    int inflate_chunk(uint64_t i, int b, size_t* keep) {
-        TextSlot& s = ts[i % NT];
-        const size_t t0 = tail[b], total = t0 + s.text_len;
-        TRY(ensure(ctx, ctx->hp_text[b], ((total + 15) & ~(size_t)15) + 32, t0 != 0));
-        TRY(launch_inflate(ctx, (const uint8_t*)ctx->hp_comp[b].p, (const sid::BgzfBlock*)ctx->inf_blocks[b].p, s.n_blocks,
-                           (uint8_t*)ctx->hp_text[b].p + t0));
-        const bool cut = !s.last && total != 0;
-        if (cut) {
-            k_last_line_end<<<1, 256, 0, ctx->stream>>>((const uint8_t*)ctx->hp_text[b].p, total, ctl_field(ctx, &Control::csv_bytes));
-            TRY(check_launch(ctx, "k_last_line_end"));
-        }
-        TRY(sync_ctl(ctx));
-        TRY(inflate_failed(ctx));
-        *keep = cut ? (size_t)ctx->h_ctl->csv_bytes : total;
-        const size_t rest = total - *keep;
-        tail[b ^ 1] = rest;
-        if (rest) {
-            TRY(ensure(ctx, ctx->hp_text[b ^ 1], ((rest + text_cap + 15) & ~(size_t)15) + 32));
-            CK(cudaMemcpyAsync(ctx->hp_text[b ^ 1].p, (const char*)ctx->hp_text[b].p + *keep, rest, cudaMemcpyDeviceToDevice, ctx->stream));
-        }
-        return SIDGPU_OK;
-    }
-
     // queues the copy of `bytes` rows in hp_csv[b] to the next pinned CSV slot
     int queue_rows(int b, uint64_t bytes, uint64_t rows) {
         uint64_t k;
@@ -280,7 +255,13 @@ struct IoPipe {
             t_prod = t_cons = 0;
             eof = false;
             carry.clear();
-            tail[0] = tail[1] = 0;
+        }
+        uint64_t launched = 0;                                      // bgzf: chunks whose inflate chain has been queued
+        if (bgzf) {
+            chunks.ctx = ctx;
+            chunks.text_cap = text_cap;
+            const int rc0 = chunks.prepare();
+            if (rc0 != SIDGPU_OK) return rc0;
         }
         std::thread rd([this] { reader(); });
         int rc = SIDGPU_OK;
@@ -306,8 +287,19 @@ struct IoPipe {
             size_t len = ts[i % NT].len;
             if (cudaStreamWaitEvent(ctx->stream, ev_in[b], 0) != cudaSuccess) { rc = ctx->fail(SIDGPU_ECUDA, "cudaStreamWaitEvent failed"); break; }
             if (bgzf) {
+                // the chain of chunk i was queued while chunk i - 1 was being called (or is queued now: the first chunk,
+                // or the reader was late); the chain of chunk i + 1 goes out as soon as this one says where its lines end
                 const double f0 = now();
-                rc = inflate_chunk(i, b, &len);
+                if (launched <= i) {
+                    rc = chunks.launch(b, ev_in[b], ts[i % NT].n_blocks, ts[i % NT].text_len, ts[i % NT].last);
+                    launched = i + 1;
+                }
+                if (rc == SIDGPU_OK) rc = chunks.finish(b, &len);
+                if (rc == SIDGPU_OK && uploaded > i + 1 && launched <= i + 1) {
+                    const TextSlot& nx = ts[(i + 1) % NT];
+                    rc = chunks.launch(b ^ 1, ev_in[b ^ 1], nx.n_blocks, nx.text_len, nx.last);
+                    launched = i + 2;
+                }
                 t_inflate += now() - f0;
                 if (rc != SIDGPU_OK) break;
             }

@@ -129,6 +129,11 @@ struct sidgpu_ctx {
     DevBuf hp_text[2], hp_csv[2];
     DevBuf hp_comp[2], inf_blocks[2];  // BGZF input: compressed chunks and their member tables (bgzf_path.inl)
     DevBuf crc_tables;                 // k_crc32_members
+    cudaStream_t inflate_stream = nullptr;              // the inflate of chunk i + 1 runs beside the calling kernels of chunk i
+    cudaEvent_t ev_inflate[2] = {nullptr, nullptr};
+    unsigned long long* d_inf = nullptr;                // per text buffer: inflate error word, end of the last whole line
+    unsigned long long* h_inf = nullptr;                // mapped pinned mirror, written by k_publish_words
+    unsigned long long* h_inf_dev = nullptr;
     cudaEvent_t hp_ev_in[2] = {nullptr, nullptr}, hp_ev_out[2] = {nullptr, nullptr};
 
     // optional per-kernel timing (sidgpu_profile): event pairs recorded around launches, resolved lazily
@@ -239,11 +244,12 @@ struct ProfScope {
     sidgpu_ctx* ctx;
     cudaEvent_t a = nullptr;
     int which;
-    ProfScope(sidgpu_ctx* c, int w) : ctx(c), which(w) {
-        if (ctx->profiling) { a = take_event(ctx); cudaEventRecord(a, ctx->stream); }
+    cudaStream_t stream;
+    ProfScope(sidgpu_ctx* c, int w, cudaStream_t s = nullptr) : ctx(c), which(w), stream(s ? s : c->stream) {
+        if (ctx->profiling) { a = take_event(ctx); cudaEventRecord(a, stream); }
     }
     ~ProfScope() {
-        if (a) { cudaEvent_t b = take_event(ctx); cudaEventRecord(b, ctx->stream); ctx->pending.push_back({a, b, which}); }
+        if (a) { cudaEvent_t b = take_event(ctx); cudaEventRecord(b, stream); ctx->pending.push_back({a, b, which}); }
     }
 };
 
@@ -1197,6 +1203,10 @@ void sidgpu_destroy(sidgpu_ctx* ctx) {
         release(*b);
     if (ctx->d_ctl) cudaFree(ctx->d_ctl);
     if (ctx->h_ctl) cudaFreeHost(ctx->h_ctl);
+    if (ctx->inflate_stream) cudaStreamDestroy(ctx->inflate_stream);
+    for (int i = 0; i < 2; ++i) if (ctx->ev_inflate[i]) cudaEventDestroy(ctx->ev_inflate[i]);
+    if (ctx->d_inf) cudaFree(ctx->d_inf);
+    if (ctx->h_inf) cudaFreeHost(ctx->h_inf);
     if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
     if (ctx->copy_out) cudaStreamDestroy(ctx->copy_out);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);

@@ -316,6 +316,25 @@ def test_call_io_bgzf_streams_the_same_rows(native, case, block):
     assert diffs <= max(2, n // 1000)
 
 
+@pytest.mark.parametrize("case", [c for c in MANIFEST["cases"] if c["csv"] in ("depth30.m_local.csv", "depth30_two_chroms.m_bayes.csv",
+                                                                                "quality30.m_quality_R.csv", "depth500.m_local.csv", "edge.m_local.csv",
+                                                                                "depth30.m_likelihood_ratio_R.csv")],
+                         ids=lambda c: c["csv"])
+def test_call_host_bgzf(native, case):
+    """sidgpu_call_host_bgzf: BGZF bytes in host memory in, rows out (small chunks: lines straddle them)."""
+    import sid_b200
+    from test_bgzf import bgzf_compress
+    text = read(case["input"])
+    with sid_b200.Context(max_chunk_bytes=1 << 16) as ctx:
+        rows, n_sites, n_rows = ctx.call_host_bgzf(bgzf_compress(text, 3000), params_from_flags(case["flags"]))
+        n, diffs = op.compare_csv(sid_b200.CSV_HEADER + rows, read(case["csv"]))
+        assert n == n_rows
+        assert diffs <= max(2, n // 1000)
+        assert ctx.call_host_bgzf(b"", params_from_flags(case["flags"]))[1:] == (0, 0)
+        with pytest.raises(sid_b200.SidGpuError):
+            ctx.call_host_bgzf(bgzf_compress(text)[:-40], params_from_flags(case["flags"]))
+
+
 def test_call_io_bgzf_errors(native, gpu_ctx):
     import io
     import sid_b200
