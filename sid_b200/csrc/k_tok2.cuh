@@ -414,21 +414,30 @@ __global__ void __launch_bounds__(TOK_THREADS, DEEP ? 2 : (QUAL ? SID_TOK2_QUAL_
                         }
                     }
                 }
-                const uint32_t my_count = __popc(st);
-                uint32_t incl = my_count;
+                // lines of 32 bytes and more start at most once per unit: their index is a population count of the
+                // ballot; a unit with two starts (short lines) sends the group through the general scan
+                const uint32_t has = __ballot_sync(0xFFFFFFFFu, st != 0);
+                if (!__any_sync(0xFFFFFFFFu, (st & (st - 1)) != 0)) {
+                    const uint32_t idx = n_lines + __popc(has & ((1u << lane) - 1u));
+                    if (st && idx < p.lines_cap) starts[idx] = (uint16_t)(slice_off + u * 32 + (__ffs((int)st) - 1));
+                    n_lines += __popc(has);
+                } else {
+                    const uint32_t my_count = __popc(st);
+                    uint32_t incl = my_count;
 #pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-                    if (lane >= d) incl += o;
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+                        if (lane >= d) incl += o;
+                    }
+                    uint32_t idx = n_lines + incl - my_count;
+                    while (st) {
+                        const int bit = __ffs((int)st) - 1;
+                        st &= st - 1;
+                        if (idx < p.lines_cap) starts[idx] = (uint16_t)(slice_off + u * 32 + bit);
+                        ++idx;
+                    }
+                    n_lines += __shfl_sync(0xFFFFFFFFu, incl, 31);
                 }
-                uint32_t idx = n_lines + incl - my_count;
-                while (st) {
-                    const int bit = __ffs((int)st) - 1;
-                    st &= st - 1;
-                    if (idx < p.lines_cap) starts[idx] = (uint16_t)(slice_off + u * 32 + bit);
-                    ++idx;
-                }
-                n_lines += __shfl_sync(0xFFFFFFFFu, incl, 31);
             }
             if (lane < (int)CW_PAD_UNITS) {
                 uint4* rec = reinterpret_cast<uint4*>(cw + (size_t)(units + lane) * CW_WORDS);
@@ -508,13 +517,12 @@ __global__ void __launch_bounds__(TOK_THREADS, DEEP ? 2 : (QUAL ? SID_TOK2_QUAL_
                         uint4 nm = make_uint4(0, 0, 0, 0);
                         if (len <= 16) {
                             const uint2 hi = load8_unaligned(txt, l0_off + 8);
-                            uint32_t wds[4] = {first8.x, first8.y, hi.x, hi.y};
-#pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                const int rem = (int)len - 4 * k;
-                                if (rem <= 0) wds[k] = 0; else if (rem < 4) wds[k] &= (1u << (8 * rem)) - 1u;
-                            }
-                            nm = make_uint4(wds[0], wds[1], wds[2], wds[3]);
+                            // the name's bytes, zero beyond its length
+                            const unsigned long long lo64 = ((unsigned long long)first8.y << 32) | first8.x, hi64 = ((unsigned long long)hi.y << 32) | hi.x;
+                            const unsigned long long mlo = len >= 8 ? ~0ull : ((1ull << (8 * len)) - 1ull);
+                            const unsigned long long mhi = len <= 8 ? 0ull : len >= 16 ? ~0ull : ((1ull << (8 * (len - 8))) - 1ull);
+                            const unsigned long long a64 = lo64 & mlo, b64 = hi64 & mhi;
+                            nm = make_uint4((uint32_t)a64, (uint32_t)(a64 >> 32), (uint32_t)b64, (uint32_t)(b64 >> 32));
                         }
                         if (len <= 16 && len == cache_len && cache_ref && nm.x == cache_name.x && nm.y == cache_name.y &&
                             nm.z == cache_name.z && nm.w == cache_name.w) {
