@@ -106,7 +106,8 @@ int sidgpu_memcpy_d2d_async(sidgpu_ctx* ctx, void* d_dst, const void* d_src, siz
  * a line that straddles range_end is read to its end (up to text_len).  Empty lines are skipped
  * (call.cpp:14).  d_text must be 16-byte aligned.
  * want_qual: 0 = five columns suffice; 1 = the quality columns are required as `quality` requires them (pileup.cpp:42-66)
- * and d_line_off is filled; 2 = d_line_off is filled, the quality columns are not looked at.
+ * and d_line_off is filled; 2 = d_line_off is filled, the quality columns are not looked at; 3 = as 2, and the tokenizer
+ * also counts the strands (a by-product of the same pass): d_fwd is filled.
  * --------------------------------------------------------------------------------------------- */
 typedef struct {
     uint64_t n_sites;          /* lines parsed by the call */
@@ -119,6 +120,9 @@ typedef struct {
     const uint32_t* d_name_ref;
     const char* d_names;
     uint64_t names_bytes;
+    /* only with want_qual == 3: per site, the profile of the bases read on the FORWARD strand (upper-case characters and
+     * '.'; pileup.cpp:78-124), packed like d_profile; the reverse strand is d_profile - d_fwd, count by count */
+    const uint64_t* d_fwd;
 } sidgpu_sites_view;
 
 int sidgpu_tokenize(sidgpu_ctx* ctx, const char* d_text, size_t text_len, size_t range_begin,

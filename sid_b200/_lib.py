@@ -32,7 +32,7 @@ class Columns(ctypes.Structure):
 class SitesView(ctypes.Structure):
     _fields_ = [("n_sites", c_u64), ("d_profile", ctypes.c_void_p), ("d_pos", ctypes.c_void_p),
                 ("d_slot", ctypes.c_void_p), ("d_line_off", ctypes.c_void_p), ("d_name_ref", ctypes.c_void_p),
-                ("d_names", ctypes.c_void_p), ("names_bytes", c_u64)]
+                ("d_names", ctypes.c_void_p), ("names_bytes", c_u64), ("d_fwd", ctypes.c_void_p)]
 
 
 class UniqueView(ctypes.Structure):

@@ -144,10 +144,11 @@ class Context:
         end = text_len if end is None else end
         v = SitesView()
         ptr = d_text.ptr if isinstance(d_text, DeviceBuffer) else d_text
-        self._ck(self.lib.sidgpu_tokenize(self.h, ptr, text_len, begin, end, 1 if want_qual else (2 if strands else 0), ctypes.byref(v)))
+        self._ck(self.lib.sidgpu_tokenize(self.h, ptr, text_len, begin, end, 1 if want_qual else (3 if strands else 0), ctypes.byref(v)))
         n = v.n_sites
         fwd = rev = None
-        if strands:
+        if strands and want_qual:
+            # the quality columns are wanted (and validated) too: the strands by their own pass over the line offsets
             buf = DeviceBuffer(self, max(16, 16 * n))
             try:
                 self._ck(self.lib.sidgpu_strand_counts(self.h, ptr, text_len, v.d_line_off, n, buf.ptr, buf.ptr + 8 * n))
@@ -155,6 +156,14 @@ class Context:
                 fwd, rev = both[:n].copy(), both[n:].copy()
             finally:
                 buf.free()
+        elif strands:
+            # a by-product of the tokenizer pass: the forward profile; the reverse one is the rest of the profile, count by count
+            fwd = self._download(v.d_fwd, np.uint64, n)
+            prof = self._download(v.d_profile, np.uint64, n)
+            f4 = np.stack([(fwd >> np.uint64(16 * i)) & np.uint64(0xFFFF) for i in range(4)], axis=1)
+            p4 = np.stack([(prof >> np.uint64(16 * i)) & np.uint64(0xFFFF) for i in range(4)], axis=1)
+            r4 = (p4 - f4) & np.uint64(0xFFFF)
+            rev = r4[:, 0] | (r4[:, 1] << np.uint64(16)) | (r4[:, 2] << np.uint64(32)) | (r4[:, 3] << np.uint64(48))
         names_pool = self._download(v.d_names, np.uint8, v.names_bytes).tobytes()
         refs = self._download(v.d_name_ref, np.uint32, n)
         cache = {}

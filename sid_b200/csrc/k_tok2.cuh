@@ -40,6 +40,7 @@ struct Tok2Params {
     uint32_t* slot;
     uint32_t* name_ref;
     uint64_t* line_off;
+    uint64_t* fwd;                  // STRANDS: per site, the profile of the bases read on the forward strand
     double* qual_l;                 // QUAL: two doubles per site, the log-likelihood sums of `-m quality` (+inf: not formed here)
     const double* qual_lut;         // QUAL: the per-read term tables (k_quality.cuh)
     unsigned long long* site_alloc;
@@ -60,9 +61,10 @@ struct Tok2Params {
 
 // units_cap: units (32 bytes) a parse warp classifies, slice + ext, plus the zero padding
 SID_HD uint32_t tok2_units(uint32_t slice, uint32_t ext) { return (slice + ext) / 32u; }
-inline uint32_t tok2_dyn_smem(uint32_t slice, uint32_t ext, uint32_t stages, bool rows) {
+inline uint32_t tok2_dyn_smem(uint32_t slice, uint32_t ext, uint32_t stages, bool rows, bool strands = false) {
     const uint32_t units = tok2_units(slice, ext) + CW_PAD_UNITS;
-    return stages * tok_text_stride(slice, ext) + 8u * (slice / 8u) * 2u + 8u * units * (CW_WORDS + 1u) * 4u + (rows ? 8u * ROW_STAGE : 0u);
+    return stages * tok_text_stride(slice, ext) + 8u * (slice / 8u) * 2u + 8u * units * (CW_WORDS + 1u) * 4u + (rows ? 8u * ROW_STAGE : 0u) +
+           (strands ? 8u * units * 4u : 0u);
 }
 
 #if defined(__CUDACC__)
@@ -142,6 +144,22 @@ __device__ __noinline__ void parse_line_slow(const uint8_t* txt, uint64_t abs0, 
         FlatSrc gsrc {text, text_len};
         parse_line(gsrc, line_abs, want_qual, pl);
     }
+}
+
+// The forward-strand profile of a line the byte-wise parser took (rare): the same walk over its bases field, from global memory.
+__device__ __noinline__ uint64_t forward_profile_slow(const uint8_t* text, uint64_t text_len, uint64_t line_abs, const ParsedLine& pl) {
+    FlatSrc src {text, text_len};
+    BasesState st;
+    st.init((uint8_t)pl.ref);
+    uint32_t c[4] = {0, 0, 0, 0};
+    for (uint32_t k = 0; k < pl.bases_len; ++k) {
+        const uint8_t ch = src.at(line_abs + pl.bases_off + k);
+        const int idx = st.feed(ch);
+        if (idx < 0) continue;
+        const uint8_t seen = ch == '.' ? st.dot_as : ch == ',' ? st.comma_as : ch;      // pileup.cpp:78-83
+        if (!(seen & 0x20u)) ++c[idx];
+    }
+    return pack_profile(c[0], c[1], c[2], c[3]);
 }
 
 // Stage 2 of a slice of LONG lines, warp-collective: the lines of the slice one per lane (line_off; `mine` false on
@@ -260,8 +278,12 @@ __device__ __forceinline__ bool parse_lines_by_windows(const uint8_t* txt, uint3
 #endif
 // QUAL: the instantiation of quality sessions: the per-read sums of callQualityBasedSimple are formed right here, from the
 // class windows of the line (k_quality.cuh: quality_sums_win), instead of a second byte-wise walk over the text in k_quality.
-template <bool ROWS, int TOK_STAGES, bool DEEP = false, bool QUAL = false>
+// STRANDS: the instantiation that also keeps, per site, the profile of the forward strand (the strands
+// parseReadBases derives and nobody reads): stage 1 stores bit plane 5 of every unit, stage 2 counts the upper-case letters
+// and the '.' beside the profile.
+template <bool ROWS, int TOK_STAGES, bool DEEP = false, bool QUAL = false, bool STRANDS = false>
 __global__ void __launch_bounds__(TOK_THREADS, DEEP ? 2 : (QUAL ? SID_TOK2_QUAL_CTAS : SID_TOK2_CTAS)) k_tok2(const Tok2Params p) {
+    static_assert(!STRANDS || (!ROWS && !DEEP && !QUAL), "strand counts come from the ordinary sites form");
     extern __shared__ __align__(128) uint8_t s_dyn[];
     __shared__ StageMeta s_meta[TOK_STAGES];
     __shared__ __align__(8) uint64_t s_full[TOK_STAGES], s_done[TOK_STAGES];
@@ -360,6 +382,7 @@ __global__ void __launch_bounds__(TOK_THREADS, DEEP ? 2 : (QUAL ? SID_TOK2_QUAL_
     uint32_t* const cw = cw_all + (size_t)pw * p.units_cap * CW_WORDS;                    // 32-byte records: 16-byte aligned
     uint32_t* const nlw = cw_all + (size_t)TOK_PARSE_WARPS * p.units_cap * CW_WORDS + (size_t)pw * p.units_cap;
     uint8_t* const stage = reinterpret_cast<uint8_t*>(cw_all + (size_t)TOK_PARSE_WARPS * p.units_cap * (CW_WORDS + 1)) + (size_t)pw * ROW_STAGE;
+    uint32_t* const p5w = cw_all + (size_t)TOK_PARSE_WARPS * p.units_cap * (CW_WORDS + 1) + (size_t)pw * p.units_cap;     // STRANDS (never with ROWS)
     uint32_t cache_len = 0, cache_ref = 0;
     uint4 cache_name = make_uint4(0, 0, 0, 0);
     for (uint32_t it = 0;; ++it) {
@@ -392,6 +415,7 @@ __global__ void __launch_bounds__(TOK_THREADS, DEEP ? 2 : (QUAL ? SID_TOK2_QUAL_
                     rec[0] = make_uint4(k.w[0], k.w[1], k.w[2], k.w[3]);
                     rec[1] = make_uint4(k.w[4], k.w[5], k.w[6], k.w[7]);
                     nlw[u] = k.nl;
+                    if (STRANDS) p5w[u] = k.p5;
                     nl = k.nl;
                     bad |= k.bad;
                     if (DEEP) tw = k.w[CW_TERM];
@@ -444,6 +468,7 @@ __global__ void __launch_bounds__(TOK_THREADS, DEEP ? 2 : (QUAL ? SID_TOK2_QUAL_
                 rec[0] = make_uint4(0, 0, 0, 0);
                 rec[1] = make_uint4(0, 0, 0, 0);
                 nlw[units + lane] = 0;
+                if (STRANDS) p5w[units + lane] = 0;
             }
             if (n_lines > p.lines_cap) {
                 if (lane == 0) report_error_at(p.error, tb, LINE_MALFORMED);
@@ -482,6 +507,7 @@ __global__ void __launch_bounds__(TOK_THREADS, DEEP ? 2 : (QUAL ? SID_TOK2_QUAL_
                 LineResult r;
                 r.status = LINE_MALFORMED;
                 bool fast = false;
+                uint64_t fwd = 0;                                             // STRANDS
                 double ql1 = bits_double(0x7FF0000000000000ull), ql2 = 0;     // QUAL: +inf = "k_quality walks this line itself"
                 if (win_ok) {
                     WinLine wl;
@@ -498,6 +524,7 @@ __global__ void __launch_bounds__(TOK_THREADS, DEEP ? 2 : (QUAL ? SID_TOK2_QUAL_
                         __syncwarp();
                     }
 #if SID_STAGE2_UNITS
+                    else if (STRANDS) fast = parse_line_units<true, true>(txt, region_off, cw, nlw, n_bits, TILE_PAD + off, wl, p5w, &fwd);
                     else fast = parse_line_units<true>(txt, region_off, cw, nlw, n_bits, TILE_PAD + off, wl);
 #else
                     else fast = parse_line_win<true>(txt, region_off, cw, nlw, n_bits, TILE_PAD + off, wl);
@@ -508,6 +535,7 @@ __global__ void __launch_bounds__(TOK_THREADS, DEEP ? 2 : (QUAL ? SID_TOK2_QUAL_
                     ParsedLine pl;
                     parse_line_slow(txt, abs0, tile_smem, p.text, p.text_len, line_abs, p.want_qual != 0, pl);
                     r.status = pl.status; r.pos = pl.pos; r.profile = pl.profile; r.chrom_off = pl.chrom_off; r.chrom_len = pl.chrom_len;
+                    if (STRANDS && pl.status == LINE_OK) fwd = forward_profile_slow(p.text, p.text_len, line_abs, pl);
                 }
                 __syncwarp();
                 const bool good = mine && r.status == LINE_OK;
@@ -552,6 +580,7 @@ __global__ void __launch_bounds__(TOK_THREADS, DEEP ? 2 : (QUAL ? SID_TOK2_QUAL_
                         p.name_ref[site] = ref;
                         if (p.profile) p.profile[site] = r.profile;
                         if (p.line_off) p.line_off[site] = line_abs;
+                        if (STRANDS) p.fwd[site] = fwd;
                         if (QUAL) { p.qual_l[2 * site] = fast ? ql1 : bits_double(0x7FF0000000000000ull); p.qual_l[2 * site + 1] = ql2; }
                         if (p.use_table) p.slot[site] = slot;
                     }

@@ -26,9 +26,11 @@ SID_HD UnitRec load_unit(const uint32_t* cw, uint32_t u) {
 SID_HD uint32_t low_bits32(uint32_t n) { return n >= 32 ? 0xFFFFFFFFu : ((1u << n) - 1u); }     // bits [0, n)
 
 // parsePileupLine + parseReadBases (pileup.cpp:13-153) of the line at line_off; arguments as parse_line_win.
-template <bool WANT_POS>
+// STRANDS: p5w holds the raw bit plane 5 of every unit (lower case); *fwd receives the profile of the bases read on the forward
+// strand (upper-case letters and '.', pileup.cpp:78-124: ReadStack::strands summed per letter; reverse = profile - fwd).
+template <bool WANT_POS, bool STRANDS = false>
 SID_HD bool parse_line_units(const uint8_t* s, uint32_t region_off, const uint32_t* cw, const uint32_t* nlw, uint32_t n_bits,
-                             uint32_t line_off, WinLine& o) {
+                             uint32_t line_off, WinLine& o, const uint32_t* p5w = nullptr, uint64_t* fwd = nullptr) {
     const uint32_t ls = line_off - region_off;                      // bit index of the line's first byte
     bool ok = line_off >= region_off && ls + 64 <= n_bits && line_off >= 12;
     const uint32_t l0 = ok ? ls : 0, h0 = ok ? line_off : region_off + 16;
@@ -100,6 +102,7 @@ SID_HD bool parse_line_units(const uint8_t* s, uint32_t region_off, const uint32
     uint32_t valid = 0xFFFFFFFFu << (a & 31);                       // bits of the unit that belong to the field (so far as it starts here)
     uint32_t skip = 0;                                              // bytes at the start of the next unit still covered by a '^' or an indel
     uint32_t cn = 0, c1 = 0, c2 = 0, c12 = 0, cd = 0;
+    uint32_t fn = 0, f1 = 0, f2 = 0, f12 = 0, fd = 0;              // STRANDS: the same counts over the forward strand only
     UnitRec r = uu == u0 ? r0 : r1;
     bool running = ok;
     while (running) {
@@ -146,6 +149,14 @@ SID_HD bool parse_line_units(const uint8_t* s, uint32_t region_off, const uint32
         c2 += pop_count(b & r.w[CW_P2]);
         c12 += pop_count(b & r.w[CW_P1] & r.w[CW_P2]);
         cd += pop_count(r.w[CW_DOT] & live);
+        if (STRANDS) {
+            const uint32_t fb = b & ~p5w[uu];                       // upper-case letters
+            fn += pop_count(fb);
+            f1 += pop_count(fb & r.w[CW_P1]);
+            f2 += pop_count(fb & r.w[CW_P2]);
+            f12 += pop_count(fb & r.w[CW_P1] & r.w[CW_P2]);
+            fd += pop_count(r.w[CW_DOT] & r.w[CW_P1] & live);       // '.' (0x2e) has bit 1, ',' (0x2c) has not
+        }
         if (last || !ok) running = false;
         else {
             ++uu;
@@ -158,6 +169,7 @@ SID_HD bool parse_line_units(const uint8_t* s, uint32_t region_off, const uint32
     WinHeader hd;
     hd.l0 = l0; hd.q4 = q4; hd.ref_base = ref_base; hd.ref_p1 = ref_p1; hd.ref_p2 = ref_p2;
     o.profile = win_profile(cn, c1, c2, c12, cd, hd);
+    if (STRANDS) *fwd = win_profile(fn, f1, f2, f12, fd, hd);
     o.status = LINE_OK;
     return ok;
 }
@@ -165,10 +177,18 @@ SID_HD bool parse_line_units(const uint8_t* s, uint32_t region_off, const uint32
 #if !defined(__CUDACC__)
 // Host check: stage 2 by units on the line at p, classified like the kernel's stage 1.
 template <bool WANT_POS>
-inline bool parse_line_units_host(const uint8_t* text, uint64_t len, uint64_t p, WinLine& o) {
+inline bool parse_line_units_host(const uint8_t* text, uint64_t len, uint64_t p, WinLine& o, uint64_t* fwd = nullptr) {
     const HostLineClasses h = classify_line_host(text, len, p);
     if (!h.usable) return false;
-    return parse_line_units<WANT_POS>(h.scratch, 0, h.cw, h.nlw, h.units * 32, h.line_off, o);
+    if (!fwd) return parse_line_units<WANT_POS>(h.scratch, 0, h.cw, h.nlw, h.units * 32, h.line_off, o);
+    // plane 5 of every classified unit, as the STRANDS tokenizer keeps it
+    static thread_local uint32_t p5w[(1u << 15) + 8];
+    for (uint32_t u = 0; u < h.units + CW_PAD_UNITS; ++u) {
+        uint32_t v = 0;
+        if (u < h.units) for (int i = 0; i < 32; ++i) v |= (uint32_t)((h.scratch[32 * u + i] >> 5) & 1u) << i;
+        p5w[u] = v;
+    }
+    return parse_line_units<WANT_POS, true>(h.scratch, 0, h.cw, h.nlw, h.units * 32, h.line_off, o, p5w, fwd);
 }
 #endif
 

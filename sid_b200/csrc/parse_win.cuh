@@ -30,6 +30,7 @@ struct UnitClasses {
     uint32_t w[CW_WORDS];   // bit i of each word <-> byte i of the unit
     uint32_t nl;            // '\n'
     uint32_t bad;           // control bytes other than '\t' and '\n' (NUL included): their lines leave the fast path
+    uint32_t p5;            // raw bit plane 5: on a letter, lower case = the reverse strand (pileup.cpp:85-124)
 };
 
 SID_HD uint32_t popc64(uint64_t x) {
@@ -85,6 +86,7 @@ SID_HD UnitClasses classify_unit(const uint32_t b[8]) {
     const uint32_t space = lop3<TA & ~TB & TC>(lop3<~TA & ~TB & ~TC>(p3, p2, p1), p0, h2);      // 0x20
     k.w[CW_TERM] = h00 | space;                                        // byte <= 0x20
     k.bad = lop3<TA & ~TB & ~TC>(h00, tab, k.nl);
+    k.p5 = p5;
     return k;
 }
 

@@ -90,6 +90,8 @@ struct sidgpu_ctx {
     DevBuf csv_status;
     // site store: arrays indexed by storage index (dense, not in file order) and order[file index] = storage index
     DevBuf pos, slot, name_ref, profile, line_off, site_suffix, order;
+    DevBuf fwd, v_fwd;               // forward-strand profile per site (k_tok2<..., STRANDS>) and its file-ordered copy
+    bool want_fwd = false, fwd_valid = false;
     DevBuf qual_l;                   // quality sessions: two doubles per site from the tokenizer (k_tok2<..., QUAL>)
     DevBuf blk, blk_part;            // block table of the running tokenizer call and its per-chunk sums
     DevBuf rows_scratch, rows_part, rows_part_rows;   // fused row writer: per-slice regions, per-chunk byte / row sums
@@ -390,7 +392,7 @@ int reset_table(sidgpu_ctx* ctx) {
 // ---- site store --------------------------------------------------------------------------------
 
 int ensure_sites(sidgpu_ctx* ctx, uint64_t n, bool keep) {
-    if (n > ctx->site_cap || (ctx->want_profile && ctx->profile.cap < n * 8) || (ctx->want_line_off && ctx->line_off.cap < n * 8) ||
+    if (n > ctx->site_cap || (ctx->want_profile && ctx->profile.cap < n * 8) || (ctx->want_line_off && ctx->line_off.cap < n * 8) || (ctx->want_fwd && ctx->fwd.cap < n * 8) ||
         (ctx->want_site_suffix && (ctx->site_suffix.cap < n * SUFFIX_BYTES || ctx->qual_l.cap < n * 16))) {
         const uint64_t cap = std::max<uint64_t>(n, ctx->site_cap);
         if (cap >= 0xFFFFFFFFull) return ctx->fail(SIDGPU_ECAPACITY, "more than 2^32 sites in one store: feed smaller ranges");
@@ -400,6 +402,7 @@ int ensure_sites(sidgpu_ctx* ctx, uint64_t n, bool keep) {
         TRY(ensure(ctx, ctx->name_ref, cap * 4, keep));
         if (ctx->want_profile) TRY(ensure(ctx, ctx->profile, cap * 8, keep));
         if (ctx->want_line_off) TRY(ensure(ctx, ctx->line_off, cap * 8, keep));
+        if (ctx->want_fwd) TRY(ensure(ctx, ctx->fwd, cap * 8, keep));
         if (ctx->want_site_suffix) TRY(ensure(ctx, ctx->site_suffix, cap * SUFFIX_BYTES, keep));
         if (ctx->want_site_suffix) TRY(ensure(ctx, ctx->qual_l, cap * 16, keep));
         ctx->site_cap = cap;
@@ -502,8 +505,15 @@ int run_tokenizer(sidgpu_ctx* ctx, const char* d_text, size_t text_len, size_t r
             q.qual_l = qual ? (double*)ctx->qual_l.p : nullptr;
             q.qual_lut = (const double*)ctx->quality_lut.p;
             ctx->qual_sums_valid = qual;
+            // strand counts as a by-product of the tokenizer: the ordinary sites form only (else: k_strand_counts over the line offsets)
+            const bool strands = ctx->want_fwd && !qual && !deep && !q.bytewise;
+            q.fwd = strands ? (uint64_t*)ctx->fwd.p : nullptr;
+            ctx->fwd_valid = strands;
             int s2 = 0, s1 = 0;
-            if (qual) {
+            if (strands) {
+                if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s2, k_tok2<false, 2, false, false, true>, TOK_THREADS, tok2_dyn_smem(slice, ext, 2, false, true)) != cudaSuccess || s2 < 1) s2 = 1;
+                s1 = 0;
+            } else if (qual) {
                 if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s2, k_tok2<false, 2, false, true>, TOK_THREADS, tok2_dyn_smem(slice, ext, 2, false)) != cudaSuccess || s2 < 1) s2 = 1;
                 if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s1, k_tok2<false, 1, false, true>, TOK_THREADS, tok2_dyn_smem(slice, ext, 1, false)) != cudaSuccess || s1 < 1) s1 = 1;
             } else if (deep) {
@@ -516,10 +526,12 @@ int run_tokenizer(sidgpu_ctx* ctx, const char* d_text, size_t text_len, size_t r
             }
             const int stages = force_stages == 1 || force_stages == 2 ? force_stages : (s1 > s2 ? 1 : 2);
             const unsigned grid = (unsigned)std::min<uint64_t>(n_tiles, (uint64_t)ctx->sm_count * (stages == 1 ? s1 : s2));
-            const uint32_t dyn = tok2_dyn_smem(slice, ext, (uint32_t)stages, false);
+            const uint32_t dyn = tok2_dyn_smem(slice, ext, (uint32_t)stages, false, strands);
             {
                 ProfScope prof(ctx, PROF_TOKENIZE);
-                if (qual) {
+                if (strands) {
+                    k_tok2<false, 2, false, false, true><<<grid, TOK_THREADS, dyn, ctx->stream>>>(q);
+                } else if (qual) {
                     if (stages == 1) k_tok2<false, 1, false, true><<<grid, TOK_THREADS, dyn, ctx->stream>>>(q);
                     else k_tok2<false, 2, false, true><<<grid, TOK_THREADS, dyn, ctx->stream>>>(q);
                 } else if (deep) {
@@ -1164,6 +1176,7 @@ int sidgpu_create(const sidgpu_config* cfg, sidgpu_ctx** out) {
         (e = cudaFuncSetAttribute(k_tok2<false, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::min<uint32_t>(227u << 10, tok2_dyn_smem(SLICE_MAX, 2016, 2, false)))) != cudaSuccess ||
         (e = cudaFuncSetAttribute(k_tok2<false, 1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tok2_dyn_smem(SLICE_MAX, 2016, 1, false))) != cudaSuccess ||
         (e = cudaFuncSetAttribute(k_tok2<false, 2, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::min<uint32_t>(227u << 10, tok2_dyn_smem(SLICE_MAX, 2016, 2, false)))) != cudaSuccess ||
+        (e = cudaFuncSetAttribute(k_tok2<false, 2, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::min<uint32_t>(227u << 10, tok2_dyn_smem(SLICE_MAX, 2016, 2, false, true)))) != cudaSuccess ||
         (e = cudaFuncSetAttribute(k_tok2<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tok2_dyn_smem(SLICE_MAX, 2016, 1, true))) != cudaSuccess ||
         (e = cudaFuncSetAttribute(k_tok2<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::min<uint32_t>(227u << 10, tok2_dyn_smem(SLICE_MAX, 2016, 2, true)))) != cudaSuccess ||
         (e = cudaFuncSetAttribute(k_rows_compact, cudaFuncAttributeMaxDynamicSharedMemorySize, (RC_THREADS / 32) * RC_STAGE)) != cudaSuccess ||
@@ -1199,7 +1212,7 @@ void sidgpu_destroy(sidgpu_ctx* ctx) {
     for (DevBuf* b : {&ctx->blk, &ctx->blk_part, &ctx->order, &ctx->v_pos, &ctx->v_slot, &ctx->v_name_ref, &ctx->v_profile, &ctx->v_line_off, &ctx->csv_status, &ctx->pos, &ctx->slot, &ctx->name_ref, &ctx->profile, &ctx->line_off,
                       &ctx->site_suffix, &ctx->rows_scratch, &ctx->rows_part, &ctx->rows_part_rows, &ctx->sort_keys, &ctx->sort_vals, &ctx->u_profile, &ctx->u_count, &ctx->u_logM,
                       &ctx->entry_to_unique, &ctx->g_e2u, &ctx->p_hom, &ctx->p_het, &ctx->adj_hom, &ctx->adj_het, &ctx->bh_c, &ctx->bh_block,
-                      &ctx->partials, &ctx->quality_lut, &ctx->hp_comp[0], &ctx->hp_comp[1], &ctx->inf_blocks[0], &ctx->inf_blocks[1], &ctx->crc_tables})
+                      &ctx->partials, &ctx->quality_lut, &ctx->hp_comp[0], &ctx->hp_comp[1], &ctx->inf_blocks[0], &ctx->inf_blocks[1], &ctx->crc_tables, &ctx->fwd, &ctx->v_fwd})
         release(*b);
     if (ctx->d_ctl) cudaFree(ctx->d_ctl);
     if (ctx->h_ctl) cudaFreeHost(ctx->h_ctl);
@@ -1293,11 +1306,14 @@ int sidgpu_tokenize(sidgpu_ctx* ctx, const char* d_text, size_t text_len, size_t
     ctx->phase = PHASE_IDLE;
     ctx->want_profile = true;
     ctx->want_line_off = want_qual != 0;
+    ctx->want_fwd = want_qual == 3;
     TRY(reset_table(ctx));
     TRY(reset_names(ctx));
     uint64_t n = 0;
     // want_qual 2: the line offsets without the quality columns (a six-column file stays valid)
-    TRY(run_tokenizer(ctx, d_text, text_len, range_begin, range_end, want_qual == 1, true, 0, false, &n, true));
+    const int rc_tok = run_tokenizer(ctx, d_text, text_len, range_begin, range_end, want_qual == 1, true, 0, false, &n, true);
+    ctx->want_fwd = false;
+    TRY(rc_tok);
     ctx->n_sites_total = n;
     ctx->chunk_begin = 0;
     ctx->chunk_sites = n;
@@ -1310,6 +1326,14 @@ int sidgpu_tokenize(sidgpu_ctx* ctx, const char* d_text, size_t text_len, size_t
     TRY(ensure(ctx, ctx->v_slot, nn * 4));
     TRY(ensure(ctx, ctx->v_name_ref, nn * 4));
     if (want_qual) TRY(ensure(ctx, ctx->v_line_off, nn * 8));
+    if (want_qual == 3) {
+        TRY(ensure(ctx, ctx->v_fwd, nn * 8));
+        if (n && !ctx->fwd_valid) {
+            // long lines (the DEEP tokenizer): the strands by a second walk over the lines, in storage order
+            TRY(ensure(ctx, ctx->fwd, nn * 8));
+            TRY(sidgpu_strand_counts(ctx, d_text, text_len, (const uint64_t*)ctx->line_off.p, n, (uint64_t*)ctx->fwd.p, nullptr));
+        }
+    }
     if (n) {
         const unsigned g = (unsigned)((n + 255) / 256);
         const uint32_t* ord = (const uint32_t*)ctx->order.p;
@@ -1318,6 +1342,7 @@ int sidgpu_tokenize(sidgpu_ctx* ctx, const char* d_text, size_t text_len, size_t
         k_gather<<<g, 256, 0, ctx->stream>>>((uint32_t*)ctx->v_slot.p, (const uint32_t*)ctx->slot.p, ord, n);
         k_gather<<<g, 256, 0, ctx->stream>>>((uint32_t*)ctx->v_name_ref.p, (const uint32_t*)ctx->name_ref.p, ord, n);
         if (want_qual) k_gather<<<g, 256, 0, ctx->stream>>>((uint64_t*)ctx->v_line_off.p, (const uint64_t*)ctx->line_off.p, ord, n);
+        if (want_qual == 3) k_gather<<<g, 256, 0, ctx->stream>>>((uint64_t*)ctx->v_fwd.p, (const uint64_t*)ctx->fwd.p, ord, n);
         TRY(check_launch(ctx, "k_gather"));
         CK(cudaStreamSynchronize(ctx->stream));
     }
@@ -1325,6 +1350,7 @@ int sidgpu_tokenize(sidgpu_ctx* ctx, const char* d_text, size_t text_len, size_t
     out->d_pos = (const int32_t*)ctx->v_pos.p;
     out->d_slot = (const uint32_t*)ctx->v_slot.p;
     out->d_line_off = want_qual ? (const uint64_t*)ctx->v_line_off.p : nullptr;
+    out->d_fwd = want_qual == 3 ? (const uint64_t*)ctx->v_fwd.p : nullptr;
     out->d_name_ref = (const uint32_t*)ctx->v_name_ref.p;
     out->d_names = ctx->names.pool;
     out->names_bytes = ctx->h_ctl->name_cursor;

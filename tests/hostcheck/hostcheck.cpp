@@ -240,11 +240,24 @@ int64_t hc_compare_parsers_units(const uint8_t* text, uint64_t len, uint64_t* n_
         ParsedLine a;
         parse_line(src, p, false, a);
         WinLine b, c, w;
-        const bool fb = parse_line_units_host<true>(text, len, p, b), fc = parse_line_units_host<false>(text, len, p, c);
+        uint64_t fwd = 0;
+        const bool fb = parse_line_units_host<true>(text, len, p, b, &fwd), fc = parse_line_units_host<false>(text, len, p, c);
         const bool fw = parse_line_win_host<true>(text, len, p, w);
         if (fb != fc) return -(k + 1);
         if (fb) {
             ++fast;
+            // the forward-strand profile against the byte-wise walk (pileup.cpp:78-124)
+            BasesState st;
+            st.init((uint8_t)a.ref);
+            uint32_t fc4[4] = {0, 0, 0, 0};
+            for (uint32_t i = 0; i < a.bases_len; ++i) {
+                const uint8_t ch = text[p + a.bases_off + i];
+                const int idx = st.feed(ch);
+                if (idx < 0) continue;
+                const uint8_t seen = ch == '.' ? st.dot_as : ch == ',' ? st.comma_as : ch;
+                if (!(seen & 0x20u)) ++fc4[idx];
+            }
+            if (fwd != pack_profile(fc4[0], fc4[1], fc4[2], fc4[3])) return -(k + 1);
             if (a.status != LINE_OK || b.status != LINE_OK || a.profile != b.profile || a.pos != b.pos || c.profile != a.profile ||
                 a.chrom_off != 0 || a.chrom_len != b.name_len || c.name_len != b.name_len || b.hdr_len != c.hdr_len ||
                 b.pos_canonical != c.pos_canonical) return -(k + 1);

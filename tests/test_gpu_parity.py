@@ -37,10 +37,15 @@ def test_tokenizer_bit_exact(native, gpu_ctx, name):
     assert got["chrom"] == want["chrom"]
 
 
+@pytest.mark.parametrize("with_quals", [False, True], ids=["by_product_of_k1", "own_pass"])
 @pytest.mark.parametrize("name", ["edge.plp", "depth30.plp", "depth500.plp", "depth5.plp", "quality30.plp", "fuzz"])
-def test_strand_counts(native, gpu_ctx, name):
+def test_strand_counts(native, gpu_ctx, name, with_quals):
     """SURVEY.md 8f row 4: ReadStack::strands (pileup.hpp:15, pileup.cpp:87-123) summed per site and letter; six-column
-    files included (the quality columns are not looked at), and the reference-character substitution of pileup.cpp:78-83."""
+    files included (the quality columns are not looked at), and the reference-character substitution of pileup.cpp:78-83.
+    Two routes: counted by the tokenizer in the same pass (k_tok2<..., STRANDS>; twice, so that depth500 also meets the
+    long-line tokenizer, which leaves them to k_strand_counts), or by k_strand_counts over the line offsets."""
+    if with_quals and name not in ("quality30.plp",):
+        pytest.skip("the quality columns are validated on this route: seven-column input only")
     if name == "fuzz":
         import random
         rnd = random.Random(5)
@@ -55,9 +60,11 @@ def test_strand_counts(native, gpu_ctx, name):
     want_fwd, want_rev = op.oracle_strand_counts(text)
     d = gpu_ctx.upload_text(text)
     try:
-        got = gpu_ctx.tokenize(d, len(text), strands=True)
+        got = gpu_ctx.tokenize(d, len(text), strands=True, want_qual=with_quals)
+        again = gpu_ctx.tokenize(d, len(text), strands=True, want_qual=with_quals)
     finally:
         d.free()
+    assert np.array_equal(got["fwd"], again["fwd"]) and np.array_equal(got["rev"], again["rev"])
     assert got["n_sites"] == len(want_fwd)
     assert np.array_equal(got["fwd"], want_fwd) and np.array_equal(got["rev"], want_rev)
     # fwd + rev is the profile, count by count (mod 65536 like profile_t)
