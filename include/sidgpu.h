@@ -74,6 +74,10 @@ typedef struct {
      * (scripts/sid-pipeline/run-sid.sh:16-17 pipes it through grep ',het,').  Sites, fits and
      * sidgpu_emit_records are unaffected; *rows_out counts the rows written. */
     int het_only;
+    /* Keep, per site, the profile of the bases read on the forward strand (ReadStack::strands,
+     * pileup.hpp:15, summed per letter; a by-product of the tokenizer pass): sidgpu_emit_columns can then deliver
+     * d_profile and d_fwd beside the call, which is what a strand-bias filter needs.  Costs 16 bytes per site of the store. */
+    int want_strands;
 } sidgpu_params;
 
 /* ------------------------------------------------------------------------------------------------
@@ -239,6 +243,8 @@ typedef struct {
     char* d_gt;
     double* d_hom_conf;
     double* d_het_conf;
+    uint64_t* d_profile;    /* the site's counts, A | C<<16 | G<<32 | T<<48 */
+    uint64_t* d_fwd;        /* those of the forward strand (sessions begun with want_strands; SIDGPU_EINVAL otherwise) */
 } sidgpu_columns;
 int sidgpu_emit_columns(sidgpu_ctx* ctx, uint64_t site_begin, uint64_t n_sites, const sidgpu_columns* cols);
 /* The chromosome-name pool of the ctx (device memory, valid until the ctx is destroyed or grown). */

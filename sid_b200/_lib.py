@@ -21,12 +21,12 @@ class Params(ctypes.Structure):
     _fields_ = [("method", ctypes.c_int), ("estimate_prior", ctypes.c_int), ("prior", ctypes.c_double),
                 ("error_threshold", ctypes.c_double), ("significance_level", ctypes.c_double),
                 ("fit_given", ctypes.c_int), ("fit_pi", ctypes.c_double), ("fit_eps", ctypes.c_double),
-                ("fit_nd", ctypes.c_double * 4), ("het_only", ctypes.c_int)]
+                ("fit_nd", ctypes.c_double * 4), ("het_only", ctypes.c_int), ("want_strands", ctypes.c_int)]
 
 
 class Columns(ctypes.Structure):
     _fields_ = [("d_pos", ctypes.c_void_p), ("d_name_ref", ctypes.c_void_p), ("d_label", ctypes.c_void_p), ("d_gt", ctypes.c_void_p),
-                ("d_hom_conf", ctypes.c_void_p), ("d_het_conf", ctypes.c_void_p)]
+                ("d_hom_conf", ctypes.c_void_p), ("d_het_conf", ctypes.c_void_p), ("d_profile", ctypes.c_void_p), ("d_fwd", ctypes.c_void_p)]
 
 
 class SitesView(ctypes.Structure):

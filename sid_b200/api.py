@@ -188,7 +188,7 @@ class Context:
     # ---- sessions
     @staticmethod
     def make_params(method, estimate_prior=False, prior=-1.0, error_threshold=0.1, significance_level=0.05, fit=None,
-                    het_only=False):
+                    het_only=False, strands=False):
         p = Params()
         p.method = METHODS[method] if isinstance(method, str) else int(method)
         p.estimate_prior = 1 if estimate_prior else 0
@@ -196,6 +196,7 @@ class Context:
         p.error_threshold = error_threshold
         p.significance_level = significance_level
         p.het_only = 1 if het_only else 0
+        p.want_strands = 1 if strands else 0
         if fit is not None:
             p.fit_given = 1
             p.fit_pi, p.fit_eps = fit[0], fit[1]
@@ -231,16 +232,26 @@ class Context:
         self._ck(self.lib.sidgpu_emit_csv(self.h, site_begin, n_sites, ptr, out_cap, ctypes.byref(b), ctypes.byref(r)))
         return b.value, r.value
 
-    def emit_columns(self, site_begin, n_sites, keep_dropped=False):
+    def emit_columns(self, site_begin, n_sites, keep_dropped=False, strands=False):
         """sidgpu_emit_columns: the rows of the session as columns (numpy arrays) instead of CSV text.
         'chrom' is dictionary encoded: chrom_codes index into chrom_names.  Sites the method drops
-        (coverage < 4 for bayes / likelihood_ratio, label 255) are filtered unless keep_dropped."""
+        (coverage < 4 for bayes / likelihood_ratio, label 255) are filtered unless keep_dropped.
+        strands (sessions begun with make_params(..., strands=True)): also 'profile' and 'fwd', the site's counts and those
+        of the forward strand as (n, 4) arrays A, C, G, T."""
         n = int(n_sites)
         bufs = {"pos": DeviceBuffer(self, max(4 * n, 4)), "name_ref": DeviceBuffer(self, max(4 * n, 4)), "label": DeviceBuffer(self, max(n, 1)),
                 "gt": DeviceBuffer(self, max(2 * n, 2)), "hom": DeviceBuffer(self, max(8 * n, 8)), "het": DeviceBuffer(self, max(8 * n, 8))}
+        if strands:
+            bufs["profile"] = DeviceBuffer(self, max(8 * n, 8))
+            bufs["fwd"] = DeviceBuffer(self, max(8 * n, 8))
         try:
-            cols = Columns(bufs["pos"].ptr, bufs["name_ref"].ptr, bufs["label"].ptr, bufs["gt"].ptr, bufs["hom"].ptr, bufs["het"].ptr)
+            cols = Columns(bufs["pos"].ptr, bufs["name_ref"].ptr, bufs["label"].ptr, bufs["gt"].ptr, bufs["hom"].ptr, bufs["het"].ptr,
+                           bufs["profile"].ptr if strands else None, bufs["fwd"].ptr if strands else None)
             self._ck(self.lib.sidgpu_emit_columns(self.h, site_begin, n, ctypes.byref(cols)))
+            if strands:
+                unpack = lambda a: np.stack([(a >> np.uint64(16 * i)) & np.uint64(0xFFFF) for i in range(4)], axis=1).astype(np.uint16)
+                profile4 = unpack(bufs["profile"].download(np.uint64, n))
+                fwd4 = unpack(bufs["fwd"].download(np.uint64, n))
             pos = bufs["pos"].download(np.int32, n)
             refs = bufs["name_ref"].download(np.uint32, n)
             label = bufs["label"].download(np.uint8, n)
@@ -260,9 +271,11 @@ class Context:
             ln = pool[r] | (pool[r + 1] << 8)
             names.append(pool[r + 2:r + 2 + ln].decode("latin-1"))
         out = {"chrom_codes": codes.astype(np.int32), "chrom_names": names, "pos": pos, "label": label, "gt": gt, "hom_conf": hom, "het_conf": het}
+        if strands:
+            out["profile"], out["fwd"] = profile4, fwd4
         if not keep_dropped:
             keep = label != 255
-            for k in ("chrom_codes", "pos", "label", "gt", "hom_conf", "het_conf"):
+            for k in ("chrom_codes", "pos", "label", "gt", "hom_conf", "het_conf") + (("profile", "fwd") if strands else ()):
                 out[k] = out[k][keep]
         return out
 
@@ -543,17 +556,19 @@ def sid_csv(text, method="local", estimate_prior=False, prior=-1.0, error_thresh
     return rows if het_only else CSV_HEADER + rows
 
 
-def call_columns(text, method="local", estimate_prior=False, prior=-1.0, error_threshold=0.1, significance_level=0.05, ctx=None, fit=None):
+def call_columns(text, method="local", estimate_prior=False, prior=-1.0, error_threshold=0.1, significance_level=0.05, ctx=None, fit=None,
+                 strands=False):
     """The rows `sid -m METHOD` prints, as columns: a dict of numpy arrays (see Context.emit_columns).
-    All four methods (`quality` without -R: the text is fed once); the text is fed from device memory in one piece."""
+    All four methods (`quality` without -R: the text is fed once); the text is fed from device memory in one piece.
+    strands: also the counts of every site and those of its forward strand ('profile', 'fwd')."""
     ctx = ctx or default_context()
     d = ctx.upload_text(text)
     try:
-        ctx.begin(Context.make_params(method, estimate_prior, prior, error_threshold, significance_level, fit=fit))
+        ctx.begin(Context.make_params(method, estimate_prior, prior, error_threshold, significance_level, fit=fit, strands=strands))
         n = ctx.feed(d, d.text_len)
         if not ctx_streams(method, estimate_prior):
             ctx.finish()
-        return ctx.emit_columns(0, n)
+        return ctx.emit_columns(0, n, strands=strands)
     finally:
         d.free()
 
@@ -569,5 +584,11 @@ def columns_to_arrow(cols):
     gt = [bytes(g).decode("latin-1") for g in cols["gt"]]
     chrom = pa.DictionaryArray.from_arrays(pa.array(cols["chrom_codes"], type=pa.int32()), pa.array(cols["chrom_names"], type=pa.string()))
     label = pa.DictionaryArray.from_arrays(pa.array(cols["label"].astype(np.int8)), pa.array(["hom", "het"]))
-    return pa.table({"chrom": chrom, "pos": pa.array(cols["pos"]), "label": label, "gt": pa.array(gt), "hom_conf": pa.array(cols["hom_conf"]),
-                     "het_conf": pa.array(cols["het_conf"])})
+    table = {"chrom": chrom, "pos": pa.array(cols["pos"]), "label": label, "gt": pa.array(gt), "hom_conf": pa.array(cols["hom_conf"]),
+             "het_conf": pa.array(cols["het_conf"])}
+    if "fwd" in cols:            # strand-aware: counts per letter on the forward and on the reverse strand
+        rev = (cols["profile"].astype(np.int32) - cols["fwd"].astype(np.int32)) & 0xFFFF
+        for i, b in enumerate("ACGT"):
+            table["fwd_" + b] = pa.array(cols["fwd"][:, i].astype(np.uint16))
+            table["rev_" + b] = pa.array(rev[:, i].astype(np.uint16))
+    return pa.table(table)

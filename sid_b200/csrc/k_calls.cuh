@@ -279,6 +279,9 @@ struct RecordParams {
     const uint32_t* name_ref_in;
     int32_t* pos;
     uint32_t* name_ref;
+    const unsigned long long* fwd_in;       // forward-strand profile per site of the store (sessions with want_strands)
+    unsigned long long* profile;
+    unsigned long long* fwd;
 };
 
 __global__ void k_records(const RecordParams p) {
@@ -292,6 +295,8 @@ __global__ void k_records(const RecordParams p) {
     if (p.gt) { p.gt[2 * i] = p.table.gt[2 * s]; p.gt[2 * i + 1] = p.table.gt[2 * s + 1]; }
     if (p.hom) p.hom[i] = p.table.hom[s];
     if (p.het) p.het[i] = p.table.het[s];
+    if (p.profile) p.profile[i] = p.table.keys[s];
+    if (p.fwd) p.fwd[i] = p.fwd_in[site];
 }
 
 #endif  // __CUDACC__

@@ -1366,7 +1366,8 @@ int sidgpu_begin(sidgpu_ctx* ctx, const sidgpu_params* params) {
     ctx->streaming = method_streams(*params);
     ctx->counting = !ctx->streaming;
     ctx->want_profile = params->method == SIDGPU_METHOD_QUALITY;      // k_quality takes the counts from the tokenizer
-    ctx->want_line_off = params->method == SIDGPU_METHOD_QUALITY;
+    ctx->want_fwd = params->want_strands != 0;
+    ctx->want_line_off = params->method == SIDGPU_METHOD_QUALITY || ctx->want_fwd;      // (strands of long lines: k_strand_counts over the offsets)
     ctx->want_site_suffix = params->method == SIDGPU_METHOD_QUALITY;
     ctx->session_prior = params->prior;
     ctx->fit_done = false;
@@ -1399,6 +1400,10 @@ int sidgpu_feed(sidgpu_ctx* ctx, const char* d_text, size_t text_len, size_t ran
     ctx->chunk_begin = base;
     ctx->chunk_sites = n;
     ctx->n_sites_total = chunk_local ? n : base + n;
+    if (ctx->want_fwd && !ctx->fwd_valid && n) {
+        // the tokenizer form of this chunk does not count strands (long lines, quality sessions): a walk over the chunk's lines
+        TRY(sidgpu_strand_counts(ctx, d_text, text_len, (const uint64_t*)ctx->line_off.p + base, n, (uint64_t*)ctx->fwd.p + base, nullptr));
+    }
     if (ctx->counting && ctx->phase == PHASE_FEED && n) {
         k_count_slots<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>((const uint32_t*)ctx->slot.p, base, n, ctx->tab.counts);
         TRY(check_launch(ctx, "k_count_slots"));
@@ -1620,14 +1625,23 @@ int sidgpu_emit_columns(sidgpu_ctx* ctx, uint64_t site_begin, uint64_t n_sites, 
     if (!ctx->streaming && ctx->phase != PHASE_FINISHED) return ctx->fail(SIDGPU_ESTATE, "this method needs sidgpu_finish first");
     if (site_begin + n_sites > ctx->n_sites_total) return ctx->fail(SIDGPU_EINVAL, "site range not in the store");
     if (n_sites == 0) return SIDGPU_OK;
+    if (cols->d_fwd && !ctx->params.want_strands) return ctx->fail(SIDGPU_EINVAL, "d_fwd needs a session begun with want_strands");
     CK(cudaSetDevice(ctx->device));
     const bool is_quality = ctx->params.method == SIDGPU_METHOD_QUALITY;
+    if (is_quality && cols->d_profile) {
+        // quality sessions keep the counts per site, not in the table
+        k_gather<<<(unsigned)((n_sites + 255) / 256), 256, 0, ctx->stream>>>((uint64_t*)cols->d_profile, (const uint64_t*)ctx->profile.p,
+                                                                            (const uint32_t*)ctx->order.p + site_begin, n_sites);
+        TRY(check_launch(ctx, "k_gather"));
+    }
     // quality: the call is per site, not per profile: k_quality writes label / genotype / confidences itself
     if (is_quality) TRY(sidgpu_emit_records(ctx, site_begin, n_sites, cols->d_label, cols->d_gt, cols->d_hom_conf, cols->d_het_conf));
     RecordParams p {site_begin, n_sites, (const uint32_t*)ctx->order.p, (const uint32_t*)ctx->slot.p, ctx->tab,
                     is_quality ? nullptr : cols->d_label, is_quality ? nullptr : cols->d_gt, is_quality ? nullptr : cols->d_hom_conf,
                     is_quality ? nullptr : cols->d_het_conf,
-                    (const int32_t*)ctx->pos.p, (const uint32_t*)ctx->name_ref.p, cols->d_pos, cols->d_name_ref};
+                    (const int32_t*)ctx->pos.p, (const uint32_t*)ctx->name_ref.p, cols->d_pos, cols->d_name_ref,
+                    (const unsigned long long*)ctx->fwd.p, is_quality ? nullptr : (unsigned long long*)cols->d_profile,
+                    (unsigned long long*)cols->d_fwd};
     k_records<<<(unsigned)((n_sites + 255) / 256), 256, 0, ctx->stream>>>(p);
     TRY(check_launch(ctx, "k_records"));
     CK(cudaStreamSynchronize(ctx->stream));

@@ -469,6 +469,37 @@ def test_columns_match_reference_csv(native, gpu_ctx, case):
         assert t.column("chrom")[0].as_py() == want[0][0] and t.column("label")[0].as_py() == want[0][2]
 
 
+@pytest.mark.parametrize("name,method", [("depth30_two_chroms.plp", "local"), ("edge.plp", "local"), ("depth30.plp", "bayes"),
+                                         ("depth500.plp", "likelihood_ratio"), ("quality30.plp", "quality"), ("depth5.plp", "bayes")])
+def test_columns_with_strand_counts(native, gpu_ctx, name, method):
+    """Strand-aware columnar output: a session begun with want_strands delivers, beside the call of every
+    row, the site's counts and those of its forward strand; rows the method drops (coverage < 4) drop here too."""
+    import sid_b200
+    text = read(name)
+    cols = sid_b200.call_columns(text, method, ctx=gpu_ctx, strands=True)
+    plain = sid_b200.call_columns(text, method, ctx=gpu_ctx)
+    for k in ("pos", "label", "gt", "hom_conf", "het_conf", "chrom_codes"):
+        assert np.array_equal(cols[k], plain[k]), k
+    want = op.oracle_call(text, "local")
+    want_fwd, want_rev = op.oracle_strand_counts(text)
+    prof = op.unpack_profiles(want["profiles"])
+    keep = np.ones(len(prof), dtype=bool) if method in ("local", "quality") else prof.astype(np.int64).sum(axis=1) >= 4
+    assert np.array_equal(cols["profile"], prof[keep])
+    assert np.array_equal(cols["fwd"], op.unpack_profiles(want_fwd)[keep])
+    t = sid_b200.columns_to_arrow(cols)
+    assert t.num_rows == int(keep.sum()) and "rev_T" in t.column_names
+    assert np.array_equal(np.asarray(t["rev_G"]), op.unpack_profiles(want_rev)[keep][:, 2])
+    # without want_strands the forward column is refused, not invented
+    gpu_ctx.begin(sid_b200.Context.make_params("local"))
+    d = gpu_ctx.upload_text(text)
+    try:
+        n = gpu_ctx.feed(d, len(text))
+        with pytest.raises(sid_b200.SidGpuError):
+            gpu_ctx.emit_columns(0, n, strands=True)
+    finally:
+        d.free()
+
+
 def test_emit_sub_ranges_concatenate(native, gpu_ctx):
     """sidgpu_emit_csv over odd-sized pieces of the store == one call over all of it (file order through order[])."""
     import sid_b200
