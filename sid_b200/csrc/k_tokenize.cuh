@@ -142,13 +142,13 @@ struct LineResult {
 __device__ __forceinline__ bool same_name_as_first(const uint8_t* s_text, uint32_t my_off, uint32_t len, uint32_t l0_off,
                                                    uint2 first8, uint32_t avail = TILE_SMEM_MAX) {
     if (len <= 7) {
+        // the name AND the delimiter after it, as one masked compare of len + 1 bytes: equal names followed by different
+        // delimiters (a space here, a tab there) only send this line through the dictionary, which finds the same name
         const uint2 mine = load8_unaligned(s_text, my_off);
-        const uint32_t bits = 8 * len;
-        uint32_t dlo, dhi, delim;
-        if (len < 4) { dlo = (mine.x ^ first8.x) & ((1u << bits) - 1u); dhi = 0; delim = (first8.x >> bits) & 0xFFu; }
-        else if (len == 4) { dlo = mine.x ^ first8.x; dhi = 0; delim = first8.y & 0xFFu; }
-        else { dlo = mine.x ^ first8.x; dhi = (mine.y ^ first8.y) & ((1u << (bits - 32)) - 1u); delim = (first8.y >> (bits - 32)) & 0xFFu; }
-        return (dlo | dhi) == 0 && (delim == '\t' || delim == ' ');
+        const uint32_t bits = 8 * (len + 1);                       // 8 .. 64
+        const uint32_t mlo = bits >= 32 ? 0xFFFFFFFFu : ((1u << bits) - 1u);
+        const uint32_t mhi = bits <= 32 ? 0u : (bits >= 64 ? 0xFFFFFFFFu : ((1u << (bits - 32)) - 1u));
+        return (((mine.x ^ first8.x) & mlo) | ((mine.y ^ first8.y) & mhi)) == 0;
     }
     if (my_off + len + 1 > avail || l0_off + len + 1 > avail) return false;
     for (uint32_t i = 0; i < len; ++i) if (s_text[my_off + i] != s_text[l0_off + i]) return false;
