@@ -489,6 +489,21 @@ def test_columns_with_strand_counts(native, gpu_ctx, name, method):
     t = sid_b200.columns_to_arrow(cols)
     assert t.num_rows == int(keep.sum()) and "rev_T" in t.column_names
     assert np.array_equal(np.asarray(t["rev_G"]), op.unpack_profiles(want_rev)[keep][:, 2])
+    # the same session fed in three pieces (the store grows, the strands of later chunks land behind the earlier ones)
+    if method in ("bayes", "likelihood_ratio"):
+        cuts = [0, text.index(b"\n", len(text) // 3) + 1, text.index(b"\n", 2 * len(text) // 3) + 1, len(text)]
+        gpu_ctx.begin(sid_b200.Context.make_params(method, strands=True))
+        n = 0
+        for a, b in zip(cuts[:-1], cuts[1:]):
+            piece = gpu_ctx.upload_text(text[a:b])
+            try:
+                n += gpu_ctx.feed(piece, b - a)
+            finally:
+                piece.free()
+        gpu_ctx.finish()
+        again = gpu_ctx.emit_columns(0, n, strands=True)
+        for k in ("pos", "label", "gt", "profile", "fwd"):
+            assert np.array_equal(again[k], cols[k]), k
     # without want_strands the forward column is refused, not invented
     gpu_ctx.begin(sid_b200.Context.make_params("local"))
     d = gpu_ctx.upload_text(text)
