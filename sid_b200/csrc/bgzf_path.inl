@@ -141,6 +141,13 @@ int finish_inflate(sidgpu_ctx* ctx, int b, size_t* line_end) {
     return SIDGPU_OK;
 }
 
+// Whoever queues inflate chains waits for the last one on every way out (an error may leave the chain of the next chunk in
+// flight; the buffers it writes belong to the ctx and are reused by the next call).
+struct InflateDrain {
+    sidgpu_ctx* ctx;
+    ~InflateDrain() { if (ctx->inflate_stream) cudaStreamSynchronize(ctx->inflate_stream); }
+};
+
 // A streamed BGZF input, chunk by chunk through the two text buffers of the ctx.  Chunk i lies compressed in hp_comp[i & 1]
 // (table in inf_blocks[i & 1]); its text goes behind the unfinished line the chunk before left at the front of
 // hp_text[i & 1].  launch(i) queues its inflate chain on the inflate stream -- for chunk i + 1 right after finish(i), so that
@@ -190,6 +197,7 @@ extern "C" int sidgpu_call_host_bgzf(sidgpu_ctx* ctx, const sidgpu_params* param
     if (!ctx || !params || (comp_len && !h_comp)) return SIDGPU_EINVAL;
     Range nvtx_range("sidgpu_call_host_bgzf");
     CK(cudaSetDevice(ctx->device));
+    InflateDrain drain_inflate {ctx};
     HostIo io(ctx);
     TRY(io.init());
     io.h_csv = h_csv;

@@ -370,6 +370,7 @@ static int call_io(sidgpu_ctx* ctx, const sidgpu_params* params, const sidgpu_io
     if (!ctx || !params || !io || !io->read || !io->write) return SIDGPU_EINVAL;
     Range nvtx_range(bgzf ? "sidgpu_call_io_bgzf" : "sidgpu_call_io");
     CK(cudaSetDevice(ctx->device));
+    InflateDrain drain_inflate {ctx};           // (bgzf) no inflate chain outlives the call, whatever way it ends
     IoPipe pipe;
     pipe.ctx = ctx;
     pipe.io = io;
