@@ -159,28 +159,28 @@ SID_HD bool build_huffman(int alphabet, const uint8_t* lengths, uint32_t n, uint
     return true;
 }
 
+// The entry (with its code length in bits 0-3) of a code longer than the fast table's index: the count/offset walk of the
+// canonical order over the bits of w.  K_INVALID | 15 for a code that is not in the alphabet.
+SID_HD uint32_t slow_entry(uint32_t w, int alphabet, const uint16_t* cnt, const uint16_t* sym) {
+    int code = 0, first = 0, index = 0;
+    for (int l = 1; l < 16; ++l) {
+        code |= (int)((w >> (l - 1)) & 1u);
+        const int count = cnt[l];
+        if (code - count < first) return symbol_entry(alphabet, sym[index + (code - first)]) | (uint32_t)l;
+        index += count;
+        first += count;
+        first <<= 1;
+        code <<= 1;
+    }
+    return make_entry(K_INVALID, 0, 0) | 15u;
+}
+
 // Next symbol with its extra bits: its entry with the value completed (base + extra bits) in bits 16-31; code and extra
 // bits are consumed.  K_INVALID for a code that is not in the alphabet.
 SID_HD uint32_t decode_entry(BitReader& br, int alphabet, const uint32_t* fast, uint32_t bits, const uint16_t* cnt, const uint16_t* sym) {
     const uint32_t w = br.window();
     uint32_t e = fast[w & ((1u << bits) - 1u)];
-    if ((e & 15u) == 0) {
-        // a code longer than the table's index: the count/offset walk of the canonical order
-        int code = 0, first = 0, index = 0;
-        e = make_entry(K_INVALID, 0, 0) | 15u;
-        for (int l = 1; l < 16; ++l) {
-            code |= (int)((w >> (l - 1)) & 1u);
-            const int count = cnt[l];
-            if (code - count < first) {
-                e = symbol_entry(alphabet, sym[index + (code - first)]) | (uint32_t)l;
-                break;
-            }
-            index += count;
-            first += count;
-            first <<= 1;
-            code <<= 1;
-        }
-    }
+    if ((e & 15u) == 0) e = slow_entry(w, alphabet, cnt, sym);
     const uint32_t cl = e & 15u, xb = (e >> 4) & 15u;
     const uint32_t extra = (w >> cl) & ((1u << xb) - 1u);          // cl + xb <= 28: all of it is in this window
     br.drop(cl + xb);

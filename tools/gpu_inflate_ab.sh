@@ -1,5 +1,5 @@
 #!/bin/bash
-# device inflate: parity tests and kernel throughput
+# device inflate: parity tests and kernel throughput (+ an ncu capture when a name is given)
 mkdir -p gpurun_out/r2b
 timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "bgzf" 2>&1 | tail -2
 timeout 300 python tools/inflate_bench.py ${1:-20000000} --kernel-only 2>&1 | tail -1 | python -c "
