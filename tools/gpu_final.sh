@@ -1,6 +1,7 @@
 # end-of-round evidence on one GPU: suite, the default bench line, the reference arm, the launch list under ncu
 mkdir -p gpurun_out/r2
 timeout 1200 python -m pytest tests -m gpu -x -q > gpurun_out/r2/pytest_final.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r2/pytest_final.log
+python __graft_entry__.py --smoke 2>&1 | tail -1
 tail -4 gpurun_out/r2/pytest_final.log
 timeout 900 python bench.py > gpurun_out/r2/bench_final.json 2> gpurun_out/r2/bench_final.err
 echo "bench rc=$?"; tail -c 2500 gpurun_out/r2/bench_final.json
