@@ -58,7 +58,7 @@ typedef struct {
 } sidgpu_config;
 
 /* Parameters of one calling session: GlobalOptions of sid.cpp:11-17.
- * (Environment: SIDGPU_SLICE_LINES=<lines per tokenizer slice, default 29.5> is a tuning knob read once
+ * (Environment: SIDGPU_SLICE_LINES=<lines per tokenizer slice, default 31> is a tuning knob read once
  * per process; results do not depend on it.) */
 typedef struct {
     int method;                 /* SIDGPU_METHOD_* */

@@ -431,7 +431,7 @@ int run_tokenizer(sidgpu_ctx* ctx, const char* d_text, size_t text_len, size_t r
     const uint64_t tile0 = range_begin & ~(uint64_t)15;
     const uint64_t span = range_end - tile0;
     // a slice (one parse warp's share of a tile) should hold about 30 lines: 32 lanes, little overflow
-    static const double slice_lines = getenv("SIDGPU_SLICE_LINES") ? atof(getenv("SIDGPU_SLICE_LINES")) : 29.5;   // tuning knob
+    static const double slice_lines = getenv("SIDGPU_SLICE_LINES") ? atof(getenv("SIDGPU_SLICE_LINES")) : 31.0;   // tuning knob
     uint32_t slice = (uint32_t)(ctx->avg_line_bytes * slice_lines) & ~31u;
     slice = std::max<uint32_t>(SLICE_MIN, std::min<uint32_t>(SLICE_MAX, slice));
     // a parse warp also classifies the bytes after its slice that its last lines reach into
@@ -611,7 +611,7 @@ int run_tok2_rows(sidgpu_ctx* ctx, const char* d_text, size_t text_len, size_t r
     if (range_begin == range_end) return sync_ctl(ctx);
     const uint64_t tile0 = range_begin & ~(uint64_t)15;
     const uint64_t span = range_end - tile0;
-    static const double slice_lines = getenv("SIDGPU_SLICE_LINES") ? atof(getenv("SIDGPU_SLICE_LINES")) : 29.5;
+    static const double slice_lines = getenv("SIDGPU_SLICE_LINES") ? atof(getenv("SIDGPU_SLICE_LINES")) : 31.0;
     static const int force_stages = getenv("SIDGPU_TOK_STAGES") ? atoi(getenv("SIDGPU_TOK_STAGES")) : 0;
     uint32_t slice = (uint32_t)(ctx->avg_line_bytes * slice_lines) & ~31u;
     slice = std::max<uint32_t>(SLICE_MIN, std::min<uint32_t>(SLICE_MAX, slice));
