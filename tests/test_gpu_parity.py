@@ -478,8 +478,10 @@ def test_columns_with_strand_counts(native, gpu_ctx, name, method):
     text = read(name)
     cols = sid_b200.call_columns(text, method, ctx=gpu_ctx, strands=True)
     plain = sid_b200.call_columns(text, method, ctx=gpu_ctx)
-    for k in ("pos", "label", "gt", "hom_conf", "het_conf", "chrom_codes"):
+    for k in ("pos", "label", "gt", "hom_conf", "het_conf"):
         assert np.array_equal(cols[k], plain[k]), k
+    # (the codes number the names in the order the dictionary met them, which differs from run to run: compare the names)
+    assert [cols["chrom_names"][c] for c in cols["chrom_codes"]] == [plain["chrom_names"][c] for c in plain["chrom_codes"]]
     want = op.oracle_call(text, "local")
     want_fwd, want_rev = op.oracle_strand_counts(text)
     prof = op.unpack_profiles(want["profiles"])
