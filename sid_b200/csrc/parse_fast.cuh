@@ -29,7 +29,7 @@ SID_HD uint32_t pop_count(uint32_t x) {
 }
 SID_HD uint32_t first_bit(uint32_t x) {        // index of the lowest set bit; 32 when x == 0
 #if defined(__CUDA_ARCH__)
-    return x ? (uint32_t)(__ffs((int)x) - 1) : 32u;
+    return (uint32_t)__clz((int)__brev(x));                 // 32 for x == 0
 #else
     return x ? (uint32_t)__builtin_ctz(x) : 32u;
 #endif

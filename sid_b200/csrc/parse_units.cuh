@@ -23,7 +23,13 @@ SID_HD UnitRec load_unit(const uint32_t* cw, uint32_t u) {
     return r;
 }
 
-SID_HD uint32_t low_bits32(uint32_t n) { return n >= 32 ? 0xFFFFFFFFu : ((1u << n) - 1u); }     // bits [0, n)
+SID_HD uint32_t low_bits32(uint32_t n) {                   // bits [0, n), n = 0 .. 32 (and beyond: all)
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_lc(0xFFFFFFFFu, 0u, n);            // the upper word of (0 : ~0) << min(n, 32): one instruction
+#else
+    return n >= 32 ? 0xFFFFFFFFu : ((1u << n) - 1u);
+#endif
+}
 
 // parsePileupLine + parseReadBases (pileup.cpp:13-153) of the line at line_off; arguments as parse_line_win.
 // STRANDS: p5w holds the raw bit plane 5 of every unit (lower case); *fwd receives the profile of the bases read on the forward
