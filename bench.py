@@ -368,36 +368,44 @@ def _bgzf_member(data):
 def bgzf_e2e_leg(args, env, ctx, h_text, text_len, n_sites, h_csv_t, csv_cap, world):
     """sidgpu_call_host_bgzf on pinned host buffers: the rank's text as a BGZF file (zlib level 6, members of 65,280 bytes).
     Python's zlib writes a sample of the text once; the file is that sample's members repeated until it holds the step's
-    number of sites (the calling path does not care that positions repeat)."""
+    number of sites (the calling path does not care that positions repeat).  The ranks agree that every one of them is set
+    up before any of them enters the timed region (a rank that could not pin its file must not leave the others in a
+    collective)."""
     import ctypes
     from concurrent.futures import ProcessPoolExecutor
     import numpy as np
     import torch
     import sid_b200
-    sample_sites = min(n_sites, args.bgzf_sample_sites)
-    cut = int(text_len * (sample_sites / n_sites))
-    raw = h_text[:cut].tobytes()
-    raw = raw[:raw.rfind(b"\n") + 1]
-    sample_sites = raw.count(b"\n")
-    workers = max(1, (os.cpu_count() or 1) // max(1, world))
-    with ProcessPoolExecutor(max_workers=workers) as ex:
-        members = b"".join(ex.map(_bgzf_member, [raw[i:i + 65280] for i in range(0, len(raw), 65280)], chunksize=64))
-    reps = max(1, n_sites // sample_sites)
-    sites = reps * sample_sites
-    comp_len = reps * len(members)
-    h_comp = torch.empty(comp_len + 64, dtype=torch.uint8, pin_memory=True)
-    view = h_comp.numpy()
-    one = np.frombuffer(members, dtype=np.uint8)
-    for r in range(reps):
-        view[r * len(members):(r + 1) * len(members)] = one
-    p = sid_b200.Context.make_params("local")
+    failure, h_comp, one_step = None, None, None
     nb, ns, nr = ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_uint64()
+    try:
+        sample_sites = min(n_sites, args.bgzf_sample_sites)
+        cut = int(text_len * (sample_sites / n_sites))
+        raw = h_text[:cut].tobytes()
+        raw = raw[:raw.rfind(b"\n") + 1]
+        sample_sites = raw.count(b"\n")
+        workers = max(1, (os.cpu_count() or 1) // max(1, world))
+        with ProcessPoolExecutor(max_workers=workers) as ex:
+            members = b"".join(ex.map(_bgzf_member, [raw[i:i + 65280] for i in range(0, len(raw), 65280)], chunksize=64))
+        reps = max(1, n_sites // sample_sites)
+        sites = reps * sample_sites
+        comp_len = reps * len(members)
+        h_comp = torch.empty(comp_len + 64, dtype=torch.uint8, pin_memory=True)
+        view = h_comp.numpy()
+        one = np.frombuffer(members, dtype=np.uint8)
+        for r in range(reps):
+            view[r * len(members):(r + 1) * len(members)] = one
+        p = sid_b200.Context.make_params("local")
 
-    def one_step():
-        ctx._ck(ctx.lib.sidgpu_call_host_bgzf(ctx.h, ctypes.byref(p), h_comp.data_ptr(), comp_len, h_csv_t.data_ptr(), csv_cap,
-                                              ctypes.byref(nb), ctypes.byref(ns), ctypes.byref(nr)))
-    one_step()
-    assert ns.value == sites, (ns.value, sites)
+        def one_step():
+            ctx._ck(ctx.lib.sidgpu_call_host_bgzf(ctx.h, ctypes.byref(p), h_comp.data_ptr(), comp_len, h_csv_t.data_ptr(), csv_cap,
+                                                  ctypes.byref(nb), ctypes.byref(ns), ctypes.byref(nr)))
+        one_step()
+        assert ns.value == sites, (ns.value, sites)
+    except Exception as e:
+        failure = "%s: %s" % (type(e).__name__, e)
+    if env.max_over_ranks(1.0 if failure else 0.0) > 0:
+        return {"error": failure or "another rank could not set the leg up"}
     env.barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
@@ -670,10 +678,7 @@ def run_ours(args):
     #      inflated on the device; only the compressed bytes cross the host link (which all ranks of a box share)
     e2e_bgzf = None
     if not args.no_e2e and not args.no_bgzf and args.method == "local" and not args.het_only:
-        try:
-            e2e_bgzf = bgzf_e2e_leg(args, env, ctx, h_text, text_len, n_sites, h_csv_t, csv_cap, world)
-        except Exception as e:                  # a side measurement never takes the headline line down
-            e2e_bgzf = {"error": "%s: %s" % (type(e).__name__, e)}
+        e2e_bgzf = bgzf_e2e_leg(args, env, ctx, h_text, text_len, n_sites, h_csv_t, csv_cap, world)      # (never raises before its ranks agree)
         env.barrier()
 
     # ---- the reference's CPU path on this box's host cores (rank 0, N=1 only)
