@@ -193,3 +193,35 @@ def test_bgzf_scan_lists_the_members():
     import gzip
     plain = np.frombuffer(gzip.compress(text), dtype=np.uint8)
     assert lib.sidgpu_bgzf_scan(plain.ctypes.data, len(plain), blocks, 4096, 1 << 40, ctypes.byref(n), ctypes.byref(consumed), ctypes.byref(tbytes)) != 0
+
+
+def test_extra_subfields_before_the_size_field(bgzf_cat, tmp_path):
+    """FEXTRA may carry other subfields beside 'B','C' (RFC 1952 2.3.1.1): both header walks skip them."""
+    import ctypes
+    import numpy as np
+    from sid_b200 import _lib
+    text = read("depth30.plp")[:50000]
+
+    def member(data):
+        c = zlib.compressobj(6, zlib.DEFLATED, -15)
+        body = c.compress(data) + c.flush()
+        extra_other = b"XY" + struct.pack("<H", 5) + b"hello"                   # a foreign subfield first
+        xlen = len(extra_other) + 6
+        bsize = 12 + xlen + len(body) + 8 - 1
+        head = b"\x1f\x8b\x08\x04" + b"\0\0\0\0" + b"\x00\xff" + struct.pack("<H", xlen) + extra_other + b"BC" + struct.pack("<HH", 2, bsize)
+        return head + body + struct.pack("<II", zlib.crc32(data) & 0xFFFFFFFF, len(data))
+
+    comp = member(text[:30000]) + member(text[30000:]) + EOF_BLOCK
+    import gzip
+    assert gzip.decompress(comp) == text
+    p = tmp_path / "x.gz"
+    p.write_bytes(comp)
+    assert cat(bgzf_cat, p) == (0, text, "")
+    lib = _lib.load()
+    blocks = (_lib.BgzfBlock * 8)()
+    n, consumed, tbytes = ctypes.c_size_t(), ctypes.c_size_t(), ctypes.c_size_t()
+    buf = np.frombuffer(comp, dtype=np.uint8)
+    assert lib.sidgpu_bgzf_scan(buf.ctypes.data, len(comp), blocks, 8, 1 << 40, ctypes.byref(n), ctypes.byref(consumed), ctypes.byref(tbytes)) == 0
+    assert (n.value, consumed.value, tbytes.value) == (2, len(comp), len(text))
+    assert zlib.decompress(comp[blocks[1].c_off:blocks[1].c_off + blocks[1].c_len], -15) == text[30000:]
+    assert blocks[1].crc == zlib.crc32(text[30000:])
