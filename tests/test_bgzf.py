@@ -98,8 +98,10 @@ def _hc_inflate(raw, n_out):
             buf = np.zeros(lead + len(raw) + 16 + 4, dtype=np.uint8)
             base = (4 - buf.ctypes.data % 4) % 4
             buf[base + lead:base + lead + len(raw)] = np.frombuffer(raw, dtype=np.uint8)
-            out = np.zeros(max(1, n_out), dtype=np.uint8)
+            out = np.zeros(n_out + 8, dtype=np.uint8)
+            out[n_out:] = 0xAB                        # whatever the stream says, nothing is written past the announced size
             rc = fn(buf.ctypes.data + base + lead, len(raw), out.ctypes.data, n_out)
+            assert out[n_out:].tobytes() == b"\xab" * 8
             res.append((rc, out[:n_out].tobytes()))
     # the same text at every alignment; a damaged stream is an error at every alignment (how far the walk got may differ)
     assert all((r[0] == 0) == (res[0][0] == 0) for r in res)
